@@ -1,0 +1,707 @@
+/*
+ * relagn_oracle.c -- CPU (FP64, scalar C) restatement of RELAGN's
+ * spectrum-evaluation path.  TEST INFRASTRUCTURE ONLY (see relagn_oracle.h).
+ *
+ * Follows the PYTHON version of the reference (not the Fortran one):
+ *   /root/reference/src/python_version/relagn.py
+ *   /root/reference/src/python_version/pyNTHCOMP.py
+ * Every function names the lines it restates.
+ */
+#include "relagn_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include "par_for.h"
+
+/* ---- constants: astropy 5.x CODATA-2018 (relagn.py:33-39) */
+static const double K_G = 6.6743e-11;
+static const double K_MSUN = 1.988409870698051e+30;
+static const double K_C = 299792458.0;
+static const double K_H = 6.62607015e-34;
+static const double K_KB = 1.380649e-23;
+static const double K_SB = 5.6703744191844314e-08;
+static const double K_KEV = 1.602176634e-16; /* J */
+static const double K_MPC_CM = 3.0856775814913674e+24;
+static const double K_PI = 3.141592653589793;
+
+void ro_constants(double *o)
+{
+    o[0] = K_G * K_MSUN; o[1] = K_C; o[2] = K_H; o[3] = K_KB;
+    o[4] = K_SB; o[5] = K_KEV; o[6] = K_MPC_CM; o[7] = K_PI;
+}
+
+/* relagn.py:583-596 */
+double ro_risco(double a)
+{
+    double Z1 = 1 + pow(1 - a * a, 1.0 / 3) * (pow(1 + a, 1.0 / 3) + pow(1 - a, 1.0 / 3));
+    double Z2 = sqrt(3 * a * a + Z1 * Z1);
+    double sgn = (a > 0) - (a < 0); /* np.sign(0) == 0 */
+    return 3 + Z2 - sgn * sqrt((3 - Z1) * (3 + Z1 + 2 * Z2));
+}
+
+/* relagn.py:624-657 */
+double ro_nt_factor(double r, double a, double risco)
+{
+    double y = sqrt(r), y_isc = sqrt(risco);
+    double ac = acos(a);
+    double y1 = 2 * cos((1.0 / 3) * ac - (K_PI / 3));
+    double y2 = 2 * cos((1.0 / 3) * ac + (K_PI / 3));
+    double y3 = -2 * cos((1.0 / 3) * ac);
+    double B = 1 - (3 / r) + ((2 * a) / pow(r, 1.5));
+    double C1 = 1 - (y_isc / y) - ((3 * a) / (2 * y)) * log(y / y_isc);
+    double C2 = ((3 * (y1 - a) * (y1 - a)) / (y * y1 * (y1 - y2) * (y1 - y3))) * log((y - y1) / (y_isc - y1));
+    C2 += ((3 * (y2 - a) * (y2 - a)) / (y * y2 * (y2 - y1) * (y2 - y3))) * log((y - y2) / (y_isc - y2));
+    C2 += ((3 * (y3 - a) * (y3 - a)) / (y * y3 * (y3 - y1) * (y3 - y2))) * log((y - y3) / (y_isc - y3));
+    return (C1 - C2) / B;
+}
+
+/* relagn.py:662-685 */
+double ro_tnt4(double r, double M, double mdot, double Mdot_edd, double Rg,
+               double a, double risco)
+{
+    double Rt = ro_nt_factor(r, a, risco);
+    double rr = r * Rg;
+    double const_fac = (3 * (K_G * K_MSUN) * M * mdot * Mdot_edd) / (8 * K_PI * K_SB * (rr * rr * rr));
+    return const_fac * Rt;
+}
+
+/* relagn.py:689-719 (open intervals: exactly 1e5 K -> 1) */
+double ro_fcol(double T)
+{
+    if (T > 1e5) {
+        double TkeV = (K_KB * T) / K_KEV;
+        return pow(72 / TkeV, 1.0 / 9);
+    } else if (T < 1e5 && T > 3e4) {
+        return pow(T / 3e4, 0.82);
+    }
+    return 1.0;
+}
+
+/* relagn.py:731-776: edges built top-down by repeated subtraction, innermost
+ * edge snapped to logr_in (bin up to 2x wide; region narrower than one step
+ * collapses to a single edge = no annulus).  returns number of edges. */
+int ro_make_rbins(double logr_in, double logr_out, double dlr, double *edges, int cap)
+{
+    /* generate descending into a temp, then reverse */
+    int n = 1, cap_t = 64;
+    double *t = (double *)malloc(sizeof(double) * cap_t);
+    double i = logr_out;
+    t[0] = logr_out;
+    while (i > logr_in) {
+        i = i - dlr;
+        if (n == cap_t) { cap_t *= 2; t = (double *)realloc(t, sizeof(double) * cap_t); }
+        t[n++] = i;
+    }
+    /* ascending view: bins[k] = t[n-1-k] */
+    int start = n - 1; /* index in t of bins[0] */
+    if (t[start] != logr_in) {
+        if (t[start] < logr_in) {
+            if (n > 1) { start -= 1; n -= 1; t[start] = logr_in; }
+            else t[start] = logr_in;
+        } else {
+            t[start] = logr_in;
+        }
+    }
+    if (n > cap) { free(t); return -n; }
+    for (int k = 0; k < n; k++) edges[k] = t[start - k];
+    free(t);
+    return n;
+}
+
+/* relagn.py:45-50 */
+void ro_black_body(double T, const double *nu, int n, double *B)
+{
+    for (int j = 0; j < n; j++) {
+        double pre = (2 * K_H * (nu[j] * nu[j] * nu[j])) / (K_C * K_C);
+        double ef = exp((K_H * nu[j]) / (K_KB * T)) - 1;
+        B[j] = K_PI * (pre / ef);
+    }
+}
+
+/* np.trapz(y, x) */
+double ro_trapz(const double *y, const double *x, int n)
+{
+    long double s = 0;
+    for (int j = 0; j + 1 < n; j++) s += (long double)((x[j + 1] - x[j]) * (y[j + 1] + y[j]) / 2.0);
+    return (double)s;
+}
+
+/* ---------------- pyNTHCOMP port ---------------- */
+
+/* pyNTHCOMP.py:175-251 */
+static void thermlc(double tautom, double theta, double deltal, const double *x,
+                    int jmax, const double *dphdot, const double *bet,
+                    const double *c2, double *dphesc)
+{
+    double a[RO_NTH], b[RO_NTH], c[RO_NTH], d[RO_NTH], alp[RO_NTH], u[RO_NTH], g[RO_NTH], gam[RO_NTH];
+    memset(a, 0, sizeof a); memset(b, 0, sizeof b); memset(c, 0, sizeof c); memset(d, 0, sizeof d);
+    memset(alp, 0, sizeof alp); memset(u, 0, sizeof u); memset(g, 0, sizeof g); memset(gam, 0, sizeof gam);
+    memset(dphesc, 0, sizeof(double) * RO_NTH);
+    double c20 = tautom / deltal;
+    for (int j = 1; j < jmax - 1; j++) {
+        double w1 = sqrt(x[j] * x[j + 1]);
+        double w2 = sqrt(x[j - 1] * x[j]);
+        a[j] = -c20 * c2[j] * (theta / deltal / w1 + 0.5);
+        double t1 = -c20 * c2[j] * (0.5 - theta / deltal / w1);
+        double t2 = c20 * c2[j - 1] * (theta / deltal / w2 + 0.5);
+        double t3 = (x[j] * x[j] * x[j]) * (tautom * bet[j]);
+        b[j] = t1 + t2 + t3;
+        c[j] = c20 * c2[j - 1] * (0.5 - theta / deltal / w2);
+        d[j] = x[j] * dphdot[j];
+    }
+    double x32 = sqrt(x[0] * x[1]);
+    double aa = (theta / deltal / x32 + 0.5) / (theta / deltal / x32 - 0.5);
+    u[jmax - 1] = 0.0;
+    alp[1] = b[1] + c[1] * aa;
+    gam[1] = a[1] / alp[1];
+    for (int j = 2; j < jmax - 1; j++) {
+        alp[j] = b[j] - c[j] * gam[j - 1];
+        gam[j] = a[j] / alp[j];
+    }
+    g[1] = d[1] / alp[1];
+    for (int j = 2; j < jmax - 2; j++) g[j] = (d[j] - c[j] * g[j - 1]) / alp[j];
+    g[jmax - 2] = (d[jmax - 2] - a[jmax - 2] * u[jmax - 1] - c[jmax - 2] * g[jmax - 3]) / alp[jmax - 2];
+    u[jmax - 2] = g[jmax - 2];
+    for (int j = 2; j < jmax + 1; j++) {
+        int jj = jmax - j;
+        u[jj] = g[jj] - gam[jj] * u[jj + 1];
+    }
+    u[0] = aa * u[1];
+    for (int j = 0; j < jmax; j++) dphesc[j] = x[j] * x[j] * u[j] * bet[j] * tautom;
+}
+
+/* pyNTHCOMP.py:80-173.  x, sptot are [RO_NTH]. */
+void ro_thcompton(double tempbb, double theta, double gamma, double *x, int *jmax_out, double *sptot)
+{
+    double dphdot[RO_NTH], rel[RO_NTH], c2[RO_NTH], bet[RO_NTH], dphesc[RO_NTH];
+    memset(dphdot, 0, sizeof dphdot); memset(rel, 0, sizeof rel); memset(c2, 0, sizeof c2);
+    memset(bet, 0, sizeof bet); memset(sptot, 0, sizeof(double) * RO_NTH); memset(x, 0, sizeof(double) * RO_NTH);
+    double tautom = sqrt(2.250 + 3.0 / (theta * ((gamma + .50) * (gamma + .50) - 2.250))) - 1.50;
+    double delta = 0.02;
+    double deltal = delta * log(10.0);
+    double xmin = 1e-4 * tempbb;
+    double xmax = 40.0 * theta;
+    int jmax = (int)(log10(xmax / xmin) / delta) + 1;
+    if (jmax > 899) jmax = 899;
+    for (int j = 0; j <= jmax; j++) x[j] = xmin * pow(10.0, j * delta);
+    for (int j = 0; j < jmax; j++) {
+        double w = x[j];
+        double w1 = sqrt(x[j] * x[j + 1]);
+        c2[j] = (w1 * w1 * w1 * w1) / (1.0 + 4.60 * w1 + 1.1 * w1 * w1);
+        if (w <= 0.05) {
+            rel[j] = (1.0 - 2.0 * w + 26.0 * w * w * 0.2);
+        } else {
+            double z1 = (1.0 + w) / (w * w * w);
+            double z2 = 1.0 + 2.0 * w;
+            double z3 = log(z2);
+            double z4 = 2.0 * w * (1.0 + w) / z2;
+            double z5 = z3 / 2.0 / w;
+            double z6 = (1.0 + 3.0 * w) / z2 / z2;
+            rel[j] = (0.75 * (z1 * (z4 - z3) + z5 - z6));
+        }
+    }
+    int jmaxth = (int)(log10(50 * tempbb / xmin) / delta);
+    if (jmaxth > 900) jmaxth = 900;
+    if (jmaxth > jmax) jmaxth = jmax;
+    double pt = K_PI * tempbb;
+    double planck = 15.0 / (pt * pt * pt * pt);
+    for (int j = 0; j < jmaxth; j++) dphdot[j] = planck * (x[j] * x[j]) / (exp(x[j] / tempbb) - 1);
+    int jnr = (int)(log10(0.10 / xmin) / delta + 1);
+    if (jnr > jmax - 1) jnr = jmax - 1;
+    int jrel = (int)(log10(1 / xmin) / delta + 1);
+    if (jrel > jmax) jrel = jmax;
+    double xnr = x[jnr - 1];
+    double xr = x[jrel - 1];
+    for (int j = 0; j < jnr - 1; j++) {
+        double taukn = tautom * rel[j];
+        bet[j] = 1.0 / tautom / (1.0 + taukn / 3.0);
+    }
+    for (int j = (jnr - 1 > 0 ? jnr - 1 : 0); j < jrel; j++) {
+        double taukn = tautom * rel[j];
+        double arg = (x[j] - xnr) / (xr - xnr);
+        double flz = 1 - arg;
+        bet[j] = 1.0 / tautom / (1.0 + taukn / 3.0 * flz);
+    }
+    for (int j = jrel; j < jmax; j++) bet[j] = 1.0 / tautom;
+    thermlc(tautom, theta, deltal, x, jmax, dphdot, bet, c2, dphesc);
+    for (int j = 0; j < jmax - 1; j++) sptot[j] = dphesc[j] * (x[j] * x[j]);
+    *jmax_out = jmax;
+}
+
+/* pyNTHCOMP.py:11-78 */
+void ro_donthcomp(const double *ear, int ne, double gamma, double kte, double ktbb, double z, double *photar)
+{
+    double xth[RO_NTH], spt[RO_NTH];
+    int nth;
+    double zfactor = 1.0 + z;
+    ro_thcompton(ktbb / 511.0, kte / 511.0, gamma, xth, &nth, spt);
+    double xninv = 511.0 / zfactor;
+    int ih = 1;
+    double xx = 1.0 / xninv;
+    while (ih < nth && xx > xth[ih]) ih++;
+    int il = ih - 1;
+    double spp = spt[il] + (spt[ih] - spt[il]) * (xx - xth[il]) / (xth[ih] - xth[il]);
+    double normfac = 1.0 / spp;
+    double *prim = (double *)calloc(ne, sizeof(double));
+    int j = 0;
+    for (int i = 0; i < ne; i++) {
+        photar[i] = 0.0;
+        while (j <= nth && 511.0 * xth[j] < ear[i] * zfactor) j++;
+        if (j <= nth) {
+            if (j > 0) {
+                int jl = j - 1;
+                prim[i] = spt[jl] + ((ear[i] / 511.0 * zfactor - xth[jl]) * (spt[jl + 1] - spt[jl]) / (xth[jl + 1] - xth[jl]));
+            } else {
+                prim[i] = spt[0];
+            }
+        }
+    }
+    for (int i = 1; i < ne; i++)
+        photar[i] = (0.5 * (prim[i] / (ear[i] * ear[i]) + prim[i - 1] / (ear[i - 1] * ear[i - 1])) * (ear[i] - ear[i - 1]) * normfac);
+    free(prim);
+}
+
+/* ---------------- model state ---------------- */
+
+typedef struct {
+    double M, dist, d, mdot, a, inc, cosinc;
+    double kTe_h, kTe_w, gamma_h, gamma_w, r_h, r_w, r_out, fcol, hmax, z;
+    double risco, r_sg, L_edd, eta, Mdot_edd, Rg, dlog_r;
+    double Ldiss, Lseed, kTseed;
+    int flags;
+} model_t;
+
+static double m_tnt4(const model_t *m, double r)
+{
+    return ro_tnt4(r, m->M, m->mdot, m->Mdot_edd, m->Rg, m->a, m->risco);
+}
+
+/* relagn.py:1227-1264 */
+static double m_lseed(const model_t *m)
+{
+    int cap = 16 + (int)(fabs(log10(m->r_out) - log10(m->r_h)) / m->dlog_r) + 8;
+    double *e = (double *)malloc(sizeof(double) * cap);
+    int n = ro_make_rbins(log10(m->r_h), log10(m->r_out), m->dlog_r, e, cap);
+    double Lseed_tot = 0;
+    double hc = m->r_h < m->hmax ? m->r_h : m->hmax;
+    for (int i = 0; i + 1 < n; i++) {
+        double dr = pow(10, e[i + 1]) - pow(10, e[i]);
+        double rmid = pow(10, e[i] + m->dlog_r / 2);
+        double cov_frac;
+        if (hc <= rmid) {
+            double theta_0 = asin(hc / rmid);
+            cov_frac = theta_0 - 0.5 * sin(2 * theta_0);
+        } else cov_frac = 0;
+        double T4 = m_tnt4(m, rmid);
+        double Fr = K_SB * T4;
+        double Lr = 2 * 2 * K_PI * rmid * dr * Fr * cov_frac / K_PI * (m->Rg * m->Rg);
+        Lseed_tot += Lr;
+    }
+    free(e);
+    return Lseed_tot;
+}
+
+/* integrand of relagn.py:1285 */
+static double m_ldiss_f(const model_t *m, double rc)
+{
+    return 2 * K_SB * m_tnt4(m, rc) * 2 * K_PI * rc * (m->Rg * m->Rg);
+}
+
+/* 15-point Gauss-Kronrod on [a,b]; returns integral, *err = |K15-G7| */
+static double gk15(const model_t *m, double a, double b, double *err)
+{
+    static const double xgk[8] = {0.991455371120812639206854697526329, 0.949107912342758524526189684047851,
+        0.864864423359769072789712788640926, 0.741531185599394439863864773280788,
+        0.586087235467691130294144838258730, 0.405845151377397166906606412076961,
+        0.207784955007898467600689403773245, 0.000000000000000000000000000000000};
+    static const double wgk[8] = {0.022935322010529224963732008058970, 0.063092092629978553290700663189204,
+        0.104790010322250183839876322541518, 0.140653259715525918745189590510238,
+        0.169004726639267902826583426598550, 0.190350578064785409913256402421014,
+        0.204432940075298892414161999234649, 0.209482141084727828012999174891714};
+    static const double wg[4] = {0.129484966168869693270611432679082, 0.279705391489276667901467771423780,
+        0.381830050505118944950369775488975, 0.417959183673469387755102040816327};
+    double c = 0.5 * (a + b), h = 0.5 * (b - a);
+    double fc = m_ldiss_f(m, c);
+    double rk = fc * wgk[7], rg = fc * wg[3];
+    for (int j = 0; j < 7; j++) {
+        double dx = h * xgk[j];
+        double f1 = m_ldiss_f(m, c - dx), f2 = m_ldiss_f(m, c + dx);
+        rk += wgk[j] * (f1 + f2);
+        if (j & 1) rg += wg[j / 2] * (f1 + f2);
+    }
+    *err = fabs((rk - rg) * h);
+    return rk * h;
+}
+
+static double adapt_gk(const model_t *m, double a, double b, double tol_abs, int depth)
+{
+    double err;
+    double v = gk15(m, a, b, &err);
+    if (err <= tol_abs || depth > 40) return v;
+    double c = 0.5 * (a + b);
+    return adapt_gk(m, a, c, tol_abs * 0.5, depth + 1) + adapt_gk(m, c, b, tol_abs * 0.5, depth + 1);
+}
+
+/* relagn.py:1268-1292: Ldiss = quad(...), Lseed; the oracle integrates to
+ * ~1e-13 relative (scipy's QAGS stops at 1.49e-8 estimated, its true error on
+ * this smooth integrand is far smaller; pinned by tests/golden). */
+static double m_hot_lumin(model_t *m)
+{
+    if (m->r_h > m->risco) {
+        double err;
+        double rough = gk15(m, m->risco, m->r_h, &err);
+        m->Ldiss = adapt_gk(m, m->risco, m->r_h, fabs(rough) * 1e-13, 0);
+    } else m->Ldiss = 0.0;
+    m->Lseed = m_lseed(m);
+    return m->Ldiss + m->Lseed;
+}
+
+/* relagn.py:1164-1197 */
+static double m_seed_temp(const model_t *m)
+{
+    double T4_edge = m_tnt4(m, m->r_h);
+    double Tedge = pow(T4_edge, 0.25);
+    double kT_edge = (K_KB * Tedge) / K_KEV;
+    double kT_seed;
+    if (m->r_w != m->r_h) {
+        double ysb = pow(m->gamma_w * (4.0 / 9), -4.5);
+        kT_seed = exp(ysb) * kT_edge;
+    } else {
+        kT_seed = kT_edge;
+        double fcol_r = m->fcol < 0 ? ro_fcol(Tedge) : m->fcol;
+        kT_seed *= fcol_r;
+    }
+    return kT_seed;
+}
+
+/* relagn.py:1877-1898 */
+static void m_set_rhot(model_t *m)
+{
+    double dlr = 1.0 / 1000;
+    int cap = 64 + (int)((log10(m->r_sg) - log10(m->risco)) / dlr);
+    if (cap < 64) cap = 64;
+    double *e = (double *)malloc(sizeof(double) * cap);
+    int n = ro_make_rbins(log10(m->risco), log10(m->r_sg), dlr, e, cap);
+    double Ldiss = 0.0, rmid = m->risco;
+    int i = 0;
+    while (Ldiss < 0.02 * m->L_edd && i < n - 1) {
+        rmid = pow(10, e[i] + dlr / 2);
+        double dr = pow(10, e[i + 1]) - pow(10, e[i]);
+        double Tnt4 = m_tnt4(m, rmid);
+        Ldiss += K_SB * Tnt4 * 4 * K_PI * rmid * dr * (m->Rg * m->Rg);
+        i++;
+    }
+    m->r_h = rmid;
+    free(e);
+}
+
+/* constructor: relagn.py:232-357 (model 0), relagn.py:1767-1857 (model 1) */
+static int m_init(model_t *m, const double *p, int model, double dr_dex)
+{
+    memset(m, 0, sizeof *m);
+    m->dlog_r = 1 / dr_dex;
+    if (model == 0) {
+        m->M = p[0]; m->dist = p[1]; m->d = p[1] * K_MPC_CM; m->mdot = pow(10, p[2]);
+        m->a = p[3]; m->cosinc = p[4]; m->inc = acos(p[4]);
+        m->kTe_h = p[5]; m->kTe_w = p[6]; m->gamma_h = p[7]; m->gamma_w = p[8];
+        m->r_h = p[9]; m->r_w = p[10]; m->r_out = pow(10, p[11]); m->fcol = p[12];
+        m->hmax = p[13]; m->z = p[14];
+    } else {
+        m->M = p[0]; m->dist = p[1]; m->d = p[1] * K_MPC_CM; m->mdot = pow(10, p[2]);
+        m->a = p[3]; m->cosinc = p[4]; m->inc = acos(p[4]); m->fcol = p[5]; m->z = p[6];
+    }
+    if (!(m->a >= -0.998 && m->a <= 0.998)) return RO_E_SPIN;
+    if (!(m->cosinc <= 1 && m->cosinc >= 0.09)) return RO_E_INC;
+    if (model == 1) {
+        double lmdot = log10(m->mdot);
+        if (!(lmdot >= -1.65 && lmdot <= 0.5)) return RO_E_MDOT;
+    }
+    m->risco = ro_risco(m->a);
+    {   /* relagn.py:599-609 */
+        double alpha = 0.1, m9 = m->M / 1e9;
+        m->r_sg = 2150 * pow(m9, -2.0 / 9) * pow(m->mdot, 4.0 / 9) * pow(alpha, 2.0 / 9);
+    }
+    m->L_edd = 1.39e31 * m->M;
+    m->eta = 1 - sqrt(1 - 2 / (3 * m->risco));
+    if (model == 0) {
+        if (p[11] < 0) m->r_out = m->r_sg;
+        if (p[10] == -1) m->r_w = m->risco;
+        if (p[9] == -1) m->r_h = m->risco;
+        if (!(m->r_w >= m->r_h)) { m->flags |= RO_F_RW_LT_RH; m->r_w = m->r_h; }
+        if (!(m->r_w <= m->r_out)) { m->flags |= RO_F_RW_GT_ROUT; m->r_w = m->r_out; }
+        if (!(m->r_h >= m->risco)) { m->flags |= RO_F_RH_LT_RISCO; m->r_h = m->risco; }
+        if (!(m->r_w >= m->risco)) { m->flags |= RO_F_RW_LT_RISCO; m->r_w = m->risco; }
+        if (!(m->hmax <= m->r_h)) { m->flags |= RO_F_HMAX_GT_RH; m->hmax = m->r_h; }
+        m->Mdot_edd = m->L_edd / (m->eta * (K_C * K_C));
+        m->Rg = ((K_G * K_MSUN) * m->M) / (K_C * K_C);
+    } else {
+        m->Mdot_edd = m->L_edd / (m->eta * (K_C * K_C));
+        m->Rg = ((K_G * K_MSUN) * m->M) / (K_C * K_C);
+        m_set_rhot(m);
+        m->r_w = 2 * m->r_h;
+        m->r_out = m->r_sg;
+        if (m->r_w > m->r_sg) m->r_w = m->r_sg;
+        m->kTe_h = 100; m->kTe_w = 0.2; m->gamma_w = 2.5;
+        m->hmax = 100.0 < m->r_h ? 100.0 : m->r_h;
+        m_hot_lumin(m);
+        m->gamma_h = (7.0 / 3) * pow(m->Ldiss / m->Lseed, -0.1);
+    }
+    return RO_OK;
+}
+
+static void m_attrs(const model_t *m, int nd, int nw, int nh, int status, double *at)
+{
+    at[RO_A_RISCO] = m->risco; at[RO_A_RSG] = m->r_sg; at[RO_A_ETA] = m->eta; at[RO_A_LEDD] = m->L_edd;
+    at[RO_A_MDOT_EDD] = m->Mdot_edd; at[RO_A_RG] = m->Rg; at[RO_A_RH] = m->r_h; at[RO_A_RW] = m->r_w;
+    at[RO_A_ROUT] = m->r_out; at[RO_A_HMAX] = m->hmax; at[RO_A_GAMMA_H] = m->gamma_h; at[RO_A_KTE_H] = m->kTe_h;
+    at[RO_A_KTE_W] = m->kTe_w; at[RO_A_GAMMA_W] = m->gamma_w; at[RO_A_KTSEED] = m->kTseed;
+    at[RO_A_LDISS] = m->Ldiss; at[RO_A_LSEED] = m->Lseed; at[RO_A_NDISC] = nd; at[RO_A_NWARM] = nw;
+    at[RO_A_NHOT] = nh; at[RO_A_FLAGS] = m->flags; at[RO_A_STATUS] = status; at[RO_A_MDOT] = m->mdot;
+    at[RO_A_INC] = m->inc;
+}
+
+static int region_bins(double r_in, double r_out, double dlr, double **edges)
+{
+    int cap = 16 + (int)(fabs(log10(r_out) - log10(r_in)) / dlr) + 8;
+    *edges = (double *)malloc(sizeof(double) * cap);
+    int n = ro_make_rbins(log10(r_in), log10(r_out), dlr, *edges, cap);
+    return n;
+}
+
+int ro_setup(const double *params, int model, double dr_dex, double *attrs)
+{
+    model_t m;
+    int st = m_init(&m, params, model, dr_dex);
+    if (st != RO_OK) { memset(attrs, 0, sizeof(double) * RO_NATTR); attrs[RO_A_STATUS] = st; return st; }
+    double *e;
+    int nad = region_bins(m.r_w, m.r_out, m.dlog_r, &e); free(e);
+    int nwc = region_bins(m.r_h, m.r_w, m.dlog_r, &e); free(e);
+    int nhc = region_bins(m.risco, m.r_h, m.dlog_r, &e); free(e);
+    if (model == 0) m_hot_lumin(&m);
+    if (m.r_h != m.risco) m.kTseed = m_seed_temp(&m);
+    int nd = (m.r_w != m.r_out && nad != 1) ? nad - 1 : 0;
+    int nw = (m.r_w != m.r_h && nwc != 1) ? nwc - 1 : 0;
+    int nh = (m.r_h != m.risco && nhc != 1) ? nhc - 1 : 0;
+    m_attrs(&m, nd, nw, nh, RO_OK, attrs);
+    return RO_OK;
+}
+
+/* ---------------- evaluation ---------------- */
+
+typedef struct {
+    int nE;
+    const double *Ebins;
+    double *dEs, *Egrid, *nu;
+    int ext;          /* low-nu extension of disc_annuli (relagn.py:868-873) */
+    double *nu_ext;   /* [50 + nE] when ext */
+} grid_t;
+
+static void grid_init(grid_t *g, const double *ebins, int nE)
+{
+    g->nE = nE; g->Ebins = ebins;
+    g->dEs = (double *)malloc(sizeof(double) * nE);
+    g->Egrid = (double *)malloc(sizeof(double) * nE);
+    g->nu = (double *)malloc(sizeof(double) * nE);
+    for (int j = 0; j < nE; j++) {
+        g->dEs[j] = ebins[j + 1] - ebins[j];
+        g->Egrid[j] = ebins[j] + 0.5 * g->dEs[j];
+        g->nu[j] = g->Egrid[j] * K_KEV / K_H;
+    }
+    g->ext = g->Egrid[0] < 1e-4;
+    g->nu_ext = NULL;
+    if (g->ext) {
+        g->nu_ext = (double *)malloc(sizeof(double) * (nE + 50));
+        double numin = g->nu[0];
+        for (int j = 1; j < nE; j++) if (g->nu[j] < numin) numin = g->nu[j];
+        double start = 1e12, stop = numin - 100;
+        double ls = log10(start), le = log10(stop), step = (le - ls) / 49;
+        for (int i = 0; i < 50; i++) g->nu_ext[i] = pow(10.0, i == 49 ? le : i * step + ls);
+        g->nu_ext[0] = start; g->nu_ext[49] = stop;
+        memcpy(g->nu_ext + 50, g->nu, sizeof(double) * nE);
+    }
+}
+static void grid_free(grid_t *g) { free(g->dEs); free(g->Egrid); free(g->nu); free(g->nu_ext); }
+
+/* relagn.py:839-896 */
+static void disc_annulus(const model_t *m, const grid_t *g, double r, double *Lnu, double *work)
+{
+    double T4 = m_tnt4(m, r);
+    double Tann = pow(T4, 0.25);
+    double fcol_r = m->fcol < 0 ? ro_fcol(Tann) : m->fcol;
+    Tann *= fcol_r;
+    const double *nu_use = g->ext ? g->nu_ext : g->nu;
+    int n = g->ext ? g->nE + 50 : g->nE;
+    double *B = work;
+    ro_black_body(Tann, nu_use, n, B);
+    double t = Tann / fcol_r;
+    double norm = K_SB * (t * t * t * t) * (m->Rg * m->Rg);
+    double radiance = ro_trapz(B, nu_use, n);
+    int off = g->ext ? 50 : 0;
+    if (radiance == 0) for (int j = 0; j < g->nE; j++) Lnu[j] = 0;
+    else for (int j = 0; j < g->nE; j++) Lnu[j] = norm * (B[j + off] / radiance);
+}
+
+/* relagn.py:900-939 */
+static void warm_annulus(const model_t *m, const grid_t *g, double r, double *Lnu)
+{
+    double T4 = m_tnt4(m, r);
+    double Tann = pow(T4, 0.25);
+    double kTann = Tann / 1.16048e7;
+    ro_donthcomp(g->Egrid, g->nE, m->gamma_w, m->kTe_w, kTann, 0, Lnu);
+    for (int j = 0; j < g->nE; j++) Lnu[j] = Lnu[j] * (1.0 / K_KEV) * K_H;
+    double norm = K_SB * (Tann * Tann * Tann * Tann) * (m->Rg * m->Rg);
+    double radiance = ro_trapz(Lnu, g->nu, g->nE);
+    if (radiance == 0) for (int j = 0; j < g->nE; j++) Lnu[j] = 0;
+    else for (int j = 0; j < g->nE; j++) Lnu[j] = norm * (Lnu[j] / radiance);
+}
+
+/* relagn.py:1200-1223 */
+static void hot_shape(model_t *m, const grid_t *g, double *F)
+{
+    m->kTseed = m_seed_temp(m);
+    if (m->kTseed < m->kTe_h) {
+        ro_donthcomp(g->Egrid, g->nE, m->gamma_h, m->kTe_h, m->kTseed, 0, F);
+        for (int j = 0; j < g->nE; j++) F[j] = F[j] * (1.0 / K_KEV) * K_H;
+    } else {
+        m->flags |= RO_F_HOT_SEED_GE_KTE;
+        for (int j = 0; j < g->nE; j++) F[j] = 0;
+    }
+}
+
+/* pack -> kyconv -> unpack (relagn.py:970-974, 997-1006) */
+static int ky_annulus(const model_t *m, const grid_t *g, const ro_tables *tab,
+                      double e0, double e1, double rmid, const double *Lnu_ann, double *Lnu_r, double *phs)
+{
+    double d2 = m->d * m->d;
+    for (int j = 0; j < g->nE; j++) {
+        double fl = (Lnu_ann[j] * 4) / K_H;
+        fl = fl / (4 * K_PI * d2);
+        phs[j] = (g->dEs[j] * fl) / g->Egrid[j];
+    }
+    double par[12] = {m->a, m->inc * (180.0 / K_PI), pow(10, e0), 0, pow(10, e1), 0, 0, rmid, 0, 0, (double)g->nE, -1};
+    int st = ro_kyconv(tab, g->Ebins, g->nE, par, phs);
+    if (st) return st;
+    for (int j = 0; j < g->nE; j++) {
+        double pr = phs[j] / g->dEs[j];
+        double L_kev = pr * g->Egrid[j] * 4 * K_PI * d2;
+        Lnu_r[j] = L_kev * K_H;
+    }
+    return 0;
+}
+
+int ro_eval(const double *params, int model, double dr_dex, const double *ebins,
+            int nE, int rel, const ro_tables *tab, double *out, double *attrs)
+{
+    model_t m;
+    double *disc = out, *warm = out + nE, *hot = out + 2 * nE, *tot = out + 3 * nE;
+    memset(out, 0, sizeof(double) * 4 * nE);
+    int st = m_init(&m, params, model, dr_dex);
+    if (st != RO_OK) {
+        if (attrs) { memset(attrs, 0, sizeof(double) * RO_NATTR); attrs[RO_A_STATUS] = st; }
+        return st;
+    }
+    grid_t g;
+    grid_init(&g, ebins, nE);
+    double *ead, *ewc, *ehc;
+    int nad = region_bins(m.r_w, m.r_out, m.dlog_r, &ead);
+    int nwc = region_bins(m.r_h, m.r_w, m.dlog_r, &ewc);
+    int nhc = region_bins(m.risco, m.r_h, m.dlog_r, &ehc);
+    double *Lann = (double *)malloc(sizeof(double) * nE);
+    double *Lr = (double *)malloc(sizeof(double) * nE);
+    double *phs = (double *)malloc(sizeof(double) * nE);
+    double *work = (double *)malloc(sizeof(double) * (nE + 50));
+    double *Fhot = (double *)calloc(nE, sizeof(double));
+    int err = 0;
+    int has_disc = (m.r_w != m.r_out && nad != 1);
+    int has_warm = (m.r_w != m.r_h && nwc != 1);
+    int has_hot = (m.r_h != m.risco && nhc != 1);
+    if (m.r_h != m.risco || model == 1) hot_shape(&m, &g, Fhot);
+    if (model == 0) m_hot_lumin(&m); /* sets Ldiss/Lseed attrs (relagn.py:1285-1289) */
+
+    /* disc: relagn.py:950-1059 */
+    if (has_disc) {
+        for (int i = 0; i + 1 < nad && !err; i++) {
+            double dr_bin = pow(10, ead[i + 1]) - pow(10, ead[i]);
+            double rmid = pow(10, ead[i] + m.dlog_r / 2);
+            disc_annulus(&m, &g, rmid, Lann, work);
+            if (rel && ead[i] <= 3 && ead[i + 1] <= 3) {
+                err = ky_annulus(&m, &g, tab, ead[i], ead[i + 1], rmid, Lann, Lr, phs);
+                for (int j = 0; j < nE; j++) disc[j] += Lr[j];
+            } else if (rel) {
+                for (int j = 0; j < nE; j++) disc[j] += Lann[j] * 2 * K_PI * 2 * rmid * dr_bin * m.cosinc / 0.5;
+            } else {
+                for (int j = 0; j < nE; j++) disc[j] += Lann[j] * 2 * K_PI * 2 * rmid * dr_bin;
+            }
+        }
+        if (!rel) for (int j = 0; j < nE; j++) disc[j] = disc[j] * m.cosinc / 0.5;
+    }
+    /* warm: relagn.py:1063-1156 */
+    if (has_warm) {
+        for (int i = 0; i + 1 < nwc && !err; i++) {
+            double dr_bin = pow(10, ewc[i + 1]) - pow(10, ewc[i]);
+            double rmid = pow(10, ewc[i] + m.dlog_r / 2);
+            warm_annulus(&m, &g, rmid, Lann);
+            if (rel && ewc[i] <= 3 && ewc[i + 1] <= 3) {
+                err = ky_annulus(&m, &g, tab, ewc[i], ewc[i + 1], rmid, Lann, Lr, phs);
+                for (int j = 0; j < nE; j++) warm[j] += Lr[j];
+            } else if (rel) {
+                for (int j = 0; j < nE; j++) warm[j] += Lann[j] * 2 * K_PI * 2 * rmid * dr_bin * m.cosinc / 0.5;
+            } else {
+                for (int j = 0; j < nE; j++) warm[j] += Lann[j] * 4 * K_PI * rmid * dr_bin;
+            }
+        }
+        if (!rel) for (int j = 0; j < nE; j++) warm[j] = warm[j] * m.cosinc / 0.5;
+    }
+    /* hot: relagn.py:1295-1401 */
+    if (has_hot) {
+        double shape_int = ro_trapz(Fhot, g.nu, nE);
+        if (rel) {
+            double Lseed = m_lseed(&m);
+            for (int i = 0; i + 1 < nhc && !err; i++) {
+                double dr_bin = pow(10, ehc[i + 1]) - pow(10, ehc[i]);
+                double rmid = pow(10, ehc[i] + m.dlog_r / 2);
+                double T4 = m_tnt4(&m, rmid);
+                double Ldiss_ann = K_SB * T4 * (m.Rg * m.Rg);
+                double Lseed_ann = Lseed / (4 * K_PI * rmid * dr_bin * (nhc - 1));
+                double Ltot_ann = Ldiss_ann + Lseed_ann;
+                for (int j = 0; j < nE; j++) Lann[j] = Ltot_ann * (Fhot[j] / shape_int);
+                if (ehc[i] <= 3 && ehc[i + 1] <= 3) {
+                    err = ky_annulus(&m, &g, tab, ehc[i], ehc[i + 1], rmid, Lann, Lr, phs);
+                    for (int j = 0; j < nE; j++) hot[j] += Lr[j] / (m.cosinc / 0.5);
+                } else {
+                    for (int j = 0; j < nE; j++) hot[j] += Lann[j] * 2 * K_PI * 2 * rmid * dr_bin;
+                }
+            }
+        } else {
+            double Lum = m_hot_lumin(&m);
+            for (int j = 0; j < nE; j++) hot[j] = Lum * (Fhot[j] / shape_int);
+        }
+    }
+    for (int j = 0; j < nE; j++) tot[j] = disc[j] + warm[j] + hot[j];
+    if (attrs) m_attrs(&m, has_disc ? nad - 1 : 0, has_warm ? nwc - 1 : 0, has_hot ? nhc - 1 : 0, err ? RO_E_GRID : RO_OK, attrs);
+    free(ead); free(ewc); free(ehc); free(Lann); free(Lr); free(phs); free(work); free(Fhot);
+    grid_free(&g);
+    return err ? RO_E_GRID : RO_OK;
+}
+
+typedef struct {
+    const double *params; int model; double dr_dex; const double *ebins; int nE, rel;
+    const ro_tables *tab; double *out, *attrs; int *status;
+} batch_ctx;
+
+static void batch_body(int p, void *vc)
+{
+    batch_ctx *c = (batch_ctx *)vc;
+    int st = ro_eval(c->params + (size_t)p * RO_NPAR, c->model, c->dr_dex, c->ebins, c->nE, c->rel, c->tab,
+                     c->out + (size_t)p * 4 * c->nE, c->attrs ? c->attrs + (size_t)p * RO_NATTR : NULL);
+    if (c->status) c->status[p] = st;
+}
+
+void ro_eval_batch(const double *params, int P, int model, double dr_dex,
+                   const double *ebins, int nE, int rel, const ro_tables *tab,
+                   double *out, double *attrs, int *status, int threads)
+{
+    batch_ctx c = {params, model, dr_dex, ebins, nE, rel, tab, out, attrs, status};
+    ro_par_for(P, threads, batch_body, &c);
+}
