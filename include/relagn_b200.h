@@ -1,0 +1,156 @@
+/*
+ * relagn_b200.h -- C ABI of the B200-native RELAGN spectrum-evaluation path.
+ *
+ * Plain pointers and sizes only (no torch / C++ types).  The library is built
+ * for sm_100a and has NO CPU fallback: every compute entry point fails with
+ * RG_E_CUDA when no usable device is present.
+ *
+ * Seams replaced (paths relative to the reference repo scotthgn/RELAGN):
+ *
+ *  B1  xspec.callModelFunction('kyconv', energies, params[12], flux)
+ *        src/python_version/relagn.py:979-1001, 1095-1099, 1353-1357
+ *        (Fortran twin: call kyconv(es, nn, kpar, ifl, ph, pherr),
+ *         src/fortran_version/relagn_dir/relagn.f:359,424,547)
+ *      -> rg_kyconv()
+ *
+ *  B2  the model classes' spectrum path: relagn.__init__ / relqso.__init__
+ *        (relagn.py:232-357, 1767-1857) + get_totSED / get_*Component
+ *        (relagn.py:1412-1577) -> do_rel*Spec / do_nonrel*Spec
+ *        (relagn.py:950-1156, 1322-1401)
+ *      -> rg_eval_batch() (device buffers) / rg_eval_batch_host() (host buffers)
+ *
+ *  Kerr transfer tables (KYCONV's FITS tables, not in the reference repo)
+ *      -> rg_tables_generate() (device ray tracer) / rg_tables_upload()
+ *
+ * Conventions: all entry points return RG_OK (0) or a negative RG_E_* code;
+ * rg_last_error() returns a static, thread-local message for the last
+ * failure.  The caller owns every buffer passed in; the context owns only its
+ * scratch, grid and table storage.  One context per device; calls on one
+ * context must be serialised by the caller (stream-ordered on `stream`).
+ */
+#ifndef RELAGN_B200_H
+#define RELAGN_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RG_VERSION 100
+
+#define RG_NPAR 15  /* relagn ctor order (relagn.py:232-247):
+                       M, dist, log_mdot, a, cos_inc, kTe_hot, kTe_warm,
+                       gamma_hot, gamma_warm, r_hot, r_warm, log_rout, fcol,
+                       h_max, z.   relqso (relagn.py:1767-1774) uses slots
+                       0..6 = M, dist, log_mdot, a, cos_inc, fcol, z. */
+#define RG_NATTR 24
+
+/* attribute slots of the per-set record returned next to the spectra
+ * (the reference's public attributes, docs/relagn_docs.tex:202-242) */
+enum {
+    RG_A_RISCO = 0, RG_A_RSG, RG_A_ETA, RG_A_LEDD, RG_A_MDOT_EDD, RG_A_RG,
+    RG_A_RH, RG_A_RW, RG_A_ROUT, RG_A_HMAX, RG_A_GAMMA_H, RG_A_KTE_H,
+    RG_A_KTE_W, RG_A_GAMMA_W, RG_A_KTSEED, RG_A_LDISS, RG_A_LSEED,
+    RG_A_NDISC, RG_A_NWARM, RG_A_NHOT, RG_A_FLAGS, RG_A_STATUS, RG_A_MDOT,
+    RG_A_INC
+};
+
+/* RG_A_FLAGS bits: the reference's print-and-clamp warnings (relagn.py:388-421) */
+#define RG_F_RW_LT_RH 1
+#define RG_F_RW_GT_ROUT 2
+#define RG_F_RH_LT_RISCO 4
+#define RG_F_RW_LT_RISCO 8
+#define RG_F_HMAX_GT_RH 16
+#define RG_F_HOT_SEED_GE_KTE 32 /* kT_seed >= kTe_hot: hot shape is zero (relagn.py:1212-1221) */
+
+/* RG_A_STATUS per set: the reference's ValueError conditions */
+#define RG_S_OK 0
+#define RG_S_SPIN 1   /* relagn.py:372-377 */
+#define RG_S_INC 2    /* relagn.py:380-386 */
+#define RG_S_MDOT 3   /* relagn.py:1861-1874 (relqso) */
+#define RG_S_CAP 4    /* internal capacity exceeded (radial bins / nthcomp grid) */
+
+/* model selector */
+#define RG_MODEL_RELAGN 0
+#define RG_MODEL_RELQSO 1
+
+/* rg_eval_batch flags */
+#define RG_FLAG_REL 1u        /* relativistic transfer (get_*(rel=True)) */
+#define RG_FLAG_COMPONENTS 2u /* out is [P][4][nE] = disc, warm, hot, total; else [P][nE] total */
+
+/* error codes */
+#define RG_OK 0
+#define RG_E_CUDA (-1)     /* CUDA runtime failure / no device */
+#define RG_E_ARG (-2)      /* bad argument */
+#define RG_E_NOTABLES (-3) /* relativistic call without tables */
+#define RG_E_GRID (-4)     /* energy grid unsupported for this call (rel needs a geometric grid) */
+#define RG_E_UNSUPPORTED (-5) /* kyconv parameter combination not implemented */
+#define RG_E_NOMEM (-6)
+
+typedef struct rg_ctx rg_ctx;
+
+int rg_version(void);
+const char *rg_last_error(void);
+
+/* one context per device.  device < 0: current device. */
+int rg_ctx_create(int device, rg_ctx **out);
+void rg_ctx_destroy(rg_ctx *ctx);
+
+/* ---- energy grid (relagn.py:335-346, new_ear relagn.py:780-805) ----
+ * ebins: host, nE+1 ascending bin edges in keV.  Derives dE, bin centres
+ * (left + dE/2), nu grid; detects a geometric grid (needed for RG_FLAG_REL). */
+int rg_set_grid(rg_ctx *ctx, const double *ebins_host, int nE);
+
+/* ---- Kerr transfer tables ----
+ * Node grid: spins[n_spin] ascending, thetas[n_inc] ascending (radians).
+ * Per node two planes g[NR][NPHI], jn[NR][NPHI] (float32); rows at
+ * r_s = r_h + (risco - r_h) 10^(s dl), columns phi_t = 2 pi t/NPHI + phi0(r_s).
+ * Layout [n_spin][n_inc][2][NR][NPHI].
+ * generate: ray-traces on the device.  upload/download: host <-> device. */
+int rg_tables_generate(rg_ctx *ctx, const double *spins, int n_spin, const double *thetas, int n_inc, int NR,
+                       int NPHI, double dl, long *n_unresolved);
+int rg_tables_upload(rg_ctx *ctx, const double *spins, int n_spin, const double *thetas, int n_inc, int NR, int NPHI,
+                     double dl, const float *data_host);
+int rg_tables_download(rg_ctx *ctx, float *data_host, size_t n_floats);
+int rg_tables_info(rg_ctx *ctx, int *n_spin, int *n_inc, int *NR, int *NPHI, double *dl, size_t *n_floats);
+
+/* ---- B1: the kyconv seam ----
+ * energies: host, nE+1 edges (geometric grid); par: the reference's 12
+ * parameters [a, inc_deg, r_in, ms, r_out, alpha, beta, r_break, zshift,
+ * ntable, nE_internal, norm]; flux: host, nE photons/bin, convolved in place.
+ * Supported: ms = 0, ntable = 0 (isotropic), norm = -1 (no renormalisation)
+ * -- exactly what the reference passes (relagn.py:997-998). */
+int rg_kyconv(rg_ctx *ctx, const double *energies_host, int nE, const double *par12, double *flux_inout_host);
+
+/* shift-histogram of one annulus on a log grid of step dlnE (diagnostic /
+ * test entry; the same device code builds every annulus inside
+ * rg_eval_batch).  H: host, cap doubles; *kmin, *nk describe the support. */
+int rg_ky_kernel(rg_ctx *ctx, double a, double theta_o, double r1, double r2, double alpha, double beta, double rb,
+                 double zshift, double dlnE, double *H_host, int cap, int *kmin, int *nk);
+
+/* ---- B2: batched spectrum evaluation ----
+ * d_params: DEVICE [P][RG_NPAR]; d_out: DEVICE [P][nE] or [P][4][nE] (W/Hz,
+ * the reference's internal Lnu before unit conversion); d_attrs: DEVICE
+ * [P][RG_NATTR] or NULL.  Uses the grid of rg_set_grid and, with RG_FLAG_REL,
+ * the resident tables.  stream: a cudaStream_t (NULL = default stream).
+ * Asynchronous with respect to the host. */
+int rg_eval_batch(rg_ctx *ctx, const double *d_params, int P, int model, double dr_dex, unsigned flags,
+                  double *d_out, double *d_attrs, void *stream);
+
+/* same with HOST buffers: stages through pinned memory, copies in and out
+ * inside the call, synchronises before returning. */
+int rg_eval_batch_host(rg_ctx *ctx, const double *params_host, int P, int model, double dr_dex, unsigned flags,
+                       double *out_host, double *attrs_host);
+
+/* number of kernels launched by this context so far (for accounting) */
+long rg_launch_count(rg_ctx *ctx);
+
+/* measured FP64 FMA throughput of the device in TFLOP/s (micro-benchmark,
+ * used as the roofline denominator of the FP64-bound kernels) */
+int rg_measure_fp64_peak(rg_ctx *ctx, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

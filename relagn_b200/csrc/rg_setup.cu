@@ -1,0 +1,373 @@
+// rg_setup.cu -- per-parameter-set setup kernel and the batched Kompaneets
+// (nthcomp) solver.
+//
+//  setup_kernel   : one thread per parameter set.  Restates the reference
+//                   constructors relagn.__init__ (relagn.py:232-357) and
+//                   relqso.__init__ (relagn.py:1767-1857): derived scalars,
+//                   clamps, region bin counts, Lseed (relagn.py:1227-1264),
+//                   Ldiss (relagn.py:1285, fixed Gauss-Legendre instead of
+//                   QUADPACK), relqso r_hot search (relagn.py:1877-1898) and
+//                   gamma_hot (relagn.py:1901-1907); reserves this set's
+//                   nthcomp systems.
+//  nthcomp_kernel : one thread per system (a warm annulus or a hot shape).
+//                   Restates pyNTHCOMP._thcompton/_thermlc
+//                   (pyNTHCOMP.py:80-251): the Thomas recurrences are strictly
+//                   serial in j, so parallelism is across systems; work arrays
+//                   live in a [j][system] scratch so a warp's accesses coalesce.
+#include "rg_common.cuh"
+#include "rg_kernels.h"
+
+// ---------------------------------------------------------------------------
+__device__ static double seed_temp(const SetRec &r, const NtConst &nt)
+{   // relagn.py:1164-1197
+    double T4 = rg_tnt4(nt, r.r_h);
+    double Tedge = pow(T4, 0.25);
+    double kT_edge = (RGK_KB * Tedge) / RGK_KEV;
+    double kT_seed;
+    if (r.r_w != r.r_h) {
+        double ysb = pow(r.gamma_w * (4.0 / 9), -4.5);
+        kT_seed = exp(ysb) * kT_edge;
+    } else {
+        double fcol_r = r.fcol < 0 ? rg_fcol(Tedge) : r.fcol;
+        kT_seed = kT_edge * fcol_r;
+    }
+    return kT_seed;
+}
+
+__device__ static double lseed_sum(const SetRec &r, const NtConst &nt)
+{   // relagn.py:1227-1264 (summed top-down; the reference sums bottom-up)
+    BinIter it;
+    it.start(log10(r.r_h), log10(r.r_out), r.dlog_r);
+    double lo, hi, tot = 0;
+    double hc = r.r_h < r.hmax ? r.r_h : r.hmax;
+    double Rg2 = r.Rg * r.Rg;
+    while (it.next(lo, hi)) {
+        double dr = pow(10.0, hi) - pow(10.0, lo);
+        double rmid = pow(10.0, lo + r.dlog_r / 2);
+        double cov = 0;
+        if (hc <= rmid) {
+            double th0 = asin(hc / rmid);
+            cov = th0 - 0.5 * sin(2 * th0);
+        }
+        double Fr = RGK_SB * rg_tnt4(nt, rmid);
+        tot += 2 * 2 * RGK_PI * rmid * dr * Fr * cov / RGK_PI * Rg2;
+    }
+    return tot;
+}
+
+__device__ static double ldiss_quad(const SetRec &r, const NtConst &nt)
+{   // relagn.py:1285-1286: int_{risco}^{r_h} 2 sigma T^4 2 pi r Rg^2 dr, composite GL16 in ln r
+    if (!(r.r_h > r.risco)) return 0.0;
+    double ta = log(r.risco), tb = log(r.r_h);
+    int npan = 2 + (int)ceil((tb - ta) * 2.0);
+    if (npan > 16) npan = 16;
+    double tot = 0;
+    for (int p = 0; p < npan; p++) {
+        double t0 = ta + (tb - ta) * p / npan, t1 = ta + (tb - ta) * (p + 1) / npan;
+        double tm = 0.5 * (t0 + t1), th = 0.5 * (t1 - t0);
+        double s = 0;
+        for (int i = 0; i < 8; i++) {
+            double rp = exp(tm + th * RG_GL16_X[i]), rm = exp(tm - th * RG_GL16_X[i]);
+            s += RG_GL16_W[i] * (rg_tnt4(nt, rp) * rp * rp + rg_tnt4(nt, rm) * rm * rm);
+        }
+        tot += s * th;
+    }
+    return 2 * RGK_SB * 2 * RGK_PI * (r.Rg * r.Rg) * tot;
+}
+
+__global__ void __launch_bounds__(128)
+setup_kernel(const double *__restrict__ params, int P, int model, double dr_dex, SetRec *__restrict__ recs,
+             int *__restrict__ sys_counter, int2 *__restrict__ syslist, int sys_cap, double *__restrict__ rq_scratch,
+             int rq_cap, double *__restrict__ attrs)
+{
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    const double *p = params + (size_t)idx * RG_NPAR;
+    SetRec r;
+    memset(&r, 0, sizeof r);
+    r.dlog_r = 1 / dr_dex;
+    double log_rout = -1, r_hot_in = 0, r_warm_in = 0;
+    r.M = p[0];
+    r.mdot = pow(10.0, p[2]);
+    r.a = p[3];
+    r.cosinc = p[4];
+    r.inc = acos(p[4]);
+    if (model == RG_MODEL_RELAGN) {
+        r.kTe_h = p[5]; r.kTe_w = p[6]; r.gamma_h = p[7]; r.gamma_w = p[8];
+        r_hot_in = p[9]; r_warm_in = p[10]; log_rout = p[11];
+        r.r_h = r_hot_in; r.r_w = r_warm_in; r.r_out = pow(10.0, log_rout);
+        r.fcol = p[12]; r.hmax = p[13];
+    } else {
+        r.fcol = p[5];
+    }
+    int status = RG_S_OK;
+    if (!(r.a >= -0.998 && r.a <= 0.998)) status = RG_S_SPIN;
+    else if (!(r.cosinc <= 1 && r.cosinc >= 0.09)) status = RG_S_INC;
+    else if (model == RG_MODEL_RELQSO) {
+        double lmdot = log10(r.mdot);
+        if (!(lmdot >= -1.65 && lmdot <= 0.5)) status = RG_S_MDOT;
+    }
+    NtConst nt;
+    if (status == RG_S_OK) {
+        r.risco = rg_risco(r.a);
+        r.r_sg = 2150 * pow(r.M / 1e9, -2.0 / 9) * pow(r.mdot, 4.0 / 9) * pow(0.1, 2.0 / 9);
+        r.L_edd = 1.39e31 * r.M;
+        r.eta = 1 - sqrt(1 - 2 / (3 * r.risco));
+        r.Mdot_edd = r.L_edd / (r.eta * (RGK_C * RGK_C));
+        r.Rg = (RGK_GMSUN * r.M) / (RGK_C * RGK_C);
+        rg_nt_prepare(nt, r.a, r.risco, r.M, r.mdot, r.Mdot_edd, r.Rg);
+        if (model == RG_MODEL_RELAGN) {
+            if (log_rout < 0) r.r_out = r.r_sg;
+            if (r_warm_in == -1) r.r_w = r.risco;
+            if (r_hot_in == -1) r.r_h = r.risco;
+            if (!(r.r_w >= r.r_h)) { r.flags |= RG_F_RW_LT_RH; r.r_w = r.r_h; }
+            if (!(r.r_w <= r.r_out)) { r.flags |= RG_F_RW_GT_ROUT; r.r_w = r.r_out; }
+            if (!(r.r_h >= r.risco)) { r.flags |= RG_F_RH_LT_RISCO; r.r_h = r.risco; }
+            if (!(r.r_w >= r.risco)) { r.flags |= RG_F_RW_LT_RISCO; r.r_w = r.risco; }
+            if (!(r.hmax <= r.r_h)) { r.flags |= RG_F_HMAX_GT_RH; r.hmax = r.r_h; }
+        } else {
+            // relqso._set_rhot (relagn.py:1877-1898): fine grid built top-down from log r_sg
+            const double dlr = 1.0 / 1000;
+            double lg_in = log10(r.risco), lg_top = log10(r.r_sg);
+            double *sc = rq_scratch + idx; // [k][P] layout
+            int n = 1;
+            double t = lg_top;
+            sc[0] = t;
+            while (t > lg_in && n < rq_cap) {
+                t = t - dlr;
+                sc[(size_t)n * P] = t;
+                n++;
+            }
+            if (t > lg_in) status = RG_S_CAP;
+            else {
+                // ascending edge i -> chain index base - i
+                int base, n_edges;
+                if (t == lg_in) { base = n - 1; n_edges = n; }
+                else if (n > 1) { base = n - 2; n_edges = n - 1; sc[(size_t)base * P] = lg_in; }
+                else { base = 0; n_edges = 1; sc[0] = lg_in; }
+                double Ldiss = 0.0, rmid = 0.0; // the reference leaves rmid undefined if the loop never runs
+                double Rg2 = r.Rg * r.Rg, thresh = 0.02 * r.L_edd;
+                int i = 0;
+                double e0 = sc[(size_t)base * P];
+                while (Ldiss < thresh && i < n_edges - 1) {
+                    double e1 = sc[(size_t)(base - i - 1) * P];
+                    rmid = pow(10.0, e0 + dlr / 2);
+                    double dr = pow(10.0, e1) - pow(10.0, e0);
+                    Ldiss += RGK_SB * rg_tnt4(nt, rmid) * 4 * RGK_PI * rmid * dr * Rg2;
+                    e0 = e1;
+                    i++;
+                }
+                r.r_h = rmid;
+                r.r_w = 2 * r.r_h;
+                r.r_out = r.r_sg;
+                if (r.r_w > r.r_sg) r.r_w = r.r_sg;
+                r.kTe_h = 100; r.kTe_w = 0.2; r.gamma_w = 2.5;
+                r.hmax = 100.0 < r.r_h ? 100.0 : r.r_h;
+            }
+        }
+    }
+    if (status == RG_S_OK) {
+        r.lg_risco = log10(r.risco); r.lg_rh = log10(r.r_h); r.lg_rw = log10(r.r_w); r.lg_rout = log10(r.r_out);
+        r.Ldiss = ldiss_quad(r, nt);
+        r.Lseed = lseed_sum(r, nt);
+        if (model == RG_MODEL_RELQSO) r.gamma_h = (7.0 / 3) * pow(r.Ldiss / r.Lseed, -0.1);
+        r.n_disc = (r.r_w != r.r_out) ? rg_count_bins(r.lg_rw, r.lg_rout, r.dlog_r) : 0;
+        r.n_warm = (r.r_w != r.r_h) ? rg_count_bins(r.lg_rh, r.lg_rw, r.dlog_r) : 0;
+        r.n_hot = (r.r_h != r.risco) ? rg_count_bins(r.lg_risco, r.lg_rh, r.dlog_r) : 0;
+        if (r.r_h != r.risco) {
+            r.kTseed = seed_temp(r, nt);
+            if (r.kTseed < r.kTe_h) r.has_hotshape = 1;
+            else r.flags |= RG_F_HOT_SEED_GE_KTE;
+        }
+        int need_hot = (r.n_hot > 0 && r.has_hotshape) ? 1 : 0;
+        int nsys = r.n_warm + need_hot;
+        r.sys_base = 0;
+        if (nsys > 0) {
+            int base = atomicAdd(sys_counter, nsys);
+            r.sys_base = base;
+            if (base + nsys <= sys_cap) {
+                for (int s = 0; s < r.n_warm; s++) syslist[base + s] = make_int2(idx, s);
+                if (need_hot) syslist[base + r.n_warm] = make_int2(idx, -1);
+            } else status = RG_S_CAP;
+        }
+    }
+    r.status = status;
+    recs[idx] = r;
+    if (attrs) {
+        double *at = attrs + (size_t)idx * RG_NATTR;
+        at[RG_A_RISCO] = r.risco; at[RG_A_RSG] = r.r_sg; at[RG_A_ETA] = r.eta; at[RG_A_LEDD] = r.L_edd;
+        at[RG_A_MDOT_EDD] = r.Mdot_edd; at[RG_A_RG] = r.Rg; at[RG_A_RH] = r.r_h; at[RG_A_RW] = r.r_w;
+        at[RG_A_ROUT] = r.r_out; at[RG_A_HMAX] = r.hmax; at[RG_A_GAMMA_H] = r.gamma_h; at[RG_A_KTE_H] = r.kTe_h;
+        at[RG_A_KTE_W] = r.kTe_w; at[RG_A_GAMMA_W] = r.gamma_w; at[RG_A_KTSEED] = r.kTseed; at[RG_A_LDISS] = r.Ldiss;
+        at[RG_A_LSEED] = r.Lseed; at[RG_A_NDISC] = r.n_disc; at[RG_A_NWARM] = r.n_warm; at[RG_A_NHOT] = r.n_hot;
+        at[RG_A_FLAGS] = r.flags; at[RG_A_STATUS] = r.status; at[RG_A_MDOT] = r.mdot; at[RG_A_INC] = r.inc;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// nthcomp: one thread per system.
+//   scratch arrays gam, g, bet: [RG_NTH][n_sys_stride] (coalesced across a warp)
+//   sptot arena: [sys][RG_SPT_STRIDE];  header: [sys][4] = xmin, normfac, jmax, 0
+__global__ void __launch_bounds__(128)
+nthcomp_kernel(const SetRec *__restrict__ recs, const int2 *__restrict__ syslist, const int *__restrict__ sys_counter,
+               int sys_cap, const double *__restrict__ p10tab, double *__restrict__ sc_gam, double *__restrict__ sc_g,
+               double *__restrict__ sc_bet, size_t sc_stride, double *__restrict__ sptot, double *__restrict__ header)
+{
+    int sys = blockIdx.x * blockDim.x + threadIdx.x;
+    int nsys = *sys_counter;
+    if (nsys > sys_cap) nsys = sys_cap;
+    if (sys >= nsys) return;
+    int2 ent = syslist[sys];
+    const SetRec &r = recs[ent.x];
+    if (r.status != RG_S_OK) return;
+    double gamma, kte, ktbb;
+    if (ent.y < 0) { // hot shape: relagn.py:1200-1223
+        gamma = r.gamma_h; kte = r.kTe_h; ktbb = r.kTseed;
+    } else {         // warm annulus ent.y (counted top-down): relagn.py:900-927
+        NtConst nt;
+        rg_nt_prepare(nt, r.a, r.risco, r.M, r.mdot, r.Mdot_edd, r.Rg);
+        BinIter it;
+        it.start(r.lg_rh, r.lg_rw, r.dlog_r);
+        double lo = 0, hi = 0;
+        for (int s = 0; s <= ent.y; s++) it.next(lo, hi);
+        double rmid = pow(10.0, lo + r.dlog_r / 2);
+        double Tann = pow(rg_tnt4(nt, rmid), 0.25);
+        gamma = r.gamma_w; kte = r.kTe_w; ktbb = Tann / 1.16048e7;
+    }
+    // ---- _thcompton (pyNTHCOMP.py:80-173) ----
+    double tempbb = ktbb / 511.0, theta = kte / 511.0;
+    double tautom = sqrt(2.250 + 3.0 / (theta * ((gamma + .50) * (gamma + .50) - 2.250))) - 1.50;
+    const double delta = 0.02;
+    double deltal = delta * log(10.0);
+    double xmin = 1e-4 * tempbb, xmax = 40.0 * theta;
+    int jmax = (int)(log10(xmax / xmin) / delta) + 1;
+    if (jmax > 899) jmax = 899;
+    double *hd = header + (size_t)sys * 4;
+    double *spt = sptot + (size_t)sys * RG_SPT_STRIDE;
+    if (jmax < 4) { // degenerate grid: the reference would index out of range; flag as empty
+        hd[0] = xmin; hd[1] = 0.0; hd[2] = 0.0; hd[3] = 0.0;
+        return;
+    }
+    int jmaxth = (int)(log10(50 * tempbb / xmin) / delta);
+    if (jmaxth > 900) jmaxth = 900;
+    if (jmaxth > jmax) jmaxth = jmax;
+    double pt = RGK_PI * tempbb;
+    double planck = 15.0 / (pt * pt * pt * pt);
+    int jnr = (int)(log10(0.10 / xmin) / delta + 1);
+    if (jnr > jmax - 1) jnr = jmax - 1;
+    int jrel = (int)(log10(1 / xmin) / delta + 1);
+    if (jrel > jmax) jrel = jmax;
+    double xnr = xmin * p10tab[jnr - 1 > 0 ? jnr - 1 : 0];
+    double xr = xmin * p10tab[jrel - 1 > 0 ? jrel - 1 : 0];
+    double c20 = tautom / deltal;
+    double tod = theta / deltal;
+
+    // rolling values: x[j-1], x[j], x[j+1], c2[j-1], c2[j]
+    double xm = xmin * p10tab[0], x0 = xmin * p10tab[1], xp;
+    double x32 = sqrt(xm * x0);
+    double aa = (tod / x32 + 0.5) / (tod / x32 - 0.5);
+    double w1 = x32;
+    double c2m = (w1 * w1 * w1 * w1) / (1.0 + 4.60 * w1 + 1.1 * w1 * w1); // c2[0]
+    double gam_prev = 0, g_prev = 0;
+    // bet[0]
+    {
+        double w = xm, rel;
+        if (w <= 0.05) rel = (1.0 - 2.0 * w + 26.0 * w * w * 0.2);
+        else {
+            double z1 = (1.0 + w) / (w * w * w), z2 = 1.0 + 2.0 * w, z3 = log(z2), z4 = 2.0 * w * (1.0 + w) / z2;
+            double z5 = z3 / 2.0 / w, z6 = (1.0 + 3.0 * w) / z2 / z2;
+            rel = (0.75 * (z1 * (z4 - z3) + z5 - z6));
+        }
+        double b0;
+        if (0 < jnr - 1) b0 = 1.0 / tautom / (1.0 + tautom * rel / 3.0);
+        else if (0 < jrel) { double flz = 1 - (w - xnr) / (xr - xnr); b0 = 1.0 / tautom / (1.0 + tautom * rel / 3.0 * flz); }
+        else b0 = 1.0 / tautom;
+        sc_bet[sys] = b0; sc_gam[sys] = 0; sc_g[sys] = 0;
+    }
+    for (int j = 1; j < jmax - 1; j++) {
+        xp = xmin * p10tab[j + 1];
+        double w1j = sqrt(x0 * xp);
+        double c2j = (w1j * w1j * w1j * w1j) / (1.0 + 4.60 * w1j + 1.1 * w1j * w1j);
+        double w2j = sqrt(xm * x0);
+        // rel, bet at j
+        double w = x0, betj;
+        if (j >= jrel) betj = 1.0 / tautom;
+        else {
+            double rel;
+            if (w <= 0.05) rel = (1.0 - 2.0 * w + 26.0 * w * w * 0.2);
+            else {
+                double z1 = (1.0 + w) / (w * w * w), z2 = 1.0 + 2.0 * w, z3 = log(z2), z4 = 2.0 * w * (1.0 + w) / z2;
+                double z5 = z3 / 2.0 / w, z6 = (1.0 + 3.0 * w) / z2 / z2;
+                rel = (0.75 * (z1 * (z4 - z3) + z5 - z6));
+            }
+            double taukn = tautom * rel;
+            if (j < jnr - 1) betj = 1.0 / tautom / (1.0 + taukn / 3.0);
+            else { double flz = 1 - (w - xnr) / (xr - xnr); betj = 1.0 / tautom / (1.0 + taukn / 3.0 * flz); }
+        }
+        double dph = (j < jmaxth) ? planck * (x0 * x0) / (exp(x0 / tempbb) - 1) : 0.0;
+        // coefficients (pyNTHCOMP.py:210-221)
+        double aj = -c20 * c2j * (tod / w1j + 0.5);
+        double t1 = -c20 * c2j * (0.5 - tod / w1j);
+        double t2 = c20 * c2m * (tod / w2j + 0.5);
+        double t3 = (x0 * x0 * x0) * (tautom * betj);
+        double bj = t1 + t2 + t3;
+        double cj = c20 * c2m * (0.5 - tod / w2j);
+        double dj = x0 * dph;
+        // Thomas forward sweep (pyNTHCOMP.py:233-242)
+        double alp, gj;
+        if (j == 1) { alp = bj + cj * aa; gj = dj / alp; }
+        else { alp = bj - cj * gam_prev; gj = (dj - cj * g_prev) / alp; }
+        double gamj = aj / alp;
+        size_t o = (size_t)j * sc_stride + sys;
+        sc_gam[o] = gamj; sc_g[o] = gj; sc_bet[o] = betj;
+        gam_prev = gamj; g_prev = gj;
+        xm = x0; x0 = xp; c2m = c2j;
+    }
+    // back substitution (pyNTHCOMP.py:243-249) and sptot = dphesc x^2 (pyNTHCOMP.py:170-171)
+    double u_next = 0.0; // u[jmax-1]
+    double u1 = 0.0;
+    spt[jmax] = 0.0; spt[jmax - 1] = 0.0;
+    for (int jj = jmax - 2; jj >= 1; jj--) {
+        size_t o = (size_t)jj * sc_stride + sys;
+        double u = sc_g[o] - sc_gam[o] * u_next;
+        double x = xmin * p10tab[jj];
+        spt[jj] = (x * x * u * sc_bet[o] * tautom) * (x * x);
+        u_next = u;
+        if (jj == 1) u1 = u;
+    }
+    {
+        double u = aa * u1;
+        double x = xmin * p10tab[0];
+        spt[0] = (x * x * u * sc_bet[sys] * tautom) * (x * x);
+    }
+    // normalisation at 1 keV (pyNTHCOMP.py:49-56)
+    double xx = 1.0 / 511.0;
+    int ih = 1;
+    while (ih < jmax && xx > xmin * p10tab[ih]) ih++;
+    int il = ih - 1;
+    double xl = xmin * p10tab[il], xh = xmin * p10tab[ih];
+    double spp = spt[il] + (spt[ih] - spt[il]) * (xx - xl) / (xh - xl);
+    hd[0] = xmin; hd[1] = 1.0 / spp; hd[2] = (double)jmax; hd[3] = ktbb;
+}
+
+// ---------------------------------------------------------------------------
+int rg_launch_setup(const double *d_params, int P, int model, double dr_dex, SetRec *recs, int *sys_counter,
+                    int2 *syslist, int sys_cap, double *rq_scratch, int rq_cap, double *d_attrs, cudaStream_t st)
+{
+    RG_CUDA_OK(cudaMemsetAsync(sys_counter, 0, sizeof(int), st));
+    setup_kernel<<<(P + 127) / 128, 128, 0, st>>>(d_params, P, model, dr_dex, recs, sys_counter, syslist, sys_cap,
+                                                  rq_scratch, rq_cap, d_attrs);
+    RG_CUDA_OK(cudaGetLastError());
+    return RG_OK;
+}
+
+int rg_launch_nthcomp(const SetRec *recs, const int2 *syslist, const int *sys_counter, int sys_cap,
+                      const double *p10tab, double *sc_gam, double *sc_g, double *sc_bet, size_t sc_stride,
+                      double *sptot, double *header, cudaStream_t st)
+{
+    // sized for the capacity: threads beyond the device-side counter exit immediately
+    nthcomp_kernel<<<(sys_cap + 127) / 128, 128, 0, st>>>(recs, syslist, sys_counter, sys_cap, p10tab, sc_gam, sc_g,
+                                                          sc_bet, sc_stride, sptot, header);
+    RG_CUDA_OK(cudaGetLastError());
+    return RG_OK;
+}

@@ -1,0 +1,129 @@
+// rg_transfer.cuh -- device code of the relativistic transfer (the KYCONV-style
+// seam, relagn.py:979-1001): table lookup for one (spin, inclination), ring
+// evaluation and the g-shift histogram deposit.  Shared by the fused spectrum
+// kernel and the stand-alone kyconv entry point.
+//
+// Discretisation (identical to oracle/kerr_oracle.c):
+//   - an annulus [r1,r2] is cut into n_sub rings at log-midpoints r_m with exact
+//     area weights A_m = (r_b^2 - r_a^2)/2;
+//   - on ring m column t (disc azimuth) the tables give g and Jn = dalpha dbeta /
+//     (dX dY); they are blended linearly between the 4 surrounding (spin,
+//     inclination) nodes and the 2 surrounding table rows;
+//   - s_t = ln g_t / dlnE is the energy shift in bins, w_t = Jn_t g_t^3 the weight
+//     density; the segment t..t+1 carries W = (w_t + w_{t+1})/2 dphi A_m spread
+//     uniformly in s over [s_t, s_{t+1}] and is deposited on integer shifts with a
+//     linear (hat) kernel.
+#pragma once
+#include "rg_kernels.h"
+
+struct TabSel {
+    const float *n00, *n01, *n10, *n11; // node planes (g at +0, jn at +plane)
+    double w00, w01, w10, w11;
+    double risco, rh;  // of the model's own spin
+    size_t plane;
+    int NR, NPHI;
+    double inv_dl;
+};
+
+__device__ inline void rg_tab_select(TabSel &ts, const TabDesc &t, double a, double theta_o)
+{
+    int m0 = 0;
+    while (m0 + 2 < t.n_spin && a >= t.spins[m0 + 1]) m0++;
+    int m1 = m0 + 1 < t.n_spin ? m0 + 1 : m0;
+    double risco = rg_risco(a);
+    double fa = 0;
+    if (m1 != m0) {
+        fa = (t.riscos[m0] - risco) / (t.riscos[m0] - t.riscos[m1]);
+        fa = fa < 0 ? 0 : (fa > 1 ? 1 : fa);
+    }
+    int n0 = 0;
+    while (n0 + 2 < t.n_inc && theta_o >= t.thetas[n0 + 1]) n0++;
+    int n1 = n0 + 1 < t.n_inc ? n0 + 1 : n0;
+    double fi = 0;
+    if (n1 != n0) {
+        fi = (theta_o - t.thetas[n0]) / (t.thetas[n1] - t.thetas[n0]);
+        fi = fi < 0 ? 0 : (fi > 1 ? 1 : fi);
+    }
+    size_t plane = (size_t)t.NR * t.NPHI;
+    ts.n00 = t.data + ((size_t)m0 * t.n_inc + n0) * 2 * plane;
+    ts.n01 = t.data + ((size_t)m0 * t.n_inc + n1) * 2 * plane;
+    ts.n10 = t.data + ((size_t)m1 * t.n_inc + n0) * 2 * plane;
+    ts.n11 = t.data + ((size_t)m1 * t.n_inc + n1) * 2 * plane;
+    ts.w00 = (1 - fa) * (1 - fi); ts.w01 = (1 - fa) * fi; ts.w10 = fa * (1 - fi); ts.w11 = fa * fi;
+    ts.risco = risco; ts.rh = 1 + sqrt(1 - a * a);
+    ts.plane = plane; ts.NR = t.NR; ts.NPHI = t.NPHI; ts.inv_dl = 1.0 / t.dl;
+}
+
+struct RingRow { int s0, s1; double fr; };
+
+__device__ inline RingRow rg_ring_row(const TabSel &ts, double rm)
+{
+    RingRow rr;
+    double ell = log10((rm - ts.rh) / (ts.risco - ts.rh)) * ts.inv_dl;
+    if (!(rm > ts.rh)) ell = 0;
+    if (ell < 0) ell = 0;
+    if (ell > ts.NR - 1) ell = ts.NR - 1;
+    int s0 = (int)floor(ell);
+    if (s0 > ts.NR - 2) s0 = ts.NR - 2;
+    if (s0 < 0) s0 = 0;
+    rr.s0 = s0; rr.s1 = s0 + 1 < ts.NR ? s0 + 1 : s0; rr.fr = ell - s0;
+    return rr;
+}
+
+// g and Jn at column p of the ring (blend of 4 nodes x 2 rows)
+__device__ inline void rg_ring_sample(const TabSel &ts, const RingRow &rr, int p, double &g, double &jn)
+{
+    size_t i0 = (size_t)rr.s0 * ts.NPHI + p, i1 = (size_t)rr.s1 * ts.NPHI + p;
+    double g0 = ts.w00 * __ldg(ts.n00 + i0) + ts.w01 * __ldg(ts.n01 + i0) + ts.w10 * __ldg(ts.n10 + i0) +
+                ts.w11 * __ldg(ts.n11 + i0);
+    double g1 = ts.w00 * __ldg(ts.n00 + i1) + ts.w01 * __ldg(ts.n01 + i1) + ts.w10 * __ldg(ts.n10 + i1) +
+                ts.w11 * __ldg(ts.n11 + i1);
+    size_t q0 = ts.plane + i0, q1 = ts.plane + i1;
+    double j0 = ts.w00 * __ldg(ts.n00 + q0) + ts.w01 * __ldg(ts.n01 + q0) + ts.w10 * __ldg(ts.n10 + q0) +
+                ts.w11 * __ldg(ts.n11 + q0);
+    double j1 = ts.w00 * __ldg(ts.n00 + q1) + ts.w01 * __ldg(ts.n01 + q1) + ts.w10 * __ldg(ts.n10 + q1) +
+                ts.w11 * __ldg(ts.n11 + q1);
+    g = g0 + rr.fr * (g1 - g0);
+    jn = j0 + rr.fr * (j1 - j0);
+}
+
+__device__ inline int rg_auto_nsub(double lnr, double dlnE)
+{
+    int nsub = 1 + (int)floor(0.5 * lnr / dlnE);
+    return nsub > 4096 ? 4096 : nsub;
+}
+
+// overlap of [lo,hi] with [L,R] weighted by the hat (1+y on [-1,0], 1-y on [0,1])
+__device__ inline double rg_hat_piece(double lo, double hi, double L, double R, bool neg)
+{
+    double l = lo > L ? lo : L, r = hi < R ? hi : R;
+    if (r <= l) return 0.0;
+    double mid = 0.5 * (l + r);
+    return (r - l) * (neg ? 1.0 + mid : 1.0 - mid);
+}
+
+// deposit weight W spread uniformly over [sa,sb] onto H[k - K_LO] (shared-memory
+// histogram, atomics).  nH = capacity.
+__device__ inline void rg_deposit(double *H, int K_LO, int nH, double sa, double sb, double W)
+{
+    double lo = sa < sb ? sa : sb, hi = sa < sb ? sb : sa;
+    double len = hi - lo;
+    if (len < 1e-12) {
+        double mid = 0.5 * (lo + hi);
+        double kf = floor(mid);
+        double f = mid - kf;
+        int i0 = (int)kf - K_LO;
+        if (i0 >= 0 && i0 + 1 < nH) {
+            atomicAdd(&H[i0], W * (1 - f));
+            atomicAdd(&H[i0 + 1], W * f);
+        }
+        return;
+    }
+    int kfirst = (int)floor(lo), klast = (int)floor(hi) + 1;
+    double inv = W / len;
+    for (int k = kfirst; k <= klast; k++) {
+        double c = rg_hat_piece(lo - k, hi - k, -1.0, 0.0, true) + rg_hat_piece(lo - k, hi - k, 0.0, 1.0, false);
+        int i = k - K_LO;
+        if (c != 0.0 && i >= 0 && i < nH) atomicAdd(&H[i], inv * c);
+    }
+}

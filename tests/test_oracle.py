@@ -1,0 +1,117 @@
+"""The CPU oracle (oracle/) against the golden fixtures generated from the
+UNMODIFIED reference (tests/golden/make_golden.py) and the reference's only
+published known answer (examples/relqso_modSpec.ipynb:81-83)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def relerr(a, b):
+    a = np.asarray(a, float)
+    b = np.asarray(b, float)
+    scale = np.maximum(np.abs(b), 1e-300)
+    m = (b != 0) | (a != 0)
+    if not m.any():
+        return 0.0
+    return float(np.max(np.abs(a - b)[m] / scale[m]))
+
+
+def peak_relerr(a, b, floor=1e-12):
+    """max |a-b| / max(|b|, floor*peak): the far Wien tail (1e-200 of the peak) is excluded."""
+    a = np.asarray(a, float)
+    b = np.asarray(b, float)
+    pk = np.max(np.abs(b))
+    if pk == 0:
+        return float(np.max(np.abs(a)))
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor * pk)))
+
+
+def test_notebook_known_answer():
+    # examples/relqso_modSpec.ipynb:81-83
+    st, at = O.setup([1e5, 1, -1, 0, 0.5, 1, 0], model=1)
+    assert st == 0
+    assert at["gamma_h"] == pytest.approx(1.9803689563797076, rel=1e-12)
+    assert at["r_h"] == 14.261351436104999
+    assert at["r_w"] == 28.522702872209997
+
+
+def test_analytic_kats():
+    L = O.lib()
+    assert L.ro_risco(0.0) == 6.0
+    assert L.ro_risco(0.998) == pytest.approx(1.236971, abs=1e-6)
+    st, at = O.setup([1e8, 100, -1, 0, 0.5, 100, 0.2, 1.7, 2.7, 10, 20, -1, 1, 10, 0])
+    assert at["eta"] == pytest.approx(1 - np.sqrt(8.0 / 9.0), rel=1e-14)
+    assert at["r_sg"] == pytest.approx(772.6699377179948, rel=1e-13)
+    assert (at["n_disc"], at["n_warm"], at["n_hot"]) == (79, 15, 11)
+
+
+@pytest.mark.parametrize("tag,model", [("relagn", 0), ("relqso", 1)])
+def test_attrs_and_nonrel_spectra(tag, model):
+    d = np.load(os.path.join(G, "golden_nonrel.npz"))
+    names = list(d["attr_names"])
+    for i, name in enumerate(d[tag + "_names"]):
+        pars = d[tag + "_params"][i]
+        for grid, key in ((d["grid1000"], "_spec1000"), (d["grid_def"], "_specdef")):
+            st, out, at = O.evaluate(pars, grid, model=model, rel=False)
+            assert st == 0
+            gold = d[tag + key][i]
+            for c in range(4):
+                assert peak_relerr(out[c], gold[c]) < 1e-9, (tag, name, key, c)
+        for k, nm in enumerate(names):
+            assert at[nm] == pytest.approx(d[tag + "_attrs"][i][k], rel=1e-11, abs=0), (name, nm)
+        ex = d[tag + "_extra"][i]
+        assert at["Ldiss"] == pytest.approx(ex[0], rel=1e-7)
+        assert at["Lseed"] == pytest.approx(ex[1], rel=1e-11)
+        nb = ex[2:].astype(int)  # edge counts of the reference's three bin arrays
+        has = [at["n_disc"], at["n_warm"], at["n_hot"]]
+        for n_edges, n_ann in zip(nb, has):
+            assert n_ann in (n_edges - 1, 0)
+
+
+def test_nthcomp_golden():
+    d = np.load(os.path.join(G, "golden_nthcomp.npz"))
+    for i, (g, kte, kbb) in enumerate(d["par"]):
+        for eg, key in ((d["egrid_def"], "out_def"), (d["egrid_1000"], "out_1000")):
+            got = O.donthcomp(eg, g, kte, kbb)
+            assert peak_relerr(got, d[key][i]) < 1e-9, (i, key)
+
+
+def test_rel_golden_reference_driver():
+    """reference driver (unmodified relagn.py do_rel*Spec) + oracle kyconv at the seam vs the
+    oracle's own whole-path evaluation: pins pack/unpack, the 10^3 Rg switch and the region sums."""
+    d = np.load(os.path.join(G, "golden_rel.npz"))
+    tab = O.Tables(d["tab_spins"], d["tab_thetas"], int(d["tab_NR"]), int(d["tab_NPHI"]), float(d["tab_dl"]),
+                   data=d["tab_data"])
+    for tag, model in (("relagn", 0), ("relqso", 1)):
+        for i, name in enumerate(d[tag + "_names"]):
+            st, out, at = O.evaluate(d[tag + "_params"][i], d["grid1000"], model=model, rel=True, tab=tab)
+            assert st == 0
+            gold = d[tag + "_spec1000"][i]
+            for c in range(4):
+                assert peak_relerr(out[c], gold[c]) < 1e-9, (tag, name, c)
+
+
+def test_kyconv_flat_limit_and_additivity():
+    d = np.load(os.path.join(G, "golden_rel.npz"))
+    tab = O.Tables(d["tab_spins"], d["tab_thetas"], int(d["tab_NR"]), int(d["tab_NPHI"]), float(d["tab_dl"]),
+                   data=d["tab_data"])
+    dlnE = np.log(1e7) / 1000
+    th = np.deg2rad(60.0)
+    # flat-space limit (relagn.py:968-969, 1010-1013): sum H -> pi (r2^2 - r1^2) cos i at large r
+    k0, H = O.ky_kernel(tab, 0.0, th, 900.0, 950.0, dlnE)
+    assert H.sum() == pytest.approx(np.pi * (950.0 ** 2 - 900.0 ** 2) * np.cos(th), rel=2e-2)
+    # additivity over annuli (tests/blurr_test.py:77-139): sum of annulus kernels == whole-disc kernel
+    edges = np.geomspace(6.0, 100.0, 41)
+    kw, Hw = O.ky_kernel(tab, 0.0, th, 6.0, 100.0, dlnE, nsub=40 * 4)
+    acc = np.zeros(4096)
+    for r1, r2 in zip(edges[:-1], edges[1:]):
+        k, Hh = O.ky_kernel(tab, 0.0, th, r1, r2, dlnE, nsub=4)
+        acc[k + 2048:k + 2048 + Hh.size] += Hh
+    whole = np.zeros(4096)
+    whole[kw + 2048:kw + 2048 + Hw.size] = Hw
+    assert np.max(np.abs(acc - whole)) < 1e-9 * whole.max()
