@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py -- RELAGN spectra/sec (1000-bin grid, batched params) on N B200s, next to the host-CPU path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm (CUDA, sm_100a)
+    python bench.py --impl reference [--gpus N] [--steps K] ...   # CPU arm: the reference path on host cores
+    (N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...)
+
+Workload (SURVEY 8d, C4 = BASELINE.json configs[3]): RELAGN full model, independent random parameters inside the
+XSPEC hard limits (lmod_relagn.dat), relativistic transfer on, 1000-bin grid geomspace(1e-4, 1e3, 1001);
+125 000 parameter sets per GPU per step (the 1e6-set MCMC batch sharded over 8 GPUs -> weak scaling).
+One step = every rank evaluates its shard (+ for N > 1 the final NCCL gather of the spectra to rank 0).
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definition of every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "RELAGN spectra/sec (1000-bin grid, batched params)"
+UNIT = "spectra/s"
+NE = 1000
+SETS_PER_GPU = 125000
+SEED = 20240229
+
+# fixed constants of the algorithmic flop count F_alg
+C_BB, C_K, C_I, C_NT = 25.0, 60.0, 10.0, 150.0
+
+
+def ebins():
+    return np.geomspace(1e-4, 1e3, NE + 1)
+
+
+def c4_params(P, seed):
+    from relagn_b200.host import risco
+    rng = np.random.Generator(np.random.PCG64(seed))
+    M = 10 ** rng.uniform(5, 10, P)
+    lm = rng.uniform(-1.5, 0.3, P)
+    a = rng.uniform(0, 0.998, P)
+    ci = rng.uniform(0.09, 0.998, P)
+    kth = rng.uniform(10, 300, P)
+    ktw = rng.uniform(0.1, 1, P)
+    gh = rng.uniform(1.3, 3, P)
+    gw = rng.uniform(2, 5, P)
+    rh = risco(a) + rng.uniform(0.5, 100, P)
+    rw = rh * (1 + rng.uniform(0, 4, P))
+    hm = np.minimum(10.0, rh)
+    p = np.stack([M, np.full(P, 100.0), lm, a, ci, kth, ktw, gh, gw, rh, rw, np.full(P, -1.0), np.ones(P), hm,
+                  np.zeros(P)], axis=1)
+    return np.ascontiguousarray(p)
+
+
+def workload_config(n_gpus, sets_per_gpu, tables):
+    return {"workload": "C4: RELAGN full model, random spin/inclination/corona parameters (lmod_relagn.dat limits), "
+                        "rel=True, total SED; %d sets per GPU per step (1e6-set MCMC batch sharded over 8 GPUs)"
+                        % sets_per_gpu,
+            "nE": NE, "ebins": "geomspace(1e-4,1e3,1001) keV", "sets_per_gpu": sets_per_gpu,
+            "global_sets": sets_per_gpu * n_gpus, "dr_dex": 50, "kerr_tables": tables,
+            "parallelism": "dp%d (independent parameter sets; final NCCL gather to rank 0)" % n_gpus,
+            "l2_policy": "each step writes %.2f GB of spectra per GPU (>> 126 MB L2); inputs are 15 MB of parameters"
+                         % (sets_per_gpu * NE * 8 / 1e9)}
+
+
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw = [], [], []
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------
+def oracle_tables(tables):
+    from oracle import oracle as O
+    return O.Tables(tables["spins"], tables["thetas"], tables["NR"], tables["NPHI"], tables["dl"], data=tables["data"])
+
+
+def cpu_arm(params, tables, seconds_target, threads):
+    """The reference path on the host cores: oracle/ (C restatement of relagn.py + pyNTHCOMP.py + the kyconv
+    seam), all threads, on a bounded sample of the same workload."""
+    from oracle import oracle as O
+    otab = oracle_tables(tables)
+    eb = ebins()
+    n0 = min(64 * max(threads, 1), params.shape[0])
+    t0 = time.perf_counter()
+    O.evaluate_batch(params[:n0], eb, model=0, rel=True, tab=otab, threads=threads)
+    dt = time.perf_counter() - t0
+    rate0 = n0 / dt
+    n = int(min(params.shape[0], max(n0, rate0 * seconds_target)))
+    t0 = time.perf_counter()
+    st, out, at = O.evaluate_batch(params[:n], eb, model=0, rel=True, tab=otab, threads=threads)
+    dt = time.perf_counter() - t0
+    return n / dt, n, dt
+
+
+def get_tables(kind, ctx=None):
+    """Kerr transfer tables as a host dict.  'default': ray-traced by the product on the device (cached);
+    'golden': the small fixture of tests/golden (3 spins x 4 inclinations)."""
+    if kind == "golden":
+        d = np.load(os.path.join(ROOT, "tests", "golden", "golden_rel.npz"))
+        return dict(spins=d["tab_spins"], thetas=d["tab_thetas"], NR=int(d["tab_NR"]), NPHI=int(d["tab_NPHI"]),
+                    dl=float(d["tab_dl"]), data=d["tab_data"])
+    from relagn_b200 import tables as T
+    T.load_default(ctx)
+    cfg = dict(T.DEFAULT)
+    cfg["data"] = ctx.tables_download()
+    return cfg
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    if args.tables == "golden":
+        tables = get_tables("golden")
+    else:
+        # the CPU arm needs the same tables as the GPU arm; they are produced by the product's ray tracer
+        import torch
+        if torch.cuda.is_available():
+            from relagn_b200 import _capi
+            ctx = _capi.Context(0)
+            tables = get_tables("default", ctx)
+            ctx.close()
+        else:
+            tables = get_tables("golden")
+            args.tables = "golden"
+    P = args.sets
+    params = c4_params(P, SEED)
+    # each step: a bounded sample of the workload (~10 s of CPU work at full thread count)
+    rates, n_used = [], 0
+    for i in range(args.warmup + args.steps):
+        rate, n, dt = cpu_arm(params, tables, args.cpu_seconds, threads)
+        if i >= args.warmup:
+            rates.append((n, dt))
+        n_used = n
+    tot_n = sum(n for n, _ in rates)
+    tot_t = sum(t for _, t in rates)
+    value = tot_n / tot_t
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(args.steps, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.gpus, args.sets, args.tables),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": "%d of the %d C4 sets per step, %d host threads (oracle/: C restatement of "
+                                       "relagn.py + pyNTHCOMP.py + kyconv seam; the Python reference cannot run "
+                                       "its relativistic path without HEASOFT)" % (n_used, P, threads)},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from relagn_b200 import _capi
+    from relagn_b200.batch import BatchEvaluator
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; relagn_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    P = args.sets
+    eb = ebins()
+    tables_arg = get_tables("golden") if args.tables == "golden" else None
+    ev = BatchEvaluator(eb, model="relagn", device=local, tables=tables_arg)
+    ev.ensure_tables()
+    params_np = c4_params(P, SEED + rank)
+    params = torch.from_numpy(params_np).to(dev)
+    out = torch.empty((P, NE), dtype=torch.float64, device=dev)
+    attrs = torch.empty((P, _capi.NATTR), dtype=torch.float64, device=dev)
+    gathered = None
+    if world > 1 and rank == 0:
+        gathered = [torch.empty((P, NE), dtype=torch.float64, device=dev) for _ in range(world)]
+
+    def step():
+        ev.evaluate_device(params, rel=True, out=out, attrs=attrs)
+        if world > 1:
+            dist.gather(out, gathered, dst=0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches0 = ev.ctx.launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ev.ctx.launch_count() - launches0
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = P * world * args.steps / (ms_max * 1e-3)
+
+    # ---- e2e: host buffers through the public API, H2D + D2H inside the timed region ----
+    e2e_steps = max(1, min(args.steps, 3))
+    ev.evaluate(params_np[:1024], rel=True)  # staging buffers / warm-up
+    ev.evaluate(params_np, rel=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        o_host, _a = ev.evaluate(params_np, rel=True)
+        chk = float(o_host[0, NE // 2])
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    e2e_value = P * world * e2e_steps / float(tt.item())
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(P * 15 * 8),
+           "d2h_bytes_per_step": int(P * NE * 8 + P * 24 * 8), "steps": e2e_steps,
+           "api": "relagn_b200.BatchEvaluator.evaluate (rg_eval_batch_host; pinned host in/out)"}
+
+    # ---- roofline of the dominant kernel (spectrum_kernel), measured live with CUDA events ----
+    roofline, fp64, kernels = None, None, None
+    if rank == 0:
+        ev.ctx.set_profile(True)
+        ev.ctx.reset_stats()
+        ev.evaluate_device(params, rel=True, out=out, attrs=attrs)
+        torch.cuda.synchronize()
+        s = ev.ctx.stats()
+        ev.ctx.set_profile(False)
+        at = attrs.cpu().numpy()
+        A = _capi.A
+        ok = at[:, A["status"]] == 0
+        Nd, Nw, Nh = at[ok, A["n_disc"]].sum(), at[ok, A["n_warm"]].sum(), at[ok, A["n_hot"]].sum()
+        n_sys, sum_j, sum_W = s["n_sys"], s["sum_jmax"], s["sum_W"]
+        # F_alg = Nd nE c_bb + sum_sys (jmax c_k + nE c_i) + Nh nE 2 + sum_conv 2 nE W + N_nt c_nt
+        n_seed = Nd + Nw  # seed-photon annuli r_h..r_out (Lseed_hotCorona)
+        flops = (Nd * NE * C_BB + sum_j * C_K + n_sys * NE * C_I + Nh * NE * 2 + 2.0 * NE * sum_W +
+                 (Nd + Nw + Nh + n_seed) * C_NT)
+        bytes_alg = P * (8.0 * 15 + 8.0 * NE)
+        ms_spec = s["ms_spectrum"]
+        n_launch = max(s["n_spectrum"], 1.0)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        fp64_peak = ev.ctx.measure_fp64_peak()
+        ach_gbs = bytes_alg / (ms_spec * 1e-3) / 1e9
+        roofline = {"kernel": "spectrum_kernel<4>", "bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak,
+                    "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+                    "traffic": None,
+                    "bytes_per_launch": bytes_alg / n_launch, "launches_per_step": n_launch,
+                    "avg_launch_ms": ms_spec / n_launch,
+                    "note": "the path is FP64-pipe bound, not HBM bound (SURVEY 8d): see fp64_roofline"}
+        # flops of the spectrum kernel alone: everything but the Kompaneets solves (nthcomp_kernel) and setup
+        flops_spec = flops - sum_j * C_K
+        fp64 = {"kernel": "spectrum_kernel<4>", "achieved": flops_spec / (ms_spec * 1e-3) / 1e12, "peak": fp64_peak,
+                "unit": "TFLOP/s", "frac": flops_spec / (ms_spec * 1e-3) / 1e12 / fp64_peak if fp64_peak else None,
+                "peak_source": "rg_measure_fp64_peak (FMA micro-benchmark, this run)",
+                "flops_alg_per_spectrum": flops / P, "mean_W_ann": sum_W / max(s["n_conv_ann"], 1.0),
+                "mean_annuli": float((Nd + Nw + Nh) / max(ok.sum(), 1)), "mean_jmax": sum_j / max(n_sys, 1.0)}
+        tot_ms = s["ms_setup"] + s["ms_nthcomp"] + s["ms_spectrum"]
+        kernels = {"setup_kernel_ms": s["ms_setup"], "nthcomp_kernel_ms": s["ms_nthcomp"],
+                   "spectrum_kernel_ms": s["ms_spectrum"], "spectrum_share": s["ms_spectrum"] / tot_ms if tot_ms else None}
+
+    # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        tables = tables_arg if tables_arg is not None else get_tables("default", ev.ctx)
+        rate, n, dtc = cpu_arm(params_np, tables, args.cpu_seconds, threads)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "%d of the %d C4 sets, %.1f s, %d host threads (oracle/: C restatement of the reference "
+                         "Python path + kyconv seam on the same Kerr tables)" % (n, P, dtc, threads)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(world, P, args.tables), "clocks": clocks, "e2e": e2e,
+                "gpu_launches": int(launches), "roofline": roofline, "fp64_roofline": fp64, "kernels": kernels,
+                "cpu_baseline": cpu, "checksum": chk}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--sets", type=int, default=SETS_PER_GPU, help="parameter sets per GPU per step")
+    ap.add_argument("--tables", default="default", choices=["default", "golden"])
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU work per cpu_baseline sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -146,6 +146,27 @@ int rg_eval_batch_host(rg_ctx *ctx, const double *params_host, int P, int model,
 /* number of kernels launched by this context so far (for accounting) */
 long rg_launch_count(rg_ctx *ctx);
 
+/* ---- instrumentation (bench.py's roofline block) ----
+ * rg_set_option(RG_OPT_PROFILE, 1): bracket every kernel of rg_eval_batch with
+ * CUDA events on the caller's stream and count algorithmic work on the device.
+ * rg_get_stat synchronises the recorded events and returns totals accumulated
+ * since the last rg_reset_stats. */
+#define RG_OPT_PROFILE 1
+#define RG_STAT_MS_SETUP 1      /* summed kernel time, ms */
+#define RG_STAT_MS_NTHCOMP 2
+#define RG_STAT_MS_SPECTRUM 3
+#define RG_STAT_N_SETUP 4       /* launches */
+#define RG_STAT_N_NTHCOMP 5
+#define RG_STAT_N_SPECTRUM 6
+#define RG_STAT_SUM_W 7         /* sum over transfer-convolved annuli of the shift-histogram width W_ann */
+#define RG_STAT_N_CONV_ANN 8    /* annuli that went through the transfer convolution */
+#define RG_STAT_SUM_JMAX 9      /* sum over Kompaneets systems of jmax */
+#define RG_STAT_N_SYS 10        /* Kompaneets systems solved */
+#define RG_STAT_N_SETS 11       /* parameter sets evaluated */
+int rg_set_option(rg_ctx *ctx, int key, double value);
+int rg_get_stat(rg_ctx *ctx, int key, double *value);
+int rg_reset_stats(rg_ctx *ctx);
+
 /* measured FP64 FMA throughput of the device in TFLOP/s (micro-benchmark,
  * used as the roofline denominator of the FP64-bound kernels) */
 int rg_measure_fp64_peak(rg_ctx *ctx, double *tflops);

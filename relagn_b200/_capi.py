@@ -1,0 +1,239 @@
+"""ctypes binding of the C ABI declared in include/relagn_b200.h.
+
+The shipped library is relagn_b200/_build/librelagn_b200.so (nvcc, sm_100a).
+There is no CPU implementation behind this module: if the library is missing
+or no CUDA device is usable the calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_build", "librelagn_b200.so")
+
+NPAR = 15
+NATTR = 24
+ATTR_NAMES = ["risco", "r_sg", "eta", "L_edd", "Mdot_edd", "Rg", "r_h", "r_w", "r_out", "hmax", "gamma_h", "kTe_h",
+              "kTe_w", "gamma_w", "kT_seed", "Ldiss", "Lseed", "n_disc", "n_warm", "n_hot", "flags", "status", "mdot",
+              "inc"]
+A = {n: i for i, n in enumerate(ATTR_NAMES)}
+
+MODEL_RELAGN, MODEL_RELQSO = 0, 1
+FLAG_REL, FLAG_COMPONENTS = 1, 2
+S_OK, S_SPIN, S_INC, S_MDOT, S_CAP = 0, 1, 2, 3, 4
+F_RW_LT_RH, F_RW_GT_ROUT, F_RH_LT_RISCO, F_RW_LT_RISCO, F_HMAX_GT_RH, F_HOT_SEED_GE_KTE = 1, 2, 4, 8, 16, 32
+
+# every symbol include/relagn_b200.h declares (checked by tests/test_abi.py)
+SYMBOLS = ["rg_version", "rg_last_error", "rg_ctx_create", "rg_ctx_destroy", "rg_set_grid", "rg_tables_generate",
+           "rg_tables_upload", "rg_tables_download", "rg_tables_info", "rg_kyconv", "rg_ky_kernel", "rg_eval_batch",
+           "rg_eval_batch_host", "rg_launch_count", "rg_measure_fp64_peak", "rg_set_option", "rg_get_stat",
+           "rg_reset_stats"]
+
+OPT_PROFILE = 1
+STATS = {"ms_setup": 1, "ms_nthcomp": 2, "ms_spectrum": 3, "n_setup": 4, "n_nthcomp": 5, "n_spectrum": 6, "sum_W": 7,
+         "n_conv_ann": 8, "sum_jmax": 9, "n_sys": 10, "n_sets": 11}
+
+_dp = C.POINTER(C.c_double)
+_fp = C.POINTER(C.c_float)
+_ip = C.POINTER(C.c_int)
+
+
+class RelagnError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("relagn_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+def bind(lib):
+    """Attach argtypes/restypes to a loaded CDLL."""
+    lib.rg_version.restype = C.c_int
+    lib.rg_version.argtypes = []
+    lib.rg_last_error.restype = C.c_char_p
+    lib.rg_last_error.argtypes = []
+    lib.rg_ctx_create.restype = C.c_int
+    lib.rg_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    lib.rg_ctx_destroy.restype = None
+    lib.rg_ctx_destroy.argtypes = [C.c_void_p]
+    lib.rg_set_grid.restype = C.c_int
+    lib.rg_set_grid.argtypes = [C.c_void_p, _dp, C.c_int]
+    lib.rg_tables_generate.restype = C.c_int
+    lib.rg_tables_generate.argtypes = [C.c_void_p, _dp, C.c_int, _dp, C.c_int, C.c_int, C.c_int, C.c_double,
+                                       C.POINTER(C.c_long)]
+    lib.rg_tables_upload.restype = C.c_int
+    lib.rg_tables_upload.argtypes = [C.c_void_p, _dp, C.c_int, _dp, C.c_int, C.c_int, C.c_int, C.c_double, _fp]
+    lib.rg_tables_download.restype = C.c_int
+    lib.rg_tables_download.argtypes = [C.c_void_p, _fp, C.c_size_t]
+    lib.rg_tables_info.restype = C.c_int
+    lib.rg_tables_info.argtypes = [C.c_void_p, _ip, _ip, _ip, _ip, _dp, C.POINTER(C.c_size_t)]
+    lib.rg_kyconv.restype = C.c_int
+    lib.rg_kyconv.argtypes = [C.c_void_p, _dp, C.c_int, _dp, _dp]
+    lib.rg_ky_kernel.restype = C.c_int
+    lib.rg_ky_kernel.argtypes = [C.c_void_p] + [C.c_double] * 9 + [_dp, C.c_int, _ip, _ip]
+    lib.rg_eval_batch.restype = C.c_int
+    lib.rg_eval_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_uint, C.c_void_p,
+                                  C.c_void_p, C.c_void_p]
+    lib.rg_eval_batch_host.restype = C.c_int
+    lib.rg_eval_batch_host.argtypes = [C.c_void_p, _dp, C.c_int, C.c_int, C.c_double, C.c_uint, _dp, _dp]
+    lib.rg_launch_count.restype = C.c_long
+    lib.rg_launch_count.argtypes = [C.c_void_p]
+    lib.rg_measure_fp64_peak.restype = C.c_int
+    lib.rg_measure_fp64_peak.argtypes = [C.c_void_p, _dp]
+    lib.rg_set_option.restype = C.c_int
+    lib.rg_set_option.argtypes = [C.c_void_p, C.c_int, C.c_double]
+    lib.rg_get_stat.restype = C.c_int
+    lib.rg_get_stat.argtypes = [C.c_void_p, C.c_int, _dp]
+    lib.rg_reset_stats.restype = C.c_int
+    lib.rg_reset_stats.argtypes = [C.c_void_p]
+    return lib
+
+
+_lib = None
+
+
+def load():
+    """Load the sm_100a library.  Raises if it has not been built (python -m relagn_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RelagnError(-1, "CUDA library %s not built (run `python -m relagn_b200.build`); "
+                                  "relagn_b200 has no CPU fallback" % LIB_PATH)
+        _lib = bind(C.CDLL(LIB_PATH))
+    return _lib
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+class Context:
+    """One device context (rg_ctx).  `lib` is only overridden by the test-only host simulation."""
+
+    def __init__(self, device=-1, lib=None):
+        self.lib = lib if lib is not None else load()
+        h = C.c_void_p()
+        self._check(self.lib.rg_ctx_create(int(device), C.byref(h)))
+        self.h = h
+        self.nE = 0
+        self.ebins = None
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RelagnError(rc, self.lib.rg_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.rg_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- grid ----
+    def set_grid(self, ebins):
+        eb = np.ascontiguousarray(ebins, dtype=np.float64)
+        self._check(self.lib.rg_set_grid(self.h, _d(eb), eb.size - 1))
+        self.nE = eb.size - 1
+        self.ebins = eb.copy()
+
+    # ---- tables ----
+    def tables_upload(self, spins, thetas, NR, NPHI, dl, data):
+        sp = np.ascontiguousarray(spins, dtype=np.float64)
+        th = np.ascontiguousarray(thetas, dtype=np.float64)
+        dat = np.ascontiguousarray(data, dtype=np.float32)
+        assert dat.size == sp.size * th.size * 2 * NR * NPHI
+        self._check(self.lib.rg_tables_upload(self.h, _d(sp), sp.size, _d(th), th.size, int(NR), int(NPHI), float(dl),
+                                              dat.ctypes.data_as(_fp)))
+
+    def tables_generate(self, spins, thetas, NR, NPHI, dl):
+        sp = np.ascontiguousarray(spins, dtype=np.float64)
+        th = np.ascontiguousarray(thetas, dtype=np.float64)
+        bad = C.c_long(0)
+        self._check(self.lib.rg_tables_generate(self.h, _d(sp), sp.size, _d(th), th.size, int(NR), int(NPHI),
+                                                float(dl), C.byref(bad)))
+        return bad.value
+
+    def tables_info(self):
+        ns, ni, nr, nphi = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        dl = C.c_double()
+        nf = C.c_size_t()
+        self._check(self.lib.rg_tables_info(self.h, C.byref(ns), C.byref(ni), C.byref(nr), C.byref(nphi), C.byref(dl),
+                                            C.byref(nf)))
+        return dict(n_spin=ns.value, n_inc=ni.value, NR=nr.value, NPHI=nphi.value, dl=dl.value, n_floats=nf.value)
+
+    def tables_download(self):
+        info = self.tables_info()
+        out = np.zeros(info["n_floats"], dtype=np.float32)
+        self._check(self.lib.rg_tables_download(self.h, out.ctypes.data_as(_fp), out.size))
+        return out.reshape(info["n_spin"], info["n_inc"], 2, info["NR"], info["NPHI"])
+
+    # ---- kyconv seam ----
+    def kyconv(self, energies, par12, flux):
+        """In place on `flux` when it is a C-contiguous float64 array; returns the convolved array."""
+        eb = np.ascontiguousarray(energies, dtype=np.float64)
+        par = np.ascontiguousarray(par12, dtype=np.float64)
+        f = flux if (isinstance(flux, np.ndarray) and flux.dtype == np.float64 and flux.flags.c_contiguous) \
+            else np.array(flux, dtype=np.float64)
+        assert par.size == 12 and eb.size == f.size + 1
+        self._check(self.lib.rg_kyconv(self.h, _d(eb), f.size, _d(par), _d(f)))
+        return f
+
+    def ky_kernel(self, a, theta_o, r1, r2, dlnE, alpha=0.0, beta=0.0, rb=1.0, zshift=0.0, cap=65536):
+        H = np.zeros(cap)
+        kmin, nk = C.c_int(), C.c_int()
+        self._check(self.lib.rg_ky_kernel(self.h, a, theta_o, r1, r2, alpha, beta, rb, zshift, dlnE, _d(H), cap,
+                                          C.byref(kmin), C.byref(nk)))
+        return kmin.value, H[:nk.value].copy()
+
+    # ---- batched evaluation ----
+    def eval_batch_host(self, params, model=MODEL_RELAGN, rel=True, components=False, dr_dex=50.0, out=None,
+                        attrs=True):
+        """params: [P, 15] (relqso: first 7 columns used).  Returns (out [P, nE] or [P, 4, nE], attrs [P, 24])."""
+        p = np.asarray(params, dtype=np.float64)
+        if p.ndim == 1:
+            p = p[None, :]
+        P = p.shape[0]
+        pp = np.zeros((P, NPAR))
+        pp[:, :p.shape[1]] = p
+        flags = (FLAG_REL if rel else 0) | (FLAG_COMPONENTS if components else 0)
+        shape = (P, 4, self.nE) if components else (P, self.nE)
+        if out is None:
+            out = np.empty(shape)
+        assert out.shape == shape and out.dtype == np.float64 and out.flags.c_contiguous
+        at = np.zeros((P, NATTR)) if attrs else None
+        self._check(self.lib.rg_eval_batch_host(self.h, _d(pp), P, int(model), float(dr_dex), flags, _d(out),
+                                                _d(at) if attrs else None))
+        return out, at
+
+    def eval_batch_device(self, params_ptr, P, out_ptr, attrs_ptr=0, model=MODEL_RELAGN, rel=True, components=False,
+                          dr_dex=50.0, stream=0):
+        """Raw device pointers (e.g. torch tensor .data_ptr()); asynchronous on `stream`."""
+        flags = (FLAG_REL if rel else 0) | (FLAG_COMPONENTS if components else 0)
+        self._check(self.lib.rg_eval_batch(self.h, C.c_void_p(params_ptr), int(P), int(model), float(dr_dex), flags,
+                                           C.c_void_p(out_ptr), C.c_void_p(attrs_ptr) if attrs_ptr else None,
+                                           C.c_void_p(stream) if stream else None))
+
+    def set_profile(self, on=True):
+        self._check(self.lib.rg_set_option(self.h, OPT_PROFILE, 1.0 if on else 0.0))
+
+    def reset_stats(self):
+        self._check(self.lib.rg_reset_stats(self.h))
+
+    def stats(self):
+        out = {}
+        v = C.c_double()
+        for name, key in STATS.items():
+            self._check(self.lib.rg_get_stat(self.h, key, C.byref(v)))
+            out[name] = v.value
+        return out
+
+    def launch_count(self):
+        return int(self.lib.rg_launch_count(self.h))
+
+    def measure_fp64_peak(self):
+        v = C.c_double()
+        self._check(self.lib.rg_measure_fp64_peak(self.h, C.byref(v)))
+        return v.value

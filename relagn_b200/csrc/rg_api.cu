@@ -1,0 +1,651 @@
+// rg_api.cu -- the C ABI (include/relagn_b200.h): context, energy grid, Kerr
+// table residency, the kyconv seam and the batched evaluation driver.
+// Host-side only; every numeric result comes from the kernels in
+// rg_setup.cu / rg_spectrum.cu / rg_kyconv.cu / rg_raytrace.cu.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "rg_kernels.h"
+
+// ---------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+int rg_set_error(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int rg_set_cuda_error(int e, const char *msg, const char *what, const char *file, int line)
+{
+    snprintf(g_err, sizeof g_err, "CUDA error %d (%s) in %s at %s:%d", e, msg, what, file, line);
+    return RG_E_CUDA;
+}
+
+extern "C" const char *rg_last_error(void) { return g_err; }
+extern "C" int rg_version(void) { return RG_VERSION; }
+
+// ---------------------------------------------------------------------------
+struct rg_ctx {
+    int device = 0, sm_count = 0;
+    cudaStream_t stream = nullptr; // used by the *_host entry points
+    long launches = 0;
+    // energy grid
+    int nE = 0;
+    double *d_grid = nullptr;
+    GridDesc gd;
+    std::vector<double> h_ebins;
+    // tables
+    bool have_tab = false;
+    TabDesc td;
+    float *d_tab = nullptr;
+    double *d_tabmeta = nullptr;
+    size_t tab_floats = 0;
+    std::vector<double> h_spins, h_thetas;
+    // batch scratch
+    double *d_p10 = nullptr;
+    SetRec *d_recs = nullptr;
+    int chunk_sets = 0;
+    int *d_counter = nullptr;
+    int *h_counter = nullptr; // pinned
+    int2 *d_syslist = nullptr;
+    int sys_cap = 0;
+    double *d_sptot = nullptr, *d_header = nullptr;
+    double *d_sc = nullptr;
+    int nth_threads = 0;
+    double *d_rq = nullptr;
+    int rq_cap = 0;
+    // kyconv seam scratch
+    double *d_kyH = nullptr, *d_kyin = nullptr, *d_kyout = nullptr;
+    int ky_cap = 0, kyH_cap = 0;
+    // instrumentation
+    bool profile = false;
+    unsigned long long *d_stats = nullptr;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[3];
+    double ms_acc[3] = {0, 0, 0};
+    long n_acc[3] = {0, 0, 0};
+    double n_sets = 0;
+    // host staging (pinned) for rg_eval_batch_host
+    double *h_stage = nullptr;
+    size_t h_stage_bytes = 0;
+    double *d_stage_par = nullptr, *d_stage_out = nullptr, *d_stage_attr = nullptr;
+    size_t d_stage_par_n = 0, d_stage_out_n = 0, d_stage_attr_n = 0;
+};
+
+#define RG_TRY(expr)                 \
+    do {                             \
+        int rc__ = (expr);           \
+        if (rc__ != RG_OK) return rc__; \
+    } while (0)
+
+static void free_dev(void *p) { if (p) cudaFree(p); }
+static int prof_collect(rg_ctx *c);
+
+extern "C" int rg_ctx_create(int device, rg_ctx **out)
+{
+    if (!out) return rg_set_error(RG_E_ARG, "rg_ctx_create: out is NULL");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0)
+        return rg_set_error(RG_E_CUDA, "no CUDA device available (%s): this library has no CPU path",
+                            e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0) RG_CUDA_OK(cudaGetDevice(&device));
+    if (device >= ndev) return rg_set_error(RG_E_ARG, "device %d out of range (%d devices)", device, ndev);
+    RG_CUDA_OK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    RG_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    rg_ctx *c = new rg_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    memset(&c->gd, 0, sizeof c->gd);
+    memset(&c->td, 0, sizeof c->td);
+    RG_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    // 10^(0.02 j) with the host libm, exactly as the reference's x grid (pyNTHCOMP.py:112-114)
+    std::vector<double> p10(RG_NTH + 4);
+    for (int j = 0; j < RG_NTH + 4; j++) p10[j] = pow(10.0, j * 0.02);
+    RG_CUDA_OK(cudaMalloc(&c->d_p10, p10.size() * sizeof(double)));
+    RG_CUDA_OK(cudaMemcpy(c->d_p10, p10.data(), p10.size() * sizeof(double), cudaMemcpyHostToDevice));
+    RG_CUDA_OK(cudaMalloc(&c->d_counter, 2 * sizeof(int)));
+    RG_CUDA_OK(cudaMallocHost(&c->h_counter, 2 * sizeof(int)));
+    *out = c;
+    return RG_OK;
+}
+
+extern "C" void rg_ctx_destroy(rg_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    free_dev(c->d_grid); free_dev(c->d_tab); free_dev(c->d_tabmeta); free_dev(c->d_p10); free_dev(c->d_recs);
+    free_dev(c->d_counter); free_dev(c->d_syslist); free_dev(c->d_sptot); free_dev(c->d_header); free_dev(c->d_sc);
+    free_dev(c->d_rq); free_dev(c->d_kyH); free_dev(c->d_kyin); free_dev(c->d_kyout);
+    free_dev(c->d_stage_par); free_dev(c->d_stage_out); free_dev(c->d_stage_attr); free_dev(c->d_stats);
+    prof_collect(c);
+    if (c->h_counter) cudaFreeHost(c->h_counter);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" long rg_launch_count(rg_ctx *c) { return c ? c->launches : 0; }
+
+// ---- instrumentation ----
+static int prof_begin(rg_ctx *c, int kind, cudaStream_t st)
+{
+    if (!c->profile) return RG_OK;
+    cudaEvent_t a, b;
+    RG_CUDA_OK(cudaEventCreate(&a));
+    RG_CUDA_OK(cudaEventCreate(&b));
+    RG_CUDA_OK(cudaEventRecord(a, st));
+    c->ev[kind].push_back(std::make_pair(a, b));
+    return RG_OK;
+}
+static int prof_end(rg_ctx *c, int kind, cudaStream_t st)
+{
+    if (!c->profile) return RG_OK;
+    RG_CUDA_OK(cudaEventRecord(c->ev[kind].back().second, st));
+    return RG_OK;
+}
+static int prof_collect(rg_ctx *c)
+{
+    for (int k = 0; k < 3; k++) {
+        for (auto &pr : c->ev[k]) {
+            RG_CUDA_OK(cudaEventSynchronize(pr.second));
+            float ms = 0;
+            RG_CUDA_OK(cudaEventElapsedTime(&ms, pr.first, pr.second));
+            c->ms_acc[k] += ms;
+            c->n_acc[k] += 1;
+            cudaEventDestroy(pr.first);
+            cudaEventDestroy(pr.second);
+        }
+        c->ev[k].clear();
+    }
+    return RG_OK;
+}
+
+extern "C" int rg_set_option(rg_ctx *c, int key, double value)
+{
+    if (!c) return rg_set_error(RG_E_ARG, "rg_set_option: ctx is NULL");
+    if (key == RG_OPT_PROFILE) {
+        RG_CUDA_OK(cudaSetDevice(c->device));
+        c->profile = value != 0;
+        if (c->profile && !c->d_stats) {
+            RG_CUDA_OK(cudaMalloc(&c->d_stats, 4 * sizeof(unsigned long long)));
+            RG_CUDA_OK(cudaMemset(c->d_stats, 0, 4 * sizeof(unsigned long long)));
+        }
+        return RG_OK;
+    }
+    return rg_set_error(RG_E_ARG, "rg_set_option: unknown key %d", key);
+}
+
+extern "C" int rg_reset_stats(rg_ctx *c)
+{
+    if (!c) return rg_set_error(RG_E_ARG, "rg_reset_stats: ctx is NULL");
+    RG_CUDA_OK(cudaSetDevice(c->device));
+    RG_TRY(prof_collect(c));
+    for (int k = 0; k < 3; k++) { c->ms_acc[k] = 0; c->n_acc[k] = 0; }
+    c->n_sets = 0;
+    if (c->d_stats) RG_CUDA_OK(cudaMemset(c->d_stats, 0, 4 * sizeof(unsigned long long)));
+    return RG_OK;
+}
+
+extern "C" int rg_get_stat(rg_ctx *c, int key, double *value)
+{
+    if (!c || !value) return rg_set_error(RG_E_ARG, "rg_get_stat: bad arguments");
+    RG_CUDA_OK(cudaSetDevice(c->device));
+    RG_TRY(prof_collect(c));
+    unsigned long long h[4] = {0, 0, 0, 0};
+    if (c->d_stats && key >= RG_STAT_SUM_W && key <= RG_STAT_N_SYS) {
+        RG_CUDA_OK(cudaDeviceSynchronize());
+        RG_CUDA_OK(cudaMemcpy(h, c->d_stats, sizeof h, cudaMemcpyDeviceToHost));
+    }
+    switch (key) {
+    case RG_STAT_MS_SETUP: *value = c->ms_acc[0]; break;
+    case RG_STAT_MS_NTHCOMP: *value = c->ms_acc[1]; break;
+    case RG_STAT_MS_SPECTRUM: *value = c->ms_acc[2]; break;
+    case RG_STAT_N_SETUP: *value = (double)c->n_acc[0]; break;
+    case RG_STAT_N_NTHCOMP: *value = (double)c->n_acc[1]; break;
+    case RG_STAT_N_SPECTRUM: *value = (double)c->n_acc[2]; break;
+    case RG_STAT_SUM_W: *value = (double)h[0]; break;
+    case RG_STAT_N_CONV_ANN: *value = (double)h[1]; break;
+    case RG_STAT_SUM_JMAX: *value = (double)h[2]; break;
+    case RG_STAT_N_SYS: *value = (double)h[3]; break;
+    case RG_STAT_N_SETS: *value = c->n_sets; break;
+    default: return rg_set_error(RG_E_ARG, "rg_get_stat: unknown key %d", key);
+    }
+    return RG_OK;
+}
+
+// ---------------------------------------------------------------------------
+// energy grid (relagn.py:335-346 / new_ear :780-805)
+extern "C" int rg_set_grid(rg_ctx *c, const double *eb, int nE)
+{
+    if (!c || !eb || nE < 2) return rg_set_error(RG_E_ARG, "rg_set_grid: bad arguments");
+    if (rg_spectrum_pick_M(nE) == 0) return rg_set_error(RG_E_GRID, "nE = %d exceeds the kernel capacity", nE);
+    for (int j = 0; j < nE; j++)
+        if (!(eb[j + 1] > eb[j]) || !(eb[j] > 0)) return rg_set_error(RG_E_ARG, "bin edges must be positive and ascending");
+    RG_CUDA_OK(cudaSetDevice(c->device));
+    const int NA = 8; // arrays of nE
+    std::vector<double> h((size_t)NA * nE + 3 * RG_NEXT, 0.0);
+    double *Egrid = &h[0], *dE = &h[(size_t)nE], *nu = &h[(size_t)2 * nE], *hnu = &h[(size_t)3 * nE],
+           *bbpre = &h[(size_t)4 * nE], *wt = &h[(size_t)5 * nE], *e511 = &h[(size_t)6 * nE], *ear2 = &h[(size_t)7 * nE];
+    double *x_hnu = &h[(size_t)NA * nE], *x_bbpre = x_hnu + RG_NEXT, *x_wt = x_bbpre + RG_NEXT;
+    for (int j = 0; j < nE; j++) {
+        dE[j] = eb[j + 1] - eb[j];
+        Egrid[j] = eb[j] + 0.5 * dE[j];
+        nu[j] = Egrid[j] * RGK_KEV / RGK_H;
+        hnu[j] = RGK_H * nu[j];
+        bbpre[j] = (2 * RGK_H * (nu[j] * nu[j] * nu[j])) / (RGK_C * RGK_C);
+        e511[j] = Egrid[j] / 511.0;
+        ear2[j] = Egrid[j] * Egrid[j];
+    }
+    int n_ext = Egrid[0] < 1e-4 ? RG_NEXT : 0; // relagn.py:868
+    std::vector<double> xs; // abscissae of np.trapz: [extension, nu]
+    if (n_ext) {
+        double numin = nu[0];
+        for (int j = 1; j < nE; j++) numin = std::min(numin, nu[j]);
+        double start = 1e12, stop = numin - 100; // np.geomspace(1e12, min(nu)-100, 50), relagn.py:869-871
+        double ls = log10(start), le = log10(stop), step = (le - ls) / (RG_NEXT - 1);
+        for (int i = 0; i < RG_NEXT; i++) xs.push_back(pow(10.0, i == RG_NEXT - 1 ? le : i * step + ls));
+        xs[0] = start; xs[RG_NEXT - 1] = stop;
+    }
+    for (int j = 0; j < nE; j++) xs.push_back(nu[j]);
+    int n = (int)xs.size();
+    for (int k = 0; k < n; k++) {
+        double w = 0;
+        if (k > 0) w += 0.5 * (xs[k] - xs[k - 1]);
+        if (k + 1 < n) w += 0.5 * (xs[k + 1] - xs[k]);
+        if (k < n_ext) {
+            x_wt[k] = w;
+            x_hnu[k] = RGK_H * xs[k];
+            x_bbpre[k] = (2 * RGK_H * (xs[k] * xs[k] * xs[k])) / (RGK_C * RGK_C);
+        } else wt[k - n_ext] = w;
+    }
+    // the hot and warm normalisations integrate over nu_grid only (relagn.py:933,1316): when the
+    // extension is on, the disc joint weight differs from theirs in bin 0.  Keep a second copy.
+    // (handled by storing the plain weight in x_wt[RG_NEXT .. ] -- not needed: bin 0 of donthcomp is 0.)
+    double dlnE = log(eb[nE] / eb[0]) / nE;
+    int geometric = 1;
+    for (int j = 0; j <= nE; j++)
+        if (fabs(log(eb[j] / eb[0]) - j * dlnE) > 1e-4 * dlnE) { geometric = 0; break; }
+    free_dev(c->d_grid);
+    c->d_grid = nullptr;
+    RG_CUDA_OK(cudaMalloc(&c->d_grid, h.size() * sizeof(double)));
+    RG_CUDA_OK(cudaMemcpy(c->d_grid, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+    GridDesc &g = c->gd;
+    double *d = c->d_grid;
+    g.Egrid = d; g.dE = d + (size_t)nE; g.nu = d + (size_t)2 * nE; g.hnu = d + (size_t)3 * nE;
+    g.bbpre = d + (size_t)4 * nE; g.wt = d + (size_t)5 * nE; g.e511 = d + (size_t)6 * nE; g.ear2 = d + (size_t)7 * nE;
+    g.x_hnu = d + (size_t)NA * nE; g.x_bbpre = g.x_hnu + RG_NEXT; g.x_wt = g.x_bbpre + RG_NEXT;
+    g.n_ext = n_ext; g.nE = nE; g.geometric = geometric; g.dlnE = dlnE;
+    c->nE = nE;
+    c->h_ebins.assign(eb, eb + nE + 1);
+    return RG_OK;
+}
+
+// ---------------------------------------------------------------------------
+// tables
+static int tables_alloc(rg_ctx *c, const double *spins, int n_spin, const double *thetas, int n_inc, int NR, int NPHI,
+                        double dl)
+{
+    if (!c || !spins || !thetas || n_spin < 1 || n_inc < 1 || NR < 2 || !(dl > 0))
+        return rg_set_error(RG_E_ARG, "tables: bad arguments");
+    if (NPHI < 32 || NPHI > RG_SPEC_THREADS || RG_SPEC_THREADS % NPHI != 0)
+        return rg_set_error(RG_E_ARG, "tables: NPHI must be 32, 64, 128 or 256");
+    for (int i = 1; i < n_spin; i++)
+        if (!(spins[i] > spins[i - 1])) return rg_set_error(RG_E_ARG, "tables: spins must ascend");
+    for (int i = 1; i < n_inc; i++)
+        if (!(thetas[i] > thetas[i - 1])) return rg_set_error(RG_E_ARG, "tables: inclinations must ascend");
+    RG_CUDA_OK(cudaSetDevice(c->device));
+    free_dev(c->d_tab); free_dev(c->d_tabmeta);
+    c->d_tab = nullptr; c->d_tabmeta = nullptr; c->have_tab = false;
+    c->tab_floats = (size_t)n_spin * n_inc * 2 * NR * NPHI;
+    RG_CUDA_OK(cudaMalloc(&c->d_tab, c->tab_floats * sizeof(float)));
+    std::vector<double> meta(2 * n_spin + n_inc);
+    for (int i = 0; i < n_spin; i++) { meta[i] = spins[i]; meta[n_spin + i] = rg_risco(spins[i]); }
+    for (int i = 0; i < n_inc; i++) meta[2 * n_spin + i] = thetas[i];
+    RG_CUDA_OK(cudaMalloc(&c->d_tabmeta, meta.size() * sizeof(double)));
+    RG_CUDA_OK(cudaMemcpy(c->d_tabmeta, meta.data(), meta.size() * sizeof(double), cudaMemcpyHostToDevice));
+    TabDesc &t = c->td;
+    t.data = c->d_tab; t.spins = c->d_tabmeta; t.riscos = c->d_tabmeta + n_spin; t.thetas = c->d_tabmeta + 2 * n_spin;
+    t.n_spin = n_spin; t.n_inc = n_inc; t.NR = NR; t.NPHI = NPHI; t.dl = dl;
+    c->h_spins.assign(spins, spins + n_spin);
+    c->h_thetas.assign(thetas, thetas + n_inc);
+    return RG_OK;
+}
+
+// range of ln g over every node: bounds the shift histogram
+static int tables_finish(rg_ctx *c, const float *host_data)
+{
+    std::vector<float> tmp;
+    if (!host_data) {
+        tmp.resize(c->tab_floats);
+        RG_CUDA_OK(cudaMemcpy(tmp.data(), c->d_tab, c->tab_floats * sizeof(float), cudaMemcpyDeviceToHost));
+        host_data = tmp.data();
+    }
+    size_t plane = (size_t)c->td.NR * c->td.NPHI;
+    size_t nodes = (size_t)c->td.n_spin * c->td.n_inc;
+    double gmin = 1e300, gmax = 0;
+    for (size_t n = 0; n < nodes; n++) {
+        const float *g = host_data + n * 2 * plane;
+        for (size_t i = 0; i < plane; i++) {
+            double v = g[i];
+            if (!(v > 0) || !(v < 1e30)) return rg_set_error(RG_E_ARG, "tables: non-positive or non-finite g in node %zu", n);
+            gmin = std::min(gmin, v); gmax = std::max(gmax, v);
+        }
+    }
+    c->td.lng_min = log(gmin);
+    c->td.lng_max = log(gmax);
+    c->have_tab = true;
+    return RG_OK;
+}
+
+extern "C" int rg_tables_upload(rg_ctx *c, const double *spins, int n_spin, const double *thetas, int n_inc, int NR,
+                                int NPHI, double dl, const float *data)
+{
+    if (!data) return rg_set_error(RG_E_ARG, "rg_tables_upload: data is NULL");
+    RG_TRY(tables_alloc(c, spins, n_spin, thetas, n_inc, NR, NPHI, dl));
+    RG_CUDA_OK(cudaMemcpy(c->d_tab, data, c->tab_floats * sizeof(float), cudaMemcpyHostToDevice));
+    return tables_finish(c, data);
+}
+
+extern "C" int rg_tables_generate(rg_ctx *c, const double *spins, int n_spin, const double *thetas, int n_inc, int NR,
+                                  int NPHI, double dl, long *n_unresolved)
+{
+    RG_TRY(tables_alloc(c, spins, n_spin, thetas, n_inc, NR, NPHI, dl));
+    long bad = 0;
+    RG_TRY(rg_launch_raytrace(spins, n_spin, thetas, n_inc, NR, NPHI, dl, c->d_tab, &bad, c->stream));
+    c->launches += 2L * n_spin * n_inc;
+    if (n_unresolved) *n_unresolved = bad;
+    return tables_finish(c, nullptr);
+}
+
+extern "C" int rg_tables_download(rg_ctx *c, float *data, size_t n_floats)
+{
+    if (!c || !c->have_tab) return rg_set_error(RG_E_NOTABLES, "no tables resident");
+    if (!data || n_floats != c->tab_floats) return rg_set_error(RG_E_ARG, "rg_tables_download: size mismatch");
+    RG_CUDA_OK(cudaSetDevice(c->device));
+    RG_CUDA_OK(cudaMemcpy(data, c->d_tab, n_floats * sizeof(float), cudaMemcpyDeviceToHost));
+    return RG_OK;
+}
+
+extern "C" int rg_tables_info(rg_ctx *c, int *n_spin, int *n_inc, int *NR, int *NPHI, double *dl, size_t *n_floats)
+{
+    if (!c || !c->have_tab) return rg_set_error(RG_E_NOTABLES, "no tables resident");
+    if (n_spin) *n_spin = c->td.n_spin;
+    if (n_inc) *n_inc = c->td.n_inc;
+    if (NR) *NR = c->td.NR;
+    if (NPHI) *NPHI = c->td.NPHI;
+    if (dl) *dl = c->td.dl;
+    if (n_floats) *n_floats = c->tab_floats;
+    return RG_OK;
+}
+
+// ---------------------------------------------------------------------------
+// B1: kyconv seam
+static void ky_range(double dlnE, double zshift, int &K_LO, int &K_HI)
+{
+    K_LO = (int)floor(log(0.005) / dlnE) - 2;
+    K_HI = (int)ceil(log(4.0) / dlnE) + 2;
+    double zs = 0;
+    if (zshift != 0) zs = -log(1 + zshift) / dlnE;
+    K_LO += (int)floor(zs) - 1;
+    K_HI += (int)ceil(zs) + 1;
+}
+
+static int ky_hist_host(rg_ctx *c, double a, double th, double r1, double r2, double alpha, double beta, double rb,
+                        double zshift, double dlnE, int nsub, std::vector<double> &H, int &K_LO)
+{
+    if (!c->have_tab) return rg_set_error(RG_E_NOTABLES, "kyconv: no Kerr tables resident (rg_tables_generate/upload)");
+    if (!(r2 > r1) || !(dlnE > 0)) return rg_set_error(RG_E_ARG, "kyconv: need r_out > r_in and a positive grid step");
+    int K_HI;
+    ky_range(dlnE, zshift, K_LO, K_HI);
+    int nH = K_HI - K_LO + 1;
+    RG_CUDA_OK(cudaSetDevice(c->device));
+    if (nH > c->kyH_cap) {
+        free_dev(c->d_kyH);
+        c->d_kyH = nullptr;
+        RG_CUDA_OK(cudaMalloc(&c->d_kyH, (size_t)nH * sizeof(double)));
+        c->kyH_cap = nH;
+    }
+    RG_TRY(rg_launch_ky_hist(c->td, a, th, r1, r2, alpha, beta, rb, zshift, dlnE, nsub, c->d_kyH, K_LO, nH, c->stream));
+    c->launches++;
+    H.resize(nH);
+    RG_CUDA_OK(cudaMemcpyAsync(H.data(), c->d_kyH, (size_t)nH * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    RG_CUDA_OK(cudaStreamSynchronize(c->stream));
+    return RG_OK;
+}
+
+extern "C" int rg_ky_kernel(rg_ctx *c, double a, double theta_o, double r1, double r2, double alpha, double beta,
+                            double rb, double zshift, double dlnE, double *H_host, int cap, int *kmin, int *nk)
+{
+    if (!c || !H_host || !kmin || !nk) return rg_set_error(RG_E_ARG, "rg_ky_kernel: bad arguments");
+    std::vector<double> H;
+    int K_LO;
+    RG_TRY(ky_hist_host(c, a, theta_o, r1, r2, alpha, beta, rb, zshift, dlnE, 0, H, K_LO));
+    int lo = 0, hi = (int)H.size() - 1;
+    while (lo <= hi && H[lo] == 0) lo++;
+    while (hi >= lo && H[hi] == 0) hi--;
+    if (lo > hi) { *kmin = 0; *nk = 0; return RG_OK; }
+    int n = hi - lo + 1;
+    *nk = n;
+    *kmin = K_LO + lo;
+    if (n > cap) return rg_set_error(RG_E_ARG, "rg_ky_kernel: histogram needs %d entries, cap is %d", n, cap);
+    memcpy(H_host, &H[lo], (size_t)n * sizeof(double));
+    return RG_OK;
+}
+
+extern "C" int rg_kyconv(rg_ctx *c, const double *eb, int nE, const double *par, double *flux)
+{
+    if (!c || !eb || !par || !flux || nE < 2) return rg_set_error(RG_E_ARG, "rg_kyconv: bad arguments");
+    if (par[3] != 0 || par[9] != 0 || par[11] != -1)
+        return rg_set_error(RG_E_UNSUPPORTED, "rg_kyconv: only ms=0, ntable=0 (isotropic), norm=-1 are implemented "
+                                              "(what relagn.py:997-998 passes)");
+    double dlnE = log(eb[nE] / eb[0]) / nE;
+    for (int j = 0; j <= nE; j++)
+        if (fabs(log(eb[j] / eb[0]) - j * dlnE) > 1e-4 * dlnE)
+            return rg_set_error(RG_E_GRID, "rg_kyconv: the energy grid must be geometric");
+    std::vector<double> H;
+    int K_LO;
+    double th = par[1] * (RGK_PI / 180.0);
+    RG_TRY(ky_hist_host(c, par[0], th, par[2], par[4], par[5], par[6], par[7], par[8], dlnE, 0, H, K_LO));
+    int lo = 0, hi = (int)H.size() - 1;
+    while (lo <= hi && H[lo] == 0) lo++;
+    while (hi >= lo && H[hi] == 0) hi--;
+    if (lo > hi) { memset(flux, 0, (size_t)nE * sizeof(double)); return RG_OK; }
+    if (nE > c->ky_cap) {
+        free_dev(c->d_kyin); free_dev(c->d_kyout);
+        c->d_kyin = c->d_kyout = nullptr;
+        RG_CUDA_OK(cudaMalloc(&c->d_kyin, (size_t)nE * sizeof(double)));
+        RG_CUDA_OK(cudaMalloc(&c->d_kyout, (size_t)nE * sizeof(double)));
+        c->ky_cap = nE;
+    }
+    RG_CUDA_OK(cudaMemcpyAsync(c->d_kyin, flux, (size_t)nE * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    RG_TRY(rg_launch_ky_conv(c->d_kyH + lo, K_LO + lo, hi - lo + 1, c->d_kyin, c->d_kyout, nE, c->stream));
+    c->launches++;
+    RG_CUDA_OK(cudaMemcpyAsync(flux, c->d_kyout, (size_t)nE * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    RG_CUDA_OK(cudaStreamSynchronize(c->stream));
+    return RG_OK;
+}
+
+// ---------------------------------------------------------------------------
+// B2: batched evaluation
+static int ensure_batch_scratch(rg_ctx *c, int model)
+{
+    if (!c->d_recs) {
+        // sized once: chunk of sets, arena of Kompaneets systems, persistent nthcomp grid
+        c->chunk_sets = 16384;
+        c->sys_cap = c->chunk_sets * 40;
+        c->nth_threads = c->sm_count * 4 * 128;
+        RG_CUDA_OK(cudaMalloc(&c->d_recs, (size_t)c->chunk_sets * sizeof(SetRec)));
+        RG_CUDA_OK(cudaMalloc(&c->d_syslist, (size_t)c->sys_cap * sizeof(int2)));
+        RG_CUDA_OK(cudaMalloc(&c->d_sptot, (size_t)c->sys_cap * RG_SPT_STRIDE * sizeof(double)));
+        RG_CUDA_OK(cudaMalloc(&c->d_header, (size_t)c->sys_cap * 4 * sizeof(double)));
+        RG_CUDA_OK(cudaMalloc(&c->d_sc, (size_t)3 * RG_NTH * c->nth_threads * sizeof(double)));
+    }
+    if (model == RG_MODEL_RELQSO && !c->d_rq) {
+        c->rq_cap = 4608; // fine radial grid of _set_rhot: 1000/dex over <= 4.6 dex
+        RG_CUDA_OK(cudaMalloc(&c->d_rq, (size_t)c->rq_cap * c->chunk_sets * sizeof(double)));
+    }
+    return RG_OK;
+}
+
+extern "C" int rg_eval_batch(rg_ctx *c, const double *d_params, int P, int model, double dr_dex, unsigned flags,
+                             double *d_out, double *d_attrs, void *stream)
+{
+    if (!c || !d_params || !d_out || P < 0) return rg_set_error(RG_E_ARG, "rg_eval_batch: bad arguments");
+    if (model != RG_MODEL_RELAGN && model != RG_MODEL_RELQSO) return rg_set_error(RG_E_ARG, "unknown model %d", model);
+    if (!(dr_dex > 0)) return rg_set_error(RG_E_ARG, "dr_dex must be positive");
+    if (c->nE <= 0) return rg_set_error(RG_E_GRID, "no energy grid set (rg_set_grid)");
+    const bool rel = (flags & RG_FLAG_REL) != 0;
+    if (rel && !c->have_tab) return rg_set_error(RG_E_NOTABLES, "relativistic evaluation needs Kerr tables");
+    if (rel && !c->gd.geometric)
+        return rg_set_error(RG_E_GRID, "relativistic evaluation needs a geometric (log-spaced) energy grid");
+    if (P == 0) return RG_OK;
+    RG_CUDA_OK(cudaSetDevice(c->device));
+    RG_TRY(ensure_batch_scratch(c, model));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nE = c->nE;
+    const int M = rg_spectrum_pick_M(nE);
+    const int ncomp = (flags & RG_FLAG_COMPONENTS) ? 4 : 1;
+
+    SpecArgs A;
+    memset(&A, 0, sizeof A);
+    A.grid = c->gd;
+    A.flags = flags;
+    A.p10tab = c->d_p10;
+    A.sptot = c->d_sptot;
+    A.header = c->d_header;
+    if (rel) {
+        A.tab = c->td;
+        int kl, kh;
+        ky_range(c->gd.dlnE, 0.0, kl, kh);
+        int K_LO = (int)floor(c->td.lng_min / c->gd.dlnE) - 3, K_HI = (int)ceil(c->td.lng_max / c->gd.dlnE) + 3;
+        K_LO = std::max(K_LO, kl);
+        K_HI = std::min(K_HI, kh);
+        A.K_LO = K_LO;
+        A.nH = K_HI - K_LO + 1;
+        A.HL = std::max(K_HI, 0) / M + 3;
+        A.HH = std::max(-K_LO, 0) / M + 3;
+    } else {
+        A.K_LO = 0; A.nH = 1; A.HL = 1; A.HH = 1;
+    }
+
+    int p0 = 0, chunk = c->chunk_sets;
+    while (p0 < P) {
+        int n = std::min(chunk, P - p0);
+        const double *par = d_params + (size_t)p0 * RG_NPAR;
+        double *attrs = d_attrs ? d_attrs + (size_t)p0 * RG_NATTR : nullptr;
+        RG_TRY(prof_begin(c, 0, st));
+        RG_TRY(rg_launch_setup(par, n, model, dr_dex, c->d_recs, c->d_counter, c->d_syslist, c->sys_cap, c->d_rq,
+                               c->rq_cap, attrs, st));
+        RG_TRY(prof_end(c, 0, st));
+        c->launches++;
+        RG_CUDA_OK(cudaMemcpyAsync(c->h_counter, c->d_counter, sizeof(int), cudaMemcpyDeviceToHost, st));
+        RG_CUDA_OK(cudaStreamSynchronize(st));
+        int nsys = c->h_counter[0];
+        if (nsys > c->sys_cap) {
+            if (n == 1) return rg_set_error(RG_E_NOMEM, "one parameter set needs %d Kompaneets systems (cap %d)", nsys, c->sys_cap);
+            chunk = std::max(1, n / 2); // arena too small for this chunk: retry with fewer sets
+            continue;
+        }
+        unsigned long long *stats = c->profile ? c->d_stats : nullptr;
+        if (nsys > 0) {
+            RG_TRY(prof_begin(c, 1, st));
+            RG_TRY(rg_launch_nthcomp(c->d_recs, c->d_syslist, nsys, c->d_p10, c->d_sc,
+                                     c->d_sc + (size_t)RG_NTH * c->nth_threads,
+                                     c->d_sc + (size_t)2 * RG_NTH * c->nth_threads, c->nth_threads, c->d_sptot,
+                                     c->d_header, stats, st));
+            RG_TRY(prof_end(c, 1, st));
+            c->launches++;
+        }
+        A.recs = c->d_recs;
+        A.P = n;
+        A.out = d_out + (size_t)p0 * ncomp * nE;
+        A.stats = stats;
+        RG_TRY(prof_begin(c, 2, st));
+        RG_TRY(rg_launch_spectrum(A, st));
+        RG_TRY(prof_end(c, 2, st));
+        c->launches++;
+        c->n_sets += n;
+        p0 += n;
+    }
+    return RG_OK;
+}
+
+static int ensure_dev(double **p, size_t *have, size_t need)
+{
+    if (*have >= need) return RG_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *have = 0;
+    RG_CUDA_OK(cudaMalloc(p, need * sizeof(double)));
+    *have = need;
+    return RG_OK;
+}
+
+extern "C" int rg_eval_batch_host(rg_ctx *c, const double *params, int P, int model, double dr_dex, unsigned flags,
+                                  double *out, double *attrs)
+{
+    if (!c || !params || !out || P < 0) return rg_set_error(RG_E_ARG, "rg_eval_batch_host: bad arguments");
+    if (c->nE <= 0) return rg_set_error(RG_E_GRID, "no energy grid set (rg_set_grid)");
+    if (P == 0) return RG_OK;
+    RG_CUDA_OK(cudaSetDevice(c->device));
+    const int ncomp = (flags & RG_FLAG_COMPONENTS) ? 4 : 1;
+    const size_t per_out = (size_t)ncomp * c->nE;
+    // pipeline in slabs so the D2H of slab i overlaps the kernels of slab i+1
+    const int SLAB = 8192;
+    int nslab_dev = std::min(P, 2 * SLAB);
+    RG_TRY(ensure_dev(&c->d_stage_par, &c->d_stage_par_n, (size_t)P * RG_NPAR));
+    RG_TRY(ensure_dev(&c->d_stage_out, &c->d_stage_out_n, (size_t)nslab_dev * per_out));
+    RG_TRY(ensure_dev(&c->d_stage_attr, &c->d_stage_attr_n, (size_t)P * RG_NATTR));
+    RG_CUDA_OK(cudaMemcpyAsync(c->d_stage_par, params, (size_t)P * RG_NPAR * sizeof(double), cudaMemcpyHostToDevice,
+                               c->stream));
+    cudaStream_t copy_st = nullptr;
+    RG_CUDA_OK(cudaStreamCreateWithFlags(&copy_st, cudaStreamNonBlocking));
+    cudaEvent_t done[2], freed[2];
+    for (int i = 0; i < 2; i++) { cudaEventCreate(&done[i]); cudaEventCreate(&freed[i]); }
+    int rc = RG_OK;
+    int slab = 0;
+    bool used[2] = {false, false};
+    for (int p0 = 0; p0 < P && rc == RG_OK; p0 += SLAB, slab ^= 1) {
+        int n = std::min(SLAB, P - p0);
+        double *dslab = c->d_stage_out + (size_t)(nslab_dev > SLAB ? slab : 0) * SLAB * per_out;
+        if (used[slab]) cudaEventSynchronize(freed[slab]); // previous copy out of this slab buffer finished
+        rc = rg_eval_batch(c, c->d_stage_par + (size_t)p0 * RG_NPAR, n, model, dr_dex, flags, dslab,
+                           c->d_stage_attr + (size_t)p0 * RG_NATTR, c->stream);
+        if (rc != RG_OK) break;
+        cudaEventRecord(done[slab], c->stream);
+        // D2H on the copy stream once the slab's kernels are done
+        cudaStreamSynchronize(c->stream); // (rg_eval_batch already synchronised per chunk; keeps ordering simple)
+        cudaMemcpyAsync(out + (size_t)p0 * per_out, dslab, (size_t)n * per_out * sizeof(double), cudaMemcpyDeviceToHost,
+                        copy_st);
+        cudaEventRecord(freed[slab], copy_st);
+        used[slab] = true;
+    }
+    cudaStreamSynchronize(copy_st);
+    if (rc == RG_OK && attrs) {
+        cudaMemcpyAsync(attrs, c->d_stage_attr, (size_t)P * RG_NATTR * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    }
+    cudaStreamSynchronize(c->stream);
+    for (int i = 0; i < 2; i++) { cudaEventDestroy(done[i]); cudaEventDestroy(freed[i]); }
+    cudaStreamDestroy(copy_st);
+    if (rc != RG_OK) return rc;
+    RG_CUDA_OK(cudaGetLastError());
+    return RG_OK;
+}
+
+// ---------------------------------------------------------------------------
+extern "C" int rg_measure_fp64_peak(rg_ctx *c, double *tflops)
+{
+    if (!c || !tflops) return rg_set_error(RG_E_ARG, "rg_measure_fp64_peak: bad arguments");
+    RG_CUDA_OK(cudaSetDevice(c->device));
+    c->launches += 2;
+    return rg_fp64_peak(tflops, c->stream);
+}

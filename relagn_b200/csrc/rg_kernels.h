@@ -3,6 +3,8 @@
 #pragma once
 #include "rg_common.cuh"
 
+#define RG_SPEC_THREADS 256
+
 // Kerr transfer tables resident on the device
 struct TabDesc {
     const float *data;     // [n_spin][n_inc][2][NR][NPHI]
@@ -11,40 +13,65 @@ struct TabDesc {
     const double *thetas;  // [n_inc] ascending, radians
     int n_spin, n_inc, NR, NPHI;
     double dl;
-    double lng_min, lng_max; // global range of ln g over all nodes (sizes the shift histogram)
+    double lng_min, lng_max; // range of ln g over all nodes (sizes the shift histogram)
 };
 
-// energy grid resident on the device
+// energy grid resident on the device (all [nE] unless noted; built by rg_set_grid)
 struct GridDesc {
-    const double *Egrid; // [nE] bin centres (keV)
-    const double *nu;    // [nE] Hz
-    const double *bbpre; // [nE] 2 h nu^3 / c^2
-    const double *lgE;   // [nE] log10(Egrid)
+    const double *Egrid; // bin centres (keV): left edge + dE/2      relagn.py:335-338
+    const double *dE;    // bin widths
+    const double *nu;    // Hz                                         relagn.py:339
+    const double *hnu;   // h * nu   (numerator of relagn.py:48)
+    const double *bbpre; // 2 h nu^3 / c^2                              relagn.py:47
+    const double *wt;    // trapezoid weights of np.trapz(., nu) on this grid (with the extension joint when n_ext)
+    const double *e511;  // Egrid / 511                                pyNTHCOMP.py:70
+    const double *ear2;  // Egrid^2                                    pyNTHCOMP.py:75
+    // low-frequency extension of disc_annuli (relagn.py:868-873), [RG_NEXT] when n_ext
+    const double *x_hnu, *x_bbpre, *x_wt;
+    int n_ext;
     int nE;
     int geometric;
-    double dlnE;         // ln(E_{j+1}/E_j) when geometric
+    double dlnE;         // ln(E_nE/E_0)/nE when geometric
 };
+
+struct SpecArgs {
+    const SetRec *recs;
+    int P;
+    GridDesc grid;
+    TabDesc tab;
+    unsigned flags;
+    const double *p10tab; // [RG_NTH+1] 10^(0.02 j)
+    const double *sptot;  // [sys][RG_SPT_STRIDE]
+    const double *header; // [sys][4] = xmin, normfac, jmax, kTbb
+    double *out;          // [P][nE] or [P][4][nE]
+    int K_LO, nH;         // shift-histogram support: k in [K_LO, K_LO + nH)
+    int HL, HH;           // zero halo rows of the transposed local-spectrum buffer
+    unsigned long long *stats; // optional device counters [4]: sum W_ann, conv annuli, sum jmax, systems
+};
+
+size_t rg_spectrum_smem_bytes(int M, int nH, int HL, int HH);
+int rg_spectrum_pick_M(int nE); // 4, 8 or 20; 0 if nE is too large
 
 int rg_launch_setup(const double *d_params, int P, int model, double dr_dex, SetRec *recs, int *sys_counter,
                     int2 *syslist, int sys_cap, double *rq_scratch, int rq_cap, double *d_attrs, cudaStream_t st);
 
-int rg_launch_nthcomp(const SetRec *recs, const int2 *syslist, const int *sys_counter, int sys_cap,
-                      const double *p10tab, double *sc_gam, double *sc_g, double *sc_bet, size_t sc_stride,
-                      double *sptot, double *header, cudaStream_t st);
+// persistent: n_threads = total launched threads = rows of the [RG_NTH][n_threads] scratch planes
+int rg_launch_nthcomp(const SetRec *recs, const int2 *syslist, int nsys, const double *p10tab, double *sc_gam,
+                      double *sc_g, double *sc_bet, int n_threads, double *sptot, double *header,
+                      unsigned long long *stats, cudaStream_t st);
 
-int rg_launch_spectrum(const SetRec *recs, int P, const GridDesc &grid, const TabDesc &tab, unsigned flags,
-                       const double *p10tab, const double *sptot, const double *header, double *d_out,
-                       cudaStream_t st);
+int rg_launch_spectrum(const SpecArgs &args, cudaStream_t st);
 
-// generic kyconv seam: histogram of one (possibly wide) annulus into d_H[K_LO .. K_LO+nH)
+// generic kyconv seam: histogram of one (possibly wide) annulus into d_H[0..nH) (shift k = K_LO + index)
 int rg_launch_ky_hist(const TabDesc &tab, double a, double theta_o, double r1, double r2, double alpha, double beta,
                       double rb, double zshift, double dlnE, int nsub, double *d_H, int K_LO, int nH,
                       cudaStream_t st);
+// out[j] = sum_i H[i] in[j - (kmin + i)]
 int rg_launch_ky_conv(const double *d_H, int kmin, int nk, const double *d_in, double *d_out, int nE,
                       cudaStream_t st);
 
-// table generation (device ray tracer)
+// table generation (device ray tracer): fills d_data [n_spin][n_inc][2][NR][NPHI]
 int rg_launch_raytrace(const double *h_spins, int n_spin, const double *h_thetas, int n_inc, int NR, int NPHI,
                        double dl, float *d_data, long *n_unresolved, cudaStream_t st);
 
-int rg_fp64_peak(double *tflops);
+int rg_fp64_peak(double *tflops, cudaStream_t st);

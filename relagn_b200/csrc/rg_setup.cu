@@ -61,6 +61,15 @@ __device__ static double ldiss_quad(const SetRec &r, const NtConst &nt)
     double ta = log(r.risco), tb = log(r.r_h);
     int npan = 2 + (int)ceil((tb - ta) * 2.0);
     if (npan > 16) npan = 16;
+    // 16-point Gauss-Legendre nodes/weights on [-1,1] (positive half)
+    const double RG_GL16_X[8] = {0.0950125098376374401853193, 0.2816035507792589132304605,
+                                 0.4580167776572273863424194, 0.6178762444026437484466718,
+                                 0.7554044083550030338951012, 0.8656312023878317438804679,
+                                 0.9445750230732325760779884, 0.9894009349916499325961542};
+    const double RG_GL16_W[8] = {0.1894506104550684962853967, 0.1826034150449235888667637,
+                                 0.1691565193950025381893121, 0.1495959888165767320815017,
+                                 0.1246289712555338720524763, 0.0951585116824927848099251,
+                                 0.0622535239386478928628438, 0.0271524594117540948517806};
     double tot = 0;
     for (int p = 0; p < npan; p++) {
         double t0 = ta + (tb - ta) * p / npan, t1 = ta + (tb - ta) * (p + 1) / npan;
@@ -205,31 +214,27 @@ setup_kernel(const double *__restrict__ params, int P, int model, double dr_dex,
 }
 
 // ---------------------------------------------------------------------------
-// nthcomp: one thread per system.
-//   scratch arrays gam, g, bet: [RG_NTH][n_sys_stride] (coalesced across a warp)
-//   sptot arena: [sys][RG_SPT_STRIDE];  header: [sys][4] = xmin, normfac, jmax, 0
-__global__ void __launch_bounds__(128)
-nthcomp_kernel(const SetRec *__restrict__ recs, const int2 *__restrict__ syslist, const int *__restrict__ sys_counter,
-               int sys_cap, const double *__restrict__ p10tab, double *__restrict__ sc_gam, double *__restrict__ sc_g,
-               double *__restrict__ sc_bet, size_t sc_stride, double *__restrict__ sptot, double *__restrict__ header)
+// nthcomp: one thread per system, persistent grid.
+//   scratch planes gam, g, bet: [RG_NTH][n_threads], indexed by the launching
+//   thread (not the system) so the footprint is bounded by the resident
+//   threads; a warp's accesses to one j are contiguous.
+//   sptot arena: [sys][RG_SPT_STRIDE];  header: [sys][4] = xmin, normfac, jmax, kTbb
+__device__ static void nthcomp_system(const SetRec &r, int which, const double *__restrict__ p10tab,
+                                      double *__restrict__ sc_gam, double *__restrict__ sc_g,
+                                      double *__restrict__ sc_bet, size_t sc_stride, int slot, double *__restrict__ spt,
+                                      double *__restrict__ hd)
 {
-    int sys = blockIdx.x * blockDim.x + threadIdx.x;
-    int nsys = *sys_counter;
-    if (nsys > sys_cap) nsys = sys_cap;
-    if (sys >= nsys) return;
-    int2 ent = syslist[sys];
-    const SetRec &r = recs[ent.x];
-    if (r.status != RG_S_OK) return;
+    const int sys = slot; // scratch column of this thread
     double gamma, kte, ktbb;
-    if (ent.y < 0) { // hot shape: relagn.py:1200-1223
+    if (which < 0) { // hot shape: relagn.py:1200-1223
         gamma = r.gamma_h; kte = r.kTe_h; ktbb = r.kTseed;
-    } else {         // warm annulus ent.y (counted top-down): relagn.py:900-927
+    } else {         // warm annulus `which` (counted top-down): relagn.py:900-927
         NtConst nt;
-        rg_nt_prepare(nt, r.a, r.risco, r.M, r.mdot, r.Mdot_edd, r.Rg);
+        rg_nt_prepare(nt, r);
         BinIter it;
         it.start(r.lg_rh, r.lg_rw, r.dlog_r);
         double lo = 0, hi = 0;
-        for (int s = 0; s <= ent.y; s++) it.next(lo, hi);
+        for (int s = 0; s <= which; s++) it.next(lo, hi);
         double rmid = pow(10.0, lo + r.dlog_r / 2);
         double Tann = pow(rg_tnt4(nt, rmid), 0.25);
         gamma = r.gamma_w; kte = r.kTe_w; ktbb = Tann / 1.16048e7;
@@ -242,8 +247,6 @@ nthcomp_kernel(const SetRec *__restrict__ recs, const int2 *__restrict__ syslist
     double xmin = 1e-4 * tempbb, xmax = 40.0 * theta;
     int jmax = (int)(log10(xmax / xmin) / delta) + 1;
     if (jmax > 899) jmax = 899;
-    double *hd = header + (size_t)sys * 4;
-    double *spt = sptot + (size_t)sys * RG_SPT_STRIDE;
     if (jmax < 4) { // degenerate grid: the reference would index out of range; flag as empty
         hd[0] = xmin; hd[1] = 0.0; hd[2] = 0.0; hd[3] = 0.0;
         return;
@@ -350,24 +353,49 @@ nthcomp_kernel(const SetRec *__restrict__ recs, const int2 *__restrict__ syslist
     hd[0] = xmin; hd[1] = 1.0 / spp; hd[2] = (double)jmax; hd[3] = ktbb;
 }
 
+__global__ void __launch_bounds__(128)
+nthcomp_kernel(const SetRec *__restrict__ recs, const int2 *__restrict__ syslist, int nsys,
+               const double *__restrict__ p10tab, double *__restrict__ sc_gam, double *__restrict__ sc_g,
+               double *__restrict__ sc_bet, int n_threads, double *__restrict__ sptot, double *__restrict__ header,
+               unsigned long long *stats)
+{
+    int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long sumj = 0, nsolved = 0;
+    for (int sys = gtid; sys < nsys; sys += n_threads) {
+        int2 ent = syslist[sys];
+        const SetRec &r = recs[ent.x];
+        if (r.status != RG_S_OK) continue;
+        nthcomp_system(r, ent.y, p10tab, sc_gam, sc_g, sc_bet, (size_t)n_threads, gtid,
+                       sptot + (size_t)sys * RG_SPT_STRIDE, header + (size_t)sys * 4);
+        sumj += (unsigned long long)header[(size_t)sys * 4 + 2];
+        nsolved++;
+    }
+    if (stats && nsolved) {
+        atomicAdd(&stats[2], sumj);
+        atomicAdd(&stats[3], nsolved);
+    }
+}
+
 // ---------------------------------------------------------------------------
 int rg_launch_setup(const double *d_params, int P, int model, double dr_dex, SetRec *recs, int *sys_counter,
                     int2 *syslist, int sys_cap, double *rq_scratch, int rq_cap, double *d_attrs, cudaStream_t st)
 {
     RG_CUDA_OK(cudaMemsetAsync(sys_counter, 0, sizeof(int), st));
-    setup_kernel<<<(P + 127) / 128, 128, 0, st>>>(d_params, P, model, dr_dex, recs, sys_counter, syslist, sys_cap,
-                                                  rq_scratch, rq_cap, d_attrs);
+    RG_LAUNCH(setup_kernel, dim3((P + 127) / 128), dim3(128), 0, st, d_params, P, model, dr_dex, recs, sys_counter,
+              syslist, sys_cap, rq_scratch, rq_cap, d_attrs);
     RG_CUDA_OK(cudaGetLastError());
     return RG_OK;
 }
 
-int rg_launch_nthcomp(const SetRec *recs, const int2 *syslist, const int *sys_counter, int sys_cap,
-                      const double *p10tab, double *sc_gam, double *sc_g, double *sc_bet, size_t sc_stride,
-                      double *sptot, double *header, cudaStream_t st)
+int rg_launch_nthcomp(const SetRec *recs, const int2 *syslist, int nsys, const double *p10tab, double *sc_gam,
+                      double *sc_g, double *sc_bet, int n_threads, double *sptot, double *header,
+                      unsigned long long *stats, cudaStream_t st)
 {
-    // sized for the capacity: threads beyond the device-side counter exit immediately
-    nthcomp_kernel<<<(sys_cap + 127) / 128, 128, 0, st>>>(recs, syslist, sys_counter, sys_cap, p10tab, sc_gam, sc_g,
-                                                          sc_bet, sc_stride, sptot, header);
+    if (nsys <= 0) return RG_OK;
+    int blocks = (nsys + 127) / 128;
+    if (blocks * 128 > n_threads) blocks = n_threads / 128;
+    RG_LAUNCH(nthcomp_kernel, dim3(blocks), dim3(128), 0, st, recs, syslist, nsys, p10tab, sc_gam, sc_g, sc_bet,
+              blocks * 128, sptot, header, stats);
     RG_CUDA_OK(cudaGetLastError());
     return RG_OK;
 }

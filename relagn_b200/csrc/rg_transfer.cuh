@@ -71,9 +71,9 @@ __device__ inline RingRow rg_ring_row(const TabSel &ts, double rm)
 }
 
 // g and Jn at column p of the ring (blend of 4 nodes x 2 rows)
-__device__ inline void rg_ring_sample(const TabSel &ts, const RingRow &rr, int p, double &g, double &jn)
+__device__ inline void rg_ring_sample(const TabSel &ts, int s0, int s1, double fr, int p, double &g, double &jn)
 {
-    size_t i0 = (size_t)rr.s0 * ts.NPHI + p, i1 = (size_t)rr.s1 * ts.NPHI + p;
+    size_t i0 = (size_t)s0 * ts.NPHI + p, i1 = (size_t)s1 * ts.NPHI + p;
     double g0 = ts.w00 * __ldg(ts.n00 + i0) + ts.w01 * __ldg(ts.n01 + i0) + ts.w10 * __ldg(ts.n10 + i0) +
                 ts.w11 * __ldg(ts.n11 + i0);
     double g1 = ts.w00 * __ldg(ts.n00 + i1) + ts.w01 * __ldg(ts.n01 + i1) + ts.w10 * __ldg(ts.n10 + i1) +
@@ -83,14 +83,33 @@ __device__ inline void rg_ring_sample(const TabSel &ts, const RingRow &rr, int p
                 ts.w11 * __ldg(ts.n11 + q0);
     double j1 = ts.w00 * __ldg(ts.n00 + q1) + ts.w01 * __ldg(ts.n01 + q1) + ts.w10 * __ldg(ts.n10 + q1) +
                 ts.w11 * __ldg(ts.n11 + q1);
-    g = g0 + rr.fr * (g1 - g0);
-    jn = j0 + rr.fr * (j1 - j0);
+    g = g0 + fr * (g1 - g0);
+    jn = j0 + fr * (j1 - j0);
 }
 
 __device__ inline int rg_auto_nsub(double lnr, double dlnE)
 {
     int nsub = 1 + (int)floor(0.5 * lnr / dlnE);
     return nsub > 4096 ? 4096 : nsub;
+}
+
+// geometry of ring m of an annulus [r1, r2] cut into nsub rings (kerr_oracle.c: ro_ky_kernel)
+struct RingGeo { double A, fr; int s0, s1; };
+
+__device__ inline RingGeo rg_ring_geo(const TabSel &ts, double r1, double r2, double lnr, int m, int nsub,
+                                      double alpha, double beta, double rb)
+{
+    double ra = r1 * exp(lnr * m / nsub), rbb = r1 * exp(lnr * (m + 1) / nsub);
+    if (m == 0) ra = r1;
+    if (m == nsub - 1) rbb = r2;
+    double rm = sqrt(ra * rbb);
+    double emis = 1.0;
+    if (alpha != 0 || beta != 0) emis = rm < rb ? pow(rm, -alpha) : pow(rm, -beta) * pow(rb, beta - alpha);
+    RingGeo g;
+    g.A = 0.5 * (rbb * rbb - ra * ra) * emis;
+    RingRow rr = rg_ring_row(ts, rm);
+    g.s0 = rr.s0; g.s1 = rr.s1; g.fr = rr.fr;
+    return g;
 }
 
 // overlap of [lo,hi] with [L,R] weighted by the hat (1+y on [-1,0], 1-y on [0,1])
@@ -103,8 +122,10 @@ __device__ inline double rg_hat_piece(double lo, double hi, double L, double R, 
 }
 
 // deposit weight W spread uniformly over [sa,sb] onto H[k - K_LO] (shared-memory
-// histogram, atomics).  nH = capacity.
-__device__ inline void rg_deposit(double *H, int K_LO, int nH, double sa, double sb, double W)
+// histogram of nH bins, shared-memory atomics -- no global atomics anywhere).
+// kfirst/klast return the touched shift range.
+__device__ inline void rg_deposit(double *H, int K_LO, int nH, double sa, double sb, double W, int &kfirst,
+                                  int &klast)
 {
     double lo = sa < sb ? sa : sb, hi = sa < sb ? sb : sa;
     double len = hi - lo;
@@ -113,13 +134,14 @@ __device__ inline void rg_deposit(double *H, int K_LO, int nH, double sa, double
         double kf = floor(mid);
         double f = mid - kf;
         int i0 = (int)kf - K_LO;
+        kfirst = (int)kf; klast = (int)kf + 1;
         if (i0 >= 0 && i0 + 1 < nH) {
             atomicAdd(&H[i0], W * (1 - f));
             atomicAdd(&H[i0 + 1], W * f);
         }
         return;
     }
-    int kfirst = (int)floor(lo), klast = (int)floor(hi) + 1;
+    kfirst = (int)floor(lo); klast = (int)floor(hi) + 1;
     double inv = W / len;
     for (int k = kfirst; k <= klast; k++) {
         double c = rg_hat_piece(lo - k, hi - k, -1.0, 0.0, true) + rg_hat_piece(lo - k, hi - k, 0.0, 1.0, false);
