@@ -157,8 +157,7 @@ def test_full_size_properties_relqso_grid(ctx):
     # batch-order invariance, bit for bit
     perm = np.random.default_rng(0).permutation(p.shape[0])[:512]
     out2, _ = ctx.eval_batch_host(p[perm], model=1, rel=True, components=True)
-    np.testing.assert_array_equal(out2[:, :2], out[perm, :2])
-    np.testing.assert_allclose(out2[:, 2], out[perm, 2], rtol=1e-12)  # hot: shared-memory atomics order
+    np.testing.assert_allclose(out2, out[perm], rtol=1e-12)
     # non-relativistic disc luminosity = sum sigma T^4 4 pi r dr Rg^2 * cos i / 0.5 (relagn.py:878-889,1046,1058)
     outn, atn = ctx.eval_batch_host(p[::97], model=1, rel=False, components=True)
     nu = (grid[:-1] + 0.5 * np.diff(grid)) * 1.602176634e-16 / 6.62607015e-34
