@@ -37,7 +37,8 @@ def build(force=False, verbose=False):
         objs.append(o)
         if not force and os.path.exists(o) and all(os.path.getmtime(d) <= os.path.getmtime(o) for d in deps):
             continue
-        cmd = [cc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+        extra = os.environ.get("RG_NVCC_EXTRA", "").split()
+        cmd = [cc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
         procs.append((s, subprocess.Popen(cmd)))
     for s, p in procs:
         if p.wait() != 0:

@@ -47,6 +47,7 @@ struct rg_ctx {
     TabDesc td;
     float *d_tab = nullptr;
     double *d_tabmeta = nullptr;
+    double *d_rowrange = nullptr;
     size_t tab_floats = 0;
     std::vector<double> h_spins, h_thetas;
     // batch scratch
@@ -123,7 +124,7 @@ extern "C" void rg_ctx_destroy(rg_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    free_dev(c->d_grid); free_dev(c->d_tab); free_dev(c->d_tabmeta); free_dev(c->d_p10); free_dev(c->d_recs);
+    free_dev(c->d_grid); free_dev(c->d_tab); free_dev(c->d_tabmeta); free_dev(c->d_rowrange); free_dev(c->d_p10); free_dev(c->d_recs);
     free_dev(c->d_counter); free_dev(c->d_syslist); free_dev(c->d_sptot); free_dev(c->d_header); free_dev(c->d_sc);
     free_dev(c->d_rq); free_dev(c->d_kyH); free_dev(c->d_kyin); free_dev(c->d_kyout);
     free_dev(c->d_stage_par); free_dev(c->d_stage_out); free_dev(c->d_stage_attr); free_dev(c->d_stats);
@@ -232,10 +233,11 @@ extern "C" int rg_set_grid(rg_ctx *c, const double *eb, int nE)
     for (int j = 0; j < nE; j++)
         if (!(eb[j + 1] > eb[j]) || !(eb[j] > 0)) return rg_set_error(RG_E_ARG, "bin edges must be positive and ascending");
     RG_CUDA_OK(cudaSetDevice(c->device));
-    const int NA = 8; // arrays of nE
+    const int NA = 9; // arrays of nE
     std::vector<double> h((size_t)NA * nE + 3 * RG_NEXT, 0.0);
     double *Egrid = &h[0], *dE = &h[(size_t)nE], *nu = &h[(size_t)2 * nE], *hnu = &h[(size_t)3 * nE],
-           *bbpre = &h[(size_t)4 * nE], *wt = &h[(size_t)5 * nE], *e511 = &h[(size_t)6 * nE], *ear2 = &h[(size_t)7 * nE];
+           *bbpre = &h[(size_t)4 * nE], *wt = &h[(size_t)5 * nE], *e511 = &h[(size_t)6 * nE], *ear2 = &h[(size_t)7 * nE],
+           *lgE = &h[(size_t)8 * nE];
     double *x_hnu = &h[(size_t)NA * nE], *x_bbpre = x_hnu + RG_NEXT, *x_wt = x_bbpre + RG_NEXT;
     for (int j = 0; j < nE; j++) {
         dE[j] = eb[j + 1] - eb[j];
@@ -245,6 +247,7 @@ extern "C" int rg_set_grid(rg_ctx *c, const double *eb, int nE)
         bbpre[j] = (2 * RGK_H * (nu[j] * nu[j] * nu[j])) / (RGK_C * RGK_C);
         e511[j] = Egrid[j] / 511.0;
         ear2[j] = Egrid[j] * Egrid[j];
+        lgE[j] = log10(Egrid[j]);
     }
     int n_ext = Egrid[0] < 1e-4 ? RG_NEXT : 0; // relagn.py:868
     std::vector<double> xs; // abscissae of np.trapz: [extension, nu]
@@ -283,6 +286,7 @@ extern "C" int rg_set_grid(rg_ctx *c, const double *eb, int nE)
     double *d = c->d_grid;
     g.Egrid = d; g.dE = d + (size_t)nE; g.nu = d + (size_t)2 * nE; g.hnu = d + (size_t)3 * nE;
     g.bbpre = d + (size_t)4 * nE; g.wt = d + (size_t)5 * nE; g.e511 = d + (size_t)6 * nE; g.ear2 = d + (size_t)7 * nE;
+    g.lgE = d + (size_t)8 * nE;
     g.x_hnu = d + (size_t)NA * nE; g.x_bbpre = g.x_hnu + RG_NEXT; g.x_wt = g.x_bbpre + RG_NEXT;
     g.n_ext = n_ext; g.nE = nE; g.geometric = geometric; g.dlnE = dlnE;
     c->nE = nE;
@@ -304,8 +308,8 @@ static int tables_alloc(rg_ctx *c, const double *spins, int n_spin, const double
     for (int i = 1; i < n_inc; i++)
         if (!(thetas[i] > thetas[i - 1])) return rg_set_error(RG_E_ARG, "tables: inclinations must ascend");
     RG_CUDA_OK(cudaSetDevice(c->device));
-    free_dev(c->d_tab); free_dev(c->d_tabmeta);
-    c->d_tab = nullptr; c->d_tabmeta = nullptr; c->have_tab = false;
+    free_dev(c->d_tab); free_dev(c->d_tabmeta); free_dev(c->d_rowrange);
+    c->d_tab = nullptr; c->d_tabmeta = nullptr; c->d_rowrange = nullptr; c->have_tab = false;
     c->tab_floats = (size_t)n_spin * n_inc * 2 * NR * NPHI;
     RG_CUDA_OK(cudaMalloc(&c->d_tab, c->tab_floats * sizeof(float)));
     std::vector<double> meta(2 * n_spin + n_inc);
@@ -333,14 +337,26 @@ static int tables_finish(rg_ctx *c, const float *host_data)
     size_t plane = (size_t)c->td.NR * c->td.NPHI;
     size_t nodes = (size_t)c->td.n_spin * c->td.n_inc;
     double gmin = 1e300, gmax = 0;
+    const int NR = c->td.NR, NP = c->td.NPHI;
+    std::vector<double> rr(nodes * NR * 2);
     for (size_t n = 0; n < nodes; n++) {
         const float *g = host_data + n * 2 * plane;
-        for (size_t i = 0; i < plane; i++) {
-            double v = g[i];
-            if (!(v > 0) || !(v < 1e30)) return rg_set_error(RG_E_ARG, "tables: non-positive or non-finite g in node %zu", n);
-            gmin = std::min(gmin, v); gmax = std::max(gmax, v);
+        for (int s = 0; s < NR; s++) {
+            double lo = 1e300, hi = 0;
+            for (int p = 0; p < NP; p++) {
+                double v = g[(size_t)s * NP + p];
+                if (!(v > 0) || !(v < 1e30))
+                    return rg_set_error(RG_E_ARG, "tables: non-positive or non-finite g in node %zu", n);
+                lo = std::min(lo, v); hi = std::max(hi, v);
+            }
+            rr[(n * NR + s) * 2] = log(lo);
+            rr[(n * NR + s) * 2 + 1] = log(hi);
+            gmin = std::min(gmin, lo); gmax = std::max(gmax, hi);
         }
     }
+    RG_CUDA_OK(cudaMalloc(&c->d_rowrange, rr.size() * sizeof(double)));
+    RG_CUDA_OK(cudaMemcpy(c->d_rowrange, rr.data(), rr.size() * sizeof(double), cudaMemcpyHostToDevice));
+    c->td.rowrange = c->d_rowrange;
     c->td.lng_min = log(gmin);
     c->td.lng_max = log(gmax);
     c->have_tab = true;
@@ -534,8 +550,9 @@ extern "C" int rg_eval_batch(rg_ctx *c, const double *d_params, int P, int model
         A.nH = K_HI - K_LO + 1;
         A.HL = std::max(K_HI, 0) / M + 3;
         A.HH = std::max(-K_LO, 0) / M + 3;
+        A.arena = std::max(2048, A.nH + 3 * M + 8);
     } else {
-        A.K_LO = 0; A.nH = 1; A.HL = 1; A.HH = 1;
+        A.K_LO = 0; A.nH = 1; A.HL = 1; A.HH = 1; A.arena = 64;
     }
 
     int p0 = 0, chunk = c->chunk_sets;

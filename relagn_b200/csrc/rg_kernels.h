@@ -14,6 +14,7 @@ struct TabDesc {
     int n_spin, n_inc, NR, NPHI;
     double dl;
     double lng_min, lng_max; // range of ln g over all nodes (sizes the shift histogram)
+    const double *rowrange;  // [n_spin*n_inc][NR][2]: min / max of ln g over the columns of each table row
 };
 
 // energy grid resident on the device (all [nE] unless noted; built by rg_set_grid)
@@ -26,6 +27,7 @@ struct GridDesc {
     const double *wt;    // trapezoid weights of np.trapz(., nu) on this grid (with the extension joint when n_ext)
     const double *e511;  // Egrid / 511                                pyNTHCOMP.py:70
     const double *ear2;  // Egrid^2                                    pyNTHCOMP.py:75
+    const double *lgE;   // log10(Egrid): seeds the Kompaneets-grid cursor search
     // low-frequency extension of disc_annuli (relagn.py:868-873), [RG_NEXT] when n_ext
     const double *x_hnu, *x_bbpre, *x_wt;
     int n_ext;
@@ -44,12 +46,13 @@ struct SpecArgs {
     const double *sptot;  // [sys][RG_SPT_STRIDE]
     const double *header; // [sys][4] = xmin, normfac, jmax, kTbb
     double *out;          // [P][nE] or [P][4][nE]
-    int K_LO, nH;         // shift-histogram support: k in [K_LO, K_LO + nH)
-    int HL, HH;           // zero halo rows of the transposed local-spectrum buffer
+    int K_LO, nH;         // widest shift-histogram support over all table nodes: k in [K_LO, K_LO + nH)
+    int HL, HH;           // zero halo columns of the transposed local-spectrum buffer
+    int arena;            // doubles in the per-CTA histogram arena
     unsigned long long *stats; // optional device counters [4]: sum W_ann, conv annuli, sum jmax, systems
 };
 
-size_t rg_spectrum_smem_bytes(int M, int nH, int HL, int HH);
+size_t rg_spectrum_smem_bytes(int M, int nH, int HL, int HH, int arena);
 int rg_spectrum_pick_M(int nE); // 4, 8 or 20; 0 if nE is too large
 
 int rg_launch_setup(const double *d_params, int P, int model, double dr_dex, SetRec *recs, int *sys_counter,

@@ -218,7 +218,7 @@ setup_kernel(const double *__restrict__ params, int P, int model, double dr_dex,
 //   scratch planes gam, g, bet: [RG_NTH][n_threads], indexed by the launching
 //   thread (not the system) so the footprint is bounded by the resident
 //   threads; a warp's accesses to one j are contiguous.
-//   sptot arena: [sys][RG_SPT_STRIDE];  header: [sys][4] = xmin, normfac, jmax, kTbb
+//   sptot arena: [sys][RG_SPT_STRIDE];  header: [sys][4] = xmin, normfac, jmax, log10(511 xmin)
 __device__ static void nthcomp_system(const SetRec &r, int which, const double *__restrict__ p10tab,
                                       double *__restrict__ sc_gam, double *__restrict__ sc_g,
                                       double *__restrict__ sc_bet, size_t sc_stride, int slot, double *__restrict__ spt,
@@ -248,7 +248,7 @@ __device__ static void nthcomp_system(const SetRec &r, int which, const double *
     int jmax = (int)(log10(xmax / xmin) / delta) + 1;
     if (jmax > 899) jmax = 899;
     if (jmax < 4) { // degenerate grid: the reference would index out of range; flag as empty
-        hd[0] = xmin; hd[1] = 0.0; hd[2] = 0.0; hd[3] = 0.0;
+        hd[0] = xmin; hd[1] = 0.0; hd[2] = 0.0; hd[3] = log10(511.0 * xmin);
         return;
     }
     int jmaxth = (int)(log10(50 * tempbb / xmin) / delta);
@@ -350,7 +350,7 @@ __device__ static void nthcomp_system(const SetRec &r, int which, const double *
     int il = ih - 1;
     double xl = xmin * p10tab[il], xh = xmin * p10tab[ih];
     double spp = spt[il] + (spt[ih] - spt[il]) * (xx - xl) / (xh - xl);
-    hd[0] = xmin; hd[1] = 1.0 / spp; hd[2] = (double)jmax; hd[3] = ktbb;
+    hd[0] = xmin; hd[1] = 1.0 / spp; hd[2] = (double)jmax; hd[3] = log10(511.0 * xmin);
 }
 
 __global__ void __launch_bounds__(128)

@@ -94,6 +94,20 @@ unsigned warp_ballot(int pred)
     return r;
 }
 
+unsigned warp_gather(uint64_t v, uint64_t *out32)
+{
+    Warp &w = warps[cur / 32];
+    int lane = cur & 31;
+    if (w.arrive == 0) w.ballot = 0;
+    w.buf[lane] = v;
+    w.ballot |= 1u << lane;
+    warp_barrier(w);
+    unsigned live = w.ballot;
+    for (int l = 0; l < 32; l++) out32[l] = w.buf[l];
+    warp_barrier(w);
+    return live;
+}
+
 void *dyn_smem() { return dsm.data(); }
 long launches() { return n_launch; }
 

@@ -60,6 +60,7 @@ void *dyn_smem();
 void sync_block();
 uint64_t warp_exchange(uint64_t v, int src_lane); // value of lane src_lane (own value if out of range)
 unsigned warp_ballot(int pred);
+unsigned warp_gather(uint64_t v, uint64_t *out32); // every live lane's value; returns the live-lane mask
 long launches();
 }
 
@@ -108,6 +109,33 @@ template <class T> static inline T __shfl_up_sync(unsigned, T v, unsigned d, int
 static inline unsigned __ballot_sync(unsigned, int p) { return hostsim::warp_ballot(p); }
 static inline int __any_sync(unsigned, int p) { return hostsim::warp_ballot(p) != 0; }
 static inline int __all_sync(unsigned, int p) { return hostsim::warp_ballot(!p) == 0; }
+template <class T> static inline unsigned __match_any_sync(unsigned, T v)
+{
+    uint64_t u = 0, all[32];
+    memcpy(&u, &v, sizeof(T));
+    unsigned live = hostsim::warp_gather(u, all), m = 0;
+    for (int l = 0; l < 32; l++)
+        if (((live >> l) & 1) && all[l] == u) m |= 1u << l;
+    return m;
+}
+static inline int __reduce_max_sync(unsigned, int v)
+{
+    uint64_t all[32];
+    unsigned live = hostsim::warp_gather((uint64_t)(int64_t)v, all);
+    int r = v;
+    for (int l = 0; l < 32; l++)
+        if ((live >> l) & 1) { int x = (int)(int64_t)all[l]; if (x > r) r = x; }
+    return r;
+}
+static inline int __reduce_min_sync(unsigned, int v)
+{
+    uint64_t all[32];
+    unsigned live = hostsim::warp_gather((uint64_t)(int64_t)v, all);
+    int r = v;
+    for (int l = 0; l < 32; l++)
+        if ((live >> l) & 1) { int x = (int)(int64_t)all[l]; if (x < r) r = x; }
+    return r;
+}
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }

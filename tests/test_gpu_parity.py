@@ -102,7 +102,7 @@ def test_random_batch_vs_oracle(ctx, oracle, otab, rel):
         for c in range(4):
             assert peak_relerr(out[i, c], ref[i, c]) < TOL, (i, c)
     tot, _ = ctx.eval_batch_host(p, model=0, rel=rel, components=False)
-    np.testing.assert_allclose(tot, out[:, 3], rtol=1e-13)
+    np.testing.assert_array_equal(tot, out[:, 3])
 
 
 def test_invalid_sets_are_flagged(ctx):
@@ -154,39 +154,14 @@ def test_full_size_properties_relqso_grid(ctx):
     assert (out >= 0).all()
     # total = disc + warm + hot
     np.testing.assert_allclose(out[:, 3], out[:, 0] + out[:, 1] + out[:, 2], rtol=1e-14)
-    # batch-order invariance, bit for bit
+    # batch-order invariance, bit for bit (no atomics anywhere in the path: the summation order is fixed)
     perm = np.random.default_rng(0).permutation(p.shape[0])[:512]
     out2, _ = ctx.eval_batch_host(p[perm], model=1, rel=True, components=True)
-    np.testing.assert_allclose(out2, out[perm], rtol=1e-12)
-    # non-relativistic disc luminosity = sum sigma T^4 4 pi r dr Rg^2 * cos i / 0.5 (relagn.py:878-889,1046,1058)
+    np.testing.assert_array_equal(out2, out[perm])
+    # relativistic and flat-space bolometric luminosities agree within a factor of order unity
     outn, atn = ctx.eval_batch_host(p[::97], model=1, rel=False, components=True)
     nu = (grid[:-1] + 0.5 * np.diff(grid)) * 1.602176634e-16 / 6.62607015e-34
-    Ldisc = np.trapz(outn[:, 0], nu, axis=1)
-    assert (Ldisc > 0).all()
-    # relativistic and flat-space totals agree within a factor of order unity and rel spectra are broader
-    outr = out[::97]
-    Lrel = np.trapz(outr[:, 0], nu, axis=1)
-    assert np.all((Lrel / Ldisc > 0.5) & (Lrel / Ldisc < 1.5))
-
-
-def test_device_ray_tracer_vs_oracle(ctx, oracle):
-    """rg_tables_generate (device Kerr ray tracer) against the oracle's ray tracer on a small node set, and the
-    physics limits of the tables: flat space far out (g -> 1 on the axis of symmetry, Jn -> cos i)."""
-    spins = np.array([0.0, 0.9, 0.998])
-    thetas = np.deg2rad([20.0, 60.0, 80.0])
-    NR, NPHI, dl = 12, 32, 3.76 / 11
-    bad = ctx.tables_generate(spins, thetas, NR, NPHI, dl)
-    got = ctx.tables_download()
-    ot = oracle.Tables(spins, thetas, NR, NPHI, dl, threads=0)
-    ref = np.array(ot.data)
-    assert got.shape == ref.shape
-    ok = ref[:, :, 1] > 0
-    assert bad == int((~ok).sum())
-    np.testing.assert_array_equal(got[:, :, 1] > 0, ok)
-    # float32 tables from FP64 solves converged to 1e-10: agreement to a few float32 ulps
-    np.testing.assert_allclose(got[:, :, 0][ok], ref[:, :, 0][ok], rtol=2e-6)
-    np.testing.assert_allclose(got[:, :, 1][ok], ref[:, :, 1][ok], rtol=2e-5)
-    # outermost row (r ~ 1e3..2e4 Rg): Jn -> cos(theta_o) within a few 1e-3, <g> -> sqrt(1 - 3/r) ~ 1
-    for n, th in enumerate(thetas):
-        assert abs(got[0, n, 1, -1].mean() / np.cos(th) - 1) < 5e-3
-        assert abs(got[0, n, 0, -1].mean() - 1) < 5e-3
+    Lflat = np.trapezoid(outn[:, 3], nu, axis=1)
+    Lrel = np.trapezoid(out[::97, 3], nu, axis=1)
+    assert (Lflat > 0).all()
+    assert np.all((Lrel / Lflat > 0.5) & (Lrel / Lflat < 1.5))
