@@ -63,6 +63,9 @@ struct rg_ctx {
     int nth_threads = 0;
     double *d_rq = nullptr;
     int rq_cap = 0;
+    int *d_queue = nullptr;
+    double *d_partial = nullptr;
+    size_t partial_n = 0;
     // kyconv seam scratch
     double *d_kyH = nullptr, *d_kyin = nullptr, *d_kyout = nullptr;
     int ky_cap = 0, kyH_cap = 0;
@@ -126,7 +129,7 @@ extern "C" void rg_ctx_destroy(rg_ctx *c)
     cudaDeviceSynchronize();
     free_dev(c->d_grid); free_dev(c->d_tab); free_dev(c->d_tabmeta); free_dev(c->d_rowrange); free_dev(c->d_p10); free_dev(c->d_recs);
     free_dev(c->d_counter); free_dev(c->d_syslist); free_dev(c->d_sptot); free_dev(c->d_header); free_dev(c->d_sc);
-    free_dev(c->d_rq); free_dev(c->d_kyH); free_dev(c->d_kyin); free_dev(c->d_kyout);
+    free_dev(c->d_rq); free_dev(c->d_queue); free_dev(c->d_partial); free_dev(c->d_kyH); free_dev(c->d_kyin); free_dev(c->d_kyout);
     free_dev(c->d_stage_par); free_dev(c->d_stage_out); free_dev(c->d_stage_attr); free_dev(c->d_stats);
     prof_collect(c);
     if (c->h_counter) cudaFreeHost(c->h_counter);
@@ -229,7 +232,7 @@ extern "C" int rg_get_stat(rg_ctx *c, int key, double *value)
 extern "C" int rg_set_grid(rg_ctx *c, const double *eb, int nE)
 {
     if (!c || !eb || nE < 2) return rg_set_error(RG_E_ARG, "rg_set_grid: bad arguments");
-    if (rg_spectrum_pick_M(nE) == 0) return rg_set_error(RG_E_GRID, "nE = %d exceeds the kernel capacity", nE);
+    if (rg_spectrum_pick_NC(nE) == 0) return rg_set_error(RG_E_GRID, "nE = %d exceeds the kernel capacity", nE);
     for (int j = 0; j < nE; j++)
         if (!(eb[j + 1] > eb[j]) || !(eb[j] > 0)) return rg_set_error(RG_E_ARG, "bin edges must be positive and ascending");
     RG_CUDA_OK(cudaSetDevice(c->device));
@@ -505,6 +508,7 @@ static int ensure_batch_scratch(rg_ctx *c, int model)
         RG_CUDA_OK(cudaMalloc(&c->d_sptot, (size_t)c->sys_cap * RG_SPT_STRIDE * sizeof(double)));
         RG_CUDA_OK(cudaMalloc(&c->d_header, (size_t)c->sys_cap * 4 * sizeof(double)));
         RG_CUDA_OK(cudaMalloc(&c->d_sc, (size_t)3 * RG_NTH * c->nth_threads * sizeof(double)));
+        RG_CUDA_OK(cudaMalloc(&c->d_queue, 2 * sizeof(int)));
     }
     if (model == RG_MODEL_RELQSO && !c->d_rq) {
         c->rq_cap = 4608; // fine radial grid of _set_rhot: 1000/dex over <= 4.6 dex
@@ -529,7 +533,7 @@ extern "C" int rg_eval_batch(rg_ctx *c, const double *d_params, int P, int model
     RG_TRY(ensure_batch_scratch(c, model));
     cudaStream_t st = (cudaStream_t)stream;
     const int nE = c->nE;
-    const int M = rg_spectrum_pick_M(nE);
+    const int NC = rg_spectrum_pick_NC(nE);
     const int ncomp = (flags & RG_FLAG_COMPONENTS) ? 4 : 1;
 
     SpecArgs A;
@@ -539,6 +543,7 @@ extern "C" int rg_eval_batch(rg_ctx *c, const double *d_params, int P, int model
     A.p10tab = c->d_p10;
     A.sptot = c->d_sptot;
     A.header = c->d_header;
+    A.queue = c->d_queue;
     if (rel) {
         A.tab = c->td;
         int kl, kh;
@@ -548,11 +553,29 @@ extern "C" int rg_eval_batch(rg_ctx *c, const double *d_params, int P, int model
         K_HI = std::min(K_HI, kh);
         A.K_LO = K_LO;
         A.nH = K_HI - K_LO + 1;
-        A.HL = std::max(K_HI, 0) / M + 3;
-        A.HH = std::max(-K_LO, 0) / M + 3;
-        A.arena = std::max(2048, A.nH + 3 * M + 8);
+        A.HL = std::max(K_HI, 0) / 8 + 3;
+        A.HH = std::max(-K_LO, 0) / 8 + 3;
     } else {
-        A.K_LO = 0; A.nH = 1; A.HL = 1; A.HH = 1; A.arena = 64;
+        A.K_LO = 0; A.nH = 1; A.HL = 1; A.HH = 1;
+    }
+    A.warps = rg_spectrum_pick_warps(NC, A.nH, A.HL, A.HH);
+    if (A.warps < 1) return rg_set_error(RG_E_GRID, "energy grid too fine for the shared-memory working set");
+    // small batches: split every set's annuli over several warps (partials are folded in block order)
+    {
+        long total_warps = (long)c->sm_count * A.warps;
+        int NB = 1;
+        if ((long)P < 2 * total_warps) NB = (int)std::min<long>(16, (2 * total_warps + P - 1) / P);
+        A.NB = NB;
+        if (NB > 1) {
+            size_t need = (size_t)std::min(P, c->chunk_sets) * NB * (ncomp == 4 ? 3 : 1) * nE;
+            if (need > c->partial_n) {
+                free_dev(c->d_partial);
+                c->d_partial = nullptr; c->partial_n = 0;
+                RG_CUDA_OK(cudaMalloc(&c->d_partial, need * sizeof(double)));
+                c->partial_n = need;
+            }
+            A.partial = c->d_partial;
+        }
     }
 
     int p0 = 0, chunk = c->chunk_sets;
@@ -588,7 +611,7 @@ extern "C" int rg_eval_batch(rg_ctx *c, const double *d_params, int P, int model
         A.out = d_out + (size_t)p0 * ncomp * nE;
         A.stats = stats;
         RG_TRY(prof_begin(c, 2, st));
-        RG_TRY(rg_launch_spectrum(A, st));
+        RG_TRY(rg_launch_spectrum(A, c->sm_count, st));
         RG_TRY(prof_end(c, 2, st));
         c->launches++;
         c->n_sets += n;

@@ -44,16 +44,21 @@ struct SpecArgs {
     unsigned flags;
     const double *p10tab; // [RG_NTH+1] 10^(0.02 j)
     const double *sptot;  // [sys][RG_SPT_STRIDE]
-    const double *header; // [sys][4] = xmin, normfac, jmax, kTbb
+    const double *header; // [sys][4] = xmin, normfac, jmax, log10(511 xmin)
     double *out;          // [P][nE] or [P][4][nE]
     int K_LO, nH;         // widest shift-histogram support over all table nodes: k in [K_LO, K_LO + nH)
     int HL, HH;           // zero halo columns of the transposed local-spectrum buffer
-    int arena;            // doubles in the per-CTA histogram arena
+    int NB;               // annulus blocks per parameter set (work items = P * NB)
+    double *partial;      // NB > 1: [P][NB][ncomp][nE] partial sums, folded by the reduce kernel
+    int *queue;           // device work-queue counter (zeroed before the launch)
+    int warps;            // warps per CTA
     unsigned long long *stats; // optional device counters [4]: sum W_ann, conv annuli, sum jmax, systems
 };
 
-size_t rg_spectrum_smem_bytes(int M, int nH, int HL, int HH, int arena);
-int rg_spectrum_pick_M(int nE); // 4, 8 or 20; 0 if nE is too large
+int rg_spectrum_pick_NC(int nE); // 256-bin chunks per warp pass: 4, 8 or 20; 0 if nE is too large
+// shared memory per CTA and the number of warps per CTA that fit (0: does not fit at all)
+size_t rg_spectrum_smem_bytes(int NC, int nH, int HL, int HH, int warps);
+int rg_spectrum_pick_warps(int NC, int nH, int HL, int HH);
 
 int rg_launch_setup(const double *d_params, int P, int model, double dr_dex, SetRec *recs, int *sys_counter,
                     int2 *syslist, int sys_cap, double *rq_scratch, int rq_cap, double *d_attrs, cudaStream_t st);
@@ -63,7 +68,7 @@ int rg_launch_nthcomp(const SetRec *recs, const int2 *syslist, int nsys, const d
                       double *sc_g, double *sc_bet, int n_threads, double *sptot, double *header,
                       unsigned long long *stats, cudaStream_t st);
 
-int rg_launch_spectrum(const SpecArgs &args, cudaStream_t st);
+int rg_launch_spectrum(const SpecArgs &args, int sm_count, cudaStream_t st);
 
 // generic kyconv seam: histogram of one (possibly wide) annulus into d_H[0..nH) (shift k = K_LO + index)
 int rg_launch_ky_hist(const TabDesc &tab, double a, double theta_o, double r1, double r2, double alpha, double beta,

@@ -1,8 +1,9 @@
-// rg_spectrum.cu -- the fused spectrum kernel: one CTA per parameter set walks
-// the set's annuli (disc, warm, hot), builds every local spectrum in registers,
-// pushes it through the relativistic transfer and accumulates the observed
-// spectrum, without touching HBM between the parameter record and the final
-// [nE] store.
+// rg_spectrum.cu -- the fused spectrum kernel.  Every WARP is an autonomous
+// worker: it pulls a (parameter set, annulus block) item from a device queue,
+// walks the annuli of that item (disc, warm, hot), builds every local spectrum
+// in registers, pushes it through the relativistic transfer and accumulates the
+// observed spectrum in registers, without touching HBM between the parameter
+// record and the final [nE] store and without a block barrier after start-up.
 //
 // Reference path restated (src/python_version/relagn.py):
 //   disc_annuli :839-896, warmComp_annuli :900-939, hotComp_annuli :1295-1318,
@@ -12,55 +13,61 @@
 //   caller's grid); the kyconv seam (:979-1001) as discretised in
 //   rg_transfer.cuh.
 //
-// Work layout.  RG_SPEC_THREADS threads (8 warps); thread t owns the M
-// consecutive energy bins j = M t + c; per-bin grid constants and accumulators
-// live in registers for the whole set.  Annuli are handled in groups:
-//
-//  phase H  one WARP per annulus builds that annulus' g-shift histogram H[k]
-//           from the Kerr table slice (4 nodes x 2 rows blended): lanes sample
-//           the ring azimuths, neighbouring samples form segments, and every
-//           segment's weight is deposited with a warp-shuffle segmented
-//           reduction keyed by the shift bin (runs of equal keys are summed by
-//           a segmented scan, the run tail owns the bin) -- no atomics, global
-//           or shared, and a summation order that does not depend on timing.
-//           Histograms of a group sit in a shared-memory arena.
-//  stream   per annulus, ONE block barrier: every thread evaluates its M bins
-//           of the local spectrum, publishes them (transposed, zero halos) and
-//           its share of the nu-integral; after the barrier the normalisation
-//           is known and out_j += scale * sum_k H[k] in[j-k] runs as a sliding
-//           register window: per tap one conflict-free shared load feeds M
-//           FMAs, H[k] is a broadcast load.  Double-buffered so the next
-//           annulus can be written while stragglers still read.
-//  hot      all hot annuli share one spectral shape, so their histograms are
-//           summed (weighted by annulus luminosity) and ONE convolution is done.
+// Work layout per warp.  The energy grid is cut into NC chunks of 256 bins;
+// in chunk ch lane l owns the 8 consecutive bins j = 8 (32 ch + l) + c.  A
+// chunk is the unit of skipping (Wien tails past the FP64 overflow point are
+// neither evaluated nor convolved) and gives every lane 8 independent
+// exp / divide / FMA chains.  Per annulus:
+//   1. the g-shift histogram H[k] of the annulus is built from the Kerr table
+//      slice (4 nodes x 2 rows blended): lanes sample the ring azimuths,
+//      neighbouring samples form segments, and every segment's weight is
+//      deposited with a warp-shuffle segmented reduction keyed by the shift bin
+//      -- no atomics, fixed summation order;
+//   2. the local spectrum (Planck / Kompaneets interpolation) is evaluated chunk
+//      by chunk in registers, written to the warp's shared-memory buffer in
+//      transposed form (row j mod 8, column j div 8, zero halos) together with
+//      the warp-reduced nu-integral;
+//   3. out_j += scale * sum_k H[k] in[j-k] runs per chunk as a sliding register
+//      window: one conflict-free shared load + one broadcast load feed 8 FMAs.
+// The hot region uses linearity: all hot annuli share one spectral shape, so
+// their histograms are summed (weighted by annulus luminosity) and ONE
+// convolution is done for the region.
 #include "rg_kernels.h"
 #include "rg_transfer.cuh"
 
-#define T_ RG_SPEC_THREADS
-#define NWARP (RG_SPEC_THREADS / 32)
 #define FULL 0xffffffffu
 #define IMAX 0x7fffffff
+#define NGRID 5 // per-bin constant arrays staged in shared memory: hnu, bbpre, wt, pk, upk
 
 static __host__ __device__ inline int round_up2(int x) { return (x + 1) & ~1; }
 
-size_t rg_spectrum_smem_bytes(int M, int nH, int HL, int HH, int arena)
+int rg_spectrum_pick_NC(int nE)
 {
-    size_t d = 0;
-    d += 2 * (size_t)M * (HL + T_ + HH);    // inT, double-buffered
-    d += (size_t)round_up2(arena);          // histogram arena
-    d += (size_t)round_up2(nH + 3 * M + 4); // hot-region summed histogram
-    d += 2 * RG_SPT_STRIDE;                 // staged Kompaneets solutions, double-buffered
-    d += 2 * NWARP;                         // reduction scratch, double-buffered
-    d += 5 * T_;                            // annulus tile scalars
-    d += 8;                                 // set scalars
-    return d * sizeof(double) + (4 * T_ + 16) * sizeof(int);
+    if (nE <= 4 * 256) return 4;
+    if (nE <= 8 * 256) return 8;
+    if (nE <= 20 * 256) return 20;
+    return 0;
 }
 
-int rg_spectrum_pick_M(int nE)
+static size_t warp_smem_doubles(int NC, int nH, int HL, int HH)
 {
-    if (nE <= 4 * T_) return 4;
-    if (nE <= 8 * T_) return 8;
-    if (nE <= 20 * T_) return 20;
+    size_t d = 8 * (size_t)(HL + 32 * NC + HH); // inT
+    d += 2 * (size_t)round_up2(nH + 24);        // H slot + hot-region sum
+    if (NC > 4) d += 8 * (size_t)32 * NC;       // accumulators (registers when NC <= 4)
+    return d;
+}
+
+size_t rg_spectrum_smem_bytes(int NC, int nH, int HL, int HH, int warps)
+{
+    size_t d = warp_smem_doubles(NC, nH, HL, HH) * warps;
+    if (NC <= 8) d += NGRID * 8 * (size_t)32 * NC; // grid constants (global memory for the finest grids)
+    return d * sizeof(double);
+}
+
+int rg_spectrum_pick_warps(int NC, int nH, int HL, int HH)
+{
+    for (int w = 8; w >= 1; w--)
+        if (rg_spectrum_smem_bytes(NC, nH, HL, HH, w) <= 225 * 1024) return w;
     return 0;
 }
 
@@ -73,50 +80,20 @@ __device__ inline double warp_sum(double v)
 
 // pyNTHCOMP.py:62-73: value of the Kompaneets solution at photon energy e (keV);
 // the reference's monotone cursor restated as a direct search seeded from log10(e).
-__device__ inline double nth_prim(const double *spt, const double *__restrict__ p10, double xmin, double lg511xmin,
-                                  int nth, double e, double e511, double lge)
+__device__ inline double nth_prim(const double *__restrict__ spt, const double *__restrict__ p10, double xmin,
+                                  double lg511xmin, int nth, double e, double e511, double lge)
 {
     int j = (int)ceil((lge - lg511xmin) * 50.0);
     if (j < 0) j = 0;
     if (j > nth + 1) j = nth + 1;
-    while (j > 0 && !(511.0 * (xmin * p10[j - 1]) < e)) j--;
-    while (j <= nth && 511.0 * (xmin * p10[j]) < e) j++;
+    while (j > 0 && !(511.0 * (xmin * __ldg(p10 + j - 1)) < e)) j--;
+    while (j <= nth && 511.0 * (xmin * __ldg(p10 + j)) < e) j++;
     if (j > nth) return 0.0;
-    if (j == 0) return spt[0];
+    if (j == 0) return __ldg(spt);
     int jl = j - 1;
-    double xl = xmin * p10[jl], xh = xmin * p10[jl + 1];
-    return spt[jl] + ((e511 - xl) * (spt[jl + 1] - spt[jl]) / (xh - xl));
-}
-
-struct Smem {
-    double *inT, *arena, *Hsum, *spt, *red, *aR1, *aR2, *aS1, *aS2, *aGeo, *setd;
-    int *aFlag, *aKmin, *aKmax, *aJz, *seti;
-    int RS, inStride;
-};
-
-template <int M>
-__device__ inline void carve(Smem &s, unsigned char *raw, int nH, int HL, int HH, int arena)
-{
-    double *d = reinterpret_cast<double *>(raw);
-    s.RS = HL + T_ + HH;
-    s.inStride = M * s.RS;
-    s.inT = d; d += 2 * (size_t)s.inStride;
-    s.arena = d; d += round_up2(arena);
-    s.Hsum = d; d += round_up2(nH + 3 * M + 4);
-    s.spt = d; d += 2 * RG_SPT_STRIDE;
-    s.red = d; d += 2 * NWARP;
-    s.aR1 = d; d += T_;
-    s.aR2 = d; d += T_;
-    s.aS1 = d; d += T_;
-    s.aS2 = d; d += T_;
-    s.aGeo = d; d += T_;
-    s.setd = d; d += 8;
-    int *i = reinterpret_cast<int *>(d);
-    s.aFlag = i; i += T_;
-    s.aKmin = i; i += T_;
-    s.aKmax = i; i += T_;
-    s.aJz = i; i += T_;
-    s.seti = i;
+    double xl = xmin * __ldg(p10 + jl), xh = xmin * __ldg(p10 + jl + 1);
+    double sl = __ldg(spt + jl), sh = __ldg(spt + jl + 1);
+    return sl + ((e511 - xl) * (sh - sl) / (xh - xl));
 }
 
 // ---------------------------------------------------------------------------
@@ -236,95 +213,226 @@ __device__ inline void warp_build_hist(double *Hs, int K_LO, int nH, const TabSe
     kmax_out = __reduce_max_sync(FULL, kl_max);
 }
 
-// tmp[c] = sum_k H[k] in[M t + c - k], k in [kmin, kmax]; Hs0 points at shift K_LO of a slot that is
-// zero-padded M in front and 2M behind; base = inT + HL + tid of the buffer to read.
-template <int M>
-__device__ inline void convolve(const double *Hs0, int K_LO, int nH, int kmin, int kmax, const double *base, int RS,
-                                double (&tmp)[M])
+// tmp[c] = sum_k H[k] in[8 col + c - k] for k in [kmin, kmax]; Hs0 points at shift K_LO of a histogram that is
+// zero-padded 8 in front and 16 behind; base = row 0 of the warp's buffer at this lane's column, RS = row stride.
+__device__ inline void convolve8(const double *Hs0, int K_LO, int nH, int kmin, int kmax, const double *base, int RS,
+                                 double (&tmp)[8])
 {
 #pragma unroll
-    for (int c = 0; c < M; c++) tmp[c] = 0.0;
+    for (int c = 0; c < 8; c++) tmp[c] = 0.0;
     if (kmin < K_LO) kmin = K_LO;
     if (kmax > K_LO + nH - 1) kmax = K_LO + nH - 1;
     if (kmin > kmax) return;
-    const int g = (kmin >= 0) ? kmin / M : -((-kmin + M - 1) / M); // floor(kmin / M)
-    const int k0 = g * M;
+    const int g = (kmin >= 0) ? (kmin >> 3) : -((-kmin + 7) >> 3); // floor(kmin / 8)
+    const int k0 = g * 8;
     const double *Hk = Hs0 + (k0 - K_LO);
-    double w[M];
+    double w[8];
 #pragma unroll
-    for (int c = 0; c < M; c++) w[c] = base[c * RS - g];
+    for (int c = 0; c < 8; c++) w[c] = base[c * RS - g];
     const double *pg = base - g - 1;
-    for (int k = k0; k <= kmax; k += M) {
+    for (int k = k0; k <= kmax; k += 8) {
 #pragma unroll
-        for (int u = 0; u < M; u++) {
+        for (int u = 0; u < 8; u++) {
             const double h = Hk[u];
 #pragma unroll
-            for (int c = 0; c < M; c++) tmp[c] = fma(h, w[(c - u + M) % M], tmp[c]);
-            // next tap needs in[M t - (k+u+1)]: row (M-u-1) % M, column t - g - 1
-            w[(M - 1 - u) % M] = pg[((M - u - 1) % M) * RS];
+            for (int c = 0; c < 8; c++) tmp[c] = fma(h, w[(c - u + 8) % 8], tmp[c]);
+            // next tap needs in[8 col - (k+u+1)]: row 7-u, column col - g - 1
+            w[(7 - u) % 8] = pg[((7 - u) % 8) * RS];
         }
-        Hk += M;
+        Hk += 8;
         pg -= 1;
     }
 }
 
-#ifndef RG_SPEC_MIN_CTAS
-#define RG_SPEC_MIN_CTAS 2
-#endif
-template <int M>
-__global__ void __launch_bounds__(RG_SPEC_THREADS, (M <= 4 ? RG_SPEC_MIN_CTAS : 1)) spectrum_kernel(SpecArgs A)
+// per-bin constants: shared memory (transposed [row c][column]) or global memory for the finest grids
+template <int NC, bool GS>
+struct GridAcc {
+    const double *sm;  // [NGRID][8][32 NC]
+    const GridDesc *g;
+    __device__ inline double hnu(int c, int col) const
+    {
+        if (GS) return sm[(0 * 8 + c) * (32 * NC) + col];
+        int j = 8 * col + c;
+        return j < g->nE ? __ldg(g->hnu + j) : 1.0;
+    }
+    __device__ inline double bbpre(int c, int col) const
+    {
+        if (GS) return sm[(1 * 8 + c) * (32 * NC) + col];
+        int j = 8 * col + c;
+        return j < g->nE ? __ldg(g->bbpre + j) : 0.0;
+    }
+    __device__ inline double wt(int c, int col) const
+    {
+        if (GS) return sm[(2 * 8 + c) * (32 * NC) + col];
+        int j = 8 * col + c;
+        return j < g->nE ? __ldg(g->wt + j) : 0.0;
+    }
+    __device__ inline double pk(int c, int col) const // pack factor of relagn.py:970-974 (h, 4 pi d^2 cancel)
+    {
+        if (GS) return sm[(3 * 8 + c) * (32 * NC) + col];
+        int j = 8 * col + c;
+        return j < g->nE ? (__ldg(g->dE + j) * 4) / __ldg(g->Egrid + j) : 0.0;
+    }
+    __device__ inline double upk(int c, int col) const // unpack factor of relagn.py:1003-1006
+    {
+        if (GS) return sm[(4 * 8 + c) * (32 * NC) + col];
+        int j = 8 * col + c;
+        return j < g->nE ? __ldg(g->Egrid + j) / __ldg(g->dE + j) : 0.0;
+    }
+};
+
+// Accumulators: registers (statically indexed through a switch on the chunk, so that the chunk loops with their
+// large bodies need not be unrolled) for NC <= 4, the warp's shared memory otherwise.
+template <int NC, bool ACC_REG>
+struct Acc {
+    double r[ACC_REG ? NC * 8 : 1];
+    double *s; // [8][32 NC] when !ACC_REG
+    int lane;
+    __device__ inline void zero()
+    {
+        if (ACC_REG) {
+#pragma unroll
+            for (int i = 0; i < NC * 8; i++) r[i] = 0.0;
+        } else {
+            for (int ch = 0; ch < NC; ch++)
+#pragma unroll
+                for (int c = 0; c < 8; c++) s[c * 32 * NC + 32 * ch + lane] = 0.0;
+        }
+    }
+    __device__ inline void add(int ch, const double (&v)[8])
+    {
+        if (ACC_REG) {
+            switch (ch) {
+            case 0:
+#pragma unroll
+                for (int c = 0; c < 8; c++) r[c] += v[c];
+                break;
+            case 1:
+#pragma unroll
+                for (int c = 0; c < 8; c++) r[(NC > 1 ? 8 : 0) + c] += v[c];
+                break;
+            case 2:
+#pragma unroll
+                for (int c = 0; c < 8; c++) r[(NC > 2 ? 16 : 0) + c] += v[c];
+                break;
+            default:
+#pragma unroll
+                for (int c = 0; c < 8; c++) r[(NC > 3 ? 24 : 0) + c] += v[c];
+                break;
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 8; c++) s[c * 32 * NC + 32 * ch + lane] += v[c];
+        }
+    }
+    // out[j] = acc (and restart) for this lane's bins; fully unrolled for the register variant
+    __device__ inline void store(double *out, int nE, bool reset)
+    {
+        if (ACC_REG) {
+#pragma unroll
+            for (int ch = 0; ch < NC; ch++) {
+                const int j0 = 8 * (32 * ch + lane);
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    if (j0 + c < nE) out[j0 + c] = r[ch * 8 + c];
+                    if (reset) r[ch * 8 + c] = 0.0;
+                }
+            }
+        } else {
+            for (int ch = 0; ch < NC; ch++) {
+                const int j0 = 8 * (32 * ch + lane);
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    double *p = &s[c * 32 * NC + 32 * ch + lane];
+                    if (j0 + c < nE) out[j0 + c] = *p;
+                    if (reset) *p = 0.0;
+                }
+            }
+        }
+    }
+};
+
+template <int NC>
+__global__ void __launch_bounds__(256, 1) spectrum_kernel(SpecArgs A)
 {
+    constexpr bool GS = NC <= 8;       // grid constants in shared memory
+    constexpr bool ACC_REG = NC <= 4;  // accumulators in registers
+    constexpr int NCOL = 32 * NC;
     RG_DYN_SMEM(smem_raw);
-    Smem s;
-    carve<M>(s, smem_raw, A.nH, A.HL, A.HH, A.arena);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int set = blockIdx.x;
     const int nE = A.grid.nE;
     const bool rel = (A.flags & RG_FLAG_REL) != 0;
     const bool comps = (A.flags & RG_FLAG_COMPONENTS) != 0;
-    const SetRec &r = A.recs[set];
-    const int j0 = M * tid;
-    double *out_set = A.out + (size_t)set * (comps ? 4 : 1) * nE;
+    const int ncomp = comps ? 4 : 1;
+    const int RS = A.HL + NCOL + A.HH;
+    const int HSZ = round_up2(A.nH + 24);
 
-    if (r.status != RG_S_OK) { // ValueError sets: zeros (the host class raises)
-        for (int c = 0; c < (comps ? 4 : 1); c++)
-            for (int j = tid; j < nE; j += T_) out_set[(size_t)c * nE + j] = 0.0;
-        return;
+    // ---- shared memory carve ----
+    double *sm = reinterpret_cast<double *>(smem_raw);
+    double *sgrid = sm;
+    if (GS) sm += NGRID * 8 * NCOL;
+    const size_t wd = 8 * (size_t)RS + 2 * (size_t)HSZ + (ACC_REG ? 0 : 8 * (size_t)NCOL);
+    double *wbase = sm + wd * warp;
+    double *inT = wbase;                  // [8][RS]
+    double *Hslot = inT + 8 * (size_t)RS; // [HSZ]: 8 zero pad, nH bins, >= 16 zero pad
+    double *Hsum = Hslot + HSZ;           // [HSZ]
+    double *acc_s = Hsum + HSZ;           // [8][NCOL] when !ACC_REG
+    (void)acc_s;
+
+    // ---- CTA prologue: stage the per-bin constants (transposed), zero the warp buffers ----
+    if (GS) {
+        for (int i = tid; i < 8 * NCOL; i += blockDim.x) {
+            int c = i / NCOL, col = i - c * NCOL;
+            int j = 8 * col + c;
+            bool ok = j < nE;
+            sgrid[(0 * 8 + c) * NCOL + col] = ok ? A.grid.hnu[j] : 1.0; // padding bins: 0 / (exp(1/kT) - 1) = 0
+            sgrid[(1 * 8 + c) * NCOL + col] = ok ? A.grid.bbpre[j] : 0.0;
+            sgrid[(2 * 8 + c) * NCOL + col] = ok ? A.grid.wt[j] : 0.0;
+            sgrid[(3 * 8 + c) * NCOL + col] = ok ? (A.grid.dE[j] * 4) / A.grid.Egrid[j] : 0.0;
+            sgrid[(4 * 8 + c) * NCOL + col] = ok ? A.grid.Egrid[j] / A.grid.dE[j] : 0.0;
+        }
     }
-
-    // zero both local-spectrum buffers (halos stay zero for the whole kernel)
-    for (int i = tid; i < 2 * s.inStride; i += T_) s.inT[i] = 0.0;
-    if (tid == 0) { s.seti[2] = 0; s.seti[3] = 0; }
-
-    // per-bin constants of this thread
-    double hnu[M], bbpre[M], wt[M], pk[M];
-#pragma unroll
-    for (int c = 0; c < M; c++) {
-        int j = j0 + c;
-        bool ok = j < nE;
-        hnu[c] = ok ? A.grid.hnu[j] : 1.0; // padding bins: 0 / (exp(1/kT) - 1) = 0
-        bbpre[c] = ok ? A.grid.bbpre[j] : 0.0;
-        wt[c] = ok ? A.grid.wt[j] : 0.0;
-        // pack factor of relagn.py:970-974 (h and 4 pi d^2 cancel against the unpack at :1003-1006)
-        pk[c] = ok ? (A.grid.dE[j] * 4) / A.grid.Egrid[j] : 0.0;
-    }
-    NtConst nt;
-    rg_nt_prepare(nt, r);
-    TabSel ts;
+    for (int i = lane; i < 8 * RS + 2 * HSZ; i += 32) wbase[i] = 0.0;
+    __syncthreads(); // the only block barrier: from here on every warp runs on its own
+    GridAcc<NC, GS> G;
+    G.sm = sgrid; G.g = &A.grid;
+    double *const inBase = inT + A.HL + lane; // row 0, this lane's column of chunk 0
     const double dlnE = A.grid.dlnE;
-    int K_LO = 0, nH = 1, SS = 8, GH = 1;
-    if (rel) {
-        rg_tab_select(ts, A.tab, r.a, r.inc);
-        // shift range this (spin, inclination) can produce: min/max of ln g over the rows of its 4 nodes
-        if (warp == 0) {
+    unsigned long long st_w = 0, st_n = 0;
+
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(A.queue, 1);
+        item = __shfl_sync(FULL, item, 0);
+        if (item >= A.P * A.NB) break;
+        const int set = item / A.NB, blk = item - set * A.NB;
+        const SetRec &r = A.recs[set];
+        double *out_item = A.NB == 1 ? A.out + (size_t)set * ncomp * nE
+                                     : A.partial + ((size_t)set * A.NB + blk) * (comps ? 3 : 1) * nE;
+        if (r.status != RG_S_OK) { // ValueError sets: zeros (the host class raises)
+            const int nwr = A.NB == 1 ? ncomp : (comps ? 3 : 1);
+            for (int j = lane; j < nwr * nE; j += 32) out_item[j] = 0.0;
+            continue;
+        }
+        const int n_tot = r.n_disc + r.n_warm + r.n_hot;
+        const int per = (n_tot + A.NB - 1) / A.NB;
+        const int g_begin = blk * per, g_end = (g_begin + per < n_tot) ? g_begin + per : n_tot;
+
+        NtConst nt;
+        rg_nt_prepare(nt, r);
+        TabSel ts;
+        int K_LO = 0, nH = 1;
+        if (rel) {
+            rg_tab_select(ts, A.tab, r.a, r.inc);
+            // shift range this (spin, inclination) can produce: min/max of ln g over the rows of its 4 nodes
             double lo = 1e300, hi = -1e300;
             const double *rr = A.tab.rowrange;
-            size_t plane2 = (size_t)A.tab.NR * 2;
-            size_t nd[4] = {(size_t)((ts.n00 - A.tab.data) / (2 * ts.plane)), (size_t)((ts.n01 - A.tab.data) / (2 * ts.plane)),
-                            (size_t)((ts.n10 - A.tab.data) / (2 * ts.plane)), (size_t)((ts.n11 - A.tab.data) / (2 * ts.plane))};
+            const size_t plane2 = (size_t)A.tab.NR * 2;
+            const size_t nd[4] = {(size_t)((ts.n00 - A.tab.data) / (2 * ts.plane)), (size_t)((ts.n01 - A.tab.data) / (2 * ts.plane)),
+                                  (size_t)((ts.n10 - A.tab.data) / (2 * ts.plane)), (size_t)((ts.n11 - A.tab.data) / (2 * ts.plane))};
             for (int q = 0; q < 4; q++)
                 for (int row = lane; row < A.tab.NR; row += 32) {
-                    double a0 = rr[nd[q] * plane2 + 2 * row], a1 = rr[nd[q] * plane2 + 2 * row + 1];
+                    double a0 = __ldg(rr + nd[q] * plane2 + 2 * row), a1 = __ldg(rr + nd[q] * plane2 + 2 * row + 1);
                     lo = a0 < lo ? a0 : lo; hi = a1 > hi ? a1 : hi;
                 }
 #pragma unroll
@@ -332,371 +440,386 @@ __global__ void __launch_bounds__(RG_SPEC_THREADS, (M <= 4 ? RG_SPEC_MIN_CTAS : 
                 double a0 = __shfl_xor_sync(FULL, lo, o), a1 = __shfl_xor_sync(FULL, hi, o);
                 lo = a0 < lo ? a0 : lo; hi = a1 > hi ? a1 : hi;
             }
-            if (lane == 0) {
-                int kl = (int)floor(lo / dlnE) - 2, kh = (int)floor(hi / dlnE) + 3;
-                if (kl < A.K_LO) kl = A.K_LO;
-                if (kh > A.K_LO + A.nH - 1) kh = A.K_LO + A.nH - 1;
-                s.seti[0] = kl; s.seti[1] = kh - kl + 1;
-            }
+            int kl = (int)floor(lo / dlnE) - 2, kh = (int)floor(hi / dlnE) + 3;
+            if (kl < A.K_LO) kl = A.K_LO;
+            if (kh > A.K_LO + A.nH - 1) kh = A.K_LO + A.nH - 1;
+            K_LO = kl; nH = kh - kl + 1;
         }
-    }
-    __syncthreads();
-    if (rel) {
-        K_LO = s.seti[0]; nH = s.seti[1];
-        SS = round_up2(nH + 3 * M + 4);
-        GH = A.arena / SS;
-        GH = GH >= 16 ? 16 : (GH >= 8 ? 8 : (GH < 1 ? 1 : GH)); // whole rounds of the 8 builder warps
-    }
-    const double Rg2 = r.Rg * r.Rg;
-    const double cosfac = r.cosinc / 0.5;
-    double tot[M];
-#pragma unroll
-    for (int c = 0; c < M; c++) tot[c] = 0.0;
-    int buf = 0;          // parity of the local-spectrum / reduction buffers
-    double *const inBase0 = s.inT + A.HL + tid;
+        const double Rg2 = r.Rg * r.Rg;
+        const double cosfac = r.cosinc / 0.5;
 
-    // ------------------------------------------------------------------
-    // regions: 0 disc [r_w, r_out], 1 warm [r_h, r_w], 2 hot [risco, r_h]
-    for (int region = 0; region < 3; region++) {
-        const int n_ann = region == 0 ? r.n_disc : (region == 1 ? r.n_warm : r.n_hot);
-        const double lg_in = region == 0 ? r.lg_rw : (region == 1 ? r.lg_rh : r.lg_risco);
-        const double lg_out = region == 0 ? r.lg_rout : (region == 1 ? r.lg_rw : r.lg_rh);
-        double accC[M], accF[M]; // through-the-transfer sum (before unpack) and flat / non-relativistic sum
-#pragma unroll
-        for (int c = 0; c < M; c++) { accC[c] = 0.0; accF[c] = 0.0; }
-        double fh[M] = {};       // hot: normalised shape Fnu_seed_hot / trapz (relagn.py:1315-1316)
-        bool any_conv = false;
-        int hk_min = IMAX, hk_max = -IMAX; // hot: support of the summed histogram
-        double Sflat = 0.0;                // hot: sum of L_ann 4 pi r dr over flat annuli
+        Acc<NC, ACC_REG> acc;
+        acc.s = acc_s; acc.lane = lane;
+        acc.zero();
+        int hz_min = IMAX, hz_max = -IMAX; // touched range of the H slot (for re-zeroing)
 
-        if (n_ann > 0 && region == 1) { // stage the first warm annulus' Kompaneets solution
-            const int sys = r.sys_base;
-            const int nth = (int)A.header[(size_t)sys * 4 + 2];
-            const double *g_spt = A.sptot + (size_t)sys * RG_SPT_STRIDE;
-            __syncthreads();
-            for (int q = tid; q <= nth; q += T_) s.spt[q] = g_spt[q];
-            __syncthreads();
-        }
-        if (n_ann > 0 && region == 2) {
-            // hot shape (relagn.py:1200-1223): donthcomp(Egrid, [gamma_h, kTe_h, kT_seed, 0, 0]) * h / keV
-            double F[M];
-#pragma unroll
-            for (int c = 0; c < M; c++) F[c] = 0.0;
-            __syncthreads();
-            if (r.has_hotshape) {
-                const int sys = r.sys_base + r.n_warm;
-                const double *hd = A.header + (size_t)sys * 4;
-                const double xmin = hd[0], normfac = hd[1], lgx = hd[3];
-                const int nth = (int)hd[2];
-                const double *g_spt = A.sptot + (size_t)sys * RG_SPT_STRIDE;
-                for (int q = tid; q <= nth; q += T_) s.spt[q] = g_spt[q];
-                __syncthreads();
-                double e_prev = 0.0, pr_prev = 0.0;
-                if (j0 > 0 && j0 - 1 < nE) {
-                    e_prev = A.grid.Egrid[j0 - 1];
-                    pr_prev = nth_prim(s.spt, A.p10tab, xmin, lgx, nth, e_prev, A.grid.e511[j0 - 1], A.grid.lgE[j0 - 1]) /
-                              A.grid.ear2[j0 - 1];
-                }
-#pragma unroll
-                for (int c = 0; c < M; c++) {
-                    int j = j0 + c;
-                    if (j < nE) {
-                        double e = A.grid.Egrid[j];
-                        double pr = nth_prim(s.spt, A.p10tab, xmin, lgx, nth, e, A.grid.e511[j], A.grid.lgE[j]) / A.grid.ear2[j];
-                        double ph = j > 0 ? (0.5 * (pr + pr_prev) * (e - e_prev) * normfac) : 0.0;
-                        F[c] = ph * (1.0 / RGK_KEV) * RGK_H;
-                        e_prev = e; pr_prev = pr;
-                    }
-                }
-            }
-            double part = 0;
-#pragma unroll
-            for (int c = 0; c < M; c++) part += F[c] * wt[c];
-            part = warp_sum(part);
-            if (lane == 0) s.red[buf * NWARP + warp] = part;
-            if (rel) {
-                for (int q = tid; q < nH + 3 * M + 4; q += T_) s.Hsum[q] = 0.0;
-            }
-            __syncthreads();
-            double shape_int = 0;
-#pragma unroll
-            for (int w = 0; w < NWARP; w++) shape_int += s.red[buf * NWARP + w];
-#pragma unroll
-            for (int c = 0; c < M; c++) fh[c] = F[c] / shape_int; // 0/0 -> NaN as in the reference (relagn.py:1316)
-            if (rel) {
-#pragma unroll
-                for (int c = 0; c < M; c++) inBase0[buf * s.inStride + c * s.RS] = fh[c] * pk[c];
-            }
-            // (published by the barriers of the annulus loop below)
-        }
+        // ------------------------------------------------------------------
+        // regions: 0 disc [r_w, r_out], 1 warm [r_h, r_w], 2 hot [risco, r_h]
+        int g_reg0 = 0; // global index of the region's first annulus
+        for (int region = 0; region < 3; region++) {
+            const int n_ann = region == 0 ? r.n_disc : (region == 1 ? r.n_warm : r.n_hot);
+            const double lg_in = region == 0 ? r.lg_rw : (region == 1 ? r.lg_rh : r.lg_risco);
+            const double lg_out = region == 0 ? r.lg_rout : (region == 1 ? r.lg_rw : r.lg_rh);
+            // annuli of this region handled by this item (region-local, counted top-down)
+            int a0 = g_begin - g_reg0, a1 = g_end - g_reg0;
+            a0 = a0 < 0 ? 0 : a0;
+            a1 = a1 > n_ann ? n_ann : a1;
+            const bool owns_first = g_begin <= g_reg0 && g_reg0 < g_end; // owns the region's first annulus
+            g_reg0 += n_ann;
+            const bool active = a0 < a1;
 
-        for (int tile0 = 0; tile0 < n_ann && !(region == 2 && !rel); tile0 += T_) {
-            const int n_tile = n_ann - tile0 < T_ ? n_ann - tile0 : T_;
-            // ---- prologue: thread i prepares annulus tile0+i (counted top-down) ----
-            __syncthreads();
-            if (tid < n_tile) {
-                BinIter it;
-                it.start(lg_in, lg_out, r.dlog_r);
-                double lo = 0, hi = 0;
-                for (int q = 0; q <= tile0 + tid; q++) it.next(lo, hi);
-                double r1 = pow(10.0, lo), r2 = pow(10.0, hi);
-                double rmid = pow(10.0, lo + r.dlog_r / 2);
-                double T4 = rg_tnt4(nt, rmid);
-                double s1, s2;
-                if (region == 0) { // relagn.py:857-883
-                    double Tann = pow(T4, 0.25);
-                    double fcol_r = r.fcol < 0 ? rg_fcol(Tann) : r.fcol;
-                    Tann = Tann * fcol_r;
-                    double t = Tann / fcol_r;
-                    s1 = RGK_KB * Tann;
-                    s2 = RGK_SB * (t * t * t * t) * Rg2;
-                } else if (region == 1) { // relagn.py:919-932
-                    double Tann = pow(T4, 0.25);
-                    s1 = 0.0;
-                    s2 = RGK_SB * (Tann * Tann * Tann * Tann) * Rg2;
-                } else { // relagn.py:1309-1314
-                    double Ldiss_ann = RGK_SB * T4 * Rg2;
-                    double Lseed_ann = r.Lseed / (4 * RGK_PI * rmid * (r2 - r1) * n_ann);
-                    s1 = Ldiss_ann + Lseed_ann;
-                    s2 = 0.0;
-                }
-                // flat space (relagn.py:1013,1110,1370) / non-relativistic (relagn.py:1046,1143) area factor
-                double geo = 2 * RGK_PI * 2 * rmid * (r2 - r1);
-                if (region != 2) geo = geo * r.cosinc / 0.5;
-                // first bin whose Planck exponent overflows (exp(x) = inf for x > 709.78 -> B = 0 exactly): the
-                // local spectrum is identically zero from there on and is neither evaluated nor convolved
-                int jz = nE;
-                if (region == 0) {
-                    const double lim = 710.0 * s1;
-                    int a = 0, b = nE; // smallest j in [0, nE] with hnu[j] > lim
-                    while (a < b) {
-                        int m = (a + b) >> 1;
-                        if (A.grid.hnu[m] > lim) b = m; else a = m + 1;
-                    }
-                    jz = a;
-                }
-                s.aJz[tid] = jz;
-                s.aR1[tid] = r1; s.aR2[tid] = r2; s.aS1[tid] = s1; s.aS2[tid] = s2; s.aGeo[tid] = geo;
-                s.aFlag[tid] = (rel && lo <= 3 && hi <= 3) ? 1 : 0; // relagn.py:992
-            }
-            __syncthreads();
+            bool hot_any_conv = false;
+            int hk_min = IMAX, hk_max = -IMAX;
+            double Sflat = 0.0;
+            double shape_int = 0.0;
 
-            for (int g0 = 0; g0 < n_tile; g0 += GH) {
-                const int ng = n_tile - g0 < GH ? n_tile - g0 : GH;
-                // ---- phase H: one warp per annulus ----
-                if (rel) {
-                    for (int i = g0 + warp; i < g0 + ng; i += NWARP) {
-                        if (!s.aFlag[i]) continue;
-                        double *slot = s.arena + (size_t)(i - g0) * SS;
-                        for (int q = lane; q < SS; q += 32) slot[q] = 0.0;
-                        __syncwarp();
-                        int kmn, kmx;
-                        warp_build_hist(slot + M, K_LO, nH, ts, s.aR1[i], s.aR2[i], dlnE, kmn, kmx);
-                        if (lane == 0) {
-                            s.aKmin[i] = kmn; s.aKmax[i] = kmx;
-                            if (kmn <= kmx) { atomicAdd(&s.seti[2], kmx - kmn + 1); atomicAdd(&s.seti[3], 1); }
-                        }
-                    }
-                    __syncthreads();
+            if (region == 2 && n_ann > 0 && (rel ? active : owns_first)) {
+                // hot shape (relagn.py:1200-1223): donthcomp(Egrid, [gamma_h, kTe_h, kT_seed, 0, 0]) * h / keV,
+                // written (times the pack factor) to the warp buffer; shape_int = trapz(Fnu, nu)
+                const double *hot_spt = nullptr;
+                double hot_xmin = 0, hot_norm = 0, hot_lgx = 0;
+                int hot_nth = 0;
+                if (r.has_hotshape) {
+                    const int sys = r.sys_base + r.n_warm;
+                    const double *hd = A.header + (size_t)sys * 4;
+                    hot_xmin = hd[0]; hot_norm = hd[1]; hot_lgx = hd[3];
+                    hot_nth = (int)hd[2];
+                    hot_spt = A.sptot + (size_t)sys * RG_SPT_STRIDE;
                 }
-
-                if (region == 2) {
-                    // hot: fold the group's histograms into the region histogram, annulus by annulus (fixed order)
-                    for (int i = g0; i < g0 + ng; i++) {
-                        const double L = s.aS1[i];
-                        if (s.aFlag[i]) {
-                            const int kmn = s.aKmin[i], kmx = s.aKmax[i];
-                            const double *slot = s.arena + (size_t)(i - g0) * SS + M;
-                            // bin q is always handled by thread q mod T_: race-free across annuli, fixed order
-                            for (int q = tid; q < nH; q += T_) {
-                                int k = K_LO + q;
-                                if (k >= kmn && k <= kmx) s.Hsum[M + q] += L * slot[q];
-                            }
-                            hk_min = kmn < hk_min ? kmn : hk_min;
-                            hk_max = kmx > hk_max ? kmx : hk_max;
-                            any_conv = true;
-                        } else {
-                            Sflat += L * s.aGeo[i];
-                        }
-                    }
-                    __syncthreads();
-                    continue;
-                }
-
-                // ---- stream: one barrier per annulus ----
-                for (int i = g0; i < g0 + ng; i++) {
-                    double L[M];
-                    double part = 0;
-                    double *inw = inBase0 + buf * s.inStride;
-                    if (region == 0) {
-                        const double kT = s.aS1[i];
-                        if (j0 >= s.aJz[i]) { // Wien tail past the overflow point: all of this thread's bins are 0
+                double part = 0;
+                for (int ch = 0; ch < NC; ch++) {
+                    const int col = 32 * ch + lane, j0 = 8 * col;
+                    double F[8];
 #pragma unroll
-                            for (int c = 0; c < M; c++) L[c] = 0.0;
-                        } else {
-#pragma unroll
-                            for (int c = 0; c < M; c++) {
-                                double ef = exp(hnu[c] / kT) - 1;
-                                L[c] = RGK_PI * (bbpre[c] / ef);
-                                part += L[c] * wt[c];
-                            }
-                        }
-                        if (A.grid.n_ext && tid < A.grid.n_ext) { // relagn.py:868-873
-                            double ef = exp(A.grid.x_hnu[tid] / kT) - 1;
-                            part += RGK_PI * (A.grid.x_bbpre[tid] / ef) * A.grid.x_wt[tid];
-                        }
-                    } else {
-                        // warm annulus: Kompaneets solution of system sys_base + (tile0 + i), staged in s.spt[parity]
-                        const int gi = tile0 + i;
-                        const int sys = r.sys_base + gi;
-                        const double *hd = A.header + (size_t)sys * 4;
-                        const double xmin = hd[0], normfac = hd[1], lgx = hd[3];
-                        const int nth = (int)hd[2];
-                        const double *spt = s.spt + (gi & 1) * RG_SPT_STRIDE;
-                        if (gi + 1 < n_ann) { // prefetch the next annulus' solution into the other buffer
-                            const int nth2 = (int)A.header[(size_t)(sys + 1) * 4 + 2];
-                            const double *g_spt = A.sptot + (size_t)(sys + 1) * RG_SPT_STRIDE;
-                            double *dst = s.spt + ((gi + 1) & 1) * RG_SPT_STRIDE;
-                            for (int q = tid; q <= nth2; q += T_) dst[q] = g_spt[q];
-                        }
+                    for (int c = 0; c < 8; c++) F[c] = 0.0;
+                    if (hot_spt && j0 < nE) {
                         double e_prev = 0.0, pr_prev = 0.0;
-                        if (j0 > 0 && j0 - 1 < nE) {
-                            e_prev = A.grid.Egrid[j0 - 1];
-                            pr_prev = nth_prim(spt, A.p10tab, xmin, lgx, nth, e_prev, A.grid.e511[j0 - 1],
-                                               A.grid.lgE[j0 - 1]) / A.grid.ear2[j0 - 1];
+                        if (j0 > 0) {
+                            e_prev = __ldg(A.grid.Egrid + j0 - 1);
+                            pr_prev = nth_prim(hot_spt, A.p10tab, hot_xmin, hot_lgx, hot_nth, e_prev,
+                                               __ldg(A.grid.e511 + j0 - 1), __ldg(A.grid.lgE + j0 - 1)) /
+                                      __ldg(A.grid.ear2 + j0 - 1);
                         }
 #pragma unroll
-                        for (int c = 0; c < M; c++) {
+                        for (int c = 0; c < 8; c++) {
                             int j = j0 + c;
-                            L[c] = 0.0;
                             if (j < nE) {
-                                double e = A.grid.Egrid[j];
-                                double pr = nth_prim(spt, A.p10tab, xmin, lgx, nth, e, A.grid.e511[j], A.grid.lgE[j]) /
-                                            A.grid.ear2[j];
-                                double ph = j > 0 ? (0.5 * (pr + pr_prev) * (e - e_prev) * normfac) : 0.0;
-                                L[c] = ph * (1.0 / RGK_KEV) * RGK_H;
+                                double e = __ldg(A.grid.Egrid + j);
+                                double pr = nth_prim(hot_spt, A.p10tab, hot_xmin, hot_lgx, hot_nth, e,
+                                                     __ldg(A.grid.e511 + j), __ldg(A.grid.lgE + j)) / __ldg(A.grid.ear2 + j);
+                                double ph = j > 0 ? (0.5 * (pr + pr_prev) * (e - e_prev) * hot_norm) : 0.0;
+                                F[c] = ph * (1.0 / RGK_KEV) * RGK_H;
                                 e_prev = e; pr_prev = pr;
                             }
-                            part += L[c] * wt[c];
                         }
                     }
-                    const bool conv = s.aFlag[i] != 0;
-                    if (conv) {
 #pragma unroll
-                        for (int c = 0; c < M; c++) inw[c * s.RS] = L[c] * pk[c];
+                    for (int c = 0; c < 8; c++) {
+                        part += F[c] * G.wt(c, col);
+                        inBase[c * RS + 32 * ch] = F[c] * G.pk(c, col);
                     }
-                    part = warp_sum(part);
-                    if (lane == 0) s.red[buf * NWARP + warp] = part;
-                    __syncthreads();
-                    double radiance = 0;
-#pragma unroll
-                    for (int w = 0; w < NWARP; w++) radiance += s.red[buf * NWARP + w];
-                    // Lnu = norm * (B / radiance), zero when the annulus emits nothing (relagn.py:885-889, 933-937)
-                    const double norm = s.aS2[i];
-                    if (conv) {
-                        double tmp[M];
-                        // taps whose sources all lie in the zero zones (j - k >= jz or j - k < 0) are skipped
-                        int k_lo = s.aKmin[i], k_hi = s.aKmax[i];
-                        {
-                            const int a = j0 - s.aJz[i] + 1, b = j0 + M - 1;
-                            k_lo = a > k_lo ? a : k_lo;
-                            k_hi = b < k_hi ? b : k_hi;
-                        }
-                        convolve<M>(s.arena + (size_t)(i - g0) * SS + M, K_LO, nH, k_lo, k_hi, inw, s.RS, tmp);
-                        if (radiance != 0) {
-                            const double scale = norm / radiance;
-#pragma unroll
-                            for (int c = 0; c < M; c++) accC[c] = fma(scale, tmp[c], accC[c]);
-                        }
-                        any_conv = true;
-                    } else if (radiance != 0) {
-                        const double scale = (norm / radiance) * s.aGeo[i];
-#pragma unroll
-                        for (int c = 0; c < M; c++) accF[c] = fma(scale, L[c], accF[c]);
-                    }
-                    buf ^= 1;
                 }
-                if (rel) __syncthreads(); // the arena is rebuilt by the next group
-            }
-        }
-
-        // ---- region epilogue ----
-        if (n_ann > 0) {
-            if (region == 2) {
+                shape_int = warp_sum(part);
                 if (rel) {
-                    if (any_conv) {
-                        __syncthreads();
-                        double tmp[M];
-                        convolve<M>(s.Hsum + M, K_LO, nH, hk_min, hk_max, inBase0 + buf * s.inStride, s.RS, tmp);
+                    for (int q = lane; q < HSZ; q += 32) Hsum[q] = 0.0;
+                }
+                __syncwarp();
+            }
+
+            if (region == 2 && !rel) {
+                // non-relativistic hot component (relagn.py:1387-1401): (Ldiss + Lseed) * Fnu / trapz(Fnu)
+                if (n_ann > 0 && owns_first) {
+                    const double Lum = r.Ldiss + r.Lseed;
+                    for (int ch = 0; ch < NC; ch++) {
+                        const int col = 32 * ch + lane;
+                        double v[8];
 #pragma unroll
-                        for (int c = 0; c < M; c++) accC[c] = tmp[c];
-                        buf ^= 1;
-                    }
-#pragma unroll
-                    for (int c = 0; c < M; c++) {
-                        int j = j0 + c;
-                        double v = 0.0;
-                        if (j < nE) {
-                            v = Sflat * fh[c];
-                            if (any_conv) v += ((accC[c] / A.grid.dE[j]) * A.grid.Egrid[j]) / cosfac; // relagn.py:1362
+                        for (int c = 0; c < 8; c++) {
+                            // the buffer holds F * pk and pk * upk = 4; F / shape_int: 0/0 -> NaN as the reference
+                            double F = inBase[c * RS + 32 * ch] * G.upk(c, col) * 0.25;
+                            v[c] = (8 * col + c < nE) ? Lum * (F / shape_int) : 0.0;
                         }
-                        accF[c] = v;
+                        acc.add(ch, v);
                     }
-                } else {
-                    const double Lum = r.Ldiss + r.Lseed; // relagn.py:1396-1398
-#pragma unroll
-                    for (int c = 0; c < M; c++) accF[c] = Lum * fh[c];
+                    __syncwarp();
                 }
             } else {
+                for (int t0 = a0; t0 < a1; t0 += 32) {
+                    const int n_tile = a1 - t0 < 32 ? a1 - t0 : 32;
+                    // ---- prologue: lane i prepares annulus t0 + i (counted top-down) ----
+                    double p_r1 = 0, p_r2 = 0, p_s1 = 0, p_s2 = 0, p_geo = 0;
+                    int p_flag = 0, p_jz = nE;
+                    if (lane < n_tile) {
+                        BinIter it;
+                        it.start(lg_in, lg_out, r.dlog_r);
+                        double lo = 0, hi = 0;
+                        for (int q = 0; q <= t0 + lane; q++) it.next(lo, hi);
+                        double r1 = pow(10.0, lo), r2 = pow(10.0, hi);
+                        double rmid = pow(10.0, lo + r.dlog_r / 2);
+                        double T4 = rg_tnt4(nt, rmid);
+                        if (region == 0) { // relagn.py:857-883
+                            double Tann = pow(T4, 0.25);
+                            double fcol_r = r.fcol < 0 ? rg_fcol(Tann) : r.fcol;
+                            Tann = Tann * fcol_r;
+                            double t = Tann / fcol_r;
+                            p_s1 = RGK_KB * Tann;
+                            p_s2 = RGK_SB * (t * t * t * t) * Rg2;
+                            // first bin whose Planck exponent overflows (exp(x) = inf for x > 709.78 -> B = 0 exactly)
+                            const double lim = 710.0 * p_s1;
+                            int a = 0, b = nE;
+                            while (a < b) {
+                                int m = (a + b) >> 1;
+                                if (__ldg(A.grid.hnu + m) > lim) b = m; else a = m + 1;
+                            }
+                            p_jz = a;
+                        } else if (region == 1) { // relagn.py:919-932
+                            double Tann = pow(T4, 0.25);
+                            p_s2 = RGK_SB * (Tann * Tann * Tann * Tann) * Rg2;
+                        } else { // relagn.py:1309-1314
+                            double Ldiss_ann = RGK_SB * T4 * Rg2;
+                            double Lseed_ann = r.Lseed / (4 * RGK_PI * rmid * (r2 - r1) * n_ann);
+                            p_s1 = Ldiss_ann + Lseed_ann;
+                        }
+                        // flat space (relagn.py:1013,1110,1370) / non-relativistic (relagn.py:1046,1143) area factor
+                        p_geo = 2 * RGK_PI * 2 * rmid * (r2 - r1);
+                        if (region != 2) p_geo = p_geo * r.cosinc / 0.5;
+                        p_r1 = r1; p_r2 = r2;
+                        p_flag = (rel && lo <= 3 && hi <= 3) ? 1 : 0; // relagn.py:992
+                    }
+
+                    for (int i = 0; i < n_tile; i++) {
+                        const double r1 = __shfl_sync(FULL, p_r1, i), r2 = __shfl_sync(FULL, p_r2, i);
+                        const double s1 = __shfl_sync(FULL, p_s1, i), s2 = __shfl_sync(FULL, p_s2, i);
+                        const double geo = __shfl_sync(FULL, p_geo, i);
+                        const bool conv = __shfl_sync(FULL, p_flag, i) != 0;
+                        const int jz = __shfl_sync(FULL, p_jz, i);
+                        int kmn = 0, kmx = -1;
+                        if (conv) {
+                            // re-zero what the previous annulus touched, then build this annulus' histogram
+                            for (int k = hz_min + lane; k <= hz_max; k += 32) {
+                                int q = k - K_LO;
+                                if (q >= 0 && q < nH) Hslot[8 + q] = 0.0;
+                            }
+                            __syncwarp();
+                            warp_build_hist(Hslot + 8, K_LO, nH, ts, r1, r2, dlnE, kmn, kmx);
+                            hz_min = kmn; hz_max = kmx;
+                            if (kmn <= kmx) { st_w += (unsigned long long)(kmx - kmn + 1); st_n += 1; }
+                        }
+                        if (region == 2) {
+                            // hot: fold into the region histogram (weighted by the annulus luminosity)
+                            if (conv) {
+                                for (int k = kmn + lane; k <= kmx; k += 32) {
+                                    int q = k - K_LO;
+                                    if (q >= 0 && q < nH) Hsum[8 + q] += s1 * Hslot[8 + q];
+                                }
+                                hk_min = kmn < hk_min ? kmn : hk_min;
+                                hk_max = kmx > hk_max ? kmx : hk_max;
+                                hot_any_conv = true;
+                                __syncwarp();
+                            } else {
+                                Sflat += s1 * geo;
+                            }
+                            continue;
+                        }
+
+                        // ---- local spectrum, chunk by chunk ----
+                        const int nch_live = region == 0 ? ((jz + 255) >> 8) : NC; // chunks holding a non-zero bin
+                        double part = 0;
+                        const double *w_spt = nullptr;
+                        double w_xmin = 0, w_norm = 0, w_lgx = 0;
+                        int w_nth = 0;
+                        if (region == 1) {
+                            const int sys = r.sys_base + t0 + i;
+                            const double *hd = A.header + (size_t)sys * 4;
+                            w_xmin = hd[0]; w_norm = hd[1]; w_lgx = hd[3];
+                            w_nth = (int)hd[2];
+                            w_spt = A.sptot + (size_t)sys * RG_SPT_STRIDE;
+                        }
+                        for (int ch = 0; ch < NC; ch++) {
+                            const int col = 32 * ch + lane, j0 = 8 * col;
+                            double L[8];
 #pragma unroll
-                for (int c = 0; c < M; c++) {
+                            for (int c = 0; c < 8; c++) L[c] = 0.0;
+                            if (ch >= nch_live) {
+                                // Wien tail past the overflow point: identically zero
+                            } else if (region == 0) {
+#pragma unroll
+                                for (int c = 0; c < 8; c++) {
+                                    double ef = exp(G.hnu(c, col) / s1) - 1;
+                                    L[c] = RGK_PI * (G.bbpre(c, col) / ef);
+                                    part += L[c] * G.wt(c, col);
+                                }
+                            } else if (j0 < nE) {
+                                double e_prev = 0.0, pr_prev = 0.0;
+                                if (j0 > 0) {
+                                    e_prev = __ldg(A.grid.Egrid + j0 - 1);
+                                    pr_prev = nth_prim(w_spt, A.p10tab, w_xmin, w_lgx, w_nth, e_prev,
+                                                       __ldg(A.grid.e511 + j0 - 1), __ldg(A.grid.lgE + j0 - 1)) /
+                                              __ldg(A.grid.ear2 + j0 - 1);
+                                }
+#pragma unroll
+                                for (int c = 0; c < 8; c++) {
+                                    int j = j0 + c;
+                                    if (j < nE) {
+                                        double e = __ldg(A.grid.Egrid + j);
+                                        double pr = nth_prim(w_spt, A.p10tab, w_xmin, w_lgx, w_nth, e,
+                                                             __ldg(A.grid.e511 + j), __ldg(A.grid.lgE + j)) /
+                                                    __ldg(A.grid.ear2 + j);
+                                        double ph = j > 0 ? (0.5 * (pr + pr_prev) * (e - e_prev) * w_norm) : 0.0;
+                                        L[c] = ph * (1.0 / RGK_KEV) * RGK_H;
+                                        e_prev = e; pr_prev = pr;
+                                    }
+                                    part += L[c] * G.wt(c, col);
+                                }
+                            }
+                            // publish: packed for the transfer convolution, plain for the flat / non-relativistic sum
+                            if (conv) {
+#pragma unroll
+                                for (int c = 0; c < 8; c++) inBase[c * RS + 32 * ch] = L[c] * G.pk(c, col);
+                            } else {
+#pragma unroll
+                                for (int c = 0; c < 8; c++) inBase[c * RS + 32 * ch] = L[c];
+                            }
+                        }
+                        if (region == 0 && A.grid.n_ext) { // relagn.py:868-873
+                            for (int q = lane; q < A.grid.n_ext; q += 32) {
+                                double ef = exp(A.grid.x_hnu[q] / s1) - 1;
+                                part += RGK_PI * (A.grid.x_bbpre[q] / ef) * A.grid.x_wt[q];
+                            }
+                        }
+                        const double radiance = warp_sum(part);
+                        __syncwarp();
+                        // Lnu = norm * (B / radiance), zero when the annulus emits nothing (relagn.py:885-889, 933-937)
+                        if (radiance != 0) {
+                            if (conv) {
+                                const double scale = s2 / radiance;
+                                for (int ch = 0; ch < NC; ch++) {
+                                    // taps whose sources all lie in the zero zones (j - k >= jz or j - k < 0) are skipped
+                                    int k_lo = 256 * ch - (region == 0 ? jz : nE) + 1, k_hi = 256 * ch + 255;
+                                    k_lo = k_lo > kmn ? k_lo : kmn;
+                                    k_hi = k_hi < kmx ? k_hi : kmx;
+                                    if (k_lo > k_hi) continue;
+                                    const int col = 32 * ch + lane;
+                                    double tmp[8];
+                                    convolve8(Hslot + 8, K_LO, nH, k_lo, k_hi, inBase + 32 * ch, RS, tmp);
+#pragma unroll
+                                    for (int c = 0; c < 8; c++) tmp[c] *= scale * G.upk(c, col);
+                                    acc.add(ch, tmp);
+                                }
+                            } else {
+                                const double scale = (s2 / radiance) * geo;
+                                for (int ch = 0; ch < nch_live; ch++) {
+                                    double v[8];
+#pragma unroll
+                                    for (int c = 0; c < 8; c++) v[c] = scale * inBase[c * RS + 32 * ch];
+                                    acc.add(ch, v);
+                                }
+                            }
+                        }
+                        __syncwarp(); // the buffer is rewritten by the next annulus
+                    }
+                }
+
+                if (region == 2 && active) {
+                    // one convolution for the whole hot region; rel result / (cos i / 0.5) (relagn.py:1362).
+                    // The buffer still holds F * pk; F / shape_int: 0/0 -> NaN as the reference (:1316)
+                    __syncwarp();
+                    for (int ch = 0; ch < NC; ch++) {
+                        const int col = 32 * ch + lane;
+                        double tmp[8];
+#pragma unroll
+                        for (int c = 0; c < 8; c++) tmp[c] = 0.0;
+                        if (hot_any_conv) convolve8(Hsum + 8, K_LO, nH, hk_min, hk_max, inBase + 32 * ch, RS, tmp);
+                        double v[8];
+#pragma unroll
+                        for (int c = 0; c < 8; c++) {
+                            v[c] = 0.0;
+                            if (8 * col + c < nE) {
+                                double F = inBase[c * RS + 32 * ch] * G.upk(c, col) * 0.25;
+                                v[c] = Sflat * (F / shape_int);
+                                if (hot_any_conv) v[c] += ((tmp[c] / shape_int) * G.upk(c, col)) / cosfac;
+                            }
+                        }
+                        acc.add(ch, v);
+                    }
+                    __syncwarp();
+                }
+            }
+
+            // ---- region epilogue: with components, store and restart the accumulators ----
+            if (comps) acc.store(out_item + (size_t)region * nE, nE, true);
+        }
+        // ---- item epilogue ----
+        if (!comps) {
+            acc.store(out_item, nE, false);
+        } else if (A.NB == 1) {
+            for (int ch = 0; ch < NC; ch++) {
+                const int j0 = 8 * (32 * ch + lane);
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
                     int j = j0 + c;
-                    double v = accF[c];
-                    if (any_conv && j < nE) v += (accC[c] / A.grid.dE[j]) * A.grid.Egrid[j]; // unpack :1003-1006
-                    accF[c] = v;
+                    if (j < nE)
+                        out_item[(size_t)3 * nE + j] = (out_item[j] + out_item[(size_t)nE + j]) + out_item[(size_t)2 * nE + j];
                 }
             }
         }
-#pragma unroll
-        for (int c = 0; c < M; c++) {
-            int j = j0 + c;
-            if (j < nE) {
-                if (comps) out_set[(size_t)region * nE + j] = accF[c];
-                tot[c] += accF[c];
-            }
+        // leave the H slot clean for the next item
+        for (int k = hz_min + lane; k <= hz_max; k += 32) {
+            int q = k - K_LO;
+            if (q >= 0 && q < nH) Hslot[8 + q] = 0.0;
         }
+        __syncwarp();
     }
-#pragma unroll
-    for (int c = 0; c < M; c++) {
-        int j = j0 + c;
-        if (j < nE) out_set[(size_t)(comps ? 3 : 0) * nE + j] = tot[c];
-    }
-    if (A.stats) {
-        __syncthreads();
-        if (tid == 0) {
-            atomicAdd(&A.stats[0], (unsigned long long)s.seti[2]);
-            atomicAdd(&A.stats[1], (unsigned long long)s.seti[3]);
-        }
+    if (A.stats && lane == 0 && st_n) {
+        atomicAdd(&A.stats[0], st_w);
+        atomicAdd(&A.stats[1], st_n);
     }
 }
 
-template <int M>
-static int launch_spec(const SpecArgs &args, cudaStream_t st)
+// NB > 1: out[set][c] = sum over blocks of partial[set][blk][c] in block order; total = disc + warm + hot
+__global__ void __launch_bounds__(256) reduce_blocks_kernel(const double *__restrict__ partial, double *__restrict__ out,
+                                                            int P, int NB, int nE, int comps)
 {
-    size_t smem = rg_spectrum_smem_bytes(M, args.nH, args.HL, args.HH, args.arena);
-    if (smem > 220 * 1024)
-        return rg_set_error(RG_E_GRID, "energy grid too fine for the shared-memory working set (%zu B)", smem);
-    RG_CUDA_OK(cudaFuncSetAttribute(spectrum_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    RG_LAUNCH(spectrum_kernel<M>, dim3(args.P), dim3(T_), smem, st, args);
+    const int npc = comps ? 3 : 1;
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)P * nE) return;
+    int set = (int)(idx / nE), j = (int)(idx - (size_t)set * nE);
+    double tot = 0;
+    for (int c = 0; c < npc; c++) {
+        double s = 0;
+        for (int b = 0; b < NB; b++) s += partial[(((size_t)set * NB + b) * npc + c) * nE + j];
+        if (comps) out[((size_t)set * 4 + c) * nE + j] = s;
+        tot += s;
+    }
+    out[((size_t)set * (comps ? 4 : 1) + (comps ? 3 : 0)) * nE + j] = tot;
+}
+
+template <int NC>
+static int launch_spec(const SpecArgs &args, int sm_count, cudaStream_t st)
+{
+    size_t smem = rg_spectrum_smem_bytes(NC, args.nH, args.HL, args.HH, args.warps);
+    RG_CUDA_OK(cudaFuncSetAttribute(spectrum_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long items = (long)args.P * args.NB;
+    long ctas = (items + args.warps - 1) / args.warps;
+    if (ctas > sm_count) ctas = sm_count; // persistent: one CTA per SM, warps pull items from the queue
+    RG_CUDA_OK(cudaMemsetAsync(args.queue, 0, sizeof(int), st));
+    RG_LAUNCH(spectrum_kernel<NC>, dim3((unsigned)ctas), dim3(32 * args.warps), smem, st, args);
     RG_CUDA_OK(cudaGetLastError());
+    if (args.NB > 1) {
+        size_t n = (size_t)args.P * args.grid.nE;
+        RG_LAUNCH(reduce_blocks_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, args.partial, args.out, args.P,
+                  args.NB, args.grid.nE, (args.flags & RG_FLAG_COMPONENTS) ? 1 : 0);
+        RG_CUDA_OK(cudaGetLastError());
+    }
     return RG_OK;
 }
 
-int rg_launch_spectrum(const SpecArgs &args, cudaStream_t st)
+int rg_launch_spectrum(const SpecArgs &args, int sm_count, cudaStream_t st)
 {
-    int M = rg_spectrum_pick_M(args.grid.nE);
-    if (M == 4) return launch_spec<4>(args, st);
-    if (M == 8) return launch_spec<8>(args, st);
-    if (M == 20) return launch_spec<20>(args, st);
-    return rg_set_error(RG_E_GRID, "nE = %d exceeds the kernel capacity (%d)", args.grid.nE, 20 * T_);
+    int NC = rg_spectrum_pick_NC(args.grid.nE);
+    if (args.warps < 1) return rg_set_error(RG_E_GRID, "energy grid too fine for the shared-memory working set");
+    if (NC == 4) return launch_spec<4>(args, sm_count, st);
+    if (NC == 8) return launch_spec<8>(args, sm_count, st);
+    if (NC == 20) return launch_spec<20>(args, sm_count, st);
+    return rg_set_error(RG_E_GRID, "nE = %d exceeds the kernel capacity (%d)", args.grid.nE, 20 * 256);
 }

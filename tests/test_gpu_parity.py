@@ -102,7 +102,8 @@ def test_random_batch_vs_oracle(ctx, oracle, otab, rel):
         for c in range(4):
             assert peak_relerr(out[i, c], ref[i, c]) < TOL, (i, c)
     tot, _ = ctx.eval_batch_host(p, model=0, rel=rel, components=False)
-    np.testing.assert_array_equal(tot, out[:, 3])
+    # total-only mode accumulates all regions in one register set; component mode sums three stored components
+    np.testing.assert_allclose(tot, out[:, 3], rtol=1e-13)
 
 
 def test_invalid_sets_are_flagged(ctx):
