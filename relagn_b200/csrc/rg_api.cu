@@ -560,14 +560,16 @@ extern "C" int rg_eval_batch(rg_ctx *c, const double *d_params, int P, int model
     }
     A.warps = rg_spectrum_pick_warps(NC, A.nH, A.HL, A.HH);
     if (A.warps < 1) return rg_set_error(RG_E_GRID, "energy grid too fine for the shared-memory working set");
-    // small batches: split every set's annuli over several warps (partials are folded in block order)
+    // small batches: split every set's annuli over several CTAs (partials are folded in block order)
     {
-        long total_warps = (long)c->sm_count * A.warps;
+        const bool comps = ncomp == 4;
         int NB = 1;
-        if ((long)P < 2 * total_warps) NB = (int)std::min<long>(16, (2 * total_warps + P - 1) / P);
+        if ((long)P < 2L * c->sm_count) NB = (int)std::min<long>(16, (2L * c->sm_count + P - 1) / P);
         A.NB = NB;
-        if (NB > 1) {
-            size_t need = (size_t)std::min(P, c->chunk_sets) * NB * (ncomp == 4 ? 3 : 1) * nE;
+        if (comps || NB > 1) {
+            // component mode keeps one partial per (block, warp) and region; total-only mode one per block
+            size_t per_set = comps ? (size_t)NB * A.warps * 3 * nE : (size_t)NB * nE;
+            size_t need = (size_t)std::min(P, c->chunk_sets) * per_set;
             if (need > c->partial_n) {
                 free_dev(c->d_partial);
                 c->d_partial = nullptr; c->partial_n = 0;

@@ -38,6 +38,7 @@
 #define FULL 0xffffffffu
 #define IMAX 0x7fffffff
 #define NGRID 5 // per-bin constant arrays staged in shared memory: hnu, bbpre, wt, pk, upk
+#define P10_N (RG_NTH + 4)
 
 static __host__ __device__ inline int round_up2(int x) { return (x + 1) & ~1; }
 
@@ -61,6 +62,7 @@ size_t rg_spectrum_smem_bytes(int NC, int nH, int HL, int HH, int warps)
 {
     size_t d = warp_smem_doubles(NC, nH, HL, HH) * warps;
     if (NC <= 8) d += NGRID * 8 * (size_t)32 * NC; // grid constants (global memory for the finest grids)
+    d += P10_N + 8 * (size_t)32 * NC + 8 + 2;      // 10^(0.02 j), hot-shape staging, reduction scratch, item slot
     return d * sizeof(double);
 }
 
@@ -80,18 +82,18 @@ __device__ inline double warp_sum(double v)
 
 // pyNTHCOMP.py:62-73: value of the Kompaneets solution at photon energy e (keV);
 // the reference's monotone cursor restated as a direct search seeded from log10(e).
-__device__ inline double nth_prim(const double *__restrict__ spt, const double *__restrict__ p10, double xmin,
+__device__ inline double nth_prim(const double *__restrict__ spt, const double *p10, double xmin,
                                   double lg511xmin, int nth, double e, double e511, double lge)
 {
     int j = (int)ceil((lge - lg511xmin) * 50.0);
     if (j < 0) j = 0;
     if (j > nth + 1) j = nth + 1;
-    while (j > 0 && !(511.0 * (xmin * __ldg(p10 + j - 1)) < e)) j--;
-    while (j <= nth && 511.0 * (xmin * __ldg(p10 + j)) < e) j++;
+    while (j > 0 && !(511.0 * (xmin * p10[j - 1]) < e)) j--; // p10 lives in shared memory: plain loads
+    while (j <= nth && 511.0 * (xmin * p10[j]) < e) j++;
     if (j > nth) return 0.0;
     if (j == 0) return __ldg(spt);
     int jl = j - 1;
-    double xl = xmin * __ldg(p10 + jl), xh = xmin * __ldg(p10 + jl + 1);
+    double xl = xmin * p10[jl], xh = xmin * p10[jl + 1];
     double sl = __ldg(spt + jl), sh = __ldg(spt + jl + 1);
     return sl + ((e511 - xl) * (sh - sl) / (xh - xl));
 }
@@ -325,6 +327,20 @@ struct Acc {
             for (int c = 0; c < 8; c++) s[c * 32 * NC + 32 * ch + lane] += v[c];
         }
     }
+    // write the accumulators into the warp's transposed buffer (row c, column 32 ch + lane)
+    __device__ inline void dump(double *inBase, int RS)
+    {
+        if (ACC_REG) {
+#pragma unroll
+            for (int ch = 0; ch < NC; ch++)
+#pragma unroll
+                for (int c = 0; c < 8; c++) inBase[c * RS + 32 * ch] = r[ch * 8 + c];
+        } else {
+            for (int ch = 0; ch < NC; ch++)
+#pragma unroll
+                for (int c = 0; c < 8; c++) inBase[c * RS + 32 * ch] = s[c * 32 * NC + 32 * ch + lane];
+        }
+    }
     // out[j] = acc (and restart) for this lane's bins; fully unrolled for the register variant
     __device__ inline void store(double *out, int nE, bool reset)
     {
@@ -360,10 +376,10 @@ __global__ void __launch_bounds__(256, 1) spectrum_kernel(SpecArgs A)
     constexpr int NCOL = 32 * NC;
     RG_DYN_SMEM(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nthreads = blockDim.x, nwarps = nthreads >> 5;
     const int nE = A.grid.nE;
     const bool rel = (A.flags & RG_FLAG_REL) != 0;
     const bool comps = (A.flags & RG_FLAG_COMPONENTS) != 0;
-    const int ncomp = comps ? 4 : 1;
     const int RS = A.HL + NCOL + A.HH;
     const int HSZ = round_up2(A.nH + 24);
 
@@ -371,7 +387,12 @@ __global__ void __launch_bounds__(256, 1) spectrum_kernel(SpecArgs A)
     double *sm = reinterpret_cast<double *>(smem_raw);
     double *sgrid = sm;
     if (GS) sm += NGRID * 8 * NCOL;
+    double *s_p10 = sm; sm += P10_N;          // 10^(0.02 j)
+    double *stage = sm; sm += 8 * NCOL;       // hot spectral shape (times pack factor), natural bin order
+    double *s_red = sm; sm += 8;
+    int *s_misc = reinterpret_cast<int *>(sm); sm += 2;
     const size_t wd = 8 * (size_t)RS + 2 * (size_t)HSZ + (ACC_REG ? 0 : 8 * (size_t)NCOL);
+    double *warp0 = sm;
     double *wbase = sm + wd * warp;
     double *inT = wbase;                  // [8][RS]
     double *Hslot = inT + 8 * (size_t)RS; // [HSZ]: 8 zero pad, nH bins, >= 16 zero pad
@@ -381,7 +402,7 @@ __global__ void __launch_bounds__(256, 1) spectrum_kernel(SpecArgs A)
 
     // ---- CTA prologue: stage the per-bin constants (transposed), zero the warp buffers ----
     if (GS) {
-        for (int i = tid; i < 8 * NCOL; i += blockDim.x) {
+        for (int i = tid; i < 8 * NCOL; i += nthreads) {
             int c = i / NCOL, col = i - c * NCOL;
             int j = 8 * col + c;
             bool ok = j < nE;
@@ -392,31 +413,85 @@ __global__ void __launch_bounds__(256, 1) spectrum_kernel(SpecArgs A)
             sgrid[(4 * 8 + c) * NCOL + col] = ok ? A.grid.Egrid[j] / A.grid.dE[j] : 0.0;
         }
     }
+    for (int i = tid; i < P10_N; i += nthreads) s_p10[i] = A.p10tab[i];
     for (int i = lane; i < 8 * RS + 2 * HSZ; i += 32) wbase[i] = 0.0;
-    __syncthreads(); // the only block barrier: from here on every warp runs on its own
     GridAcc<NC, GS> G;
     G.sm = sgrid; G.g = &A.grid;
     double *const inBase = inT + A.HL + lane; // row 0, this lane's column of chunk 0
     const double dlnE = A.grid.dlnE;
     unsigned long long st_w = 0, st_n = 0;
 
+    // The warps of a CTA work on ONE (parameter set, annulus block) item at a time, annulus g -> warp g mod nwarps.
+    // They exchange no data while walking the annuli; the per-round barrier only keeps them in the same code
+    // region (one instruction-cache working set per SM instead of eight).
     for (;;) {
-        int item = 0;
-        if (lane == 0) item = atomicAdd(A.queue, 1);
-        item = __shfl_sync(FULL, item, 0);
+        __syncthreads();
+        if (tid == 0) s_misc[0] = atomicAdd(A.queue, 1);
+        __syncthreads();
+        const int item = s_misc[0];
         if (item >= A.P * A.NB) break;
         const int set = item / A.NB, blk = item - set * A.NB;
         const SetRec &r = A.recs[set];
-        double *out_item = A.NB == 1 ? A.out + (size_t)set * ncomp * nE
-                                     : A.partial + ((size_t)set * A.NB + blk) * (comps ? 3 : 1) * nE;
+        // destinations: component mode -> per-warp partial arrays [item][warp][3][nE] (folded by the reduce kernel);
+        // total-only mode -> the CTA folds its warps in shared memory and stores once
+        double *part_w = comps ? A.partial + (((size_t)item * nwarps + warp) * 3) * nE : nullptr;
+        double *out_tot = comps ? nullptr : (A.NB == 1 ? A.out + (size_t)set * nE : A.partial + (size_t)item * nE);
         if (r.status != RG_S_OK) { // ValueError sets: zeros (the host class raises)
-            const int nwr = A.NB == 1 ? ncomp : (comps ? 3 : 1);
-            for (int j = lane; j < nwr * nE; j += 32) out_item[j] = 0.0;
+            if (comps) { for (int j = lane; j < 3 * nE; j += 32) part_w[j] = 0.0; }
+            else { for (int j = tid; j < nE; j += nthreads) out_tot[j] = 0.0; }
             continue;
         }
         const int n_tot = r.n_disc + r.n_warm + r.n_hot;
         const int per = (n_tot + A.NB - 1) / A.NB;
         const int g_begin = blk * per, g_end = (g_begin + per < n_tot) ? g_begin + per : n_tot;
+        const int g_warm0 = r.n_disc, g_hot0 = r.n_disc + r.n_warm;
+        const bool hot_here = r.n_hot > 0 && g_end > g_hot0 && g_begin < n_tot;       // item holds hot annuli
+        const bool owns_hot0 = r.n_hot > 0 && g_begin <= g_hot0 && g_hot0 < g_end;    // ... the first of them
+        const bool need_shape = rel ? hot_here : owns_hot0;
+
+        // ---- hot spectral shape, computed once by the whole CTA (relagn.py:1200-1223):
+        //      donthcomp(Egrid, [gamma_h, kTe_h, kT_seed, 0, 0]) * h / keV; shape_int = trapz(Fnu, nu)
+        double shape_int = 0.0;
+        if (need_shape) {
+            const int BPT = (8 * NCOL + nthreads - 1) / nthreads;
+            double part = 0;
+            const double *hot_spt = nullptr;
+            double hot_xmin = 0, hot_norm = 0, hot_lgx = 0;
+            int hot_nth = 0;
+            if (r.has_hotshape) {
+                const int sys = r.sys_base + r.n_warm;
+                const double *hd = A.header + (size_t)sys * 4;
+                hot_xmin = hd[0]; hot_norm = hd[1]; hot_lgx = hd[3];
+                hot_nth = (int)hd[2];
+                hot_spt = A.sptot + (size_t)sys * RG_SPT_STRIDE;
+            }
+            const int j0 = BPT * tid;
+            double e_prev = 0.0, pr_prev = 0.0;
+            if (hot_spt && j0 > 0 && j0 - 1 < nE) {
+                e_prev = __ldg(A.grid.Egrid + j0 - 1);
+                pr_prev = nth_prim(hot_spt, s_p10, hot_xmin, hot_lgx, hot_nth, e_prev, __ldg(A.grid.e511 + j0 - 1),
+                                   __ldg(A.grid.lgE + j0 - 1)) / __ldg(A.grid.ear2 + j0 - 1);
+            }
+            for (int q = 0; q < BPT; q++) {
+                const int j = j0 + q;
+                if (j >= 8 * NCOL) break;
+                double F = 0.0;
+                if (hot_spt && j < nE) {
+                    double e = __ldg(A.grid.Egrid + j);
+                    double pr = nth_prim(hot_spt, s_p10, hot_xmin, hot_lgx, hot_nth, e, __ldg(A.grid.e511 + j),
+                                         __ldg(A.grid.lgE + j)) / __ldg(A.grid.ear2 + j);
+                    double ph = j > 0 ? (0.5 * (pr + pr_prev) * (e - e_prev) * hot_norm) : 0.0;
+                    F = ph * (1.0 / RGK_KEV) * RGK_H;
+                    e_prev = e; pr_prev = pr;
+                }
+                part += F * G.wt(j & 7, j >> 3);
+                stage[j] = F * G.pk(j & 7, j >> 3);
+            }
+            part = warp_sum(part);
+            if (lane == 0) s_red[warp] = part;
+            __syncthreads();
+            for (int w = 0; w < nwarps; w++) shape_int += s_red[w];
+        }
 
         NtConst nt;
         rg_nt_prepare(nt, r);
@@ -451,316 +526,260 @@ __global__ void __launch_bounds__(256, 1) spectrum_kernel(SpecArgs A)
         Acc<NC, ACC_REG> acc;
         acc.s = acc_s; acc.lane = lane;
         acc.zero();
+        if (comps) { for (int j = lane; j < 3 * nE; j += 32) part_w[j] = 0.0; }
+        if (rel && hot_here) { for (int q = lane; q < HSZ; q += 32) Hsum[q] = 0.0; }
+        __syncwarp();
+        int cur_region = 0;                // component mode: region the accumulators currently belong to
         int hz_min = IMAX, hz_max = -IMAX; // touched range of the H slot (for re-zeroing)
+        bool hot_any_conv = false, hot_mine = false;
+        int hk_min = IMAX, hk_max = -IMAX;
+        double Sflat = 0.0;
 
-        // ------------------------------------------------------------------
-        // regions: 0 disc [r_w, r_out], 1 warm [r_h, r_w], 2 hot [risco, r_h]
-        int g_reg0 = 0; // global index of the region's first annulus
-        for (int region = 0; region < 3; region++) {
-            const int n_ann = region == 0 ? r.n_disc : (region == 1 ? r.n_warm : r.n_hot);
-            const double lg_in = region == 0 ? r.lg_rw : (region == 1 ? r.lg_rh : r.lg_risco);
-            const double lg_out = region == 0 ? r.lg_rout : (region == 1 ? r.lg_rw : r.lg_rh);
-            // annuli of this region handled by this item (region-local, counted top-down)
-            int a0 = g_begin - g_reg0, a1 = g_end - g_reg0;
-            a0 = a0 < 0 ? 0 : a0;
-            a1 = a1 > n_ann ? n_ann : a1;
-            const bool owns_first = g_begin <= g_reg0 && g_reg0 < g_end; // owns the region's first annulus
-            g_reg0 += n_ann;
-            const bool active = a0 < a1;
-
-            bool hot_any_conv = false;
-            int hk_min = IMAX, hk_max = -IMAX;
-            double Sflat = 0.0;
-            double shape_int = 0.0;
-
-            if (region == 2 && n_ann > 0 && (rel ? active : owns_first)) {
-                // hot shape (relagn.py:1200-1223): donthcomp(Egrid, [gamma_h, kTe_h, kT_seed, 0, 0]) * h / keV,
-                // written (times the pack factor) to the warp buffer; shape_int = trapz(Fnu, nu)
-                const double *hot_spt = nullptr;
-                double hot_xmin = 0, hot_norm = 0, hot_lgx = 0;
-                int hot_nth = 0;
-                if (r.has_hotshape) {
-                    const int sys = r.sys_base + r.n_warm;
-                    const double *hd = A.header + (size_t)sys * 4;
-                    hot_xmin = hd[0]; hot_norm = hd[1]; hot_lgx = hd[3];
-                    hot_nth = (int)hd[2];
-                    hot_spt = A.sptot + (size_t)sys * RG_SPT_STRIDE;
+        const int n_rounds = (g_end - g_begin + nwarps - 1) / nwarps;
+        for (int m0 = 0; m0 < n_rounds; m0 += 32) {
+            // ---- prologue: lane m prepares this warp's annulus of round m0 + m: g = g_begin + warp + nwarps (m0 + m),
+            //      counted top-down through disc [r_w, r_out], warm [r_h, r_w], hot [risco, r_h] ----
+            double p_r1 = 0, p_r2 = 0, p_s1 = 0, p_s2 = 0, p_geo = 0;
+            int p_flag = 0, p_jz = nE, p_region = -1, p_loc = 0;
+            {
+                const int g = g_begin + warp + nwarps * (m0 + lane);
+                if (m0 + lane < n_rounds && g < g_end) {
+                    const int region = g < g_warm0 ? 0 : (g < g_hot0 ? 1 : 2);
+                    const int a = g - (region == 0 ? 0 : (region == 1 ? g_warm0 : g_hot0));
+                    const double lg_in = region == 0 ? r.lg_rw : (region == 1 ? r.lg_rh : r.lg_risco);
+                    const double lg_out = region == 0 ? r.lg_rout : (region == 1 ? r.lg_rw : r.lg_rh);
+                    BinIter it;
+                    it.start(lg_in, lg_out, r.dlog_r);
+                    double lo = 0, hi = 0;
+                    for (int q = 0; q <= a; q++) it.next(lo, hi);
+                    double r1 = pow(10.0, lo), r2 = pow(10.0, hi);
+                    double rmid = pow(10.0, lo + r.dlog_r / 2);
+                    double T4 = rg_tnt4(nt, rmid);
+                    if (region == 0) { // relagn.py:857-883
+                        double Tann = pow(T4, 0.25);
+                        double fcol_r = r.fcol < 0 ? rg_fcol(Tann) : r.fcol;
+                        Tann = Tann * fcol_r;
+                        double t = Tann / fcol_r;
+                        p_s1 = RGK_KB * Tann;
+                        p_s2 = RGK_SB * (t * t * t * t) * Rg2;
+                        // first bin whose Planck exponent overflows (exp(x) = inf for x > 709.78 -> B = 0 exactly)
+                        const double lim = 710.0 * p_s1;
+                        int lo_j = 0, hi_j = nE;
+                        while (lo_j < hi_j) {
+                            int m = (lo_j + hi_j) >> 1;
+                            if (__ldg(A.grid.hnu + m) > lim) hi_j = m; else lo_j = m + 1;
+                        }
+                        p_jz = lo_j;
+                    } else if (region == 1) { // relagn.py:919-932
+                        double Tann = pow(T4, 0.25);
+                        p_s2 = RGK_SB * (Tann * Tann * Tann * Tann) * Rg2;
+                    } else { // relagn.py:1309-1314
+                        double Ldiss_ann = RGK_SB * T4 * Rg2;
+                        double Lseed_ann = r.Lseed / (4 * RGK_PI * rmid * (r2 - r1) * r.n_hot);
+                        p_s1 = Ldiss_ann + Lseed_ann;
+                    }
+                    // flat space (relagn.py:1013,1110,1370) / non-relativistic (relagn.py:1046,1143) area factor
+                    p_geo = 2 * RGK_PI * 2 * rmid * (r2 - r1);
+                    if (region != 2) p_geo = p_geo * r.cosinc / 0.5;
+                    p_r1 = r1; p_r2 = r2;
+                    p_flag = (rel && lo <= 3 && hi <= 3) ? 1 : 0; // relagn.py:992
+                    p_region = region; p_loc = a;
                 }
+            }
+            const int mt = n_rounds - m0 < 32 ? n_rounds - m0 : 32;
+            for (int mi = 0; mi < mt; mi++) {
+                __syncthreads(); // lockstep only: no data crosses warps here
+                const int region = __shfl_sync(FULL, p_region, mi);
+                if (region < 0) continue; // no annulus left for this warp in this round
+                if (region == 2 && !rel) continue; // non-relativistic hot component needs no annuli (relagn.py:1387-1401)
+                const double r1 = __shfl_sync(FULL, p_r1, mi), r2 = __shfl_sync(FULL, p_r2, mi);
+                const double s1 = __shfl_sync(FULL, p_s1, mi), s2 = __shfl_sync(FULL, p_s2, mi);
+                const double geo = __shfl_sync(FULL, p_geo, mi);
+                const bool conv = __shfl_sync(FULL, p_flag, mi) != 0;
+                const int jz = __shfl_sync(FULL, p_jz, mi);
+                const int loc = __shfl_sync(FULL, p_loc, mi);
+                if (comps && region != cur_region && region != 2) { // (hot contributes after the loop)
+                    acc.store(part_w + (size_t)cur_region * nE, nE, true);
+                    cur_region = region;
+                }
+                int kmn = 0, kmx = -1;
+                if (conv) {
+                    // re-zero what the previous annulus touched, then build this annulus' histogram
+                    for (int k = hz_min + lane; k <= hz_max; k += 32) {
+                        int q = k - K_LO;
+                        if (q >= 0 && q < nH) Hslot[8 + q] = 0.0;
+                    }
+                    __syncwarp();
+                    warp_build_hist(Hslot + 8, K_LO, nH, ts, r1, r2, dlnE, kmn, kmx);
+                    hz_min = kmn; hz_max = kmx;
+                    if (kmn <= kmx) { st_w += (unsigned long long)(kmx - kmn + 1); st_n += 1; }
+                }
+                if (region == 2) {
+                    // hot: fold into this warp's region histogram (weighted by the annulus luminosity)
+                    hot_mine = true;
+                    if (conv) {
+                        for (int k = kmn + lane; k <= kmx; k += 32) {
+                            int q = k - K_LO;
+                            if (q >= 0 && q < nH) Hsum[8 + q] += s1 * Hslot[8 + q];
+                        }
+                        hk_min = kmn < hk_min ? kmn : hk_min;
+                        hk_max = kmx > hk_max ? kmx : hk_max;
+                        hot_any_conv = true;
+                        __syncwarp();
+                    } else {
+                        Sflat += s1 * geo;
+                    }
+                    continue;
+                }
+
+                // ---- local spectrum, chunk by chunk ----
+                const int nch_live = region == 0 ? ((jz + 255) >> 8) : NC; // chunks holding a non-zero bin
                 double part = 0;
+                const double *w_spt = nullptr;
+                double w_xmin = 0, w_norm = 0, w_lgx = 0;
+                int w_nth = 0;
+                if (region == 1) {
+                    const int sys = r.sys_base + loc;
+                    const double *hd = A.header + (size_t)sys * 4;
+                    w_xmin = hd[0]; w_norm = hd[1]; w_lgx = hd[3];
+                    w_nth = (int)hd[2];
+                    w_spt = A.sptot + (size_t)sys * RG_SPT_STRIDE;
+                }
                 for (int ch = 0; ch < NC; ch++) {
                     const int col = 32 * ch + lane, j0 = 8 * col;
-                    double F[8];
+                    double L[8];
 #pragma unroll
-                    for (int c = 0; c < 8; c++) F[c] = 0.0;
-                    if (hot_spt && j0 < nE) {
+                    for (int c = 0; c < 8; c++) L[c] = 0.0;
+                    if (ch >= nch_live) {
+                        // Wien tail past the overflow point: identically zero
+                    } else if (region == 0) {
+#pragma unroll
+                        for (int c = 0; c < 8; c++) {
+                            double ef = exp(G.hnu(c, col) / s1) - 1;
+                            L[c] = RGK_PI * (G.bbpre(c, col) / ef);
+                            part += L[c] * G.wt(c, col);
+                        }
+                    } else if (j0 < nE) {
                         double e_prev = 0.0, pr_prev = 0.0;
                         if (j0 > 0) {
                             e_prev = __ldg(A.grid.Egrid + j0 - 1);
-                            pr_prev = nth_prim(hot_spt, A.p10tab, hot_xmin, hot_lgx, hot_nth, e_prev,
-                                               __ldg(A.grid.e511 + j0 - 1), __ldg(A.grid.lgE + j0 - 1)) /
-                                      __ldg(A.grid.ear2 + j0 - 1);
+                            pr_prev = nth_prim(w_spt, s_p10, w_xmin, w_lgx, w_nth, e_prev, __ldg(A.grid.e511 + j0 - 1),
+                                               __ldg(A.grid.lgE + j0 - 1)) / __ldg(A.grid.ear2 + j0 - 1);
                         }
 #pragma unroll
                         for (int c = 0; c < 8; c++) {
                             int j = j0 + c;
                             if (j < nE) {
                                 double e = __ldg(A.grid.Egrid + j);
-                                double pr = nth_prim(hot_spt, A.p10tab, hot_xmin, hot_lgx, hot_nth, e,
-                                                     __ldg(A.grid.e511 + j), __ldg(A.grid.lgE + j)) / __ldg(A.grid.ear2 + j);
-                                double ph = j > 0 ? (0.5 * (pr + pr_prev) * (e - e_prev) * hot_norm) : 0.0;
-                                F[c] = ph * (1.0 / RGK_KEV) * RGK_H;
+                                double pr = nth_prim(w_spt, s_p10, w_xmin, w_lgx, w_nth, e, __ldg(A.grid.e511 + j),
+                                                     __ldg(A.grid.lgE + j)) / __ldg(A.grid.ear2 + j);
+                                double ph = j > 0 ? (0.5 * (pr + pr_prev) * (e - e_prev) * w_norm) : 0.0;
+                                L[c] = ph * (1.0 / RGK_KEV) * RGK_H;
                                 e_prev = e; pr_prev = pr;
                             }
+                            part += L[c] * G.wt(c, col);
                         }
                     }
+                    // publish: packed for the transfer convolution, plain for the flat / non-relativistic sum
+                    if (conv) {
 #pragma unroll
-                    for (int c = 0; c < 8; c++) {
-                        part += F[c] * G.wt(c, col);
-                        inBase[c * RS + 32 * ch] = F[c] * G.pk(c, col);
+                        for (int c = 0; c < 8; c++) inBase[c * RS + 32 * ch] = L[c] * G.pk(c, col);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 8; c++) inBase[c * RS + 32 * ch] = L[c];
                     }
                 }
-                shape_int = warp_sum(part);
-                if (rel) {
-                    for (int q = lane; q < HSZ; q += 32) Hsum[q] = 0.0;
+                if (region == 0 && A.grid.n_ext) { // relagn.py:868-873
+                    for (int q = lane; q < A.grid.n_ext; q += 32) {
+                        double ef = exp(A.grid.x_hnu[q] / s1) - 1;
+                        part += RGK_PI * (A.grid.x_bbpre[q] / ef) * A.grid.x_wt[q];
+                    }
                 }
+                const double radiance = warp_sum(part);
                 __syncwarp();
-            }
-
-            if (region == 2 && !rel) {
-                // non-relativistic hot component (relagn.py:1387-1401): (Ldiss + Lseed) * Fnu / trapz(Fnu)
-                if (n_ann > 0 && owns_first) {
-                    const double Lum = r.Ldiss + r.Lseed;
-                    for (int ch = 0; ch < NC; ch++) {
-                        const int col = 32 * ch + lane;
-                        double v[8];
-#pragma unroll
-                        for (int c = 0; c < 8; c++) {
-                            // the buffer holds F * pk and pk * upk = 4; F / shape_int: 0/0 -> NaN as the reference
-                            double F = inBase[c * RS + 32 * ch] * G.upk(c, col) * 0.25;
-                            v[c] = (8 * col + c < nE) ? Lum * (F / shape_int) : 0.0;
-                        }
-                        acc.add(ch, v);
-                    }
-                    __syncwarp();
-                }
-            } else {
-                for (int t0 = a0; t0 < a1; t0 += 32) {
-                    const int n_tile = a1 - t0 < 32 ? a1 - t0 : 32;
-                    // ---- prologue: lane i prepares annulus t0 + i (counted top-down) ----
-                    double p_r1 = 0, p_r2 = 0, p_s1 = 0, p_s2 = 0, p_geo = 0;
-                    int p_flag = 0, p_jz = nE;
-                    if (lane < n_tile) {
-                        BinIter it;
-                        it.start(lg_in, lg_out, r.dlog_r);
-                        double lo = 0, hi = 0;
-                        for (int q = 0; q <= t0 + lane; q++) it.next(lo, hi);
-                        double r1 = pow(10.0, lo), r2 = pow(10.0, hi);
-                        double rmid = pow(10.0, lo + r.dlog_r / 2);
-                        double T4 = rg_tnt4(nt, rmid);
-                        if (region == 0) { // relagn.py:857-883
-                            double Tann = pow(T4, 0.25);
-                            double fcol_r = r.fcol < 0 ? rg_fcol(Tann) : r.fcol;
-                            Tann = Tann * fcol_r;
-                            double t = Tann / fcol_r;
-                            p_s1 = RGK_KB * Tann;
-                            p_s2 = RGK_SB * (t * t * t * t) * Rg2;
-                            // first bin whose Planck exponent overflows (exp(x) = inf for x > 709.78 -> B = 0 exactly)
-                            const double lim = 710.0 * p_s1;
-                            int a = 0, b = nE;
-                            while (a < b) {
-                                int m = (a + b) >> 1;
-                                if (__ldg(A.grid.hnu + m) > lim) b = m; else a = m + 1;
-                            }
-                            p_jz = a;
-                        } else if (region == 1) { // relagn.py:919-932
-                            double Tann = pow(T4, 0.25);
-                            p_s2 = RGK_SB * (Tann * Tann * Tann * Tann) * Rg2;
-                        } else { // relagn.py:1309-1314
-                            double Ldiss_ann = RGK_SB * T4 * Rg2;
-                            double Lseed_ann = r.Lseed / (4 * RGK_PI * rmid * (r2 - r1) * n_ann);
-                            p_s1 = Ldiss_ann + Lseed_ann;
-                        }
-                        // flat space (relagn.py:1013,1110,1370) / non-relativistic (relagn.py:1046,1143) area factor
-                        p_geo = 2 * RGK_PI * 2 * rmid * (r2 - r1);
-                        if (region != 2) p_geo = p_geo * r.cosinc / 0.5;
-                        p_r1 = r1; p_r2 = r2;
-                        p_flag = (rel && lo <= 3 && hi <= 3) ? 1 : 0; // relagn.py:992
-                    }
-
-                    for (int i = 0; i < n_tile; i++) {
-                        const double r1 = __shfl_sync(FULL, p_r1, i), r2 = __shfl_sync(FULL, p_r2, i);
-                        const double s1 = __shfl_sync(FULL, p_s1, i), s2 = __shfl_sync(FULL, p_s2, i);
-                        const double geo = __shfl_sync(FULL, p_geo, i);
-                        const bool conv = __shfl_sync(FULL, p_flag, i) != 0;
-                        const int jz = __shfl_sync(FULL, p_jz, i);
-                        int kmn = 0, kmx = -1;
-                        if (conv) {
-                            // re-zero what the previous annulus touched, then build this annulus' histogram
-                            for (int k = hz_min + lane; k <= hz_max; k += 32) {
-                                int q = k - K_LO;
-                                if (q >= 0 && q < nH) Hslot[8 + q] = 0.0;
-                            }
-                            __syncwarp();
-                            warp_build_hist(Hslot + 8, K_LO, nH, ts, r1, r2, dlnE, kmn, kmx);
-                            hz_min = kmn; hz_max = kmx;
-                            if (kmn <= kmx) { st_w += (unsigned long long)(kmx - kmn + 1); st_n += 1; }
-                        }
-                        if (region == 2) {
-                            // hot: fold into the region histogram (weighted by the annulus luminosity)
-                            if (conv) {
-                                for (int k = kmn + lane; k <= kmx; k += 32) {
-                                    int q = k - K_LO;
-                                    if (q >= 0 && q < nH) Hsum[8 + q] += s1 * Hslot[8 + q];
-                                }
-                                hk_min = kmn < hk_min ? kmn : hk_min;
-                                hk_max = kmx > hk_max ? kmx : hk_max;
-                                hot_any_conv = true;
-                                __syncwarp();
-                            } else {
-                                Sflat += s1 * geo;
-                            }
-                            continue;
-                        }
-
-                        // ---- local spectrum, chunk by chunk ----
-                        const int nch_live = region == 0 ? ((jz + 255) >> 8) : NC; // chunks holding a non-zero bin
-                        double part = 0;
-                        const double *w_spt = nullptr;
-                        double w_xmin = 0, w_norm = 0, w_lgx = 0;
-                        int w_nth = 0;
-                        if (region == 1) {
-                            const int sys = r.sys_base + t0 + i;
-                            const double *hd = A.header + (size_t)sys * 4;
-                            w_xmin = hd[0]; w_norm = hd[1]; w_lgx = hd[3];
-                            w_nth = (int)hd[2];
-                            w_spt = A.sptot + (size_t)sys * RG_SPT_STRIDE;
-                        }
+                // Lnu = norm * (B / radiance), zero when the annulus emits nothing (relagn.py:885-889, 933-937)
+                if (radiance != 0) {
+                    if (conv) {
+                        const double scale = s2 / radiance;
                         for (int ch = 0; ch < NC; ch++) {
-                            const int col = 32 * ch + lane, j0 = 8 * col;
-                            double L[8];
+                            // taps whose sources all lie in the zero zones (j - k >= jz or j - k < 0) are skipped
+                            int k_lo = 256 * ch - (region == 0 ? jz : nE) + 1, k_hi = 256 * ch + 255;
+                            k_lo = k_lo > kmn ? k_lo : kmn;
+                            k_hi = k_hi < kmx ? k_hi : kmx;
+                            if (k_lo > k_hi) continue;
+                            const int col = 32 * ch + lane;
+                            double tmp[8];
+                            convolve8(Hslot + 8, K_LO, nH, k_lo, k_hi, inBase + 32 * ch, RS, tmp);
 #pragma unroll
-                            for (int c = 0; c < 8; c++) L[c] = 0.0;
-                            if (ch >= nch_live) {
-                                // Wien tail past the overflow point: identically zero
-                            } else if (region == 0) {
-#pragma unroll
-                                for (int c = 0; c < 8; c++) {
-                                    double ef = exp(G.hnu(c, col) / s1) - 1;
-                                    L[c] = RGK_PI * (G.bbpre(c, col) / ef);
-                                    part += L[c] * G.wt(c, col);
-                                }
-                            } else if (j0 < nE) {
-                                double e_prev = 0.0, pr_prev = 0.0;
-                                if (j0 > 0) {
-                                    e_prev = __ldg(A.grid.Egrid + j0 - 1);
-                                    pr_prev = nth_prim(w_spt, A.p10tab, w_xmin, w_lgx, w_nth, e_prev,
-                                                       __ldg(A.grid.e511 + j0 - 1), __ldg(A.grid.lgE + j0 - 1)) /
-                                              __ldg(A.grid.ear2 + j0 - 1);
-                                }
-#pragma unroll
-                                for (int c = 0; c < 8; c++) {
-                                    int j = j0 + c;
-                                    if (j < nE) {
-                                        double e = __ldg(A.grid.Egrid + j);
-                                        double pr = nth_prim(w_spt, A.p10tab, w_xmin, w_lgx, w_nth, e,
-                                                             __ldg(A.grid.e511 + j), __ldg(A.grid.lgE + j)) /
-                                                    __ldg(A.grid.ear2 + j);
-                                        double ph = j > 0 ? (0.5 * (pr + pr_prev) * (e - e_prev) * w_norm) : 0.0;
-                                        L[c] = ph * (1.0 / RGK_KEV) * RGK_H;
-                                        e_prev = e; pr_prev = pr;
-                                    }
-                                    part += L[c] * G.wt(c, col);
-                                }
-                            }
-                            // publish: packed for the transfer convolution, plain for the flat / non-relativistic sum
-                            if (conv) {
-#pragma unroll
-                                for (int c = 0; c < 8; c++) inBase[c * RS + 32 * ch] = L[c] * G.pk(c, col);
-                            } else {
-#pragma unroll
-                                for (int c = 0; c < 8; c++) inBase[c * RS + 32 * ch] = L[c];
-                            }
+                            for (int c = 0; c < 8; c++) tmp[c] *= scale * G.upk(c, col);
+                            acc.add(ch, tmp);
                         }
-                        if (region == 0 && A.grid.n_ext) { // relagn.py:868-873
-                            for (int q = lane; q < A.grid.n_ext; q += 32) {
-                                double ef = exp(A.grid.x_hnu[q] / s1) - 1;
-                                part += RGK_PI * (A.grid.x_bbpre[q] / ef) * A.grid.x_wt[q];
-                            }
-                        }
-                        const double radiance = warp_sum(part);
-                        __syncwarp();
-                        // Lnu = norm * (B / radiance), zero when the annulus emits nothing (relagn.py:885-889, 933-937)
-                        if (radiance != 0) {
-                            if (conv) {
-                                const double scale = s2 / radiance;
-                                for (int ch = 0; ch < NC; ch++) {
-                                    // taps whose sources all lie in the zero zones (j - k >= jz or j - k < 0) are skipped
-                                    int k_lo = 256 * ch - (region == 0 ? jz : nE) + 1, k_hi = 256 * ch + 255;
-                                    k_lo = k_lo > kmn ? k_lo : kmn;
-                                    k_hi = k_hi < kmx ? k_hi : kmx;
-                                    if (k_lo > k_hi) continue;
-                                    const int col = 32 * ch + lane;
-                                    double tmp[8];
-                                    convolve8(Hslot + 8, K_LO, nH, k_lo, k_hi, inBase + 32 * ch, RS, tmp);
+                    } else {
+                        const double scale = (s2 / radiance) * geo;
+                        for (int ch = 0; ch < nch_live; ch++) {
+                            double v[8];
 #pragma unroll
-                                    for (int c = 0; c < 8; c++) tmp[c] *= scale * G.upk(c, col);
-                                    acc.add(ch, tmp);
-                                }
-                            } else {
-                                const double scale = (s2 / radiance) * geo;
-                                for (int ch = 0; ch < nch_live; ch++) {
-                                    double v[8];
-#pragma unroll
-                                    for (int c = 0; c < 8; c++) v[c] = scale * inBase[c * RS + 32 * ch];
-                                    acc.add(ch, v);
-                                }
-                            }
+                            for (int c = 0; c < 8; c++) v[c] = scale * inBase[c * RS + 32 * ch];
+                            acc.add(ch, v);
                         }
-                        __syncwarp(); // the buffer is rewritten by the next annulus
                     }
                 }
-
-                if (region == 2 && active) {
-                    // one convolution for the whole hot region; rel result / (cos i / 0.5) (relagn.py:1362).
-                    // The buffer still holds F * pk; F / shape_int: 0/0 -> NaN as the reference (:1316)
-                    __syncwarp();
-                    for (int ch = 0; ch < NC; ch++) {
-                        const int col = 32 * ch + lane;
-                        double tmp[8];
-#pragma unroll
-                        for (int c = 0; c < 8; c++) tmp[c] = 0.0;
-                        if (hot_any_conv) convolve8(Hsum + 8, K_LO, nH, hk_min, hk_max, inBase + 32 * ch, RS, tmp);
-                        double v[8];
-#pragma unroll
-                        for (int c = 0; c < 8; c++) {
-                            v[c] = 0.0;
-                            if (8 * col + c < nE) {
-                                double F = inBase[c * RS + 32 * ch] * G.upk(c, col) * 0.25;
-                                v[c] = Sflat * (F / shape_int);
-                                if (hot_any_conv) v[c] += ((tmp[c] / shape_int) * G.upk(c, col)) / cosfac;
-                            }
-                        }
-                        acc.add(ch, v);
-                    }
-                    __syncwarp();
-                }
+                __syncwarp(); // the buffer is rewritten by the next annulus
             }
-
-            // ---- region epilogue: with components, store and restart the accumulators ----
-            if (comps) acc.store(out_item + (size_t)region * nE, nE, true);
         }
-        // ---- item epilogue ----
-        if (!comps) {
-            acc.store(out_item, nE, false);
-        } else if (A.NB == 1) {
+
+        // ---- hot region: one convolution per warp over the histograms it collected ----
+        const bool nonrel_hot = !rel && owns_hot0 && warp == 0; // (Ldiss + Lseed) * Fnu / trapz(Fnu), relagn.py:1387-1401
+        if ((rel && hot_mine) || nonrel_hot) {
+            if (comps && cur_region != 2) {
+                acc.store(part_w + (size_t)cur_region * nE, nE, true);
+                cur_region = 2;
+            }
+            __syncwarp();
             for (int ch = 0; ch < NC; ch++) {
-                const int j0 = 8 * (32 * ch + lane);
+#pragma unroll
+                for (int c = 0; c < 8; c++) inBase[c * RS + 32 * ch] = stage[8 * (32 * ch + lane) + c];
+            }
+            __syncwarp();
+            const double Lum = r.Ldiss + r.Lseed;
+            for (int ch = 0; ch < NC; ch++) {
+                const int col = 32 * ch + lane;
+                double tmp[8];
+#pragma unroll
+                for (int c = 0; c < 8; c++) tmp[c] = 0.0;
+                if (rel && hot_any_conv) convolve8(Hsum + 8, K_LO, nH, hk_min, hk_max, inBase + 32 * ch, RS, tmp);
+                double v[8];
 #pragma unroll
                 for (int c = 0; c < 8; c++) {
-                    int j = j0 + c;
-                    if (j < nE)
-                        out_item[(size_t)3 * nE + j] = (out_item[j] + out_item[(size_t)nE + j]) + out_item[(size_t)2 * nE + j];
+                    v[c] = 0.0;
+                    if (8 * col + c < nE) {
+                        // the buffer holds F * pk and pk * upk = 4; F / shape_int: 0/0 -> NaN as the reference (:1316)
+                        double F = inBase[c * RS + 32 * ch] * G.upk(c, col) * 0.25;
+                        if (rel) {
+                            v[c] = Sflat * (F / shape_int);
+                            if (hot_any_conv) v[c] += ((tmp[c] / shape_int) * G.upk(c, col)) / cosfac; // relagn.py:1362
+                        } else {
+                            v[c] = Lum * (F / shape_int);
+                        }
+                    }
                 }
+                acc.add(ch, v);
+            }
+            __syncwarp();
+        }
+
+        // ---- item epilogue ----
+        if (comps) {
+            acc.store(part_w + (size_t)cur_region * nE, nE, false);
+        } else {
+            // fold the warps in shared memory (fixed order) and store once
+            acc.dump(inBase, RS);
+            __syncthreads();
+            for (int j = tid; j < nE; j += nthreads) {
+                const size_t off = (size_t)(j & 7) * RS + A.HL + (j >> 3);
+                double v = 0.0;
+                for (int w = 0; w < nwarps; w++) v += warp0[wd * w + off];
+                out_tot[j] = v;
             }
         }
         // leave the H slot clean for the next item
@@ -768,7 +787,6 @@ __global__ void __launch_bounds__(256, 1) spectrum_kernel(SpecArgs A)
             int q = k - K_LO;
             if (q >= 0 && q < nH) Hslot[8 + q] = 0.0;
         }
-        __syncwarp();
     }
     if (A.stats && lane == 0 && st_n) {
         atomicAdd(&A.stats[0], st_w);
@@ -776,9 +794,10 @@ __global__ void __launch_bounds__(256, 1) spectrum_kernel(SpecArgs A)
     }
 }
 
-// NB > 1: out[set][c] = sum over blocks of partial[set][blk][c] in block order; total = disc + warm + hot
-__global__ void __launch_bounds__(256) reduce_blocks_kernel(const double *__restrict__ partial, double *__restrict__ out,
-                                                            int P, int NB, int nE, int comps)
+// Fold partial spectra: out[set][c] = sum_q partial[set][q][c] in fixed order q = 0..nparts-1
+// (component mode: q runs over blocks x warps and total = disc + warm + hot; total-only mode: q runs over blocks)
+__global__ void __launch_bounds__(256) reduce_parts_kernel(const double *__restrict__ partial, double *__restrict__ out,
+                                                           int P, int nparts, int nE, int comps)
 {
     const int npc = comps ? 3 : 1;
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -787,7 +806,7 @@ __global__ void __launch_bounds__(256) reduce_blocks_kernel(const double *__rest
     double tot = 0;
     for (int c = 0; c < npc; c++) {
         double s = 0;
-        for (int b = 0; b < NB; b++) s += partial[(((size_t)set * NB + b) * npc + c) * nE + j];
+        for (int q = 0; q < nparts; q++) s += partial[(((size_t)set * nparts + q) * npc + c) * nE + j];
         if (comps) out[((size_t)set * 4 + c) * nE + j] = s;
         tot += s;
     }
@@ -800,15 +819,15 @@ static int launch_spec(const SpecArgs &args, int sm_count, cudaStream_t st)
     size_t smem = rg_spectrum_smem_bytes(NC, args.nH, args.HL, args.HH, args.warps);
     RG_CUDA_OK(cudaFuncSetAttribute(spectrum_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long items = (long)args.P * args.NB;
-    long ctas = (items + args.warps - 1) / args.warps;
-    if (ctas > sm_count) ctas = sm_count; // persistent: one CTA per SM, warps pull items from the queue
+    long ctas = items < sm_count ? items : sm_count; // persistent: one CTA per SM, CTAs pull items from the queue
     RG_CUDA_OK(cudaMemsetAsync(args.queue, 0, sizeof(int), st));
     RG_LAUNCH(spectrum_kernel<NC>, dim3((unsigned)ctas), dim3(32 * args.warps), smem, st, args);
     RG_CUDA_OK(cudaGetLastError());
-    if (args.NB > 1) {
+    const bool comps = (args.flags & RG_FLAG_COMPONENTS) != 0;
+    if (comps || args.NB > 1) {
         size_t n = (size_t)args.P * args.grid.nE;
-        RG_LAUNCH(reduce_blocks_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, args.partial, args.out, args.P,
-                  args.NB, args.grid.nE, (args.flags & RG_FLAG_COMPONENTS) ? 1 : 0);
+        RG_LAUNCH(reduce_parts_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, args.partial, args.out, args.P,
+                  comps ? args.NB * args.warps : args.NB, args.grid.nE, comps ? 1 : 0);
         RG_CUDA_OK(cudaGetLastError());
     }
     return RG_OK;
