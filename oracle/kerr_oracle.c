@@ -28,8 +28,8 @@
  *    (removes frame-dragging winding between rows), float32;
  *  - lookup: linear in log10((r - r_h)/(risco - r_h)) of the model's own spin,
  *    in risco(a) between spin nodes and in theta between inclination nodes;
- *  - an annulus is cut into n_sub rings at log-midpoints with exact area
- *    weights; each ring is a closed polyline in phi; every phi segment spreads
+ *  - an annulus is cut into n_sub rings (ro_auto_nsub: radial shift variation per
+ *    ring below ~half an energy bin) at log-midpoints with exact area weights; each ring is a closed polyline in phi; every phi segment spreads
  *    its weight uniformly in s = ln(g)/dlnE between its end points and is
  *    deposited on integer shifts with a linear (hat) kernel;
  *  - on a geometric energy grid the convolution is out_j = sum_k Hc[k] in_{j-k}.
@@ -468,6 +468,25 @@ static void deposit(double *H, int K_LO, int nH, double sa, double sb, double W)
     }
 }
 
+/* number of rings an annulus [r1,r2] is cut into: the radial variation of the shift across one ring is kept
+ * below about half an energy bin.  |d ln g / d ln r| <= kappa with kappa = 1.5/(r-3) + 0.5/sqrt(r) (gravitational
+ * + orbital Doppler term of a Keplerian disc), capped at 0.5 (the value at r = 6) and used as 0.5 for wide annuli
+ * (the stand-alone kyconv seam) where one kappa does not describe the whole annulus. */
+int ro_auto_nsub(double r1, double r2, double dlnE)
+{
+    double lnr = log(r2 / r1);
+    double kappa = 0.5;
+    if (lnr <= 0.2) {
+        double rg = sqrt(r1 * r2);
+        if (rg > 6.0) {
+            kappa = 1.5 / (rg - 3.0) + 0.5 / sqrt(rg);
+            if (kappa > 0.5) kappa = 0.5;
+        }
+    }
+    int nsub = 1 + (int)floor(kappa * lnr / dlnE);
+    return nsub > 4096 ? 4096 : nsub;
+}
+
 int ro_ky_kernel(const ro_tables *t, double a, double theta_o, double r1, double r2,
                  double alpha, double beta, double rb, double zshift, double dlnE, int nsub,
                  double *Hc, int cap, int *kmin, int *nk)
@@ -494,10 +513,7 @@ int ro_ky_kernel(const ro_tables *t, double a, double theta_o, double r1, double
     double w00 = (1 - fa) * (1 - fi), w01 = (1 - fa) * fi, w10 = fa * (1 - fi), w11 = fa * fi;
 
     double lnr = log(r2 / r1);
-    if (nsub <= 0) {
-        nsub = 1 + (int)floor(0.5 * lnr / dlnE);
-        if (nsub > 4096) nsub = 4096;
-    }
+    if (nsub <= 0) nsub = ro_auto_nsub(r1, r2, dlnE);
     int K_LO = (int)floor(log(0.005) / dlnE) - 2, K_HI = (int)ceil(log(4.0) / dlnE) + 2;
     int zoff = 0;
     double zs = 0;

@@ -4,6 +4,7 @@
 // rg_setup.cu / rg_spectrum.cu / rg_kyconv.cu / rg_raytrace.cu.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -58,7 +59,8 @@ struct rg_ctx {
     int *h_counter = nullptr; // pinned
     int2 *d_syslist = nullptr;
     int sys_cap = 0;
-    double *d_sptot = nullptr, *d_header = nullptr;
+    double *d_sptot = nullptr, *d_header = nullptr, *d_farr = nullptr;
+    int farr_nE = 0;
     double *d_sc = nullptr;
     int nth_threads = 0;
     double *d_rq = nullptr;
@@ -128,7 +130,7 @@ extern "C" void rg_ctx_destroy(rg_ctx *c)
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     free_dev(c->d_grid); free_dev(c->d_tab); free_dev(c->d_tabmeta); free_dev(c->d_rowrange); free_dev(c->d_p10); free_dev(c->d_recs);
-    free_dev(c->d_counter); free_dev(c->d_syslist); free_dev(c->d_sptot); free_dev(c->d_header); free_dev(c->d_sc);
+    free_dev(c->d_counter); free_dev(c->d_syslist); free_dev(c->d_sptot); free_dev(c->d_farr); free_dev(c->d_header); free_dev(c->d_sc);
     free_dev(c->d_rq); free_dev(c->d_queue); free_dev(c->d_partial); free_dev(c->d_kyH); free_dev(c->d_kyin); free_dev(c->d_kyout);
     free_dev(c->d_stage_par); free_dev(c->d_stage_out); free_dev(c->d_stage_attr); free_dev(c->d_stats);
     prof_collect(c);
@@ -502,13 +504,19 @@ static int ensure_batch_scratch(rg_ctx *c, int model)
         // sized once: chunk of sets, arena of Kompaneets systems, persistent nthcomp grid
         c->chunk_sets = 16384;
         c->sys_cap = c->chunk_sets * 40;
-        c->nth_threads = c->sm_count * 4 * 128;
+        c->nth_threads = c->sm_count * 5 * 128;
         RG_CUDA_OK(cudaMalloc(&c->d_recs, (size_t)c->chunk_sets * sizeof(SetRec)));
         RG_CUDA_OK(cudaMalloc(&c->d_syslist, (size_t)c->sys_cap * sizeof(int2)));
         RG_CUDA_OK(cudaMalloc(&c->d_sptot, (size_t)c->sys_cap * RG_SPT_STRIDE * sizeof(double)));
         RG_CUDA_OK(cudaMalloc(&c->d_header, (size_t)c->sys_cap * 4 * sizeof(double)));
         RG_CUDA_OK(cudaMalloc(&c->d_sc, (size_t)3 * RG_NTH * c->nth_threads * sizeof(double)));
         RG_CUDA_OK(cudaMalloc(&c->d_queue, 2 * sizeof(int)));
+    }
+    if (c->farr_nE < c->nE) { // Comptonised spectra on the grid: [sys_cap][nE]
+        free_dev(c->d_farr);
+        c->d_farr = nullptr; c->farr_nE = 0;
+        RG_CUDA_OK(cudaMalloc(&c->d_farr, (size_t)c->sys_cap * c->nE * sizeof(double)));
+        c->farr_nE = c->nE;
     }
     if (model == RG_MODEL_RELQSO && !c->d_rq) {
         c->rq_cap = 4608; // fine radial grid of _set_rhot: 1000/dex over <= 4.6 dex
@@ -541,7 +549,7 @@ extern "C" int rg_eval_batch(rg_ctx *c, const double *d_params, int P, int model
     A.grid = c->gd;
     A.flags = flags;
     A.p10tab = c->d_p10;
-    A.sptot = c->d_sptot;
+    A.farr = c->d_farr;
     A.header = c->d_header;
     A.queue = c->d_queue;
     if (rel) {
@@ -559,6 +567,10 @@ extern "C" int rg_eval_batch(rg_ctx *c, const double *d_params, int P, int model
         A.K_LO = 0; A.nH = 1; A.HL = 1; A.HH = 1;
     }
     A.warps = rg_spectrum_pick_warps(NC, A.nH, A.HL, A.HH);
+    if (const char *e = getenv("RG_SPEC_WARPS")) { // tuning knob: cap the warps per CTA
+        int w = atoi(e);
+        if (w >= 1 && w < A.warps) A.warps = w;
+    }
     if (A.warps < 1) return rg_set_error(RG_E_GRID, "energy grid too fine for the shared-memory working set");
     // small batches: split every set's annuli over several CTAs (partials are folded in block order)
     {
@@ -600,11 +612,12 @@ extern "C" int rg_eval_batch(rg_ctx *c, const double *d_params, int P, int model
         }
         unsigned long long *stats = c->profile ? c->d_stats : nullptr;
         if (nsys > 0) {
+            c->launches++; // nthcomp_interp_kernel
             RG_TRY(prof_begin(c, 1, st));
             RG_TRY(rg_launch_nthcomp(c->d_recs, c->d_syslist, nsys, c->d_p10, c->d_sc,
                                      c->d_sc + (size_t)RG_NTH * c->nth_threads,
                                      c->d_sc + (size_t)2 * RG_NTH * c->nth_threads, c->nth_threads, c->d_sptot,
-                                     c->d_header, stats, st));
+                                     c->d_header, c->gd, c->d_farr, stats, st));
             RG_TRY(prof_end(c, 1, st));
             c->launches++;
         }

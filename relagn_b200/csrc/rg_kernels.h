@@ -43,7 +43,7 @@ struct SpecArgs {
     TabDesc tab;
     unsigned flags;
     const double *p10tab; // [RG_NTH+1] 10^(0.02 j)
-    const double *sptot;  // [sys][RG_SPT_STRIDE]
+    const double *farr;   // [sys][nE] Comptonised spectra on the energy grid (nthcomp_kernel)
     const double *header; // [sys][4] = xmin, normfac, jmax, log10(511 xmin)
     double *out;          // [P][nE] or [P][4][nE]
     int K_LO, nH;         // widest shift-histogram support over all table nodes: k in [K_LO, K_LO + nH)
@@ -66,7 +66,7 @@ int rg_launch_setup(const double *d_params, int P, int model, double dr_dex, Set
 // persistent: n_threads = total launched threads = rows of the [RG_NTH][n_threads] scratch planes
 int rg_launch_nthcomp(const SetRec *recs, const int2 *syslist, int nsys, const double *p10tab, double *sc_gam,
                       double *sc_g, double *sc_bet, int n_threads, double *sptot, double *header,
-                      unsigned long long *stats, cudaStream_t st);
+                      const GridDesc &grid, double *farr, unsigned long long *stats, cudaStream_t st);
 
 int rg_launch_spectrum(const SpecArgs &args, int sm_count, cudaStream_t st);
 

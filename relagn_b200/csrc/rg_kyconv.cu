@@ -77,10 +77,7 @@ int rg_launch_ky_hist(const TabDesc &tab, double a, double theta_o, double r1, d
     if (smem > 200 * 1024) return rg_set_error(RG_E_GRID, "energy grid too fine for the kyconv histogram");
     double zs = 0.0;
     if (zshift != 0) zs = -log(1 + zshift) / dlnE;
-    if (nsub <= 0) {
-        nsub = 1 + (int)floor(0.5 * log(r2 / r1) / dlnE);
-        if (nsub > 4096) nsub = 4096;
-    }
+    if (nsub <= 0) nsub = rg_auto_nsub(r1, r2, log(r2 / r1), dlnE);
     RG_CUDA_OK(cudaFuncSetAttribute(ky_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     RG_LAUNCH(ky_hist_kernel, dim3(1), dim3(KT), smem, st, tab, a, theta_o, r1, r2, alpha, beta, rb, zs, dlnE, nsub,
               d_H, K_LO, nH);

@@ -218,7 +218,8 @@ setup_kernel(const double *__restrict__ params, int P, int model, double dr_dex,
 //   scratch planes gam, g, bet: [RG_NTH][n_threads], indexed by the launching
 //   thread (not the system) so the footprint is bounded by the resident
 //   threads; a warp's accesses to one j are contiguous.
-//   sptot arena: [sys][RG_SPT_STRIDE];  header: [sys][4] = xmin, normfac, jmax, log10(511 xmin)
+//   sptot arena: [sys][RG_SPT_STRIDE];  header: [sys][4] = xmin, normfac, jmax, log10(511 xmin);
+//   farr arena: [sys][nE] = the Comptonised spectrum on the caller's energy grid
 __device__ static void nthcomp_system(const SetRec &r, int which, const double *__restrict__ p10tab,
                                       double *__restrict__ sc_gam, double *__restrict__ sc_g,
                                       double *__restrict__ sc_bet, size_t sc_stride, int slot, double *__restrict__ spt,
@@ -350,7 +351,8 @@ __device__ static void nthcomp_system(const SetRec &r, int which, const double *
     int il = ih - 1;
     double xl = xmin * p10tab[il], xh = xmin * p10tab[ih];
     double spp = spt[il] + (spt[ih] - spt[il]) * (xx - xl) / (xh - xl);
-    hd[0] = xmin; hd[1] = 1.0 / spp; hd[2] = (double)jmax; hd[3] = log10(511.0 * xmin);
+    const double normfac = 1.0 / spp;
+    hd[0] = xmin; hd[1] = normfac; hd[2] = (double)jmax; hd[3] = log10(511.0 * xmin);
 }
 
 __global__ void __launch_bounds__(128)
@@ -376,6 +378,58 @@ nthcomp_kernel(const SetRec *__restrict__ recs, const int2 *__restrict__ syslist
     }
 }
 
+// donthcomp's interpolation of the Kompaneets solution onto the caller's grid (pyNTHCOMP.py:57-76), then * h / keV
+// (relagn.py:929-930, 1217-1218): one warp per system, lanes over consecutive energy bins (coalesced stores).
+// The reference's monotone cursor is restated as a direct search seeded from log10(E) and fixed up with the
+// reference's own comparisons, so every bin lands in exactly the cell the cursor would have reached.
+__global__ void __launch_bounds__(256)
+nthcomp_interp_kernel(const SetRec *__restrict__ recs, const int2 *__restrict__ syslist, int nsys,
+                      const double *__restrict__ p10tab, const double *__restrict__ sptot,
+                      const double *__restrict__ header, GridDesc grid, double *__restrict__ farr)
+{
+    const int lane = threadIdx.x & 31;
+    const int sys = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (sys >= nsys) return;
+    if (recs[syslist[sys].x].status != RG_S_OK) return;
+    const double *hd = header + (size_t)sys * 4;
+    const double xmin = hd[0], normfac = hd[1], lgx = hd[3];
+    const int nth = (int)hd[2];
+    const double *spt = sptot + (size_t)sys * RG_SPT_STRIDE;
+    double *F = farr + (size_t)sys * grid.nE;
+    const int nE = grid.nE;
+    double carry_pr = 0.0, carry_e = 0.0; // bin i0 - 1 of the previous pass
+    for (int i0 = 0; i0 < nE; i0 += 32) {
+        const int i = i0 + lane;
+        double e = 0.0, pr = 0.0;
+        if (i < nE) {
+            e = __ldg(grid.Egrid + i);
+            int j = (int)ceil((__ldg(grid.lgE + i) - lgx) * 50.0);
+            if (j < 0) j = 0;
+            if (j > nth + 1) j = nth + 1;
+            while (j > 0 && !(511.0 * (xmin * __ldg(p10tab + j - 1)) < e)) j--;
+            while (j <= nth && 511.0 * (xmin * __ldg(p10tab + j)) < e) j++;
+            double prim = 0.0;
+            if (j <= nth) {
+                if (j > 0) {
+                    const int jl = j - 1;
+                    const double xl = xmin * __ldg(p10tab + jl), xh = xmin * __ldg(p10tab + jl + 1);
+                    const double sl = spt[jl], sh = spt[jl + 1];
+                    prim = sl + ((__ldg(grid.e511 + i) - xl) * (sh - sl) / (xh - xl));
+                } else prim = spt[0];
+            }
+            pr = prim / __ldg(grid.ear2 + i);
+        }
+        double pr_prev = __shfl_up_sync(0xffffffffu, pr, 1), e_prev = __shfl_up_sync(0xffffffffu, e, 1);
+        if (lane == 0) { pr_prev = carry_pr; e_prev = carry_e; }
+        if (i < nE) {
+            const double ph = i > 0 ? (0.5 * (pr + pr_prev) * (e - e_prev) * normfac) : 0.0;
+            F[i] = ph * (1.0 / RGK_KEV) * RGK_H;
+        }
+        carry_pr = __shfl_sync(0xffffffffu, pr, 31);
+        carry_e = __shfl_sync(0xffffffffu, e, 31);
+    }
+}
+
 // ---------------------------------------------------------------------------
 int rg_launch_setup(const double *d_params, int P, int model, double dr_dex, SetRec *recs, int *sys_counter,
                     int2 *syslist, int sys_cap, double *rq_scratch, int rq_cap, double *d_attrs, cudaStream_t st)
@@ -389,13 +443,16 @@ int rg_launch_setup(const double *d_params, int P, int model, double dr_dex, Set
 
 int rg_launch_nthcomp(const SetRec *recs, const int2 *syslist, int nsys, const double *p10tab, double *sc_gam,
                       double *sc_g, double *sc_bet, int n_threads, double *sptot, double *header,
-                      unsigned long long *stats, cudaStream_t st)
+                      const GridDesc &grid, double *farr, unsigned long long *stats, cudaStream_t st)
 {
     if (nsys <= 0) return RG_OK;
     int blocks = (nsys + 127) / 128;
     if (blocks * 128 > n_threads) blocks = n_threads / 128;
     RG_LAUNCH(nthcomp_kernel, dim3(blocks), dim3(128), 0, st, recs, syslist, nsys, p10tab, sc_gam, sc_g, sc_bet,
               blocks * 128, sptot, header, stats);
+    RG_CUDA_OK(cudaGetLastError());
+    RG_LAUNCH(nthcomp_interp_kernel, dim3((unsigned)(((size_t)nsys * 32 + 255) / 256)), dim3(256), 0, st, recs, syslist,
+              nsys, p10tab, sptot, header, grid, farr);
     RG_CUDA_OK(cudaGetLastError());
     return RG_OK;
 }

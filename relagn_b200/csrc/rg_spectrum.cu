@@ -38,7 +38,6 @@
 #define FULL 0xffffffffu
 #define IMAX 0x7fffffff
 #define NGRID 5 // per-bin constant arrays staged in shared memory: hnu, bbpre, wt, pk, upk
-#define P10_N (RG_NTH + 4)
 
 static __host__ __device__ inline int round_up2(int x) { return (x + 1) & ~1; }
 
@@ -53,7 +52,7 @@ int rg_spectrum_pick_NC(int nE)
 static size_t warp_smem_doubles(int NC, int nH, int HL, int HH)
 {
     size_t d = 8 * (size_t)(HL + 32 * NC + HH); // inT
-    d += 2 * (size_t)round_up2(nH + 24);        // H slot + hot-region sum
+    d += (size_t)round_up2(nH + 24);            // H slot (per-annulus histogram; hot-region sum once the warp reaches the hot annuli)
     if (NC > 4) d += 8 * (size_t)32 * NC;       // accumulators (registers when NC <= 4)
     return d;
 }
@@ -62,14 +61,14 @@ size_t rg_spectrum_smem_bytes(int NC, int nH, int HL, int HH, int warps)
 {
     size_t d = warp_smem_doubles(NC, nH, HL, HH) * warps;
     if (NC <= 8) d += NGRID * 8 * (size_t)32 * NC; // grid constants (global memory for the finest grids)
-    d += P10_N + 8 * (size_t)32 * NC + 8 + 2;      // 10^(0.02 j), hot-shape staging, reduction scratch, item slot
+    d += 16 + 2;                                   // reduction scratch, item slot
     return d * sizeof(double);
 }
 
 int rg_spectrum_pick_warps(int NC, int nH, int HL, int HH)
 {
-    for (int w = 8; w >= 1; w--)
-        if (rg_spectrum_smem_bytes(NC, nH, HL, HH, w) <= 225 * 1024) return w;
+    for (int w = (NC <= 4 ? 12 : 8); w >= 1; w--)
+        if (rg_spectrum_smem_bytes(NC, nH, HL, HH, w) <= 227 * 1024 - 512) return w;
     return 0;
 }
 
@@ -78,24 +77,6 @@ __device__ inline double warp_sum(double v)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
     return v;
-}
-
-// pyNTHCOMP.py:62-73: value of the Kompaneets solution at photon energy e (keV);
-// the reference's monotone cursor restated as a direct search seeded from log10(e).
-__device__ inline double nth_prim(const double *__restrict__ spt, const double *p10, double xmin,
-                                  double lg511xmin, int nth, double e, double e511, double lge)
-{
-    int j = (int)ceil((lge - lg511xmin) * 50.0);
-    if (j < 0) j = 0;
-    if (j > nth + 1) j = nth + 1;
-    while (j > 0 && !(511.0 * (xmin * p10[j - 1]) < e)) j--; // p10 lives in shared memory: plain loads
-    while (j <= nth && 511.0 * (xmin * p10[j]) < e) j++;
-    if (j > nth) return 0.0;
-    if (j == 0) return __ldg(spt);
-    int jl = j - 1;
-    double xl = xmin * p10[jl], xh = xmin * p10[jl + 1];
-    double sl = __ldg(spt + jl), sh = __ldg(spt + jl + 1);
-    return sl + ((e511 - xl) * (sh - sl) / (xh - xl));
 }
 
 // ---------------------------------------------------------------------------
@@ -174,14 +155,14 @@ __device__ inline void warp_deposit(double *Hs, int K_LO, int nH, double sa, dou
     }
 }
 
-// One warp builds the shift histogram of annulus [r1, r2] into Hs (zeroed by the caller).
+// One warp adds weight x (shift histogram of annulus [r1, r2]) to Hs.
 __device__ inline void warp_build_hist(double *Hs, int K_LO, int nH, const TabSel &ts, double r1, double r2, double dlnE,
-                                       int &kmin_out, int &kmax_out)
+                                       double weight, int &kmin_out, int &kmax_out)
 {
     const int lane = threadIdx.x & 31;
     const int NP = ts.NPHI, nq = NP >> 5;
     const double lnr = log(r2 / r1);
-    const int nsub = rg_auto_nsub(lnr, dlnE);
+    const int nsub = rg_auto_nsub(r1, r2, lnr, dlnE);
     const double dphi = 2 * RGK_PI / NP;
     int kf_min = IMAX, kl_max = -IMAX;
     for (int m0 = 0; m0 < nsub; m0 += 32) {
@@ -205,7 +186,7 @@ __device__ inline void warp_build_hist(double *Hs, int K_LO, int nH, const TabSe
                 } else { sn0 = s_first; wn0 = w_first; }
                 double sb = __shfl_down_sync(FULL, s_cur, 1), wb = __shfl_down_sync(FULL, w_cur, 1);
                 if (lane == 31) { sb = sn0; wb = wn0; }
-                const double W = 0.5 * (w_cur + wb) * dphi * A;
+                const double W = 0.5 * (w_cur + wb) * dphi * A * weight;
                 warp_deposit(Hs, K_LO, nH, s_cur, sb, W, kf_min, kl_max);
                 s_cur = s_nxt; w_cur = w_nxt;
             }
@@ -369,7 +350,7 @@ struct Acc {
 };
 
 template <int NC>
-__global__ void __launch_bounds__(256, 1) spectrum_kernel(SpecArgs A)
+__global__ void __launch_bounds__(NC <= 4 ? 384 : 256, 1) spectrum_kernel(SpecArgs A)
 {
     constexpr bool GS = NC <= 8;       // grid constants in shared memory
     constexpr bool ACC_REG = NC <= 4;  // accumulators in registers
@@ -387,17 +368,14 @@ __global__ void __launch_bounds__(256, 1) spectrum_kernel(SpecArgs A)
     double *sm = reinterpret_cast<double *>(smem_raw);
     double *sgrid = sm;
     if (GS) sm += NGRID * 8 * NCOL;
-    double *s_p10 = sm; sm += P10_N;          // 10^(0.02 j)
-    double *stage = sm; sm += 8 * NCOL;       // hot spectral shape (times pack factor), natural bin order
-    double *s_red = sm; sm += 8;
+    double *s_red = sm; sm += 16;
     int *s_misc = reinterpret_cast<int *>(sm); sm += 2;
-    const size_t wd = 8 * (size_t)RS + 2 * (size_t)HSZ + (ACC_REG ? 0 : 8 * (size_t)NCOL);
+    const size_t wd = 8 * (size_t)RS + (size_t)HSZ + (ACC_REG ? 0 : 8 * (size_t)NCOL);
     double *warp0 = sm;
     double *wbase = sm + wd * warp;
     double *inT = wbase;                  // [8][RS]
     double *Hslot = inT + 8 * (size_t)RS; // [HSZ]: 8 zero pad, nH bins, >= 16 zero pad
-    double *Hsum = Hslot + HSZ;           // [HSZ]
-    double *acc_s = Hsum + HSZ;           // [8][NCOL] when !ACC_REG
+    double *acc_s = Hslot + HSZ;          // [8][NCOL] when !ACC_REG
     (void)acc_s;
 
     // ---- CTA prologue: stage the per-bin constants (transposed), zero the warp buffers ----
@@ -413,8 +391,7 @@ __global__ void __launch_bounds__(256, 1) spectrum_kernel(SpecArgs A)
             sgrid[(4 * 8 + c) * NCOL + col] = ok ? A.grid.Egrid[j] / A.grid.dE[j] : 0.0;
         }
     }
-    for (int i = tid; i < P10_N; i += nthreads) s_p10[i] = A.p10tab[i];
-    for (int i = lane; i < 8 * RS + 2 * HSZ; i += 32) wbase[i] = 0.0;
+    for (int i = lane; i < 8 * RS + HSZ; i += 32) wbase[i] = 0.0;
     GridAcc<NC, GS> G;
     G.sm = sgrid; G.g = &A.grid;
     double *const inBase = inT + A.HL + lane; // row 0, this lane's column of chunk 0
@@ -449,44 +426,15 @@ __global__ void __launch_bounds__(256, 1) spectrum_kernel(SpecArgs A)
         const bool owns_hot0 = r.n_hot > 0 && g_begin <= g_hot0 && g_hot0 < g_end;    // ... the first of them
         const bool need_shape = rel ? hot_here : owns_hot0;
 
-        // ---- hot spectral shape, computed once by the whole CTA (relagn.py:1200-1223):
-        //      donthcomp(Egrid, [gamma_h, kTe_h, kT_seed, 0, 0]) * h / keV; shape_int = trapz(Fnu, nu)
+        // ---- hot spectral shape (relagn.py:1200-1223): donthcomp(Egrid, [gamma_h, kTe_h, kT_seed, 0, 0]) * h / keV was
+        //      put on the grid by nthcomp_kernel; here only shape_int = trapz(Fnu, nu), once per CTA
         double shape_int = 0.0;
+        const double *hot_F = nullptr;
         if (need_shape) {
-            const int BPT = (8 * NCOL + nthreads - 1) / nthreads;
+            if (r.has_hotshape) hot_F = A.farr + (size_t)(r.sys_base + r.n_warm) * nE;
             double part = 0;
-            const double *hot_spt = nullptr;
-            double hot_xmin = 0, hot_norm = 0, hot_lgx = 0;
-            int hot_nth = 0;
-            if (r.has_hotshape) {
-                const int sys = r.sys_base + r.n_warm;
-                const double *hd = A.header + (size_t)sys * 4;
-                hot_xmin = hd[0]; hot_norm = hd[1]; hot_lgx = hd[3];
-                hot_nth = (int)hd[2];
-                hot_spt = A.sptot + (size_t)sys * RG_SPT_STRIDE;
-            }
-            const int j0 = BPT * tid;
-            double e_prev = 0.0, pr_prev = 0.0;
-            if (hot_spt && j0 > 0 && j0 - 1 < nE) {
-                e_prev = __ldg(A.grid.Egrid + j0 - 1);
-                pr_prev = nth_prim(hot_spt, s_p10, hot_xmin, hot_lgx, hot_nth, e_prev, __ldg(A.grid.e511 + j0 - 1),
-                                   __ldg(A.grid.lgE + j0 - 1)) / __ldg(A.grid.ear2 + j0 - 1);
-            }
-            for (int q = 0; q < BPT; q++) {
-                const int j = j0 + q;
-                if (j >= 8 * NCOL) break;
-                double F = 0.0;
-                if (hot_spt && j < nE) {
-                    double e = __ldg(A.grid.Egrid + j);
-                    double pr = nth_prim(hot_spt, s_p10, hot_xmin, hot_lgx, hot_nth, e, __ldg(A.grid.e511 + j),
-                                         __ldg(A.grid.lgE + j)) / __ldg(A.grid.ear2 + j);
-                    double ph = j > 0 ? (0.5 * (pr + pr_prev) * (e - e_prev) * hot_norm) : 0.0;
-                    F = ph * (1.0 / RGK_KEV) * RGK_H;
-                    e_prev = e; pr_prev = pr;
-                }
-                part += F * G.wt(j & 7, j >> 3);
-                stage[j] = F * G.pk(j & 7, j >> 3);
-            }
+            if (hot_F)
+                for (int j = tid; j < nE; j += nthreads) part += __ldg(hot_F + j) * G.wt(j & 7, j >> 3);
             part = warp_sum(part);
             if (lane == 0) s_red[warp] = part;
             __syncthreads();
@@ -527,7 +475,6 @@ __global__ void __launch_bounds__(256, 1) spectrum_kernel(SpecArgs A)
         acc.s = acc_s; acc.lane = lane;
         acc.zero();
         if (comps) { for (int j = lane; j < 3 * nE; j += 32) part_w[j] = 0.0; }
-        if (rel && hot_here) { for (int q = lane; q < HSZ; q += 32) Hsum[q] = 0.0; }
         __syncwarp();
         int cur_region = 0;                // component mode: region the accumulators currently belong to
         int hz_min = IMAX, hz_max = -IMAX; // touched range of the H slot (for re-zeroing)
@@ -604,28 +551,28 @@ __global__ void __launch_bounds__(256, 1) spectrum_kernel(SpecArgs A)
                 }
                 int kmn = 0, kmx = -1;
                 if (conv) {
-                    // re-zero what the previous annulus touched, then build this annulus' histogram
-                    for (int k = hz_min + lane; k <= hz_max; k += 32) {
-                        int q = k - K_LO;
-                        if (q >= 0 && q < nH) Hslot[8 + q] = 0.0;
+                    // disc / warm: re-zero what the previous annulus touched, then build this annulus' histogram.
+                    // hot: the slot turns into the region histogram -- every hot annulus adds its own, weighted by
+                    // the annulus luminosity (the warp meets its hot annuli last, so the slot is free by then)
+                    if (region != 2 || !hot_any_conv) {
+                        for (int k = hz_min + lane; k <= hz_max; k += 32) {
+                            int q = k - K_LO;
+                            if (q >= 0 && q < nH) Hslot[8 + q] = 0.0;
+                        }
+                        hz_min = IMAX; hz_max = -IMAX;
+                        __syncwarp();
                     }
-                    __syncwarp();
-                    warp_build_hist(Hslot + 8, K_LO, nH, ts, r1, r2, dlnE, kmn, kmx);
-                    hz_min = kmn; hz_max = kmx;
+                    warp_build_hist(Hslot + 8, K_LO, nH, ts, r1, r2, dlnE, region == 2 ? s1 : 1.0, kmn, kmx);
+                    hz_min = kmn < hz_min ? kmn : hz_min;
+                    hz_max = kmx > hz_max ? kmx : hz_max;
                     if (kmn <= kmx) { st_w += (unsigned long long)(kmx - kmn + 1); st_n += 1; }
                 }
                 if (region == 2) {
-                    // hot: fold into this warp's region histogram (weighted by the annulus luminosity)
                     hot_mine = true;
                     if (conv) {
-                        for (int k = kmn + lane; k <= kmx; k += 32) {
-                            int q = k - K_LO;
-                            if (q >= 0 && q < nH) Hsum[8 + q] += s1 * Hslot[8 + q];
-                        }
                         hk_min = kmn < hk_min ? kmn : hk_min;
                         hk_max = kmx > hk_max ? kmx : hk_max;
                         hot_any_conv = true;
-                        __syncwarp();
                     } else {
                         Sflat += s1 * geo;
                     }
@@ -635,16 +582,8 @@ __global__ void __launch_bounds__(256, 1) spectrum_kernel(SpecArgs A)
                 // ---- local spectrum, chunk by chunk ----
                 const int nch_live = region == 0 ? ((jz + 255) >> 8) : NC; // chunks holding a non-zero bin
                 double part = 0;
-                const double *w_spt = nullptr;
-                double w_xmin = 0, w_norm = 0, w_lgx = 0;
-                int w_nth = 0;
-                if (region == 1) {
-                    const int sys = r.sys_base + loc;
-                    const double *hd = A.header + (size_t)sys * 4;
-                    w_xmin = hd[0]; w_norm = hd[1]; w_lgx = hd[3];
-                    w_nth = (int)hd[2];
-                    w_spt = A.sptot + (size_t)sys * RG_SPT_STRIDE;
-                }
+                // warm annulus: its Comptonised spectrum is already on the grid (nthcomp_kernel)
+                const double *w_F = region == 1 ? A.farr + (size_t)(r.sys_base + loc) * nE : nullptr;
                 for (int ch = 0; ch < NC; ch++) {
                     const int col = 32 * ch + lane, j0 = 8 * col;
                     double L[8];
@@ -660,23 +599,9 @@ __global__ void __launch_bounds__(256, 1) spectrum_kernel(SpecArgs A)
                             part += L[c] * G.wt(c, col);
                         }
                     } else if (j0 < nE) {
-                        double e_prev = 0.0, pr_prev = 0.0;
-                        if (j0 > 0) {
-                            e_prev = __ldg(A.grid.Egrid + j0 - 1);
-                            pr_prev = nth_prim(w_spt, s_p10, w_xmin, w_lgx, w_nth, e_prev, __ldg(A.grid.e511 + j0 - 1),
-                                               __ldg(A.grid.lgE + j0 - 1)) / __ldg(A.grid.ear2 + j0 - 1);
-                        }
 #pragma unroll
                         for (int c = 0; c < 8; c++) {
-                            int j = j0 + c;
-                            if (j < nE) {
-                                double e = __ldg(A.grid.Egrid + j);
-                                double pr = nth_prim(w_spt, s_p10, w_xmin, w_lgx, w_nth, e, __ldg(A.grid.e511 + j),
-                                                     __ldg(A.grid.lgE + j)) / __ldg(A.grid.ear2 + j);
-                                double ph = j > 0 ? (0.5 * (pr + pr_prev) * (e - e_prev) * w_norm) : 0.0;
-                                L[c] = ph * (1.0 / RGK_KEV) * RGK_H;
-                                e_prev = e; pr_prev = pr;
-                            }
+                            L[c] = j0 + c < nE ? __ldg(w_F + j0 + c) : 0.0;
                             part += L[c] * G.wt(c, col);
                         }
                     }
@@ -737,8 +662,12 @@ __global__ void __launch_bounds__(256, 1) spectrum_kernel(SpecArgs A)
             }
             __syncwarp();
             for (int ch = 0; ch < NC; ch++) {
+                const int col = 32 * ch + lane;
 #pragma unroll
-                for (int c = 0; c < 8; c++) inBase[c * RS + 32 * ch] = stage[8 * (32 * ch + lane) + c];
+                for (int c = 0; c < 8; c++) {
+                    const int j = 8 * col + c;
+                    inBase[c * RS + 32 * ch] = (hot_F && j < nE) ? __ldg(hot_F + j) * G.pk(c, col) : 0.0;
+                }
             }
             __syncwarp();
             const double Lum = r.Ldiss + r.Lseed;
@@ -747,7 +676,7 @@ __global__ void __launch_bounds__(256, 1) spectrum_kernel(SpecArgs A)
                 double tmp[8];
 #pragma unroll
                 for (int c = 0; c < 8; c++) tmp[c] = 0.0;
-                if (rel && hot_any_conv) convolve8(Hsum + 8, K_LO, nH, hk_min, hk_max, inBase + 32 * ch, RS, tmp);
+                if (rel && hot_any_conv) convolve8(Hslot + 8, K_LO, nH, hk_min, hk_max, inBase + 32 * ch, RS, tmp);
                 double v[8];
 #pragma unroll
                 for (int c = 0; c < 8; c++) {

@@ -87,9 +87,20 @@ __device__ inline void rg_ring_sample(const TabSel &ts, int s0, int s1, double f
     jn = j0 + fr * (j1 - j0);
 }
 
-__device__ inline int rg_auto_nsub(double lnr, double dlnE)
+// Number of rings an annulus [r1, r2] is cut into: the radial variation of the shift across one ring stays below
+// about half an energy bin.  |d ln g / d ln r| <= kappa = 1.5/(r-3) + 0.5/sqrt(r) (gravitational + orbital Doppler
+// term of a Keplerian disc), capped at 0.5 (its value at r = 6); wide annuli (the stand-alone kyconv seam) use 0.5.
+__host__ __device__ inline int rg_auto_nsub(double r1, double r2, double lnr, double dlnE)
 {
-    int nsub = 1 + (int)floor(0.5 * lnr / dlnE);
+    double kappa = 0.5;
+    if (lnr <= 0.2) {
+        double rg = sqrt(r1 * r2);
+        if (rg > 6.0) {
+            kappa = 1.5 / (rg - 3.0) + 0.5 / sqrt(rg);
+            if (kappa > 0.5) kappa = 0.5;
+        }
+    }
+    int nsub = 1 + (int)floor(kappa * lnr / dlnE);
     return nsub > 4096 ? 4096 : nsub;
 }
 
