@@ -153,8 +153,12 @@ def get_tables(kind, ctx=None):
         return dict(spins=d["tab_spins"], thetas=d["tab_thetas"], NR=int(d["tab_NR"]), NPHI=int(d["tab_NPHI"]),
                     dl=float(d["tab_dl"]), data=d["tab_data"])
     from relagn_b200 import tables as T
-    T.load_default(ctx)
     cfg = dict(T.DEFAULT)
+    cached = T.cached_default()
+    if cached is not None:      # the product's own ray-traced tables, stored by relagn_b200/tables.py
+        cfg["data"] = cached
+        return cfg
+    T.load_default(ctx)
     cfg["data"] = ctx.tables_download()
     return cfg
 
@@ -168,15 +172,19 @@ def run_reference(args):
         tables = get_tables("golden")
     else:
         # the CPU arm needs the same tables as the GPU arm; they are produced by the product's ray tracer
-        import torch
-        if torch.cuda.is_available():
-            from relagn_b200 import _capi
-            ctx = _capi.Context(0)
-            tables = get_tables("default", ctx)
-            ctx.close()
+        from relagn_b200 import tables as T
+        if T.cached_default() is not None:
+            tables = get_tables("default")
         else:
-            tables = get_tables("golden")
-            args.tables = "golden"
+            import torch
+            if torch.cuda.is_available():
+                from relagn_b200 import _capi
+                ctx = _capi.Context(0)
+                tables = get_tables("default", ctx)
+                ctx.close()
+            else:
+                tables = get_tables("golden")
+                args.tables = "golden"
     P = args.sets
     params = c4_params(P, SEED)
     # each step: a bounded sample of the workload (~10 s of CPU work at full thread count)
@@ -312,10 +320,19 @@ def run_ours(args):
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         fp64_peak = ev.ctx.measure_fp64_peak()
         ach_gbs = bytes_alg / (ms_spec * 1e-3) / 1e9
+        # DRAM bytes of one spectrum_kernel launch from the committed `ncu --set full` capture (profiles/), scaled to
+        # this run's sets per launch; the excess over bytes_per_launch is the Comptonised-spectra arena (farr) that
+        # nthcomp_interp_kernel writes and this kernel reads once (~29 systems x 8 kB per set), not a re-read
+        traffic = None
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r1g_summary.json")))
+            traffic = prof["spectrum_dram_bytes_per_set"] * (P / n_launch)
+        except Exception:
+            pass
         roofline = {"kernel": "spectrum_kernel<4>", "bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak,
                     "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
-                    "traffic": None,
+                    "traffic": traffic,
                     "bytes_per_launch": bytes_alg / n_launch, "launches_per_step": n_launch,
                     "avg_launch_ms": ms_spec / n_launch,
                     "note": "the path is FP64-pipe bound, not HBM bound (SURVEY 8d): see fp64_roofline"}

@@ -37,6 +37,9 @@
 
 #define FULL 0xffffffffu
 #define IMAX 0x7fffffff
+#ifndef RG_LOCKSTEP
+#define RG_LOCKSTEP 4 // block barrier every RG_LOCKSTEP rounds (power of two)
+#endif
 #define NGRID 5 // per-bin constant arrays staged in shared memory: hnu, bbpre, wt, pk, upk
 
 static __host__ __device__ inline int round_up2(int x) { return (x + 1) & ~1; }
@@ -535,7 +538,7 @@ __global__ void __launch_bounds__(NC <= 4 ? 384 : 256, 1) spectrum_kernel(SpecAr
             }
             const int mt = n_rounds - m0 < 32 ? n_rounds - m0 : 32;
             for (int mi = 0; mi < mt; mi++) {
-                __syncthreads(); // lockstep only: no data crosses warps here
+                if (((m0 + mi) & (RG_LOCKSTEP - 1)) == 0) __syncthreads(); // lockstep only: no data crosses warps here
                 const int region = __shfl_sync(FULL, p_region, mi);
                 if (region < 0) continue; // no annulus left for this warp in this round
                 if (region == 2 && !rel) continue; // non-relativistic hot component needs no annuli (relagn.py:1387-1401)
@@ -581,6 +584,7 @@ __global__ void __launch_bounds__(NC <= 4 ? 384 : 256, 1) spectrum_kernel(SpecAr
 
                 // ---- local spectrum, chunk by chunk ----
                 const int nch_live = region == 0 ? ((jz + 255) >> 8) : NC; // chunks holding a non-zero bin
+                const double inv_kT = region == 0 ? 1.0 / s1 : 0.0;
                 double part = 0;
                 // warm annulus: its Comptonised spectrum is already on the grid (nthcomp_kernel)
                 const double *w_F = region == 1 ? A.farr + (size_t)(r.sys_base + loc) * nE : nullptr;
@@ -592,9 +596,11 @@ __global__ void __launch_bounds__(NC <= 4 ? 384 : 256, 1) spectrum_kernel(SpecAr
                     if (ch >= nch_live) {
                         // Wien tail past the overflow point: identically zero
                     } else if (region == 0) {
+                        // x = h nu / kT as a multiplication by 1/kT (one division per annulus instead of one per bin;
+                        // the last-bit difference in x moves exp(x) by < 1e-13 relative)
 #pragma unroll
                         for (int c = 0; c < 8; c++) {
-                            double ef = exp(G.hnu(c, col) / s1) - 1;
+                            double ef = exp(G.hnu(c, col) * inv_kT) - 1;
                             L[c] = RGK_PI * (G.bbpre(c, col) / ef);
                             part += L[c] * G.wt(c, col);
                         }

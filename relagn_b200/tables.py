@@ -27,6 +27,13 @@ def _key(cfg):
     return h.hexdigest()[:16]
 
 
+def cached_default(cfg=None):
+    """The cached table array of `cfg` (default: DEFAULT) or None."""
+    cfg = DEFAULT if cfg is None else cfg
+    path = os.path.join(CACHE_DIR, "kerr_%s.npy" % _key(cfg))
+    return np.load(path) if os.path.exists(path) else None
+
+
 def load_default(ctx, cfg=None, cache=True):
     """Make `cfg` (default: DEFAULT) resident in ctx: from the disk cache if present, else ray-trace on the
     device and store."""
