@@ -166,3 +166,35 @@ def test_full_size_properties_relqso_grid(ctx):
     Lrel = np.trapezoid(out[::97, 3], nu, axis=1)
     assert (Lflat > 0).all()
     assert np.all((Lrel / Lflat > 0.5) & (Lrel / Lflat < 1.5))
+
+
+def test_python_default_grid_rel(ctx, oracle, otab):
+    """The Python class's own default grid (1999 bins, 1e-4..1e4 keV): the NC = 8 instantiation, relativistic."""
+    grid = np.geomspace(1e-4, 1e4, 2000)
+    ctx.set_grid(grid)
+    upload_golden_tables(ctx)
+    p = np.array([[1e8, 100, -1, 0, 0.5, 100, 0.2, 1.7, 2.7, 10, 20, -1, 1, 10, 0],
+                  [1e7, 100, -0.5, 0.9, 0.8, 150, 0.3, 1.9, 2.5, 8, 30, -1, 1, 8, 0]])
+    st, ref, rat = oracle.evaluate_batch(p, grid, model=0, rel=True, tab=otab)
+    out, at = ctx.eval_batch_host(p, model=0, rel=True, components=True)
+    for i in range(2):
+        for c in range(4):
+            assert peak_relerr(out[i, c], ref[i, c]) < TOL, (i, c)
+
+
+def test_hires_config5(ctx, oracle, otab):
+    """BASELINE config 5: 5000 energy bins x ~2000 annuli (dr_dex = 700, log_rout = 3), a = 0.998 -- the NC = 20
+    instantiation with the annuli of one set split over several CTAs."""
+    grid = np.geomspace(1e-4, 1e3, 5001)
+    ctx.set_grid(grid)
+    upload_golden_tables(ctx)
+    p = np.array([[1e8, 100, -1, 0.998, 0.5, 100, 0.2, 1.7, 2.7, 10, 20, 3, 1, 10, 0],
+                  [1e8, 100, -1, 0.998, 0.9, 100, 0.2, 1.7, 2.7, 10, 20, 3, 1, 10, 0]])
+    st, ref, rat = oracle.evaluate_batch(p, grid, model=0, rel=True, tab=otab, dr_dex=700.0)
+    out, at = ctx.eval_batch_host(p, model=0, rel=True, components=True, dr_dex=700.0)
+    assert list(at[0, 17:20]) == [1189, 210, 635]   # SURVEY App. E
+    for i in range(2):
+        for c in range(4):
+            assert peak_relerr(out[i, c], ref[i, c]) < TOL, (i, c)
+    tot, _ = ctx.eval_batch_host(p, model=0, rel=True, components=False, dr_dex=700.0)
+    np.testing.assert_allclose(tot, out[:, 3], rtol=1e-12)
