@@ -519,8 +519,8 @@ static int ensure_batch_scratch(rg_ctx *c, int model)
         c->farr_nE = c->nE;
     }
     if (model == RG_MODEL_RELQSO && !c->d_rq) {
-        c->rq_cap = 4608; // fine radial grid of _set_rhot: 1000/dex over <= 4.6 dex
-        RG_CUDA_OK(cudaMalloc(&c->d_rq, (size_t)c->rq_cap * c->chunk_sets * sizeof(double)));
+        c->rq_cap = 1; // r_hot per set, filled by relqso_rhot_kernel
+        RG_CUDA_OK(cudaMalloc(&c->d_rq, (size_t)c->chunk_sets * sizeof(double)));
     }
     return RG_OK;
 }
@@ -601,7 +601,7 @@ extern "C" int rg_eval_batch(rg_ctx *c, const double *d_params, int P, int model
         RG_TRY(rg_launch_setup(par, n, model, dr_dex, c->d_recs, c->d_counter, c->d_syslist, c->sys_cap, c->d_rq,
                                c->rq_cap, attrs, st));
         RG_TRY(prof_end(c, 0, st));
-        c->launches++;
+        c->launches += model == RG_MODEL_RELQSO ? 2 : 1;
         RG_CUDA_OK(cudaMemcpyAsync(c->h_counter, c->d_counter, sizeof(int), cudaMemcpyDeviceToHost, st));
         RG_CUDA_OK(cudaStreamSynchronize(st));
         int nsys = c->h_counter[0];

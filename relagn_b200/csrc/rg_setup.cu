@@ -84,6 +84,93 @@ __device__ static double ldiss_quad(const SetRec &r, const NtConst &nt)
     return 2 * RGK_SB * 2 * RGK_PI * (r.Rg * r.Rg) * tot;
 }
 
+// relqso._set_rhot (relagn.py:1877-1898): r_hot is the mid-radius of the fine-grid bin (1000 per decade, built
+// top-down from log r_sg by repeated subtraction exactly as _make_rbins does) in which the dissipated luminosity,
+// summed inside-out, first exceeds 0.02 L_Edd.  One CTA per parameter set: thread 0 runs the subtraction chain
+// (serial by construction, ~3000 additions) into shared memory; the expensive part -- the Novikov-Thorne
+// temperature of every bin -- is evaluated 128 bins at a time by the whole CTA; thread 0 then adds the 128 terms in
+// the reference's order and tests the threshold before every addition, so the chosen bin and the value of r_hot are
+// those of the sequential loop, bit for bit.
+#define RQ_CAP 4608
+__global__ void __launch_bounds__(128)
+relqso_rhot_kernel(const double *__restrict__ params, int P, double *__restrict__ rh_out)
+{
+    __shared__ double edges[RQ_CAP]; // descending: edges[k] = the k-th edge below log r_sg
+    __shared__ double terms[128], rmids[128];
+    __shared__ int s_n, s_base, s_nedges, s_done;
+    __shared__ double s_Ldiss, s_rh;
+    const int idx = blockIdx.x, tid = threadIdx.x;
+    if (idx >= P) return;
+    const double *p = params + (size_t)idx * RG_NPAR;
+    const double M = p[0], mdot = pow(10.0, p[2]), a = p[3], cosinc = p[4];
+    bool ok = (a >= -0.998 && a <= 0.998) && (cosinc <= 1 && cosinc >= 0.09);
+    if (ok) {
+        double lmdot = log10(mdot);
+        ok = lmdot >= -1.65 && lmdot <= 0.5;
+    }
+    if (!ok) { // the setup kernel reports the reference's ValueError
+        if (tid == 0) rh_out[idx] = 0.0;
+        return;
+    }
+    const double risco = rg_risco(a);
+    const double r_sg = 2150 * pow(M / 1e9, -2.0 / 9) * pow(mdot, 4.0 / 9) * pow(0.1, 2.0 / 9);
+    const double L_edd = 1.39e31 * M;
+    const double eta = 1 - sqrt(1 - 2 / (3 * risco));
+    const double Mdot_edd = L_edd / (eta * (RGK_C * RGK_C));
+    const double Rg = (RGK_GMSUN * M) / (RGK_C * RGK_C);
+    NtConst nt;
+    rg_nt_prepare(nt, a, risco, M, mdot, Mdot_edd, Rg);
+    const double dlr = 1.0 / 1000;
+    const double lg_in = log10(risco), lg_top = log10(r_sg);
+    if (tid == 0) {
+        int n = 1;
+        double t = lg_top;
+        edges[0] = t;
+        while (t > lg_in && n < RQ_CAP) {
+            t = t - dlr;
+            edges[n] = t;
+            n++;
+        }
+        int base, n_edges;
+        if (t > lg_in) { n = -1; base = 0; n_edges = 0; } // capacity exceeded
+        else if (t == lg_in) { base = n - 1; n_edges = n; }
+        else if (n > 1) { base = n - 2; n_edges = n - 1; edges[base] = lg_in; }
+        else { base = 0; n_edges = 1; edges[0] = lg_in; }
+        s_n = n; s_base = base; s_nedges = n_edges; s_done = 0; s_Ldiss = 0.0; s_rh = risco;
+    }
+    __syncthreads();
+    if (s_n < 0) {
+        if (tid == 0) rh_out[idx] = nan("");
+        return;
+    }
+    const int base = s_base, nbins = s_nedges - 1;
+    const double Rg2 = Rg * Rg, thresh = 0.02 * L_edd;
+    for (int i0 = 0; i0 < nbins; i0 += 128) {
+        const int i = i0 + tid;
+        if (i < nbins) { // ascending edge i lives at chain index base - i
+            double e0 = edges[base - i], e1 = edges[base - i - 1];
+            double rmid = pow(10.0, e0 + dlr / 2);
+            double dr = pow(10.0, e1) - pow(10.0, e0);
+            terms[tid] = RGK_SB * rg_tnt4(nt, rmid) * 4 * RGK_PI * rmid * dr * Rg2;
+            rmids[tid] = rmid;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double Ldiss = s_Ldiss, rh = s_rh;
+            int nq = nbins - i0 < 128 ? nbins - i0 : 128, done = 0;
+            for (int q = 0; q < nq; q++) {
+                if (!(Ldiss < thresh)) { done = 1; break; }
+                Ldiss += terms[q];
+                rh = rmids[q];
+            }
+            s_Ldiss = Ldiss; s_rh = rh; s_done = done;
+        }
+        __syncthreads();
+        if (s_done) break;
+    }
+    if (tid == 0) rh_out[idx] = s_rh;
+}
+
 __global__ void __launch_bounds__(128)
 setup_kernel(const double *__restrict__ params, int P, int model, double dr_dex, SetRec *__restrict__ recs,
              int *__restrict__ sys_counter, int2 *__restrict__ syslist, int sys_cap, double *__restrict__ rq_scratch,
@@ -135,38 +222,11 @@ setup_kernel(const double *__restrict__ params, int P, int model, double dr_dex,
             if (!(r.r_w >= r.risco)) { r.flags |= RG_F_RW_LT_RISCO; r.r_w = r.risco; }
             if (!(r.hmax <= r.r_h)) { r.flags |= RG_F_HMAX_GT_RH; r.hmax = r.r_h; }
         } else {
-            // relqso._set_rhot (relagn.py:1877-1898): fine grid built top-down from log r_sg
-            const double dlr = 1.0 / 1000;
-            double lg_in = log10(r.risco), lg_top = log10(r.r_sg);
-            double *sc = rq_scratch + idx; // [k][P] layout
-            int n = 1;
-            double t = lg_top;
-            sc[0] = t;
-            while (t > lg_in && n < rq_cap) {
-                t = t - dlr;
-                sc[(size_t)n * P] = t;
-                n++;
-            }
-            if (t > lg_in) status = RG_S_CAP;
+            // relqso._set_rhot (relagn.py:1877-1898): done by relqso_rhot_kernel (one CTA per set)
+            double rh = rq_scratch[idx];
+            if (!(rh == rh)) status = RG_S_CAP; // NaN: fine radial grid longer than the kernel's capacity
             else {
-                // ascending edge i -> chain index base - i
-                int base, n_edges;
-                if (t == lg_in) { base = n - 1; n_edges = n; }
-                else if (n > 1) { base = n - 2; n_edges = n - 1; sc[(size_t)base * P] = lg_in; }
-                else { base = 0; n_edges = 1; sc[0] = lg_in; }
-                double Ldiss = 0.0, rmid = 0.0; // the reference leaves rmid undefined if the loop never runs
-                double Rg2 = r.Rg * r.Rg, thresh = 0.02 * r.L_edd;
-                int i = 0;
-                double e0 = sc[(size_t)base * P];
-                while (Ldiss < thresh && i < n_edges - 1) {
-                    double e1 = sc[(size_t)(base - i - 1) * P];
-                    rmid = pow(10.0, e0 + dlr / 2);
-                    double dr = pow(10.0, e1) - pow(10.0, e0);
-                    Ldiss += RGK_SB * rg_tnt4(nt, rmid) * 4 * RGK_PI * rmid * dr * Rg2;
-                    e0 = e1;
-                    i++;
-                }
-                r.r_h = rmid;
+                r.r_h = rh;
                 r.r_w = 2 * r.r_h;
                 r.r_out = r.r_sg;
                 if (r.r_w > r.r_sg) r.r_w = r.r_sg;
@@ -435,6 +495,10 @@ int rg_launch_setup(const double *d_params, int P, int model, double dr_dex, Set
                     int2 *syslist, int sys_cap, double *rq_scratch, int rq_cap, double *d_attrs, cudaStream_t st)
 {
     RG_CUDA_OK(cudaMemsetAsync(sys_counter, 0, sizeof(int), st));
+    if (model == RG_MODEL_RELQSO) {
+        RG_LAUNCH(relqso_rhot_kernel, dim3(P), dim3(128), 0, st, d_params, P, rq_scratch);
+        RG_CUDA_OK(cudaGetLastError());
+    }
     RG_LAUNCH(setup_kernel, dim3((P + 127) / 128), dim3(128), 0, st, d_params, P, model, dr_dex, recs, sys_counter,
               syslist, sys_cap, rq_scratch, rq_cap, d_attrs);
     RG_CUDA_OK(cudaGetLastError());
