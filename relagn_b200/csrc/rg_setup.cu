@@ -280,7 +280,7 @@ setup_kernel(const double *__restrict__ params, int P, int model, double dr_dex,
 //   threads; a warp's accesses to one j are contiguous.
 //   sptot arena: [sys][RG_SPT_STRIDE];  header: [sys][4] = xmin, normfac, jmax, log10(511 xmin);
 //   farr arena: [sys][nE] = the Comptonised spectrum on the caller's energy grid
-__device__ static void nthcomp_system(const SetRec &r, int which, const double *__restrict__ p10tab,
+__device__ static void nthcomp_system(const SetRec &r, int which, const double *p10tab,
                                       double *__restrict__ sc_gam, double *__restrict__ sc_g,
                                       double *__restrict__ sc_bet, size_t sc_stride, int slot, double *__restrict__ spt,
                                       double *__restrict__ hd)
@@ -383,7 +383,7 @@ __device__ static void nthcomp_system(const SetRec &r, int which, const double *
         else { alp = bj - cj * gam_prev; gj = (dj - cj * g_prev) / alp; }
         double gamj = aj / alp;
         size_t o = (size_t)j * sc_stride + sys;
-        sc_gam[o] = gamj; sc_g[o] = gj; sc_bet[o] = betj;
+        RG_STCS(&sc_gam[o], gamj); RG_STCS(&sc_g[o], gj); RG_STCS(&sc_bet[o], betj); // streamed: read back once
         gam_prev = gamj; g_prev = gj;
         xm = x0; x0 = xp; c2m = c2j;
     }
@@ -391,13 +391,29 @@ __device__ static void nthcomp_system(const SetRec &r, int which, const double *
     double u_next = 0.0; // u[jmax-1]
     double u1 = 0.0;
     spt[jmax] = 0.0; spt[jmax - 1] = 0.0;
-    for (int jj = jmax - 2; jj >= 1; jj--) {
-        size_t o = (size_t)jj * sc_stride + sys;
-        double u = sc_g[o] - sc_gam[o] * u_next;
-        double x = xmin * p10tab[jj];
-        spt[jj] = (x * x * u * sc_bet[o] * tautom) * (x * x);
-        u_next = u;
-        if (jj == 1) u1 = u;
+    // The scratch planes are far larger than L2, so the reads below come from HBM: the loads of 4 steps are issued
+    // together (their addresses do not depend on u), then the dependent recurrence runs on registers.
+    for (int jj = jmax - 2; jj >= 1;) {
+        const int nb = jj >= 4 ? 4 : jj; // steps jj, jj-1, ..., jj-nb+1
+        double gg[4], gm[4], bt[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (q < nb) {
+                size_t o = (size_t)(jj - q) * sc_stride + sys;
+                gg[q] = RG_LDCS(&sc_g[o]); gm[q] = RG_LDCS(&sc_gam[o]); bt[q] = RG_LDCS(&sc_bet[o]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (q < nb) {
+                double u = gg[q] - gm[q] * u_next;
+                double x = xmin * p10tab[jj - q];
+                spt[jj - q] = (x * x * u * bt[q] * tautom) * (x * x);
+                u_next = u;
+                if (jj - q == 1) u1 = u;
+            }
+        }
+        jj -= nb;
     }
     {
         double u = aa * u1;
@@ -415,19 +431,24 @@ __device__ static void nthcomp_system(const SetRec &r, int which, const double *
     hd[0] = xmin; hd[1] = normfac; hd[2] = (double)jmax; hd[3] = log10(511.0 * xmin);
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 5)
 nthcomp_kernel(const SetRec *__restrict__ recs, const int2 *__restrict__ syslist, int nsys,
                const double *__restrict__ p10tab, double *__restrict__ sc_gam, double *__restrict__ sc_g,
                double *__restrict__ sc_bet, int n_threads, double *__restrict__ sptot, double *__restrict__ header,
                unsigned long long *stats)
 {
+    // 10^(0.02 j) is read at every step of both sweeps: keep it in shared memory (the scratch stream would keep
+    // evicting it from L1)
+    __shared__ double s_p10[RG_NTH + 4];
+    for (int i = threadIdx.x; i < RG_NTH + 4; i += blockDim.x) s_p10[i] = p10tab[i];
+    __syncthreads();
     int gtid = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long sumj = 0, nsolved = 0;
     for (int sys = gtid; sys < nsys; sys += n_threads) {
         int2 ent = syslist[sys];
         const SetRec &r = recs[ent.x];
         if (r.status != RG_S_OK) continue;
-        nthcomp_system(r, ent.y, p10tab, sc_gam, sc_g, sc_bet, (size_t)n_threads, gtid,
+        nthcomp_system(r, ent.y, s_p10, sc_gam, sc_g, sc_bet, (size_t)n_threads, gtid,
                        sptot + (size_t)sys * RG_SPT_STRIDE, header + (size_t)sys * 4);
         sumj += (unsigned long long)header[(size_t)sys * 4 + 2];
         nsolved++;
