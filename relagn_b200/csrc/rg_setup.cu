@@ -333,6 +333,9 @@ __device__ static void nthcomp_system(const SetRec &r, int which, const double *
     double w1 = x32;
     double c2m = (w1 * w1 * w1 * w1) / (1.0 + 4.60 * w1 + 1.1 * w1 * w1); // c2[0]
     double gam_prev = 0, g_prev = 0;
+    // w2[j] = sqrt(x[j-1] x[j]) is w1[j-1], and theta/deltal/w2[j] the previous step's theta/deltal/w1: carried over
+    // (same operands, same operations: bit-identical to recomputing them as pyNTHCOMP.py:211-212 does)
+    double tow1_prev = tod / x32;
     // bet[0]
     {
         double w = xm, rel;
@@ -352,7 +355,6 @@ __device__ static void nthcomp_system(const SetRec &r, int which, const double *
         xp = xmin * p10tab[j + 1];
         double w1j = sqrt(x0 * xp);
         double c2j = (w1j * w1j * w1j * w1j) / (1.0 + 4.60 * w1j + 1.1 * w1j * w1j);
-        double w2j = sqrt(xm * x0);
         // rel, bet at j
         double w = x0, betj;
         if (j >= jrel) betj = 1.0 / tautom;
@@ -370,12 +372,13 @@ __device__ static void nthcomp_system(const SetRec &r, int which, const double *
         }
         double dph = (j < jmaxth) ? planck * (x0 * x0) / (exp(x0 / tempbb) - 1) : 0.0;
         // coefficients (pyNTHCOMP.py:210-221)
-        double aj = -c20 * c2j * (tod / w1j + 0.5);
-        double t1 = -c20 * c2j * (0.5 - tod / w1j);
-        double t2 = c20 * c2m * (tod / w2j + 0.5);
+        const double tow1 = tod / w1j, tow2 = tow1_prev;
+        double aj = -c20 * c2j * (tow1 + 0.5);
+        double t1 = -c20 * c2j * (0.5 - tow1);
+        double t2 = c20 * c2m * (tow2 + 0.5);
         double t3 = (x0 * x0 * x0) * (tautom * betj);
         double bj = t1 + t2 + t3;
-        double cj = c20 * c2m * (0.5 - tod / w2j);
+        double cj = c20 * c2m * (0.5 - tow2);
         double dj = x0 * dph;
         // Thomas forward sweep (pyNTHCOMP.py:233-242)
         double alp, gj;
@@ -385,7 +388,7 @@ __device__ static void nthcomp_system(const SetRec &r, int which, const double *
         size_t o = (size_t)j * sc_stride + sys;
         RG_STCS(&sc_gam[o], gamj); RG_STCS(&sc_g[o], gj); RG_STCS(&sc_bet[o], betj); // streamed: read back once
         gam_prev = gamj; g_prev = gj;
-        xm = x0; x0 = xp; c2m = c2j;
+        xm = x0; x0 = xp; c2m = c2j; tow1_prev = tow1;
     }
     // back substitution (pyNTHCOMP.py:243-249) and sptot = dphesc x^2 (pyNTHCOMP.py:170-171)
     double u_next = 0.0; // u[jmax-1]

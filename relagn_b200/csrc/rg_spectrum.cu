@@ -601,7 +601,7 @@ __global__ void __launch_bounds__(NC <= 4 ? 384 : 256, 1) spectrum_kernel(SpecAr
 #pragma unroll
                         for (int c = 0; c < 8; c++) {
                             double ef = exp(G.hnu(c, col) * inv_kT) - 1;
-                            L[c] = RGK_PI * (G.bbpre(c, col) / ef);
+                            L[c] = (RGK_PI * G.bbpre(c, col)) * __drcp_rn(ef); // 1/inf = 0 past the overflow point
                             part += L[c] * G.wt(c, col);
                         }
                     } else if (j0 < nE) {
