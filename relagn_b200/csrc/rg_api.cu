@@ -655,7 +655,7 @@ extern "C" int rg_eval_batch_host(rg_ctx *c, const double *params, int P, int mo
     const int ncomp = (flags & RG_FLAG_COMPONENTS) ? 4 : 1;
     const size_t per_out = (size_t)ncomp * c->nE;
     // pipeline in slabs so the D2H of slab i overlaps the kernels of slab i+1
-    const int SLAB = 8192;
+    const int SLAB = 16384; // = the chunk of rg_eval_batch: one setup/nthcomp/spectrum launch set per slab
     int nslab_dev = std::min(P, 2 * SLAB);
     RG_TRY(ensure_dev(&c->d_stage_par, &c->d_stage_par_n, (size_t)P * RG_NPAR));
     RG_TRY(ensure_dev(&c->d_stage_out, &c->d_stage_out_n, (size_t)nslab_dev * per_out));
