@@ -198,3 +198,66 @@ def test_hires_config5(ctx, oracle, otab):
             assert peak_relerr(out[i, c], ref[i, c]) < TOL, (i, c)
     tot, _ = ctx.eval_batch_host(p, model=0, rel=True, components=False, dr_dex=700.0)
     np.testing.assert_allclose(tot, out[:, 3], rtol=1e-12)
+
+
+def test_edge_grids(ctx, oracle, otab):
+    """Grids the reference accepts through new_ear (relagn.py:780-805): a grid reaching below 1e-4 keV switches on the
+    low-frequency extension of disc_annuli (:868-873); a non-geometric grid is fine without the transfer and is
+    refused with it (kyconv restatement needs log-spaced bins); a tiny grid; an empty batch."""
+    from relagn_b200 import _capi
+    upload_golden_tables(ctx)
+    p = np.array([[1e8, 100, -1, 0, 0.5, 100, 0.2, 1.7, 2.7, 10, 20, -1, 1, 10, 0],
+                  [1e6, 100, -0.3, 0.5, 0.7, 80, 0.3, 2.0, 2.4, 12, 40, -1, -1, 10, 0]])
+    grid = np.geomspace(1e-5, 1e2, 701)
+    ctx.set_grid(grid)
+    for rel in (False, True):
+        st, ref, rat = oracle.evaluate_batch(p, grid, model=0, rel=rel, tab=otab)
+        out, at = ctx.eval_batch_host(p, model=0, rel=rel, components=True)
+        for i in range(2):
+            for c in range(4):
+                assert peak_relerr(out[i, c], ref[i, c]) < TOL, ("ext", rel, i, c)
+    g2 = np.concatenate([np.linspace(1e-3, 1e-1, 200, endpoint=False), np.geomspace(1e-1, 1e2, 300)])
+    ctx.set_grid(g2)
+    st, ref, rat = oracle.evaluate_batch(p, g2, model=0, rel=False)
+    out, at = ctx.eval_batch_host(p, model=0, rel=False, components=True)
+    for i in range(2):
+        for c in range(4):
+            assert peak_relerr(out[i, c], ref[i, c]) < TOL, ("nongeo", i, c)
+    with pytest.raises(_capi.RelagnError) as ei:
+        ctx.eval_batch_host(p, model=0, rel=True)
+    assert ei.value.code == -4  # RG_E_GRID
+    g3 = np.geomspace(0.1, 10, 9)
+    ctx.set_grid(g3)
+    st, ref, rat = oracle.evaluate_batch(p, g3, model=0, rel=True, tab=otab)
+    out, at = ctx.eval_batch_host(p, model=0, rel=True, components=True)
+    for i in range(2):
+        for c in range(4):
+            assert peak_relerr(out[i, c], ref[i, c]) < TOL, ("tiny", i, c)
+    out0, at0 = ctx.eval_batch_host(np.zeros((0, 15)), model=0, rel=True)
+    assert out0.shape == (0, 8) and at0.shape == (0, 24)
+
+
+def test_class_api_on_device():
+    """The class API end to end on the GPU: default relagn / relqso objects against the reference goldens."""
+    from relagn_b200 import relagn, relqso
+    from relagn_b200 import model
+    t = golden_tables()
+    model.set_tables(t)
+    dn = np.load(os.path.join(GOLDEN, "golden_nonrel.npz"))
+    dr = np.load(os.path.join(GOLDEN, "golden_rel.npz"))
+    u = np.load(os.path.join(GOLDEN, "golden_units.npz"))
+    o = relagn()
+    assert o.Egrid.size == 1999 and (o.risco, len(o.logr_ad_bins), len(o.logr_wc_bins), len(o.logr_hc_bins)) == (6.0, 80, 16, 12)
+    o.set_units("SI")
+    assert peak_relerr(o.get_totSED(rel=False), dn["relagn_specdef"][0][3]) < TOL
+    o.new_ear(dn["grid1000"])
+    assert peak_relerr(o.get_totSED(rel=True), dr["relagn_spec1000"][0][3]) < TOL
+    assert peak_relerr(o.get_DiscComponent(rel=True), dr["relagn_spec1000"][0][0]) < TOL
+    o.set_units("counts")
+    o.set_flux()
+    assert peak_relerr(o.get_totSED(rel=False), u["counts_1"]) < TOL
+    q = relqso()
+    assert q.r_h == 14.261351436104999 and q.r_w == 28.522702872209997
+    assert q.gamma_h == pytest.approx(1.9803689563797076, rel=1e-12)
+    with pytest.raises(ValueError, match="not physical"):
+        relagn(a=1.2)
