@@ -483,7 +483,9 @@ int ro_auto_nsub(double r1, double r2, double dlnE)
             if (kappa > 0.5) kappa = 0.5;
         }
     }
-    int nsub = 1 + (int)floor(kappa * lnr / dlnE);
+    /* + 1e-9: grids commensurate with the radial binning (e.g. 100 bins per decade against 50 annuli per decade)
+     * put kappa lnr / dlnE on an integer; the bias keeps the floor independent of last-bit differences of log() */
+    int nsub = 1 + (int)floor(kappa * lnr / dlnE + 1e-9);
     return nsub > 4096 ? 4096 : nsub;
 }
 

@@ -100,7 +100,9 @@ __host__ __device__ inline int rg_auto_nsub(double r1, double r2, double lnr, do
             if (kappa > 0.5) kappa = 0.5;
         }
     }
-    int nsub = 1 + (int)floor(kappa * lnr / dlnE);
+    // + 1e-9: grids commensurate with the radial binning put kappa lnr / dlnE on an integer; the bias keeps the floor
+    // independent of last-bit differences between CUDA's and the host's log()
+    int nsub = 1 + (int)floor(kappa * lnr / dlnE + 1e-9);
     return nsub > 4096 ? 4096 : nsub;
 }
 
