@@ -325,7 +325,7 @@ def run_ours(args):
         # nthcomp_interp_kernel writes and this kernel reads once (~29 systems x 8 kB per set), not a re-read
         traffic = None
         try:
-            prof = json.load(open(os.path.join(ROOT, "profiles", "r1g_summary.json")))
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r1h_summary.json")))
             traffic = prof["spectrum_dram_bytes_per_set"] * (P / n_launch)
         except Exception:
             pass

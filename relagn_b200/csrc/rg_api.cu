@@ -61,6 +61,7 @@ struct rg_ctx {
     int sys_cap = 0;
     double *d_sptot = nullptr, *d_header = nullptr, *d_farr = nullptr;
     int farr_nE = 0;
+    int farr_cap = 0; // systems the farr arena holds at the current grid (<= sys_cap)
     double *d_sc = nullptr;
     int nth_threads = 0;
     double *d_rq = nullptr;
@@ -512,10 +513,12 @@ static int ensure_batch_scratch(rg_ctx *c, int model)
         RG_CUDA_OK(cudaMalloc(&c->d_sc, (size_t)3 * RG_NTH * c->nth_threads * sizeof(double)));
         RG_CUDA_OK(cudaMalloc(&c->d_queue, 2 * sizeof(int)));
     }
-    if (c->farr_nE < c->nE) { // Comptonised spectra on the grid: [sys_cap][nE]
+    if (c->farr_nE != c->nE) { // Comptonised spectra on the grid: [farr_cap][nE], at most ~6 GB
         free_dev(c->d_farr);
         c->d_farr = nullptr; c->farr_nE = 0;
-        RG_CUDA_OK(cudaMalloc(&c->d_farr, (size_t)c->sys_cap * c->nE * sizeof(double)));
+        size_t cap = (size_t)6e9 / ((size_t)c->nE * sizeof(double));
+        c->farr_cap = (int)std::min<size_t>((size_t)c->sys_cap, std::max<size_t>(cap, 4096));
+        RG_CUDA_OK(cudaMalloc(&c->d_farr, (size_t)c->farr_cap * c->nE * sizeof(double)));
         c->farr_nE = c->nE;
     }
     if (model == RG_MODEL_RELQSO && !c->d_rq) {
@@ -598,15 +601,15 @@ extern "C" int rg_eval_batch(rg_ctx *c, const double *d_params, int P, int model
         const double *par = d_params + (size_t)p0 * RG_NPAR;
         double *attrs = d_attrs ? d_attrs + (size_t)p0 * RG_NATTR : nullptr;
         RG_TRY(prof_begin(c, 0, st));
-        RG_TRY(rg_launch_setup(par, n, model, dr_dex, c->d_recs, c->d_counter, c->d_syslist, c->sys_cap, c->d_rq,
+        RG_TRY(rg_launch_setup(par, n, model, dr_dex, c->d_recs, c->d_counter, c->d_syslist, c->farr_cap, c->d_rq,
                                c->rq_cap, attrs, st));
         RG_TRY(prof_end(c, 0, st));
         c->launches += model == RG_MODEL_RELQSO ? 2 : 1;
         RG_CUDA_OK(cudaMemcpyAsync(c->h_counter, c->d_counter, sizeof(int), cudaMemcpyDeviceToHost, st));
         RG_CUDA_OK(cudaStreamSynchronize(st));
         int nsys = c->h_counter[0];
-        if (nsys > c->sys_cap) {
-            if (n == 1) return rg_set_error(RG_E_NOMEM, "one parameter set needs %d Kompaneets systems (cap %d)", nsys, c->sys_cap);
+        if (nsys > c->farr_cap) {
+            if (n == 1) return rg_set_error(RG_E_NOMEM, "one parameter set needs %d Kompaneets systems (cap %d)", nsys, c->farr_cap);
             chunk = std::max(1, n / 2); // arena too small for this chunk: retry with fewer sets
             continue;
         }

@@ -16,7 +16,8 @@ TOL = 1e-9
 
 @pytest.fixture(scope="module")
 def ctx():
-    from relagn_b200 import _capi
+    from relagn_b200 import _capi, build
+    build.build()  # no-op when relagn_b200/_build/librelagn_b200.so is current (it travels with the snapshot)
     c = _capi.Context(0)
     yield c
     c.close()
