@@ -351,26 +351,30 @@ __device__ static void nthcomp_system(const SetRec &r, int which, const double *
         else b0 = 1.0 / tautom;
         sc_bet[sys] = b0; sc_gam[sys] = 0; sc_g[sys] = 0;
     }
+    const double itau = 1.0 / tautom, rxr = 1.0 / (xr - xnr), itbb = 1.0 / tempbb;
     for (int j = 1; j < jmax - 1; j++) {
         xp = xmin * p10tab[j + 1];
         double w1j = sqrt(x0 * xp);
         double c2j = (w1j * w1j * w1j * w1j) / (1.0 + 4.60 * w1j + 1.1 * w1j * w1j);
         // rel, bet at j
         double w = x0, betj;
-        if (j >= jrel) betj = 1.0 / tautom;
+        if (j >= jrel) betj = itau;
         else {
             double rel;
             if (w <= 0.05) rel = (1.0 - 2.0 * w + 26.0 * w * w * 0.2);
             else {
-                double z1 = (1.0 + w) / (w * w * w), z2 = 1.0 + 2.0 * w, z3 = log(z2), z4 = 2.0 * w * (1.0 + w) / z2;
-                double z5 = z3 / 2.0 / w, z6 = (1.0 + 3.0 * w) / z2 / z2;
+                // Klein-Nishina factor (pyNTHCOMP.py:128-136) with the six divisions by w and 1 + 2w folded into
+                // two reciprocals (last-bit differences only)
+                const double rw = 1.0 / w, z2 = 1.0 + 2.0 * w, rz = 1.0 / z2, z3 = log(z2);
+                double z1 = (1.0 + w) * (rw * rw * rw), z4 = 2.0 * w * (1.0 + w) * rz;
+                double z5 = z3 * 0.5 * rw, z6 = (1.0 + 3.0 * w) * (rz * rz);
                 rel = (0.75 * (z1 * (z4 - z3) + z5 - z6));
             }
             double taukn = tautom * rel;
-            if (j < jnr - 1) betj = 1.0 / tautom / (1.0 + taukn / 3.0);
-            else { double flz = 1 - (w - xnr) / (xr - xnr); betj = 1.0 / tautom / (1.0 + taukn / 3.0 * flz); }
+            if (j < jnr - 1) betj = itau / (1.0 + taukn / 3.0);
+            else { double flz = 1 - (w - xnr) * rxr; betj = itau / (1.0 + taukn / 3.0 * flz); }
         }
-        double dph = (j < jmaxth) ? planck * (x0 * x0) / (exp(x0 / tempbb) - 1) : 0.0;
+        double dph = (j < jmaxth) ? planck * (x0 * x0) / (exp(x0 * itbb) - 1) : 0.0;
         // coefficients (pyNTHCOMP.py:210-221)
         const double tow1 = tod / w1j, tow2 = tow1_prev;
         double aj = -c20 * c2j * (tow1 + 0.5);
@@ -381,10 +385,12 @@ __device__ static void nthcomp_system(const SetRec &r, int which, const double *
         double cj = c20 * c2m * (0.5 - tow2);
         double dj = x0 * dph;
         // Thomas forward sweep (pyNTHCOMP.py:233-242)
+        // one reciprocal of the pivot serves both quotients (pyNTHCOMP.py:234-241)
         double alp, gj;
-        if (j == 1) { alp = bj + cj * aa; gj = dj / alp; }
-        else { alp = bj - cj * gam_prev; gj = (dj - cj * g_prev) / alp; }
-        double gamj = aj / alp;
+        if (j == 1) alp = bj + cj * aa; else alp = bj - cj * gam_prev;
+        const double ralp = 1.0 / alp;
+        if (j == 1) gj = dj * ralp; else gj = (dj - cj * g_prev) * ralp;
+        double gamj = aj * ralp;
         size_t o = (size_t)j * sc_stride + sys;
         RG_STCS(&sc_gam[o], gamj); RG_STCS(&sc_g[o], gj); RG_STCS(&sc_bet[o], betj); // streamed: read back once
         gam_prev = gamj; g_prev = gj;
@@ -471,6 +477,9 @@ nthcomp_interp_kernel(const SetRec *__restrict__ recs, const int2 *__restrict__ 
                       const double *__restrict__ p10tab, const double *__restrict__ sptot,
                       const double *__restrict__ header, GridDesc grid, double *__restrict__ farr)
 {
+    __shared__ double s_p10[RG_NTH + 4];
+    for (int i = threadIdx.x; i < RG_NTH + 4; i += blockDim.x) s_p10[i] = p10tab[i];
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     const int sys = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (sys >= nsys) return;
@@ -490,13 +499,13 @@ nthcomp_interp_kernel(const SetRec *__restrict__ recs, const int2 *__restrict__ 
             int j = (int)ceil((__ldg(grid.lgE + i) - lgx) * 50.0);
             if (j < 0) j = 0;
             if (j > nth + 1) j = nth + 1;
-            while (j > 0 && !(511.0 * (xmin * __ldg(p10tab + j - 1)) < e)) j--;
-            while (j <= nth && 511.0 * (xmin * __ldg(p10tab + j)) < e) j++;
+            while (j > 0 && !(511.0 * (xmin * s_p10[j - 1]) < e)) j--;
+            while (j <= nth && 511.0 * (xmin * s_p10[j]) < e) j++;
             double prim = 0.0;
             if (j <= nth) {
                 if (j > 0) {
                     const int jl = j - 1;
-                    const double xl = xmin * __ldg(p10tab + jl), xh = xmin * __ldg(p10tab + jl + 1);
+                    const double xl = xmin * s_p10[jl], xh = xmin * s_p10[jl + 1];
                     const double sl = spt[jl], sh = spt[jl + 1];
                     prim = sl + ((__ldg(grid.e511 + i) - xl) * (sh - sl) / (xh - xl));
                 } else prim = spt[0];
