@@ -240,7 +240,7 @@ def run_ours(args):
         gathered = [torch.empty((P, NE), dtype=torch.float64, device=dev) for _ in range(world)]
 
     def step():
-        ev.evaluate_device(params, rel=True, out=out, attrs=attrs)
+        ev.evaluate_device(params, rel=True, out=out, attrs=attrs, fp32=args.fp32)
         if world > 1:
             dist.gather(out, gathered, dst=0)
 
@@ -274,12 +274,12 @@ def run_ours(args):
 
     # ---- e2e: host buffers through the public API, H2D + D2H inside the timed region ----
     e2e_steps = max(1, min(args.steps, 3))
-    ev.evaluate(params_np[:1024], rel=True)  # staging buffers / warm-up
-    ev.evaluate(params_np, rel=True)
+    ev.evaluate(params_np[:1024], rel=True, fp32=args.fp32)  # staging buffers / warm-up
+    ev.evaluate(params_np, rel=True, fp32=args.fp32)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        o_host, _a = ev.evaluate(params_np, rel=True)
+        o_host, _a = ev.evaluate(params_np, rel=True, fp32=args.fp32)
         chk = float(o_host[0, NE // 2])
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
@@ -296,7 +296,7 @@ def run_ours(args):
     if rank == 0:
         ev.ctx.set_profile(True)
         ev.ctx.reset_stats()
-        ev.evaluate_device(params, rel=True, out=out, attrs=attrs)
+        ev.evaluate_device(params, rel=True, out=out, attrs=attrs, fp32=args.fp32)
         torch.cuda.synchronize()
         s = ev.ctx.stats()
         ev.ctx.set_profile(False)
@@ -360,7 +360,7 @@ def run_ours(args):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32 (spectra/transfer) + f64 (setup, nthcomp, histograms)" if args.fp32 else "f64", "data": "synthetic",
                 "config": workload_config(world, P, args.tables), "clocks": clocks, "e2e": e2e,
                 "gpu_launches": int(launches), "roofline": roofline, "fp64_roofline": fp64, "kernels": kernels,
                 "cpu_baseline": cpu, "checksum": chk}
@@ -381,6 +381,7 @@ def main():
     ap.add_argument("--tables", default="default", choices=["default", "golden"])
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU work per cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--fp32", action="store_true", help="RG_FLAG_FP32 mode (stated bound 1e-5 within 20 decades of the peak)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

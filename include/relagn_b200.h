@@ -78,6 +78,8 @@ enum {
 /* rg_eval_batch flags */
 #define RG_FLAG_REL 1u        /* relativistic transfer (get_*(rel=True)) */
 #define RG_FLAG_COMPONENTS 2u /* out is [P][4][nE] = disc, warm, hot, total; else [P][nE] total */
+#define RG_FLAG_FP32 4u       /* single-precision local spectra / transfer convolution / accumulation (outputs stay
+                                 double; setup, Kompaneets solve, histograms and normalisations stay FP64) */
 
 /* error codes */
 #define RG_OK 0

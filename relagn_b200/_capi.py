@@ -20,7 +20,7 @@ ATTR_NAMES = ["risco", "r_sg", "eta", "L_edd", "Mdot_edd", "Rg", "r_h", "r_w", "
 A = {n: i for i, n in enumerate(ATTR_NAMES)}
 
 MODEL_RELAGN, MODEL_RELQSO = 0, 1
-FLAG_REL, FLAG_COMPONENTS = 1, 2
+FLAG_REL, FLAG_COMPONENTS, FLAG_FP32 = 1, 2, 4
 S_OK, S_SPIN, S_INC, S_MDOT, S_CAP = 0, 1, 2, 3, 4
 F_RW_LT_RH, F_RW_GT_ROUT, F_RH_LT_RISCO, F_RW_LT_RISCO, F_HMAX_GT_RH, F_HOT_SEED_GE_KTE = 1, 2, 4, 8, 16, 32
 
@@ -190,7 +190,7 @@ class Context:
 
     # ---- batched evaluation ----
     def eval_batch_host(self, params, model=MODEL_RELAGN, rel=True, components=False, dr_dex=50.0, out=None,
-                        attrs=True):
+                        attrs=True, fp32=False):
         """params: [P, 15] (relqso: first 7 columns used).  Returns (out [P, nE] or [P, 4, nE], attrs [P, 24])."""
         p = np.asarray(params, dtype=np.float64)
         if p.ndim == 1:
@@ -198,7 +198,7 @@ class Context:
         P = p.shape[0]
         pp = np.zeros((P, NPAR))
         pp[:, :p.shape[1]] = p
-        flags = (FLAG_REL if rel else 0) | (FLAG_COMPONENTS if components else 0)
+        flags = (FLAG_REL if rel else 0) | (FLAG_COMPONENTS if components else 0) | (FLAG_FP32 if fp32 else 0)
         shape = (P, 4, self.nE) if components else (P, self.nE)
         if out is None:
             out = np.empty(shape)
@@ -209,9 +209,9 @@ class Context:
         return out, at
 
     def eval_batch_device(self, params_ptr, P, out_ptr, attrs_ptr=0, model=MODEL_RELAGN, rel=True, components=False,
-                          dr_dex=50.0, stream=0):
+                          dr_dex=50.0, stream=0, fp32=False):
         """Raw device pointers (e.g. torch tensor .data_ptr()); asynchronous on `stream`."""
-        flags = (FLAG_REL if rel else 0) | (FLAG_COMPONENTS if components else 0)
+        flags = (FLAG_REL if rel else 0) | (FLAG_COMPONENTS if components else 0) | (FLAG_FP32 if fp32 else 0)
         self._check(self.lib.rg_eval_batch(self.h, C.c_void_p(params_ptr), int(P), int(model), float(dr_dex), flags,
                                            C.c_void_p(out_ptr), C.c_void_p(attrs_ptr) if attrs_ptr else None,
                                            C.c_void_p(stream) if stream else None))

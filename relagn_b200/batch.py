@@ -49,7 +49,7 @@ class BatchEvaluator:
         self._tables_ready = True
 
     # ---- device-resident path -------------------------------------------------
-    def evaluate_device(self, params, rel=True, components=False, out=None, attrs=None):
+    def evaluate_device(self, params, rel=True, components=False, out=None, attrs=None, fp32=False):
         """params: CUDA float64 tensor [P, 15].  Returns (out, attrs) CUDA tensors; asynchronous on the current
         torch stream."""
         assert params.is_cuda and params.dtype == torch.float64 and params.is_contiguous()
@@ -65,11 +65,11 @@ class BatchEvaluator:
         assert tuple(out.shape) == shape and out.is_contiguous()
         stream = torch.cuda.current_stream(self.device).cuda_stream
         self.ctx.eval_batch_device(params.data_ptr(), P, out.data_ptr(), attrs.data_ptr(), model=self.model, rel=rel,
-                                   components=components, dr_dex=self.dr_dex, stream=stream)
+                                   components=components, dr_dex=self.dr_dex, stream=stream, fp32=fp32)
         return out, attrs
 
     # ---- host path (the call a user of the reference's class makes, batched) ----
-    def evaluate(self, params, rel=True, components=False):
+    def evaluate(self, params, rel=True, components=False, fp32=False):
         """params: array-like [P, n] on the host.  Returns (spectra ndarray [P, nE] or [P, 4, nE] in W/Hz,
         attrs ndarray [P, 24]).  Stages through pinned memory; H2D and D2H happen inside this call."""
         p = np.asarray(params, dtype=np.float64)
@@ -88,7 +88,7 @@ class BatchEvaluator:
         pin[:, :p.shape[1]] = torch.from_numpy(p)
         out = self._pin_out[:P * ncomp * self.nE].view((P, 4, self.nE) if components else (P, self.nE))
         out_np, at = self.ctx.eval_batch_host(pin.numpy(), model=self.model, rel=rel, components=components,
-                                              dr_dex=self.dr_dex, out=out.numpy())
+                                              dr_dex=self.dr_dex, out=out.numpy(), fp32=fp32)
         return out_np, at
 
 

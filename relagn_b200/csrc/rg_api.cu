@@ -569,7 +569,7 @@ extern "C" int rg_eval_batch(rg_ctx *c, const double *d_params, int P, int model
     } else {
         A.K_LO = 0; A.nH = 1; A.HL = 1; A.HH = 1;
     }
-    A.warps = rg_spectrum_pick_warps(NC, A.nH, A.HL, A.HH);
+    A.warps = rg_spectrum_pick_warps(NC, A.nH, A.HL, A.HH, (flags & RG_FLAG_FP32) ? 1 : 0);
     if (const char *e = getenv("RG_SPEC_WARPS")) { // tuning knob: cap the warps per CTA
         int w = atoi(e);
         if (w >= 1 && w < A.warps) A.warps = w;

@@ -57,8 +57,8 @@ struct SpecArgs {
 
 int rg_spectrum_pick_NC(int nE); // 256-bin chunks per warp pass: 4, 8 or 20; 0 if nE is too large
 // shared memory per CTA and the number of warps per CTA that fit (0: does not fit at all)
-size_t rg_spectrum_smem_bytes(int NC, int nH, int HL, int HH, int warps);
-int rg_spectrum_pick_warps(int NC, int nH, int HL, int HH);
+size_t rg_spectrum_smem_bytes(int NC, int nH, int HL, int HH, int warps, int fp32);
+int rg_spectrum_pick_warps(int NC, int nH, int HL, int HH, int fp32);
 
 int rg_launch_setup(const double *d_params, int P, int model, double dr_dex, SetRec *recs, int *sys_counter,
                     int2 *syslist, int sys_cap, double *rq_scratch, int rq_cap, double *d_attrs, cudaStream_t st);

@@ -52,34 +52,45 @@ int rg_spectrum_pick_NC(int nE)
     return 0;
 }
 
-static size_t warp_smem_doubles(int NC, int nH, int HL, int HH)
+// shared memory per CTA: [per-bin constants (R, NC <= 8)] [reduction scratch, item slot]
+//                        [per warp: transposed spectrum buffer (R) | histogram slot (double) | accumulators (R, NC > 4)]
+size_t rg_spectrum_smem_bytes(int NC, int nH, int HL, int HH, int warps, int fp32)
 {
-    size_t d = 8 * (size_t)(HL + 32 * NC + HH); // inT
-    d += (size_t)round_up2(nH + 24);            // H slot (per-annulus histogram; hot-region sum once the warp reaches the hot annuli)
-    if (NC > 4) d += 8 * (size_t)32 * NC;       // accumulators (registers when NC <= 4)
-    return d;
+    size_t rsz = fp32 ? 4 : 8;
+    size_t w = 8 * (size_t)(HL + 32 * NC + HH) * rsz + (size_t)round_up2(nH + 24) * 8;
+    if (NC > 4) w += 8 * (size_t)32 * NC * rsz; // accumulators (registers when NC <= 4)
+    size_t b = w * warps + 18 * 8;
+    if (NC <= 8) b += NGRID * 8 * (size_t)32 * NC * rsz; // grid constants (global memory for the finest grids)
+    return b;
 }
 
-size_t rg_spectrum_smem_bytes(int NC, int nH, int HL, int HH, int warps)
+int rg_spectrum_pick_warps(int NC, int nH, int HL, int HH, int fp32)
 {
-    size_t d = warp_smem_doubles(NC, nH, HL, HH) * warps;
-    if (NC <= 8) d += NGRID * 8 * (size_t)32 * NC; // grid constants (global memory for the finest grids)
-    d += 16 + 2;                                   // reduction scratch, item slot
-    return d * sizeof(double);
-}
-
-int rg_spectrum_pick_warps(int NC, int nH, int HL, int HH)
-{
-    for (int w = (NC <= 4 ? 12 : 8); w >= 1; w--)
-        if (rg_spectrum_smem_bytes(NC, nH, HL, HH, w) <= 227 * 1024 - 512) return w;
+    for (int w = (NC <= 4 ? (fp32 ? 16 : 12) : 8); w >= 1; w--)
+        if (rg_spectrum_smem_bytes(NC, nH, HL, HH, w, fp32) <= 227 * 1024 - 512) return w;
     return 0;
 }
 
-__device__ inline double warp_sum(double v)
+template <typename T>
+__device__ inline T warp_sum(T v)
 {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
     return v;
+}
+
+// Planck function of one bin: pi * (2 h nu^3 / c^2) / (exp(x) - 1), x = h nu / kT (relagn.py:45-50).
+// FP64: exp(x) - 1 as the reference writes it, then a reciprocal multiply (1/inf = 0 past the overflow point).
+// FP32 mode: expm1f keeps the relative accuracy at small x, where exp(x) - 1 would cancel in single precision.
+__device__ inline double planck_bin(double hnu, double bbpre, double inv_kT)
+{
+    double ef = exp(hnu * inv_kT) - 1;
+    return (RGK_PI * bbpre) * __drcp_rn(ef);
+}
+__device__ inline float planck_bin(float hnu, float bbpre, float inv_kT)
+{
+    float ef = expm1f(hnu * inv_kT);
+    return (3.14159265358979f * bbpre) / ef;
 }
 
 // ---------------------------------------------------------------------------
@@ -201,25 +212,26 @@ __device__ inline void warp_build_hist(double *Hs, int K_LO, int nH, const TabSe
 
 // tmp[c] = sum_k H[k] in[8 col + c - k] for k in [kmin, kmax]; Hs0 points at shift K_LO of a histogram that is
 // zero-padded 8 in front and 16 behind; base = row 0 of the warp's buffer at this lane's column, RS = row stride.
-__device__ inline void convolve8(const double *Hs0, int K_LO, int nH, int kmin, int kmax, const double *base, int RS,
-                                 double (&tmp)[8])
+template <typename R>
+__device__ inline void convolve8(const double *Hs0, int K_LO, int nH, int kmin, int kmax, const R *base, int RS,
+                                 R (&tmp)[8])
 {
 #pragma unroll
-    for (int c = 0; c < 8; c++) tmp[c] = 0.0;
+    for (int c = 0; c < 8; c++) tmp[c] = 0;
     if (kmin < K_LO) kmin = K_LO;
     if (kmax > K_LO + nH - 1) kmax = K_LO + nH - 1;
     if (kmin > kmax) return;
     const int g = (kmin >= 0) ? (kmin >> 3) : -((-kmin + 7) >> 3); // floor(kmin / 8)
     const int k0 = g * 8;
     const double *Hk = Hs0 + (k0 - K_LO);
-    double w[8];
+    R w[8];
 #pragma unroll
     for (int c = 0; c < 8; c++) w[c] = base[c * RS - g];
-    const double *pg = base - g - 1;
+    const R *pg = base - g - 1;
     for (int k = k0; k <= kmax; k += 8) {
 #pragma unroll
         for (int u = 0; u < 8; u++) {
-            const double h = Hk[u];
+            const R h = (R)Hk[u];
 #pragma unroll
             for (int c = 0; c < 8; c++) tmp[c] = fma(h, w[(c - u + 8) % 8], tmp[c]);
             // next tap needs in[8 col - (k+u+1)]: row 7-u, column col - g - 1
@@ -231,61 +243,61 @@ __device__ inline void convolve8(const double *Hs0, int K_LO, int nH, int kmin, 
 }
 
 // per-bin constants: shared memory (transposed [row c][column]) or global memory for the finest grids
-template <int NC, bool GS>
+template <int NC, bool GS, typename R>
 struct GridAcc {
-    const double *sm;  // [NGRID][8][32 NC]
+    const R *sm;       // [NGRID][8][32 NC]
     const GridDesc *g;
-    __device__ inline double hnu(int c, int col) const
+    __device__ inline R hnu(int c, int col) const
     {
         if (GS) return sm[(0 * 8 + c) * (32 * NC) + col];
         int j = 8 * col + c;
-        return j < g->nE ? __ldg(g->hnu + j) : 1.0;
+        return (R)(j < g->nE ? __ldg(g->hnu + j) : 1.0);
     }
-    __device__ inline double bbpre(int c, int col) const
+    __device__ inline R bbpre(int c, int col) const
     {
         if (GS) return sm[(1 * 8 + c) * (32 * NC) + col];
         int j = 8 * col + c;
-        return j < g->nE ? __ldg(g->bbpre + j) : 0.0;
+        return (R)(j < g->nE ? __ldg(g->bbpre + j) : 0.0);
     }
-    __device__ inline double wt(int c, int col) const
+    __device__ inline R wt(int c, int col) const
     {
         if (GS) return sm[(2 * 8 + c) * (32 * NC) + col];
         int j = 8 * col + c;
-        return j < g->nE ? __ldg(g->wt + j) : 0.0;
+        return (R)(j < g->nE ? __ldg(g->wt + j) : 0.0);
     }
-    __device__ inline double pk(int c, int col) const // pack factor of relagn.py:970-974 (h, 4 pi d^2 cancel)
+    __device__ inline R pk(int c, int col) const // pack factor of relagn.py:970-974 (h, 4 pi d^2 cancel)
     {
         if (GS) return sm[(3 * 8 + c) * (32 * NC) + col];
         int j = 8 * col + c;
-        return j < g->nE ? (__ldg(g->dE + j) * 4) / __ldg(g->Egrid + j) : 0.0;
+        return (R)(j < g->nE ? (__ldg(g->dE + j) * 4) / __ldg(g->Egrid + j) : 0.0);
     }
-    __device__ inline double upk(int c, int col) const // unpack factor of relagn.py:1003-1006
+    __device__ inline R upk(int c, int col) const // unpack factor of relagn.py:1003-1006
     {
         if (GS) return sm[(4 * 8 + c) * (32 * NC) + col];
         int j = 8 * col + c;
-        return j < g->nE ? __ldg(g->Egrid + j) / __ldg(g->dE + j) : 0.0;
+        return (R)(j < g->nE ? __ldg(g->Egrid + j) / __ldg(g->dE + j) : 0.0);
     }
 };
 
 // Accumulators: registers (statically indexed through a switch on the chunk, so that the chunk loops with their
 // large bodies need not be unrolled) for NC <= 4, the warp's shared memory otherwise.
-template <int NC, bool ACC_REG>
+template <int NC, bool ACC_REG, typename R>
 struct Acc {
-    double r[ACC_REG ? NC * 8 : 1];
-    double *s; // [8][32 NC] when !ACC_REG
+    R r[ACC_REG ? NC * 8 : 1];
+    R *s; // [8][32 NC] when !ACC_REG
     int lane;
     __device__ inline void zero()
     {
         if (ACC_REG) {
 #pragma unroll
-            for (int i = 0; i < NC * 8; i++) r[i] = 0.0;
+            for (int i = 0; i < NC * 8; i++) r[i] = 0;
         } else {
             for (int ch = 0; ch < NC; ch++)
 #pragma unroll
-                for (int c = 0; c < 8; c++) s[c * 32 * NC + 32 * ch + lane] = 0.0;
+                for (int c = 0; c < 8; c++) s[c * 32 * NC + 32 * ch + lane] = 0;
         }
     }
-    __device__ inline void add(int ch, const double (&v)[8])
+    __device__ inline void add(int ch, const R (&v)[8])
     {
         if (ACC_REG) {
             switch (ch) {
@@ -312,7 +324,7 @@ struct Acc {
         }
     }
     // write the accumulators into the warp's transposed buffer (row c, column 32 ch + lane)
-    __device__ inline void dump(double *inBase, int RS)
+    __device__ inline void dump(R *inBase, int RS)
     {
         if (ACC_REG) {
 #pragma unroll
@@ -334,8 +346,8 @@ struct Acc {
                 const int j0 = 8 * (32 * ch + lane);
 #pragma unroll
                 for (int c = 0; c < 8; c++) {
-                    if (j0 + c < nE) out[j0 + c] = r[ch * 8 + c];
-                    if (reset) r[ch * 8 + c] = 0.0;
+                    if (j0 + c < nE) out[j0 + c] = (double)r[ch * 8 + c];
+                    if (reset) r[ch * 8 + c] = 0;
                 }
             }
         } else {
@@ -343,17 +355,20 @@ struct Acc {
                 const int j0 = 8 * (32 * ch + lane);
 #pragma unroll
                 for (int c = 0; c < 8; c++) {
-                    double *p = &s[c * 32 * NC + 32 * ch + lane];
-                    if (j0 + c < nE) out[j0 + c] = *p;
-                    if (reset) *p = 0.0;
+                    R *p = &s[c * 32 * NC + 32 * ch + lane];
+                    if (j0 + c < nE) out[j0 + c] = (double)*p;
+                    if (reset) *p = 0;
                 }
             }
         }
     }
 };
 
-template <int NC>
-__global__ void __launch_bounds__(NC <= 4 ? 384 : 256, 1) spectrum_kernel(SpecArgs A)
+// R = double: the FP64 path (reference precision).  R = float (RG_FLAG_FP32): local spectra, the shared-memory
+// buffer, the convolution and the accumulators in single precision -- the histogram, every per-annulus scalar, the
+// Kompaneets solve and the normalisations stay FP64.
+template <int NC, typename R>
+__global__ void __launch_bounds__(NC <= 4 ? (sizeof(R) == 4 ? 512 : 384) : 256, 1) spectrum_kernel(SpecArgs A)
 {
     constexpr bool GS = NC <= 8;       // grid constants in shared memory
     constexpr bool ACC_REG = NC <= 4;  // accumulators in registers
@@ -367,18 +382,18 @@ __global__ void __launch_bounds__(NC <= 4 ? 384 : 256, 1) spectrum_kernel(SpecAr
     const int RS = A.HL + NCOL + A.HH;
     const int HSZ = round_up2(A.nH + 24);
 
-    // ---- shared memory carve ----
-    double *sm = reinterpret_cast<double *>(smem_raw);
-    double *sgrid = sm;
-    if (GS) sm += NGRID * 8 * NCOL;
-    double *s_red = sm; sm += 16;
-    int *s_misc = reinterpret_cast<int *>(sm); sm += 2;
-    const size_t wd = 8 * (size_t)RS + (size_t)HSZ + (ACC_REG ? 0 : 8 * (size_t)NCOL);
-    double *warp0 = sm;
-    double *wbase = sm + wd * warp;
-    double *inT = wbase;                  // [8][RS]
-    double *Hslot = inT + 8 * (size_t)RS; // [HSZ]: 8 zero pad, nH bins, >= 16 zero pad
-    double *acc_s = Hslot + HSZ;          // [8][NCOL] when !ACC_REG
+    // ---- shared memory carve: [grid constants (R)] [16 doubles + item slot] [per warp: inT (R) | Hslot (double) | acc (R)]
+    //      (every piece is a multiple of 8 bytes for both R) ----
+    unsigned char *smb = smem_raw;
+    R *sgrid = reinterpret_cast<R *>(smb);
+    if (GS) smb += (size_t)NGRID * 8 * NCOL * sizeof(R);
+    double *s_red = reinterpret_cast<double *>(smb); smb += 16 * sizeof(double);
+    int *s_misc = reinterpret_cast<int *>(smb); smb += 2 * sizeof(double);
+    const size_t wd = 8 * (size_t)RS * sizeof(R) + (size_t)HSZ * sizeof(double) + (ACC_REG ? 0 : 8 * (size_t)NCOL * sizeof(R));
+    unsigned char *const warp0 = smb;
+    R *inT = reinterpret_cast<R *>(smb + wd * warp);                   // [8][RS]
+    double *Hslot = reinterpret_cast<double *>(inT + 8 * (size_t)RS);  // [HSZ]: 8 zero pad, nH bins, >= 16 zero pad
+    R *acc_s = reinterpret_cast<R *>(Hslot + HSZ);                     // [8][NCOL] when !ACC_REG
     (void)acc_s;
 
     // ---- CTA prologue: stage the per-bin constants (transposed), zero the warp buffers ----
@@ -387,17 +402,18 @@ __global__ void __launch_bounds__(NC <= 4 ? 384 : 256, 1) spectrum_kernel(SpecAr
             int c = i / NCOL, col = i - c * NCOL;
             int j = 8 * col + c;
             bool ok = j < nE;
-            sgrid[(0 * 8 + c) * NCOL + col] = ok ? A.grid.hnu[j] : 1.0; // padding bins: 0 / (exp(1/kT) - 1) = 0
-            sgrid[(1 * 8 + c) * NCOL + col] = ok ? A.grid.bbpre[j] : 0.0;
-            sgrid[(2 * 8 + c) * NCOL + col] = ok ? A.grid.wt[j] : 0.0;
-            sgrid[(3 * 8 + c) * NCOL + col] = ok ? (A.grid.dE[j] * 4) / A.grid.Egrid[j] : 0.0;
-            sgrid[(4 * 8 + c) * NCOL + col] = ok ? A.grid.Egrid[j] / A.grid.dE[j] : 0.0;
+            sgrid[(0 * 8 + c) * NCOL + col] = (R)(ok ? A.grid.hnu[j] : 1.0); // padding bins: 0 / (exp(1/kT) - 1) = 0
+            sgrid[(1 * 8 + c) * NCOL + col] = (R)(ok ? A.grid.bbpre[j] : 0.0);
+            sgrid[(2 * 8 + c) * NCOL + col] = (R)(ok ? A.grid.wt[j] : 0.0);
+            sgrid[(3 * 8 + c) * NCOL + col] = (R)(ok ? (A.grid.dE[j] * 4) / A.grid.Egrid[j] : 0.0);
+            sgrid[(4 * 8 + c) * NCOL + col] = (R)(ok ? A.grid.Egrid[j] / A.grid.dE[j] : 0.0);
         }
     }
-    for (int i = lane; i < 8 * RS + HSZ; i += 32) wbase[i] = 0.0;
-    GridAcc<NC, GS> G;
+    for (int i = lane; i < 8 * RS; i += 32) inT[i] = 0;
+    for (int i = lane; i < HSZ; i += 32) Hslot[i] = 0.0;
+    GridAcc<NC, GS, R> G;
     G.sm = sgrid; G.g = &A.grid;
-    double *const inBase = inT + A.HL + lane; // row 0, this lane's column of chunk 0
+    R *const inBase = inT + A.HL + lane; // row 0, this lane's column of chunk 0
     const double dlnE = A.grid.dlnE;
     unsigned long long st_w = 0, st_n = 0;
 
@@ -437,7 +453,7 @@ __global__ void __launch_bounds__(NC <= 4 ? 384 : 256, 1) spectrum_kernel(SpecAr
             if (r.has_hotshape) hot_F = A.farr + (size_t)(r.sys_base + r.n_warm) * nE;
             double part = 0;
             if (hot_F)
-                for (int j = tid; j < nE; j += nthreads) part += __ldg(hot_F + j) * G.wt(j & 7, j >> 3);
+                for (int j = tid; j < nE; j += nthreads) part += __ldg(hot_F + j) * __ldg(A.grid.wt + j);
             part = warp_sum(part);
             if (lane == 0) s_red[warp] = part;
             __syncthreads();
@@ -474,7 +490,7 @@ __global__ void __launch_bounds__(NC <= 4 ? 384 : 256, 1) spectrum_kernel(SpecAr
         const double Rg2 = r.Rg * r.Rg;
         const double cosfac = r.cosinc / 0.5;
 
-        Acc<NC, ACC_REG> acc;
+        Acc<NC, ACC_REG, R> acc;
         acc.s = acc_s; acc.lane = lane;
         acc.zero();
         if (comps) { for (int j = lane; j < 3 * nE; j += 32) part_w[j] = 0.0; }
@@ -513,7 +529,8 @@ __global__ void __launch_bounds__(NC <= 4 ? 384 : 256, 1) spectrum_kernel(SpecAr
                         p_s1 = RGK_KB * Tann;
                         p_s2 = RGK_SB * (t * t * t * t) * Rg2;
                         // first bin whose Planck exponent overflows (exp(x) = inf for x > 709.78 -> B = 0 exactly)
-                        const double lim = 710.0 * p_s1;
+                        // (single precision: expm1f overflows past x = 88.7)
+                        const double lim = (sizeof(R) == 4 ? 89.0 : 710.0) * p_s1;
                         int lo_j = 0, hi_j = nE;
                         while (lo_j < hi_j) {
                             int m = (lo_j + hi_j) >> 1;
@@ -584,15 +601,15 @@ __global__ void __launch_bounds__(NC <= 4 ? 384 : 256, 1) spectrum_kernel(SpecAr
 
                 // ---- local spectrum, chunk by chunk ----
                 const int nch_live = region == 0 ? ((jz + 255) >> 8) : NC; // chunks holding a non-zero bin
-                const double inv_kT = region == 0 ? 1.0 / s1 : 0.0;
-                double part = 0;
+                const R inv_kT = (R)(region == 0 ? 1.0 / s1 : 0.0);
+                R part = 0;
                 // warm annulus: its Comptonised spectrum is already on the grid (nthcomp_kernel)
                 const double *w_F = region == 1 ? A.farr + (size_t)(r.sys_base + loc) * nE : nullptr;
                 for (int ch = 0; ch < NC; ch++) {
                     const int col = 32 * ch + lane, j0 = 8 * col;
-                    double L[8];
+                    R L[8];
 #pragma unroll
-                    for (int c = 0; c < 8; c++) L[c] = 0.0;
+                    for (int c = 0; c < 8; c++) L[c] = 0;
                     if (ch >= nch_live) {
                         // Wien tail past the overflow point: identically zero
                     } else if (region == 0) {
@@ -600,14 +617,13 @@ __global__ void __launch_bounds__(NC <= 4 ? 384 : 256, 1) spectrum_kernel(SpecAr
                         // the last-bit difference in x moves exp(x) by < 1e-13 relative)
 #pragma unroll
                         for (int c = 0; c < 8; c++) {
-                            double ef = exp(G.hnu(c, col) * inv_kT) - 1;
-                            L[c] = (RGK_PI * G.bbpre(c, col)) * __drcp_rn(ef); // 1/inf = 0 past the overflow point
+                            L[c] = planck_bin(G.hnu(c, col), G.bbpre(c, col), inv_kT);
                             part += L[c] * G.wt(c, col);
                         }
                     } else if (j0 < nE) {
 #pragma unroll
                         for (int c = 0; c < 8; c++) {
-                            L[c] = j0 + c < nE ? __ldg(w_F + j0 + c) : 0.0;
+                            L[c] = (R)(j0 + c < nE ? __ldg(w_F + j0 + c) : 0.0);
                             part += L[c] * G.wt(c, col);
                         }
                     }
@@ -623,10 +639,10 @@ __global__ void __launch_bounds__(NC <= 4 ? 384 : 256, 1) spectrum_kernel(SpecAr
                 if (region == 0 && A.grid.n_ext) { // relagn.py:868-873
                     for (int q = lane; q < A.grid.n_ext; q += 32) {
                         double ef = exp(A.grid.x_hnu[q] / s1) - 1;
-                        part += RGK_PI * (A.grid.x_bbpre[q] / ef) * A.grid.x_wt[q];
+                        part += (R)(RGK_PI * (A.grid.x_bbpre[q] / ef) * A.grid.x_wt[q]);
                     }
                 }
-                const double radiance = warp_sum(part);
+                const double radiance = (double)warp_sum(part);
                 __syncwarp();
                 // Lnu = norm * (B / radiance), zero when the annulus emits nothing (relagn.py:885-889, 933-937)
                 if (radiance != 0) {
@@ -639,18 +655,19 @@ __global__ void __launch_bounds__(NC <= 4 ? 384 : 256, 1) spectrum_kernel(SpecAr
                             k_hi = k_hi < kmx ? k_hi : kmx;
                             if (k_lo > k_hi) continue;
                             const int col = 32 * ch + lane;
-                            double tmp[8];
-                            convolve8(Hslot + 8, K_LO, nH, k_lo, k_hi, inBase + 32 * ch, RS, tmp);
+                            R tmp[8];
+                            convolve8<R>(Hslot + 8, K_LO, nH, k_lo, k_hi, inBase + 32 * ch, RS, tmp);
+                            // (the scale factor alone can exceed the single-precision range: multiply in double)
 #pragma unroll
-                            for (int c = 0; c < 8; c++) tmp[c] *= scale * G.upk(c, col);
+                            for (int c = 0; c < 8; c++) tmp[c] = (R)((double)tmp[c] * (scale * (double)G.upk(c, col)));
                             acc.add(ch, tmp);
                         }
                     } else {
                         const double scale = (s2 / radiance) * geo;
                         for (int ch = 0; ch < nch_live; ch++) {
-                            double v[8];
+                            R v[8];
 #pragma unroll
-                            for (int c = 0; c < 8; c++) v[c] = scale * inBase[c * RS + 32 * ch];
+                            for (int c = 0; c < 8; c++) v[c] = (R)(scale * (double)inBase[c * RS + 32 * ch]);
                             acc.add(ch, v);
                         }
                     }
@@ -672,29 +689,30 @@ __global__ void __launch_bounds__(NC <= 4 ? 384 : 256, 1) spectrum_kernel(SpecAr
 #pragma unroll
                 for (int c = 0; c < 8; c++) {
                     const int j = 8 * col + c;
-                    inBase[c * RS + 32 * ch] = (hot_F && j < nE) ? __ldg(hot_F + j) * G.pk(c, col) : 0.0;
+                    inBase[c * RS + 32 * ch] = (hot_F && j < nE) ? (R)__ldg(hot_F + j) * G.pk(c, col) : (R)0;
                 }
             }
             __syncwarp();
             const double Lum = r.Ldiss + r.Lseed;
             for (int ch = 0; ch < NC; ch++) {
                 const int col = 32 * ch + lane;
-                double tmp[8];
+                R tmp[8];
 #pragma unroll
-                for (int c = 0; c < 8; c++) tmp[c] = 0.0;
-                if (rel && hot_any_conv) convolve8(Hslot + 8, K_LO, nH, hk_min, hk_max, inBase + 32 * ch, RS, tmp);
-                double v[8];
+                for (int c = 0; c < 8; c++) tmp[c] = 0;
+                if (rel && hot_any_conv) convolve8<R>(Hslot + 8, K_LO, nH, hk_min, hk_max, inBase + 32 * ch, RS, tmp);
+                R v[8];
 #pragma unroll
                 for (int c = 0; c < 8; c++) {
-                    v[c] = 0.0;
+                    v[c] = 0;
                     if (8 * col + c < nE) {
                         // the buffer holds F * pk and pk * upk = 4; F / shape_int: 0/0 -> NaN as the reference (:1316)
-                        double F = inBase[c * RS + 32 * ch] * G.upk(c, col) * 0.25;
+                        double F = (double)inBase[c * RS + 32 * ch] * (double)G.upk(c, col) * 0.25;
                         if (rel) {
-                            v[c] = Sflat * (F / shape_int);
-                            if (hot_any_conv) v[c] += ((tmp[c] / shape_int) * G.upk(c, col)) / cosfac; // relagn.py:1362
+                            double vv = Sflat * (F / shape_int);
+                            if (hot_any_conv) vv += (((double)tmp[c] / shape_int) * (double)G.upk(c, col)) / cosfac; // relagn.py:1362
+                            v[c] = (R)vv;
                         } else {
-                            v[c] = Lum * (F / shape_int);
+                            v[c] = (R)(Lum * (F / shape_int));
                         }
                     }
                 }
@@ -712,9 +730,9 @@ __global__ void __launch_bounds__(NC <= 4 ? 384 : 256, 1) spectrum_kernel(SpecAr
             __syncthreads();
             for (int j = tid; j < nE; j += nthreads) {
                 const size_t off = (size_t)(j & 7) * RS + A.HL + (j >> 3);
-                double v = 0.0;
-                for (int w = 0; w < nwarps; w++) v += warp0[wd * w + off];
-                out_tot[j] = v;
+                R v = 0;
+                for (int w = 0; w < nwarps; w++) v += reinterpret_cast<const R *>(warp0 + wd * w)[off];
+                out_tot[j] = (double)v;
             }
         }
         // leave the H slot clean for the next item
@@ -748,15 +766,16 @@ __global__ void __launch_bounds__(256) reduce_parts_kernel(const double *__restr
     out[((size_t)set * (comps ? 4 : 1) + (comps ? 3 : 0)) * nE + j] = tot;
 }
 
-template <int NC>
+template <int NC, typename R>
 static int launch_spec(const SpecArgs &args, int sm_count, cudaStream_t st)
 {
-    size_t smem = rg_spectrum_smem_bytes(NC, args.nH, args.HL, args.HH, args.warps);
-    RG_CUDA_OK(cudaFuncSetAttribute(spectrum_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    size_t smem = rg_spectrum_smem_bytes(NC, args.nH, args.HL, args.HH, args.warps, sizeof(R) == 4);
+    auto kern = spectrum_kernel<NC, R>;
+    RG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long items = (long)args.P * args.NB;
     long ctas = items < sm_count ? items : sm_count; // persistent: one CTA per SM, CTAs pull items from the queue
     RG_CUDA_OK(cudaMemsetAsync(args.queue, 0, sizeof(int), st));
-    RG_LAUNCH(spectrum_kernel<NC>, dim3((unsigned)ctas), dim3(32 * args.warps), smem, st, args);
+    RG_LAUNCH(kern, dim3((unsigned)ctas), dim3(32 * args.warps), smem, st, args);
     RG_CUDA_OK(cudaGetLastError());
     const bool comps = (args.flags & RG_FLAG_COMPONENTS) != 0;
     if (comps || args.NB > 1) {
@@ -772,8 +791,9 @@ int rg_launch_spectrum(const SpecArgs &args, int sm_count, cudaStream_t st)
 {
     int NC = rg_spectrum_pick_NC(args.grid.nE);
     if (args.warps < 1) return rg_set_error(RG_E_GRID, "energy grid too fine for the shared-memory working set");
-    if (NC == 4) return launch_spec<4>(args, sm_count, st);
-    if (NC == 8) return launch_spec<8>(args, sm_count, st);
-    if (NC == 20) return launch_spec<20>(args, sm_count, st);
+    const bool fp32 = (args.flags & RG_FLAG_FP32) != 0;
+    if (NC == 4) return fp32 ? launch_spec<4, float>(args, sm_count, st) : launch_spec<4, double>(args, sm_count, st);
+    if (NC == 8) return fp32 ? launch_spec<8, float>(args, sm_count, st) : launch_spec<8, double>(args, sm_count, st);
+    if (NC == 20) return fp32 ? launch_spec<20, float>(args, sm_count, st) : launch_spec<20, double>(args, sm_count, st);
     return rg_set_error(RG_E_GRID, "nE = %d exceeds the kernel capacity (%d)", args.grid.nE, 20 * 256);
 }
