@@ -551,9 +551,7 @@ extern "C" int rg_eval_batch(rg_ctx *c, const double *d_params, int P, int model
     memset(&A, 0, sizeof A);
     A.grid = c->gd;
     A.flags = flags;
-    A.p10tab = c->d_p10;
     A.farr = c->d_farr;
-    A.header = c->d_header;
     A.queue = c->d_queue;
     if (rel) {
         A.tab = c->td;

@@ -42,9 +42,7 @@ struct SpecArgs {
     GridDesc grid;
     TabDesc tab;
     unsigned flags;
-    const double *p10tab; // [RG_NTH+1] 10^(0.02 j)
     const double *farr;   // [sys][nE] Comptonised spectra on the energy grid (nthcomp_kernel)
-    const double *header; // [sys][4] = xmin, normfac, jmax, log10(511 xmin)
     double *out;          // [P][nE] or [P][4][nE]
     int K_LO, nH;         // widest shift-histogram support over all table nodes: k in [K_LO, K_LO + nH)
     int HL, HH;           // zero halo columns of the transposed local-spectrum buffer

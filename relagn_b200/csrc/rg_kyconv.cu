@@ -1,57 +1,36 @@
 // rg_kyconv.cu -- the stand-alone convolution seam (B1):
 //   xspec.callModelFunction('kyconv', energies, params[12], flux)
 //   (src/python_version/relagn.py:979-1001; tests/blurr_test.py:51-54,111-119)
-// One annulus of arbitrary width and emissivity (alpha, beta, r_break): the
-// shift histogram is built by one CTA (rings in passes of 256/NPHI, shared-
-// memory atomics), then a second kernel applies it to the photon spectrum.
-// The same device functions (rg_transfer.cuh) build every annulus inside the
-// fused spectrum kernel.
+// One annulus of arbitrary width and emissivity (alpha, beta, r_break): one CTA of 8 warps builds the shift
+// histogram -- ring m goes to warp m mod 8, every warp deposits into its own shared-memory copy with the
+// warp-shuffle segmented reduction of rg_transfer.cuh (no atomics), the copies are folded in warp order -- then a
+// second kernel applies it to the photon spectrum.  The same device functions build every annulus inside the fused
+// spectrum kernel.
 #include "rg_kernels.h"
 #include "rg_transfer.cuh"
 
 #define KT 256
+#define KW (KT / 32)
 
 __global__ void __launch_bounds__(KT)
 ky_hist_kernel(TabDesc tab, double a, double theta_o, double r1, double r2, double alpha, double beta, double rb,
                double zs, double dlnE, int nsub, double *__restrict__ H_out, int K_LO, int nH)
 {
     RG_DYN_SMEM(smem_raw);
-    double *H = reinterpret_cast<double *>(smem_raw);
-    __shared__ double sv[KT], wv[KT], rA[8], rFr[8];
-    __shared__ int rS0[8], rS1[8];
-    const int tid = threadIdx.x;
-    for (int i = tid; i < nH; i += KT) H[i] = 0.0;
+    double *H = reinterpret_cast<double *>(smem_raw); // [KW][nH]
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < KW * nH; i += KT) H[i] = 0.0;
     TabSel ts;
     rg_tab_select(ts, tab, a, theta_o);
-    const int NP = ts.NPHI;
-    const int rpp = KT / NP;
-    double lnr = log(r2 / r1);
-    double dphi = 2 * RGK_PI / NP;
     __syncthreads();
-    for (int m0 = 0; m0 < nsub; m0 += rpp) {
-        int nr = nsub - m0 < rpp ? nsub - m0 : rpp;
-        if (tid < nr) {
-            RingGeo g = rg_ring_geo(ts, r1, r2, lnr, m0 + tid, nsub, alpha, beta, rb);
-            rA[tid] = g.A; rFr[tid] = g.fr; rS0[tid] = g.s0; rS1[tid] = g.s1;
-        }
-        __syncthreads();
-        int slot = tid / NP, p = tid - slot * NP;
-        if (slot < nr) {
-            double gg, jj;
-            rg_ring_sample(ts, rS0[slot], rS1[slot], rFr[slot], p, gg, jj);
-            sv[tid] = log(gg) / dlnE + zs;
-            wv[tid] = jj * gg * gg * gg;
-        }
-        __syncthreads();
-        if (slot < nr) {
-            int t1 = (p + 1 == NP) ? tid - (NP - 1) : tid + 1;
-            double W = 0.5 * (wv[tid] + wv[t1]) * dphi * rA[slot];
-            int kf, kl;
-            rg_deposit(H, K_LO, nH, sv[tid], sv[t1], W, kf, kl);
-        }
-        __syncthreads();
+    int kmn, kmx;
+    warp_build_rings(H + (size_t)warp * nH, K_LO, nH, ts, r1, r2, dlnE, nsub, warp, KW, alpha, beta, rb, zs, 1.0, kmn, kmx);
+    __syncthreads();
+    for (int i = tid; i < nH; i += KT) {
+        double v = 0.0;
+        for (int w = 0; w < KW; w++) v += H[(size_t)w * nH + i];
+        H_out[i] = v;
     }
-    for (int i = tid; i < nH; i += KT) H_out[i] = H[i];
 }
 
 __global__ void __launch_bounds__(KT)
@@ -73,8 +52,8 @@ int rg_launch_ky_hist(const TabDesc &tab, double a, double theta_o, double r1, d
                       cudaStream_t st)
 {
     if (KT % tab.NPHI != 0 || tab.NPHI < 32) return rg_set_error(RG_E_ARG, "NPHI must divide %d and be >= 32", KT);
-    size_t smem = (size_t)nH * sizeof(double);
-    if (smem > 200 * 1024) return rg_set_error(RG_E_GRID, "energy grid too fine for the kyconv histogram");
+    size_t smem = (size_t)KW * nH * sizeof(double);
+    if (smem > 220 * 1024) return rg_set_error(RG_E_GRID, "energy grid too fine for the kyconv histogram");
     double zs = 0.0;
     if (zshift != 0) zs = -log(1 + zshift) / dlnE;
     if (nsub <= 0) nsub = rg_auto_nsub(r1, r2, log(r2 / r1), dlnE);

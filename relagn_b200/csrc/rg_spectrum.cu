@@ -93,123 +93,6 @@ __device__ inline float planck_bin(float hnu, float bbpre, float inv_kT)
     return (3.14159265358979f * bbpre) / ef;
 }
 
-// ---------------------------------------------------------------------------
-// Deterministic warp-cooperative deposit of one segment per lane into Hs[k - K_LO]
-// (Hs is owned by this warp).  The weight W of segment [sa, sb] (in units of
-// shift bins) is spread uniformly and binned with the linear (hat) kernel onto
-// bins kfirst + c.  Neighbouring lanes mostly start in the same bin, so lanes
-// are grouped into runs of equal kfirst (one ballot); for every bin offset c the
-// run is summed by a segmented inclusive scan (shuffles) and written once by the
-// run's last lane.  Runs that are not adjacent but share kfirst are written in
-// successive rounds in lane order, so no two lanes ever update one bin at once
-// and the summation order is fixed.
-__device__ inline double seg_contrib(bool point, int c, int nb, int kfirst, double lo, double hi, double f, double W,
-                                     double inv)
-{
-    if (c >= nb) return 0.0;
-    if (point) return c == 0 ? W * (1 - f) : W * f;
-    const int k = kfirst + c;
-    return inv * (rg_hat_piece(lo - k, hi - k, -1.0, 0.0, true) + rg_hat_piece(lo - k, hi - k, 0.0, 1.0, false));
-}
-
-__device__ inline void warp_deposit(double *Hs, int K_LO, int nH, double sa, double sb, double W, int &kf_min,
-                                    int &kl_max)
-{
-    const int lane = threadIdx.x & 31;
-    double lo = sa < sb ? sa : sb, hi = sa < sb ? sb : sa;
-    double len = hi - lo;
-    const bool point = len < 1e-12;
-    int kfirst, nb;
-    double f = 0, inv = 0;
-    if (point) {
-        double mid = 0.5 * (lo + hi);
-        double kf = floor(mid);
-        f = mid - kf;
-        kfirst = (int)kf; nb = 2;
-    } else {
-        kfirst = (int)floor(lo);
-        nb = (int)floor(hi) + 1 - kfirst + 1;
-        inv = W / len;
-    }
-    kf_min = kfirst < kf_min ? kfirst : kf_min;
-    {
-        int kl = kfirst + nb - 1;
-        kl_max = kl > kl_max ? kl : kl_max;
-    }
-    // run structure (the same for every bin offset)
-    const int kprev = __shfl_up_sync(FULL, kfirst, 1);
-    const unsigned heads = __ballot_sync(FULL, lane == 0 || kfirst != kprev);
-    const int start = 31 - __clz((int)(heads & (0xffffffffu >> (31 - lane))));
-    const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
-    const unsigned peers = __match_any_sync(FULL, tail ? kfirst : (-0x40000000 - lane));
-    const int myround = tail ? __popc(peers & ((1u << lane) - 1u)) : -1;
-    const int nrounds = __reduce_max_sync(FULL, myround) + 1;
-    const int nbmax = __reduce_max_sync(FULL, nb);
-    for (int c0 = 0; c0 < nbmax; c0 += 3) {
-        double v0 = seg_contrib(point, c0, nb, kfirst, lo, hi, f, W, inv);
-        double v1 = seg_contrib(point, c0 + 1, nb, kfirst, lo, hi, f, W, inv);
-        double v2 = seg_contrib(point, c0 + 2, nb, kfirst, lo, hi, f, W, inv);
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            double u0 = __shfl_up_sync(FULL, v0, d), u1 = __shfl_up_sync(FULL, v1, d), u2 = __shfl_up_sync(FULL, v2, d);
-            if (lane - d >= start) { v0 += u0; v1 += u1; v2 += u2; }
-        }
-        const int i0 = kfirst + c0 - K_LO;
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            const double v = c == 0 ? v0 : (c == 1 ? v1 : v2);
-            for (int rd = 0; rd < nrounds; rd++) {
-                if (myround == rd && c0 + c < nbmax) {
-                    int i = i0 + c;
-                    if (i >= 0 && i < nH) Hs[i] += v;
-                }
-                __syncwarp();
-            }
-        }
-    }
-}
-
-// One warp adds weight x (shift histogram of annulus [r1, r2]) to Hs.
-__device__ inline void warp_build_hist(double *Hs, int K_LO, int nH, const TabSel &ts, double r1, double r2, double dlnE,
-                                       double weight, int &kmin_out, int &kmax_out)
-{
-    const int lane = threadIdx.x & 31;
-    const int NP = ts.NPHI, nq = NP >> 5;
-    const double lnr = log(r2 / r1);
-    const int nsub = rg_auto_nsub(r1, r2, lnr, dlnE);
-    const double dphi = 2 * RGK_PI / NP;
-    int kf_min = IMAX, kl_max = -IMAX;
-    for (int m0 = 0; m0 < nsub; m0 += 32) {
-        const int nr = nsub - m0 < 32 ? nsub - m0 : 32;
-        RingGeo geo;
-        geo.A = 0; geo.fr = 0; geo.s0 = 0; geo.s1 = 0;
-        if (lane < nr) geo = rg_ring_geo(ts, r1, r2, lnr, m0 + lane, nsub, 0.0, 0.0, 1.0);
-        for (int m = 0; m < nr; m++) {
-            const double A = __shfl_sync(FULL, geo.A, m), fr = __shfl_sync(FULL, geo.fr, m);
-            const int s0 = __shfl_sync(FULL, geo.s0, m), s1 = __shfl_sync(FULL, geo.s1, m);
-            double g, jn;
-            rg_ring_sample(ts, s0, s1, fr, lane, g, jn);
-            double s_cur = log(g) / dlnE, w_cur = jn * g * g * g;
-            const double s_first = __shfl_sync(FULL, s_cur, 0), w_first = __shfl_sync(FULL, w_cur, 0);
-            for (int q = 0; q < nq; q++) {
-                double s_nxt = 0, w_nxt = 0, sn0, wn0;
-                if (q + 1 < nq) {
-                    rg_ring_sample(ts, s0, s1, fr, lane + 32 * (q + 1), g, jn);
-                    s_nxt = log(g) / dlnE; w_nxt = jn * g * g * g;
-                    sn0 = __shfl_sync(FULL, s_nxt, 0); wn0 = __shfl_sync(FULL, w_nxt, 0);
-                } else { sn0 = s_first; wn0 = w_first; }
-                double sb = __shfl_down_sync(FULL, s_cur, 1), wb = __shfl_down_sync(FULL, w_cur, 1);
-                if (lane == 31) { sb = sn0; wb = wn0; }
-                const double W = 0.5 * (w_cur + wb) * dphi * A * weight;
-                warp_deposit(Hs, K_LO, nH, s_cur, sb, W, kf_min, kl_max);
-                s_cur = s_nxt; w_cur = w_nxt;
-            }
-        }
-    }
-    kmin_out = __reduce_min_sync(FULL, kf_min);
-    kmax_out = __reduce_max_sync(FULL, kl_max);
-}
-
 // tmp[c] = sum_k H[k] in[8 col + c - k] for k in [kmin, kmax]; Hs0 points at shift K_LO of a histogram that is
 // zero-padded 8 in front and 16 behind; base = row 0 of the warp's buffer at this lane's column, RS = row stride.
 template <typename R>

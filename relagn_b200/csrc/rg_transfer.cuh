@@ -134,31 +134,133 @@ __device__ inline double rg_hat_piece(double lo, double hi, double L, double R, 
     return (r - l) * (neg ? 1.0 + mid : 1.0 - mid);
 }
 
-// deposit weight W spread uniformly over [sa,sb] onto H[k - K_LO] (shared-memory
-// histogram of nH bins, shared-memory atomics -- no global atomics anywhere).
-// kfirst/klast return the touched shift range.
-__device__ inline void rg_deposit(double *H, int K_LO, int nH, double sa, double sb, double W, int &kfirst,
-                                  int &klast)
+#define RG_FULL 0xffffffffu
+#define RG_IMAX 0x7fffffff
+
+// ---------------------------------------------------------------------------
+// Deterministic warp-cooperative deposit of one segment per lane into Hs[k - K_LO]
+// (Hs is owned by this warp).  The weight W of segment [sa, sb] (in units of
+// shift bins) is spread uniformly and binned with the linear (hat) kernel onto
+// bins kfirst + c.  Neighbouring lanes mostly start in the same bin, so lanes
+// are grouped into runs of equal kfirst (one ballot); for every bin offset c the
+// run is summed by a segmented inclusive scan (shuffles) and written once by the
+// run's last lane.  Runs that are not adjacent but share kfirst are written in
+// successive rounds in lane order, so no two lanes ever update one bin at once
+// and the summation order is fixed.
+__device__ inline double seg_contrib(bool point, int c, int nb, int kfirst, double lo, double hi, double f, double W,
+                                     double inv)
 {
+    if (c >= nb) return 0.0;
+    if (point) return c == 0 ? W * (1 - f) : W * f;
+    const int k = kfirst + c;
+    return inv * (rg_hat_piece(lo - k, hi - k, -1.0, 0.0, true) + rg_hat_piece(lo - k, hi - k, 0.0, 1.0, false));
+}
+
+__device__ inline void warp_deposit(double *Hs, int K_LO, int nH, double sa, double sb, double W, int &kf_min,
+                                    int &kl_max)
+{
+    const int lane = threadIdx.x & 31;
     double lo = sa < sb ? sa : sb, hi = sa < sb ? sb : sa;
     double len = hi - lo;
-    if (len < 1e-12) {
+    const bool point = len < 1e-12;
+    int kfirst, nb;
+    double f = 0, inv = 0;
+    if (point) {
         double mid = 0.5 * (lo + hi);
         double kf = floor(mid);
-        double f = mid - kf;
-        int i0 = (int)kf - K_LO;
-        kfirst = (int)kf; klast = (int)kf + 1;
-        if (i0 >= 0 && i0 + 1 < nH) {
-            atomicAdd(&H[i0], W * (1 - f));
-            atomicAdd(&H[i0 + 1], W * f);
-        }
-        return;
+        f = mid - kf;
+        kfirst = (int)kf; nb = 2;
+    } else {
+        kfirst = (int)floor(lo);
+        nb = (int)floor(hi) + 1 - kfirst + 1;
+        inv = W / len;
     }
-    kfirst = (int)floor(lo); klast = (int)floor(hi) + 1;
-    double inv = W / len;
-    for (int k = kfirst; k <= klast; k++) {
-        double c = rg_hat_piece(lo - k, hi - k, -1.0, 0.0, true) + rg_hat_piece(lo - k, hi - k, 0.0, 1.0, false);
-        int i = k - K_LO;
-        if (c != 0.0 && i >= 0 && i < nH) atomicAdd(&H[i], inv * c);
+    kf_min = kfirst < kf_min ? kfirst : kf_min;
+    {
+        int kl = kfirst + nb - 1;
+        kl_max = kl > kl_max ? kl : kl_max;
+    }
+    // run structure (the same for every bin offset)
+    const int kprev = __shfl_up_sync(RG_FULL, kfirst, 1);
+    const unsigned heads = __ballot_sync(RG_FULL, lane == 0 || kfirst != kprev);
+    const int start = 31 - __clz((int)(heads & (0xffffffffu >> (31 - lane))));
+    const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
+    const unsigned peers = __match_any_sync(RG_FULL, tail ? kfirst : (-0x40000000 - lane));
+    const int myround = tail ? __popc(peers & ((1u << lane) - 1u)) : -1;
+    const int nrounds = __reduce_max_sync(RG_FULL, myround) + 1;
+    const int nbmax = __reduce_max_sync(RG_FULL, nb);
+    for (int c0 = 0; c0 < nbmax; c0 += 3) {
+        double v0 = seg_contrib(point, c0, nb, kfirst, lo, hi, f, W, inv);
+        double v1 = seg_contrib(point, c0 + 1, nb, kfirst, lo, hi, f, W, inv);
+        double v2 = seg_contrib(point, c0 + 2, nb, kfirst, lo, hi, f, W, inv);
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            double u0 = __shfl_up_sync(RG_FULL, v0, d), u1 = __shfl_up_sync(RG_FULL, v1, d), u2 = __shfl_up_sync(RG_FULL, v2, d);
+            if (lane - d >= start) { v0 += u0; v1 += u1; v2 += u2; }
+        }
+        const int i0 = kfirst + c0 - K_LO;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const double v = c == 0 ? v0 : (c == 1 ? v1 : v2);
+            for (int rd = 0; rd < nrounds; rd++) {
+                if (myround == rd && c0 + c < nbmax) {
+                    int i = i0 + c;
+                    if (i >= 0 && i < nH) Hs[i] += v;
+                }
+                __syncwarp();
+            }
+        }
     }
 }
+
+// One warp adds weight x (shift histogram of rings m_begin, m_begin + m_step, ... of annulus [r1, r2] cut into nsub
+// rings) to Hs.  alpha, beta, rb: kyconv's broken power-law emissivity; zs: redshift in units of shift bins.
+__device__ inline void warp_build_rings(double *Hs, int K_LO, int nH, const TabSel &ts, double r1, double r2, double dlnE,
+                                        int nsub, int m_begin, int m_step, double alpha, double beta, double rb, double zs,
+                                        double weight, int &kmin_out, int &kmax_out)
+{
+    const int lane = threadIdx.x & 31;
+    const int NP = ts.NPHI, nq = NP >> 5;
+    const double lnr = log(r2 / r1);
+    const double dphi = 2 * RGK_PI / NP;
+    int kf_min = RG_IMAX, kl_max = -RG_IMAX;
+    const int n_mine = m_begin < nsub ? (nsub - m_begin + m_step - 1) / m_step : 0;
+    for (int m0 = 0; m0 < n_mine; m0 += 32) {
+        const int nr = n_mine - m0 < 32 ? n_mine - m0 : 32;
+        RingGeo geo;
+        geo.A = 0; geo.fr = 0; geo.s0 = 0; geo.s1 = 0;
+        if (lane < nr) geo = rg_ring_geo(ts, r1, r2, lnr, m_begin + (m0 + lane) * m_step, nsub, alpha, beta, rb);
+        for (int m = 0; m < nr; m++) {
+            const double A = __shfl_sync(RG_FULL, geo.A, m), fr = __shfl_sync(RG_FULL, geo.fr, m);
+            const int s0 = __shfl_sync(RG_FULL, geo.s0, m), s1 = __shfl_sync(RG_FULL, geo.s1, m);
+            double g, jn;
+            rg_ring_sample(ts, s0, s1, fr, lane, g, jn);
+            double s_cur = log(g) / dlnE + zs, w_cur = jn * g * g * g;
+            const double s_first = __shfl_sync(RG_FULL, s_cur, 0), w_first = __shfl_sync(RG_FULL, w_cur, 0);
+            for (int q = 0; q < nq; q++) {
+                double s_nxt = 0, w_nxt = 0, sn0, wn0;
+                if (q + 1 < nq) {
+                    rg_ring_sample(ts, s0, s1, fr, lane + 32 * (q + 1), g, jn);
+                    s_nxt = log(g) / dlnE + zs; w_nxt = jn * g * g * g;
+                    sn0 = __shfl_sync(RG_FULL, s_nxt, 0); wn0 = __shfl_sync(RG_FULL, w_nxt, 0);
+                } else { sn0 = s_first; wn0 = w_first; }
+                double sb = __shfl_down_sync(RG_FULL, s_cur, 1), wb = __shfl_down_sync(RG_FULL, w_cur, 1);
+                if (lane == 31) { sb = sn0; wb = wn0; }
+                const double W = 0.5 * (w_cur + wb) * dphi * A * weight;
+                warp_deposit(Hs, K_LO, nH, s_cur, sb, W, kf_min, kl_max);
+                s_cur = s_nxt; w_cur = w_nxt;
+            }
+        }
+    }
+    kmin_out = __reduce_min_sync(RG_FULL, kf_min);
+    kmax_out = __reduce_max_sync(RG_FULL, kl_max);
+}
+
+// One warp adds weight x (shift histogram of the whole annulus [r1, r2], ring count by rg_auto_nsub) to Hs.
+__device__ inline void warp_build_hist(double *Hs, int K_LO, int nH, const TabSel &ts, double r1, double r2, double dlnE,
+                                       double weight, int &kmin_out, int &kmax_out)
+{
+    const int nsub = rg_auto_nsub(r1, r2, log(r2 / r1), dlnE);
+    warp_build_rings(Hs, K_LO, nH, ts, r1, r2, dlnE, nsub, 0, 1, 0.0, 0.0, 1.0, 0.0, weight, kmin_out, kmax_out);
+}
+
