@@ -145,6 +145,65 @@ int rg_eval_batch(rg_ctx *ctx, const double *d_params, int P, int model, double 
 int rg_eval_batch_host(rg_ctx *ctx, const double *params_host, int P, int model, double dr_dex, unsigned flags,
                        double *out_host, double *attrs_host);
 
+/* ---- f1: observation epilogue on the device -------------------------------
+ * Unit conversion of rg_eval_batch's W/Hz spectra, restating the reference's
+ * host epilogue _to_newUnit / _to_flux (relagn.py:487-564) for whole batches:
+ *   RG_UNIT_SI       W/Hz               (identity)
+ *   RG_UNIT_CGS      erg/s/Hz           L * 1e7
+ *   RG_UNIT_CGS_WAVE erg/s/Angstrom     L nu^2 / c * 1e-10 * 1e7
+ *   RG_UNIT_SI_WAVE  W/Angstrom         L nu^2 / c * 1e-10
+ *   RG_UNIT_COUNTS   photons/s/keV      (L / h) / E
+ * as_flux != 0 divides by 4 pi d^2 (1 + z) with d in cm (cgs, cgs_wave,
+ * counts) or m (SI, SI_wave) -- distance and redshift are read per set from
+ * d_params (relagn slots 1 and 14, relqso slots 1 and 6).
+ * d_lnu, d_out: DEVICE [P][ncomp][nE]; d_out may alias d_lnu. */
+#define RG_UNIT_SI 0
+#define RG_UNIT_CGS 1
+#define RG_UNIT_CGS_WAVE 2
+#define RG_UNIT_SI_WAVE 3
+#define RG_UNIT_COUNTS 4
+int rg_convert_batch(rg_ctx *ctx, const double *d_lnu, const double *d_params, int P, int model, int ncomp, int unit,
+                     int as_flux, double *d_out, void *stream);
+
+/* Instrument grid: the XSPEC additive-model contract of the Fortran twin
+ * (relagn.f:17-115: photar(ne) in photons/cm^2/s per bin of the caller's
+ * ear(0:ne)).  The model grid is shifted to the observer's frame, edges and
+ * photons both divided by (1 + z) (relagn.f:98-102), and rebinned by
+ * fractional bin overlap -- XSPEC's inibin/erebin (relagn.f:110-112; HEASOFT,
+ * restated from its documented behaviour).
+ * ear_host: ne + 1 ascending edges in keV (observer frame). */
+int rg_set_instrument(rg_ctx *ctx, const double *ear_host, int ne);
+/* d_lnu: DEVICE [P][nE] total SED in W/Hz; d_photar: DEVICE [P][ne]. */
+int rg_photar_batch(rg_ctx *ctx, const double *d_lnu, const double *d_params, int P, int model, double *d_photar,
+                    void *stream);
+
+/* ---- f2: fit statistic on the device --------------------------------------
+ * Folds photar through an instrument response and reduces against observed
+ * counts, so that one scalar per parameter set leaves the GPU (the fit / MCMC
+ * use the reference documents, docs/relagn_docs.tex:136).
+ * Response in CSR over detector channels:
+ *   model_c = exposure * sum_{k in [rowptr[c], rowptr[c+1])} val[k] * photar[col[k]]
+ * (val = RMF x ARF in cm^2, col = index into the instrument grid).
+ * Statistic (XSPEC definitions):
+ *   RG_FIT_CHI2  sum_c ((D_c - model_c) / sigma_c)^2
+ *   RG_FIT_CSTAT 2 sum_c (model_c - D_c + D_c (ln D_c - ln model_c)), D_c = 0 -> model_c */
+#define RG_FIT_CHI2 0
+#define RG_FIT_CSTAT 1
+int rg_set_response(rg_ctx *ctx, int n_chan, const int *rowptr_host, const int *col_host, const double *val_host,
+                    double exposure);
+/* counts_host [n_chan]; sigma_host [n_chan] (RG_FIT_CHI2) or NULL (RG_FIT_CSTAT) */
+int rg_set_data(rg_ctx *ctx, const double *counts_host, const double *sigma_host, int kind);
+/* d_lnu: DEVICE [P][nE]; d_stat: DEVICE [P]; d_folded: DEVICE [P][n_chan] model counts or NULL */
+int rg_fitstat_batch(rg_ctx *ctx, const double *d_lnu, const double *d_params, int P, int model, double *d_stat,
+                     double *d_folded, void *stream);
+/* parameters -> statistic in one call: the spectra stay in a context-owned slab and never leave the device.
+ * d_params DEVICE [P][RG_NPAR], d_stat DEVICE [P], d_attrs DEVICE [P][RG_NATTR] or NULL. */
+int rg_eval_fitstat_batch(rg_ctx *ctx, const double *d_params, int P, int model, double dr_dex, unsigned flags,
+                          double *d_stat, double *d_attrs, void *stream);
+/* same with HOST buffers (15 doubles in, 1 double out per set) */
+int rg_eval_fitstat_batch_host(rg_ctx *ctx, const double *params_host, int P, int model, double dr_dex,
+                               unsigned flags, double *stat_host, double *attrs_host);
+
 /* number of kernels launched by this context so far (for accounting) */
 long rg_launch_count(rg_ctx *ctx);
 
@@ -165,6 +224,8 @@ long rg_launch_count(rg_ctx *ctx);
 #define RG_STAT_SUM_JMAX 9      /* sum over Kompaneets systems of jmax */
 #define RG_STAT_N_SYS 10        /* Kompaneets systems solved */
 #define RG_STAT_N_SETS 11       /* parameter sets evaluated */
+#define RG_STAT_MS_OBSERVE 12    /* summed time of the observation-epilogue kernels, ms */
+#define RG_STAT_N_OBSERVE 13
 int rg_set_option(rg_ctx *ctx, int key, double value);
 int rg_get_stat(rg_ctx *ctx, int key, double *value);
 int rg_reset_stats(rg_ctx *ctx);

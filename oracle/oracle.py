@@ -26,7 +26,8 @@ _ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 
 def build(force=False):
     """Compile the oracle with gcc (idempotent)."""
-    srcs = [os.path.join(_HERE, f) for f in ("relagn_oracle.c", "kerr_oracle.c", "relagn_oracle.h", "par_for.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("relagn_oracle.c", "kerr_oracle.c", "observe_oracle.c",
+                                             "relagn_oracle.h", "par_for.h")]
     if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
     return _SO
@@ -81,6 +82,12 @@ def lib():
     L.ro_kyconv.argtypes = [C.c_void_p, _dp, C.c_int, _dp, _dp]
     L.ro_constants.restype = None
     L.ro_constants.argtypes = [_dp]
+    L.ro_convert.restype = None
+    L.ro_convert.argtypes = [_dp, C.c_int, _dp, C.c_int, C.c_int, C.c_double, C.c_double, _dp]
+    L.ro_photar.restype = None
+    L.ro_photar.argtypes = [_dp, C.c_int, _dp, C.c_double, C.c_double, _dp, C.c_int, _dp]
+    L.ro_fold_stat.restype = C.c_double
+    L.ro_fold_stat.argtypes = [_dp, C.c_int, _ip, _ip, _dp, C.c_double, _dp, C.c_void_p, C.c_int, C.c_void_p]
     _lib = L
     return L
 
@@ -213,3 +220,42 @@ def evaluate_batch(params, ebins, model=0, rel=False, tab=None, dr_dex=50.0, thr
     lib().ro_eval_batch(pp, P, model, dr_dex, ebins, nE, int(bool(rel)), tab.ptr if tab is not None else None, out,
                         at, st, threads)
     return st, out, at
+
+
+# ---- observation epilogue (observe_oracle.c) ----
+UNITS = {"SI": 0, "cgs": 1, "cgs_wave": 2, "SI_wave": 3, "counts": 4}
+
+
+def convert(L, ebins, unit, as_flux, dist_mpc, z):
+    """relagn.py:487-564 on one spectrum [nE] (W/Hz)."""
+    L = np.ascontiguousarray(L, dtype=np.float64)
+    eb = np.ascontiguousarray(ebins, dtype=np.float64)
+    out = np.zeros_like(L)
+    lib().ro_convert(L, L.size, eb, UNITS[unit] if isinstance(unit, str) else int(unit), int(bool(as_flux)),
+                     float(dist_mpc), float(z), out)
+    return out
+
+
+def photar(L, ebins, dist_mpc, z, ear):
+    """relagn.f:98-112: photons/cm^2/s per bin of the observer's grid `ear` (edges, keV)."""
+    L = np.ascontiguousarray(L, dtype=np.float64)
+    eb = np.ascontiguousarray(ebins, dtype=np.float64)
+    ear = np.ascontiguousarray(ear, dtype=np.float64)
+    out = np.zeros(ear.size - 1)
+    lib().ro_photar(L, L.size, eb, float(dist_mpc), float(z), ear, ear.size - 1, out)
+    return out
+
+
+def fold_stat(photar_, rowptr, col, val, exposure, counts, sigma=None, kind=0):
+    """(statistic, folded model counts [n_chan]); kind 0 chi^2 (needs sigma), 1 Cash."""
+    ph = np.ascontiguousarray(photar_, dtype=np.float64)
+    rp = np.ascontiguousarray(rowptr, dtype=np.int32)
+    cl = np.ascontiguousarray(col, dtype=np.int32)
+    vl = np.ascontiguousarray(val, dtype=np.float64)
+    cn = np.ascontiguousarray(counts, dtype=np.float64)
+    n_chan = rp.size - 1
+    folded = np.zeros(n_chan)
+    sg = np.ascontiguousarray(sigma, dtype=np.float64) if sigma is not None else None
+    st = lib().ro_fold_stat(ph, n_chan, rp, cl, vl, float(exposure), cn, sg.ctypes.data if sg is not None else None,
+                            int(kind), folded.ctypes.data)
+    return st, folded

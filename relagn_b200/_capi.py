@@ -28,11 +28,15 @@ F_RW_LT_RH, F_RW_GT_ROUT, F_RH_LT_RISCO, F_RW_LT_RISCO, F_HMAX_GT_RH, F_HOT_SEED
 SYMBOLS = ["rg_version", "rg_last_error", "rg_ctx_create", "rg_ctx_destroy", "rg_set_grid", "rg_tables_generate",
            "rg_tables_upload", "rg_tables_download", "rg_tables_info", "rg_kyconv", "rg_ky_kernel", "rg_eval_batch",
            "rg_eval_batch_host", "rg_launch_count", "rg_measure_fp64_peak", "rg_set_option", "rg_get_stat",
-           "rg_reset_stats"]
+           "rg_reset_stats", "rg_convert_batch", "rg_set_instrument", "rg_photar_batch", "rg_set_response",
+           "rg_set_data", "rg_fitstat_batch", "rg_eval_fitstat_batch", "rg_eval_fitstat_batch_host"]
+
+UNITS = {"SI": 0, "cgs": 1, "cgs_wave": 2, "SI_wave": 3, "counts": 4}  # RG_UNIT_*
+FIT_CHI2, FIT_CSTAT = 0, 1
 
 OPT_PROFILE = 1
 STATS = {"ms_setup": 1, "ms_nthcomp": 2, "ms_spectrum": 3, "n_setup": 4, "n_nthcomp": 5, "n_spectrum": 6, "sum_W": 7,
-         "n_conv_ann": 8, "sum_jmax": 9, "n_sys": 10, "n_sets": 11}
+         "n_conv_ann": 8, "sum_jmax": 9, "n_sys": 10, "n_sets": 11, "ms_observe": 12, "n_observe": 13}
 
 _dp = C.POINTER(C.c_double)
 _fp = C.POINTER(C.c_float)
@@ -85,6 +89,23 @@ def bind(lib):
     lib.rg_get_stat.argtypes = [C.c_void_p, C.c_int, _dp]
     lib.rg_reset_stats.restype = C.c_int
     lib.rg_reset_stats.argtypes = [C.c_void_p]
+    vp = C.c_void_p
+    lib.rg_convert_batch.restype = C.c_int
+    lib.rg_convert_batch.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
+    lib.rg_set_instrument.restype = C.c_int
+    lib.rg_set_instrument.argtypes = [vp, _dp, C.c_int]
+    lib.rg_photar_batch.restype = C.c_int
+    lib.rg_photar_batch.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, vp]
+    lib.rg_set_response.restype = C.c_int
+    lib.rg_set_response.argtypes = [vp, C.c_int, _ip, _ip, _dp, C.c_double]
+    lib.rg_set_data.restype = C.c_int
+    lib.rg_set_data.argtypes = [vp, _dp, _dp, C.c_int]
+    lib.rg_fitstat_batch.restype = C.c_int
+    lib.rg_fitstat_batch.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, vp, vp]
+    lib.rg_eval_fitstat_batch.restype = C.c_int
+    lib.rg_eval_fitstat_batch.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double, C.c_uint, vp, vp, vp]
+    lib.rg_eval_fitstat_batch_host.restype = C.c_int
+    lib.rg_eval_fitstat_batch_host.argtypes = [vp, _dp, C.c_int, C.c_int, C.c_double, C.c_uint, _dp, _dp]
     return lib
 
 
@@ -215,6 +236,71 @@ class Context:
         self._check(self.lib.rg_eval_batch(self.h, C.c_void_p(params_ptr), int(P), int(model), float(dr_dex), flags,
                                            C.c_void_p(out_ptr), C.c_void_p(attrs_ptr) if attrs_ptr else None,
                                            C.c_void_p(stream) if stream else None))
+
+    # ---- observation epilogue ----
+    def convert_device(self, lnu_ptr, params_ptr, P, ncomp, unit, as_flux, out_ptr, model=MODEL_RELAGN, stream=0):
+        """relagn.py:487-564 on device buffers [P][ncomp][nE]; out_ptr may equal lnu_ptr."""
+        u = UNITS[unit] if isinstance(unit, str) else int(unit)
+        self._check(self.lib.rg_convert_batch(self.h, C.c_void_p(lnu_ptr), C.c_void_p(params_ptr) if params_ptr else None,
+                                              int(P), int(model), int(ncomp), u, int(bool(as_flux)),
+                                              C.c_void_p(out_ptr), C.c_void_p(stream) if stream else None))
+
+    def set_instrument(self, ear):
+        e = np.ascontiguousarray(ear, dtype=np.float64)
+        self._check(self.lib.rg_set_instrument(self.h, _d(e), e.size - 1))
+        self.ne = e.size - 1
+        self.n_chan = 0
+
+    def set_response(self, rowptr, col, val, exposure=1.0):
+        """CSR over channels: model_c = exposure * sum_k val[k] * photar[col[k]]."""
+        rp = np.ascontiguousarray(rowptr, dtype=np.int32)
+        cl = np.ascontiguousarray(col, dtype=np.int32)
+        vl = np.ascontiguousarray(val, dtype=np.float64)
+        assert rp[-1] == cl.size == vl.size
+        self._check(self.lib.rg_set_response(self.h, rp.size - 1, rp.ctypes.data_as(_ip), cl.ctypes.data_as(_ip),
+                                             _d(vl), float(exposure)))
+        self.n_chan = rp.size - 1
+
+    def set_data(self, counts, sigma=None, stat="chi2"):
+        kind = {"chi2": FIT_CHI2, "cstat": FIT_CSTAT}[stat]
+        cn = np.ascontiguousarray(counts, dtype=np.float64)
+        assert cn.size == self.n_chan
+        sg = np.ascontiguousarray(sigma, dtype=np.float64) if sigma is not None else None
+        self._check(self.lib.rg_set_data(self.h, _d(cn), _d(sg) if sg is not None else None, kind))
+
+    def photar_device(self, lnu_ptr, params_ptr, P, photar_ptr, model=MODEL_RELAGN, stream=0):
+        self._check(self.lib.rg_photar_batch(self.h, C.c_void_p(lnu_ptr), C.c_void_p(params_ptr), int(P), int(model),
+                                             C.c_void_p(photar_ptr), C.c_void_p(stream) if stream else None))
+
+    def fitstat_device(self, lnu_ptr, params_ptr, P, stat_ptr, folded_ptr=0, model=MODEL_RELAGN, stream=0):
+        self._check(self.lib.rg_fitstat_batch(self.h, C.c_void_p(lnu_ptr), C.c_void_p(params_ptr), int(P), int(model),
+                                              C.c_void_p(stat_ptr), C.c_void_p(folded_ptr) if folded_ptr else None,
+                                              C.c_void_p(stream) if stream else None))
+
+    def eval_fitstat_device(self, params_ptr, P, stat_ptr, attrs_ptr=0, model=MODEL_RELAGN, rel=True, dr_dex=50.0,
+                            stream=0, fp32=False):
+        flags = (FLAG_REL if rel else 0) | (FLAG_FP32 if fp32 else 0)
+        self._check(self.lib.rg_eval_fitstat_batch(self.h, C.c_void_p(params_ptr), int(P), int(model), float(dr_dex),
+                                                   flags, C.c_void_p(stat_ptr),
+                                                   C.c_void_p(attrs_ptr) if attrs_ptr else None,
+                                                   C.c_void_p(stream) if stream else None))
+
+    def eval_fitstat_host(self, params, model=MODEL_RELAGN, rel=True, dr_dex=50.0, attrs=False, fp32=False, out=None):
+        """params [P, 15] on the host -> statistic [P] (and attrs [P, 24]); 120 B in, 8 B out per set."""
+        p = np.asarray(params, dtype=np.float64)
+        if p.ndim == 1:
+            p = p[None, :]
+        P = p.shape[0]
+        if p.shape[1] != NPAR or not p.flags.c_contiguous:
+            pp = np.zeros((P, NPAR))
+            pp[:, :p.shape[1]] = p
+            p = pp
+        flags = (FLAG_REL if rel else 0) | (FLAG_FP32 if fp32 else 0)
+        st = out if out is not None else np.empty(P)
+        at = np.zeros((P, NATTR)) if attrs else None
+        self._check(self.lib.rg_eval_fitstat_batch_host(self.h, _d(p), P, int(model), float(dr_dex), flags, _d(st),
+                                                        _d(at) if attrs else None))
+        return (st, at) if attrs else st
 
     def set_profile(self, on=True):
         self._check(self.lib.rg_set_option(self.h, OPT_PROFILE, 1.0 if on else 0.0))

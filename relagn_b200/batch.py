@@ -92,6 +92,71 @@ class BatchEvaluator:
         return out_np, at
 
 
+    # ---- observation epilogue on the device ---------------------
+    def convert_device(self, spectra, params, unit="cgs", as_flux=False, out=None):
+        """The reference's getter epilogue (_to_newUnit / _to_flux, relagn.py:487-564) for a whole batch on the device.
+        spectra: CUDA [P, nE] or [P, 4, nE] W/Hz; params: CUDA [P, 15].  out=None converts in place."""
+        assert spectra.is_cuda and spectra.dtype == torch.float64 and spectra.is_contiguous()
+        P = spectra.shape[0]
+        ncomp = spectra.shape[1] if spectra.dim() == 3 else 1
+        if out is None:
+            out = spectra
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self.ctx.convert_device(spectra.data_ptr(), params.data_ptr(), P, ncomp, unit, as_flux, out.data_ptr(),
+                                model=self.model, stream=stream)
+        return out
+
+    def set_instrument(self, ear, rowptr=None, col=None, val=None, exposure=1.0):
+        """Observer-frame instrument grid (bin edges, keV) and optionally its response in CSR over channels."""
+        self.ctx.set_instrument(ear)
+        if rowptr is not None:
+            self.ctx.set_response(rowptr, col, val, exposure)
+
+    def set_data(self, counts, sigma=None, stat="chi2"):
+        self.ctx.set_data(counts, sigma, stat)
+
+    def photar_device(self, spectra, params, out=None):
+        """XSPEC additive-model output (relagn.f:98-112): photons/cm^2/s per instrument bin, CUDA [P, ne]."""
+        P = spectra.shape[0]
+        if out is None:
+            out = torch.empty((P, self.ctx.ne), dtype=torch.float64, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self.ctx.photar_device(spectra.data_ptr(), params.data_ptr(), P, out.data_ptr(), model=self.model,
+                               stream=stream)
+        return out
+
+    def fitstat_device(self, params, rel=True, out=None, fp32=False):
+        """params CUDA [P, 15] -> fit statistic CUDA [P]; the spectra never leave the device."""
+        assert params.is_cuda and params.dtype == torch.float64 and params.is_contiguous()
+        if rel:
+            self.ensure_tables()
+        P = params.shape[0]
+        if out is None:
+            out = torch.empty(P, dtype=torch.float64, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self.ctx.eval_fitstat_device(params.data_ptr(), P, out.data_ptr(), model=self.model, rel=rel,
+                                     dr_dex=self.dr_dex, stream=stream, fp32=fp32)
+        return out
+
+    def fitstat(self, params, rel=True, fp32=False):
+        """Host in, host out: 120 B per set up, 8 B per set down (the fit / MCMC inner loop)."""
+        p = np.asarray(params, dtype=np.float64)
+        if p.ndim == 1:
+            p = p[None, :]
+        P = p.shape[0]
+        if rel:
+            self.ensure_tables()
+        if self._pin_in is None or self._pin_in.shape[0] < P:
+            self._pin_in = torch.zeros((P, _capi.NPAR), dtype=torch.float64).pin_memory()
+        if getattr(self, "_pin_stat", None) is None or self._pin_stat.numel() < P:
+            self._pin_stat = torch.empty(P, dtype=torch.float64).pin_memory()
+        pin = self._pin_in[:P]
+        pin.zero_()
+        pin[:, :p.shape[1]] = torch.from_numpy(p)
+        return self.ctx.eval_fitstat_host(pin.numpy(), model=self.model, rel=rel, dr_dex=self.dr_dex, fp32=fp32,
+                                          out=self._pin_stat[:P].numpy())
+
+
 def shard_bounds(P, world, rank):
     """Contiguous split of P parameter sets over `world` ranks."""
     base, rem = divmod(P, world)
@@ -113,3 +178,16 @@ def evaluate_sharded(evaluator, params_local, rel=True, gather_dst=0, group=None
         gathered = [torch.empty_like(out) for _ in range(world)]
     dist.gather(out, gathered, dst=gather_dst, group=group)
     return out, gathered
+
+
+def fitstat_sharded(evaluator, params_local, rel=True, gather_dst=0, group=None):
+    """Sharded fit statistic: every rank reduces its own shard to one double per set on the device; the final
+    gather moves 8 B per set instead of 8 nE ("collapses the all-gather")."""
+    import torch.distributed as dist
+    stat = evaluator.fitstat_device(params_local, rel=rel)
+    if gather_dst is None or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return stat, None
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    gathered = [torch.empty_like(stat) for _ in range(world)] if rank == gather_dst else None
+    dist.gather(stat, gathered, dst=gather_dst, group=group)
+    return stat, gathered

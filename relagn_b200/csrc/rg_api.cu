@@ -75,10 +75,23 @@ struct rg_ctx {
     // instrumentation
     bool profile = false;
     unsigned long long *d_stats = nullptr;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[3];
-    double ms_acc[3] = {0, 0, 0};
-    long n_acc[3] = {0, 0, 0};
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[4]; // setup, nthcomp, spectrum, observation epilogue
+    double ms_acc[4] = {0, 0, 0, 0};
+    long n_acc[4] = {0, 0, 0, 0};
     double n_sets = 0;
+    // observation epilogue: model edges, instrument grid, response (sliced ELL), data, spectra slab
+    double *d_ebins = nullptr;
+    double *d_ear = nullptr;
+    int ne = 0;
+    int n_chan = 0, fit_kind = RG_FIT_CHI2;
+    bool have_data = false;
+    int *d_sl_off = nullptr, *d_ell_col = nullptr;
+    double *d_ell_val = nullptr, *d_counts = nullptr, *d_sigma = nullptr;
+    double exposure = 1.0;
+    double *d_slab = nullptr;
+    size_t slab_n = 0;
+    double *d_stage_stat = nullptr;
+    size_t d_stage_stat_n = 0;
     // host staging (pinned) for rg_eval_batch_host
     double *h_stage = nullptr;
     size_t h_stage_bytes = 0;
@@ -134,6 +147,8 @@ extern "C" void rg_ctx_destroy(rg_ctx *c)
     free_dev(c->d_counter); free_dev(c->d_syslist); free_dev(c->d_sptot); free_dev(c->d_farr); free_dev(c->d_header); free_dev(c->d_sc);
     free_dev(c->d_rq); free_dev(c->d_queue); free_dev(c->d_partial); free_dev(c->d_kyH); free_dev(c->d_kyin); free_dev(c->d_kyout);
     free_dev(c->d_stage_par); free_dev(c->d_stage_out); free_dev(c->d_stage_attr); free_dev(c->d_stats);
+    free_dev(c->d_ebins); free_dev(c->d_ear); free_dev(c->d_sl_off); free_dev(c->d_ell_col); free_dev(c->d_ell_val);
+    free_dev(c->d_counts); free_dev(c->d_sigma); free_dev(c->d_slab); free_dev(c->d_stage_stat);
     prof_collect(c);
     if (c->h_counter) cudaFreeHost(c->h_counter);
     if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -162,7 +177,7 @@ static int prof_end(rg_ctx *c, int kind, cudaStream_t st)
 }
 static int prof_collect(rg_ctx *c)
 {
-    for (int k = 0; k < 3; k++) {
+    for (int k = 0; k < 4; k++) {
         for (auto &pr : c->ev[k]) {
             RG_CUDA_OK(cudaEventSynchronize(pr.second));
             float ms = 0;
@@ -197,7 +212,7 @@ extern "C" int rg_reset_stats(rg_ctx *c)
     if (!c) return rg_set_error(RG_E_ARG, "rg_reset_stats: ctx is NULL");
     RG_CUDA_OK(cudaSetDevice(c->device));
     RG_TRY(prof_collect(c));
-    for (int k = 0; k < 3; k++) { c->ms_acc[k] = 0; c->n_acc[k] = 0; }
+    for (int k = 0; k < 4; k++) { c->ms_acc[k] = 0; c->n_acc[k] = 0; }
     c->n_sets = 0;
     if (c->d_stats) RG_CUDA_OK(cudaMemset(c->d_stats, 0, 4 * sizeof(unsigned long long)));
     return RG_OK;
@@ -225,6 +240,8 @@ extern "C" int rg_get_stat(rg_ctx *c, int key, double *value)
     case RG_STAT_SUM_JMAX: *value = (double)h[2]; break;
     case RG_STAT_N_SYS: *value = (double)h[3]; break;
     case RG_STAT_N_SETS: *value = c->n_sets; break;
+    case RG_STAT_MS_OBSERVE: *value = c->ms_acc[3]; break;
+    case RG_STAT_N_OBSERVE: *value = (double)c->n_acc[3]; break;
     default: return rg_set_error(RG_E_ARG, "rg_get_stat: unknown key %d", key);
     }
     return RG_OK;
@@ -297,6 +314,10 @@ extern "C" int rg_set_grid(rg_ctx *c, const double *eb, int nE)
     g.n_ext = n_ext; g.nE = nE; g.geometric = geometric; g.dlnE = dlnE;
     c->nE = nE;
     c->h_ebins.assign(eb, eb + nE + 1);
+    free_dev(c->d_ebins);
+    c->d_ebins = nullptr;
+    RG_CUDA_OK(cudaMalloc(&c->d_ebins, (size_t)(nE + 1) * sizeof(double)));
+    RG_CUDA_OK(cudaMemcpy(c->d_ebins, eb, (size_t)(nE + 1) * sizeof(double), cudaMemcpyHostToDevice));
     return RG_OK;
 }
 
@@ -694,6 +715,198 @@ extern "C" int rg_eval_batch_host(rg_ctx *c, const double *params, int P, int mo
     cudaStreamDestroy(copy_st);
     if (rc != RG_OK) return rc;
     RG_CUDA_OK(cudaGetLastError());
+    return RG_OK;
+}
+
+// ---------------------------------------------------------------------------
+// f1 / f2: observation epilogue (rg_observe.cu)
+extern "C" int rg_convert_batch(rg_ctx *c, const double *d_lnu, const double *d_params, int P, int model, int ncomp,
+                                int unit, int as_flux, double *d_out, void *stream)
+{
+    if (!c || !d_lnu || !d_out || P < 0 || ncomp < 1) return rg_set_error(RG_E_ARG, "rg_convert_batch: bad arguments");
+    if (unit < RG_UNIT_SI || unit > RG_UNIT_COUNTS) return rg_set_error(RG_E_ARG, "rg_convert_batch: unknown unit %d", unit);
+    if (as_flux && !d_params) return rg_set_error(RG_E_ARG, "rg_convert_batch: flux needs the parameter rows (distance, z)");
+    if (model != RG_MODEL_RELAGN && model != RG_MODEL_RELQSO) return rg_set_error(RG_E_ARG, "unknown model %d", model);
+    if (c->nE <= 0) return rg_set_error(RG_E_GRID, "no energy grid set (rg_set_grid)");
+    if (P == 0) return RG_OK;
+    RG_CUDA_OK(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    RG_TRY(prof_begin(c, 3, st));
+    RG_TRY(rg_launch_convert(d_lnu, d_params, P, model, ncomp, unit, as_flux, c->gd, d_out, c->sm_count, st));
+    RG_TRY(prof_end(c, 3, st));
+    c->launches++;
+    return RG_OK;
+}
+
+extern "C" int rg_set_instrument(rg_ctx *c, const double *ear, int ne)
+{
+    if (!c || !ear || ne < 1) return rg_set_error(RG_E_ARG, "rg_set_instrument: bad arguments");
+    for (int i = 0; i < ne; i++)
+        if (!(ear[i + 1] > ear[i]) || !(ear[i] >= 0)) return rg_set_error(RG_E_ARG, "instrument bin edges must ascend");
+    RG_CUDA_OK(cudaSetDevice(c->device));
+    free_dev(c->d_ear);
+    c->d_ear = nullptr; c->ne = 0;
+    RG_CUDA_OK(cudaMalloc(&c->d_ear, (size_t)(ne + 1) * sizeof(double)));
+    RG_CUDA_OK(cudaMemcpy(c->d_ear, ear, (size_t)(ne + 1) * sizeof(double), cudaMemcpyHostToDevice));
+    c->ne = ne;
+    // a response / data set belongs to one instrument grid
+    c->n_chan = 0; c->have_data = false;
+    return RG_OK;
+}
+
+extern "C" int rg_set_response(rg_ctx *c, int n_chan, const int *rowptr, const int *col, const double *val,
+                               double exposure)
+{
+    if (!c || n_chan < 1 || !rowptr || !col || !val) return rg_set_error(RG_E_ARG, "rg_set_response: bad arguments");
+    if (c->ne <= 0) return rg_set_error(RG_E_GRID, "rg_set_response: set the instrument grid first (rg_set_instrument)");
+    if (!(exposure > 0)) return rg_set_error(RG_E_ARG, "rg_set_response: exposure must be positive");
+    for (int ch = 0; ch < n_chan; ch++) {
+        if (rowptr[ch + 1] < rowptr[ch]) return rg_set_error(RG_E_ARG, "rg_set_response: rowptr must not descend");
+        for (int k = rowptr[ch]; k < rowptr[ch + 1]; k++)
+            if (col[k] < 0 || col[k] >= c->ne) return rg_set_error(RG_E_ARG, "rg_set_response: column %d outside the instrument grid", col[k]);
+    }
+    // sliced ELL: 32 channels per slice, width = longest row of the slice, entries [k][lane] (coalesced per warp)
+    const int ns = (n_chan + 31) / 32;
+    std::vector<int> off(ns + 1, 0);
+    for (int s = 0; s < ns; s++) {
+        int w = 0;
+        for (int ch = 32 * s; ch < std::min(n_chan, 32 * s + 32); ch++) w = std::max(w, rowptr[ch + 1] - rowptr[ch]);
+        off[s + 1] = off[s] + 32 * w;
+    }
+    std::vector<int> ecol((size_t)std::max(off[ns], 1), -1);
+    std::vector<double> eval((size_t)std::max(off[ns], 1), 0.0);
+    for (int ch = 0; ch < n_chan; ch++) {
+        const int s = ch >> 5, lane = ch & 31;
+        for (int k = rowptr[ch]; k < rowptr[ch + 1]; k++) {
+            size_t q = (size_t)off[s] + (size_t)32 * (k - rowptr[ch]) + lane;
+            ecol[q] = col[k];
+            eval[q] = val[k];
+        }
+    }
+    RG_CUDA_OK(cudaSetDevice(c->device));
+    free_dev(c->d_sl_off); free_dev(c->d_ell_col); free_dev(c->d_ell_val);
+    c->d_sl_off = nullptr; c->d_ell_col = nullptr; c->d_ell_val = nullptr; c->n_chan = 0; c->have_data = false;
+    RG_CUDA_OK(cudaMalloc(&c->d_sl_off, off.size() * sizeof(int)));
+    RG_CUDA_OK(cudaMalloc(&c->d_ell_col, ecol.size() * sizeof(int)));
+    RG_CUDA_OK(cudaMalloc(&c->d_ell_val, eval.size() * sizeof(double)));
+    RG_CUDA_OK(cudaMemcpy(c->d_sl_off, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice));
+    RG_CUDA_OK(cudaMemcpy(c->d_ell_col, ecol.data(), ecol.size() * sizeof(int), cudaMemcpyHostToDevice));
+    RG_CUDA_OK(cudaMemcpy(c->d_ell_val, eval.data(), eval.size() * sizeof(double), cudaMemcpyHostToDevice));
+    c->n_chan = n_chan;
+    c->exposure = exposure;
+    return RG_OK;
+}
+
+extern "C" int rg_set_data(rg_ctx *c, const double *counts, const double *sigma, int kind)
+{
+    if (!c || !counts) return rg_set_error(RG_E_ARG, "rg_set_data: bad arguments");
+    if (c->n_chan <= 0) return rg_set_error(RG_E_ARG, "rg_set_data: set the response first (rg_set_response)");
+    if (kind != RG_FIT_CHI2 && kind != RG_FIT_CSTAT) return rg_set_error(RG_E_ARG, "rg_set_data: unknown statistic %d", kind);
+    if (kind == RG_FIT_CHI2) {
+        if (!sigma) return rg_set_error(RG_E_ARG, "rg_set_data: chi^2 needs the per-channel sigma");
+        for (int i = 0; i < c->n_chan; i++)
+            if (!(sigma[i] > 0)) return rg_set_error(RG_E_ARG, "rg_set_data: sigma must be positive (channel %d)", i);
+    }
+    RG_CUDA_OK(cudaSetDevice(c->device));
+    free_dev(c->d_counts); free_dev(c->d_sigma);
+    c->d_counts = nullptr; c->d_sigma = nullptr; c->have_data = false;
+    RG_CUDA_OK(cudaMalloc(&c->d_counts, (size_t)c->n_chan * sizeof(double)));
+    RG_CUDA_OK(cudaMemcpy(c->d_counts, counts, (size_t)c->n_chan * sizeof(double), cudaMemcpyHostToDevice));
+    if (sigma) {
+        RG_CUDA_OK(cudaMalloc(&c->d_sigma, (size_t)c->n_chan * sizeof(double)));
+        RG_CUDA_OK(cudaMemcpy(c->d_sigma, sigma, (size_t)c->n_chan * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    c->fit_kind = kind;
+    c->have_data = true;
+    return RG_OK;
+}
+
+static int observe_launch(rg_ctx *c, const double *d_lnu, const double *d_params, int P, int model, double *d_photar,
+                          double *d_stat, double *d_folded, cudaStream_t st)
+{
+    ObsArgs A;
+    memset(&A, 0, sizeof A);
+    A.lnu = d_lnu; A.params = d_params; A.P = P; A.model = model;
+    A.grid = c->gd; A.ebins = c->d_ebins; A.nE = c->nE;
+    A.ear = c->d_ear; A.ne = c->ne;
+    A.photar = d_photar;
+    if (d_stat) {
+        A.n_chan = c->n_chan; A.sl_off = c->d_sl_off; A.ell_col = c->d_ell_col; A.ell_val = c->d_ell_val;
+        A.exposure = c->exposure; A.counts = c->d_counts; A.sigma = c->d_sigma; A.kind = c->fit_kind;
+        A.folded = d_folded; A.stat = d_stat;
+    }
+    RG_TRY(prof_begin(c, 3, st));
+    RG_TRY(rg_launch_observe(A, c->sm_count, st));
+    RG_TRY(prof_end(c, 3, st));
+    c->launches++;
+    return RG_OK;
+}
+
+static int observe_check(rg_ctx *c, const void *a, const void *b, const void *o, int P, int model, bool need_fit,
+                         const char *who)
+{
+    if (!c || !a || !b || !o || P < 0) return rg_set_error(RG_E_ARG, "%s: bad arguments", who);
+    if (model != RG_MODEL_RELAGN && model != RG_MODEL_RELQSO) return rg_set_error(RG_E_ARG, "unknown model %d", model);
+    if (c->nE <= 0) return rg_set_error(RG_E_GRID, "no energy grid set (rg_set_grid)");
+    if (c->ne <= 0) return rg_set_error(RG_E_GRID, "%s: no instrument grid set (rg_set_instrument)", who);
+    if (need_fit && (c->n_chan <= 0 || !c->have_data))
+        return rg_set_error(RG_E_ARG, "%s: needs a response and a data set (rg_set_response, rg_set_data)", who);
+    return RG_OK;
+}
+
+extern "C" int rg_photar_batch(rg_ctx *c, const double *d_lnu, const double *d_params, int P, int model,
+                               double *d_photar, void *stream)
+{
+    RG_TRY(observe_check(c, d_lnu, d_params, d_photar, P, model, false, "rg_photar_batch"));
+    if (P == 0) return RG_OK;
+    RG_CUDA_OK(cudaSetDevice(c->device));
+    return observe_launch(c, d_lnu, d_params, P, model, d_photar, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int rg_fitstat_batch(rg_ctx *c, const double *d_lnu, const double *d_params, int P, int model,
+                                double *d_stat, double *d_folded, void *stream)
+{
+    RG_TRY(observe_check(c, d_lnu, d_params, d_stat, P, model, true, "rg_fitstat_batch"));
+    if (P == 0) return RG_OK;
+    RG_CUDA_OK(cudaSetDevice(c->device));
+    return observe_launch(c, d_lnu, d_params, P, model, nullptr, d_stat, d_folded, (cudaStream_t)stream);
+}
+
+extern "C" int rg_eval_fitstat_batch(rg_ctx *c, const double *d_params, int P, int model, double dr_dex, unsigned flags,
+                                     double *d_stat, double *d_attrs, void *stream)
+{
+    RG_TRY(observe_check(c, d_params, d_params, d_stat, P, model, true, "rg_eval_fitstat_batch"));
+    if (flags & RG_FLAG_COMPONENTS) return rg_set_error(RG_E_ARG, "rg_eval_fitstat_batch: the statistic uses the total SED only");
+    if (P == 0) return RG_OK;
+    RG_CUDA_OK(cudaSetDevice(c->device));
+    const int SLAB = 16384; // = the chunk of rg_eval_batch
+    RG_TRY(ensure_dev(&c->d_slab, &c->slab_n, (size_t)std::min(P, SLAB) * c->nE));
+    for (int p0 = 0; p0 < P; p0 += SLAB) {
+        const int n = std::min(SLAB, P - p0);
+        const double *par = d_params + (size_t)p0 * RG_NPAR;
+        RG_TRY(rg_eval_batch(c, par, n, model, dr_dex, flags, c->d_slab, d_attrs ? d_attrs + (size_t)p0 * RG_NATTR : nullptr,
+                             stream));
+        RG_TRY(observe_launch(c, c->d_slab, par, n, model, nullptr, d_stat + p0, nullptr, (cudaStream_t)stream));
+    }
+    return RG_OK;
+}
+
+extern "C" int rg_eval_fitstat_batch_host(rg_ctx *c, const double *params, int P, int model, double dr_dex,
+                                          unsigned flags, double *stat, double *attrs)
+{
+    if (!c || !params || !stat || P < 0) return rg_set_error(RG_E_ARG, "rg_eval_fitstat_batch_host: bad arguments");
+    if (P == 0) return RG_OK;
+    RG_CUDA_OK(cudaSetDevice(c->device));
+    RG_TRY(ensure_dev(&c->d_stage_par, &c->d_stage_par_n, (size_t)P * RG_NPAR));
+    RG_TRY(ensure_dev(&c->d_stage_stat, &c->d_stage_stat_n, (size_t)P));
+    if (attrs) RG_TRY(ensure_dev(&c->d_stage_attr, &c->d_stage_attr_n, (size_t)P * RG_NATTR));
+    RG_CUDA_OK(cudaMemcpyAsync(c->d_stage_par, params, (size_t)P * RG_NPAR * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    RG_TRY(rg_eval_fitstat_batch(c, c->d_stage_par, P, model, dr_dex, flags, c->d_stage_stat, attrs ? c->d_stage_attr : nullptr,
+                                 c->stream));
+    RG_CUDA_OK(cudaMemcpyAsync(stat, c->d_stage_stat, (size_t)P * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (attrs)
+        RG_CUDA_OK(cudaMemcpyAsync(attrs, c->d_stage_attr, (size_t)P * RG_NATTR * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    RG_CUDA_OK(cudaStreamSynchronize(c->stream));
     return RG_OK;
 }
 

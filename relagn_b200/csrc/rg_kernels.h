@@ -81,3 +81,31 @@ int rg_launch_raytrace(const double *h_spins, int n_spin, const double *h_thetas
                        double dl, float *d_data, long *n_unresolved, cudaStream_t st);
 
 int rg_fp64_peak(double *tflops, cudaStream_t st);
+
+// ---- observation epilogue (rg_observe.cu) ----
+struct ObsArgs {
+    const double *lnu;    // [P][nE] total SED, W/Hz
+    const double *params; // [P][RG_NPAR]
+    int P, model;
+    GridDesc grid;
+    const double *ebins;  // [nE+1] model bin edges (device)
+    int nE;
+    const double *ear;    // [ne+1] instrument bin edges, observer frame (device)
+    int ne;
+    double *photar;       // [P][ne] or null
+    // response in sliced ELL: slice s = channels 32 s .. 32 s + 31, entries sl_off[s] .. sl_off[s+1], laid out [k][lane];
+    // col < 0 marks padding
+    int n_chan;           // 0: rebin only
+    const int *sl_off;
+    const int *ell_col;
+    const double *ell_val;
+    double exposure;
+    const double *counts, *sigma;
+    int kind;
+    double *folded;       // [P][n_chan] or null
+    double *stat;         // [P]
+};
+size_t rg_observe_smem_bytes(int nE, int ne);
+int rg_launch_observe(const ObsArgs &A, int sm_count, cudaStream_t st);
+int rg_launch_convert(const double *d_lnu, const double *d_params, int P, int model, int ncomp, int unit, int as_flux,
+                      const GridDesc &g, double *d_out, int sm_count, cudaStream_t st);

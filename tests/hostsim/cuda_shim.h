@@ -152,6 +152,7 @@ static inline int atomicCAS(int *p, int c, int v) { int o = *p; if (o == c) *p =
 static inline double rsqrt(double x) { return 1.0 / sqrt(x); }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __dsub_rn(double a, double b) { return a - b; }
 static inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }
 static inline double __drcp_rn(double a) { return 1.0 / a; }
 static inline double __ddiv_rn(double a, double b) { return a / b; }

@@ -285,3 +285,113 @@ def test_fp32_mode_stated_bound(ctx, oracle, otab):
         for i in range(p.shape[0]):
             for c in range(4):
                 assert peak_relerr(out[i, c], ref[i, c], floor=1e-20) < 1e-5, (rel, i, c)
+
+
+def test_observation_epilogue(ctx, oracle, otab):
+    """SURVEY 8 f1/f2 on the device, through the C ABI with torch-owned buffers: unit conversion bit-identical to the
+    oracle (and <= 1e-14 from the unmodified reference's getters), XSPEC-contract photar bit-identical, folded counts
+    bit-identical, statistic 1e-12; parameters -> statistic in one call on a C4 batch, relativistic."""
+    import torch
+    from tests.util import toy_response
+    O = oracle
+    dn = np.load(os.path.join(GOLDEN, "golden_nonrel.npz"))
+    u = np.load(os.path.join(GOLDEN, "golden_units.npz"))
+    eb = dn["grid1000"]
+    ctx.set_grid(eb)
+    sel = [0, 6, 8, 15]
+    P = len(sel)
+    par = np.ascontiguousarray(dn["relagn_params"][sel])
+    L = np.ascontiguousarray(dn["relagn_spec1000"][sel][:, 3, :])
+    d_par = torch.from_numpy(par).cuda()
+    d_L = torch.from_numpy(L).cuda()
+    for unit in ["SI", "cgs", "cgs_wave", "SI_wave", "counts"]:
+        for fl in (False, True):
+            d_out = torch.empty_like(d_L)
+            ctx.convert_device(d_L.data_ptr(), d_par.data_ptr(), P, 1, unit, fl, d_out.data_ptr())
+            out = d_out.cpu().numpy()
+            for k in range(P):
+                assert np.array_equal(out[k], O.convert(L[k], eb, unit, fl, par[k, 1], par[k, 14])), (unit, fl, k)
+            assert peak_relerr(out[0], u["%s_%d" % (unit, fl)]) < 1e-14
+    for ear in (np.linspace(0.3, 10.0, 257), np.geomspace(5e-5, 3e3, 65), np.array([2e3, 3e3, 4e3]), eb[::7].copy(),
+                eb / 1.5):
+        ctx.set_instrument(ear)
+        d_ph = torch.empty((P, ear.size - 1), dtype=torch.float64, device="cuda")
+        ctx.photar_device(d_L.data_ptr(), d_par.data_ptr(), P, d_ph.data_ptr())
+        ph = d_ph.cpu().numpy()
+        for k in range(P):
+            assert np.array_equal(ph[k], O.photar(L[k], eb, par[k, 1], par[k, 14], ear)), k
+    ear = np.geomspace(0.3, 10.0, 201)
+    rp, cl, vl = toy_response(ear)
+    expo = 5e4
+    ctx.set_instrument(ear)
+    ctx.set_response(rp, cl, vl, expo)
+    pho = np.stack([O.photar(L[k], eb, par[k, 1], par[k, 14], ear) for k in range(P)])
+    _, folded0 = O.fold_stat(pho[0], rp, cl, vl, expo, np.zeros(rp.size - 1), None, 1)
+    data = np.random.Generator(np.random.PCG64(3)).poisson(np.maximum(folded0, 0)).astype(float)
+    sig = np.sqrt(np.maximum(data, 1.0))
+    for stat, kind in (("chi2", 0), ("cstat", 1)):
+        ctx.set_data(data, sig if kind == 0 else None, stat)
+        d_st = torch.empty(P, dtype=torch.float64, device="cuda")
+        d_fo = torch.empty((P, rp.size - 1), dtype=torch.float64, device="cuda")
+        ctx.fitstat_device(d_L.data_ptr(), d_par.data_ptr(), P, d_st.data_ptr(), d_fo.data_ptr())
+        st, fo = d_st.cpu().numpy(), d_fo.cpu().numpy()
+        for k in range(P):
+            s_ref, f_ref = O.fold_stat(pho[k], rp, cl, vl, expo, data, sig if kind == 0 else None, kind)
+            assert np.array_equal(fo[k], f_ref)
+            assert st[k] == pytest.approx(s_ref, rel=1e-12)
+    # parameters -> Cash statistic in one call (relativistic, C4 draws, two slabs' worth of chunking not needed here)
+    upload_golden_tables(ctx)
+    t = golden_tables()
+    p = c4_params(300)
+    p[:, 3] = np.clip(p[:, 3], t["spins"][0], t["spins"][-1])
+    p[:, 14] = np.linspace(0, 0.8, 300)  # redshifts
+    st = ctx.eval_fitstat_host(p, model=0, rel=True)
+    spec, at = ctx.eval_batch_host(p, model=0, rel=True)
+    for k in range(300):
+        s_ref, _ = O.fold_stat(O.photar(spec[k], eb, p[k, 1], p[k, 14], ear), rp, cl, vl, expo, data, None, 1)
+        assert st[k] == pytest.approx(s_ref, rel=1e-12), k
+    # ... and against the oracle's own spectra (tolerance of the spectrum path)
+    _, osp, _ = O.evaluate_batch(p[:40], eb, model=0, rel=True, tab=otab)
+    for k in range(40):
+        s_ref, _ = O.fold_stat(O.photar(osp[k, 3], eb, p[k, 1], p[k, 14], ear), rp, cl, vl, expo, data, None, 1)
+        assert st[k] == pytest.approx(s_ref, rel=1e-8), k
+
+
+def test_batch_evaluator_fitstat_api():
+    """The host-facing call of the fit / MCMC inner loop: BatchEvaluator.fitstat == evaluate + host epilogue."""
+    import torch
+    from relagn_b200.batch import BatchEvaluator
+    from oracle import oracle as O
+    from tests.util import toy_response
+    eb = np.geomspace(1e-4, 1e3, 1001)
+    t = golden_tables()
+    ev = BatchEvaluator(eb, model="relagn", tables=t)
+    ear = np.geomspace(0.3, 10.0, 201)
+    rp, cl, vl = toy_response(ear)
+    ev.set_instrument(ear, rp, cl, vl, exposure=2e4)
+    p = c4_params(20000, seed=5)  # more than one 16384-set slab
+    p[:, 3] = np.clip(p[:, 3], t["spins"][0], t["spins"][-1])
+    p[:, 14] = 0.1
+    spec, _ = ev.evaluate(p[:64], rel=True)
+    _, f0 = O.fold_stat(O.photar(spec[0], eb, p[0, 1], p[0, 14], ear), rp, cl, vl, 2e4, np.zeros(rp.size - 1), None, 1)
+    data = np.round(f0)
+    ev.set_data(data, np.sqrt(np.maximum(data, 1.0)), "chi2")
+    st = ev.fitstat(p, rel=True).copy()
+    assert st.shape == (20000,) and np.all(np.isfinite(st))
+    for k in range(64):
+        s_ref, _ = O.fold_stat(O.photar(spec[k], eb, p[k, 1], p[k, 14], ear), rp, cl, vl, 2e4, data,
+                               np.sqrt(np.maximum(data, 1.0)), 0)
+        assert st[k] == pytest.approx(s_ref, rel=1e-12)
+    assert np.argmin(st[:64]) == 0
+    # same set in different slabs / positions gives the same bits (batch-order independence)
+    q = np.concatenate([p[19990:], p[:10]])
+    st_q = ev.fitstat(q, rel=True)
+    assert np.array_equal(st_q[:10], st[19990:]) and np.array_equal(st_q[10:], st[:10])
+    # device-resident variant + in-place unit conversion of a spectra batch
+    d_p = torch.from_numpy(p[:64]).cuda()
+    d_st = ev.fitstat_device(d_p, rel=True)
+    assert np.array_equal(d_st.cpu().numpy(), st[:64])
+    d_spec, _ = ev.evaluate_device(d_p, rel=True)
+    ref = O.convert(d_spec[3].cpu().numpy(), eb, "counts", True, p[3, 1], p[3, 14])
+    ev.convert_device(d_spec, d_p, unit="counts", as_flux=True)
+    assert np.array_equal(d_spec[3].cpu().numpy(), ref)

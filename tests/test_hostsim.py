@@ -86,3 +86,104 @@ def test_class_api_units(ctx, monkeypatch):
     q = model.relqso()   # examples/relqso_modSpec.ipynb:81-83
     assert q.r_h == 14.261351436104999 and q.r_w == 28.522702872209997
     assert q.gamma_h == pytest.approx(1.9803689563797076, rel=1e-12)
+
+
+def test_observation_epilogue_vs_oracle(ctx):
+    """SURVEY 8 f1/f2 logic on the CPU-only box: unit conversion (relagn.py:487-564), the XSPEC-contract rebin
+    (relagn.f:98-112) and the folded fit statistic against oracle/observe_oracle.c; the conversion also against
+    the unmodified reference's getter outputs."""
+    from oracle import oracle as O
+    from tests.util import toy_response
+    dn = np.load(os.path.join(GOLDEN, "golden_nonrel.npz"))
+    u = np.load(os.path.join(GOLDEN, "golden_units.npz"))
+    eb = dn["grid1000"]
+    nE = eb.size - 1
+    ctx.set_grid(eb)
+    sel = [0, 6, 8, 15]  # default, z = 0.5, face-on, a C4 draw
+    P = len(sel)
+    par = np.ascontiguousarray(dn["relagn_params"][sel])
+    L = np.ascontiguousarray(dn["relagn_spec1000"][sel][:, 3, :])
+    # ---- f1: units x flux, bit-identical to the oracle; the default set against the reference's own getters ----
+    for unit in ["SI", "cgs", "cgs_wave", "SI_wave", "counts"]:
+        for fl in (False, True):
+            out = np.empty_like(L)
+            ctx.convert_device(L.ctypes.data, par.ctypes.data, P, 1, unit, fl, out.ctypes.data)
+            for k in range(P):
+                assert np.array_equal(out[k], O.convert(L[k], eb, unit, fl, par[k, 1], par[k, 14])), (unit, fl, k)
+            assert peak_relerr(out[0], u["%s_%d" % (unit, fl)]) < 1e-14
+    # components layout [P][4][nE], in place
+    L4 = np.ascontiguousarray(dn["relagn_spec1000"][sel])
+    buf = L4.copy()
+    ctx.convert_device(buf.ctypes.data, par.ctypes.data, P, 4, "counts", True, buf.ctypes.data)
+    assert np.array_equal(buf[1, 0], O.convert(L4[1, 0], eb, "counts", True, par[1, 1], par[1, 14]))
+    assert peak_relerr(buf[1, 3], u["z05_counts_1"]) < 1e-14
+
+    # ---- f1: rebin onto instrument grids ----
+    grids = [np.linspace(0.3, 10.0, 257),                 # linear channels inside the model grid
+             np.geomspace(5e-5, 3e3, 65),                 # wider than the model grid on both sides: edge bins clipped
+             np.array([2e3, 3e3, 4e3]),                   # entirely outside: zeros
+             eb[::7].copy()]                              # every 7th model edge: whole-bin sums (z = 0 sets)
+    for ear in grids:
+        ctx.set_instrument(ear)
+        ph = np.empty((P, ear.size - 1))
+        ctx.photar_device(L.ctypes.data, par.ctypes.data, P, ph.ctypes.data)
+        for k in range(P):
+            assert np.array_equal(ph[k], O.photar(L[k], eb, par[k, 1], par[k, 14], ear)), k
+    assert np.all(ph[[0, 2, 3]] > 0)
+    cnt = np.stack([O.convert(L[k], eb, "counts", True, par[k, 1], par[k, 14]) for k in range(P)]) * np.diff(eb)
+    k0 = 0  # z = 0: grid of every 7th edge -> sums of 7 model bins
+    ref = np.add.reduceat(cnt[k0][:(nE // 7) * 7], np.arange(0, (nE // 7) * 7, 7))
+    assert np.allclose(ph[k0][:nE // 7], ref, rtol=1e-13, atol=0)
+    ctx.set_instrument(np.array([2e3, 3e3, 4e3]))
+    z = np.empty((P, 2))
+    ctx.photar_device(L.ctypes.data, par.ctypes.data, P, z.ctypes.data)
+    assert np.all(z == 0)
+    # identity: the observer-frame image of the model grid returns the per-bin photons exactly (z = 0.5 set)
+    k = 1
+    ear = eb / (1 + par[k, 14])
+    ctx.set_instrument(ear)
+    idn = np.empty((P, nE))
+    ctx.photar_device(L.ctypes.data, par.ctypes.data, P, idn.ctypes.data)
+    assert np.array_equal(idn[k], cnt[k])
+    # photon conservation on a coarse grid spanning the whole (redshifted) model grid
+    ear = np.geomspace(eb[0] / 1.5, eb[-1], 40)
+    ear[0], ear[-1] = eb[0] / 1.5, eb[-1]
+    ctx.set_instrument(ear)
+    co = np.empty((P, 39))
+    ctx.photar_device(L.ctypes.data, par.ctypes.data, P, co.ctypes.data)
+    assert co[k].sum() == pytest.approx(cnt[k].sum(), rel=1e-13)
+
+    # ---- f2: response fold + statistic ----
+    ear = np.geomspace(0.3, 10.0, 201)
+    rp, cl, vl = toy_response(ear)
+    expo = 5e4
+    ctx.set_instrument(ear)
+    ctx.set_response(rp, cl, vl, expo)
+    pho = np.stack([O.photar(L[k], eb, par[k, 1], par[k, 14], ear) for k in range(P)])
+    _, folded0 = O.fold_stat(pho[0], rp, cl, vl, expo, np.zeros(rp.size - 1), None, 1)
+    rng = np.random.Generator(np.random.PCG64(3))
+    data = rng.poisson(np.maximum(folded0, 0)).astype(float)
+    sig = np.sqrt(np.maximum(data, 1.0))
+    for stat, kind in (("chi2", 0), ("cstat", 1)):
+        ctx.set_data(data, sig if kind == 0 else None, stat)
+        st = np.empty(P)
+        fo = np.empty((P, rp.size - 1))
+        ctx.fitstat_device(L.ctypes.data, par.ctypes.data, P, st.ctypes.data, fo.ctypes.data)
+        for k in range(P):
+            s_ref, f_ref = O.fold_stat(pho[k], rp, cl, vl, expo, data, sig if kind == 0 else None, kind)
+            assert np.array_equal(fo[k], f_ref)
+            assert st[k] == pytest.approx(s_ref, rel=1e-12)
+        assert st[0] < st[2]  # the data were drawn from set 0
+    # parameters -> statistic in one call equals evaluate + epilogue
+    st2 = ctx.eval_fitstat_host(par, model=0, rel=False)
+    spec, _ = ctx.eval_batch_host(par, model=0, rel=False)
+    for k in range(P):
+        s_ref, _ = O.fold_stat(O.photar(spec[k], eb, par[k, 1], par[k, 14], ear), rp, cl, vl, expo, data, None, 1)
+        assert st2[k] == pytest.approx(s_ref, rel=1e-12)
+    # error behaviour
+    with pytest.raises(Exception):
+        ctx.set_data(data[:-1], None, "cstat")
+    with pytest.raises(Exception):
+        ctx.set_instrument(np.array([1.0, 0.5, 2.0]))
+    with pytest.raises(Exception):
+        ctx.set_response(rp, cl + 1000, vl, expo)

@@ -64,3 +64,26 @@ def c3_params(n=100):
     p[:, 5] = 1.0
     p[:, 6] = 0.0
     return p
+
+
+def toy_response(ear, n_chan=96, seed=7):
+    """A small instrument for the observation-epilogue tests: Gaussian redistribution (sigma ~ 2.5 instrument bins,
+    cut at 4 sigma) times a smooth effective area, CSR over channels; ragged rows incl. one empty channel."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    ne = len(ear) - 1
+    ec = 0.5 * (np.asarray(ear)[1:] + np.asarray(ear)[:-1])
+    centre = np.linspace(0, ne - 1, n_chan)
+    rowptr, col, val = [0], [], []
+    for c in range(n_chan):
+        if c == 5:
+            rowptr.append(len(col))  # a dead channel
+            continue
+        sig = 1.5 + 2.0 * rng.random()
+        lo, hi = int(max(0, np.floor(centre[c] - 4 * sig))), int(min(ne - 1, np.ceil(centre[c] + 4 * sig)))
+        for i in range(lo, hi + 1):
+            w = np.exp(-0.5 * ((i - centre[c]) / sig) ** 2) / (sig * np.sqrt(2 * np.pi))
+            area = 400.0 * np.exp(-0.5 * (np.log(ec[i] / 1.5) / 1.2) ** 2)
+            col.append(i)
+            val.append(w * area)
+        rowptr.append(len(col))
+    return np.array(rowptr, dtype=np.int32), np.array(col, dtype=np.int32), np.array(val)
