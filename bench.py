@@ -58,6 +58,23 @@ def c4_params(P, seed):
     return np.ascontiguousarray(p)
 
 
+def synth_instrument(ne=1024, n_chan=1024):
+    """Synthetic CCD-like instrument for the fit-statistic block: `ne` log-spaced bins over 0.3-10 keV, Gaussian
+    redistribution (sigma 2 bins, cut at 4 sigma: 17 entries per channel) times a smooth effective area; CSR."""
+    ear = np.geomspace(0.3, 10.0, ne + 1)
+    ec = 0.5 * (ear[1:] + ear[:-1])
+    area = 400.0 * np.exp(-0.5 * (np.log(ec / 1.5) / 1.2) ** 2)
+    centre = np.linspace(0, ne - 1, n_chan)
+    off = np.arange(-8, 9)
+    idx = np.rint(centre)[:, None].astype(int) + off[None, :]
+    ok = (idx >= 0) & (idx < ne)
+    w = np.exp(-0.5 * ((idx - centre[:, None]) / 2.0) ** 2) / (2.0 * np.sqrt(2 * np.pi))
+    rowptr = np.concatenate([[0], np.cumsum(ok.sum(axis=1))]).astype(np.int32)
+    col = idx[ok].astype(np.int32)
+    val = (w * area[np.clip(idx, 0, ne - 1)])[ok]
+    return ear, rowptr, col, val
+
+
 def workload_config(n_gpus, sets_per_gpu, tables):
     return {"workload": "C4: RELAGN full model, random spin/inclination/corona parameters (lmod_relagn.dat limits), "
                         "rel=True, total SED; %d sets per GPU per step (1e6-set MCMC batch sharded over 8 GPUs)"
@@ -291,6 +308,45 @@ def run_ours(args):
            "d2h_bytes_per_step": int(P * NE * 8 + P * 24 * 8), "steps": e2e_steps,
            "api": "relagn_b200.BatchEvaluator.evaluate (rg_eval_batch_host; pinned host in/out)"}
 
+    # ---- fit-statistic mode: parameters -> Cash statistic, the spectra never leave the GPU ----
+    fit = None
+    if not args.no_fit:
+        from relagn_b200.batch import fitstat_sharded
+        ear, rp, cl, vl = synth_instrument()
+        ev.set_instrument(ear, rp, cl, vl, exposure=5e4)
+        d_fold = torch.empty((1, rp.size - 1), dtype=torch.float64, device=dev)
+        d_s1 = torch.empty(1, dtype=torch.float64, device=dev)
+        ev.ctx.set_data(np.ones(rp.size - 1), None, "cstat")
+        ev.ctx.fitstat_device(out.data_ptr(), params.data_ptr(), 1, d_s1.data_ptr(), d_fold.data_ptr())
+        ev.set_data(np.round(d_fold.cpu().numpy()[0]), None, "cstat")  # "observed" counts: the model of set 0
+        d_stat = torch.empty(P, dtype=torch.float64, device=dev)
+        fitstat_sharded(ev, params, rel=True)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(e2e_steps):
+            fitstat_sharded(ev, params, rel=True)
+        f1.record()
+        barrier()
+        tf = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device=dev)
+        ev.fitstat(params_np, rel=True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            st_host = ev.fitstat(params_np, rel=True)
+            chk_fit = float(st_host[0])
+        dtf = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+            dist.all_reduce(dtf, op=dist.ReduceOp.MAX)
+        fit = {"what": "parameters -> Cash statistic on the device (rebin to 1024 instrument bins, 1024-channel "
+                       "response, rg_eval_fitstat_batch); one double per set leaves the GPU",
+               "value": P * world * e2e_steps / (float(tf.item()) * 1e-3), "unit": UNIT,
+               "e2e": {"value": P * world * e2e_steps / float(dtf.item()), "unit": UNIT,
+                       "h2d_bytes_per_step": int(P * 15 * 8), "d2h_bytes_per_step": int(P * 8),
+                       "api": "relagn_b200.BatchEvaluator.fitstat (rg_eval_fitstat_batch_host)"},
+               "stat_of_set0": chk_fit}
+
     # ---- roofline of the dominant kernel (spectrum_kernel), measured live with CUDA events ----
     roofline, fp64, kernels = None, None, None
     if rank == 0:
@@ -343,6 +399,32 @@ def run_ours(args):
                 "peak_source": "rg_measure_fp64_peak (FMA micro-benchmark, this run)",
                 "flops_alg_per_spectrum": flops / P, "mean_W_ann": sum_W / max(s["n_conv_ann"], 1.0),
                 "mean_annuli": float((Nd + Nw + Nh) / max(ok.sum(), 1)), "mean_jmax": sum_j / max(n_sys, 1.0)}
+        # HBM-bound epilogue kernels, timed alone on the resident spectra of this step
+        if fit is not None:
+            hbm_burst = float(peaks.get("hbm_gbs_burst", peaks.get("hbm_gbs", 6650.0)))
+            ev.ctx.set_profile(True)
+            ev.ctx.reset_stats()
+            for _ in range(5):
+                ev.ctx.fitstat_device(out.data_ptr(), params.data_ptr(), P, d_stat.data_ptr())
+            torch.cuda.synchronize()
+            ms_obs = ev.ctx.stats()["ms_observe"] / 5
+            ev.ctx.reset_stats()
+            scratch = torch.empty_like(out)
+            for _ in range(5):
+                ev.ctx.convert_device(out.data_ptr(), params.data_ptr(), P, 1, "counts", True, scratch.data_ptr())
+            torch.cuda.synchronize()
+            ms_cv = ev.ctx.stats()["ms_observe"] / 5
+            del scratch
+            ev.ctx.set_profile(False)
+            b_obs, b_cv = P * (8.0 * NE + 8.0 * 15 + 8.0), P * (16.0 * NE + 8.0 * 15)
+            fit["roofline"] = {
+                "observe_kernel": {"bound": "hbm", "achieved": b_obs / (ms_obs * 1e-3) / 1e9, "peak": hbm_burst,
+                                   "unit": "GB/s", "frac": b_obs / (ms_obs * 1e-3) / 1e9 / hbm_burst,
+                                   "ms": ms_obs, "bytes_per_launch": b_obs},
+                "convert_kernel": {"bound": "hbm", "achieved": b_cv / (ms_cv * 1e-3) / 1e9, "peak": hbm_burst,
+                                   "unit": "GB/s", "frac": b_cv / (ms_cv * 1e-3) / 1e9 / hbm_burst,
+                                   "ms": ms_cv, "bytes_per_launch": b_cv},
+                "peak_source": "MEASURED_PEAKS.json (burst figure: kernels timed alone)"}
         tot_ms = s["ms_setup"] + s["ms_nthcomp"] + s["ms_spectrum"]
         kernels = {"setup_kernel_ms": s["ms_setup"], "nthcomp_kernel_ms": s["ms_nthcomp"],
                    "spectrum_kernel_ms": s["ms_spectrum"], "spectrum_share": s["ms_spectrum"] / tot_ms if tot_ms else None}
@@ -363,7 +445,7 @@ def run_ours(args):
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32 (spectra/transfer) + f64 (setup, nthcomp, histograms)" if args.fp32 else "f64", "data": "synthetic",
                 "config": workload_config(world, P, args.tables), "clocks": clocks, "e2e": e2e,
                 "gpu_launches": int(launches), "roofline": roofline, "fp64_roofline": fp64, "kernels": kernels,
-                "cpu_baseline": cpu, "checksum": chk}
+                "cpu_baseline": cpu, "fit_statistic": fit, "checksum": chk}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -381,6 +463,7 @@ def main():
     ap.add_argument("--tables", default="default", choices=["default", "golden"])
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU work per cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-fit", action="store_true", help="skip the fit-statistic (SURVEY 8 f2) block")
     ap.add_argument("--fp32", action="store_true", help="RG_FLAG_FP32 mode (stated bound 1e-5 within 20 decades of the peak)")
     args = ap.parse_args()
     if args.impl == "reference":

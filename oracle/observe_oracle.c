@@ -55,16 +55,18 @@ void ro_photar(const double *L, int nE, const double *ebins, double dist_mpc, do
                double *photar)
 {
     double d = dist_mpc * K_MPC_CM;
-    double den = 4 * K_PI * (d * d) * (1 + z);
+    double inv_den = 1.0 / (4 * K_PI * (d * d) * (1 + z));
     double zf = 1 + z;
-    /* photons/cm^2/s per model bin: counts flux (relagn.py:509-516, 561) times the bin width */
+    /* photons/cm^2/s per model bin: counts flux (relagn.py:509-516, 561) times the bin width, grouped as
+     * L * [dE / (h E)] * [1 / (4 pi d^2 (1 + z))] (the device keeps the first bracket per bin, the second per set;
+     * <= 2 ulp from the reference's left-to-right order, checked against ro_convert in tests/test_oracle.py) */
     /* (variable-length arrays keep the oracle allocation-free; nE is at most a few thousand) */
     double ph[nE > 0 ? nE : 1], x[nE + 1];
     for (int j = 0; j <= nE; j++) x[j] = ebins[j] / zf;
     for (int j = 0; j < nE; j++) {
         double dE = ebins[j + 1] - ebins[j];
         double E = ebins[j] + dE / 2;
-        ph[j] = (((L[j] / K_H) / E) / den) * dE;
+        ph[j] = (L[j] * (dE / (K_H * E))) * inv_den;
     }
     for (int i = 0; i < ne; i++) {
         double lo = ear[i], hi = ear[i + 1];
@@ -100,7 +102,7 @@ double ro_fold_stat(const double *photar, int n_chan, const int *rowptr, const i
         if (folded) folded[c] = m;
         double D = counts[c];
         if (kind == 0) {
-            double t = (D - m) / sigma[c];
+            double t = (D - m) * (1.0 / sigma[c]);
             stat = stat + t * t;
         } else {
             double mm = m < 1e-300 ? 1e-300 : m;

@@ -81,7 +81,10 @@ struct rg_ctx {
     double n_sets = 0;
     // observation epilogue: model edges, instrument grid, response (sliced ELL), data, spectra slab
     double *d_ebins = nullptr;
-    double *d_ear = nullptr;
+    const double *d_kph = nullptr; // inside d_grid
+    double *d_ear = nullptr, *d_pos0 = nullptr;
+    std::vector<double> h_ear;
+    bool pos0_dirty = true;
     int ne = 0;
     int n_chan = 0, fit_kind = RG_FIT_CHI2;
     bool have_data = false;
@@ -148,7 +151,7 @@ extern "C" void rg_ctx_destroy(rg_ctx *c)
     free_dev(c->d_rq); free_dev(c->d_queue); free_dev(c->d_partial); free_dev(c->d_kyH); free_dev(c->d_kyin); free_dev(c->d_kyout);
     free_dev(c->d_stage_par); free_dev(c->d_stage_out); free_dev(c->d_stage_attr); free_dev(c->d_stats);
     free_dev(c->d_ebins); free_dev(c->d_ear); free_dev(c->d_sl_off); free_dev(c->d_ell_col); free_dev(c->d_ell_val);
-    free_dev(c->d_counts); free_dev(c->d_sigma); free_dev(c->d_slab); free_dev(c->d_stage_stat);
+    free_dev(c->d_counts); free_dev(c->d_sigma); free_dev(c->d_slab); free_dev(c->d_stage_stat); free_dev(c->d_pos0);
     prof_collect(c);
     if (c->h_counter) cudaFreeHost(c->h_counter);
     if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -256,11 +259,11 @@ extern "C" int rg_set_grid(rg_ctx *c, const double *eb, int nE)
     for (int j = 0; j < nE; j++)
         if (!(eb[j + 1] > eb[j]) || !(eb[j] > 0)) return rg_set_error(RG_E_ARG, "bin edges must be positive and ascending");
     RG_CUDA_OK(cudaSetDevice(c->device));
-    const int NA = 9; // arrays of nE
+    const int NA = 10; // arrays of nE
     std::vector<double> h((size_t)NA * nE + 3 * RG_NEXT, 0.0);
     double *Egrid = &h[0], *dE = &h[(size_t)nE], *nu = &h[(size_t)2 * nE], *hnu = &h[(size_t)3 * nE],
            *bbpre = &h[(size_t)4 * nE], *wt = &h[(size_t)5 * nE], *e511 = &h[(size_t)6 * nE], *ear2 = &h[(size_t)7 * nE],
-           *lgE = &h[(size_t)8 * nE];
+           *lgE = &h[(size_t)8 * nE], *kph = &h[(size_t)9 * nE];
     double *x_hnu = &h[(size_t)NA * nE], *x_bbpre = x_hnu + RG_NEXT, *x_wt = x_bbpre + RG_NEXT;
     for (int j = 0; j < nE; j++) {
         dE[j] = eb[j + 1] - eb[j];
@@ -271,6 +274,7 @@ extern "C" int rg_set_grid(rg_ctx *c, const double *eb, int nE)
         e511[j] = Egrid[j] / 511.0;
         ear2[j] = Egrid[j] * Egrid[j];
         lgE[j] = log10(Egrid[j]);
+        kph[j] = dE[j] / (RGK_H * Egrid[j]); // W/Hz -> photons/s per bin (relagn.py:509-516 times dE)
     }
     int n_ext = Egrid[0] < 1e-4 ? RG_NEXT : 0; // relagn.py:868
     std::vector<double> xs; // abscissae of np.trapz: [extension, nu]
@@ -310,6 +314,8 @@ extern "C" int rg_set_grid(rg_ctx *c, const double *eb, int nE)
     g.Egrid = d; g.dE = d + (size_t)nE; g.nu = d + (size_t)2 * nE; g.hnu = d + (size_t)3 * nE;
     g.bbpre = d + (size_t)4 * nE; g.wt = d + (size_t)5 * nE; g.e511 = d + (size_t)6 * nE; g.ear2 = d + (size_t)7 * nE;
     g.lgE = d + (size_t)8 * nE;
+    c->d_kph = d + (size_t)9 * nE;
+    c->pos0_dirty = true;
     g.x_hnu = d + (size_t)NA * nE; g.x_bbpre = g.x_hnu + RG_NEXT; g.x_wt = g.x_bbpre + RG_NEXT;
     g.n_ext = n_ext; g.nE = nE; g.geometric = geometric; g.dlnE = dlnE;
     c->nE = nE;
@@ -749,6 +755,8 @@ extern "C" int rg_set_instrument(rg_ctx *c, const double *ear, int ne)
     RG_CUDA_OK(cudaMalloc(&c->d_ear, (size_t)(ne + 1) * sizeof(double)));
     RG_CUDA_OK(cudaMemcpy(c->d_ear, ear, (size_t)(ne + 1) * sizeof(double), cudaMemcpyHostToDevice));
     c->ne = ne;
+    c->h_ear.assign(ear, ear + ne + 1);
+    c->pos0_dirty = true;
     // a response / data set belongs to one instrument grid
     c->n_chan = 0; c->have_data = false;
     return RG_OK;
@@ -773,7 +781,7 @@ extern "C" int rg_set_response(rg_ctx *c, int n_chan, const int *rowptr, const i
         for (int ch = 32 * s; ch < std::min(n_chan, 32 * s + 32); ch++) w = std::max(w, rowptr[ch + 1] - rowptr[ch]);
         off[s + 1] = off[s] + 32 * w;
     }
-    std::vector<int> ecol((size_t)std::max(off[ns], 1), -1);
+    std::vector<int> ecol((size_t)std::max(off[ns], 1), 0); // padding: (column 0, value 0) adds +0
     std::vector<double> eval((size_t)std::max(off[ns], 1), 0.0);
     for (int ch = 0; ch < n_chan; ch++) {
         const int s = ch >> 5, lane = ch & 31;
@@ -812,10 +820,11 @@ extern "C" int rg_set_data(rg_ctx *c, const double *counts, const double *sigma,
     c->d_counts = nullptr; c->d_sigma = nullptr; c->have_data = false;
     RG_CUDA_OK(cudaMalloc(&c->d_counts, (size_t)c->n_chan * sizeof(double)));
     RG_CUDA_OK(cudaMemcpy(c->d_counts, counts, (size_t)c->n_chan * sizeof(double), cudaMemcpyHostToDevice));
-    if (sigma) {
-        RG_CUDA_OK(cudaMalloc(&c->d_sigma, (size_t)c->n_chan * sizeof(double)));
-        RG_CUDA_OK(cudaMemcpy(c->d_sigma, sigma, (size_t)c->n_chan * sizeof(double), cudaMemcpyHostToDevice));
-    }
+    // per-channel constant of the statistic: 1 / sigma_c (chi^2) or ln D_c (Cash)
+    std::vector<double> aux((size_t)c->n_chan, 0.0);
+    for (int i = 0; i < c->n_chan; i++) aux[i] = kind == RG_FIT_CHI2 ? 1.0 / sigma[i] : (counts[i] > 0 ? log(counts[i]) : 0.0);
+    RG_CUDA_OK(cudaMalloc(&c->d_sigma, (size_t)c->n_chan * sizeof(double)));
+    RG_CUDA_OK(cudaMemcpy(c->d_sigma, aux.data(), (size_t)c->n_chan * sizeof(double), cudaMemcpyHostToDevice));
     c->fit_kind = kind;
     c->have_data = true;
     return RG_OK;
@@ -827,8 +836,21 @@ static int observe_launch(rg_ctx *c, const double *d_lnu, const double *d_params
     ObsArgs A;
     memset(&A, 0, sizeof A);
     A.lnu = d_lnu; A.params = d_params; A.P = P; A.model = model;
-    A.grid = c->gd; A.ebins = c->d_ebins; A.nE = c->nE;
+    if (c->pos0_dirty) { // position of every instrument edge on the (geometric) model grid at z = 0
+        free_dev(c->d_pos0);
+        c->d_pos0 = nullptr;
+        if (c->gd.geometric) {
+            std::vector<double> pos((size_t)c->ne);
+            for (int i = 0; i < c->ne; i++) pos[i] = c->h_ear[i] > 0 ? log(c->h_ear[i] / c->h_ebins[0]) / c->gd.dlnE : -1e9;
+            RG_CUDA_OK(cudaMalloc(&c->d_pos0, pos.size() * sizeof(double)));
+            RG_CUDA_OK(cudaMemcpyAsync(c->d_pos0, pos.data(), pos.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+            RG_CUDA_OK(cudaStreamSynchronize(st)); // pos is a local
+        }
+        c->pos0_dirty = false;
+    }
+    A.grid = c->gd; A.ebins = c->d_ebins; A.nE = c->nE; A.kph = c->d_kph;
     A.ear = c->d_ear; A.ne = c->ne;
+    A.pos0 = c->d_pos0; A.inv_dlnE = c->gd.geometric ? 1.0 / c->gd.dlnE : 0.0;
     A.photar = d_photar;
     if (d_stat) {
         A.n_chan = c->n_chan; A.sl_off = c->d_sl_off; A.ell_col = c->d_ell_col; A.ell_val = c->d_ell_val;

@@ -90,8 +90,11 @@ struct ObsArgs {
     GridDesc grid;
     const double *ebins;  // [nE+1] model bin edges (device)
     int nE;
+    const double *kph;    // [nE] dE / (h E): W/Hz -> photons/s per model bin (rg_set_grid)
     const double *ear;    // [ne+1] instrument bin edges, observer frame (device)
     int ne;
+    const double *pos0;   // [ne] ln(ear_i / ebins_0) / dlnE when the model grid is geometric, else null
+    double inv_dlnE;
     double *photar;       // [P][ne] or null
     // response in sliced ELL: slice s = channels 32 s .. 32 s + 31, entries sl_off[s] .. sl_off[s+1], laid out [k][lane];
     // col < 0 marks padding
@@ -100,7 +103,7 @@ struct ObsArgs {
     const int *ell_col;
     const double *ell_val;
     double exposure;
-    const double *counts, *sigma;
+    const double *counts, *sigma; // sigma: 1 / sigma_c (chi^2) or ln D_c (Cash; 0 where D_c = 0)
     int kind;
     double *folded;       // [P][n_chan] or null
     double *stat;         // [P]

@@ -48,11 +48,24 @@ __global__ void __launch_bounds__(256) convert_kernel(const double *__restrict__
         }
         const double *src = lnu + row * nE;
         double *dst = out + row * nE;
+        if ((nE & 1) == 0 && (((uintptr_t)lnu | (uintptr_t)out) & 15) == 0) { // 16-byte accesses (rows stay aligned)
+            const double2 *src2 = reinterpret_cast<const double2 *>(src);
+            double2 *dst2 = reinterpret_cast<double2 *>(dst);
 #pragma unroll 4
-        for (int j = lane; j < nE; j += 32) {
-            double v = convert_bin<UNIT>(RG_LDCS(src + j), g, j);
-            if (FLUX) v = __ddiv_rn(v, den);
-            RG_STCS(dst + j, v);
+            for (int j = lane; j < (nE >> 1); j += 32) {
+                double2 v = RG_LDCS(src2 + j);
+                v.x = convert_bin<UNIT>(v.x, g, 2 * j);
+                v.y = convert_bin<UNIT>(v.y, g, 2 * j + 1);
+                if (FLUX) { v.x = __ddiv_rn(v.x, den); v.y = __ddiv_rn(v.y, den); }
+                RG_STCS(dst2 + j, v);
+            }
+        } else {
+#pragma unroll 4
+            for (int j = lane; j < nE; j += 32) {
+                double v = convert_bin<UNIT>(RG_LDCS(src + j), g, j);
+                if (FLUX) v = __ddiv_rn(v, den);
+                RG_STCS(dst + j, v);
+            }
         }
     }
 }
@@ -63,7 +76,7 @@ static int launch_convert_u(const double *d_lnu, const double *d_params, int P, 
 {
     const long rows = (long)P * ncomp;
     long blocks = (rows + 7) / 8; // 8 warps per CTA
-    const long cap = (long)sm_count * 8;
+    const long cap = (long)sm_count * 16;
     if (blocks > cap) blocks = cap;
     if (as_flux)
         RG_LAUNCH((convert_kernel<UNIT, true>), dim3((unsigned)blocks), dim3(256), 0, st, d_lnu, d_params, rows, ncomp, model, g, d_out);
@@ -102,29 +115,37 @@ __global__ void __launch_bounds__(OBS_THREADS) observe_kernel(ObsArgs A)
     const int nE = A.nE, ne = A.ne;
     for (int set = blockIdx.x; set < A.P; set += gridDim.x) {
         const double *p = A.params + (size_t)set * RG_NPAR;
-        const double d = __dmul_rn(p[1], RGK_MPC_CM);
-        const double zf = 1 + p[par_slot_z(A.model)];
-        const double den = __dmul_rn(__dmul_rn(4 * RGK_PI, __dmul_rn(d, d)), zf);
+        const double d = __dmul_rn(__ldg(p + 1), RGK_MPC_CM);
+        const double zf = 1 + __ldg(p + par_slot_z(A.model));
+        const double inv_den = __ddiv_rn(1.0, __dmul_rn(__dmul_rn(4 * RGK_PI, __dmul_rn(d, d)), zf));
         const double *L = A.lnu + (size_t)set * nE;
-        // ---- photons per model bin, observer-frame edges (relagn.f:98-102; relagn.py:509-516, 561) ----
+        // ---- observer-frame edges (relagn.f:98-102) and photons per model bin: counts flux (relagn.py:509-516, 561)
+        //      times the bin width, as L * [dE / (h E)] * [1 / (4 pi d^2 (1 + z))] ----
         for (int j = tid; j <= nE; j += nthr) x[j] = __ddiv_rn(__ldg(A.ebins + j), zf);
-        for (int j = tid; j < nE; j += nthr) {
-            double v = __ddiv_rn(__ddiv_rn(__ddiv_rn(RG_LDCS(L + j), RGK_H), __ldg(A.grid.Egrid + j)), den);
-            ph[j] = __dmul_rn(v, __ldg(A.grid.dE + j));
-        }
+        for (int j = tid; j < nE; j += nthr) ph[j] = __dmul_rn(__dmul_rn(RG_LDCS(L + j), __ldg(A.kph + j)), inv_den);
         __syncthreads();
         // ---- rebin onto the instrument grid (inibin / erebin): fractional overlap, fixed summation order ----
+        const double zshift = A.pos0 ? log(zf) * A.inv_dlnE : 0.0;
         for (int i = tid; i < ne; i += nthr) {
             const double lo = __ldg(A.ear + i), hi = __ldg(A.ear + i + 1);
             double acc = 0.0;
             if (hi > x[0] && lo < x[nE] && hi > lo) {
-                // js: first model bin with x[js+1] > lo;  je: last model bin with x[je] < hi
-                int a = 0, b = nE - 1;
-                while (a < b) { int m = (a + b) >> 1; if (x[m + 1] > lo) b = m; else a = m + 1; }
-                const int js = a;
-                a = js; b = nE - 1;
-                while (a < b) { int m = (a + b + 1) >> 1; if (x[m] < hi) a = m; else b = m - 1; }
-                const int je = a;
+                // js: first model bin with x[js+1] > lo.  Geometric model grid: start from the analytic position
+                // (edge position at z = 0, precomputed per instrument edge, plus the redshift); else bisect.
+                int js;
+                if (A.pos0) {
+                    const double q = floor(__ldg(A.pos0 + i) + zshift);
+                    js = q < 0 ? 0 : (q > nE - 1 ? nE - 1 : (int)q);
+                } else {
+                    int a = 0, b = nE - 1;
+                    while (a < b) { int m = (a + b) >> 1; if (x[m + 1] > lo) b = m; else a = m + 1; }
+                    js = a;
+                }
+                while (js < nE - 1 && x[js + 1] <= lo) js++;
+                while (js > 0 && x[js] > lo) js--;
+                // je: last model bin with x[je] < hi
+                int je = js;
+                while (je + 1 < nE && x[je + 1] < hi) je++;
                 if (js == je) {
                     double l = lo > x[js] ? lo : x[js], r = hi < x[js + 1] ? hi : x[js + 1];
                     acc = __dmul_rn(ph[js], __ddiv_rn(__dsub_rn(r, l), __dsub_rn(x[js + 1], x[js])));
@@ -141,27 +162,27 @@ __global__ void __launch_bounds__(OBS_THREADS) observe_kernel(ObsArgs A)
         }
         if (A.n_chan == 0) { __syncthreads(); continue; } // photar only
         __syncthreads();
-        // ---- fold through the response (sliced ELL: slice = 32 channels, entries [k][lane]) + statistic ----
+        // ---- fold through the response (sliced ELL: slice = 32 channels, entries [k][lane]; padding entries are
+        //      (column 0, value 0) and add +0) + statistic ----
         double part = 0.0;
         for (int c = tid; c < ((A.n_chan + 31) & ~31); c += nthr) {
             const int s = c >> 5, lane = c & 31;
             const int off = __ldg(A.sl_off + s), w = __ldg(A.sl_off + s + 1) - off;
+            const int *cp = A.ell_col + off + lane;
+            const double *vp = A.ell_val + off + lane;
             double m = 0.0;
-            for (int k = 0; k < w; k += 32) {
-                const int q = off + k + lane;
-                const int cl = __ldg(A.ell_col + q);
-                if (cl >= 0) m = __dadd_rn(m, __dmul_rn(__ldg(A.ell_val + q), pa[cl]));
-            }
+#pragma unroll 4
+            for (int k = 0; k < w; k += 32) m = __dadd_rn(m, __dmul_rn(__ldg(vp + k), pa[__ldg(cp + k)]));
             if (c < A.n_chan) {
                 m = __dmul_rn(A.exposure, m);
                 if (A.folded) A.folded[(size_t)set * A.n_chan + c] = m;
                 const double D = __ldg(A.counts + c);
                 if (A.kind == RG_FIT_CHI2) {
-                    const double t = __ddiv_rn(__dsub_rn(D, m), __ldg(A.sigma + c));
+                    const double t = __dmul_rn(__dsub_rn(D, m), __ldg(A.sigma + c)); // sigma holds 1 / sigma_c
                     part += t * t;
                 } else {
                     const double mm = m < 1e-300 ? 1e-300 : m;
-                    const double t = D > 0 ? (mm - D) + D * (log(D) - log(mm)) : mm;
+                    const double t = D > 0 ? (mm - D) + D * (__ldg(A.sigma + c) - log(mm)) : mm; // sigma holds ln D_c
                     part += 2 * t;
                 }
             }

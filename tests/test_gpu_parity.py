@@ -383,10 +383,9 @@ def test_batch_evaluator_fitstat_api():
                                np.sqrt(np.maximum(data, 1.0)), 0)
         assert st[k] == pytest.approx(s_ref, rel=1e-12)
     assert np.argmin(st[:64]) == 0
-    # same set in different slabs / positions gives the same bits (batch-order independence)
-    q = np.concatenate([p[19990:], p[:10]])
-    st_q = ev.fitstat(q, rel=True)
-    assert np.array_equal(st_q[:10], st[19990:]) and np.array_equal(st_q[10:], st[:10])
+    # the same sets in another order and in other slabs give the same bits (batch-order independence)
+    st_q = ev.fitstat(p[::-1].copy(), rel=True)
+    assert np.array_equal(st_q[::-1], st)
     # device-resident variant + in-place unit conversion of a spectra batch
     d_p = torch.from_numpy(p[:64]).cuda()
     d_st = ev.fitstat_device(d_p, rel=True)

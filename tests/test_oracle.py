@@ -115,3 +115,41 @@ def test_kyconv_flat_limit_and_additivity():
     whole = np.zeros(4096)
     whole[kw + 2048:kw + 2048 + Hw.size] = Hw
     assert np.max(np.abs(acc - whole)) < 1e-9 * whole.max()
+
+
+def test_observation_epilogue_oracle_pins():
+    """observe_oracle.c against the unmodified reference's getters (golden_units.npz) and its own invariants."""
+    import os
+    from tests.util import GOLDEN, peak_relerr
+    u = np.load(os.path.join(GOLDEN, "golden_units.npz"))
+    dn = np.load(os.path.join(GOLDEN, "golden_nonrel.npz"))
+    eb = dn["grid1000"]
+    L = dn["relagn_spec1000"][0][3]
+    for unit in ["cgs", "cgs_wave", "SI", "SI_wave", "counts"]:
+        for fl in (0, 1):
+            assert peak_relerr(O.convert(L, eb, unit, fl, 100.0, 0.0), u["%s_%d" % (unit, fl)]) < 1e-14
+    Lz = dn["relagn_spec1000"][6][3]  # z = 0.5
+    cz = O.convert(Lz, eb, "counts", 1, 100.0, 0.5)
+    assert peak_relerr(cz, u["z05_counts_1"]) < 1e-14
+    # XSPEC contract (relagn.f:98-112): on the observer-frame image of the model grid photar = counts flux x dE
+    ph = O.photar(Lz, eb, 100.0, 0.5, eb / 1.5)
+    np.testing.assert_allclose(ph, cz * np.diff(eb), rtol=1e-15, atol=0)
+    # photon conservation on any grid that covers the model grid; zeros outside it; clipped edge bins
+    ear = np.geomspace(eb[0] / 3, eb[-1] * 2, 57)
+    assert O.photar(Lz, eb, 100.0, 0.5, ear).sum() == pytest.approx(ph.sum(), rel=1e-13)
+    assert np.all(O.photar(Lz, eb, 100.0, 0.5, np.array([2e3, 3e3, 5e3])) == 0)
+    half = O.photar(Lz, eb, 100.0, 0.5, np.array([eb[10] / 1.5, 0.5 * (eb[10] + eb[11]) / 1.5]))
+    assert half[0] == pytest.approx(0.5 * ph[10], rel=1e-12)
+    # statistic: chi^2 of the model against itself is 0; Cash of the model against itself is 0 and positive elsewhere
+    from tests.util import toy_response
+    ear = np.geomspace(0.3, 10.0, 201)
+    rp, cl, vl = toy_response(ear)
+    pa = O.photar(L, eb, 100.0, 0.0, ear)
+    _, folded = O.fold_stat(pa, rp, cl, vl, 1e4, np.zeros(rp.size - 1), None, 1)
+    assert folded[5] == 0 and np.all(folded[6:] > 0)
+    s0, _ = O.fold_stat(pa, rp, cl, vl, 1e4, folded, np.ones_like(folded), 0)
+    assert s0 == 0
+    c0, _ = O.fold_stat(pa, rp, cl, vl, 1e4, folded, None, 1)
+    assert abs(c0) < 1e-6 * folded.sum() * 1e-6 + 1e-290 * 2 * folded.size + 1e-9
+    c1, _ = O.fold_stat(pa, rp, cl, vl, 1e4, 1.2 * folded, None, 1)
+    assert c1 > 0
