@@ -125,15 +125,6 @@ __device__ inline RingGeo rg_ring_geo(const TabSel &ts, double r1, double r2, do
     return g;
 }
 
-// overlap of [lo,hi] with [L,R] weighted by the hat (1+y on [-1,0], 1-y on [0,1])
-__device__ inline double rg_hat_piece(double lo, double hi, double L, double R, bool neg)
-{
-    double l = lo > L ? lo : L, r = hi < R ? hi : R;
-    if (r <= l) return 0.0;
-    double mid = 0.5 * (l + r);
-    return (r - l) * (neg ? 1.0 + mid : 1.0 - mid);
-}
-
 #define RG_FULL 0xffffffffu
 #define RG_IMAX 0x7fffffff
 
@@ -141,19 +132,29 @@ __device__ inline double rg_hat_piece(double lo, double hi, double L, double R, 
 // Deterministic warp-cooperative deposit of one segment per lane into Hs[k - K_LO]
 // (Hs is owned by this warp).  The weight W of segment [sa, sb] (in units of
 // shift bins) is spread uniformly and binned with the linear (hat) kernel onto
-// bins kfirst + c.  Neighbouring lanes mostly start in the same bin, so lanes
-// are grouped into runs of equal kfirst (one ballot); for every bin offset c the
-// run is summed by a segmented inclusive scan (shuffles) and written once by the
-// run's last lane.  Runs that are not adjacent but share kfirst are written in
-// successive rounds in lane order, so no two lanes ever update one bin at once
-// and the summation order is fixed.
-__device__ inline double seg_contrib(bool point, int c, int nb, int kfirst, double lo, double hi, double f, double W,
-                                     double inv)
+// bins kfirst + c.  The part of the segment inside the unit interval
+// [k, k+1] carries weight wl = W (overlap / length) centred at offset mid in
+// [0, 1]; the hat hands wl mid to bin k+1 and wl - wl mid to bin k -- so one
+// interval evaluation feeds two bins (a degenerate segment is the same formula
+// with wl = W on its own interval).  Neighbouring lanes mostly start in the
+// same bin, so lanes are grouped into runs of equal kfirst (one ballot); for
+// every bin offset c the run is summed by a segmented inclusive scan (shuffles,
+// as many steps as the longest run needs) and written once by the run's last
+// lane.  Runs that are not adjacent but share kfirst are written in successive
+// rounds in lane order, so no two lanes ever update one bin at once and the
+// summation order is fixed.
+struct SegIv { double up, dn; }; // weight handed to bin k+1 / bin k by the part of the segment inside [k, k+1]
+
+__device__ inline SegIv seg_interval(bool point, int m, double km, double lo, double hi, double W, double inv)
 {
-    if (c >= nb) return 0.0;
-    if (point) return c == 0 ? W * (1 - f) : W * f;
-    const int k = kfirst + c;
-    return inv * (rg_hat_piece(lo - k, hi - k, -1.0, 0.0, true) + rg_hat_piece(lo - k, hi - k, 0.0, 1.0, false));
+    const double a = lo > km ? lo : km, b = hi < km + 1.0 ? hi : km + 1.0;
+    const double l = b - a;
+    double wl = l > 0 ? inv * l : 0.0;
+    if (point) wl = m == 0 ? W : 0.0;
+    SegIv r;
+    r.up = wl * (0.5 * (a + b) - km);
+    r.dn = wl - r.up;
+    return r;
 }
 
 __device__ inline void warp_deposit(double *Hs, int K_LO, int nH, double sa, double sb, double W, int &kf_min,
@@ -161,20 +162,13 @@ __device__ inline void warp_deposit(double *Hs, int K_LO, int nH, double sa, dou
 {
     const int lane = threadIdx.x & 31;
     double lo = sa < sb ? sa : sb, hi = sa < sb ? sb : sa;
-    double len = hi - lo;
+    const double len = hi - lo;
     const bool point = len < 1e-12;
-    int kfirst, nb;
-    double f = 0, inv = 0;
-    if (point) {
-        double mid = 0.5 * (lo + hi);
-        double kf = floor(mid);
-        f = mid - kf;
-        kfirst = (int)kf; nb = 2;
-    } else {
-        kfirst = (int)floor(lo);
-        nb = (int)floor(hi) + 1 - kfirst + 1;
-        inv = W / len;
-    }
+    if (point) lo = hi = 0.5 * (lo + hi);
+    const double kf = floor(lo);
+    const int kfirst = (int)kf;
+    const int nb = point ? 2 : (int)floor(hi) + 1 - kfirst + 1;
+    const double inv = point ? 0.0 : W / len;
     kf_min = kfirst < kf_min ? kfirst : kf_min;
     {
         int kl = kfirst + nb - 1;
@@ -189,22 +183,25 @@ __device__ inline void warp_deposit(double *Hs, int K_LO, int nH, double sa, dou
     const int myround = tail ? __popc(peers & ((1u << lane) - 1u)) : -1;
     const int nrounds = __reduce_max_sync(RG_FULL, myround) + 1;
     const int nbmax = __reduce_max_sync(RG_FULL, nb);
+    const int maxrun = __reduce_max_sync(RG_FULL, lane - start + 1);
+    double carry = 0.0; // weight the previous interval hands up to the first bin of this group
     for (int c0 = 0; c0 < nbmax; c0 += 3) {
-        double v0 = seg_contrib(point, c0, nb, kfirst, lo, hi, f, W, inv);
-        double v1 = seg_contrib(point, c0 + 1, nb, kfirst, lo, hi, f, W, inv);
-        double v2 = seg_contrib(point, c0 + 2, nb, kfirst, lo, hi, f, W, inv);
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
+        const SegIv i0 = seg_interval(point, c0, kf + c0, lo, hi, W, inv);
+        const SegIv i1 = seg_interval(point, c0 + 1, kf + (c0 + 1), lo, hi, W, inv);
+        const SegIv i2 = seg_interval(point, c0 + 2, kf + (c0 + 2), lo, hi, W, inv);
+        double v0 = carry + i0.dn, v1 = i0.up + i1.dn, v2 = i1.up + i2.dn;
+        carry = i2.up;
+        for (int d = 1; d < maxrun; d <<= 1) {
             double u0 = __shfl_up_sync(RG_FULL, v0, d), u1 = __shfl_up_sync(RG_FULL, v1, d), u2 = __shfl_up_sync(RG_FULL, v2, d);
             if (lane - d >= start) { v0 += u0; v1 += u1; v2 += u2; }
         }
-        const int i0 = kfirst + c0 - K_LO;
+        const int i0x = kfirst + c0 - K_LO;
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             const double v = c == 0 ? v0 : (c == 1 ? v1 : v2);
             for (int rd = 0; rd < nrounds; rd++) {
                 if (myround == rd && c0 + c < nbmax) {
-                    int i = i0 + c;
+                    int i = i0x + c;
                     if (i >= 0 && i < nH) Hs[i] += v;
                 }
                 __syncwarp();

@@ -389,7 +389,8 @@ def test_batch_evaluator_fitstat_api():
     # device-resident variant + in-place unit conversion of a spectra batch
     d_p = torch.from_numpy(p[:64]).cuda()
     d_st = ev.fitstat_device(d_p, rel=True)
-    assert np.array_equal(d_st.cpu().numpy(), st[:64])
+    # (a 64-set batch splits every set's annuli over several CTAs: same numbers to rounding, not the same bits)
+    np.testing.assert_allclose(d_st.cpu().numpy(), st[:64], rtol=1e-11)
     d_spec, _ = ev.evaluate_device(d_p, rel=True)
     ref = O.convert(d_spec[3].cpu().numpy(), eb, "counts", True, p[3, 1], p[3, 14])
     ev.convert_device(d_spec, d_p, unit="counts", as_flux=True)
