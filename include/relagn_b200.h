@@ -204,6 +204,25 @@ int rg_eval_fitstat_batch(rg_ctx *ctx, const double *d_params, int P, int model,
 int rg_eval_fitstat_batch_host(rg_ctx *ctx, const double *params_host, int P, int model, double dr_dex,
                                unsigned flags, double *stat_host, double *attrs_host);
 
+/* ---- B3: XSPEC local-model ABI (Fortran twins) ------------------------------
+ * relagn_ / relqso_ are the C symbols a gfortran-built XSPEC resolves for
+ *   subroutine relagn(ear,ne,param,ifl,photar,photer)   relagn.f:17-115, lmod_relagn.dat (15 parameters)
+ *   subroutine relqso(ear,ne,param,ifl,photar,photer)   relqso.f, lmod_relqso.dat (6 parameters + $rel switch)
+ * real*4 arrays by reference: ear(0:ne) keV, photar(ne) photons/cm^2/s per bin.  They restate the wrapper of
+ * relagn.f:60-112 (2000-bin model grid covering the caller's grid times 1 + z, redshift, inibin/erebin rebin,
+ * `save oldpar` memoisation) over rg_eval_batch + rg_photar_batch; the physics is the Python class's.
+ * The first call creates a process-wide context on the current device and loads the default Kerr tables
+ * (rg_tables_default); rg_xspec_bind substitutes a caller-owned context. */
+void relagn_(const float *ear, const int *ne, const float *param, const int *ifl, float *photar, float *photer);
+void relqso_(const float *ear, const int *ne, const float *param, const int *ifl, float *photar, float *photer);
+/* double-precision core of the two: par[RG_NPAR] in the Python constructor order, flags = RG_FLAG_REL or 0 */
+int rg_xspec_eval(int model, unsigned flags, const double *ear_host, int ne, const double *par_host,
+                  double *photar_host);
+int rg_xspec_bind(rg_ctx *ctx);
+/* the package's default Kerr node grid (11 spins x 14 inclinations x 64 x 64): from the .npy cache written by the
+ * Python layer (npy_path, or $RELAGN_B200_TABLES when NULL) or ray-traced on the device when there is none */
+int rg_tables_default(rg_ctx *ctx, const char *npy_path);
+
 /* number of kernels launched by this context so far (for accounting) */
 long rg_launch_count(rg_ctx *ctx);
 

@@ -29,7 +29,9 @@ SYMBOLS = ["rg_version", "rg_last_error", "rg_ctx_create", "rg_ctx_destroy", "rg
            "rg_tables_upload", "rg_tables_download", "rg_tables_info", "rg_kyconv", "rg_ky_kernel", "rg_eval_batch",
            "rg_eval_batch_host", "rg_launch_count", "rg_measure_fp64_peak", "rg_set_option", "rg_get_stat",
            "rg_reset_stats", "rg_convert_batch", "rg_set_instrument", "rg_photar_batch", "rg_set_response",
-           "rg_set_data", "rg_fitstat_batch", "rg_eval_fitstat_batch", "rg_eval_fitstat_batch_host"]
+           "rg_set_data", "rg_fitstat_batch", "rg_eval_fitstat_batch", "rg_eval_fitstat_batch_host",
+           "rg_xspec_eval", "rg_xspec_bind", "rg_tables_default"]
+XSPEC_SYMBOLS = ["relagn_", "relqso_"]  # gfortran names of the XSPEC local models (seam B3)
 
 UNITS = {"SI": 0, "cgs": 1, "cgs_wave": 2, "SI_wave": 3, "counts": 4}  # RG_UNIT_*
 FIT_CHI2, FIT_CSTAT = 0, 1
@@ -106,6 +108,16 @@ def bind(lib):
     lib.rg_eval_fitstat_batch.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double, C.c_uint, vp, vp, vp]
     lib.rg_eval_fitstat_batch_host.restype = C.c_int
     lib.rg_eval_fitstat_batch_host.argtypes = [vp, _dp, C.c_int, C.c_int, C.c_double, C.c_uint, _dp, _dp]
+    lib.rg_xspec_eval.restype = C.c_int
+    lib.rg_xspec_eval.argtypes = [C.c_int, C.c_uint, _dp, C.c_int, _dp, _dp]
+    lib.rg_xspec_bind.restype = C.c_int
+    lib.rg_xspec_bind.argtypes = [vp]
+    lib.rg_tables_default.restype = C.c_int
+    lib.rg_tables_default.argtypes = [vp, C.c_char_p]
+    for name in XSPEC_SYMBOLS:
+        f = getattr(lib, name)
+        f.restype = None
+        f.argtypes = [_fp, _ip, _fp, _ip, _fp, _fp]
     return lib
 
 
@@ -301,6 +313,34 @@ class Context:
         self._check(self.lib.rg_eval_fitstat_batch_host(self.h, _d(p), P, int(model), float(dr_dex), flags, _d(st),
                                                         _d(at) if attrs else None))
         return (st, at) if attrs else st
+
+    # ---- XSPEC local-model ABI (seam B3) ----
+    def xspec_bind(self):
+        """Route relagn_ / relqso_ / rg_xspec_eval of this process through this context (and its tables)."""
+        self._check(self.lib.rg_xspec_bind(self.h))
+
+    def tables_default(self, npy_path=None):
+        self._check(self.lib.rg_tables_default(self.h, npy_path.encode() if npy_path else None))
+
+    def xspec_model(self, name, ear, param):
+        """Call the XSPEC entry point `relagn_` / `relqso_` exactly as XSPEC does (real*4 arrays by reference)."""
+        e = np.ascontiguousarray(ear, dtype=np.float32)
+        p = np.ascontiguousarray(param, dtype=np.float32)
+        ne = C.c_int(e.size - 1)
+        ifl = C.c_int(1)
+        photar = np.zeros(e.size - 1, dtype=np.float32)
+        photer = np.zeros(e.size - 1, dtype=np.float32)
+        getattr(self.lib, name + "_")(e.ctypes.data_as(_fp), C.byref(ne), p.ctypes.data_as(_fp), C.byref(ifl),
+                                      photar.ctypes.data_as(_fp), photer.ctypes.data_as(_fp))
+        return photar
+
+    def xspec_eval(self, model, rel, ear, par):
+        e = np.ascontiguousarray(ear, dtype=np.float64)
+        p = np.zeros(NPAR)
+        p[:len(par)] = par
+        out = np.zeros(e.size - 1)
+        self._check(self.lib.rg_xspec_eval(int(model), FLAG_REL if rel else 0, _d(e), e.size - 1, _d(p), _d(out)))
+        return out
 
     def set_profile(self, on=True):
         self._check(self.lib.rg_set_option(self.h, OPT_PROFILE, 1.0 if on else 0.0))

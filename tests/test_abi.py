@@ -23,6 +23,8 @@ def test_library_exports_every_declared_symbol():
     for sym in decl:
         assert hasattr(lib, sym), sym
     assert sorted(_capi.SYMBOLS) == decl
+    for sym in _capi.XSPEC_SYMBOLS:  # the gfortran names XSPEC resolves (lmod_relagn.dat, lmod_relqso.dat)
+        assert hasattr(lib, sym), sym
     assert lib.rg_version() == 100
 
 

@@ -395,3 +395,43 @@ def test_batch_evaluator_fitstat_api():
     ref = O.convert(d_spec[3].cpu().numpy(), eb, "counts", True, p[3, 1], p[3, 14])
     ev.convert_device(d_spec, d_p, unit="counts", as_flux=True)
     assert np.array_equal(d_spec[3].cpu().numpy(), ref)
+
+
+def test_xspec_local_model_abi(ctx, oracle, otab):
+    """Seam B3: relagn_ / relqso_ with XSPEC's calling convention (real*4 by reference) against the oracle's statement
+    of relagn.f:60-112; rg_tables_default from the package's .npy cache."""
+    from tests.util import xspec_reference
+    upload_golden_tables(ctx)
+    ctx.xspec_bind()
+    try:
+        for ear in (np.linspace(0.3, 10.0, 1025), np.geomspace(0.1, 200.0, 301),
+                    np.concatenate([[0.0], np.linspace(0.05, 12.0, 500)])):
+            ear = ear.astype(np.float32)
+            par = np.array([1e8, 100, -1, 0.7, 0.5, 100, 0.2, 1.7, 2.7, 10, 20, -1, 1, 10, 0.05], dtype=np.float32)
+            got = ctx.xspec_model("relagn", ear, par)
+            ref = xspec_reference(oracle, otab, 0, True, ear.astype(np.float64), par.astype(np.float64))
+            np.testing.assert_allclose(got, ref.astype(np.float32), rtol=3e-7)
+            assert np.array_equal(ctx.xspec_model("relagn", ear, par), got)
+        for relsw in (0, 1):
+            q = np.array([1e7, 10, -0.5, 0.0, 0.5, 0.02, relsw], dtype=np.float32)
+            got = ctx.xspec_model("relqso", ear, q)
+            p7 = np.array([q[0], q[1], q[2], q[3], q[4], 1.0, q[5]], dtype=np.float64)
+            ref = xspec_reference(oracle, otab, 1, bool(relsw), ear.astype(np.float64), p7)
+            np.testing.assert_allclose(got, ref.astype(np.float32), rtol=3e-7)
+        # out-of-range spin: the reference raises; XSPEC has no error channel -> zeros
+        bad = par.copy()
+        bad[3] = 0.9999
+        assert np.all(ctx.xspec_model("relagn", ear, bad) == 0)
+    finally:
+        ctx.lib.rg_xspec_bind(None)
+    # default tables through the C entry point (the .npy cache of relagn_b200/_tables travels with the package)
+    from relagn_b200 import tables as T
+    import glob
+    files = glob.glob(os.path.join(T.CACHE_DIR, "kerr_*.npy"))
+    if files:
+        ctx.tables_default(files[0])
+        info = ctx.tables_info()
+        assert (info["n_spin"], info["n_inc"], info["NR"], info["NPHI"]) == (11, 14, 64, 64)
+        assert np.array_equal(ctx.tables_download(), np.load(files[0]))
+    with pytest.raises(Exception):
+        ctx.tables_default("/nonexistent/kerr.npy")

@@ -188,3 +188,29 @@ def test_observation_epilogue_vs_oracle(ctx):
         ctx.set_instrument(np.array([1.0, 0.5, 2.0]))
     with pytest.raises(Exception):
         ctx.set_response(rp, cl + 1000, vl, expo)
+
+
+def test_xspec_local_model_abi(ctx):
+    """Seam B3 on the CPU-only box: relagn_ / relqso_ called the way XSPEC calls a Fortran local model (real*4 by
+    reference) against the oracle's statement of relagn.f:60-112."""
+    from oracle import oracle as O
+    from tests.util import xspec_reference
+    t = golden_tables()
+    otab = O.Tables(t["spins"], t["thetas"], t["NR"], t["NPHI"], t["dl"], data=t["data"])
+    ctx.xspec_bind()
+    try:
+        ear = np.linspace(0.3, 10.0, 101).astype(np.float32)
+        par = np.array([1e8, 100, -1, 0.7, 0.5, 100, 0.2, 1.7, 2.7, 10, 20, -1, 1, 10, 0.05], dtype=np.float32)
+        got = ctx.xspec_model("relagn", ear, par)
+        ref = xspec_reference(O, otab, 0, True, ear.astype(np.float64), par.astype(np.float64))
+        assert got.dtype == np.float32 and np.all(got > 0)
+        np.testing.assert_allclose(got, ref.astype(np.float32), rtol=3e-7)
+        assert np.array_equal(ctx.xspec_model("relagn", ear, par), got)  # memoised (relagn.f:37,62-66)
+        # relqso: M, Dist, log_mdot, astar, cos_inc, redshift, $rel
+        q = np.array([1e7, 10, -0.5, 0.0, 0.5, 0.0, 0], dtype=np.float32)
+        got = ctx.xspec_model("relqso", ear[:40], q)
+        p7 = [float(q[0]), float(q[1]), float(q[2]), float(q[3]), float(q[4]), 1.0, float(q[5])]
+        ref = xspec_reference(O, otab, 1, False, ear[:40].astype(np.float64), np.array(p7))
+        np.testing.assert_allclose(got, ref.astype(np.float32), rtol=3e-7)
+    finally:
+        ctx.lib.rg_xspec_bind(None)

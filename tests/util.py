@@ -87,3 +87,17 @@ def toy_response(ear, n_chan=96, seed=7):
             val.append(w * area)
         rowptr.append(len(col))
     return np.array(rowptr, dtype=np.int32), np.array(col, dtype=np.int32), np.array(val)
+
+
+def xspec_reference(O, otab, model, rel, ear, par):
+    """What relagn_ / relqso_ must return (relagn.f:60-112 with the Python class's physics), from the oracle:
+    2000-bin model grid over [min(1e-4, ear0 (1+z)), max(1e3, earN (1+z))], evaluate, redshift + inibin/erebin."""
+    ear = np.asarray(ear, dtype=np.float64)
+    z = par[6] if model == 1 else par[14]
+    lo = ear[1] - (ear[2] - ear[1]) / 10.0 if ear[0] == 0 else min(1e-4, ear[0] * (1 + z))
+    hi = max(1e3, ear[-1] * (1 + z))
+    enew = np.exp(np.log(lo) + np.log(hi / lo) / 2000 * np.arange(2001))
+    enew[0], enew[-1] = lo, hi
+    st, out, _ = O.evaluate(par, enew, model=model, rel=rel, tab=otab)
+    assert st == 0
+    return O.photar(out[3], enew, par[1], z, ear)
