@@ -280,14 +280,17 @@ setup_kernel(const double *__restrict__ params, int P, int model, double dr_dex,
 //   threads; a warp's accesses to one j are contiguous.
 //   sptot arena: [sys][RG_SPT_STRIDE];  header: [sys][4] = xmin, normfac, jmax, log10(511 xmin);
 //   farr arena: [sys][nE] = the Comptonised spectrum on the caller's energy grid
-__device__ static void nthcomp_system(const SetRec &r, int which, const double *p10tab,
+// Called by all 32 lanes of a warp together (`valid` = this lane has a system): the back substitution walks the
+// scratch rows in warp-uniform order so that a warp's loads of one row stay contiguous.
+__device__ static void nthcomp_system(bool valid, const SetRec &r, int which, const double *p10tab,
                                       double *__restrict__ sc_gam, double *__restrict__ sc_g,
                                       double *__restrict__ sc_bet, size_t sc_stride, int slot, double *__restrict__ spt,
                                       double *__restrict__ hd)
 {
     const int sys = slot; // scratch column of this thread
-    double gamma, kte, ktbb;
-    if (which < 0) { // hot shape: relagn.py:1200-1223
+    double gamma = 2.0, kte = 1.0, ktbb = 0.01;
+    if (!valid) {
+    } else if (which < 0) { // hot shape: relagn.py:1200-1223
         gamma = r.gamma_h; kte = r.kTe_h; ktbb = r.kTseed;
     } else {         // warm annulus `which` (counted top-down): relagn.py:900-927
         NtConst nt;
@@ -308,10 +311,11 @@ __device__ static void nthcomp_system(const SetRec &r, int which, const double *
     double xmin = 1e-4 * tempbb, xmax = 40.0 * theta;
     int jmax = (int)(log10(xmax / xmin) / delta) + 1;
     if (jmax > 899) jmax = 899;
-    if (jmax < 4) { // degenerate grid: the reference would index out of range; flag as empty
+    if (valid && jmax < 4) { // degenerate grid: the reference would index out of range; flag as empty
         hd[0] = xmin; hd[1] = 0.0; hd[2] = 0.0; hd[3] = log10(511.0 * xmin);
-        return;
+        valid = false;
     }
+    if (!valid) jmax = 0; // idle lane: both sweeps fall through, the warp collectives below still see it
     int jmaxth = (int)(log10(50 * tempbb / xmin) / delta);
     if (jmaxth > 900) jmaxth = 900;
     if (jmaxth > jmax) jmaxth = jmax;
@@ -349,7 +353,7 @@ __device__ static void nthcomp_system(const SetRec &r, int which, const double *
         if (0 < jnr - 1) b0 = 1.0 / tautom / (1.0 + tautom * rel / 3.0);
         else if (0 < jrel) { double flz = 1 - (w - xnr) / (xr - xnr); b0 = 1.0 / tautom / (1.0 + tautom * rel / 3.0 * flz); }
         else b0 = 1.0 / tautom;
-        sc_bet[sys] = b0; sc_gam[sys] = 0; sc_g[sys] = 0;
+        if (valid) { sc_bet[sys] = b0; sc_gam[sys] = 0; sc_g[sys] = 0; }
     }
     const double itau = 1.0 / tautom, rxr = 1.0 / (xr - xnr), itbb = 1.0 / tempbb;
     for (int j = 1; j < jmax - 1; j++) {
@@ -399,22 +403,27 @@ __device__ static void nthcomp_system(const SetRec &r, int which, const double *
     // back substitution (pyNTHCOMP.py:243-249) and sptot = dphesc x^2 (pyNTHCOMP.py:170-171)
     double u_next = 0.0; // u[jmax-1]
     double u1 = 0.0;
-    spt[jmax] = 0.0; spt[jmax - 1] = 0.0;
-    // The scratch planes are far larger than L2, so the reads below come from HBM: the loads of 4 steps are issued
-    // together (their addresses do not depend on u), then the dependent recurrence runs on registers.
-    for (int jj = jmax - 2; jj >= 1;) {
-        const int nb = jj >= 4 ? 4 : jj; // steps jj, jj-1, ..., jj-nb+1
+    if (valid) { spt[jmax] = 0.0; spt[jmax - 1] = 0.0; }
+    // The scratch planes are far larger than L2, so the reads below come from HBM.  Neighbouring lanes hold systems
+    // whose jmax differ by a step or two: the warp walks the rows from its highest jmax down TOGETHER (a lane joins
+    // when the row reaches its own jmax - 2), so every row is read as one contiguous run of the plane instead of 32
+    // scattered sectors.  The loads of 4 rows are issued together (their addresses do not depend on u), then the
+    // dependent recurrence runs on registers.
+    const int jtop_me = jmax - 2;
+    const int jtop = __reduce_max_sync(0xffffffffu, jtop_me);
+    for (int jj = jtop; jj >= 1;) {
+        const int nb = jj >= 4 ? 4 : jj; // rows jj, jj-1, ..., jj-nb+1
         double gg[4], gm[4], bt[4];
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-            if (q < nb) {
+            if (q < nb && jj - q <= jtop_me) {
                 size_t o = (size_t)(jj - q) * sc_stride + sys;
                 gg[q] = RG_LDCS(&sc_g[o]); gm[q] = RG_LDCS(&sc_gam[o]); bt[q] = RG_LDCS(&sc_bet[o]);
             }
         }
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-            if (q < nb) {
+            if (q < nb && jj - q <= jtop_me) {
                 double u = gg[q] - gm[q] * u_next;
                 double x = xmin * p10tab[jj - q];
                 spt[jj - q] = (x * x * u * bt[q] * tautom) * (x * x);
@@ -424,6 +433,7 @@ __device__ static void nthcomp_system(const SetRec &r, int which, const double *
         }
         jj -= nb;
     }
+    if (!valid) return;
     {
         double u = aa * u1;
         double x = xmin * p10tab[0];
@@ -453,14 +463,20 @@ nthcomp_kernel(const SetRec *__restrict__ recs, const int2 *__restrict__ syslist
     __syncthreads();
     int gtid = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long sumj = 0, nsolved = 0;
-    for (int sys = gtid; sys < nsys; sys += n_threads) {
-        int2 ent = syslist[sys];
+    const int lane = threadIdx.x & 31;
+    for (int s0 = gtid - lane; s0 < nsys; s0 += n_threads) { // warp-uniform trip count: the lanes solve together
+        const int sys = s0 + lane;
+        bool valid = sys < nsys;
+        int2 ent = valid ? syslist[sys] : make_int2(0, 0);
         const SetRec &r = recs[ent.x];
-        if (r.status != RG_S_OK) continue;
-        nthcomp_system(r, ent.y, s_p10, sc_gam, sc_g, sc_bet, (size_t)n_threads, gtid,
-                       sptot + (size_t)sys * RG_SPT_STRIDE, header + (size_t)sys * 4);
-        sumj += (unsigned long long)header[(size_t)sys * 4 + 2];
-        nsolved++;
+        valid = valid && r.status == RG_S_OK;
+        const size_t so = valid ? (size_t)sys : 0;
+        nthcomp_system(valid, r, ent.y, s_p10, sc_gam, sc_g, sc_bet, (size_t)n_threads, gtid,
+                       sptot + so * RG_SPT_STRIDE, header + so * 4);
+        if (valid) {
+            sumj += (unsigned long long)header[(size_t)sys * 4 + 2];
+            nsolved++;
+        }
     }
     if (stats && nsolved) {
         atomicAdd(&stats[2], sumj);

@@ -112,9 +112,9 @@ struct RingGeo { double A, fr; int s0, s1; };
 __device__ inline RingGeo rg_ring_geo(const TabSel &ts, double r1, double r2, double lnr, int m, int nsub,
                                       double alpha, double beta, double rb)
 {
-    double ra = r1 * exp(lnr * m / nsub), rbb = r1 * exp(lnr * (m + 1) / nsub);
-    if (m == 0) ra = r1;
-    if (m == nsub - 1) rbb = r2;
+    // ring edges r1 (r2/r1)^(m/nsub); the outermost edges are r1 and r2 themselves (most annuli are a single ring)
+    const double ra = m == 0 ? r1 : r1 * exp(lnr * m / nsub);
+    const double rbb = m == nsub - 1 ? r2 : r1 * exp(lnr * (m + 1) / nsub);
     double rm = sqrt(ra * rbb);
     double emis = 1.0;
     if (alpha != 0 || beta != 0) emis = rm < rb ? pow(rm, -alpha) : pow(rm, -beta) * pow(rb, beta - alpha);
@@ -220,6 +220,7 @@ __device__ inline void warp_build_rings(double *Hs, int K_LO, int nH, const TabS
     const int NP = ts.NPHI, nq = NP >> 5;
     const double lnr = log(r2 / r1);
     const double dphi = 2 * RGK_PI / NP;
+    const double inv_dlnE = 1.0 / dlnE; // shift in bins = ln g / dlnE, as one multiplication per sample
     int kf_min = RG_IMAX, kl_max = -RG_IMAX;
     const int n_mine = m_begin < nsub ? (nsub - m_begin + m_step - 1) / m_step : 0;
     for (int m0 = 0; m0 < n_mine; m0 += 32) {
@@ -232,13 +233,13 @@ __device__ inline void warp_build_rings(double *Hs, int K_LO, int nH, const TabS
             const int s0 = __shfl_sync(RG_FULL, geo.s0, m), s1 = __shfl_sync(RG_FULL, geo.s1, m);
             double g, jn;
             rg_ring_sample(ts, s0, s1, fr, lane, g, jn);
-            double s_cur = log(g) / dlnE + zs, w_cur = jn * g * g * g;
+            double s_cur = log(g) * inv_dlnE + zs, w_cur = jn * g * g * g;
             const double s_first = __shfl_sync(RG_FULL, s_cur, 0), w_first = __shfl_sync(RG_FULL, w_cur, 0);
             for (int q = 0; q < nq; q++) {
                 double s_nxt = 0, w_nxt = 0, sn0, wn0;
                 if (q + 1 < nq) {
                     rg_ring_sample(ts, s0, s1, fr, lane + 32 * (q + 1), g, jn);
-                    s_nxt = log(g) / dlnE + zs; w_nxt = jn * g * g * g;
+                    s_nxt = log(g) * inv_dlnE + zs; w_nxt = jn * g * g * g;
                     sn0 = __shfl_sync(RG_FULL, s_nxt, 0); wn0 = __shfl_sync(RG_FULL, w_nxt, 0);
                 } else { sn0 = s_first; wn0 = w_first; }
                 double sb = __shfl_down_sync(RG_FULL, s_cur, 1), wb = __shfl_down_sync(RG_FULL, w_cur, 1);
