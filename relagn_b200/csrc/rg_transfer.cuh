@@ -145,17 +145,38 @@ __device__ inline RingGeo rg_ring_geo(const TabSel &ts, double r1, double r2, do
 // summation order is fixed.
 struct SegIv { double up, dn; }; // weight handed to bin k+1 / bin k by the part of the segment inside [k, k+1]
 
-__device__ inline SegIv seg_interval(bool point, int m, double km, double lo, double hi, double W, double inv)
+// first interval [kf, kf+1], kf = floor(lo): the part starts at lo itself
+__device__ inline SegIv seg_first(bool point, double kf, double lo, double hi, double W, double inv)
 {
-    const double a = lo > km ? lo : km, b = hi < km + 1.0 ? hi : km + 1.0;
-    const double l = b - a;
-    double wl = l > 0 ? inv * l : 0.0;
-    if (point) wl = m == 0 ? W : 0.0;
+    const double b = hi < kf + 1.0 ? hi : kf + 1.0;
+    const double wl = point ? W : inv * (b - lo);
     SegIv r;
-    r.up = wl * (0.5 * (a + b) - km);
+    r.up = wl * (0.5 * (lo + b) - kf);
     r.dn = wl - r.up;
     return r;
 }
+
+// a later interval [km, km+1]: the part starts at km (lo lies below it), its centre sits at half its length
+__device__ inline SegIv seg_next(double km, double hi, double inv)
+{
+    const double b = hi < km + 1.0 ? hi : km + 1.0;
+    const double l = b - km;
+    const double wl = l > 0 ? inv * l : 0.0;
+    SegIv r;
+    r.up = wl * (0.5 * l);
+    r.dn = wl - r.up;
+    return r;
+}
+
+// one step of the segmented inclusive scan over the runs: lanes at least d behind their run head take the value d
+// lanes below (the 0/1 factor keeps the addition exact and the code branch-free)
+#define RG_SCAN_STEP(d)                                                              \
+    {                                                                                \
+        const double mk = (lane - (d) >= start) ? 1.0 : 0.0;                         \
+        v0 = fma(__shfl_up_sync(RG_FULL, v0, (d)), mk, v0);                          \
+        if (nlive > 1) v1 = fma(__shfl_up_sync(RG_FULL, v1, (d)), mk, v1);           \
+        if (nlive > 2) v2 = fma(__shfl_up_sync(RG_FULL, v2, (d)), mk, v2);           \
+    }
 
 __device__ inline void warp_deposit(double *Hs, int K_LO, int nH, double sa, double sb, double W, int &kf_min,
                                     int &kl_max)
@@ -185,30 +206,38 @@ __device__ inline void warp_deposit(double *Hs, int K_LO, int nH, double sa, dou
     const int nbmax = __reduce_max_sync(RG_FULL, nb);
     const int maxrun = __reduce_max_sync(RG_FULL, lane - start + 1);
     double carry = 0.0; // weight the previous interval hands up to the first bin of this group
+    double km = kf;     // lower edge of the group's first interval
     for (int c0 = 0; c0 < nbmax; c0 += 3) {
-        const SegIv i0 = seg_interval(point, c0, kf + c0, lo, hi, W, inv);
-        const SegIv i1 = seg_interval(point, c0 + 1, kf + (c0 + 1), lo, hi, W, inv);
-        const SegIv i2 = seg_interval(point, c0 + 2, kf + (c0 + 2), lo, hi, W, inv);
-        double v0 = carry + i0.dn, v1 = i0.up + i1.dn, v2 = i1.up + i2.dn;
-        carry = i2.up;
-        for (int d = 1; d < maxrun; d <<= 1) {
-            double u0 = __shfl_up_sync(RG_FULL, v0, d), u1 = __shfl_up_sync(RG_FULL, v1, d), u2 = __shfl_up_sync(RG_FULL, v2, d);
-            if (lane - d >= start) { v0 += u0; v1 += u1; v2 += u2; }
+        const int nlive = nbmax - c0 < 3 ? nbmax - c0 : 3; // bins of this group that any lane reaches (warp-uniform)
+        double v0, v1 = 0.0, v2 = 0.0;
+        {
+            const SegIv iv = c0 == 0 ? seg_first(point, kf, lo, hi, W, inv) : seg_next(km, hi, inv);
+            v0 = carry + iv.dn; carry = iv.up;
         }
-        const int i0x = kfirst + c0 - K_LO;
+        if (nlive > 1) { const SegIv iv = seg_next(km + 1.0, hi, inv); v1 = carry + iv.dn; carry = iv.up; }
+        if (nlive > 2) { const SegIv iv = seg_next(km + 2.0, hi, inv); v2 = carry + iv.dn; carry = iv.up; }
+        km += 3.0;
+        if (maxrun > 1) RG_SCAN_STEP(1)
+        if (maxrun > 2) RG_SCAN_STEP(2)
+        if (maxrun > 4) RG_SCAN_STEP(4)
+        if (maxrun > 8) RG_SCAN_STEP(8)
+        if (maxrun > 16) RG_SCAN_STEP(16)
+        const int ib = kfirst + c0 - K_LO;
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            const double v = c == 0 ? v0 : (c == 1 ? v1 : v2);
-            for (int rd = 0; rd < nrounds; rd++) {
-                if (myround == rd && c0 + c < nbmax) {
-                    int i = i0x + c;
-                    if (i >= 0 && i < nH) Hs[i] += v;
+            if (c < nlive) {
+                const double v = c == 0 ? v0 : (c == 1 ? v1 : v2);
+                const unsigned i = (unsigned)(ib + c);
+                const bool ok = i < (unsigned)nH; // 0 <= ib + c < nH
+                for (int rd = 0; rd < nrounds; rd++) {
+                    if (myround == rd && ok) Hs[i] += v;
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         }
     }
 }
+#undef RG_SCAN_STEP
 
 // One warp adds weight x (shift histogram of rings m_begin, m_begin + m_step, ... of annulus [r1, r2] cut into nsub
 // rings) to Hs.  alpha, beta, rb: kyconv's broken power-law emissivity; zs: redshift in units of shift bins.
