@@ -245,6 +245,8 @@ long rg_launch_count(rg_ctx *ctx);
 #define RG_STAT_N_SETS 11       /* parameter sets evaluated */
 #define RG_STAT_MS_OBSERVE 12    /* summed time of the observation-epilogue kernels, ms */
 #define RG_STAT_N_OBSERVE 13
+#define RG_STAT_MS_HIST 14       /* summed time of hist_kernel (shift histograms of the transfer), ms */
+#define RG_STAT_N_HIST 15
 int rg_set_option(rg_ctx *ctx, int key, double value);
 int rg_get_stat(rg_ctx *ctx, int key, double *value);
 int rg_reset_stats(rg_ctx *ctx);

@@ -38,7 +38,7 @@ FIT_CHI2, FIT_CSTAT = 0, 1
 
 OPT_PROFILE = 1
 STATS = {"ms_setup": 1, "ms_nthcomp": 2, "ms_spectrum": 3, "n_setup": 4, "n_nthcomp": 5, "n_spectrum": 6, "sum_W": 7,
-         "n_conv_ann": 8, "sum_jmax": 9, "n_sys": 10, "n_sets": 11, "ms_observe": 12, "n_observe": 13}
+         "n_conv_ann": 8, "sum_jmax": 9, "n_sys": 10, "n_sets": 11, "ms_observe": 12, "n_observe": 13, "ms_hist": 14, "n_hist": 15}
 
 _dp = C.POINTER(C.c_double)
 _fp = C.POINTER(C.c_float)

@@ -69,15 +69,19 @@ struct rg_ctx {
     int *d_queue = nullptr;
     double *d_partial = nullptr;
     size_t partial_n = 0;
+    double *d_hist = nullptr; // shift-histogram arena [annuli of the chunk][hstride]
+    size_t hist_n = 0;
+    cudaStream_t side = nullptr;            // hist_kernel runs here, next to the Kompaneets solves on the caller's stream
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // kyconv seam scratch
     double *d_kyH = nullptr, *d_kyin = nullptr, *d_kyout = nullptr;
     int ky_cap = 0, kyH_cap = 0;
     // instrumentation
     bool profile = false;
     unsigned long long *d_stats = nullptr;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[4]; // setup, nthcomp, spectrum, observation epilogue
-    double ms_acc[4] = {0, 0, 0, 0};
-    long n_acc[4] = {0, 0, 0, 0};
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[5]; // setup, nthcomp, spectrum, observation epilogue, hist
+    double ms_acc[5] = {0, 0, 0, 0, 0};
+    long n_acc[5] = {0, 0, 0, 0, 0};
     double n_sets = 0;
     // observation epilogue: model edges, instrument grid, response (sliced ELL), data, spectra slab
     double *d_ebins = nullptr;
@@ -130,6 +134,9 @@ extern "C" int rg_ctx_create(int device, rg_ctx **out)
     memset(&c->gd, 0, sizeof c->gd);
     memset(&c->td, 0, sizeof c->td);
     RG_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    RG_CUDA_OK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+    RG_CUDA_OK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    RG_CUDA_OK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     // 10^(0.02 j) with the host libm, exactly as the reference's x grid (pyNTHCOMP.py:112-114)
     std::vector<double> p10(RG_NTH + 4);
     for (int j = 0; j < RG_NTH + 4; j++) p10[j] = pow(10.0, j * 0.02);
@@ -148,7 +155,7 @@ extern "C" void rg_ctx_destroy(rg_ctx *c)
     cudaDeviceSynchronize();
     free_dev(c->d_grid); free_dev(c->d_tab); free_dev(c->d_tabmeta); free_dev(c->d_rowrange); free_dev(c->d_p10); free_dev(c->d_recs);
     free_dev(c->d_counter); free_dev(c->d_syslist); free_dev(c->d_sptot); free_dev(c->d_farr); free_dev(c->d_header); free_dev(c->d_sc);
-    free_dev(c->d_rq); free_dev(c->d_queue); free_dev(c->d_partial); free_dev(c->d_kyH); free_dev(c->d_kyin); free_dev(c->d_kyout);
+    free_dev(c->d_rq); free_dev(c->d_queue); free_dev(c->d_partial); free_dev(c->d_hist); free_dev(c->d_kyH); free_dev(c->d_kyin); free_dev(c->d_kyout);
     free_dev(c->d_stage_par); free_dev(c->d_stage_out); free_dev(c->d_stage_attr); free_dev(c->d_stats);
     free_dev(c->d_ebins); free_dev(c->d_ear); free_dev(c->d_sl_off); free_dev(c->d_ell_col); free_dev(c->d_ell_val);
     free_dev(c->d_counts); free_dev(c->d_sigma); free_dev(c->d_slab); free_dev(c->d_stage_stat); free_dev(c->d_pos0);
@@ -156,6 +163,9 @@ extern "C" void rg_ctx_destroy(rg_ctx *c)
     if (c->h_counter) cudaFreeHost(c->h_counter);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->side) cudaStreamDestroy(c->side);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     delete c;
 }
 
@@ -180,7 +190,7 @@ static int prof_end(rg_ctx *c, int kind, cudaStream_t st)
 }
 static int prof_collect(rg_ctx *c)
 {
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < 5; k++) {
         for (auto &pr : c->ev[k]) {
             RG_CUDA_OK(cudaEventSynchronize(pr.second));
             float ms = 0;
@@ -215,7 +225,7 @@ extern "C" int rg_reset_stats(rg_ctx *c)
     if (!c) return rg_set_error(RG_E_ARG, "rg_reset_stats: ctx is NULL");
     RG_CUDA_OK(cudaSetDevice(c->device));
     RG_TRY(prof_collect(c));
-    for (int k = 0; k < 4; k++) { c->ms_acc[k] = 0; c->n_acc[k] = 0; }
+    for (int k = 0; k < 5; k++) { c->ms_acc[k] = 0; c->n_acc[k] = 0; }
     c->n_sets = 0;
     if (c->d_stats) RG_CUDA_OK(cudaMemset(c->d_stats, 0, 4 * sizeof(unsigned long long)));
     return RG_OK;
@@ -245,6 +255,8 @@ extern "C" int rg_get_stat(rg_ctx *c, int key, double *value)
     case RG_STAT_N_SETS: *value = c->n_sets; break;
     case RG_STAT_MS_OBSERVE: *value = c->ms_acc[3]; break;
     case RG_STAT_N_OBSERVE: *value = (double)c->n_acc[3]; break;
+    case RG_STAT_MS_HIST: *value = c->ms_acc[4]; break;
+    case RG_STAT_N_HIST: *value = (double)c->n_acc[4]; break;
     default: return rg_set_error(RG_E_ARG, "rg_get_stat: unknown key %d", key);
     }
     return RG_OK;
@@ -526,6 +538,8 @@ extern "C" int rg_kyconv(rg_ctx *c, const double *eb, int nE, const double *par,
 
 // ---------------------------------------------------------------------------
 // B2: batched evaluation
+static int ensure_dev(double **p, size_t *have, size_t need);
+
 static int ensure_batch_scratch(rg_ctx *c, int model)
 {
     if (!c->d_recs) {
@@ -591,6 +605,7 @@ extern "C" int rg_eval_batch(rg_ctx *c, const double *d_params, int P, int model
         A.nH = K_HI - K_LO + 1;
         A.HL = std::max(K_HI, 0) / 8 + 3;
         A.HH = std::max(-K_LO, 0) / 8 + 3;
+        A.hstride = (A.nH + 2) & ~1; // slot 0 = (first shift, count), then up to nH bins
     } else {
         A.K_LO = 0; A.nH = 1; A.HL = 1; A.HH = 1;
     }
@@ -630,13 +645,39 @@ extern "C" int rg_eval_batch(rg_ctx *c, const double *d_params, int P, int model
                                c->rq_cap, attrs, st));
         RG_TRY(prof_end(c, 0, st));
         c->launches += model == RG_MODEL_RELQSO ? 2 : 1;
-        RG_CUDA_OK(cudaMemcpyAsync(c->h_counter, c->d_counter, sizeof(int), cudaMemcpyDeviceToHost, st));
+        RG_CUDA_OK(cudaMemcpyAsync(c->h_counter, c->d_counter, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
         RG_CUDA_OK(cudaStreamSynchronize(st));
         int nsys = c->h_counter[0];
-        if (nsys > c->farr_cap) {
-            if (n == 1) return rg_set_error(RG_E_NOMEM, "one parameter set needs %d Kompaneets systems (cap %d)", nsys, c->farr_cap);
-            chunk = std::max(1, n / 2); // arena too small for this chunk: retry with fewer sets
+        const size_t hist_need = rel ? (size_t)c->h_counter[1] * (size_t)A.hstride : 0;
+        if (nsys > c->farr_cap || hist_need * sizeof(double) > (size_t)8e9) {
+            if (n == 1) return rg_set_error(RG_E_NOMEM, "one parameter set needs %d Kompaneets systems (cap %d) / %zu histogram doubles", nsys, c->farr_cap, hist_need);
+            chunk = std::max(1, n / 2); // arenas too small for this chunk: retry with fewer sets
             continue;
+        }
+        // The shift histograms (hist_kernel) and the Kompaneets solves (nthcomp kernels) both depend on the setup
+        // kernel only and are both latency bound: they run side by side, the histograms on the context's side stream
+        // (with profiling on they are serialised on the caller's stream so that the event brackets mean something).
+        bool forked = false;
+        if (rel) {
+            RG_TRY(ensure_dev(&c->d_hist, &c->hist_n, hist_need));
+            HistArgs H;
+            memset(&H, 0, sizeof H);
+            H.recs = c->d_recs; H.P = n; H.tab = c->td; H.dlnE = c->gd.dlnE; H.K_LO = A.K_LO; H.nH = A.nH;
+            H.NBH = n >= 2 * c->sm_count ? 1 : (int)std::min<long>(32, (4L * c->sm_count + n - 1) / n);
+            H.hist = c->d_hist; H.hstride = A.hstride;
+            cudaStream_t hs = st;
+            if (!c->profile && nsys > 0 && !getenv("RG_NO_SIDE_STREAM")) {
+                RG_CUDA_OK(cudaEventRecord(c->ev_fork, st));
+                RG_CUDA_OK(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+                hs = c->side;
+                forked = true;
+            }
+            RG_TRY(prof_begin(c, 4, hs));
+            RG_TRY(rg_launch_hist(H, hs));
+            RG_TRY(prof_end(c, 4, hs));
+            if (forked) RG_CUDA_OK(cudaEventRecord(c->ev_join, c->side));
+            c->launches++;
+            A.hist = c->d_hist;
         }
         unsigned long long *stats = c->profile ? c->d_stats : nullptr;
         if (nsys > 0) {
@@ -649,6 +690,7 @@ extern "C" int rg_eval_batch(rg_ctx *c, const double *d_params, int P, int model
             RG_TRY(prof_end(c, 1, st));
             c->launches++;
         }
+        if (forked) RG_CUDA_OK(cudaStreamWaitEvent(st, c->ev_join, 0));
         A.recs = c->d_recs;
         A.P = n;
         A.out = d_out + (size_t)p0 * ncomp * nE;

@@ -1,0 +1,88 @@
+// rg_hist.cu -- the shift histograms of the relativistic transfer, one WARP per annulus.
+//
+// The kyconv seam of the reference (relagn.py:979-1001) turns every annulus [r1, r2] into a transfer kernel on the
+// log-energy grid; rg_transfer.cuh builds it as a histogram over integer bin shifts from the Kerr table slice of the
+// set's (spin, inclination).  Building it is a chain of dependent warp shuffles and shared-memory updates -- latency
+// bound, few registers -- while the consumer (spectrum_kernel: Planck function + banded convolution) is register
+// heavy and runs at 12 warps per SM.  Doing the build here, in its own kernel at 3x the occupancy, hides those
+// latencies behind other warps; the histograms (W ~ 20 doubles per annulus) travel through a global arena that stays
+// in L2 / HBM for a few hundred microseconds: [annulus][hstride] doubles, slot 0 = (first shift, count) as two ints.
+#include "rg_kernels.h"
+#include "rg_transfer.cuh"
+
+#define HIST_WARPS 8
+#ifndef RG_HIST_MINB
+#define RG_HIST_MINB 4 // resident CTAs per SM the register budget is cut for
+#endif
+
+static __host__ __device__ inline int hist_round_up2(int x) { return (x + 1) & ~1; }
+
+__global__ void __launch_bounds__(32 * HIST_WARPS, RG_HIST_MINB) hist_kernel(HistArgs A)
+{
+    RG_DYN_SMEM(smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int HSZ = hist_round_up2(A.nH + 24);
+    double *Hslot = reinterpret_cast<double *>(smem_raw) + (size_t)warp * HSZ; // 8 zero pad | nH bins | zero pad
+    for (int i = lane; i < HSZ; i += 32) Hslot[i] = 0.0;
+    __syncwarp();
+    const int set = blockIdx.x / A.NBH, blk = blockIdx.x - set * A.NBH;
+    const SetRec &r = A.recs[set];
+    if (r.status != RG_S_OK) return;
+    const int n_tot = r.n_disc + r.n_warm + r.n_hot;
+    const int g_warm0 = r.n_disc, g_hot0 = r.n_disc + r.n_warm;
+    TabSel ts;
+    rg_tab_select(ts, A.tab, r.a, r.inc);
+    const int wstride = HIST_WARPS * A.NBH, w0 = blk * HIST_WARPS + warp;
+    const int n_mine = w0 < n_tot ? (n_tot - w0 + wstride - 1) / wstride : 0;
+    for (int m0 = 0; m0 < n_mine; m0 += 32) {
+        // lane m prepares this warp's annulus number m0 + m: its edges (relagn.py:731-776, :962-964) and whether the
+        // reference sends it through kyconv (:992)
+        double p_r1 = 0, p_r2 = 0;
+        int p_flag = 0, p_g = 0;
+        if (m0 + lane < n_mine) {
+            const int g = w0 + wstride * (m0 + lane);
+            const int region = g < g_warm0 ? 0 : (g < g_hot0 ? 1 : 2);
+            const int a = g - (region == 0 ? 0 : (region == 1 ? g_warm0 : g_hot0));
+            const double lg_in = region == 0 ? r.lg_rw : (region == 1 ? r.lg_rh : r.lg_risco);
+            const double lg_out = region == 0 ? r.lg_rout : (region == 1 ? r.lg_rw : r.lg_rh);
+            BinIter it;
+            it.start(lg_in, lg_out, r.dlog_r);
+            double lo = 0, hi = 0;
+            for (int q = 0; q <= a; q++) it.next(lo, hi);
+            p_r1 = pow(10.0, lo); p_r2 = pow(10.0, hi);
+            p_flag = (lo <= 3 && hi <= 3) ? 1 : 0;
+            p_g = g;
+        }
+        const int mt = n_mine - m0 < 32 ? n_mine - m0 : 32;
+        for (int mi = 0; mi < mt; mi++) {
+            const double r1 = __shfl_sync(RG_FULL, p_r1, mi), r2 = __shfl_sync(RG_FULL, p_r2, mi);
+            const int flag = __shfl_sync(RG_FULL, p_flag, mi), g = __shfl_sync(RG_FULL, p_g, mi);
+            double *row = A.hist + (size_t)(r.ann_base + g) * A.hstride;
+            int kmn = 0, kmx = -1;
+            if (flag) {
+                warp_build_hist(Hslot + 8, A.K_LO, A.nH, ts, r1, r2, A.dlnE, 1.0, kmn, kmx);
+                if (kmn < A.K_LO) kmn = A.K_LO;
+                if (kmx > A.K_LO + A.nH - 1) kmx = A.K_LO + A.nH - 1;
+                __syncwarp();
+            }
+            const int nk = kmx >= kmn ? kmx - kmn + 1 : 0;
+            if (lane == 0) *reinterpret_cast<int2 *>(row) = make_int2(kmn, nk);
+            for (int k = lane; k < nk; k += 32) {
+                const int q = 8 + kmn - A.K_LO + k;
+                row[1 + k] = Hslot[q];
+                Hslot[q] = 0.0; // leave the slot clean for the next annulus
+            }
+            __syncwarp();
+        }
+    }
+}
+
+int rg_launch_hist(const HistArgs &A, cudaStream_t st)
+{
+    if (A.P == 0) return RG_OK;
+    size_t smem = (size_t)HIST_WARPS * hist_round_up2(A.nH + 24) * sizeof(double);
+    RG_CUDA_OK(cudaFuncSetAttribute(hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RG_LAUNCH(hist_kernel, dim3((unsigned)((long)A.P * A.NBH)), dim3(32 * HIST_WARPS), smem, st, A);
+    RG_CUDA_OK(cudaGetLastError());
+    return RG_OK;
+}

@@ -48,6 +48,8 @@ struct SpecArgs {
     int HL, HH;           // zero halo columns of the transposed local-spectrum buffer
     int NB;               // annulus blocks per parameter set (work items = P * NB)
     double *partial;      // NB > 1: [P][NB][ncomp][nE] partial sums, folded by the reduce kernel
+    const double *hist;   // shift histograms built by hist_kernel: [annulus][hstride], slot 0 = (first shift, count)
+    int hstride;
     int *queue;           // device work-queue counter (zeroed before the launch)
     int warps;            // warps per CTA
     unsigned long long *stats; // optional device counters [4]: sum W_ann, conv annuli, sum jmax, systems
@@ -67,6 +69,19 @@ int rg_launch_nthcomp(const SetRec *recs, const int2 *syslist, int nsys, const d
                       const GridDesc &grid, double *farr, unsigned long long *stats, cudaStream_t st);
 
 int rg_launch_spectrum(const SpecArgs &args, int sm_count, cudaStream_t st);
+
+// shift histograms of every annulus of every set (rg_hist.cu); annulus g of set p lives at row recs[p].ann_base + g
+struct HistArgs {
+    const SetRec *recs;
+    int P;
+    TabDesc tab;
+    double dlnE;
+    int K_LO, nH;  // widest support over all table nodes
+    int NBH;       // CTAs per parameter set
+    double *hist;  // [total annuli][hstride]
+    int hstride;   // >= nH + 1
+};
+int rg_launch_hist(const HistArgs &A, cudaStream_t st);
 
 // generic kyconv seam: histogram of one (possibly wide) annulus into d_H[0..nH) (shift k = K_LO + index)
 int rg_launch_ky_hist(const TabDesc &tab, double a, double theta_o, double r1, double r2, double alpha, double beta,

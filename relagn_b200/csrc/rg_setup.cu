@@ -248,6 +248,7 @@ setup_kernel(const double *__restrict__ params, int P, int model, double dr_dex,
             if (r.kTseed < r.kTe_h) r.has_hotshape = 1;
             else r.flags |= RG_F_HOT_SEED_GE_KTE;
         }
+        r.ann_base = atomicAdd(sys_counter + 1, r.n_disc + r.n_warm + r.n_hot); // rows of the shift-histogram arena
         int need_hot = (r.n_hot > 0 && r.has_hotshape) ? 1 : 0;
         int nsys = r.n_warm + need_hot;
         r.sys_base = 0;
@@ -543,7 +544,7 @@ nthcomp_interp_kernel(const SetRec *__restrict__ recs, const int2 *__restrict__ 
 int rg_launch_setup(const double *d_params, int P, int model, double dr_dex, SetRec *recs, int *sys_counter,
                     int2 *syslist, int sys_cap, double *rq_scratch, int rq_cap, double *d_attrs, cudaStream_t st)
 {
-    RG_CUDA_OK(cudaMemsetAsync(sys_counter, 0, sizeof(int), st));
+    RG_CUDA_OK(cudaMemsetAsync(sys_counter, 0, 2 * sizeof(int), st)); // [0] Kompaneets systems, [1] annuli
     if (model == RG_MODEL_RELQSO) {
         RG_LAUNCH(relqso_rhot_kernel, dim3(P), dim3(128), 0, st, d_params, P, rq_scratch);
         RG_CUDA_OK(cudaGetLastError());

@@ -41,6 +41,9 @@
 #define RG_LOCKSTEP 4 // block barrier every RG_LOCKSTEP rounds (power of two)
 #endif
 #define NGRID 5 // per-bin constant arrays staged in shared memory: hnu, bbpre, wt, pk, upk
+#ifndef RG_SPEC_W64
+#define RG_SPEC_W64 12 // warps per CTA of the FP64 kernel on grids of <= 1024 bins (register budget 65536 / (32 W))
+#endif
 
 static __host__ __device__ inline int round_up2(int x) { return (x + 1) & ~1; }
 
@@ -66,7 +69,7 @@ size_t rg_spectrum_smem_bytes(int NC, int nH, int HL, int HH, int warps, int fp3
 
 int rg_spectrum_pick_warps(int NC, int nH, int HL, int HH, int fp32)
 {
-    for (int w = (NC <= 4 ? (fp32 ? 16 : 12) : 8); w >= 1; w--)
+    for (int w = (NC <= 4 ? (fp32 ? 16 : RG_SPEC_W64) : 8); w >= 1; w--)
         if (rg_spectrum_smem_bytes(NC, nH, HL, HH, w, fp32) <= 227 * 1024 - 512) return w;
     return 0;
 }
@@ -251,7 +254,7 @@ struct Acc {
 // buffer, the convolution and the accumulators in single precision -- the histogram, every per-annulus scalar, the
 // Kompaneets solve and the normalisations stay FP64.
 template <int NC, typename R>
-__global__ void __launch_bounds__(NC <= 4 ? (sizeof(R) == 4 ? 512 : 384) : 256, 1) spectrum_kernel(SpecArgs A)
+__global__ void __launch_bounds__(NC <= 4 ? (sizeof(R) == 4 ? 512 : 32 * RG_SPEC_W64) : 256, 1) spectrum_kernel(SpecArgs A)
 {
     constexpr bool GS = NC <= 8;       // grid constants in shared memory
     constexpr bool ACC_REG = NC <= 4;  // accumulators in registers
@@ -297,7 +300,6 @@ __global__ void __launch_bounds__(NC <= 4 ? (sizeof(R) == 4 ? 512 : 384) : 256, 
     GridAcc<NC, GS, R> G;
     G.sm = sgrid; G.g = &A.grid;
     R *const inBase = inT + A.HL + lane; // row 0, this lane's column of chunk 0
-    const double dlnE = A.grid.dlnE;
     unsigned long long st_w = 0, st_n = 0;
 
     // The warps of a CTA work on ONE (parameter set, annulus block) item at a time, annulus g -> warp g mod nwarps.
@@ -345,31 +347,8 @@ __global__ void __launch_bounds__(NC <= 4 ? (sizeof(R) == 4 ? 512 : 384) : 256, 
 
         NtConst nt;
         rg_nt_prepare(nt, r);
-        TabSel ts;
-        int K_LO = 0, nH = 1;
-        if (rel) {
-            rg_tab_select(ts, A.tab, r.a, r.inc);
-            // shift range this (spin, inclination) can produce: min/max of ln g over the rows of its 4 nodes
-            double lo = 1e300, hi = -1e300;
-            const double *rr = A.tab.rowrange;
-            const size_t plane2 = (size_t)A.tab.NR * 2;
-            const size_t nd[4] = {(size_t)((ts.n00 - A.tab.data) / (2 * ts.plane)), (size_t)((ts.n01 - A.tab.data) / (2 * ts.plane)),
-                                  (size_t)((ts.n10 - A.tab.data) / (2 * ts.plane)), (size_t)((ts.n11 - A.tab.data) / (2 * ts.plane))};
-            for (int q = 0; q < 4; q++)
-                for (int row = lane; row < A.tab.NR; row += 32) {
-                    double a0 = __ldg(rr + nd[q] * plane2 + 2 * row), a1 = __ldg(rr + nd[q] * plane2 + 2 * row + 1);
-                    lo = a0 < lo ? a0 : lo; hi = a1 > hi ? a1 : hi;
-                }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                double a0 = __shfl_xor_sync(FULL, lo, o), a1 = __shfl_xor_sync(FULL, hi, o);
-                lo = a0 < lo ? a0 : lo; hi = a1 > hi ? a1 : hi;
-            }
-            int kl = (int)floor(lo / dlnE) - 2, kh = (int)floor(hi / dlnE) + 3;
-            if (kl < A.K_LO) kl = A.K_LO;
-            if (kh > A.K_LO + A.nH - 1) kh = A.K_LO + A.nH - 1;
-            K_LO = kl; nH = kh - kl + 1;
-        }
+        // shift range of the histograms (hist_kernel builds them on the same range): widest support over the table
+        const int K_LO = A.K_LO, nH = A.nH;
         const double Rg2 = r.Rg * r.Rg;
         const double cosfac = r.cosinc / 0.5;
 
@@ -454,9 +433,10 @@ __global__ void __launch_bounds__(NC <= 4 ? (sizeof(R) == 4 ? 512 : 384) : 256, 
                 }
                 int kmn = 0, kmx = -1;
                 if (conv) {
-                    // disc / warm: re-zero what the previous annulus touched, then build this annulus' histogram.
-                    // hot: the slot turns into the region histogram -- every hot annulus adds its own, weighted by
-                    // the annulus luminosity (the warp meets its hot annuli last, so the slot is free by then)
+                    // disc / warm: re-zero what the previous annulus touched, then fetch this annulus' histogram
+                    // (built by hist_kernel).  hot: the slot turns into the region histogram -- every hot annulus adds
+                    // its own, weighted by the annulus luminosity (the warp meets its hot annuli last, so the slot is
+                    // free by then)
                     if (region != 2 || !hot_any_conv) {
                         for (int k = hz_min + lane; k <= hz_max; k += 32) {
                             int q = k - K_LO;
@@ -465,10 +445,22 @@ __global__ void __launch_bounds__(NC <= 4 ? (sizeof(R) == 4 ? 512 : 384) : 256, 
                         hz_min = IMAX; hz_max = -IMAX;
                         __syncwarp();
                     }
-                    warp_build_hist(Hslot + 8, K_LO, nH, ts, r1, r2, dlnE, region == 2 ? s1 : 1.0, kmn, kmx);
-                    hz_min = kmn < hz_min ? kmn : hz_min;
-                    hz_max = kmx > hz_max ? kmx : hz_max;
-                    if (kmn <= kmx) { st_w += (unsigned long long)(kmx - kmn + 1); st_n += 1; }
+                    const int g = (region == 0 ? 0 : (region == 1 ? g_warm0 : g_hot0)) + loc;
+                    const double *row = A.hist + (size_t)(r.ann_base + g) * A.hstride;
+                    const int2 hd = __ldg(reinterpret_cast<const int2 *>(row));
+                    kmn = hd.x; kmx = hd.x + hd.y - 1;
+                    double *Hd = Hslot + 8 + (kmn - K_LO);
+                    if (region == 2) {
+                        for (int k = lane; k < hd.y; k += 32) Hd[k] += s1 * __ldg(row + 1 + k);
+                    } else {
+                        for (int k = lane; k < hd.y; k += 32) Hd[k] = __ldg(row + 1 + k);
+                    }
+                    __syncwarp();
+                    if (kmn <= kmx) {
+                        hz_min = kmn < hz_min ? kmn : hz_min;
+                        hz_max = kmx > hz_max ? kmx : hz_max;
+                        st_w += (unsigned long long)(kmx - kmn + 1); st_n += 1;
+                    }
                 }
                 if (region == 2) {
                     hot_mine = true;

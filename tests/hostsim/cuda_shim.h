@@ -196,6 +196,9 @@ cudaError_t cudaGetDevice(int *d);
 cudaError_t cudaGetDeviceCount(int *n);
 cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int d);
 cudaError_t cudaEventCreate(cudaEvent_t *e);
+enum { cudaEventDisableTiming = 2 };
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned);
+cudaError_t cudaStreamWaitEvent(cudaStream_t s, cudaEvent_t e, unsigned flags = 0);
 cudaError_t cudaEventDestroy(cudaEvent_t e);
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s = 0);
 cudaError_t cudaEventSynchronize(cudaEvent_t e);
