@@ -47,6 +47,7 @@ struct rg_ctx {
     bool have_tab = false;
     TabDesc td;
     float *d_tab = nullptr;
+    double2 *d_tab2 = nullptr; // (g, jn) pairs in double: one 16-byte load per table node
     double *d_tabmeta = nullptr;
     double *d_rowrange = nullptr;
     size_t tab_floats = 0;
@@ -153,7 +154,7 @@ extern "C" void rg_ctx_destroy(rg_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    free_dev(c->d_grid); free_dev(c->d_tab); free_dev(c->d_tabmeta); free_dev(c->d_rowrange); free_dev(c->d_p10); free_dev(c->d_recs);
+    free_dev(c->d_grid); free_dev(c->d_tab); free_dev(c->d_tab2); free_dev(c->d_tabmeta); free_dev(c->d_rowrange); free_dev(c->d_p10); free_dev(c->d_recs);
     free_dev(c->d_counter); free_dev(c->d_syslist); free_dev(c->d_sptot); free_dev(c->d_farr); free_dev(c->d_header); free_dev(c->d_sc);
     free_dev(c->d_rq); free_dev(c->d_queue); free_dev(c->d_partial); free_dev(c->d_hist); free_dev(c->d_kyH); free_dev(c->d_kyin); free_dev(c->d_kyout);
     free_dev(c->d_stage_par); free_dev(c->d_stage_out); free_dev(c->d_stage_attr); free_dev(c->d_stats);
@@ -353,8 +354,8 @@ static int tables_alloc(rg_ctx *c, const double *spins, int n_spin, const double
     for (int i = 1; i < n_inc; i++)
         if (!(thetas[i] > thetas[i - 1])) return rg_set_error(RG_E_ARG, "tables: inclinations must ascend");
     RG_CUDA_OK(cudaSetDevice(c->device));
-    free_dev(c->d_tab); free_dev(c->d_tabmeta); free_dev(c->d_rowrange);
-    c->d_tab = nullptr; c->d_tabmeta = nullptr; c->d_rowrange = nullptr; c->have_tab = false;
+    free_dev(c->d_tab); free_dev(c->d_tab2); free_dev(c->d_tabmeta); free_dev(c->d_rowrange);
+    c->d_tab = nullptr; c->d_tab2 = nullptr; c->d_tabmeta = nullptr; c->d_rowrange = nullptr; c->have_tab = false;
     c->tab_floats = (size_t)n_spin * n_inc * 2 * NR * NPHI;
     RG_CUDA_OK(cudaMalloc(&c->d_tab, c->tab_floats * sizeof(float)));
     std::vector<double> meta(2 * n_spin + n_inc);
@@ -398,6 +399,17 @@ static int tables_finish(rg_ctx *c, const float *host_data)
             rr[(n * NR + s) * 2 + 1] = log(hi);
             gmin = std::min(gmin, lo); gmax = std::max(gmax, hi);
         }
+    }
+    {
+        std::vector<double2> pairs(nodes * plane);
+        for (size_t n = 0; n < nodes; n++)
+            for (size_t i = 0; i < plane; i++) {
+                pairs[n * plane + i].x = (double)host_data[n * 2 * plane + i];
+                pairs[n * plane + i].y = (double)host_data[n * 2 * plane + plane + i];
+            }
+        RG_CUDA_OK(cudaMalloc(&c->d_tab2, pairs.size() * sizeof(double2)));
+        RG_CUDA_OK(cudaMemcpy(c->d_tab2, pairs.data(), pairs.size() * sizeof(double2), cudaMemcpyHostToDevice));
+        c->td.pairs = c->d_tab2;
     }
     RG_CUDA_OK(cudaMalloc(&c->d_rowrange, rr.size() * sizeof(double)));
     RG_CUDA_OK(cudaMemcpy(c->d_rowrange, rr.data(), rr.size() * sizeof(double), cudaMemcpyHostToDevice));

@@ -38,7 +38,9 @@ __global__ void __launch_bounds__(32 * HIST_WARPS, RG_HIST_MINB) hist_kernel(His
         // lane m prepares this warp's annulus number m0 + m: its edges (relagn.py:731-776, :962-964) and whether the
         // reference sends it through kyconv (:992)
         double p_r1 = 0, p_r2 = 0;
-        int p_flag = 0, p_g = 0;
+        int p_flag = 0, p_g = 0, p_nsub = 1;
+        RingGeo p_geo; // of the annulus' only ring when p_nsub == 1 (most annuli)
+        p_geo.A = 0; p_geo.fr = 0; p_geo.s0 = 0; p_geo.s1 = 0;
         if (m0 + lane < n_mine) {
             const int g = w0 + wstride * (m0 + lane);
             const int region = g < g_warm0 ? 0 : (g < g_hot0 ? 1 : 2);
@@ -52,15 +54,25 @@ __global__ void __launch_bounds__(32 * HIST_WARPS, RG_HIST_MINB) hist_kernel(His
             p_r1 = pow(10.0, lo); p_r2 = pow(10.0, hi);
             p_flag = (lo <= 3 && hi <= 3) ? 1 : 0;
             p_g = g;
+            if (p_flag) {
+                const double lnr = log(p_r2 / p_r1);
+                p_nsub = rg_auto_nsub(p_r1, p_r2, lnr, A.dlnE);
+                if (p_nsub == 1) p_geo = rg_ring_geo(ts, p_r1, p_r2, lnr, 0, 1, 0.0, 0.0, 1.0);
+            }
         }
         const int mt = n_mine - m0 < 32 ? n_mine - m0 : 32;
         for (int mi = 0; mi < mt; mi++) {
             const double r1 = __shfl_sync(RG_FULL, p_r1, mi), r2 = __shfl_sync(RG_FULL, p_r2, mi);
             const int flag = __shfl_sync(RG_FULL, p_flag, mi), g = __shfl_sync(RG_FULL, p_g, mi);
+            const int nsub = __shfl_sync(RG_FULL, p_nsub, mi);
+            RingGeo geo;
+            geo.A = __shfl_sync(RG_FULL, p_geo.A, mi); geo.fr = __shfl_sync(RG_FULL, p_geo.fr, mi);
+            geo.s0 = __shfl_sync(RG_FULL, p_geo.s0, mi); geo.s1 = __shfl_sync(RG_FULL, p_geo.s1, mi);
             double *row = A.hist + (size_t)(r.ann_base + g) * A.hstride;
             int kmn = 0, kmx = -1;
             if (flag) {
-                warp_build_hist(Hslot + 8, A.K_LO, A.nH, ts, r1, r2, A.dlnE, 1.0, kmn, kmx);
+                warp_build_rings(Hslot + 8, A.K_LO, A.nH, ts, r1, r2, A.dlnE, nsub, 0, 1, 0.0, 0.0, 1.0, 0.0, 1.0, kmn, kmx,
+                                 nsub == 1 ? &geo : nullptr);
                 if (kmn < A.K_LO) kmn = A.K_LO;
                 if (kmx > A.K_LO + A.nH - 1) kmx = A.K_LO + A.nH - 1;
                 __syncwarp();

@@ -7,7 +7,8 @@
 
 // Kerr transfer tables resident on the device
 struct TabDesc {
-    const float *data;     // [n_spin][n_inc][2][NR][NPHI]
+    const float *data;     // [n_spin][n_inc][2][NR][NPHI] (the layout of the C ABI)
+    const double2 *pairs;  // [n_spin][n_inc][NR][NPHI] of (g, jn): what the kernels read
     const double *spins;   // [n_spin] ascending
     const double *riscos;  // [n_spin]
     const double *thetas;  // [n_inc] ascending, radians

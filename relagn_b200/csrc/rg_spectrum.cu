@@ -1,28 +1,22 @@
-// rg_spectrum.cu -- the fused spectrum kernel.  Every WARP is an autonomous
-// worker: it pulls a (parameter set, annulus block) item from a device queue,
-// walks the annuli of that item (disc, warm, hot), builds every local spectrum
-// in registers, pushes it through the relativistic transfer and accumulates the
-// observed spectrum in registers, without touching HBM between the parameter
-// record and the final [nE] store and without a block barrier after start-up.
+// rg_spectrum.cu -- the fused spectrum kernel.  The warps of a persistent CTA share one (parameter set, annulus
+// block) item pulled from a device queue; every warp walks its own annuli of that item (disc, warm, hot), builds the
+// local spectrum in registers, pushes it through the relativistic transfer and accumulates the observed spectrum
+// in registers, without touching HBM between the parameter record and the final [nE] store.
 //
 // Reference path restated (src/python_version/relagn.py):
 //   disc_annuli :839-896, warmComp_annuli :900-939, hotComp_annuli :1295-1318,
 //   do_relDiscSpec :950-1027, do_relWarmCompSpec :1063-1124,
-//   do_relHotCompSpec :1322-1384, do_nonrel* :1030-1059,1127-1156,1387-1401,
-//   pyNTHCOMP.donthcomp :57-76 (interpolation of the Kompaneets solution on the
-//   caller's grid); the kyconv seam (:979-1001) as discretised in
-//   rg_transfer.cuh.
+//   do_relHotCompSpec :1322-1384, do_nonrel* :1030-1059,1127-1156,1387-1401;
+//   the Comptonised spectra arrive on the caller's grid from nthcomp_interp_kernel (pyNTHCOMP.donthcomp :57-76),
+//   the transfer kernel of every annulus (the kyconv seam, :979-1001) as a shift histogram from hist_kernel.
 //
 // Work layout per warp.  The energy grid is cut into NC chunks of 256 bins;
 // in chunk ch lane l owns the 8 consecutive bins j = 8 (32 ch + l) + c.  A
 // chunk is the unit of skipping (Wien tails past the FP64 overflow point are
 // neither evaluated nor convolved) and gives every lane 8 independent
 // exp / divide / FMA chains.  Per annulus:
-//   1. the g-shift histogram H[k] of the annulus is built from the Kerr table
-//      slice (4 nodes x 2 rows blended): lanes sample the ring azimuths,
-//      neighbouring samples form segments, and every segment's weight is
-//      deposited with a warp-shuffle segmented reduction keyed by the shift bin
-//      -- no atomics, fixed summation order;
+//   1. the g-shift histogram H[k] of the annulus (built by hist_kernel with a warp-shuffle segmented reduction
+//      keyed by the shift bin -- no atomics, fixed summation order) is fetched into the warp's shared-memory slot;
 //   2. the local spectrum (Planck / Kompaneets interpolation) is evaluated chunk
 //      by chunk in registers, written to the warp's shared-memory buffer in
 //      transposed form (row j mod 8, column j div 8, zero halos) together with

@@ -17,7 +17,7 @@
 #include "rg_kernels.h"
 
 struct TabSel {
-    const float *n00, *n01, *n10, *n11; // node planes (g at +0, jn at +plane)
+    const double2 *n00, *n01, *n10, *n11; // node planes [NR][NPHI] of (g, jn) pairs
     double w00, w01, w10, w11;
     double risco, rh;  // of the model's own spin
     size_t plane;
@@ -45,10 +45,10 @@ __device__ inline void rg_tab_select(TabSel &ts, const TabDesc &t, double a, dou
         fi = fi < 0 ? 0 : (fi > 1 ? 1 : fi);
     }
     size_t plane = (size_t)t.NR * t.NPHI;
-    ts.n00 = t.data + ((size_t)m0 * t.n_inc + n0) * 2 * plane;
-    ts.n01 = t.data + ((size_t)m0 * t.n_inc + n1) * 2 * plane;
-    ts.n10 = t.data + ((size_t)m1 * t.n_inc + n0) * 2 * plane;
-    ts.n11 = t.data + ((size_t)m1 * t.n_inc + n1) * 2 * plane;
+    ts.n00 = t.pairs + ((size_t)m0 * t.n_inc + n0) * plane;
+    ts.n01 = t.pairs + ((size_t)m0 * t.n_inc + n1) * plane;
+    ts.n10 = t.pairs + ((size_t)m1 * t.n_inc + n0) * plane;
+    ts.n11 = t.pairs + ((size_t)m1 * t.n_inc + n1) * plane;
     ts.w00 = (1 - fa) * (1 - fi); ts.w01 = (1 - fa) * fi; ts.w10 = fa * (1 - fi); ts.w11 = fa * fi;
     ts.risco = risco; ts.rh = 1 + sqrt(1 - a * a);
     ts.plane = plane; ts.NR = t.NR; ts.NPHI = t.NPHI; ts.inv_dl = 1.0 / t.dl;
@@ -73,16 +73,14 @@ __device__ inline RingRow rg_ring_row(const TabSel &ts, double rm)
 // g and Jn at column p of the ring (blend of 4 nodes x 2 rows)
 __device__ inline void rg_ring_sample(const TabSel &ts, int s0, int s1, double fr, int p, double &g, double &jn)
 {
-    size_t i0 = (size_t)s0 * ts.NPHI + p, i1 = (size_t)s1 * ts.NPHI + p;
-    double g0 = ts.w00 * __ldg(ts.n00 + i0) + ts.w01 * __ldg(ts.n01 + i0) + ts.w10 * __ldg(ts.n10 + i0) +
-                ts.w11 * __ldg(ts.n11 + i0);
-    double g1 = ts.w00 * __ldg(ts.n00 + i1) + ts.w01 * __ldg(ts.n01 + i1) + ts.w10 * __ldg(ts.n10 + i1) +
-                ts.w11 * __ldg(ts.n11 + i1);
-    size_t q0 = ts.plane + i0, q1 = ts.plane + i1;
-    double j0 = ts.w00 * __ldg(ts.n00 + q0) + ts.w01 * __ldg(ts.n01 + q0) + ts.w10 * __ldg(ts.n10 + q0) +
-                ts.w11 * __ldg(ts.n11 + q0);
-    double j1 = ts.w00 * __ldg(ts.n00 + q1) + ts.w01 * __ldg(ts.n01 + q1) + ts.w10 * __ldg(ts.n10 + q1) +
-                ts.w11 * __ldg(ts.n11 + q1);
+    // one 16-byte load per node and row brings g and Jn together (the tables are float32 widened once at upload)
+    const int i0 = s0 * ts.NPHI + p, i1 = s1 * ts.NPHI + p;
+    const double2 a0 = __ldg(ts.n00 + i0), b0 = __ldg(ts.n01 + i0), c0 = __ldg(ts.n10 + i0), d0 = __ldg(ts.n11 + i0);
+    const double2 a1 = __ldg(ts.n00 + i1), b1 = __ldg(ts.n01 + i1), c1 = __ldg(ts.n10 + i1), d1 = __ldg(ts.n11 + i1);
+    double g0 = ts.w00 * a0.x + ts.w01 * b0.x + ts.w10 * c0.x + ts.w11 * d0.x;
+    double g1 = ts.w00 * a1.x + ts.w01 * b1.x + ts.w10 * c1.x + ts.w11 * d1.x;
+    double j0 = ts.w00 * a0.y + ts.w01 * b0.y + ts.w10 * c0.y + ts.w11 * d0.y;
+    double j1 = ts.w00 * a1.y + ts.w01 * b1.y + ts.w10 * c1.y + ts.w11 * d1.y;
     g = g0 + fr * (g1 - g0);
     jn = j0 + fr * (j1 - j0);
 }
@@ -243,11 +241,12 @@ __device__ inline void warp_deposit(double *Hs, int K_LO, int nH, double sa, dou
 // rings) to Hs.  alpha, beta, rb: kyconv's broken power-law emissivity; zs: redshift in units of shift bins.
 __device__ inline void warp_build_rings(double *Hs, int K_LO, int nH, const TabSel &ts, double r1, double r2, double dlnE,
                                         int nsub, int m_begin, int m_step, double alpha, double beta, double rb, double zs,
-                                        double weight, int &kmin_out, int &kmax_out)
+                                        double weight, int &kmin_out, int &kmax_out, const RingGeo *single = nullptr)
 {
+    // single: geometry of the annulus' only ring when the caller has it already (nsub == 1, warp-uniform)
     const int lane = threadIdx.x & 31;
     const int NP = ts.NPHI, nq = NP >> 5;
-    const double lnr = log(r2 / r1);
+    const double lnr = single ? 0.0 : log(r2 / r1);
     const double dphi = 2 * RGK_PI / NP;
     const double inv_dlnE = 1.0 / dlnE; // shift in bins = ln g / dlnE, as one multiplication per sample
     int kf_min = RG_IMAX, kl_max = -RG_IMAX;
@@ -256,10 +255,11 @@ __device__ inline void warp_build_rings(double *Hs, int K_LO, int nH, const TabS
         const int nr = n_mine - m0 < 32 ? n_mine - m0 : 32;
         RingGeo geo;
         geo.A = 0; geo.fr = 0; geo.s0 = 0; geo.s1 = 0;
-        if (lane < nr) geo = rg_ring_geo(ts, r1, r2, lnr, m_begin + (m0 + lane) * m_step, nsub, alpha, beta, rb);
+        if (single) geo = *single;
+        else if (lane < nr) geo = rg_ring_geo(ts, r1, r2, lnr, m_begin + (m0 + lane) * m_step, nsub, alpha, beta, rb);
         for (int m = 0; m < nr; m++) {
-            const double A = __shfl_sync(RG_FULL, geo.A, m), fr = __shfl_sync(RG_FULL, geo.fr, m);
-            const int s0 = __shfl_sync(RG_FULL, geo.s0, m), s1 = __shfl_sync(RG_FULL, geo.s1, m);
+            const double A = single ? geo.A : __shfl_sync(RG_FULL, geo.A, m), fr = single ? geo.fr : __shfl_sync(RG_FULL, geo.fr, m);
+            const int s0 = single ? geo.s0 : __shfl_sync(RG_FULL, geo.s0, m), s1 = single ? geo.s1 : __shfl_sync(RG_FULL, geo.s1, m);
             double g, jn;
             rg_ring_sample(ts, s0, s1, fr, lane, g, jn);
             double s_cur = log(g) * inv_dlnE + zs, w_cur = jn * g * g * g;
