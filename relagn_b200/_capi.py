@@ -223,21 +223,27 @@ class Context:
 
     # ---- batched evaluation ----
     def eval_batch_host(self, params, model=MODEL_RELAGN, rel=True, components=False, dr_dex=50.0, out=None,
-                        attrs=True, fp32=False):
-        """params: [P, 15] (relqso: first 7 columns used).  Returns (out [P, nE] or [P, 4, nE], attrs [P, 24])."""
+                        attrs=True, fp32=False, attrs_out=None):
+        """params: [P, 15] (relqso: first 7 columns used).  Returns (out [P, nE] or [P, 4, nE], attrs [P, 24]).
+        out / attrs_out: caller-owned result buffers (e.g. pinned memory) to fill instead of fresh arrays."""
         p = np.asarray(params, dtype=np.float64)
         if p.ndim == 1:
             p = p[None, :]
         P = p.shape[0]
-        pp = np.zeros((P, NPAR))
-        pp[:, :p.shape[1]] = p
+        if p.shape[1] != NPAR or not p.flags.c_contiguous:
+            pp = np.zeros((P, NPAR))
+            pp[:, :p.shape[1]] = p
+            p = pp
         flags = (FLAG_REL if rel else 0) | (FLAG_COMPONENTS if components else 0) | (FLAG_FP32 if fp32 else 0)
         shape = (P, 4, self.nE) if components else (P, self.nE)
         if out is None:
             out = np.empty(shape)
         assert out.shape == shape and out.dtype == np.float64 and out.flags.c_contiguous
-        at = np.zeros((P, NATTR)) if attrs else None
-        self._check(self.lib.rg_eval_batch_host(self.h, _d(pp), P, int(model), float(dr_dex), flags, _d(out),
+        at = None
+        if attrs:
+            at = attrs_out if attrs_out is not None else np.empty((P, NATTR))
+            assert at.shape == (P, NATTR) and at.dtype == np.float64 and at.flags.c_contiguous
+        self._check(self.lib.rg_eval_batch_host(self.h, _d(p), P, int(model), float(dr_dex), flags, _d(out),
                                                 _d(at) if attrs else None))
         return out, at
 

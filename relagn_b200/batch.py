@@ -71,7 +71,8 @@ class BatchEvaluator:
     # ---- host path (the call a user of the reference's class makes, batched) ----
     def evaluate(self, params, rel=True, components=False, fp32=False):
         """params: array-like [P, n] on the host.  Returns (spectra ndarray [P, nE] or [P, 4, nE] in W/Hz,
-        attrs ndarray [P, 24]).  Stages through pinned memory; H2D and D2H happen inside this call."""
+        attrs ndarray [P, 24]).  Stages through pinned memory; H2D and D2H happen inside this call.  The returned
+        arrays are views of the evaluator's pinned staging buffers: copy them before the next call if both are needed."""
         p = np.asarray(params, dtype=np.float64)
         if p.ndim == 1:
             p = p[None, :]
@@ -83,12 +84,16 @@ class BatchEvaluator:
             self._pin_in = torch.zeros((P, _capi.NPAR), dtype=torch.float64).pin_memory()
         if self._pin_out is None or self._pin_out.numel() < P * ncomp * self.nE:
             self._pin_out = torch.empty(P * ncomp * self.nE, dtype=torch.float64).pin_memory()
+        if getattr(self, "_pin_attr", None) is None or self._pin_attr.shape[0] < P:
+            self._pin_attr = torch.empty((P, _capi.NATTR), dtype=torch.float64).pin_memory()
         pin = self._pin_in[:P]
-        pin.zero_()
+        if p.shape[1] != _capi.NPAR:
+            pin.zero_()
         pin[:, :p.shape[1]] = torch.from_numpy(p)
         out = self._pin_out[:P * ncomp * self.nE].view((P, 4, self.nE) if components else (P, self.nE))
         out_np, at = self.ctx.eval_batch_host(pin.numpy(), model=self.model, rel=rel, components=components,
-                                              dr_dex=self.dr_dex, out=out.numpy(), fp32=fp32)
+                                              dr_dex=self.dr_dex, out=out.numpy(), fp32=fp32,
+                                              attrs_out=self._pin_attr[:P].numpy())
         return out_np, at
 
 
@@ -151,7 +156,8 @@ class BatchEvaluator:
         if getattr(self, "_pin_stat", None) is None or self._pin_stat.numel() < P:
             self._pin_stat = torch.empty(P, dtype=torch.float64).pin_memory()
         pin = self._pin_in[:P]
-        pin.zero_()
+        if p.shape[1] != _capi.NPAR:
+            pin.zero_()
         pin[:, :p.shape[1]] = torch.from_numpy(p)
         return self.ctx.eval_fitstat_host(pin.numpy(), model=self.model, rel=rel, dr_dex=self.dr_dex, fp32=fp32,
                                           out=self._pin_stat[:P].numpy())

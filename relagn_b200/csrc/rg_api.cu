@@ -272,11 +272,11 @@ extern "C" int rg_set_grid(rg_ctx *c, const double *eb, int nE)
     for (int j = 0; j < nE; j++)
         if (!(eb[j + 1] > eb[j]) || !(eb[j] > 0)) return rg_set_error(RG_E_ARG, "bin edges must be positive and ascending");
     RG_CUDA_OK(cudaSetDevice(c->device));
-    const int NA = 10; // arrays of nE
+    const int NA = 11; // arrays of nE
     std::vector<double> h((size_t)NA * nE + 3 * RG_NEXT, 0.0);
     double *Egrid = &h[0], *dE = &h[(size_t)nE], *nu = &h[(size_t)2 * nE], *hnu = &h[(size_t)3 * nE],
            *bbpre = &h[(size_t)4 * nE], *wt = &h[(size_t)5 * nE], *e511 = &h[(size_t)6 * nE], *ear2 = &h[(size_t)7 * nE],
-           *lgE = &h[(size_t)8 * nE], *kph = &h[(size_t)9 * nE];
+           *lgE = &h[(size_t)8 * nE], *kph = &h[(size_t)9 * nE], *rear2 = &h[(size_t)10 * nE];
     double *x_hnu = &h[(size_t)NA * nE], *x_bbpre = x_hnu + RG_NEXT, *x_wt = x_bbpre + RG_NEXT;
     for (int j = 0; j < nE; j++) {
         dE[j] = eb[j + 1] - eb[j];
@@ -288,6 +288,7 @@ extern "C" int rg_set_grid(rg_ctx *c, const double *eb, int nE)
         ear2[j] = Egrid[j] * Egrid[j];
         lgE[j] = log10(Egrid[j]);
         kph[j] = dE[j] / (RGK_H * Egrid[j]); // W/Hz -> photons/s per bin (relagn.py:509-516 times dE)
+        rear2[j] = 1.0 / ear2[j];
     }
     int n_ext = Egrid[0] < 1e-4 ? RG_NEXT : 0; // relagn.py:868
     std::vector<double> xs; // abscissae of np.trapz: [extension, nu]
@@ -328,6 +329,7 @@ extern "C" int rg_set_grid(rg_ctx *c, const double *eb, int nE)
     g.bbpre = d + (size_t)4 * nE; g.wt = d + (size_t)5 * nE; g.e511 = d + (size_t)6 * nE; g.ear2 = d + (size_t)7 * nE;
     g.lgE = d + (size_t)8 * nE;
     c->d_kph = d + (size_t)9 * nE;
+    g.rear2 = d + (size_t)10 * nE;
     c->pos0_dirty = true;
     g.x_hnu = d + (size_t)NA * nE; g.x_bbpre = g.x_hnu + RG_NEXT; g.x_wt = g.x_bbpre + RG_NEXT;
     g.n_ext = n_ext; g.nE = nE; g.geometric = geometric; g.dlnE = dlnE;

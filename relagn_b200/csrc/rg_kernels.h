@@ -29,6 +29,7 @@ struct GridDesc {
     const double *e511;  // Egrid / 511                                pyNTHCOMP.py:70
     const double *ear2;  // Egrid^2                                    pyNTHCOMP.py:75
     const double *lgE;   // log10(Egrid): seeds the Kompaneets-grid cursor search
+    const double *rear2; // 1 / Egrid^2
     // low-frequency extension of disc_annuli (relagn.py:868-873), [RG_NEXT] when n_ext
     const double *x_hnu, *x_bbpre, *x_wt;
     int n_ext;

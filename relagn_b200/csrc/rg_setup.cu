@@ -495,7 +495,9 @@ nthcomp_interp_kernel(const SetRec *__restrict__ recs, const int2 *__restrict__ 
                       const double *__restrict__ header, GridDesc grid, double *__restrict__ farr)
 {
     __shared__ double s_p10[RG_NTH + 4];
+    __shared__ double s_rdp[RG_NTH + 4]; // 1 / (10^(0.02 (j+1)) - 10^(0.02 j)): the cell width of the x grid, per unit xmin
     for (int i = threadIdx.x; i < RG_NTH + 4; i += blockDim.x) s_p10[i] = p10tab[i];
+    for (int i = threadIdx.x; i < RG_NTH + 3; i += blockDim.x) s_rdp[i] = 1.0 / (p10tab[i + 1] - p10tab[i]);
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int sys = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -503,6 +505,9 @@ nthcomp_interp_kernel(const SetRec *__restrict__ recs, const int2 *__restrict__ 
     if (recs[syslist[sys].x].status != RG_S_OK) return;
     const double *hd = header + (size_t)sys * 4;
     const double xmin = hd[0], normfac = hd[1], lgx = hd[3];
+    const double rxmin = 1.0 / xmin;
+    // photon flux -> W/Hz (relagn.py:929-930) folded into the normalisation
+    const double outfac = (1.0 / RGK_KEV) * RGK_H;
     const int nth = (int)hd[2];
     const double *spt = sptot + (size_t)sys * RG_SPT_STRIDE;
     double *F = farr + (size_t)sys * grid.nE;
@@ -522,18 +527,20 @@ nthcomp_interp_kernel(const SetRec *__restrict__ recs, const int2 *__restrict__ 
             if (j <= nth) {
                 if (j > 0) {
                     const int jl = j - 1;
-                    const double xl = xmin * s_p10[jl], xh = xmin * s_p10[jl + 1];
+                    // linear interpolation inside the cell [xl, xh] (pyNTHCOMP.py:66-71); the division by the cell
+                    // width is a multiplication by (1 / xmin) (1 / (10^(0.02 (jl+1)) - 10^(0.02 jl)))
+                    const double xl = xmin * s_p10[jl];
                     const double sl = spt[jl], sh = spt[jl + 1];
-                    prim = sl + ((__ldg(grid.e511 + i) - xl) * (sh - sl) / (xh - xl));
+                    prim = sl + ((__ldg(grid.e511 + i) - xl) * (sh - sl)) * (rxmin * s_rdp[jl]);
                 } else prim = spt[0];
             }
-            pr = prim / __ldg(grid.ear2 + i);
+            pr = prim * __ldg(grid.rear2 + i); // prim / E^2 (pyNTHCOMP.py:75)
         }
         double pr_prev = __shfl_up_sync(0xffffffffu, pr, 1), e_prev = __shfl_up_sync(0xffffffffu, e, 1);
         if (lane == 0) { pr_prev = carry_pr; e_prev = carry_e; }
         if (i < nE) {
             const double ph = i > 0 ? (0.5 * (pr + pr_prev) * (e - e_prev) * normfac) : 0.0;
-            F[i] = ph * (1.0 / RGK_KEV) * RGK_H;
+            F[i] = ph * outfac;
         }
         carry_pr = __shfl_sync(0xffffffffu, pr, 31);
         carry_e = __shfl_sync(0xffffffffu, e, 31);
