@@ -49,14 +49,14 @@ int rg_spectrum_pick_NC(int nE)
     return 0;
 }
 
-// shared memory per CTA: [per-bin constants (R, NC <= 8)] [reduction scratch, item slot]
+// shared memory per CTA: [per-bin constants (R, NC <= 8)] [reduction scratch, item slot, hot ranges]
 //                        [per warp: transposed spectrum buffer (R) | histogram slot (double) | accumulators (R, NC > 4)]
 size_t rg_spectrum_smem_bytes(int NC, int nH, int HL, int HH, int warps, int fp32)
 {
     size_t rsz = fp32 ? 4 : 8;
     size_t w = 8 * (size_t)(HL + 32 * NC + HH) * rsz + (size_t)round_up2(nH + 24) * 8;
     if (NC > 4) w += 8 * (size_t)32 * NC * rsz; // accumulators (registers when NC <= 4)
-    size_t b = w * warps + 18 * 8;
+    size_t b = w * warps + (18 + 16) * 8;
     if (NC <= 8) b += NGRID * 8 * (size_t)32 * NC * rsz; // grid constants (global memory for the finest grids)
     return b;
 }
@@ -269,6 +269,7 @@ __global__ void __launch_bounds__(NC <= 4 ? (sizeof(R) == 4 ? 512 : 32 * RG_SPEC
     if (GS) smb += (size_t)NGRID * 8 * NCOL * sizeof(R);
     double *s_red = reinterpret_cast<double *>(smb); smb += 16 * sizeof(double);
     int *s_misc = reinterpret_cast<int *>(smb); smb += 2 * sizeof(double);
+    int *s_hot = reinterpret_cast<int *>(smb); smb += 16 * sizeof(double); // per warp: shift range of its hot histogram
     const size_t wd = 8 * (size_t)RS * sizeof(R) + (size_t)HSZ * sizeof(double) + (ACC_REG ? 0 : 8 * (size_t)NCOL * sizeof(R));
     unsigned char *const warp0 = smb;
     R *inT = reinterpret_cast<R *>(smb + wd * warp);                   // [8][RS]
@@ -361,8 +362,8 @@ __global__ void __launch_bounds__(NC <= 4 ? (sizeof(R) == 4 ? 512 : 32 * RG_SPEC
         for (int m0 = 0; m0 < n_rounds; m0 += 32) {
             // ---- prologue: lane m prepares this warp's annulus of round m0 + m: g = g_begin + warp + nwarps (m0 + m),
             //      counted top-down through disc [r_w, r_out], warm [r_h, r_w], hot [risco, r_h] ----
-            double p_r1 = 0, p_r2 = 0, p_s1 = 0, p_s2 = 0, p_geo = 0;
-            int p_flag = 0, p_jz = nE, p_region = -1, p_loc = 0;
+            double p_s1 = 0, p_s2 = 0, p_geo = 0;
+            int p_flag = 0, p_jz = nE, p_region = -1, p_loc = 0, p_kmn = 0, p_nk = 0;
             {
                 const int g = g_begin + warp + nwarps * (m0 + lane);
                 if (m0 + lane < n_rounds && g < g_end) {
@@ -404,9 +405,12 @@ __global__ void __launch_bounds__(NC <= 4 ? (sizeof(R) == 4 ? 512 : 32 * RG_SPEC
                     // flat space (relagn.py:1013,1110,1370) / non-relativistic (relagn.py:1046,1143) area factor
                     p_geo = 2 * RGK_PI * 2 * rmid * (r2 - r1);
                     if (region != 2) p_geo = p_geo * r.cosinc / 0.5;
-                    p_r1 = r1; p_r2 = r2;
                     p_flag = (rel && lo <= 3 && hi <= 3) ? 1 : 0; // relagn.py:992
                     p_region = region; p_loc = a;
+                    if (p_flag) { // support of the annulus' shift histogram (slot 0 of its arena row)
+                        const int2 hd = __ldg(reinterpret_cast<const int2 *>(A.hist + (size_t)(r.ann_base + g) * A.hstride));
+                        p_kmn = hd.x; p_nk = hd.y;
+                    }
                 }
             }
             const int mt = n_rounds - m0 < 32 ? n_rounds - m0 : 32;
@@ -415,7 +419,6 @@ __global__ void __launch_bounds__(NC <= 4 ? (sizeof(R) == 4 ? 512 : 32 * RG_SPEC
                 const int region = __shfl_sync(FULL, p_region, mi);
                 if (region < 0) continue; // no annulus left for this warp in this round
                 if (region == 2 && !rel) continue; // non-relativistic hot component needs no annuli (relagn.py:1387-1401)
-                const double r1 = __shfl_sync(FULL, p_r1, mi), r2 = __shfl_sync(FULL, p_r2, mi);
                 const double s1 = __shfl_sync(FULL, p_s1, mi), s2 = __shfl_sync(FULL, p_s2, mi);
                 const double geo = __shfl_sync(FULL, p_geo, mi);
                 const bool conv = __shfl_sync(FULL, p_flag, mi) != 0;
@@ -425,13 +428,24 @@ __global__ void __launch_bounds__(NC <= 4 ? (sizeof(R) == 4 ? 512 : 32 * RG_SPEC
                     acc.store(part_w + (size_t)cur_region * nE, nE, true);
                     cur_region = region;
                 }
-                int kmn = 0, kmx = -1;
+                // The annulus' shift histogram (built by hist_kernel) is requested here and installed in the warp's
+                // slot only when the convolution needs it, so that the loads fly during the local-spectrum evaluation.
+                // disc / warm: the slot is re-zeroed where the previous annulus touched it.  hot: the slot turns into
+                // the region histogram -- every hot annulus adds its own, weighted by the annulus luminosity (the warp
+                // meets its hot annuli last, so the slot is free by then).
+                int kmn = 0, kmx = -1, nk = 0;
+                const double *hrow = nullptr;
+                double h0 = 0.0, h1 = 0.0;
                 if (conv) {
-                    // disc / warm: re-zero what the previous annulus touched, then fetch this annulus' histogram
-                    // (built by hist_kernel).  hot: the slot turns into the region histogram -- every hot annulus adds
-                    // its own, weighted by the annulus luminosity (the warp meets its hot annuli last, so the slot is
-                    // free by then)
-                    if (region != 2 || !hot_any_conv) {
+                    const int g = (region == 0 ? 0 : (region == 1 ? g_warm0 : g_hot0)) + loc;
+                    hrow = A.hist + (size_t)(r.ann_base + g) * A.hstride + 1;
+                    kmn = __shfl_sync(FULL, p_kmn, mi); nk = __shfl_sync(FULL, p_nk, mi);
+                    kmx = kmn + nk - 1;
+                    if (lane < nk) h0 = __ldg(hrow + lane);
+                    if (lane + 32 < nk) h1 = __ldg(hrow + lane + 32);
+                }
+                auto install_hist = [&](bool fresh, double wgt) {
+                    if (fresh) {
                         for (int k = hz_min + lane; k <= hz_max; k += 32) {
                             int q = k - K_LO;
                             if (q >= 0 && q < nH) Hslot[8 + q] = 0.0;
@@ -439,23 +453,18 @@ __global__ void __launch_bounds__(NC <= 4 ? (sizeof(R) == 4 ? 512 : 32 * RG_SPEC
                         hz_min = IMAX; hz_max = -IMAX;
                         __syncwarp();
                     }
-                    const int g = (region == 0 ? 0 : (region == 1 ? g_warm0 : g_hot0)) + loc;
-                    const double *row = A.hist + (size_t)(r.ann_base + g) * A.hstride;
-                    const int2 hd = __ldg(reinterpret_cast<const int2 *>(row));
-                    kmn = hd.x; kmx = hd.x + hd.y - 1;
                     double *Hd = Hslot + 8 + (kmn - K_LO);
-                    if (region == 2) {
-                        for (int k = lane; k < hd.y; k += 32) Hd[k] += s1 * __ldg(row + 1 + k);
-                    } else {
-                        for (int k = lane; k < hd.y; k += 32) Hd[k] = __ldg(row + 1 + k);
-                    }
+                    if (lane < nk) Hd[lane] += wgt * h0;
+                    if (lane + 32 < nk) Hd[lane + 32] += wgt * h1;
+                    for (int k = lane + 64; k < nk; k += 32) Hd[k] += wgt * __ldg(hrow + k);
                     __syncwarp();
-                    if (kmn <= kmx) {
+                    if (nk > 0) {
                         hz_min = kmn < hz_min ? kmn : hz_min;
                         hz_max = kmx > hz_max ? kmx : hz_max;
-                        st_w += (unsigned long long)(kmx - kmn + 1); st_n += 1;
+                        st_w += (unsigned long long)nk; st_n += 1;
                     }
-                }
+                };
+                if (conv && region == 2) install_hist(!hot_any_conv, s1);
                 if (region == 2) {
                     hot_mine = true;
                     if (conv) {
@@ -514,6 +523,7 @@ __global__ void __launch_bounds__(NC <= 4 ? (sizeof(R) == 4 ? 512 : 32 * RG_SPEC
                 const double radiance = (double)warp_sum(part);
                 __syncwarp();
                 // Lnu = norm * (B / radiance), zero when the annulus emits nothing (relagn.py:885-889, 933-937)
+                if (conv) install_hist(true, 1.0);
                 if (radiance != 0) {
                     if (conv) {
                         const double scale = s2 / radiance;
@@ -545,9 +555,65 @@ __global__ void __launch_bounds__(NC <= 4 ? (sizeof(R) == 4 ? 512 : 32 * RG_SPEC
             }
         }
 
-        // ---- hot region: one convolution per warp over the histograms it collected ----
+        // ---- hot region.  Every warp holds the weighted histogram of its own hot annuli; the region is linear in
+        //      its one spectral shape, so the CTA sums those histograms (fixed warp order) and does ONE convolution,
+        //      shared between the warps by tap range -- instead of one full convolution per warp ----
         const bool nonrel_hot = !rel && owns_hot0 && warp == 0; // (Ldiss + Lseed) * Fnu / trapz(Fnu), relagn.py:1387-1401
-        if ((rel && hot_mine) || nonrel_hot) {
+        int t_lo = 0, t_hi = -1; // this warp's share of the taps
+        bool cta_conv = false;
+        // the summed histogram carries the region's luminosity (up to ~1e40 W): it is stored in units of Ldiss + Lseed so
+        // that the single-precision variant can hold it, and the convolution is scaled back in double
+        const double Lhot = (r.Ldiss + r.Lseed) > 0 ? r.Ldiss + r.Lseed : 1.0;
+        double conv_unit = 1.0;
+        if (rel && hot_here) {   // (item-level condition: the same for every warp of the CTA)
+            if (lane == 0) {
+                s_hot[2 * warp] = hot_any_conv ? hk_min : IMAX;
+                s_hot[2 * warp + 1] = hot_any_conv ? hk_max : -IMAX;
+            }
+            __syncthreads();
+            int ck_min = IMAX, ck_max = -IMAX;
+            for (int w = 0; w < nwarps; w++) {
+                ck_min = s_hot[2 * w] < ck_min ? s_hot[2 * w] : ck_min;
+                ck_max = s_hot[2 * w + 1] > ck_max ? s_hot[2 * w + 1] : ck_max;
+            }
+            if (ck_min < K_LO) ck_min = K_LO;
+            if (ck_max > K_LO + nH - 1) ck_max = K_LO + nH - 1;
+            const int T = (ck_max - ck_min + nwarps) / nwarps; // taps per warp
+            // (the sums below sit in 8 registers per lane: wider shares -- the finest grids run 2 warps per CTA over
+            //  > 1000 shifts -- keep one convolution per warp)
+            cta_conv = ck_min <= ck_max && T <= 256;
+            if (!cta_conv && hot_any_conv) { t_lo = hk_min; t_hi = hk_max; }
+            if (cta_conv) {
+                t_lo = ck_min + warp * T;
+                t_hi = t_lo + T - 1 < ck_max ? t_lo + T - 1 : ck_max;
+                double hs[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    hs[q] = 0.0;
+                    const int k = t_lo + lane + 32 * q;
+                    if (k <= t_hi)
+                        for (int w = 0; w < nwarps; w++)
+                            if (s_hot[2 * w] <= s_hot[2 * w + 1]) // warps without hot annuli hold disc / warm leftovers
+                                hs[q] += reinterpret_cast<const double *>(reinterpret_cast<const R *>(warp0 + wd * w) + 8 * (size_t)RS)[8 + k - K_LO];
+                }
+                __syncthreads(); // every warp has read the others' slots
+                for (int k = hz_min + lane; k <= hz_max; k += 32) {
+                    int q = k - K_LO;
+                    if (q >= 0 && q < nH) Hslot[8 + q] = 0.0;
+                }
+                hz_min = IMAX; hz_max = -IMAX;
+                __syncwarp();
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    const int k = t_lo + lane + 32 * q;
+                    if (k <= t_hi) Hslot[8 + k - K_LO] = hs[q] * (1.0 / Lhot);
+                }
+                conv_unit = Lhot;
+                if (t_lo <= t_hi) { hz_min = t_lo; hz_max = t_hi; }
+                __syncwarp();
+            }
+        }
+        if ((rel && (hot_mine || t_lo <= t_hi)) || nonrel_hot) {
             if (comps && cur_region != 2) {
                 acc.store(part_w + (size_t)cur_region * nE, nE, true);
                 cur_region = 2;
@@ -563,12 +629,13 @@ __global__ void __launch_bounds__(NC <= 4 ? (sizeof(R) == 4 ? 512 : 32 * RG_SPEC
             }
             __syncwarp();
             const double Lum = r.Ldiss + r.Lseed;
+            const bool conv_here = rel && t_lo <= t_hi;
             for (int ch = 0; ch < NC; ch++) {
                 const int col = 32 * ch + lane;
                 R tmp[8];
 #pragma unroll
                 for (int c = 0; c < 8; c++) tmp[c] = 0;
-                if (rel && hot_any_conv) convolve8<R>(Hslot + 8, K_LO, nH, hk_min, hk_max, inBase + 32 * ch, RS, tmp);
+                if (conv_here) convolve8<R>(Hslot + 8, K_LO, nH, t_lo, t_hi, inBase + 32 * ch, RS, tmp);
                 R v[8];
 #pragma unroll
                 for (int c = 0; c < 8; c++) {
@@ -577,8 +644,8 @@ __global__ void __launch_bounds__(NC <= 4 ? (sizeof(R) == 4 ? 512 : 32 * RG_SPEC
                         // the buffer holds F * pk and pk * upk = 4; F / shape_int: 0/0 -> NaN as the reference (:1316)
                         double F = (double)inBase[c * RS + 32 * ch] * (double)G.upk(c, col) * 0.25;
                         if (rel) {
-                            double vv = Sflat * (F / shape_int);
-                            if (hot_any_conv) vv += (((double)tmp[c] / shape_int) * (double)G.upk(c, col)) / cosfac; // relagn.py:1362
+                            double vv = hot_mine ? Sflat * (F / shape_int) : 0.0;
+                            if (conv_here) vv += ((((double)tmp[c] * conv_unit) / shape_int) * (double)G.upk(c, col)) / cosfac; // relagn.py:1362
                             v[c] = (R)vv;
                         } else {
                             v[c] = (R)(Lum * (F / shape_int));
