@@ -232,7 +232,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from relagn_b200 import _capi
-    from relagn_b200.batch import BatchEvaluator
+    from relagn_b200.batch import BatchEvaluator, evaluate_sharded
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -257,9 +257,13 @@ def run_ours(args):
         gathered = [torch.empty((P, NE), dtype=torch.float64, device=dev) for _ in range(world)]
 
     def step():
-        ev.evaluate_device(params, rel=True, out=out, attrs=attrs, fp32=args.fp32)
-        if world > 1:
-            dist.gather(out, gathered, dst=0)
+        if world > 1 and not args.fp32:
+            # pieces of the shard are gathered to rank 0 while the next piece is computed (batch.evaluate_sharded)
+            evaluate_sharded(ev, params, rel=True, gather_dst=0, out=out, attrs=attrs, gathered=gathered)
+        else:
+            ev.evaluate_device(params, rel=True, out=out, attrs=attrs, fp32=args.fp32)
+            if world > 1:
+                dist.gather(out, gathered, dst=0)
 
     def barrier():
         if world > 1:

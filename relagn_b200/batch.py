@@ -170,20 +170,59 @@ def shard_bounds(P, world, rank):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def evaluate_sharded(evaluator, params_local, rel=True, gather_dst=0, group=None):
+def evaluate_sharded(evaluator, params_local, rel=True, gather_dst=0, group=None, pieces=4, out=None, attrs=None,
+                     gathered=None):
     """One process per GPU: every rank evaluates its own shard (device tensor [P_local, 15]); the only collective
-    is the final gather of the spectra to `gather_dst` over NCCL (gather_dst=None: no gather).
+    is the gather of the spectra to `gather_dst` over NCCL (gather_dst=None: no gather).  The shard is evaluated in
+    `pieces` contiguous pieces and the gather of piece i is issued on a side stream while piece i+1 is computed, so
+    only the last piece's transfer is exposed.  out / attrs / gathered: optional preallocated result tensors
+    ([P_local, nE], [P_local, 24], list of world x [P_local, nE] on the destination rank).
     Returns (local_out, gathered or None)."""
     import torch.distributed as dist
-    out, _ = evaluator.evaluate_device(params_local, rel=rel)
-    if gather_dst is None or not dist.is_initialized() or dist.get_world_size(group) == 1:
-        return out, None
+    P = params_local.shape[0]
+    multi = gather_dst is not None and dist.is_initialized() and dist.get_world_size(group) > 1
+    if not multi:
+        if out is not None:
+            evaluator.evaluate_device(params_local, rel=rel, out=out, attrs=attrs)
+            return out, None
+        return evaluator.evaluate_device(params_local, rel=rel)[0], None
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    gathered = None
-    if rank == gather_dst:
-        gathered = [torch.empty_like(out) for _ in range(world)]
-    dist.gather(out, gathered, dst=gather_dst, group=group)
-    return out, gathered
+    # piece boundaries on multiples of the library's 16384-set chunk
+    n_chunks = max(1, (P + 16383) // 16384)
+    pieces = max(1, min(int(pieces), n_chunks))
+    edges = [min(P, ((n_chunks * i) // pieces) * 16384) for i in range(pieces)] + [P]
+    cuda = params_local.is_cuda
+    side = torch.cuda.Stream(device=params_local.device) if cuda else None
+    outs, works = [], []
+    for lo, hi in zip(edges[:-1], edges[1:]):
+        if hi <= lo:
+            continue
+        if out is not None:
+            evaluator.evaluate_device(params_local[lo:hi], rel=rel, out=out[lo:hi],
+                                      attrs=None if attrs is None else attrs[lo:hi])
+            piece = out[lo:hi]
+        else:
+            piece = evaluator.evaluate_device(params_local[lo:hi], rel=rel)[0]
+            outs.append(piece)
+        if rank == gather_dst and gathered is None:
+            gathered = [torch.empty((P,) + tuple(piece.shape[1:]), dtype=piece.dtype, device=piece.device)
+                        for _ in range(world)]
+        dst_views = [g[lo:hi] for g in gathered] if rank == gather_dst else None
+        if cuda:
+            done = torch.cuda.Event()
+            done.record()
+            with torch.cuda.stream(side):
+                side.wait_event(done)
+                works.append(dist.gather(piece, dst_views, dst=gather_dst, group=group, async_op=True))
+        else:
+            dist.gather(piece, dst_views, dst=gather_dst, group=group)
+    for w in works:
+        w.wait()
+    if cuda:
+        torch.cuda.current_stream(params_local.device).wait_stream(side)
+    if out is None:
+        out = outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
+    return out, gathered if rank == gather_dst else None
 
 
 def fitstat_sharded(evaluator, params_local, rel=True, gather_dst=0, group=None):

@@ -187,7 +187,7 @@ __device__ inline void warp_deposit(double *Hs, int K_LO, int nH, double sa, dou
     const double kf = floor(lo);
     const int kfirst = (int)kf;
     const int nb = point ? 2 : (int)floor(hi) + 1 - kfirst + 1;
-    const double inv = point ? 0.0 : W / len;
+    const double inv = point ? 0.0 : W * __drcp_rn(len); // len >= 1e-12: the plain reciprocal is safe
     kf_min = kfirst < kf_min ? kfirst : kf_min;
     {
         int kl = kfirst + nb - 1;
@@ -262,6 +262,7 @@ __device__ inline void warp_build_rings(double *Hs, int K_LO, int nH, const TabS
             const int s0 = single ? geo.s0 : __shfl_sync(RG_FULL, geo.s0, m), s1 = single ? geo.s1 : __shfl_sync(RG_FULL, geo.s1, m);
             double g, jn;
             rg_ring_sample(ts, s0, s1, fr, lane, g, jn);
+            const double cW = 0.5 * dphi * A * weight; // segment weight = (w_t + w_{t+1}) cW
             double s_cur = log(g) * inv_dlnE + zs, w_cur = jn * g * g * g;
             const double s_first = __shfl_sync(RG_FULL, s_cur, 0), w_first = __shfl_sync(RG_FULL, w_cur, 0);
             for (int q = 0; q < nq; q++) {
@@ -273,7 +274,7 @@ __device__ inline void warp_build_rings(double *Hs, int K_LO, int nH, const TabS
                 } else { sn0 = s_first; wn0 = w_first; }
                 double sb = __shfl_down_sync(RG_FULL, s_cur, 1), wb = __shfl_down_sync(RG_FULL, w_cur, 1);
                 if (lane == 31) { sb = sn0; wb = wn0; }
-                const double W = 0.5 * (w_cur + wb) * dphi * A * weight;
+                const double W = (w_cur + wb) * cW;
                 warp_deposit(Hs, K_LO, nH, s_cur, sb, W, kf_min, kl_max);
                 s_cur = s_nxt; w_cur = w_nxt;
             }

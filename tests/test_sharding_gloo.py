@@ -4,6 +4,7 @@ import os
 import socket
 
 import numpy as np
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -53,11 +54,12 @@ def test_shard_bounds_cover_everything():
             assert max(sizes) - min(sizes) <= 1
 
 
-def test_two_rank_gather_gloo():
+@pytest.mark.parametrize("P", [10, 80000])  # 80000: three 16384-aligned pieces per rank, gathered piece by piece
+def test_two_rank_gather_gloo(P):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    P = 10  # equal shards: dist.gather needs equal sizes (the driver pads otherwise)
+    # equal shards: dist.gather needs equal sizes (the driver pads otherwise)
     procs = [ctx.Process(target=_worker, args=(r, 2, port, P, q)) for r in range(2)]
     for p in procs:
         p.start()
