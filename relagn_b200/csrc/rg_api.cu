@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <vector>
 
 #include "rg_kernels.h"
@@ -139,8 +140,10 @@ extern "C" int rg_ctx_create(int device, rg_ctx **out)
     RG_CUDA_OK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     RG_CUDA_OK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     // 10^(0.02 j) with the host libm, exactly as the reference's x grid (pyNTHCOMP.py:112-114)
-    std::vector<double> p10(RG_NTH + 4);
+    // followed by the reciprocal cell widths 1 / (10^(0.02 (j+1)) - 10^(0.02 j)) the interpolation kernel multiplies by
+    std::vector<double> p10(2 * (RG_NTH + 4), 0.0);
     for (int j = 0; j < RG_NTH + 4; j++) p10[j] = pow(10.0, j * 0.02);
+    for (int j = 0; j < RG_NTH + 3; j++) p10[RG_NTH + 4 + j] = 1.0 / (p10[j + 1] - p10[j]);
     RG_CUDA_OK(cudaMalloc(&c->d_p10, p10.size() * sizeof(double)));
     RG_CUDA_OK(cudaMemcpy(c->d_p10, p10.data(), p10.size() * sizeof(double), cudaMemcpyHostToDevice));
     RG_CUDA_OK(cudaMalloc(&c->d_counter, 2 * sizeof(int)));
@@ -554,24 +557,47 @@ extern "C" int rg_kyconv(rg_ctx *c, const double *eb, int nE, const double *par,
 // B2: batched evaluation
 static int ensure_dev(double **p, size_t *have, size_t need);
 
-static int ensure_batch_scratch(rg_ctx *c, int model)
+// Chunk of sets one setup / nthcomp / hist / spectrum launch sequence covers.  Larger chunks amortise the host
+// round trip after the setup kernel and the launch tails (65 536 instead of 16 384: +4.7 % on C4); the arenas scale
+// with the chunk (65 536 sets at nE = 1000: 19 GB of Kompaneets solutions, 21 GB of Comptonised spectra, <= 15 GB of
+// shift histograms -- sized for the 180 GB of a B200), so small batches get small arenas.
+#define RG_CHUNK_MAX 65536
+static int pick_chunk_sets(int P)
 {
-    if (!c->d_recs) {
-        // sized once: chunk of sets, arena of Kompaneets systems, persistent nthcomp grid
-        c->chunk_sets = 16384;
-        c->sys_cap = c->chunk_sets * 40;
+    int cap = RG_CHUNK_MAX;
+    if (const char *e = getenv("RG_CHUNK_SETS")) { // tuning knob: upper bound of the chunk
+        int v = atoi(e);
+        if (v >= 1024 && v <= 131072) cap = v;
+    }
+    int want = 4096;
+    while (want < P && want < cap) want *= 4;
+    return std::min(want, cap);
+}
+
+static int ensure_batch_scratch(rg_ctx *c, int model, int P)
+{
+    if (!c->d_sc) { // persistent nthcomp grid and its scratch planes: sized by the machine, not by the batch
         c->nth_threads = c->sm_count * 5 * 128;
-        RG_CUDA_OK(cudaMalloc(&c->d_recs, (size_t)c->chunk_sets * sizeof(SetRec)));
-        RG_CUDA_OK(cudaMalloc(&c->d_syslist, (size_t)c->sys_cap * sizeof(int2)));
-        RG_CUDA_OK(cudaMalloc(&c->d_sptot, (size_t)c->sys_cap * RG_SPT_STRIDE * sizeof(double)));
-        RG_CUDA_OK(cudaMalloc(&c->d_header, (size_t)c->sys_cap * 4 * sizeof(double)));
         RG_CUDA_OK(cudaMalloc(&c->d_sc, (size_t)3 * RG_NTH * c->nth_threads * sizeof(double)));
         RG_CUDA_OK(cudaMalloc(&c->d_queue, 2 * sizeof(int)));
     }
-    if (c->farr_nE != c->nE) { // Comptonised spectra on the grid: [farr_cap][nE], at most ~6 GB
+    const int want = pick_chunk_sets(P);
+    if (want > c->chunk_sets) { // grow: per-set records, arena of Kompaneets systems
+        free_dev(c->d_recs); free_dev(c->d_syslist); free_dev(c->d_sptot); free_dev(c->d_header); free_dev(c->d_rq);
+        free_dev(c->d_farr);
+        c->d_recs = nullptr; c->d_syslist = nullptr; c->d_sptot = c->d_header = c->d_farr = c->d_rq = nullptr;
+        c->farr_nE = 0; c->chunk_sets = 0;
+        c->sys_cap = want * 40;
+        RG_CUDA_OK(cudaMalloc(&c->d_recs, (size_t)want * sizeof(SetRec)));
+        RG_CUDA_OK(cudaMalloc(&c->d_syslist, (size_t)c->sys_cap * sizeof(int2)));
+        RG_CUDA_OK(cudaMalloc(&c->d_sptot, (size_t)c->sys_cap * RG_SPT_STRIDE * sizeof(double)));
+        RG_CUDA_OK(cudaMalloc(&c->d_header, (size_t)c->sys_cap * 4 * sizeof(double)));
+        c->chunk_sets = want;
+    }
+    if (c->farr_nE != c->nE) { // Comptonised spectra on the grid: [farr_cap][nE], 6 GB per 16 384 sets of the chunk
         free_dev(c->d_farr);
         c->d_farr = nullptr; c->farr_nE = 0;
-        size_t cap = (size_t)6e9 / ((size_t)c->nE * sizeof(double));
+        size_t cap = (size_t)(6e9 * (c->chunk_sets / 16384.0)) / ((size_t)c->nE * sizeof(double));
         c->farr_cap = (int)std::min<size_t>((size_t)c->sys_cap, std::max<size_t>(cap, 4096));
         RG_CUDA_OK(cudaMalloc(&c->d_farr, (size_t)c->farr_cap * c->nE * sizeof(double)));
         c->farr_nE = c->nE;
@@ -596,7 +622,7 @@ extern "C" int rg_eval_batch(rg_ctx *c, const double *d_params, int P, int model
         return rg_set_error(RG_E_GRID, "relativistic evaluation needs a geometric (log-spaced) energy grid");
     if (P == 0) return RG_OK;
     RG_CUDA_OK(cudaSetDevice(c->device));
-    RG_TRY(ensure_batch_scratch(c, model));
+    RG_TRY(ensure_batch_scratch(c, model, P));
     cudaStream_t st = (cudaStream_t)stream;
     const int nE = c->nE;
     const int NC = rg_spectrum_pick_NC(nE);
@@ -659,11 +685,11 @@ extern "C" int rg_eval_batch(rg_ctx *c, const double *d_params, int P, int model
                                c->rq_cap, attrs, st));
         RG_TRY(prof_end(c, 0, st));
         c->launches += model == RG_MODEL_RELQSO ? 2 : 1;
-        RG_CUDA_OK(cudaMemcpyAsync(c->h_counter, c->d_counter, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        RG_TRY(rg_launch_counters_out(c->d_counter, c->h_counter, st)); // zero-copy store, not a D2H copy
         RG_CUDA_OK(cudaStreamSynchronize(st));
         int nsys = c->h_counter[0];
         const size_t hist_need = rel ? (size_t)c->h_counter[1] * (size_t)A.hstride : 0;
-        if (nsys > c->farr_cap || hist_need * sizeof(double) > (size_t)8e9) {
+        if (nsys > c->farr_cap || hist_need * sizeof(double) > (size_t)(8e9 * (c->chunk_sets / 16384.0))) {
             if (n == 1) return rg_set_error(RG_E_NOMEM, "one parameter set needs %d Kompaneets systems (cap %d) / %zu histogram doubles", nsys, c->farr_cap, hist_need);
             chunk = std::max(1, n / 2); // arenas too small for this chunk: retry with fewer sets
             continue;
@@ -738,42 +764,55 @@ extern "C" int rg_eval_batch_host(rg_ctx *c, const double *params, int P, int mo
     RG_CUDA_OK(cudaSetDevice(c->device));
     const int ncomp = (flags & RG_FLAG_COMPONENTS) ? 4 : 1;
     const size_t per_out = (size_t)ncomp * c->nE;
-    // pipeline in slabs so the D2H of slab i overlaps the kernels of slab i+1
-    const int SLAB = 16384; // = the chunk of rg_eval_batch: one setup/nthcomp/spectrum launch set per slab
-    int nslab_dev = std::min(P, 2 * SLAB);
+    // pipeline in slabs so the D2H of slab i overlaps the kernels of slab i+1.  A slab is one chunk of rg_eval_batch
+    // (one setup/nthcomp/hist/spectrum launch sequence); slabs shrink towards the end of the batch (half of what is
+    // left, in steps of 8192) so that the copy nobody hides -- the last slab's -- is a small one.
+    const int SLAB_MAX = pick_chunk_sets(P);
+    int SMIN = 8192; // smallest slab
+    if (const char *e = getenv("RG_SLAB_MIN")) { int v = atoi(e); if (v >= 1024 && v <= 65536) SMIN = v & ~1023; } // tuning knob
+    const int SREST = SMIN + SMIN / 2; // what is left below this goes as one slab
+    const bool piped = P > SREST; // more than one slab: two staging buffers
+    const int slab_cap = piped ? std::max(SREST, std::min(SLAB_MAX, std::max(SMIN, (P / 2) / SMIN * SMIN))) : P;
     RG_TRY(ensure_dev(&c->d_stage_par, &c->d_stage_par_n, (size_t)P * RG_NPAR));
-    RG_TRY(ensure_dev(&c->d_stage_out, &c->d_stage_out_n, (size_t)nslab_dev * per_out));
+    RG_TRY(ensure_dev(&c->d_stage_out, &c->d_stage_out_n, (size_t)(piped ? 2 : 1) * slab_cap * per_out));
     RG_TRY(ensure_dev(&c->d_stage_attr, &c->d_stage_attr_n, (size_t)P * RG_NATTR));
     RG_CUDA_OK(cudaMemcpyAsync(c->d_stage_par, params, (size_t)P * RG_NPAR * sizeof(double), cudaMemcpyHostToDevice,
                                c->stream));
     cudaStream_t copy_st = nullptr;
     RG_CUDA_OK(cudaStreamCreateWithFlags(&copy_st, cudaStreamNonBlocking));
-    cudaEvent_t done[2], freed[2];
-    for (int i = 0; i < 2; i++) { cudaEventCreate(&done[i]); cudaEventCreate(&freed[i]); }
+    cudaEvent_t freed[2];
+    for (int i = 0; i < 2; i++) cudaEventCreate(&freed[i]);
     int rc = RG_OK;
     int slab = 0;
     bool used[2] = {false, false};
-    for (int p0 = 0; p0 < P && rc == RG_OK; p0 += SLAB, slab ^= 1) {
-        int n = std::min(SLAB, P - p0);
-        double *dslab = c->d_stage_out + (size_t)(nslab_dev > SLAB ? slab : 0) * SLAB * per_out;
+    const bool trace = getenv("RG_TRACE_HOST") != nullptr; // host-side timeline of the slab pipeline on stderr
+    auto now_ms = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now_ms();
+    for (int p0 = 0; p0 < P && rc == RG_OK; slab ^= 1) {
+        const int left = P - p0;
+        int n = left;
+        if (left > SREST) n = std::min(SLAB_MAX, std::max(SMIN, (left / 2) / SMIN * SMIN));
+        double *dslab = c->d_stage_out + (size_t)(piped ? slab : 0) * slab_cap * per_out;
         if (used[slab]) cudaEventSynchronize(freed[slab]); // previous copy out of this slab buffer finished
         rc = rg_eval_batch(c, c->d_stage_par + (size_t)p0 * RG_NPAR, n, model, dr_dex, flags, dslab,
                            c->d_stage_attr + (size_t)p0 * RG_NATTR, c->stream);
         if (rc != RG_OK) break;
-        cudaEventRecord(done[slab], c->stream);
         // D2H on the copy stream once the slab's kernels are done
-        cudaStreamSynchronize(c->stream); // (rg_eval_batch already synchronised per chunk; keeps ordering simple)
+        cudaStreamSynchronize(c->stream);
+        if (trace) fprintf(stderr, "[rg host] slab of %d sets done at %.2f ms\n", n, now_ms() - t_begin);
         cudaMemcpyAsync(out + (size_t)p0 * per_out, dslab, (size_t)n * per_out * sizeof(double), cudaMemcpyDeviceToHost,
                         copy_st);
         cudaEventRecord(freed[slab], copy_st);
         used[slab] = true;
+        p0 += n;
     }
     cudaStreamSynchronize(copy_st);
+    if (trace) fprintf(stderr, "[rg host] last D2H done at %.2f ms\n", now_ms() - t_begin);
     if (rc == RG_OK && attrs) {
         cudaMemcpyAsync(attrs, c->d_stage_attr, (size_t)P * RG_NATTR * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
     }
     cudaStreamSynchronize(c->stream);
-    for (int i = 0; i < 2; i++) { cudaEventDestroy(done[i]); cudaEventDestroy(freed[i]); }
+    for (int i = 0; i < 2; i++) cudaEventDestroy(freed[i]);
     cudaStreamDestroy(copy_st);
     if (rc != RG_OK) return rc;
     RG_CUDA_OK(cudaGetLastError());
@@ -957,7 +996,7 @@ extern "C" int rg_eval_fitstat_batch(rg_ctx *c, const double *d_params, int P, i
     if (flags & RG_FLAG_COMPONENTS) return rg_set_error(RG_E_ARG, "rg_eval_fitstat_batch: the statistic uses the total SED only");
     if (P == 0) return RG_OK;
     RG_CUDA_OK(cudaSetDevice(c->device));
-    const int SLAB = 16384; // = the chunk of rg_eval_batch
+    const int SLAB = pick_chunk_sets(P); // = the chunk of rg_eval_batch
     RG_TRY(ensure_dev(&c->d_slab, &c->slab_n, (size_t)std::min(P, SLAB) * c->nE));
     for (int p0 = 0; p0 < P; p0 += SLAB) {
         const int n = std::min(SLAB, P - p0);

@@ -98,6 +98,7 @@ int rg_launch_raytrace(const double *h_spins, int n_spin, const double *h_thetas
                        double dl, float *d_data, long *n_unresolved, cudaStream_t st);
 
 int rg_fp64_peak(double *tflops, cudaStream_t st);
+int rg_launch_counters_out(const int *d_counter, int *h_mapped, cudaStream_t st);
 
 // ---- observation epilogue (rg_observe.cu) ----
 struct ObsArgs {

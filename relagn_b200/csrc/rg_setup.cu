@@ -412,14 +412,24 @@ __device__ static void nthcomp_system(bool valid, const SetRec &r, int which, co
     // dependent recurrence runs on registers.
     const int jtop_me = jmax - 2;
     const int jtop = __reduce_max_sync(0xffffffffu, jtop_me);
+    // The next group's loads are in flight while the current group's dependent chain runs (register double buffer).
+    double gg[4] = {0, 0, 0, 0}, gm[4] = {0, 0, 0, 0}, bt[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        if (jtop - q >= 1 && jtop - q <= jtop_me) {
+            size_t o = (size_t)(jtop - q) * sc_stride + sys;
+            gg[q] = RG_LDCS(&sc_g[o]); gm[q] = RG_LDCS(&sc_gam[o]); bt[q] = RG_LDCS(&sc_bet[o]);
+        }
+    }
     for (int jj = jtop; jj >= 1;) {
         const int nb = jj >= 4 ? 4 : jj; // rows jj, jj-1, ..., jj-nb+1
-        double gg[4], gm[4], bt[4];
+        const int jn = jj - nb;          // first row of the next group
+        double ngg[4] = {0, 0, 0, 0}, ngm[4] = {0, 0, 0, 0}, nbt[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-            if (q < nb && jj - q <= jtop_me) {
-                size_t o = (size_t)(jj - q) * sc_stride + sys;
-                gg[q] = RG_LDCS(&sc_g[o]); gm[q] = RG_LDCS(&sc_gam[o]); bt[q] = RG_LDCS(&sc_bet[o]);
+            if (jn - q >= 1 && jn - q <= jtop_me) {
+                size_t o = (size_t)(jn - q) * sc_stride + sys;
+                ngg[q] = RG_LDCS(&sc_g[o]); ngm[q] = RG_LDCS(&sc_gam[o]); nbt[q] = RG_LDCS(&sc_bet[o]);
             }
         }
 #pragma unroll
@@ -432,7 +442,9 @@ __device__ static void nthcomp_system(bool valid, const SetRec &r, int which, co
                 if (jj - q == 1) u1 = u;
             }
         }
-        jj -= nb;
+#pragma unroll
+        for (int q = 0; q < 4; q++) { gg[q] = ngg[q]; gm[q] = ngm[q]; bt[q] = nbt[q]; }
+        jj = jn;
     }
     if (!valid) return;
     {
@@ -497,7 +509,7 @@ nthcomp_interp_kernel(const SetRec *__restrict__ recs, const int2 *__restrict__ 
     __shared__ double s_p10[RG_NTH + 4];
     __shared__ double s_rdp[RG_NTH + 4]; // 1 / (10^(0.02 (j+1)) - 10^(0.02 j)): the cell width of the x grid, per unit xmin
     for (int i = threadIdx.x; i < RG_NTH + 4; i += blockDim.x) s_p10[i] = p10tab[i];
-    for (int i = threadIdx.x; i < RG_NTH + 3; i += blockDim.x) s_rdp[i] = 1.0 / (p10tab[i + 1] - p10tab[i]);
+    for (int i = threadIdx.x; i < RG_NTH + 3; i += blockDim.x) s_rdp[i] = p10tab[RG_NTH + 4 + i];
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int sys = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -558,6 +570,23 @@ int rg_launch_setup(const double *d_params, int P, int model, double dr_dex, Set
     }
     RG_LAUNCH(setup_kernel, dim3((P + 127) / 128), dim3(128), 0, st, d_params, P, model, dr_dex, recs, sys_counter,
               syslist, sys_cap, rq_scratch, rq_cap, d_attrs);
+    RG_CUDA_OK(cudaGetLastError());
+    return RG_OK;
+}
+
+// The two counters of the setup kernel reach the host by a store from the device into pinned (mapped) memory: a
+// cudaMemcpy D2H would queue on the copy engine behind whatever large copy is in flight there -- the previous slab's
+// spectra in rg_eval_batch_host, a caller's own transfer -- and the chunk would wait for all of it.
+__global__ void counters_out_kernel(const int *__restrict__ ctr, int *__restrict__ host_mapped)
+{
+    host_mapped[0] = ctr[0];
+    host_mapped[1] = ctr[1];
+    __threadfence_system();
+}
+
+int rg_launch_counters_out(const int *d_counter, int *h_mapped, cudaStream_t st)
+{
+    RG_LAUNCH(counters_out_kernel, dim3(1), dim3(1), 0, st, d_counter, h_mapped);
     RG_CUDA_OK(cudaGetLastError());
     return RG_OK;
 }

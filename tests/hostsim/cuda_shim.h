@@ -68,6 +68,7 @@ static inline void __syncthreads() { hostsim::sync_block(); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { hostsim::warp_ballot(0); }
 static inline void __threadfence() {}
 static inline void __threadfence_block() {}
+static inline void __threadfence_system() {}
 
 template <class T> static inline T __ldg(const T *p) { return *p; }
 
