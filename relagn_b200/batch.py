@@ -170,12 +170,30 @@ def shard_bounds(P, world, rank):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def evaluate_sharded(evaluator, params_local, rel=True, gather_dst=0, group=None, pieces=4, out=None, attrs=None,
+def piece_edges(P, pieces=None, chunk_max=65536, piece_min=8192):
+    """Piece boundaries of a shard of P sets.  pieces=None: every piece is half of what is left (multiples of
+    `piece_min`, at most the library's chunk of `chunk_max` sets), so the early pieces run at the full chunk size and
+    the last one -- whose transfer nobody hides -- is small (the same plan as rg_eval_batch_host's slabs).
+    pieces=n: n roughly equal pieces on multiples of 16384 sets."""
+    if pieces is not None:
+        n_chunks = max(1, (P + 16383) // 16384)
+        pieces = max(1, min(int(pieces), n_chunks))
+        return [min(P, ((n_chunks * i) // pieces) * 16384) for i in range(pieces)] + [P]
+    edges, lo = [0], 0
+    while lo < P:
+        left = P - lo
+        n = left if left <= piece_min + piece_min // 2 else min(chunk_max, max(piece_min, (left // 2) // piece_min * piece_min))
+        lo += n
+        edges.append(lo)
+    return edges
+
+
+def evaluate_sharded(evaluator, params_local, rel=True, gather_dst=0, group=None, pieces=None, out=None, attrs=None,
                      gathered=None):
     """One process per GPU: every rank evaluates its own shard (device tensor [P_local, 15]); the only collective
     is the gather of the spectra to `gather_dst` over NCCL (gather_dst=None: no gather).  The shard is evaluated in
-    `pieces` contiguous pieces and the gather of piece i is issued on a side stream while piece i+1 is computed, so
-    only the last piece's transfer is exposed.  out / attrs / gathered: optional preallocated result tensors
+    contiguous pieces (`piece_edges`) and the gather of piece i is issued on a side stream while piece i+1 is
+    computed, so only the last (small) piece's transfer is exposed.  out / attrs / gathered: optional preallocated result tensors
     ([P_local, nE], [P_local, 24], list of world x [P_local, nE] on the destination rank).
     Returns (local_out, gathered or None)."""
     import torch.distributed as dist
@@ -187,10 +205,7 @@ def evaluate_sharded(evaluator, params_local, rel=True, gather_dst=0, group=None
             return out, None
         return evaluator.evaluate_device(params_local, rel=rel)[0], None
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    # piece boundaries on multiples of the library's 16384-set chunk
-    n_chunks = max(1, (P + 16383) // 16384)
-    pieces = max(1, min(int(pieces), n_chunks))
-    edges = [min(P, ((n_chunks * i) // pieces) * 16384) for i in range(pieces)] + [P]
+    edges = piece_edges(P, pieces)
     cuda = params_local.is_cuda
     side = torch.cuda.Stream(device=params_local.device) if cuda else None
     outs, works = [], []

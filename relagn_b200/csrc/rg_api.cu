@@ -577,7 +577,7 @@ static int pick_chunk_sets(int P)
 static int ensure_batch_scratch(rg_ctx *c, int model, int P)
 {
     if (!c->d_sc) { // persistent nthcomp grid and its scratch planes: sized by the machine, not by the batch
-        c->nth_threads = c->sm_count * 5 * 128;
+        c->nth_threads = c->sm_count * RG_NTH_MINB * 128;
         RG_CUDA_OK(cudaMalloc(&c->d_sc, (size_t)3 * RG_NTH * c->nth_threads * sizeof(double)));
         RG_CUDA_OK(cudaMalloc(&c->d_queue, 2 * sizeof(int)));
     }

@@ -97,6 +97,9 @@ int rg_launch_ky_conv(const double *d_H, int kmin, int nk, const double *d_in, d
 int rg_launch_raytrace(const double *h_spins, int n_spin, const double *h_thetas, int n_inc, int NR, int NPHI,
                        double dl, float *d_data, long *n_unresolved, cudaStream_t st);
 
+#ifndef RG_NTH_MINB
+#define RG_NTH_MINB 5 // resident 128-thread CTAs per SM of the persistent nthcomp grid
+#endif
 int rg_fp64_peak(double *tflops, cudaStream_t st);
 int rg_launch_counters_out(const int *d_counter, int *h_mapped, cudaStream_t st);
 

@@ -463,7 +463,7 @@ __device__ static void nthcomp_system(bool valid, const SetRec &r, int which, co
     hd[0] = xmin; hd[1] = normfac; hd[2] = (double)jmax; hd[3] = log10(511.0 * xmin);
 }
 
-__global__ void __launch_bounds__(128, 5)
+__global__ void __launch_bounds__(128, RG_NTH_MINB)
 nthcomp_kernel(const SetRec *__restrict__ recs, const int2 *__restrict__ syslist, int nsys,
                const double *__restrict__ p10tab, double *__restrict__ sc_gam, double *__restrict__ sc_g,
                double *__restrict__ sc_bet, int n_threads, double *__restrict__ sptot, double *__restrict__ header,

@@ -630,6 +630,10 @@ __global__ void __launch_bounds__(NC <= 4 ? (sizeof(R) == 4 ? 512 : 32 * RG_SPEC
             __syncwarp();
             const double Lum = r.Ldiss + r.Lseed;
             const bool conv_here = rel && t_lo <= t_hi;
+            // 1 / trapz(Fnu) and the factors of relagn.py:1362 once per item instead of three divisions per bin and warp
+            // (0 / 0 -> NaN as the reference's division gives, relagn.py:1316: 1/0 = inf, 0 * inf = NaN)
+            const double r_shape = 1.0 / shape_int;
+            const double conv_fac = (conv_unit / shape_int) / cosfac;
             for (int ch = 0; ch < NC; ch++) {
                 const int col = 32 * ch + lane;
                 R tmp[8];
@@ -644,11 +648,11 @@ __global__ void __launch_bounds__(NC <= 4 ? (sizeof(R) == 4 ? 512 : 32 * RG_SPEC
                         // the buffer holds F * pk and pk * upk = 4; F / shape_int: 0/0 -> NaN as the reference (:1316)
                         double F = (double)inBase[c * RS + 32 * ch] * (double)G.upk(c, col) * 0.25;
                         if (rel) {
-                            double vv = hot_mine ? Sflat * (F / shape_int) : 0.0;
-                            if (conv_here) vv += ((((double)tmp[c] * conv_unit) / shape_int) * (double)G.upk(c, col)) / cosfac; // relagn.py:1362
+                            double vv = hot_mine ? Sflat * (F * r_shape) : 0.0;
+                            if (conv_here) vv += ((double)tmp[c] * conv_fac) * (double)G.upk(c, col); // relagn.py:1362
                             v[c] = (R)vv;
                         } else {
-                            v[c] = (R)(Lum * (F / shape_int));
+                            v[c] = (R)(Lum * (F * r_shape));
                         }
                     }
                 }

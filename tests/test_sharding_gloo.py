@@ -54,7 +54,19 @@ def test_shard_bounds_cover_everything():
             assert max(sizes) - min(sizes) <= 1
 
 
-@pytest.mark.parametrize("P", [10, 80000])  # 80000: three 16384-aligned pieces per rank, gathered piece by piece
+def test_piece_edges_cover_the_shard():
+    from relagn_b200.batch import piece_edges
+    for P in (1, 5000, 12288, 12289, 20000, 125000, 1000000):
+        for pieces in (None, 1, 4):
+            e = piece_edges(P, pieces)
+            assert e[0] == 0 and e[-1] == P and all(b >= a for a, b in zip(e, e[1:]))
+        e = piece_edges(P)
+        sizes = [b - a for a, b in zip(e, e[1:])]
+        assert max(sizes) <= 65536 and sizes[-1] <= 12288            # the exposed transfer is the small last piece
+        assert all(n % 8192 == 0 for n in sizes[:-1])
+
+
+@pytest.mark.parametrize("P", [10, 80000])  # 80000: four shrinking pieces per rank (40000 sets each), gathered piece by piece
 def test_two_rank_gather_gloo(P):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()

@@ -21,7 +21,10 @@ KEYS = ["dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum
 out = {"command": "python bench.py --sets %d --steps 1 --warmup 3 --no-cpu under `ncu --set full --clock-control none "
                   "--import-source on -k regex:<kernel> -s 3 -c 1` (tools/gpu_profile.sh %s), after the same command "
                   "exited 0 without ncu" % (sets, tag), "sets_per_launch": sets}
-for name, rep in (("spectrum_kernel", "prof_spectrum_%s.ncu-rep" % tag), ("nthcomp_kernel", "prof_nthcomp_%s.ncu-rep" % tag)):
+for name, rep in (("spectrum_kernel", "prof_spectrum_%s.ncu-rep" % tag), ("nthcomp_kernel", "prof_nthcomp_%s.ncu-rep" % tag),
+                  ("hist_kernel", "prof_hist_%s.ncu-rep" % tag)):
+    if not os.path.exists(os.path.join(ROOT, "gpurun_out", rep)):
+        continue
     path = os.path.join(ROOT, "gpurun_out", rep)
     raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     open(os.path.join(ROOT, "profiles", "%s_%s_raw.csv" % (tag, name.split("_")[0])), "w").write(raw)
