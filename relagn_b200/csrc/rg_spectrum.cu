@@ -68,6 +68,10 @@ int rg_spectrum_pick_warps(int NC, int nH, int HL, int HH, int fp32)
     return 0;
 }
 
+#ifndef RG_WARM_PREFETCH
+#define RG_WARM_PREFETCH 1
+#endif
+
 template <typename T>
 __device__ inline T warp_sum(T v)
 {
@@ -424,6 +428,17 @@ __global__ void __launch_bounds__(NC <= 4 ? (sizeof(R) == 4 ? 512 : 32 * RG_SPEC
                 const bool conv = __shfl_sync(FULL, p_flag, mi) != 0;
                 const int jz = __shfl_sync(FULL, p_jz, mi);
                 const int loc = __shfl_sync(FULL, p_loc, mi);
+#if RG_WARM_PREFETCH
+                // the warp's next annulus, if warm: its Comptonised spectrum (8 nE bytes of the farr arena, far larger
+                // than L2) is requested into L2 now, a whole annulus ahead of the loads that consume it
+                if (mi + 1 < mt) {
+                    const int nreg = __shfl_sync(FULL, p_region, mi + 1), nloc = __shfl_sync(FULL, p_loc, mi + 1);
+                    if (nreg == 1) {
+                        const char *row = reinterpret_cast<const char *>(A.farr + (size_t)(r.sys_base + nloc) * nE);
+                        for (int b = lane * 128; b < nE * 8; b += 32 * 128) RG_PREFETCH_L2(row + b);
+                    }
+                }
+#endif
                 if (comps && region != cur_region && region != 2) { // (hot contributes after the loop)
                     acc.store(part_w + (size_t)cur_region * nE, nE, true);
                     cur_region = region;
