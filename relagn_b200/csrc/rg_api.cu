@@ -141,9 +141,14 @@ extern "C" int rg_ctx_create(int device, rg_ctx **out)
     RG_CUDA_OK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     // 10^(0.02 j) with the host libm, exactly as the reference's x grid (pyNTHCOMP.py:112-114)
     // followed by the reciprocal cell widths 1 / (10^(0.02 (j+1)) - 10^(0.02 j)) the interpolation kernel multiplies by
-    std::vector<double> p10(2 * (RG_NTH + 4), 0.0);
+    // and by sqrt(10^(0.02 j) 10^(0.02 (j+1))) and its reciprocal for the Kompaneets coefficients (layout: rg_kernels.h)
+    std::vector<double> p10(RG_P10_LEN, 0.0);
     for (int j = 0; j < RG_NTH + 4; j++) p10[j] = pow(10.0, j * 0.02);
-    for (int j = 0; j < RG_NTH + 3; j++) p10[RG_NTH + 4 + j] = 1.0 / (p10[j + 1] - p10[j]);
+    for (int j = 0; j < RG_NTH + 3; j++) {
+        p10[RG_P10_RDP + j] = 1.0 / (p10[j + 1] - p10[j]);
+        p10[RG_P10_W1 + j] = sqrt(p10[j] * p10[j + 1]);
+        p10[RG_P10_RW1 + j] = 1.0 / p10[RG_P10_W1 + j];
+    }
     RG_CUDA_OK(cudaMalloc(&c->d_p10, p10.size() * sizeof(double)));
     RG_CUDA_OK(cudaMemcpy(c->d_p10, p10.data(), p10.size() * sizeof(double), cudaMemcpyHostToDevice));
     RG_CUDA_OK(cudaMalloc(&c->d_counter, 2 * sizeof(int)));
@@ -578,7 +583,8 @@ static int ensure_batch_scratch(rg_ctx *c, int model, int P)
 {
     if (!c->d_sc) { // persistent nthcomp grid and its scratch planes: sized by the machine, not by the batch
         c->nth_threads = c->sm_count * RG_NTH_MINB * 128;
-        RG_CUDA_OK(cudaMalloc(&c->d_sc, (size_t)3 * RG_NTH * c->nth_threads * sizeof(double)));
+        // two [RG_NTH][threads] planes (gamma, g of the Thomas sweep) + one row (bet[0])
+        RG_CUDA_OK(cudaMalloc(&c->d_sc, ((size_t)2 * RG_NTH + 1) * c->nth_threads * sizeof(double)));
         RG_CUDA_OK(cudaMalloc(&c->d_queue, 2 * sizeof(int)));
     }
     const int want = pick_chunk_sets(P);

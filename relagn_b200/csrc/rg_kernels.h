@@ -97,6 +97,11 @@ int rg_launch_ky_conv(const double *d_H, int kmin, int nk, const double *d_in, d
 int rg_launch_raytrace(const double *h_spins, int n_spin, const double *h_thetas, int n_inc, int NR, int NPHI,
                        double dl, float *d_data, long *n_unresolved, cudaStream_t st);
 
+// layout of the resident 10^(0.02 j) table (rg_ctx::d_p10): four runs of RG_NTH + 4 doubles
+#define RG_P10_RDP (3 * (RG_NTH + 4))       // 1 / (10^(0.02 (j+1)) - 10^(0.02 j)): reciprocal cell widths (interpolation kernel)
+#define RG_P10_W1 (RG_NTH + 4)       // sqrt(10^(0.02 j) 10^(0.02 (j+1))): w1 of pyNTHCOMP.py:117 per unit xmin
+#define RG_P10_RW1 (2 * (RG_NTH + 4)) // 1 / that
+#define RG_P10_LEN (4 * (RG_NTH + 4))
 #ifndef RG_NTH_MINB
 #define RG_NTH_MINB 5 // resident 128-thread CTAs per SM of the persistent nthcomp grid
 #endif

@@ -276,7 +276,7 @@ setup_kernel(const double *__restrict__ params, int P, int model, double dr_dex,
 
 // ---------------------------------------------------------------------------
 // nthcomp: one thread per system, persistent grid.
-//   scratch planes gam, g, bet: [RG_NTH][n_threads], indexed by the launching
+//   scratch planes gam, g: [RG_NTH][n_threads] (bet: row 0 only, the rest is recomputed), indexed by the launching
 //   thread (not the system) so the footprint is bounded by the resident
 //   threads; a warp's accesses to one j are contiguous.
 //   sptot arena: [sys][RG_SPT_STRIDE];  header: [sys][4] = xmin, normfac, jmax, log10(511 xmin);
@@ -356,32 +356,40 @@ __device__ static void nthcomp_system(bool valid, const SetRec &r, int which, co
         else b0 = 1.0 / tautom;
         if (valid) { sc_bet[sys] = b0; sc_gam[sys] = 0; sc_g[sys] = 0; }
     }
-    const double itau = 1.0 / tautom, rxr = 1.0 / (xr - xnr), itbb = 1.0 / tempbb;
+    const double itau = 1.0 / tautom, rxr = 1.0 / (xr - xnr), itbb = 1.0 / tempbb, todx = tod / xmin;
+    const double third = 1.0 / 3.0;
+    // bet[j] of pyNTHCOMP.py:124-148 at x = x[j] (j >= 1); a pure function of the row, so the back substitution can
+    // recompute it bit for bit instead of reading a third scratch plane back (the solve is bound by the
+    // HBM round trip of the planes, not by instructions: 37 -> 34 ms per 125 000 sets)
+    auto bet_at = [&](int j, double w) -> double {
+        if (j >= jrel) return itau;
+        double rel;
+        if (w <= 0.05) rel = (1.0 - 2.0 * w + 26.0 * w * w * 0.2);
+        else {
+            // Klein-Nishina factor (pyNTHCOMP.py:128-136) with the six divisions by w and 1 + 2w folded into
+            // two reciprocals (last-bit differences only)
+            const double rw = 1.0 / w, z2 = 1.0 + 2.0 * w, rz = 1.0 / z2, z3 = log(z2);
+            double z1 = (1.0 + w) * (rw * rw * rw), z4 = 2.0 * w * (1.0 + w) * rz;
+            double z5 = z3 * 0.5 * rw, z6 = (1.0 + 3.0 * w) * (rz * rz);
+            rel = (0.75 * (z1 * (z4 - z3) + z5 - z6));
+        }
+        const double taukn = tautom * rel;
+        if (j < jnr - 1) return itau * __drcp_rn(1.0 + taukn * third);
+        const double flz = 1 - (w - xnr) * rxr;
+        return itau * __drcp_rn(1.0 + taukn * third * flz);
+    };
     for (int j = 1; j < jmax - 1; j++) {
         xp = xmin * p10tab[j + 1];
-        double w1j = sqrt(x0 * xp);
-        double c2j = (w1j * w1j * w1j * w1j) / (1.0 + 4.60 * w1j + 1.1 * w1j * w1j);
+        // w1 = sqrt(x[j] x[j+1]) = xmin 10^(0.02 j + 0.01) and theta / deltal / w1 from the resident tables: no
+        // square root and one division less per row (last-bit differences against pyNTHCOMP.py:117,211)
+        const double w1j = xmin * p10tab[RG_P10_W1 + j];
+        // (quotients as reciprocal multiplies: rcp.rn + mul instead of div.rn, last-bit differences)
+        double c2j = (w1j * w1j * w1j * w1j) * __drcp_rn(1.0 + 4.60 * w1j + 1.1 * w1j * w1j);
         // rel, bet at j
-        double w = x0, betj;
-        if (j >= jrel) betj = itau;
-        else {
-            double rel;
-            if (w <= 0.05) rel = (1.0 - 2.0 * w + 26.0 * w * w * 0.2);
-            else {
-                // Klein-Nishina factor (pyNTHCOMP.py:128-136) with the six divisions by w and 1 + 2w folded into
-                // two reciprocals (last-bit differences only)
-                const double rw = 1.0 / w, z2 = 1.0 + 2.0 * w, rz = 1.0 / z2, z3 = log(z2);
-                double z1 = (1.0 + w) * (rw * rw * rw), z4 = 2.0 * w * (1.0 + w) * rz;
-                double z5 = z3 * 0.5 * rw, z6 = (1.0 + 3.0 * w) * (rz * rz);
-                rel = (0.75 * (z1 * (z4 - z3) + z5 - z6));
-            }
-            double taukn = tautom * rel;
-            if (j < jnr - 1) betj = itau / (1.0 + taukn / 3.0);
-            else { double flz = 1 - (w - xnr) * rxr; betj = itau / (1.0 + taukn / 3.0 * flz); }
-        }
-        double dph = (j < jmaxth) ? planck * (x0 * x0) / (exp(x0 * itbb) - 1) : 0.0;
+        const double betj = bet_at(j, x0);
+        double dph = (j < jmaxth) ? planck * (x0 * x0) * __drcp_rn(exp(x0 * itbb) - 1) : 0.0;
         // coefficients (pyNTHCOMP.py:210-221)
-        const double tow1 = tod / w1j, tow2 = tow1_prev;
+        const double tow1 = todx * p10tab[RG_P10_RW1 + j], tow2 = tow1_prev;
         double aj = -c20 * c2j * (tow1 + 0.5);
         double t1 = -c20 * c2j * (0.5 - tow1);
         double t2 = c20 * c2m * (tow2 + 0.5);
@@ -397,7 +405,7 @@ __device__ static void nthcomp_system(bool valid, const SetRec &r, int which, co
         if (j == 1) gj = dj * ralp; else gj = (dj - cj * g_prev) * ralp;
         double gamj = aj * ralp;
         size_t o = (size_t)j * sc_stride + sys;
-        RG_STCS(&sc_gam[o], gamj); RG_STCS(&sc_g[o], gj); RG_STCS(&sc_bet[o], betj); // streamed: read back once
+        RG_STCS(&sc_gam[o], gamj); RG_STCS(&sc_g[o], gj); // streamed: read back once
         gam_prev = gamj; g_prev = gj;
         xm = x0; x0 = xp; c2m = c2j; tow1_prev = tow1;
     }
@@ -413,23 +421,23 @@ __device__ static void nthcomp_system(bool valid, const SetRec &r, int which, co
     const int jtop_me = jmax - 2;
     const int jtop = __reduce_max_sync(0xffffffffu, jtop_me);
     // The next group's loads are in flight while the current group's dependent chain runs (register double buffer).
-    double gg[4] = {0, 0, 0, 0}, gm[4] = {0, 0, 0, 0}, bt[4] = {0, 0, 0, 0};
+    double gg[4] = {0, 0, 0, 0}, gm[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         if (jtop - q >= 1 && jtop - q <= jtop_me) {
             size_t o = (size_t)(jtop - q) * sc_stride + sys;
-            gg[q] = RG_LDCS(&sc_g[o]); gm[q] = RG_LDCS(&sc_gam[o]); bt[q] = RG_LDCS(&sc_bet[o]);
+            gg[q] = RG_LDCS(&sc_g[o]); gm[q] = RG_LDCS(&sc_gam[o]);
         }
     }
     for (int jj = jtop; jj >= 1;) {
         const int nb = jj >= 4 ? 4 : jj; // rows jj, jj-1, ..., jj-nb+1
         const int jn = jj - nb;          // first row of the next group
-        double ngg[4] = {0, 0, 0, 0}, ngm[4] = {0, 0, 0, 0}, nbt[4] = {0, 0, 0, 0};
+        double ngg[4] = {0, 0, 0, 0}, ngm[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             if (jn - q >= 1 && jn - q <= jtop_me) {
                 size_t o = (size_t)(jn - q) * sc_stride + sys;
-                ngg[q] = RG_LDCS(&sc_g[o]); ngm[q] = RG_LDCS(&sc_gam[o]); nbt[q] = RG_LDCS(&sc_bet[o]);
+                ngg[q] = RG_LDCS(&sc_g[o]); ngm[q] = RG_LDCS(&sc_gam[o]);
             }
         }
 #pragma unroll
@@ -437,13 +445,14 @@ __device__ static void nthcomp_system(bool valid, const SetRec &r, int which, co
             if (q < nb && jj - q <= jtop_me) {
                 double u = gg[q] - gm[q] * u_next;
                 double x = xmin * p10tab[jj - q];
-                spt[jj - q] = (x * x * u * bt[q] * tautom) * (x * x);
+                const double btq = bet_at(jj - q, x); // recomputed: no third scratch plane
+                spt[jj - q] = (x * x * u * btq * tautom) * (x * x);
                 u_next = u;
                 if (jj - q == 1) u1 = u;
             }
         }
 #pragma unroll
-        for (int q = 0; q < 4; q++) { gg[q] = ngg[q]; gm[q] = ngm[q]; bt[q] = nbt[q]; }
+        for (int q = 0; q < 4; q++) { gg[q] = ngg[q]; gm[q] = ngm[q]; }
         jj = jn;
     }
     if (!valid) return;
@@ -471,8 +480,12 @@ nthcomp_kernel(const SetRec *__restrict__ recs, const int2 *__restrict__ syslist
 {
     // 10^(0.02 j) is read at every step of both sweeps: keep it in shared memory (the scratch stream would keep
     // evicting it from L1)
-    __shared__ double s_p10[RG_NTH + 4];
-    for (int i = threadIdx.x; i < RG_NTH + 4; i += blockDim.x) s_p10[i] = p10tab[i];
+    __shared__ double s_p10[RG_P10_RW1 + RG_NTH + 4]; // 10^(0.02 j) | w1 | 1 / w1
+    for (int i = threadIdx.x; i < RG_NTH + 4; i += blockDim.x) {
+        s_p10[i] = p10tab[i];
+        s_p10[RG_P10_W1 + i] = p10tab[RG_P10_W1 + i];
+        s_p10[RG_P10_RW1 + i] = p10tab[RG_P10_RW1 + i];
+    }
     __syncthreads();
     int gtid = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long sumj = 0, nsolved = 0;
@@ -509,7 +522,7 @@ nthcomp_interp_kernel(const SetRec *__restrict__ recs, const int2 *__restrict__ 
     __shared__ double s_p10[RG_NTH + 4];
     __shared__ double s_rdp[RG_NTH + 4]; // 1 / (10^(0.02 (j+1)) - 10^(0.02 j)): the cell width of the x grid, per unit xmin
     for (int i = threadIdx.x; i < RG_NTH + 4; i += blockDim.x) s_p10[i] = p10tab[i];
-    for (int i = threadIdx.x; i < RG_NTH + 3; i += blockDim.x) s_rdp[i] = p10tab[RG_NTH + 4 + i];
+    for (int i = threadIdx.x; i < RG_NTH + 3; i += blockDim.x) s_rdp[i] = p10tab[RG_P10_RDP + i];
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int sys = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
