@@ -383,16 +383,19 @@ def run_ours(args):
         # DRAM bytes of one spectrum_kernel launch from the committed `ncu --set full` capture (profiles/), scaled to
         # this run's sets per launch; the excess over bytes_per_launch is the Comptonised-spectra arena (farr) that
         # nthcomp_interp_kernel writes and this kernel reads once (~29 systems x 8 kB per set), not a re-read
-        traffic = None
-        try:
-            prof = json.load(open(os.path.join(ROOT, "profiles", "r1n_summary.json")))
-            traffic = prof["spectrum_dram_bytes_per_set"] * (P / n_launch)
-        except Exception:
-            pass
+        traffic, traffic_src = None, None
+        for tag in ("r1q", "r1p", "r1n"):  # latest capture first
+            try:
+                prof = json.load(open(os.path.join(ROOT, "profiles", tag + "_summary.json")))
+                traffic = prof["spectrum_dram_bytes_per_set"] * (P / n_launch)
+                traffic_src = "profiles/%s_summary.json (dram__bytes_read.sum + dram__bytes_write.sum per set x sets per launch)" % tag
+                break
+            except Exception:
+                pass
         roofline = {"kernel": "spectrum_kernel<4>", "bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak,
                     "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
-                    "traffic": traffic,
+                    "traffic": traffic, "traffic_source": traffic_src,
                     "bytes_per_launch": bytes_alg / n_launch, "launches_per_step": n_launch,
                     "avg_launch_ms": ms_spec / n_launch,
                     "note": "the path is FP64-pipe bound, not HBM bound (SURVEY 8d): this block is the HBM figure the "

@@ -10,4 +10,5 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:spectrum_kernel -s 3 -c 1 -o gpurun_out/prof_spectrum_$TAG -f $CMD > gpurun_out/ncu_full_$TAG.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:nthcomp_kernel -s 3 -c 1 -o gpurun_out/prof_nthcomp_$TAG -f $CMD > gpurun_out/ncu_full2_$TAG.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:hist_kernel -s 3 -c 1 -o gpurun_out/prof_hist_$TAG -f $CMD > gpurun_out/ncu_full3_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:nthcomp_interp -s 3 -c 1 -o gpurun_out/prof_interp_$TAG -f $CMD > gpurun_out/ncu_full4_$TAG.log 2>&1
 ls -la gpurun_out/
