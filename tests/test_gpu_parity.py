@@ -169,6 +169,34 @@ def test_full_size_properties_relqso_grid(ctx):
     assert np.all((Lrel / Lflat > 0.5) & (Lrel / Lflat < 1.5))
 
 
+def test_full_size_c4_batch_chunking_invariance():
+    """Config 4 at the per-GPU size of the metric (125 000 sets): the spectra do not depend on how the batch is cut
+    into chunks / host slabs, bit for bit -- a small batch, then the full batch through the host-slab pipeline (the
+    context's arenas grow from the 4096-set to the 65 536-set chunk in between), then the device-resident path."""
+    import torch
+    from relagn_b200 import _capi
+    from relagn_b200.batch import BatchEvaluator
+    grid = np.geomspace(1e-4, 1e3, 1001)
+    t = golden_tables()
+    ev = BatchEvaluator(grid, model="relagn", device=0, tables=t)
+    p = c4_params(125000, seed=11)
+    small, at_small = ev.evaluate(p[:300])
+    small, at_small = small.copy(), at_small.copy()
+    full, at_full = ev.evaluate(p)                      # slabs of 57 344, 32 768, 16 384, 8 192, 10 312 sets
+    full, at_full = full.copy(), at_full.copy()
+    assert full.shape == (125000, 1000)
+    ok = at_full[:, _capi.A["status"]] == 0
+    assert ok.mean() > 0.9 and np.isfinite(full[ok]).all() and (full[ok] >= 0).all()
+    np.testing.assert_array_equal(full[:300], small)
+    np.testing.assert_array_equal(at_full[:300], at_small)
+    # device-resident path: chunks of 65 536 + 59 464 sets
+    dev, _ = ev.evaluate_device(torch.from_numpy(p).to("cuda:0"))
+    np.testing.assert_array_equal(dev.cpu().numpy(), full)
+    # a slice from the middle of the batch, evaluated on its own
+    mid, _ = ev.evaluate(p[70000:70300])   # (>= 2 x #SM sets: below that a set is split over several CTAs)
+    np.testing.assert_array_equal(mid, full[70000:70300])
+
+
 def test_python_default_grid_rel(ctx, oracle, otab):
     """The Python class's own default grid (1999 bins, 1e-4..1e4 keV): the NC = 8 instantiation, relativistic."""
     grid = np.geomspace(1e-4, 1e4, 2000)
