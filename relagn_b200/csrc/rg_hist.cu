@@ -17,6 +17,9 @@
 
 static __host__ __device__ inline int hist_round_up2(int x) { return (x + 1) & ~1; }
 
+// one annulus as lane m prepares it for the warp
+struct PrepRec { double r1, r2; RingGeo geo; int flag, g, nsub, pad; };
+
 __global__ void __launch_bounds__(32 * HIST_WARPS, RG_HIST_MINB) hist_kernel(HistArgs A)
 {
     RG_DYN_SMEM(smem_raw);
@@ -24,24 +27,32 @@ __global__ void __launch_bounds__(32 * HIST_WARPS, RG_HIST_MINB) hist_kernel(His
     const int HSZ = hist_round_up2(A.nH + 24);
     double *Hslot = reinterpret_cast<double *>(smem_raw) + (size_t)warp * HSZ; // 8 zero pad | nH bins | zero pad
     for (int i = lane; i < HSZ; i += 32) Hslot[i] = 0.0;
+    PrepRec *prep = reinterpret_cast<PrepRec *>(reinterpret_cast<double *>(smem_raw) + (size_t)HIST_WARPS * HSZ) + 32 * warp;
     __syncwarp();
     const int set = blockIdx.x / A.NBH, blk = blockIdx.x - set * A.NBH;
     const SetRec &r = A.recs[set];
     if (r.status != RG_S_OK) return;
     const int n_tot = r.n_disc + r.n_warm + r.n_hot;
     const int g_warm0 = r.n_disc, g_hot0 = r.n_disc + r.n_warm;
-    TabSel ts;
-    rg_tab_select(ts, A.tab, r.a, r.inc);
+    // the table selection of the set (4 node planes, blend weights, row geometry: 26 registers' worth, the same for
+    // the whole CTA) lives in shared memory: at the 64-register budget of 32 warps per SM the compiler otherwise
+    // spills and rematerialises (r1q: 440 bytes of spill loads, S2R / address rebuilds = 10 % of the instructions)
+    __shared__ TabSel s_ts;
+    if (threadIdx.x == 0) rg_tab_select(s_ts, A.tab, r.a, r.inc);
+    __syncthreads();
+    const TabSel &ts = s_ts;
     const int wstride = HIST_WARPS * A.NBH, w0 = blk * HIST_WARPS + warp;
     const int n_mine = w0 < n_tot ? (n_tot - w0 + wstride - 1) / wstride : 0;
     for (int m0 = 0; m0 < n_mine; m0 += 32) {
         // lane m prepares this warp's annulus number m0 + m: its edges (relagn.py:731-776, :962-964) and whether the
         // reference sends it through kyconv (:992)
-        double p_r1 = 0, p_r2 = 0;
-        int p_flag = 0, p_g = 0, p_nsub = 1;
-        RingGeo p_geo; // of the annulus' only ring when p_nsub == 1 (most annuli)
-        p_geo.A = 0; p_geo.fr = 0; p_geo.s0 = 0; p_geo.s1 = 0;
+        // (the prepared values go through the warp's shared-memory table, not through registers + shuffles: 13
+        //  registers less across the ring loop)
+        __syncwarp(); // the previous pass has been read
         if (m0 + lane < n_mine) {
+            PrepRec pr;
+            pr.r1 = 0; pr.r2 = 0; pr.flag = 0; pr.g = 0; pr.nsub = 1;
+            pr.geo.A = 0; pr.geo.fr = 0; pr.geo.s0 = 0; pr.geo.s1 = 0; // of the annulus' only ring when nsub == 1 (most annuli)
             const int g = w0 + wstride * (m0 + lane);
             const int region = g < g_warm0 ? 0 : (g < g_hot0 ? 1 : 2);
             const int a = g - (region == 0 ? 0 : (region == 1 ? g_warm0 : g_hot0));
@@ -51,23 +62,22 @@ __global__ void __launch_bounds__(32 * HIST_WARPS, RG_HIST_MINB) hist_kernel(His
             it.start(lg_in, lg_out, r.dlog_r);
             double lo = 0, hi = 0;
             for (int q = 0; q <= a; q++) it.next(lo, hi);
-            p_r1 = pow(10.0, lo); p_r2 = pow(10.0, hi);
-            p_flag = (lo <= 3 && hi <= 3) ? 1 : 0;
-            p_g = g;
-            if (p_flag) {
-                const double lnr = log(p_r2 / p_r1);
-                p_nsub = rg_auto_nsub(p_r1, p_r2, lnr, A.dlnE);
-                if (p_nsub == 1) p_geo = rg_ring_geo(ts, p_r1, p_r2, lnr, 0, 1, 0.0, 0.0, 1.0);
+            pr.r1 = pow(10.0, lo); pr.r2 = pow(10.0, hi);
+            pr.flag = (lo <= 3 && hi <= 3) ? 1 : 0;
+            pr.g = g;
+            if (pr.flag) {
+                const double lnr = log(pr.r2 / pr.r1);
+                pr.nsub = rg_auto_nsub(pr.r1, pr.r2, lnr, A.dlnE);
+                if (pr.nsub == 1) pr.geo = rg_ring_geo(ts, pr.r1, pr.r2, lnr, 0, 1, 0.0, 0.0, 1.0);
             }
+            prep[lane] = pr;
         }
+        __syncwarp();
         const int mt = n_mine - m0 < 32 ? n_mine - m0 : 32;
         for (int mi = 0; mi < mt; mi++) {
-            const double r1 = __shfl_sync(RG_FULL, p_r1, mi), r2 = __shfl_sync(RG_FULL, p_r2, mi);
-            const int flag = __shfl_sync(RG_FULL, p_flag, mi), g = __shfl_sync(RG_FULL, p_g, mi);
-            const int nsub = __shfl_sync(RG_FULL, p_nsub, mi);
-            RingGeo geo;
-            geo.A = __shfl_sync(RG_FULL, p_geo.A, mi); geo.fr = __shfl_sync(RG_FULL, p_geo.fr, mi);
-            geo.s0 = __shfl_sync(RG_FULL, p_geo.s0, mi); geo.s1 = __shfl_sync(RG_FULL, p_geo.s1, mi);
+            const double r1 = prep[mi].r1, r2 = prep[mi].r2;
+            const int flag = prep[mi].flag, g = prep[mi].g, nsub = prep[mi].nsub;
+            const RingGeo geo = prep[mi].geo;
             double *row = A.hist + (size_t)(r.ann_base + g) * A.hstride;
             int kmn = 0, kmx = -1;
             if (flag) {
@@ -92,7 +102,7 @@ __global__ void __launch_bounds__(32 * HIST_WARPS, RG_HIST_MINB) hist_kernel(His
 int rg_launch_hist(const HistArgs &A, cudaStream_t st)
 {
     if (A.P == 0) return RG_OK;
-    size_t smem = (size_t)HIST_WARPS * hist_round_up2(A.nH + 24) * sizeof(double);
+    size_t smem = (size_t)HIST_WARPS * (hist_round_up2(A.nH + 24) * sizeof(double) + 32 * sizeof(PrepRec));
     RG_CUDA_OK(cudaFuncSetAttribute(hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     RG_LAUNCH(hist_kernel, dim3((unsigned)((long)A.P * A.NBH)), dim3(32 * HIST_WARPS), smem, st, A);
     RG_CUDA_OK(cudaGetLastError());
