@@ -10,7 +10,9 @@
 #include "rg_kernels.h"
 #include "rg_transfer.cuh"
 
+#ifndef HIST_WARPS
 #define HIST_WARPS 8
+#endif
 #ifndef RG_HIST_MINB
 #define RG_HIST_MINB 4 // resident CTAs per SM the register budget is cut for
 #endif
