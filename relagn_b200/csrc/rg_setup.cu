@@ -283,6 +283,19 @@ setup_kernel(const double *__restrict__ params, int P, int model, double dr_dex,
 //   farr arena: [sys][nE] = the Comptonised spectrum on the caller's energy grid
 // Called by all 32 lanes of a warp together (`valid` = this lane has a system): the back substitution walks the
 // scratch rows in warp-uniform order so that a warp's loads of one row stay contiguous.
+#ifndef RG_NTH_WARPMAJOR
+#define RG_NTH_WARPMAJOR 1
+#endif
+#if RG_NTH_WARPMAJOR
+// warp-major scratch [warp][row][gamma | g][32 lanes]: the 512 bytes a warp writes per row follow each other in
+// memory, so the forward sweep streams through its own 450 kB region and the back substitution walks it in reverse --
+// DRAM pages see runs of rows instead of one 256-byte burst per row-major plane row (758 kB apart)
+#define SC_GAM(j) sc_gam[((size_t)(sys >> 5) * RG_NTH + (size_t)(j)) * 64 + (sys & 31)]
+#define SC_G(j) sc_gam[((size_t)(sys >> 5) * RG_NTH + (size_t)(j)) * 64 + 32 + (sys & 31)]
+#else
+#define SC_GAM(j) sc_gam[(size_t)(j) * sc_stride + sys]
+#define SC_G(j) sc_g[(size_t)(j) * sc_stride + sys]
+#endif
 __device__ static void nthcomp_system(bool valid, const SetRec &r, int which, const double *p10tab,
                                       double *__restrict__ sc_gam, double *__restrict__ sc_g,
                                       double *__restrict__ sc_bet, size_t sc_stride, int slot, double *__restrict__ spt,
@@ -354,7 +367,7 @@ __device__ static void nthcomp_system(bool valid, const SetRec &r, int which, co
         if (0 < jnr - 1) b0 = 1.0 / tautom / (1.0 + tautom * rel / 3.0);
         else if (0 < jrel) { double flz = 1 - (w - xnr) / (xr - xnr); b0 = 1.0 / tautom / (1.0 + tautom * rel / 3.0 * flz); }
         else b0 = 1.0 / tautom;
-        if (valid) { sc_bet[sys] = b0; sc_gam[sys] = 0; sc_g[sys] = 0; }
+        if (valid) { sc_bet[sys] = b0; SC_GAM(0) = 0; SC_G(0) = 0; }
     }
     const double itau = 1.0 / tautom, rxr = 1.0 / (xr - xnr), itbb = 1.0 / tempbb, todx = tod / xmin;
     const double third = 1.0 / 3.0;
@@ -404,8 +417,7 @@ __device__ static void nthcomp_system(bool valid, const SetRec &r, int which, co
         const double ralp = 1.0 / alp;
         if (j == 1) gj = dj * ralp; else gj = (dj - cj * g_prev) * ralp;
         double gamj = aj * ralp;
-        size_t o = (size_t)j * sc_stride + sys;
-        RG_STCS(&sc_gam[o], gamj); RG_STCS(&sc_g[o], gj); // streamed: read back once
+        RG_STCS(&SC_GAM(j), gamj); RG_STCS(&SC_G(j), gj); // streamed: read back once
         gam_prev = gamj; g_prev = gj;
         xm = x0; x0 = xp; c2m = c2j; tow1_prev = tow1;
     }
@@ -425,8 +437,7 @@ __device__ static void nthcomp_system(bool valid, const SetRec &r, int which, co
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         if (jtop - q >= 1 && jtop - q <= jtop_me) {
-            size_t o = (size_t)(jtop - q) * sc_stride + sys;
-            gg[q] = RG_LDCS(&sc_g[o]); gm[q] = RG_LDCS(&sc_gam[o]);
+            gg[q] = RG_LDCS(&SC_G(jtop - q)); gm[q] = RG_LDCS(&SC_GAM(jtop - q));
         }
     }
     for (int jj = jtop; jj >= 1;) {
@@ -436,8 +447,7 @@ __device__ static void nthcomp_system(bool valid, const SetRec &r, int which, co
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             if (jn - q >= 1 && jn - q <= jtop_me) {
-                size_t o = (size_t)(jn - q) * sc_stride + sys;
-                ngg[q] = RG_LDCS(&sc_g[o]); ngm[q] = RG_LDCS(&sc_gam[o]);
+                ngg[q] = RG_LDCS(&SC_G(jn - q)); ngm[q] = RG_LDCS(&SC_GAM(jn - q));
             }
         }
 #pragma unroll
