@@ -115,6 +115,7 @@ __device__ inline void convolve8(const double *Hs0, int K_LO, int nH, int kmin, 
     for (int k = k0; k <= kmax; k += 8) {
 #pragma unroll
         for (int u = 0; u < 8; u++) {
+            if (u == 4 && k + 4 > kmax) break; // the last group's upper half holds no tap (warp-uniform)
             const R h = (R)Hk[u];
 #pragma unroll
             for (int c = 0; c < 8; c++) tmp[c] = fma(h, w[(c - u + 8) % 8], tmp[c]);
