@@ -68,6 +68,9 @@ int rg_spectrum_pick_warps(int NC, int nH, int HL, int HH, int fp32)
     return 0;
 }
 
+#ifndef RG_CONV_HALFSTART
+#define RG_CONV_HALFSTART 1
+#endif
 #ifndef RG_WARM_PREFETCH
 #define RG_WARM_PREFETCH 1
 #endif
@@ -109,10 +112,34 @@ __device__ inline void convolve8(const double *Hs0, int K_LO, int nH, int kmin, 
     const int k0 = g * 8;
     const double *Hk = Hs0 + (k0 - K_LO);
     R w[8];
+    const R *pg = base - g - 1;
+#if RG_CONV_HALFSTART
+    // the first group's lower half holds no tap when kmin sits in its upper half (warp-uniform): enter the window
+    // in the state it has after four taps and run taps 4..7 only
+    const bool half = kmin - k0 >= 4;
+#pragma unroll
+    for (int c = 0; c < 4; c++) w[c] = base[c * RS - g];
+#pragma unroll
+    for (int c = 4; c < 8; c++) w[c] = half ? pg[c * RS] : base[c * RS - g];
+    int kb = k0;
+    if (half) {
+#pragma unroll
+        for (int u = 4; u < 8; u++) {
+            const R h = (R)Hk[u];
+#pragma unroll
+            for (int c = 0; c < 8; c++) tmp[c] = fma(h, w[(c - u + 8) % 8], tmp[c]);
+            w[(7 - u) % 8] = pg[((7 - u) % 8) * RS];
+        }
+        Hk += 8;
+        pg -= 1;
+        kb += 8;
+    }
+    for (int k = kb; k <= kmax; k += 8) {
+#else
 #pragma unroll
     for (int c = 0; c < 8; c++) w[c] = base[c * RS - g];
-    const R *pg = base - g - 1;
     for (int k = k0; k <= kmax; k += 8) {
+#endif
 #pragma unroll
         for (int u = 0; u < 8; u++) {
             if (u == 4 && k + 4 > kmax) break; // the last group's upper half holds no tap (warp-uniform)
