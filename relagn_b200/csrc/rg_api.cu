@@ -73,6 +73,8 @@ struct rg_ctx {
     size_t partial_n = 0;
     double *d_hist = nullptr; // shift-histogram arena [annuli of the chunk][hstride]
     size_t hist_n = 0;
+    double *d_edges = nullptr; // radial bin edges [annuli of the chunk] as (lo, hi) pairs
+    size_t edges_n = 0;
     cudaStream_t side = nullptr;            // hist_kernel runs here, next to the Kompaneets solves on the caller's stream
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // kyconv seam scratch
@@ -164,7 +166,7 @@ extern "C" void rg_ctx_destroy(rg_ctx *c)
     cudaDeviceSynchronize();
     free_dev(c->d_grid); free_dev(c->d_tab); free_dev(c->d_tab2); free_dev(c->d_tabmeta); free_dev(c->d_rowrange); free_dev(c->d_p10); free_dev(c->d_recs);
     free_dev(c->d_counter); free_dev(c->d_syslist); free_dev(c->d_sptot); free_dev(c->d_farr); free_dev(c->d_header); free_dev(c->d_sc);
-    free_dev(c->d_rq); free_dev(c->d_queue); free_dev(c->d_partial); free_dev(c->d_hist); free_dev(c->d_kyH); free_dev(c->d_kyin); free_dev(c->d_kyout);
+    free_dev(c->d_rq); free_dev(c->d_queue); free_dev(c->d_partial); free_dev(c->d_hist); free_dev(c->d_edges); free_dev(c->d_kyH); free_dev(c->d_kyin); free_dev(c->d_kyout);
     free_dev(c->d_stage_par); free_dev(c->d_stage_out); free_dev(c->d_stage_attr); free_dev(c->d_stats);
     free_dev(c->d_ebins); free_dev(c->d_ear); free_dev(c->d_sl_off); free_dev(c->d_ell_col); free_dev(c->d_ell_val);
     free_dev(c->d_counts); free_dev(c->d_sigma); free_dev(c->d_slab); free_dev(c->d_stage_stat); free_dev(c->d_pos0);
@@ -703,6 +705,11 @@ extern "C" int rg_eval_batch(rg_ctx *c, const double *d_params, int P, int model
         // The shift histograms (hist_kernel) and the Kompaneets solves (nthcomp kernels) both depend on the setup
         // kernel only and are both latency bound: they run side by side, the histograms on the context's side stream
         // (with profiling on they are serialised on the caller's stream so that the event brackets mean something).
+        // radial bin edges of every annulus of the chunk, for hist_kernel and spectrum_kernel
+        RG_TRY(ensure_dev(&c->d_edges, &c->edges_n, (size_t)2 * std::max(c->h_counter[1], 1)));
+        RG_TRY(rg_launch_edges(c->d_recs, n, reinterpret_cast<double2 *>(c->d_edges), st));
+        c->launches++;
+        A.edges = reinterpret_cast<const double2 *>(c->d_edges);
         bool forked = false;
         unsigned long long *stats = c->profile ? c->d_stats : nullptr;
         int nth_run = c->nth_threads; // threads of the persistent nthcomp grid
@@ -729,9 +736,9 @@ extern "C" int rg_eval_batch(rg_ctx *c, const double *d_params, int P, int model
             RG_TRY(ensure_dev(&c->d_hist, &c->hist_n, hist_need));
             HistArgs H;
             memset(&H, 0, sizeof H);
-            H.recs = c->d_recs; H.P = n; H.tab = c->td; H.dlnE = c->gd.dlnE; H.K_LO = A.K_LO; H.nH = A.nH;
+            H.recs = c->d_recs; H.P = n; H.tab = c->td; H.dlnE = c->gd.dlnE; H.inv_dlnE = 1.0 / c->gd.dlnE; H.K_LO = A.K_LO; H.nH = A.nH;
             H.NBH = n >= 2 * c->sm_count ? 1 : (int)std::min<long>(32, (4L * c->sm_count + n - 1) / n);
-            H.hist = c->d_hist; H.hstride = A.hstride;
+            H.hist = c->d_hist; H.hstride = A.hstride; H.edges = A.edges;
             cudaStream_t hs = st;
             if (!c->profile && nsys > 0 && !getenv("RG_NO_SIDE_STREAM")) {
                 RG_CUDA_OK(cudaEventRecord(c->ev_fork, st));

@@ -58,12 +58,9 @@ __global__ void __launch_bounds__(32 * HIST_WARPS, RG_HIST_MINB) hist_kernel(His
             const int g = w0 + wstride * (m0 + lane);
             const int region = g < g_warm0 ? 0 : (g < g_hot0 ? 1 : 2);
             const int a = g - (region == 0 ? 0 : (region == 1 ? g_warm0 : g_hot0));
-            const double lg_in = region == 0 ? r.lg_rw : (region == 1 ? r.lg_rh : r.lg_risco);
-            const double lg_out = region == 0 ? r.lg_rout : (region == 1 ? r.lg_rw : r.lg_rh);
-            BinIter it;
-            it.start(lg_in, lg_out, r.dlog_r);
-            double lo = 0, hi = 0;
-            for (int q = 0; q <= a; q++) it.next(lo, hi);
+            (void)a;
+            const double2 eg = __ldg(A.edges + r.ann_base + g); // (lo, hi) in log10 r (edges_kernel)
+            const double lo = eg.x, hi = eg.y;
             pr.r1 = pow(10.0, lo); pr.r2 = pow(10.0, hi);
             pr.flag = (lo <= 3 && hi <= 3) ? 1 : 0;
             pr.g = g;
@@ -84,7 +81,7 @@ __global__ void __launch_bounds__(32 * HIST_WARPS, RG_HIST_MINB) hist_kernel(His
             int kmn = 0, kmx = -1;
             if (flag) {
                 warp_build_rings(Hslot + 8, A.K_LO, A.nH, ts, r1, r2, A.dlnE, nsub, 0, 1, 0.0, 0.0, 1.0, 0.0, 1.0, kmn, kmx,
-                                 nsub == 1 ? &geo : nullptr);
+                                 nsub == 1 ? &geo : nullptr, A.inv_dlnE);
                 if (kmn < A.K_LO) kmn = A.K_LO;
                 if (kmx > A.K_LO + A.nH - 1) kmx = A.K_LO + A.nH - 1;
                 __syncwarp();

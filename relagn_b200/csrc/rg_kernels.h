@@ -52,6 +52,7 @@ struct SpecArgs {
     double *partial;      // NB > 1: [P][NB][ncomp][nE] partial sums, folded by the reduce kernel
     const double *hist;   // shift histograms built by hist_kernel: [annulus][hstride], slot 0 = (first shift, count)
     int hstride;
+    const double2 *edges; // (lo, hi) of every annulus in log10 r: [annulus], rows as in the histogram arena (edges_kernel)
     int *queue;           // device work-queue counter (zeroed before the launch)
     int warps;            // warps per CTA
     unsigned long long *stats; // optional device counters [4]: sum W_ann, conv annuli, sum jmax, systems
@@ -77,13 +78,17 @@ struct HistArgs {
     const SetRec *recs;
     int P;
     TabDesc tab;
-    double dlnE;
+    double dlnE, inv_dlnE;
     int K_LO, nH;  // widest support over all table nodes
     int NBH;       // CTAs per parameter set
     double *hist;  // [total annuli][hstride]
     int hstride;   // >= nH + 1
+    const double2 *edges; // [total annuli] (lo, hi) in log10 r (edges_kernel)
 };
 int rg_launch_hist(const HistArgs &A, cudaStream_t st);
+// radial bin edges of every annulus of every set (relagn.py:731-776), one thread per (set, region): the chain of
+// repeated subtractions is walked once here instead of by every consumer lane
+int rg_launch_edges(const SetRec *recs, int P, double2 *edges, cudaStream_t st);
 
 // generic kyconv seam: histogram of one (possibly wide) annulus into d_H[0..nH) (shift k = K_LO + index)
 int rg_launch_ky_hist(const TabDesc &tab, double a, double theta_o, double r1, double r2, double alpha, double beta,

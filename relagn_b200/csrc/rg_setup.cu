@@ -597,6 +597,37 @@ int rg_launch_setup(const double *d_params, int P, int model, double dr_dex, Set
     return RG_OK;
 }
 
+// Radial bin edges (relagn.py:731-776: top-down by repeated subtraction, innermost bin widened) of every annulus,
+// written once per (set, region) to edges[ann_base + g] = (lo, hi) in log10 r; g counts disc, warm, hot top-down.
+// hist_kernel and spectrum_kernel used to walk this chain per lane up to its own annulus (O(N^2) per set).
+__global__ void __launch_bounds__(128) edges_kernel(const SetRec *__restrict__ recs, int P, double2 *__restrict__ edges)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 3 * P) return;
+    const int set = t / 3, region = t - 3 * set;
+    const SetRec &r = recs[set];
+    if (r.status != RG_S_OK) return;
+    const double lg_in = region == 0 ? r.lg_rw : (region == 1 ? r.lg_rh : r.lg_risco);
+    const double lg_out = region == 0 ? r.lg_rout : (region == 1 ? r.lg_rw : r.lg_rh);
+    const int n = region == 0 ? r.n_disc : (region == 1 ? r.n_warm : r.n_hot);
+    double2 *e = edges + r.ann_base + (region == 0 ? 0 : (region == 1 ? r.n_disc : r.n_disc + r.n_warm));
+    BinIter it;
+    it.start(lg_in, lg_out, r.dlog_r);
+    double lo = 0, hi = 0;
+    for (int a = 0; a < n; a++) {
+        it.next(lo, hi);
+        e[a] = make_double2(lo, hi);
+    }
+}
+
+int rg_launch_edges(const SetRec *recs, int P, double2 *edges, cudaStream_t st)
+{
+    if (P <= 0) return RG_OK;
+    RG_LAUNCH(edges_kernel, dim3((3 * P + 127) / 128), dim3(128), 0, st, recs, P, edges);
+    RG_CUDA_OK(cudaGetLastError());
+    return RG_OK;
+}
+
 // The two counters of the setup kernel reach the host by a store from the device into pinned (mapped) memory: a
 // cudaMemcpy D2H would queue on the copy engine behind whatever large copy is in flight there -- the previous slab's
 // spectra in rg_eval_batch_host, a caller's own transfer -- and the chunk would wait for all of it.

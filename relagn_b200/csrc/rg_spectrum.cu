@@ -433,12 +433,8 @@ __global__ void __launch_bounds__(NC <= 4 ? (sizeof(R) == 4 ? 512 : 32 * RG_SPEC
                 if (m0 + lane < n_rounds && g < g_end) {
                     const int region = g < g_warm0 ? 0 : (g < g_hot0 ? 1 : 2);
                     const int a = g - (region == 0 ? 0 : (region == 1 ? g_warm0 : g_hot0));
-                    const double lg_in = region == 0 ? r.lg_rw : (region == 1 ? r.lg_rh : r.lg_risco);
-                    const double lg_out = region == 0 ? r.lg_rout : (region == 1 ? r.lg_rw : r.lg_rh);
-                    BinIter it;
-                    it.start(lg_in, lg_out, r.dlog_r);
-                    double lo = 0, hi = 0;
-                    for (int q = 0; q <= a; q++) it.next(lo, hi);
+                    const double2 eg = __ldg(A.edges + r.ann_base + g); // (lo, hi) in log10 r (edges_kernel)
+                    const double lo = eg.x, hi = eg.y;
                     double r1 = pow(10.0, lo), r2 = pow(10.0, hi);
                     double rmid = pow(10.0, lo + r.dlog_r / 2);
                     double T4 = rg_tnt4(nt, rmid);

@@ -23,6 +23,7 @@ struct TabSel {
     size_t plane;
     int NR, NPHI;
     double inv_dl;
+    double dphi; // 2 pi / NPHI
 };
 
 __device__ inline void rg_tab_select(TabSel &ts, const TabDesc &t, double a, double theta_o)
@@ -52,6 +53,7 @@ __device__ inline void rg_tab_select(TabSel &ts, const TabDesc &t, double a, dou
     ts.w00 = (1 - fa) * (1 - fi); ts.w01 = (1 - fa) * fi; ts.w10 = fa * (1 - fi); ts.w11 = fa * fi;
     ts.risco = risco; ts.rh = 1 + sqrt(1 - a * a);
     ts.plane = plane; ts.NR = t.NR; ts.NPHI = t.NPHI; ts.inv_dl = 1.0 / t.dl;
+    ts.dphi = 2 * RGK_PI / t.NPHI;
 }
 
 struct RingRow { int s0, s1; double fr; };
@@ -241,14 +243,16 @@ __device__ inline void warp_deposit(double *Hs, int K_LO, int nH, double sa, dou
 // rings) to Hs.  alpha, beta, rb: kyconv's broken power-law emissivity; zs: redshift in units of shift bins.
 __device__ inline void warp_build_rings(double *Hs, int K_LO, int nH, const TabSel &ts, double r1, double r2, double dlnE,
                                         int nsub, int m_begin, int m_step, double alpha, double beta, double rb, double zs,
-                                        double weight, int &kmin_out, int &kmax_out, const RingGeo *single = nullptr)
+                                        double weight, int &kmin_out, int &kmax_out, const RingGeo *single = nullptr,
+                                        double inv_dlnE_in = 0.0)
 {
     // single: geometry of the annulus' only ring when the caller has it already (nsub == 1, warp-uniform)
     const int lane = threadIdx.x & 31;
     const int NP = ts.NPHI, nq = NP >> 5;
     const double lnr = single ? 0.0 : log(r2 / r1);
-    const double dphi = 2 * RGK_PI / NP;
-    const double inv_dlnE = 1.0 / dlnE; // shift in bins = ln g / dlnE, as one multiplication per sample
+    const double dphi = ts.dphi;
+    // shift in bins = ln g / dlnE, as one multiplication per sample (the caller may pass the reciprocal)
+    const double inv_dlnE = inv_dlnE_in != 0.0 ? inv_dlnE_in : 1.0 / dlnE;
     int kf_min = RG_IMAX, kl_max = -RG_IMAX;
     const int n_mine = m_begin < nsub ? (nsub - m_begin + m_step - 1) / m_step : 0;
     for (int m0 = 0; m0 < n_mine; m0 += 32) {
