@@ -400,7 +400,7 @@ __device__ static void nthcomp_system(bool valid, const SetRec &r, int which, co
         double c2j = (w1j * w1j * w1j * w1j) * __drcp_rn(1.0 + 4.60 * w1j + 1.1 * w1j * w1j);
         // rel, bet at j
         const double betj = bet_at(j, x0);
-        double dph = (j < jmaxth) ? planck * (x0 * x0) * __drcp_rn(exp(x0 * itbb) - 1) : 0.0;
+        double dph = (j < jmaxth) ? planck * (x0 * x0) * __drcp_rn(rg_exp_pos(x0 * itbb) - 1) : 0.0;
         // coefficients (pyNTHCOMP.py:210-221)
         const double tow1 = todx * p10tab[RG_P10_RW1 + j], tow2 = tow1_prev;
         double aj = -c20 * c2j * (tow1 + 0.5);

@@ -86,38 +86,6 @@ __device__ inline T warp_sum(T v)
 // Planck function of one bin: pi * (2 h nu^3 / c^2) / (exp(x) - 1), x = h nu / kT (relagn.py:45-50).
 // FP64: exp(x) - 1 as the reference writes it, then a reciprocal multiply (1/inf = 0 past the overflow point).
 // FP32 mode: expm1f keeps the relative accuracy at small x, where exp(x) - 1 would cancel in single precision.
-#ifndef RG_OWN_EXP
-#define RG_OWN_EXP 1
-#endif
-#if RG_OWN_EXP && !defined(RG_HOSTSIM)
-// exp(x) for x >= 0 with the scheme and coefficients of CUDA's own exp() fast path (n = rint(x log2 e), two-step
-// Cody-Waite reduction, degree-11 polynomial, exponent insertion) -- bit-identical to it below x = 708 -- but with the
-// coefficients in constant memory: the library version materialises every 64-bit coefficient with two UMOVs in front
-// of each DFMA (22 issue slots per call, r1q: UMOV = 12 % of this kernel's instructions) and carries a slow-path
-// branch.  Overflow: x is clamped to 709.9, where 2^(n-1) p 2 rounds to +inf exactly as exp() does beyond 709.78.
-static __constant__ unsigned long long RG_EXPB[13] = {
-    0x3ff71547652b82feULL, 0x3fe62e42fefa39efULL, 0x3c7abc9e3b39803fULL, // log2 e, ln 2 (high), ln 2 (low)
-    0x3e5ade1569ce2bdfULL, 0x3e928af3fca213eaULL, 0x3ec71dee62401315ULL, 0x3efa01997c89eb71ULL, 0x3f2a01a014761f65ULL,
-    0x3f56c16c1852b7afULL, 0x3f81111111122322ULL, 0x3fa55555555502a1ULL, 0x3fc5555555555511ULL, 0x3fe000000000000bULL};
-#define RG_EK(i) __longlong_as_double((long long)RG_EXPB[i])
-__device__ __forceinline__ double rg_exp_pos(double x)
-{
-    const double MAGIC = 6755399441055744.0; // 1.5 * 2^52
-    const double xc = x > 709.9 ? 709.9 : x;
-    const double t = fma(xc, RG_EK(0), MAGIC);
-    const int n = __double2loint(t);
-    const double r = t - MAGIC;
-    double f = fma(r, -RG_EK(1), xc);
-    f = fma(r, -RG_EK(2), f);
-    double p = fma(f, RG_EK(3), RG_EK(4));
-    p = fma(p, f, RG_EK(5)); p = fma(p, f, RG_EK(6)); p = fma(p, f, RG_EK(7)); p = fma(p, f, RG_EK(8));
-    p = fma(p, f, RG_EK(9)); p = fma(p, f, RG_EK(10)); p = fma(p, f, RG_EK(11)); p = fma(p, f, RG_EK(12));
-    p = fma(p, f, 1.0); p = fma(p, f, 1.0);
-    return __hiloint2double(__double2hiint(p) + ((n - 1) << 20), __double2loint(p)) * 2.0;
-}
-#else
-__device__ __forceinline__ double rg_exp_pos(double x) { return exp(x); }
-#endif
 __device__ inline double planck_bin(double hnu, double bbpre, double inv_kT)
 {
     double ef = rg_exp_pos(hnu * inv_kT) - 1;

@@ -125,6 +125,15 @@ __device__ inline RingGeo rg_ring_geo(const TabSel &ts, double r1, double r2, do
     return g;
 }
 
+// ln g of a table sample: rg_log_pos (bit-identical to log(), fewer issue slots); RG_HIST_OWN_LOG=0 for A/B
+#ifndef RG_HIST_OWN_LOG
+#define RG_HIST_OWN_LOG 1
+#endif
+#if RG_HIST_OWN_LOG
+#define RG_LOG_G(g) rg_log_pos(g)
+#else
+#define RG_LOG_G(g) log(g)
+#endif
 #define RG_FULL 0xffffffffu
 #define RG_IMAX 0x7fffffff
 
@@ -200,9 +209,17 @@ __device__ inline void warp_deposit(double *Hs, int K_LO, int nH, double sa, dou
     const unsigned heads = __ballot_sync(RG_FULL, lane == 0 || kfirst != kprev);
     const int start = 31 - __clz((int)(heads & (0xffffffffu >> (31 - lane))));
     const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
-    const unsigned peers = __match_any_sync(RG_FULL, tail ? kfirst : (-0x40000000 - lane));
-    const int myround = tail ? __popc(peers & ((1u << lane) - 1u)) : -1;
-    const int nrounds = __reduce_max_sync(RG_FULL, myround) + 1;
+    // first bins monotone along the lanes (the usual case: a ring's half is one monotone branch of g(phi)): equal
+    // first bins are neighbours, every bin has one run and one round does it -- no match needed
+    int myround, nrounds;
+    if (__all_sync(RG_FULL, lane == 0 || kfirst >= kprev) || __all_sync(RG_FULL, lane == 0 || kfirst <= kprev)) {
+        myround = tail ? 0 : -1;
+        nrounds = 1;
+    } else {
+        const unsigned peers = __match_any_sync(RG_FULL, tail ? kfirst : (-0x40000000 - lane));
+        myround = tail ? __popc(peers & ((1u << lane) - 1u)) : -1;
+        nrounds = __reduce_max_sync(RG_FULL, myround) + 1;
+    }
     const int nbmax = __reduce_max_sync(RG_FULL, nb);
     const int maxrun = __reduce_max_sync(RG_FULL, lane - start + 1);
     double carry = 0.0; // weight the previous interval hands up to the first bin of this group
@@ -244,7 +261,7 @@ __device__ inline void warp_deposit(double *Hs, int K_LO, int nH, double sa, dou
 __device__ inline void warp_build_rings(double *Hs, int K_LO, int nH, const TabSel &ts, double r1, double r2, double dlnE,
                                         int nsub, int m_begin, int m_step, double alpha, double beta, double rb, double zs,
                                         double weight, int &kmin_out, int &kmax_out, const RingGeo *single = nullptr,
-                                        double inv_dlnE_in = 0.0)
+                                        double inv_dlnE_in = 0.0, volatile double *stash = nullptr)
 {
     // single: geometry of the annulus' only ring when the caller has it already (nsub == 1, warp-uniform)
     const int lane = threadIdx.x & 31;
@@ -267,20 +284,29 @@ __device__ inline void warp_build_rings(double *Hs, int K_LO, int nH, const TabS
             double g, jn;
             rg_ring_sample(ts, s0, s1, fr, lane, g, jn);
             const double cW = 0.5 * dphi * A * weight; // segment weight = (w_t + w_{t+1}) cW
-            double s_cur = log(g) * inv_dlnE + zs, w_cur = jn * g * g * g;
-            const double s_first = __shfl_sync(RG_FULL, s_cur, 0), w_first = __shfl_sync(RG_FULL, w_cur, 0);
+            double s_cur = RG_LOG_G(g) * inv_dlnE + zs, w_cur = jn * g * g * g;
+            // stash (72 doubles of the warp's shared memory, optional): what the NEXT deposit needs -- the following
+            // chunk's samples and the ring's first sample -- waits there instead of in 8 registers while the current
+            // deposit, the most register-hungry part, runs
+            double s_first = __shfl_sync(RG_FULL, s_cur, 0), w_first = __shfl_sync(RG_FULL, w_cur, 0);
+            if (stash && lane == 0) { stash[64] = s_first; stash[65] = w_first; }
             for (int q = 0; q < nq; q++) {
                 double s_nxt = 0, w_nxt = 0, sn0, wn0;
                 if (q + 1 < nq) {
                     rg_ring_sample(ts, s0, s1, fr, lane + 32 * (q + 1), g, jn);
-                    s_nxt = log(g) * inv_dlnE + zs; w_nxt = jn * g * g * g;
+                    s_nxt = RG_LOG_G(g) * inv_dlnE + zs; w_nxt = jn * g * g * g;
                     sn0 = __shfl_sync(RG_FULL, s_nxt, 0); wn0 = __shfl_sync(RG_FULL, w_nxt, 0);
+                    if (stash) { stash[lane] = s_nxt; stash[32 + lane] = w_nxt; }
+                } else if (stash) {
+                    __syncwarp();
+                    sn0 = stash[64]; wn0 = stash[65];
                 } else { sn0 = s_first; wn0 = w_first; }
                 double sb = __shfl_down_sync(RG_FULL, s_cur, 1), wb = __shfl_down_sync(RG_FULL, w_cur, 1);
                 if (lane == 31) { sb = sn0; wb = wn0; }
                 const double W = (w_cur + wb) * cW;
                 warp_deposit(Hs, K_LO, nH, s_cur, sb, W, kf_min, kl_max);
-                s_cur = s_nxt; w_cur = w_nxt;
+                if (stash) { s_cur = stash[lane]; w_cur = stash[32 + lane]; }
+                else { s_cur = s_nxt; w_cur = w_nxt; }
             }
         }
     }
