@@ -828,14 +828,14 @@ extern "C" int rg_eval_batch_host(rg_ctx *c, const double *params, int P, int mo
         cudaMemcpyAsync(out + (size_t)p0 * per_out, dslab, (size_t)n * per_out * sizeof(double), cudaMemcpyDeviceToHost,
                         copy_st);
         cudaEventRecord(freed[slab], copy_st);
+        if (attrs) // the slab's attributes ride behind its spectra
+            cudaMemcpyAsync(attrs + (size_t)p0 * RG_NATTR, c->d_stage_attr + (size_t)p0 * RG_NATTR,
+                            (size_t)n * RG_NATTR * sizeof(double), cudaMemcpyDeviceToHost, copy_st);
         used[slab] = true;
         p0 += n;
     }
     cudaStreamSynchronize(copy_st);
     if (trace) fprintf(stderr, "[rg host] last D2H done at %.2f ms\n", now_ms() - t_begin);
-    if (rc == RG_OK && attrs) {
-        cudaMemcpyAsync(attrs, c->d_stage_attr, (size_t)P * RG_NATTR * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
-    }
     cudaStreamSynchronize(c->stream);
     for (int i = 0; i < 2; i++) cudaEventDestroy(freed[i]);
     cudaStreamDestroy(copy_st);
