@@ -1,47 +1,12 @@
+// Bit-exactness check of rg_exp_pos (rg_common.cuh) against CUDA's exp() -- run on the GPU box:
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I relagn_b200/csrc -o /tmp/ec tools/exp_check.cu && /tmp/ec
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cmath>
 #include <vector>
-__constant__ double RG_EXPC[16] = {
-    1.4426950408889634074,            // log2(e)
-    -6.93147180369123816490e-01,      // -ln2 hi
-    -1.90821492927058770002e-10,      // -ln2 lo   (placeholders, replaced below by bit patterns)
-};
-__device__ __forceinline__ double bits(unsigned hi, unsigned lo) { return __hiloint2double((int)hi, (int)lo); }
-__constant__ unsigned long long RG_EXPB[14] = {
-    0x3ff71547652b82feULL, // log2 e
-    0x3fe62e42fefa39efULL, // ln2 hi
-    0x3c7abc9e3b39803fULL, // ln2 lo
-    0x3e5ade1569ce2bdfULL, // c11
-    0x3e928af3fca213eaULL, // c10
-    0x3ec71dee62401315ULL, // c9
-    0x3efa01997c89eb71ULL, // c8
-    0x3f2a01a014761f65ULL, // c7
-    0x3f56c16c1852b7afULL, // c6
-    0x3f81111111122322ULL, // c5
-    0x3fa55555555502a1ULL, // c4
-    0x3fc5555555555511ULL, // c3
-    0x3fe000000000000bULL, // c2
-    0ULL};
-__device__ __forceinline__ double K(int i) { return __longlong_as_double((long long)RG_EXPB[i]); }
-__device__ __forceinline__ double exp_pos(double x)
-{
-    const double MAGIC = 6755399441055744.0;
-    const double xc = fmin(x, 709.9);
-    const double t = fma(xc, K(0), MAGIC);
-    const int n = __double2loint(t);
-    const double r = t - MAGIC;
-    double f = fma(r, -K(1), xc);
-    f = fma(r, -K(2), f);
-    double p = fma(f, K(3), K(4));
-    p = fma(p, f, K(5)); p = fma(p, f, K(6)); p = fma(p, f, K(7)); p = fma(p, f, K(8)); p = fma(p, f, K(9));
-    p = fma(p, f, K(10)); p = fma(p, f, K(11)); p = fma(p, f, K(12));
-    p = fma(p, f, 1.0); p = fma(p, f, 1.0);
-    const double s = __hiloint2double(__double2hiint(p) + ((n - 1) << 20), __double2loint(p));
-    return s * 2.0;
-}
+#include "rg_common.cuh"
 __global__ void k_ref(const double *x, double *y, int n) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) y[i] = exp(x[i]); }
-__global__ void k_my(const double *x, double *y, int n) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) y[i] = exp_pos(x[i]); }
+__global__ void k_my(const double *x, double *y, int n) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) y[i] = rg_exp_pos(x[i]); }
 int main()
 {
     const int N = 1 << 22;
