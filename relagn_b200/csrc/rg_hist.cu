@@ -13,9 +13,6 @@
 #ifndef HIST_WARPS
 #define HIST_WARPS 8
 #endif
-#ifndef RG_HIST_STASH
-#define RG_HIST_STASH 1
-#endif
 #ifndef RG_HIST_MINB
 #define RG_HIST_MINB 4 // resident CTAs per SM the register budget is cut for
 #endif
@@ -33,7 +30,6 @@ __global__ void __launch_bounds__(32 * HIST_WARPS, RG_HIST_MINB) hist_kernel(His
     double *Hslot = reinterpret_cast<double *>(smem_raw) + (size_t)warp * HSZ; // 8 zero pad | nH bins | zero pad
     for (int i = lane; i < HSZ; i += 32) Hslot[i] = 0.0;
     PrepRec *prep = reinterpret_cast<PrepRec *>(reinterpret_cast<double *>(smem_raw) + (size_t)HIST_WARPS * HSZ) + 32 * warp;
-    volatile double *stash = reinterpret_cast<double *>(smem_raw) + (size_t)HIST_WARPS * HSZ + (size_t)HIST_WARPS * 32 * (sizeof(PrepRec) / 8) + 72 * warp;
     __syncwarp();
     const int set = blockIdx.x / A.NBH, blk = blockIdx.x - set * A.NBH;
     const SetRec &r = A.recs[set];
@@ -85,7 +81,7 @@ __global__ void __launch_bounds__(32 * HIST_WARPS, RG_HIST_MINB) hist_kernel(His
             int kmn = 0, kmx = -1;
             if (flag) {
                 warp_build_rings(Hslot + 8, A.K_LO, A.nH, ts, r1, r2, A.dlnE, nsub, 0, 1, 0.0, 0.0, 1.0, 0.0, 1.0, kmn, kmx,
-                                 nsub == 1 ? &geo : nullptr, A.inv_dlnE, RG_HIST_STASH ? stash : nullptr);
+                                 nsub == 1 ? &geo : nullptr, A.inv_dlnE);
                 if (kmn < A.K_LO) kmn = A.K_LO;
                 if (kmx > A.K_LO + A.nH - 1) kmx = A.K_LO + A.nH - 1;
                 __syncwarp();
@@ -105,7 +101,7 @@ __global__ void __launch_bounds__(32 * HIST_WARPS, RG_HIST_MINB) hist_kernel(His
 int rg_launch_hist(const HistArgs &A, cudaStream_t st)
 {
     if (A.P == 0) return RG_OK;
-    size_t smem = (size_t)HIST_WARPS * (hist_round_up2(A.nH + 24) * sizeof(double) + 32 * sizeof(PrepRec) + 72 * sizeof(double));
+    size_t smem = (size_t)HIST_WARPS * (hist_round_up2(A.nH + 24) * sizeof(double) + 32 * sizeof(PrepRec));
     RG_CUDA_OK(cudaFuncSetAttribute(hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     RG_LAUNCH(hist_kernel, dim3((unsigned)((long)A.P * A.NBH)), dim3(32 * HIST_WARPS), smem, st, A);
     RG_CUDA_OK(cudaGetLastError());

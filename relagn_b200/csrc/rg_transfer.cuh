@@ -261,7 +261,7 @@ __device__ inline void warp_deposit(double *Hs, int K_LO, int nH, double sa, dou
 __device__ inline void warp_build_rings(double *Hs, int K_LO, int nH, const TabSel &ts, double r1, double r2, double dlnE,
                                         int nsub, int m_begin, int m_step, double alpha, double beta, double rb, double zs,
                                         double weight, int &kmin_out, int &kmax_out, const RingGeo *single = nullptr,
-                                        double inv_dlnE_in = 0.0, volatile double *stash = nullptr)
+                                        double inv_dlnE_in = 0.0)
 {
     // single: geometry of the annulus' only ring when the caller has it already (nsub == 1, warp-uniform)
     const int lane = threadIdx.x & 31;
@@ -285,28 +285,19 @@ __device__ inline void warp_build_rings(double *Hs, int K_LO, int nH, const TabS
             rg_ring_sample(ts, s0, s1, fr, lane, g, jn);
             const double cW = 0.5 * dphi * A * weight; // segment weight = (w_t + w_{t+1}) cW
             double s_cur = RG_LOG_G(g) * inv_dlnE + zs, w_cur = jn * g * g * g;
-            // stash (72 doubles of the warp's shared memory, optional): what the NEXT deposit needs -- the following
-            // chunk's samples and the ring's first sample -- waits there instead of in 8 registers while the current
-            // deposit, the most register-hungry part, runs
-            double s_first = __shfl_sync(RG_FULL, s_cur, 0), w_first = __shfl_sync(RG_FULL, w_cur, 0);
-            if (stash && lane == 0) { stash[64] = s_first; stash[65] = w_first; }
+            const double s_first = __shfl_sync(RG_FULL, s_cur, 0), w_first = __shfl_sync(RG_FULL, w_cur, 0);
             for (int q = 0; q < nq; q++) {
                 double s_nxt = 0, w_nxt = 0, sn0, wn0;
                 if (q + 1 < nq) {
                     rg_ring_sample(ts, s0, s1, fr, lane + 32 * (q + 1), g, jn);
                     s_nxt = RG_LOG_G(g) * inv_dlnE + zs; w_nxt = jn * g * g * g;
                     sn0 = __shfl_sync(RG_FULL, s_nxt, 0); wn0 = __shfl_sync(RG_FULL, w_nxt, 0);
-                    if (stash) { stash[lane] = s_nxt; stash[32 + lane] = w_nxt; }
-                } else if (stash) {
-                    __syncwarp();
-                    sn0 = stash[64]; wn0 = stash[65];
                 } else { sn0 = s_first; wn0 = w_first; }
                 double sb = __shfl_down_sync(RG_FULL, s_cur, 1), wb = __shfl_down_sync(RG_FULL, w_cur, 1);
                 if (lane == 31) { sb = sn0; wb = wn0; }
                 const double W = (w_cur + wb) * cW;
                 warp_deposit(Hs, K_LO, nH, s_cur, sb, W, kf_min, kl_max);
-                if (stash) { s_cur = stash[lane]; w_cur = stash[32 + lane]; }
-                else { s_cur = s_nxt; w_cur = w_nxt; }
+                s_cur = s_nxt; w_cur = w_nxt;
             }
         }
     }
