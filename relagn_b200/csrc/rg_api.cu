@@ -717,9 +717,12 @@ extern "C" int rg_eval_batch(rg_ctx *c, const double *d_params, int P, int model
             int k = atoi(e);
             if (k >= 1 && k <= RG_NTH_MINB) nth_run = c->sm_count * k * 128;
         }
-        // the persistent nthcomp grid is launched first and hist_kernel fills the SMs as it drains (then runs next to the
-        // interpolation kernel): 2 % faster than the other order.  RG_HIST_FIRST: tuning knob for the other order
-        const bool nth_first = getenv("RG_HIST_FIRST") == nullptr;
+        // Which of the two gets the SMs first is decided by the launch order.  hist_kernel first: its CTAs take every
+        // SM and the persistent nthcomp grid moves in as they drain (144.8 ms per 125 000 sets); nthcomp first: the
+        // two share the SMs for the whole solve and slow each other down (155.2 ms; one stream, no overlap: 146.8 ms).
+        // With the larger shared-memory footprint hist_kernel had before r1r the order was the other way round by
+        // 2 % -- measure again when either kernel's resources change (RG_NTH_FIRST=1: tuning knob for the other order)
+        const bool nth_first = getenv("RG_NTH_FIRST") != nullptr;
         auto launch_nth = [&]() -> int {
             if (nsys <= 0) return RG_OK;
             c->launches++; // nthcomp_interp_kernel
