@@ -140,6 +140,21 @@ int rg_ky_kernel(rg_ctx *ctx, double a, double theta_o, double r1, double r2, do
 int rg_eval_batch(rg_ctx *ctx, const double *d_params, int P, int model, double dr_dex, unsigned flags,
                   double *d_out, double *d_attrs, void *stream);
 
+/* rg_eval_batch with a completion hook per piece: the spectra come out in
+ * pieces of about piece_sets parameter sets (a short remainder joins the last
+ * piece; batches small enough to be split over several CTAs per set come as
+ * one piece per chunk); on_piece(user, first_set, n_sets) is called on the
+ * calling thread right after the kernels that complete rows [first_set,
+ * first_set + n_sets) of d_out (and d_attrs) have been enqueued on `stream`
+ * -- record an event there and chain the transfer of that range (D2H copy,
+ * NCCL gather) on another stream while the next piece is computed.  This is
+ * what rg_eval_batch_host and batch.evaluate_sharded do; the reference has
+ * no counterpart (its batch loop is the caller's Python loop over objects). */
+typedef void (*rg_piece_fn)(void *user, int first_set, int n_sets);
+int rg_eval_batch_pieces(rg_ctx *ctx, const double *d_params, int P, int model, double dr_dex, unsigned flags,
+                         double *d_out, double *d_attrs, void *stream, int piece_sets, rg_piece_fn on_piece,
+                         void *user);
+
 /* same with HOST buffers: stages through pinned memory, copies in and out
  * inside the call, synchronises before returning. */
 int rg_eval_batch_host(rg_ctx *ctx, const double *params_host, int P, int model, double dr_dex, unsigned flags,

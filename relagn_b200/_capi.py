@@ -27,7 +27,7 @@ F_RW_LT_RH, F_RW_GT_ROUT, F_RH_LT_RISCO, F_RW_LT_RISCO, F_HMAX_GT_RH, F_HOT_SEED
 # every symbol include/relagn_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = ["rg_version", "rg_last_error", "rg_ctx_create", "rg_ctx_destroy", "rg_set_grid", "rg_tables_generate",
            "rg_tables_upload", "rg_tables_download", "rg_tables_info", "rg_kyconv", "rg_ky_kernel", "rg_eval_batch",
-           "rg_eval_batch_host", "rg_launch_count", "rg_measure_fp64_peak", "rg_set_option", "rg_get_stat",
+           "rg_eval_batch_pieces", "rg_eval_batch_host", "rg_launch_count", "rg_measure_fp64_peak", "rg_set_option", "rg_get_stat",
            "rg_reset_stats", "rg_convert_batch", "rg_set_instrument", "rg_photar_batch", "rg_set_response",
            "rg_set_data", "rg_fitstat_batch", "rg_eval_fitstat_batch", "rg_eval_fitstat_batch_host",
            "rg_xspec_eval", "rg_xspec_bind", "rg_tables_default"]
@@ -40,6 +40,7 @@ OPT_PROFILE = 1
 STATS = {"ms_setup": 1, "ms_nthcomp": 2, "ms_spectrum": 3, "n_setup": 4, "n_nthcomp": 5, "n_spectrum": 6, "sum_W": 7,
          "n_conv_ann": 8, "sum_jmax": 9, "n_sys": 10, "n_sets": 11, "ms_observe": 12, "n_observe": 13, "ms_hist": 14, "n_hist": 15}
 
+PIECE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int)  # rg_piece_fn(user, first_set, n_sets)
 _dp = C.POINTER(C.c_double)
 _fp = C.POINTER(C.c_float)
 _ip = C.POINTER(C.c_int)
@@ -79,6 +80,9 @@ def bind(lib):
     lib.rg_eval_batch.restype = C.c_int
     lib.rg_eval_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_uint, C.c_void_p,
                                   C.c_void_p, C.c_void_p]
+    lib.rg_eval_batch_pieces.restype = C.c_int
+    lib.rg_eval_batch_pieces.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_uint, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_int, PIECE_FN, C.c_void_p]
     lib.rg_eval_batch_host.restype = C.c_int
     lib.rg_eval_batch_host.argtypes = [C.c_void_p, _dp, C.c_int, C.c_int, C.c_double, C.c_uint, _dp, _dp]
     lib.rg_launch_count.restype = C.c_long
@@ -254,6 +258,27 @@ class Context:
         self._check(self.lib.rg_eval_batch(self.h, C.c_void_p(params_ptr), int(P), int(model), float(dr_dex), flags,
                                            C.c_void_p(out_ptr), C.c_void_p(attrs_ptr) if attrs_ptr else None,
                                            C.c_void_p(stream) if stream else None))
+
+    def eval_batch_device_pieces(self, params_ptr, P, out_ptr, piece_sets, on_piece, attrs_ptr=0, model=MODEL_RELAGN,
+                                 rel=True, components=False, dr_dex=50.0, stream=0, fp32=False):
+        """rg_eval_batch_pieces: on_piece(first_set, n_sets) is called on this thread as soon as the kernels that
+        complete those rows of the output are enqueued on `stream`."""
+        flags = (FLAG_REL if rel else 0) | (FLAG_COMPONENTS if components else 0) | (FLAG_FP32 if fp32 else 0)
+        err = []
+
+        def _cb(_user, first, n):
+            try:
+                on_piece(int(first), int(n))
+            except BaseException as e:  # an exception must not unwind through the C frames
+                err.append(e)
+
+        cb = PIECE_FN(_cb)
+        self._check(self.lib.rg_eval_batch_pieces(self.h, C.c_void_p(params_ptr), int(P), int(model), float(dr_dex),
+                                                  flags, C.c_void_p(out_ptr),
+                                                  C.c_void_p(attrs_ptr) if attrs_ptr else None,
+                                                  C.c_void_p(stream) if stream else None, int(piece_sets), cb, None))
+        if err:
+            raise err[0]
 
     # ---- observation epilogue (SURVEY 8 f1, f2) ----
     def convert_device(self, lnu_ptr, params_ptr, P, ncomp, unit, as_flux, out_ptr, model=MODEL_RELAGN, stream=0):

@@ -69,6 +69,28 @@ class BatchEvaluator:
         return out, attrs
 
     # ---- host path (the call a user of the reference's class makes, batched) ----
+    def evaluate_device_pieces(self, params, on_piece, piece_sets=16384, rel=True, components=False, out=None,
+                               attrs=None, fp32=False):
+        """evaluate_device with a hook: on_piece(first_set, n_sets) is called as soon as the kernels that complete
+        those rows of `out` are enqueued on the current torch stream (rg_eval_batch_pieces) -- record an event there
+        and move the piece (NCCL gather, copy) on another stream while the next one is computed."""
+        assert params.is_cuda and params.dtype == torch.float64 and params.is_contiguous()
+        assert params.shape[1] == _capi.NPAR
+        if rel:
+            self.ensure_tables()
+        P = params.shape[0]
+        shape = (P, 4, self.nE) if components else (P, self.nE)
+        if out is None:
+            out = torch.empty(shape, dtype=torch.float64, device=self.device)
+        if attrs is None:
+            attrs = torch.empty((P, _capi.NATTR), dtype=torch.float64, device=self.device)
+        assert tuple(out.shape) == shape and out.is_contiguous()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self.ctx.eval_batch_device_pieces(params.data_ptr(), P, out.data_ptr(), piece_sets, on_piece,
+                                          attrs_ptr=attrs.data_ptr(), model=self.model, rel=rel, components=components,
+                                          dr_dex=self.dr_dex, stream=stream, fp32=fp32)
+        return out, attrs
+
     def evaluate(self, params, rel=True, components=False, fp32=False):
         """params: array-like [P, n] on the host.  Returns (spectra ndarray [P, nE] or [P, 4, nE] in W/Hz,
         attrs ndarray [P, 24]).  Stages through pinned memory; H2D and D2H happen inside this call.  The returned
@@ -189,7 +211,7 @@ def piece_edges(P, pieces=None, chunk_max=65536, piece_min=8192):
 
 
 def evaluate_sharded(evaluator, params_local, rel=True, gather_dst=0, group=None, pieces=None, out=None, attrs=None,
-                     gathered=None):
+                     gathered=None, piece_sets=16384):
     """One process per GPU: every rank evaluates its own shard (device tensor [P_local, 15]); the only collective
     is the gather of the spectra to `gather_dst` over NCCL (gather_dst=None: no gather).  The shard is evaluated in
     contiguous pieces (`piece_edges`) and the gather of piece i is issued on a side stream while piece i+1 is
@@ -205,9 +227,31 @@ def evaluate_sharded(evaluator, params_local, rel=True, gather_dst=0, group=None
             return out, None
         return evaluator.evaluate_device(params_local, rel=rel)[0], None
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    edges = piece_edges(P, pieces)
     cuda = params_local.is_cuda
     side = torch.cuda.Stream(device=params_local.device) if cuda else None
+    if cuda and pieces is None and hasattr(evaluator, "evaluate_device_pieces"):
+        # the library evaluates the shard in its own (large) chunks and reports every finished piece of the spectra:
+        # its gather is issued on the side stream while the next piece is computed
+        if out is None:
+            out = torch.empty((P, evaluator.nE), dtype=torch.float64, device=params_local.device)
+        if rank == gather_dst and gathered is None:
+            gathered = [torch.empty_like(out) for _ in range(world)]
+        works = []
+
+        def on_piece(lo, n):
+            done = torch.cuda.Event()
+            done.record()
+            with torch.cuda.stream(side):
+                side.wait_event(done)
+                dst_views = [g[lo:lo + n] for g in gathered] if rank == gather_dst else None
+                works.append(dist.gather(out[lo:lo + n], dst_views, dst=gather_dst, group=group, async_op=True))
+
+        evaluator.evaluate_device_pieces(params_local, on_piece, piece_sets=piece_sets, rel=rel, out=out, attrs=attrs)
+        for w in works:
+            w.wait()
+        torch.cuda.current_stream(params_local.device).wait_stream(side)
+        return out, gathered if rank == gather_dst else None
+    edges = piece_edges(P, pieces)
     outs, works = [], []
     for lo, hi in zip(edges[:-1], edges[1:]):
         if hi <= lo:

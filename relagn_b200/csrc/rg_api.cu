@@ -617,8 +617,8 @@ static int ensure_batch_scratch(rg_ctx *c, int model, int P)
     return RG_OK;
 }
 
-extern "C" int rg_eval_batch(rg_ctx *c, const double *d_params, int P, int model, double dr_dex, unsigned flags,
-                             double *d_out, double *d_attrs, void *stream)
+static int eval_batch_impl(rg_ctx *c, const double *d_params, int P, int model, double dr_dex, unsigned flags,
+                           double *d_out, double *d_attrs, void *stream, int piece_sets, rg_piece_fn on_piece, void *user)
 {
     if (!c || !d_params || !d_out || P < 0) return rg_set_error(RG_E_ARG, "rg_eval_batch: bad arguments");
     if (model != RG_MODEL_RELAGN && model != RG_MODEL_RELQSO) return rg_set_error(RG_E_ARG, "unknown model %d", model);
@@ -764,13 +764,44 @@ extern "C" int rg_eval_batch(rg_ctx *c, const double *d_params, int P, int model
         A.out = d_out + (size_t)p0 * ncomp * nE;
         A.stats = stats;
         RG_TRY(prof_begin(c, 2, st));
-        RG_TRY(rg_launch_spectrum(A, c->sm_count, st));
+        if (on_piece && piece_sets > 0 && A.NB == 1 && n > piece_sets + piece_sets / 2) {
+            // the chunk's spectrum kernel in sub-launches of piece_sets sets (setup, Kompaneets solves and histograms
+            // stay chunk-wide): the caller starts moving a piece out while the next one is computed
+            for (int q0 = 0; q0 < n;) {
+                int nq = std::min(piece_sets, n - q0);
+                if (n - q0 - nq < piece_sets / 2) nq = n - q0; // a short remainder joins the last piece
+                A.recs = c->d_recs + q0;
+                A.P = nq;
+                A.out = d_out + (size_t)(p0 + q0) * ncomp * nE;
+                RG_TRY(rg_launch_spectrum(A, c->sm_count, st));
+                c->launches++;
+                on_piece(user, p0 + q0, nq);
+                q0 += nq;
+            }
+        } else {
+            RG_TRY(rg_launch_spectrum(A, c->sm_count, st));
+            c->launches++;
+            if (on_piece) on_piece(user, p0, n);
+        }
         RG_TRY(prof_end(c, 2, st));
-        c->launches++;
         c->n_sets += n;
         p0 += n;
     }
     return RG_OK;
+}
+
+extern "C" int rg_eval_batch(rg_ctx *c, const double *d_params, int P, int model, double dr_dex, unsigned flags,
+                             double *d_out, double *d_attrs, void *stream)
+{
+    return eval_batch_impl(c, d_params, P, model, dr_dex, flags, d_out, d_attrs, stream, 0, nullptr, nullptr);
+}
+
+extern "C" int rg_eval_batch_pieces(rg_ctx *c, const double *d_params, int P, int model, double dr_dex, unsigned flags,
+                                    double *d_out, double *d_attrs, void *stream, int piece_sets, rg_piece_fn on_piece,
+                                    void *user)
+{
+    if (piece_sets < 1 || !on_piece) return rg_set_error(RG_E_ARG, "rg_eval_batch_pieces: piece_sets >= 1 and a callback are needed");
+    return eval_batch_impl(c, d_params, P, model, dr_dex, flags, d_out, d_attrs, stream, piece_sets, on_piece, user);
 }
 
 static int ensure_dev(double **p, size_t *have, size_t need)
@@ -792,56 +823,62 @@ extern "C" int rg_eval_batch_host(rg_ctx *c, const double *params, int P, int mo
     RG_CUDA_OK(cudaSetDevice(c->device));
     const int ncomp = (flags & RG_FLAG_COMPONENTS) ? 4 : 1;
     const size_t per_out = (size_t)ncomp * c->nE;
-    // pipeline in slabs so the D2H of slab i overlaps the kernels of slab i+1.  A slab is one chunk of rg_eval_batch
-    // (one setup/nthcomp/hist/spectrum launch sequence); slabs shrink towards the end of the batch (half of what is
-    // left, in steps of 8192) so that the copy nobody hides -- the last slab's -- is a small one.
-    const int SLAB_MAX = pick_chunk_sets(P);
-    int SMIN = 8192; // smallest slab
-    if (const char *e = getenv("RG_SLAB_MIN")) { int v = atoi(e); if (v >= 1024 && v <= 65536) SMIN = v & ~1023; } // tuning knob
-    const int SREST = SMIN + SMIN / 2; // what is left below this goes as one slab
-    const bool piped = P > SREST; // more than one slab: two staging buffers
-    const int slab_cap = piped ? std::max(SREST, std::min(SLAB_MAX, std::max(SMIN, (P / 2) / SMIN * SMIN))) : P;
+    // The batch is evaluated in the chunks of rg_eval_batch (up to 65 536 sets: one setup / nthcomp / hist launch
+    // sequence each); the spectrum kernel of a chunk goes in sub-launches of PIECE sets and every finished piece is
+    // copied out on a second stream behind an event while the next piece is computed -- the only copy nobody hides
+    // is the last piece's.  (Until r1r the slabs themselves shrank towards the end of the batch; small chunks run
+    // 6-12 % slower per set than large ones.)  Batches beyond SUPER sets go in rounds so that the staging buffer stays
+    // bounded.
+    int PIECE = 16384;
+    if (const char *e = getenv("RG_PIECE_SETS")) { int v = atoi(e); if (v >= 1 && v <= 65536) PIECE = v; } // tuning / test knob
+    const int SUPER = 262144;
+    const int stage_rows = std::min(P, SUPER);
     RG_TRY(ensure_dev(&c->d_stage_par, &c->d_stage_par_n, (size_t)P * RG_NPAR));
-    RG_TRY(ensure_dev(&c->d_stage_out, &c->d_stage_out_n, (size_t)(piped ? 2 : 1) * slab_cap * per_out));
+    RG_TRY(ensure_dev(&c->d_stage_out, &c->d_stage_out_n, (size_t)stage_rows * per_out));
     RG_TRY(ensure_dev(&c->d_stage_attr, &c->d_stage_attr_n, (size_t)P * RG_NATTR));
     RG_CUDA_OK(cudaMemcpyAsync(c->d_stage_par, params, (size_t)P * RG_NPAR * sizeof(double), cudaMemcpyHostToDevice,
                                c->stream));
-    cudaStream_t copy_st = nullptr;
-    RG_CUDA_OK(cudaStreamCreateWithFlags(&copy_st, cudaStreamNonBlocking));
-    cudaEvent_t freed[2];
-    for (int i = 0; i < 2; i++) cudaEventCreate(&freed[i]);
-    int rc = RG_OK;
-    int slab = 0;
-    bool used[2] = {false, false};
-    const bool trace = getenv("RG_TRACE_HOST") != nullptr; // host-side timeline of the slab pipeline on stderr
+    struct Pipe {
+        rg_ctx *c; cudaStream_t copy_st; cudaEvent_t ev;
+        double *out_host, *attrs_host; size_t per_out; int base; // first set of the round
+        bool trace; double t0;
+    } pipe;
+    pipe.c = c; pipe.copy_st = nullptr; pipe.ev = nullptr; pipe.out_host = out; pipe.attrs_host = attrs;
+    pipe.per_out = per_out; pipe.base = 0;
+    pipe.trace = getenv("RG_TRACE_HOST") != nullptr; // host-side timeline of the pipeline on stderr
     auto now_ms = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    const double t_begin = now_ms();
-    for (int p0 = 0; p0 < P && rc == RG_OK; slab ^= 1) {
-        const int left = P - p0;
-        int n = left;
-        if (left > SREST) n = std::min(SLAB_MAX, std::max(SMIN, (left / 2) / SMIN * SMIN));
-        double *dslab = c->d_stage_out + (size_t)(piped ? slab : 0) * slab_cap * per_out;
-        if (used[slab]) cudaEventSynchronize(freed[slab]); // previous copy out of this slab buffer finished
-        rc = rg_eval_batch(c, c->d_stage_par + (size_t)p0 * RG_NPAR, n, model, dr_dex, flags, dslab,
-                           c->d_stage_attr + (size_t)p0 * RG_NATTR, c->stream);
-        if (rc != RG_OK) break;
-        // D2H on the copy stream once the slab's kernels are done
-        cudaStreamSynchronize(c->stream);
-        if (trace) fprintf(stderr, "[rg host] slab of %d sets done at %.2f ms\n", n, now_ms() - t_begin);
-        cudaMemcpyAsync(out + (size_t)p0 * per_out, dslab, (size_t)n * per_out * sizeof(double), cudaMemcpyDeviceToHost,
-                        copy_st);
-        cudaEventRecord(freed[slab], copy_st);
-        if (attrs) // the slab's attributes ride behind its spectra
-            cudaMemcpyAsync(attrs + (size_t)p0 * RG_NATTR, c->d_stage_attr + (size_t)p0 * RG_NATTR,
-                            (size_t)n * RG_NATTR * sizeof(double), cudaMemcpyDeviceToHost, copy_st);
-        used[slab] = true;
-        p0 += n;
+    pipe.t0 = now_ms();
+    RG_CUDA_OK(cudaStreamCreateWithFlags(&pipe.copy_st, cudaStreamNonBlocking));
+    RG_CUDA_OK(cudaEventCreateWithFlags(&pipe.ev, cudaEventDisableTiming));
+    auto on_piece = [](void *u, int first, int n) {
+        Pipe *p = static_cast<Pipe *>(u);
+        rg_ctx *c = p->c;
+        cudaEventRecord(p->ev, c->stream);
+        cudaStreamWaitEvent(p->copy_st, p->ev, 0);
+        const int g = p->base + first; // set index in the whole batch
+        cudaMemcpyAsync(p->out_host + (size_t)g * p->per_out, c->d_stage_out + (size_t)first * p->per_out,
+                        (size_t)n * p->per_out * sizeof(double), cudaMemcpyDeviceToHost, p->copy_st);
+        if (p->attrs_host)
+            cudaMemcpyAsync(p->attrs_host + (size_t)g * RG_NATTR, c->d_stage_attr + (size_t)g * RG_NATTR,
+                            (size_t)n * RG_NATTR * sizeof(double), cudaMemcpyDeviceToHost, p->copy_st);
+        if (p->trace) {
+            auto t = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+            fprintf(stderr, "[rg host] piece of %d sets enqueued at %.2f ms\n", n, t - p->t0);
+        }
+    };
+    int rc = RG_OK;
+    for (int r0 = 0; r0 < P && rc == RG_OK; r0 += SUPER) {
+        const int nr = std::min(SUPER, P - r0);
+        pipe.base = r0;
+        if (r0 > 0) cudaStreamSynchronize(pipe.copy_st); // the staging buffer is about to be overwritten
+        rc = eval_batch_impl(c, c->d_stage_par + (size_t)r0 * RG_NPAR, nr, model, dr_dex, flags, c->d_stage_out,
+                             c->d_stage_attr + (size_t)r0 * RG_NATTR, c->stream, PIECE, on_piece, &pipe);
     }
-    cudaStreamSynchronize(copy_st);
-    if (trace) fprintf(stderr, "[rg host] last D2H done at %.2f ms\n", now_ms() - t_begin);
     cudaStreamSynchronize(c->stream);
-    for (int i = 0; i < 2; i++) cudaEventDestroy(freed[i]);
-    cudaStreamDestroy(copy_st);
+    cudaStreamSynchronize(pipe.copy_st);
+    if (pipe.trace) fprintf(stderr, "[rg host] last D2H done at %.2f ms\n", now_ms() - pipe.t0);
+    cudaEventDestroy(pipe.ev);
+    cudaStreamDestroy(pipe.copy_st);
     if (rc != RG_OK) return rc;
     RG_CUDA_OK(cudaGetLastError());
     return RG_OK;

@@ -182,7 +182,7 @@ def test_full_size_c4_batch_chunking_invariance():
     p = c4_params(125000, seed=11)
     small, at_small = ev.evaluate(p[:300])
     small, at_small = small.copy(), at_small.copy()
-    full, at_full = ev.evaluate(p)                      # slabs of 57 344, 32 768, 16 384, 8 192, 10 312 sets
+    full, at_full = ev.evaluate(p)                      # chunks of 65 536 + 59 464 sets, copied out in pieces of 16 384
     full, at_full = full.copy(), at_full.copy()
     assert full.shape == (125000, 1000)
     ok = at_full[:, _capi.A["status"]] == 0
@@ -192,6 +192,15 @@ def test_full_size_c4_batch_chunking_invariance():
     # device-resident path: chunks of 65 536 + 59 464 sets
     dev, _ = ev.evaluate_device(torch.from_numpy(p).to("cuda:0"))
     np.testing.assert_array_equal(dev.cpu().numpy(), full)
+    # the same with the completion hook (rg_eval_batch_pieces): contiguous pieces that cover the batch, same bits
+    pieces = []
+    dev2, _ = ev.evaluate_device_pieces(torch.from_numpy(p).to("cuda:0"), lambda lo, n: pieces.append((lo, n)),
+                                        piece_sets=16384)
+    torch.cuda.synchronize()
+    assert pieces[0][0] == 0 and sum(n for _, n in pieces) == 125000
+    assert all(a[0] + a[1] == b[0] for a, b in zip(pieces, pieces[1:]))
+    assert max(n for _, n in pieces) <= 16384 + 8192 and len(pieces) >= 7
+    np.testing.assert_array_equal(dev2.cpu().numpy(), full)
     # a slice from the middle of the batch, evaluated on its own
     mid, _ = ev.evaluate(p[70000:70300])   # (>= 2 x #SM sets: below that a set is split over several CTAs)
     np.testing.assert_array_equal(mid, full[70000:70300])

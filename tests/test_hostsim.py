@@ -42,6 +42,21 @@ def test_nonrel_and_rel_vs_reference_goldens(ctx):
     assert at[0, A["r_h"]] == 14.261351436104999 and at[0, A["r_w"]] == 28.522702872209997
 
 
+def test_host_pipeline_pieces(ctx, monkeypatch):
+    """rg_eval_batch_host: the spectra do not depend on how the spectrum kernel is cut into pieces (and every row and
+    attribute reaches the host): 12 sets as one piece, as pieces of 5 (5 + 7: the short remainder joins) and of 3."""
+    dn = np.load(os.path.join(GOLDEN, "golden_nonrel.npz"))
+    ctx.set_grid(dn["grid1000"])
+    p = np.concatenate([dn["relagn_params"][:6], dn["relagn_params"][:6][::-1]])  # 12 sets >= 2 x 4 simulated SMs
+    ref, at_ref = ctx.eval_batch_host(p, model=0, rel=True)
+    assert np.isfinite(ref).all() and (ref.max(axis=1) > 0).all()
+    for piece in ("5", "3"):
+        monkeypatch.setenv("RG_PIECE_SETS", piece)
+        out, at = ctx.eval_batch_host(p, model=0, rel=True)
+        np.testing.assert_array_equal(out, ref)
+        np.testing.assert_array_equal(at, at_ref)
+
+
 def test_python_default_grid(ctx):
     dn = np.load(os.path.join(GOLDEN, "golden_nonrel.npz"))
     ctx.set_grid(dn["grid_def"])   # 1999 bins -> the M = 8 instantiation
