@@ -109,11 +109,14 @@ class BatchEvaluator:
         if getattr(self, "_pin_attr", None) is None or self._pin_attr.shape[0] < P:
             self._pin_attr = torch.empty((P, _capi.NATTR), dtype=torch.float64).pin_memory()
         pin = self._pin_in[:P]
-        if p.shape[1] != _capi.NPAR:
+        pin_np = pin.numpy()
+        if p.shape[1] == _capi.NPAR:
+            np.copyto(pin_np, p)  # one straight memcpy into the pinned staging rows
+        else:
             pin.zero_()
-        pin[:, :p.shape[1]] = torch.from_numpy(p)
+            pin_np[:, :p.shape[1]] = p
         out = self._pin_out[:P * ncomp * self.nE].view((P, 4, self.nE) if components else (P, self.nE))
-        out_np, at = self.ctx.eval_batch_host(pin.numpy(), model=self.model, rel=rel, components=components,
+        out_np, at = self.ctx.eval_batch_host(pin_np, model=self.model, rel=rel, components=components,
                                               dr_dex=self.dr_dex, out=out.numpy(), fp32=fp32,
                                               attrs_out=self._pin_attr[:P].numpy())
         return out_np, at
@@ -211,11 +214,14 @@ def piece_edges(P, pieces=None, chunk_max=65536, piece_min=8192):
 
 
 def evaluate_sharded(evaluator, params_local, rel=True, gather_dst=0, group=None, pieces=None, out=None, attrs=None,
-                     gathered=None, piece_sets=16384):
+                     gathered=None, hook=False, piece_sets=16384):
     """One process per GPU: every rank evaluates its own shard (device tensor [P_local, 15]); the only collective
     is the gather of the spectra to `gather_dst` over NCCL (gather_dst=None: no gather).  The shard is evaluated in
     contiguous pieces (`piece_edges`) and the gather of piece i is issued on a side stream while piece i+1 is
-    computed, so only the last (small) piece's transfer is exposed.  out / attrs / gathered: optional preallocated result tensors
+    computed, so only the last (small) piece's transfer is exposed.  hook=True: the library evaluates the shard in its
+    own large chunks and the gathers are issued from the completion hook of rg_eval_batch_pieces instead -- measured
+    slower at 8 GPUs (156.4 against 151.9 ms per step: the NCCL kernels of eight gathers per step compete with the
+    persistent spectrum kernel for the SMs of the receiving rank), kept for transports that do not need SMs.  out / attrs / gathered: optional preallocated result tensors
     ([P_local, nE], [P_local, 24], list of world x [P_local, nE] on the destination rank).
     Returns (local_out, gathered or None)."""
     import torch.distributed as dist
@@ -229,7 +235,7 @@ def evaluate_sharded(evaluator, params_local, rel=True, gather_dst=0, group=None
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     cuda = params_local.is_cuda
     side = torch.cuda.Stream(device=params_local.device) if cuda else None
-    if cuda and pieces is None and hasattr(evaluator, "evaluate_device_pieces"):
+    if cuda and hook and hasattr(evaluator, "evaluate_device_pieces"):
         # the library evaluates the shard in its own (large) chunks and reports every finished piece of the spectra:
         # its gather is issued on the side stream while the next piece is computed
         if out is None:
