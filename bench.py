@@ -256,8 +256,16 @@ def run_ours(args):
     if world > 1 and rank == 0:
         gathered = [torch.empty((P, NE), dtype=torch.float64, device=dev) for _ in range(world)]
 
+    transport = None
+    if world > 1 and os.environ.get("RG_SHARD_TRANSPORT", "") == "p2p":
+        from relagn_b200.batch import PeerGather
+        transport = PeerGather(P, NE, dev)
+        gathered = None
+
     def step():
-        if world > 1 and not args.fp32:
+        if transport is not None:
+            evaluate_sharded(ev, params, rel=True, gather_dst=0, out=out, attrs=attrs, transport=transport)
+        elif world > 1 and not args.fp32:
             # pieces of the shard are gathered to rank 0 while the next piece is computed (batch.evaluate_sharded)
             evaluate_sharded(ev, params, rel=True, gather_dst=0, out=out, attrs=attrs, gathered=gathered)
         else:

@@ -213,8 +213,42 @@ def piece_edges(P, pieces=None, chunk_max=65536, piece_min=8192):
     return edges
 
 
+class PeerGather:
+    """Gather of the spectra to one rank by peer-to-peer copies over NVLink (copy engines) instead of NCCL kernels:
+    every rank owns a window [world, P, nE] in torch symmetric memory, maps the destination rank's window and writes
+    its pieces straight into its own row there.  No SM is taken from the compute kernels, so the pieces can follow the
+    completion hook of rg_eval_batch_pieces.  Opt-in (evaluate_sharded(transport=PeerGather(...))): needs P2P access
+    between all GPUs of the group and a driver that exports symmetric allocations; construct it collectively."""
+
+    def __init__(self, P, nE, device, group=None, dst=0):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank, self.dst = dist.get_world_size(self.group), dist.get_rank(self.group), dst
+        self.P, self.nE = P, nE
+        self.window = symm_mem.empty((self.world, P, nE), dtype=torch.float64, device=device)
+        self.hdl = symm_mem.rendezvous(self.window, self.group)
+        self.remote = self.hdl.get_buffer(dst, (self.world, P, nE), torch.float64)
+        self.side = torch.cuda.Stream(device=device)
+
+    def put(self, piece, lo):
+        """Called after the kernels that complete `piece` (rows lo.. of the local shard) are enqueued."""
+        done = torch.cuda.Event()
+        done.record()
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(done)
+            self.remote[self.rank, lo:lo + piece.shape[0]].copy_(piece, non_blocking=True)
+
+    def finish(self):
+        """All pieces of all ranks have landed when this returns on the destination rank."""
+        import torch.distributed as dist
+        self.side.synchronize()
+        dist.barrier(group=self.group)
+        return [self.window[r] for r in range(self.world)] if self.rank == self.dst else None
+
+
 def evaluate_sharded(evaluator, params_local, rel=True, gather_dst=0, group=None, pieces=None, out=None, attrs=None,
-                     gathered=None, hook=False, piece_sets=16384):
+                     gathered=None, hook=False, piece_sets=16384, transport=None):
     """One process per GPU: every rank evaluates its own shard (device tensor [P_local, 15]); the only collective
     is the gather of the spectra to `gather_dst` over NCCL (gather_dst=None: no gather).  The shard is evaluated in
     contiguous pieces (`piece_edges`) and the gather of piece i is issued on a side stream while piece i+1 is
@@ -235,6 +269,13 @@ def evaluate_sharded(evaluator, params_local, rel=True, gather_dst=0, group=None
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     cuda = params_local.is_cuda
     side = torch.cuda.Stream(device=params_local.device) if cuda else None
+    if cuda and transport is not None:
+        # peer-to-peer transport: large chunks, every finished piece is written into the destination rank's window
+        if out is None:
+            out = torch.empty((P, evaluator.nE), dtype=torch.float64, device=params_local.device)
+        evaluator.evaluate_device_pieces(params_local, lambda lo, n: transport.put(out[lo:lo + n], lo),
+                                         piece_sets=piece_sets, rel=rel, out=out, attrs=attrs)
+        return out, transport.finish()
     if cuda and hook and hasattr(evaluator, "evaluate_device_pieces"):
         # the library evaluates the shard in its own (large) chunks and reports every finished piece of the spectra:
         # its gather is issued on the side stream while the next piece is computed
