@@ -8,7 +8,8 @@
 Workload (SURVEY 8d, C4 = BASELINE.json configs[3]): RELAGN full model, independent random parameters inside the
 XSPEC hard limits (lmod_relagn.dat), relativistic transfer on, 1000-bin grid geomspace(1e-4, 1e3, 1001);
 125 000 parameter sets per GPU per step (the 1e6-set MCMC batch sharded over 8 GPUs -> weak scaling).
-One step = every rank evaluates its shard (+ for N > 1 the final NCCL gather of the spectra to rank 0).
+One step = every rank evaluates its shard (+ for N > 1 the gather of the spectra to rank 0: peer-to-peer window
+writes over NVLink, NCCL gather as the fallback).
 
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definition of every field.
 """
@@ -81,7 +82,7 @@ def workload_config(n_gpus, sets_per_gpu, tables):
                         % sets_per_gpu,
             "nE": NE, "ebins": "geomspace(1e-4,1e3,1001) keV", "sets_per_gpu": sets_per_gpu,
             "global_sets": sets_per_gpu * n_gpus, "dr_dex": 50, "kerr_tables": tables,
-            "parallelism": "dp%d (independent parameter sets; final NCCL gather to rank 0)" % n_gpus,
+            "parallelism": "dp%d (independent parameter sets; spectra gathered to rank 0 inside the step)" % n_gpus,
             "l2_policy": "each step writes %.2f GB of spectra per GPU (>> 126 MB L2); inputs are 15 MB of parameters"
                          % (sets_per_gpu * NE * 8 / 1e9)}
 
@@ -256,11 +257,25 @@ def run_ours(args):
     if world > 1 and rank == 0:
         gathered = [torch.empty((P, NE), dtype=torch.float64, device=dev) for _ in range(world)]
 
+    # N > 1: the spectra reach rank 0 by peer-to-peer window writes over NVLink (batch.PeerGather: copy engines, no SMs
+    # taken from the kernels; 145.9 ms per step at 8 GPUs) when every rank can set the window up, else by the NCCL
+    # gather (152.6 ms).  RG_SHARD_TRANSPORT=nccl forces the latter.
     transport = None
-    if world > 1 and os.environ.get("RG_SHARD_TRANSPORT", "") == "p2p":
-        from relagn_b200.batch import PeerGather
-        transport = PeerGather(P, NE, dev)
-        gathered = None
+    if world > 1 and os.environ.get("RG_SHARD_TRANSPORT", "p2p") == "p2p":
+        ok = 1
+        try:
+            from relagn_b200.batch import PeerGather
+            transport = PeerGather(P, NE, dev)
+        except Exception as e:  # no P2P / no symmetric-memory support on this box
+            sys.stderr.write("bench: peer-to-peer gather unavailable (%s); using the NCCL gather\n" % (e,))
+            ok = 0
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            transport = None
+        else:
+            gathered = None
+    gather_kind = "peer-to-peer window writes over NVLink (copy engines)" if transport is not None else "NCCL gather"
 
     def step():
         if transport is not None:
@@ -462,7 +477,8 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32 (spectra/transfer) + f64 (setup, nthcomp, histograms)" if args.fp32 else "f64", "data": "synthetic",
-                "config": workload_config(world, P, args.tables), "clocks": clocks, "e2e": e2e,
+                "config": workload_config(world, P, args.tables), "gather_transport": gather_kind if world > 1 else None,
+                "clocks": clocks, "e2e": e2e,
                 "gpu_launches": int(launches), "roofline": roofline, "fp64_roofline": fp64, "kernels": kernels,
                 "cpu_baseline": cpu, "fit_statistic": fit, "checksum": chk}
         print(json.dumps(line))
