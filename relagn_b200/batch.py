@@ -240,7 +240,9 @@ class PeerGather:
             self.remote[self.rank, lo:lo + piece.shape[0]].copy_(piece, non_blocking=True)
 
     def finish(self):
-        """All pieces of all ranks have landed when this returns on the destination rank."""
+        """All pieces of all ranks have landed when this returns on the destination rank.  The returned rows are views
+        of the window: the next evaluate_sharded(transport=self) of any rank overwrites them, so the destination rank
+        consumes (or copies) them and the group synchronises before the next step is started."""
         import torch.distributed as dist
         self.side.synchronize()
         dist.barrier(group=self.group)
