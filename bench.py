@@ -257,11 +257,13 @@ def run_ours(args):
     if world > 1 and rank == 0:
         gathered = [torch.empty((P, NE), dtype=torch.float64, device=dev) for _ in range(world)]
 
-    # N > 1: the spectra reach rank 0 by peer-to-peer window writes over NVLink (batch.PeerGather: copy engines, no SMs
-    # taken from the kernels; 145.9 ms per step at 8 GPUs) when every rank can set the window up, else by the NCCL
-    # gather (152.6 ms).  RG_SHARD_TRANSPORT=nccl forces the latter.
+    # N > 1: the spectra reach rank 0 either by peer-to-peer window writes over NVLink (batch.PeerGather: copy engines,
+    # no SMs taken from the kernels) or by the NCCL gather of the shrinking pieces.  When every rank can set the window
+    # up, both are timed before the warm-up (untimed region, device events, max over ranks, clock sampler running as in
+    # the timed region) and the faster one runs the timed steps; RG_SHARD_TRANSPORT=nccl|p2p forces one.
     transport = None
-    if world > 1 and os.environ.get("RG_SHARD_TRANSPORT", "p2p") == "p2p":
+    want = os.environ.get("RG_SHARD_TRANSPORT", "auto")
+    if world > 1 and not args.fp32 and want in ("auto", "p2p"):
         ok = 1
         try:
             from relagn_b200.batch import PeerGather
@@ -273,9 +275,6 @@ def run_ours(args):
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if int(flag.item()) == 0:
             transport = None
-        else:
-            gathered = None
-    gather_kind = "peer-to-peer window writes over NVLink (copy engines)" if transport is not None else "NCCL gather"
 
     def step():
         if transport is not None:
@@ -292,6 +291,32 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    transport_ms = None
+    if transport is not None and want == "auto":
+        def trial(tr, n=3):
+            nonlocal transport
+            transport = tr
+            step()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(n):
+                step()
+            b.record()
+            barrier()
+            tm = torch.tensor([a.elapsed_time(b) / n], dtype=torch.float64, device=dev)
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            return float(tm.item())
+        p2p = transport
+        probe = ClockSampler(local)
+        if rank == 0:
+            probe.start()
+        transport_ms = {"p2p": trial(p2p), "nccl": trial(None)}
+        if rank == 0:
+            probe.stop()
+        transport = p2p if transport_ms["p2p"] <= transport_ms["nccl"] else None  # same numbers on every rank
+    gather_kind = "peer-to-peer window writes over NVLink (copy engines)" if transport is not None else "NCCL gather"
 
     for _ in range(args.warmup):
         step()
@@ -477,7 +502,7 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32 (spectra/transfer) + f64 (setup, nthcomp, histograms)" if args.fp32 else "f64", "data": "synthetic",
-                "config": workload_config(world, P, args.tables), "gather_transport": gather_kind if world > 1 else None,
+                "config": workload_config(world, P, args.tables), "gather_transport": gather_kind if world > 1 else None, "gather_transport_trial_ms": transport_ms,
                 "clocks": clocks, "e2e": e2e,
                 "gpu_launches": int(launches), "roofline": roofline, "fp64_roofline": fp64, "kernels": kernels,
                 "cpu_baseline": cpu, "fit_statistic": fit, "checksum": chk}
