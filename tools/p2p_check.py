@@ -22,14 +22,21 @@ torch.cuda.synchronize()
 if rank == 0:
     same = all(torch.equal(a, b) for a, b in zip(g_nccl, g_p2p))
     print("p2p gather equals nccl gather:", same, flush=True)
+# `sampler` / `attrs` as further arguments: the two things bench.py's step has that this check does not
+sampler = bench.ClockSampler(local) if "sampler" in sys.argv[2:] and rank == 0 else None
+if sampler is not None:
+    sampler.start()
+extra = {"attrs": torch.empty((P, 24), dtype=torch.float64, device=dev)} if "attrs" in sys.argv[2:] else {}
 for name, kw in (("nccl pieces", {}), ("p2p hook", {"transport": tr})):
     for it in range(4):
         if it == 1:
             dist.barrier(); torch.cuda.synchronize(); t0 = time.perf_counter()
-        evaluate_sharded(ev, params, rel=True, gather_dst=0, out=out, gathered=g_nccl if not kw else None, **kw)
+        evaluate_sharded(ev, params, rel=True, gather_dst=0, out=out, gathered=g_nccl if not kw else None, **extra, **kw)
     dist.barrier(); torch.cuda.synchronize()
     dt = torch.tensor([(time.perf_counter() - t0) / 3], device=dev)
     dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     if rank == 0:
         print("%s: %.1f ms per step, %.0f spectra/s" % (name, dt.item() * 1e3, P * world / dt.item()), flush=True)
+if sampler is not None:
+    sampler.stop()
 dist.destroy_process_group()
