@@ -142,7 +142,7 @@ class ClockSampler:
 # ---------------------------------------------------------------------------
 def oracle_tables(tables):
     from oracle import oracle as O
-    return O.Tables(tables["spins"], tables["thetas"], tables["NR"], tables["NPHI"], tables["dl"], data=tables["data"])
+    return O.Tables(tables["spins"], tables["thetas"], tables["NR"], tables["NPHI"], tables["r_in"], data=tables["data"])
 
 
 def cpu_arm(params, tables, seconds_target, threads):
@@ -169,7 +169,7 @@ def get_tables(kind, ctx=None):
     if kind == "golden":
         d = np.load(os.path.join(ROOT, "tests", "golden", "golden_rel.npz"))
         return dict(spins=d["tab_spins"], thetas=d["tab_thetas"], NR=int(d["tab_NR"]), NPHI=int(d["tab_NPHI"]),
-                    dl=float(d["tab_dl"]), data=d["tab_data"])
+                    r_in=float(d["tab_r_in"]), data=d["tab_data"])
     from relagn_b200 import tables as T
     cfg = dict(T.DEFAULT)
     cached = T.cached_default()

@@ -104,18 +104,23 @@ void rg_ctx_destroy(rg_ctx *ctx);
  * (left + dE/2), nu grid; detects a geometric grid (needed for RG_FLAG_REL). */
 int rg_set_grid(rg_ctx *ctx, const double *ebins_host, int nE);
 
-/* ---- Kerr transfer tables ----
+/* ---- Kerr transfer tables (format 2) ----
  * Node grid: spins[n_spin] ascending, thetas[n_inc] ascending (radians).
- * Per node two planes g[NR][NPHI], jn[NR][NPHI] (float32); rows at
- * r_s = r_h + (risco - r_h) 10^(s dl), columns phi_t = 2 pi t/NPHI + phi0(r_s).
- * Layout [n_spin][n_inc][2][NR][NPHI].
- * generate: ray-traces on the device.  upload/download: host <-> device. */
+ * Per node two planes g[NR][NPHI], jn[NR][NPHI] (float32).  Rows are the SAME physical radii for every node,
+ * uniform in x(r) = 1/r + 1/sqrt(r) from r_in (row 0) to 1000 r_g (row NR-1: the reference leaves kyconv beyond
+ * log r = 3, relagn.py:992); rows inside 1.02 x the photon orbit of the node's spin carry no data (g = jn = 0).
+ * Columns phi_t = 2 pi t/NPHI + phi0(r_s), phi0 = disc azimuth of the ray alpha = 0, beta < 0.
+ * Layout [n_spin][n_inc][2][NR][NPHI].  A model (a, i) is looked up by Lagrange interpolation over up to 4 spin
+ * nodes x 4 inclination nodes of ln g and jn at fixed physical radius; adjacent spin nodes must both have data at
+ * the innermost radius of any model between them (upload/generate fail otherwise).
+ * generate: ray-traces on the device (*n_unresolved: points the solver lost; they keep jn = 0).
+ * upload/download: host <-> device. */
 int rg_tables_generate(rg_ctx *ctx, const double *spins, int n_spin, const double *thetas, int n_inc, int NR,
-                       int NPHI, double dl, long *n_unresolved);
+                       int NPHI, double r_in, long *n_unresolved);
 int rg_tables_upload(rg_ctx *ctx, const double *spins, int n_spin, const double *thetas, int n_inc, int NR, int NPHI,
-                     double dl, const float *data_host);
+                     double r_in, const float *data_host);
 int rg_tables_download(rg_ctx *ctx, float *data_host, size_t n_floats);
-int rg_tables_info(rg_ctx *ctx, int *n_spin, int *n_inc, int *NR, int *NPHI, double *dl, size_t *n_floats);
+int rg_tables_info(rg_ctx *ctx, int *n_spin, int *n_inc, int *NR, int *NPHI, double *r_in, size_t *n_floats);
 
 /* ---- B1: the kyconv seam ----
  * energies: host, nE+1 edges (geometric grid); par: the reference's 12

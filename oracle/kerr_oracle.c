@@ -276,11 +276,21 @@ static int march_to(double a, double th, double phi, double r_from, double r_to,
     return 1;
 }
 
-/* table row radius: r_s = r_h + (risco - r_h) 10^(s dl), r_h = 1 + sqrt(1-a^2) */
-static double row_radius(double a, int s, double dl)
+/* Table rows are the same physical radii for every node: uniform in x(r) = 1/r + C/sqrt(r) from r_in to
+ * RO_TAB_ROUT (C = 1).  g and Jn of a Keplerian disc are close to low-order polynomials of r^(-1/2), which keeps
+ * the linear row interpolation accurate with few rows; the 1/r term packs the rows closer where the relativistic
+ * terms are steep (near the ISCO of fast spins).  Row s: x_s = x(r_in) + s (x(r_out) - x(r_in)) / (NR - 1). */
+#define RO_TAB_ROUT 1000.0
+#define RO_ROW_C 1.0
+static double row_x(double r) { return 1.0 / r + RO_ROW_C / sqrt(r); }
+double ro_row_radius(double r_in, int NR, int s)
 {
-    double rh = 1 + sqrt(1 - a * a), ri = ro_risco(a);
-    return rh + (ri - rh) * pow(10.0, s * dl);
+    double x0 = row_x(r_in), x1 = row_x(RO_TAB_ROUT);
+    double x = x0 + s * ((x1 - x0) / (NR - 1));
+    if (s == 0) return r_in;
+    if (s == NR - 1) return RO_TAB_ROUT;
+    double u = 0.5 * (-RO_ROW_C + sqrt(RO_ROW_C * RO_ROW_C + 4 * x));
+    return 1.0 / (u * u);
 }
 
 /* disc azimuth of the "front" ray (alpha = 0, beta < 0) landing on radius r_e:
@@ -324,22 +334,28 @@ static int front_ray(double a, double th, double r_e, double *beta_f, double *ph
     return 1;
 }
 
-typedef struct { double a, theta_o, dl, co; int NR, NPHI; float *g, *jn; int *fail; const double *phi0; } node_ctx;
+typedef struct { double a, theta_o, co; int NR, NPHI; float *g, *jn; int *fail; const double *phi0; const double *rows; double r_valid; double *solA, *solB; } node_ctx;
 
 static void node_body(int t, void *vc)
 {
     node_ctx *c = (node_ctx *)vc;
-    double a = c->a, theta_o = c->theta_o, dl = c->dl, co = c->co;
+    double a = c->a, theta_o = c->theta_o, co = c->co;
     int NR = c->NR, NPHI = c->NPHI;
     float *g = c->g, *jn = c->jn;
     int nfail = 0;
     double A1 = 0, B1 = 0, A2 = 0, B2 = 0, r1 = 0; /* solutions at rows s+1, s+2 */
     int have = 0;
     for (int s = NR - 1; s >= 0; s--) {
-        double r = row_radius(a, s, dl);
+        double r = c->rows[s];
         double phi = 2 * PI * t / NPHI + c->phi0[s];
         double A, B, gg = 1, jj = co;
         int ok = 0;
+        c->solA[(size_t)s * NPHI + t] = NAN; c->solB[(size_t)s * NPHI + t] = NAN;
+        if (!(r > c->r_valid)) { /* no circular orbit (r <= photon orbit): the row carries no data */
+            g[(size_t)s * NPHI + t] = 0.0f;
+            jn[(size_t)s * NPHI + t] = 0.0f;
+            continue;
+        }
         if (have >= 2) { A = 2 * A1 - A2; B = 2 * B1 - B2; ok = ro_solve_point(a, theta_o, r, phi, &A, &B, &gg, &jj); }
         if (!ok && have >= 1) { /* rotate the previous solution by the change of azimuth origin, then march */
             double dph = c->phi0[s] - c->phi0[s + 1];
@@ -362,6 +378,7 @@ static void node_body(int t, void *vc)
         }
         g[(size_t)s * NPHI + t] = (float)gg;
         jn[(size_t)s * NPHI + t] = (float)jj;
+        c->solA[(size_t)s * NPHI + t] = A; c->solB[(size_t)s * NPHI + t] = B;
         if (have >= 1) { A2 = A1; B2 = B1; }
         A1 = A; B1 = B; r1 = r;
         have = have < 2 ? have + 1 : 2;
@@ -369,12 +386,21 @@ static void node_body(int t, void *vc)
     c->fail[t] = nfail;
 }
 
-int ro_node_phi0(double a, double theta_o, int NR, double dl, double *phi0)
+/* innermost radius a table row may have for spin a: a little outside the photon orbit
+ * r_ph = 2 (1 + cos(2/3 acos(-a))), inside which no circular orbit exists (the Keplerian g is imaginary) */
+double ro_r_valid(double a)
+{
+    double rph = 2 * (1 + cos(2.0 / 3.0 * acos(-a)));
+    return 1.02 * rph;
+}
+
+int ro_node_phi0(double a, double theta_o, int NR, const double *rows, double *phi0)
 {
     double bf = 0;
     int bad = 0;
     for (int s = NR - 1; s >= 0; s--) {
-        double r = row_radius(a, s, dl);
+        double r = rows[s];
+        if (!(r > ro_r_valid(a))) { phi0[s] = s + 1 < NR ? phi0[s + 1] : 0; continue; }
         if (s == NR - 1) bf = -r * cos(theta_o);
         double p = 0;
         if (!front_ray(a, theta_o, r, &bf, &p)) { bad++; p = s + 1 < NR ? phi0[s + 1] : 0; }
@@ -383,58 +409,225 @@ int ro_node_phi0(double a, double theta_o, int NR, double dl, double *phi0)
     return bad;
 }
 
-int ro_make_node(double a, double theta_o, int NR, int NPHI, double dl, float *g, float *jn, int threads)
+/* continuation along the ring: from the solved point (r, phi_from; A, B) to (r, phi_to), halving the step on failure */
+static int march_phi(double a, double th, double r, double phi_from, double phi_to, double *A, double *B,
+                     double *g, double *jn, int depth)
+{
+    double At = *A, Bt = *B;
+    if (ro_solve_point(a, th, r, phi_to, &At, &Bt, g, jn)) { *A = At; *B = Bt; return 1; }
+    if (depth >= 8) return 0;
+    double pm = 0.5 * (phi_from + phi_to);
+    double Am = *A, Bm = *B, gm, jm;
+    if (!march_phi(a, th, r, phi_from, pm, &Am, &Bm, &gm, &jm, depth + 1)) return 0;
+    if (!march_phi(a, th, r, pm, phi_to, &Am, &Bm, g, jn, depth + 1)) return 0;
+    *A = Am; *B = Bm;
+    return 1;
+}
+
+typedef struct { node_ctx *c; int *list; int *fixed; } repair_ctx;
+
+static void repair_body(int i, void *vc)
+{
+    repair_ctx *rc = (repair_ctx *)vc;
+    node_ctx *c = rc->c;
+    int NPHI = c->NPHI;
+    int s = rc->list[i] / NPHI, t = rc->list[i] % NPHI;
+    double r = c->rows[s], phi = 2 * PI * t / NPHI + c->phi0[s];
+    for (int side = 0; side < 2 && !rc->fixed[i]; side++) {
+        int tn = (t + (side ? 1 : NPHI - 1)) % NPHI;
+        double A = c->solA[(size_t)s * NPHI + tn], B = c->solB[(size_t)s * NPHI + tn];
+        if (A != A) continue;
+        double phin = phi + (side ? 1 : -1) * 2 * PI / NPHI, gg, jj;
+        if (march_phi(c->a, c->theta_o, r, phin, phi, &A, &B, &gg, &jj, 0)) {
+            /* results are published after the sweep (the neighbours of this sweep must not depend on its order) */
+            c->g[(size_t)s * NPHI + t] = (float)gg; c->jn[(size_t)s * NPHI + t] = (float)jj;
+            rc->fixed[i] = 1;
+            ((double *)c->solA)[(size_t)c->NR * NPHI + i] = A; ((double *)c->solB)[(size_t)c->NR * NPHI + i] = B;
+        }
+    }
+}
+
+int ro_make_node_rows(double a, double theta_o, int NR, const double *rows, int NPHI, float *g, float *jn, int threads)
 {
     int *fail = (int *)calloc(NPHI, sizeof(int));
     double *phi0 = (double *)calloc(NR, sizeof(double));
-    int nfail = ro_node_phi0(a, theta_o, NR, dl, phi0);
-    node_ctx c = {a, theta_o, dl, cos(theta_o), NR, NPHI, g, jn, fail, phi0};
+    size_t np = (size_t)NR * NPHI;
+    double *solA = (double *)malloc(sizeof(double) * 2 * np), *solB = (double *)malloc(sizeof(double) * 2 * np);
+    int nbad0 = ro_node_phi0(a, theta_o, NR, rows, phi0);
+    node_ctx c = {a, theta_o, cos(theta_o), NR, NPHI, g, jn, fail, phi0, rows, ro_r_valid(a), solA, solB};
     ro_par_for(NPHI, threads, node_body, &c);
+    int nfail = 0;
     for (int t = 0; t < NPHI; t++) nfail += fail[t];
-    free(fail); free(phi0);
+    /* repair sweeps: points the radial continuation lost are retried along the ring from solved neighbours */
+    for (int sweep = 0; sweep < 6 && nfail > 0; sweep++) {
+        int *list = (int *)malloc(sizeof(int) * np), *fixed = (int *)calloc(np, sizeof(int));
+        int n = 0;
+        for (size_t i = 0; i < np; i++)
+            if (rows[i / NPHI] > c.r_valid && solA[i] != solA[i]) list[n++] = (int)i;
+        repair_ctx rc = {&c, list, fixed};
+        ro_par_for(n, threads, repair_body, &rc);
+        int nfix = 0;
+        for (int i = 0; i < n; i++)
+            if (fixed[i]) { solA[list[i]] = solA[np + i]; solB[list[i]] = solB[np + i]; nfix++; }
+        free(list); free(fixed);
+        nfail = n - nfix;
+        if (nfix == 0) break;
+    }
+    nfail += nbad0;
+    free(fail); free(phi0); free(solA); free(solB);
+    return nfail;
+}
+
+int ro_make_node(double a, double theta_o, int NR, int NPHI, double r_in, float *g, float *jn, int threads)
+{
+    double *rows = (double *)malloc(sizeof(double) * NR);
+    for (int s = 0; s < NR; s++) rows[s] = ro_row_radius(r_in, NR, s);
+    int nfail = ro_make_node_rows(a, theta_o, NR, rows, NPHI, g, jn, threads);
+    free(rows);
     return nfail;
 }
 
 /* ------------------------------------------------------------------ */
 struct ro_tables {
     int n_spin, n_inc, NR, NPHI;
-    double dl;
-    double *spins, *riscos, *thetas;
-    float *data; /* [n_spin][n_inc][2][NR][NPHI] */
+    double r_in;
+    double *spins, *thetas, *rows;
+    int *first_row;  /* [n_spin]: first row outside ro_r_valid(spin) */
+    float *data;     /* [n_spin][n_inc][2][NR][NPHI]: g, Jn (the layout of the C ABI) */
+    float *lg;       /* [n_spin][n_inc][NR][NPHI]: (float) log((double) g), 0 where g = 0 (ro_tables_finish) */
+    int ready;
+    long serial;
 };
+static long g_tab_serial = 0;
 
-ro_tables *ro_tables_create(const double *spins, int n_spin, const double *thetas, int n_inc, int NR, int NPHI, double dl)
+ro_tables *ro_tables_create(const double *spins, int n_spin, const double *thetas, int n_inc, int NR, int NPHI, double r_in)
 {
     ro_tables *t = (ro_tables *)calloc(1, sizeof *t);
-    t->n_spin = n_spin; t->n_inc = n_inc; t->NR = NR; t->NPHI = NPHI; t->dl = dl;
+    t->n_spin = n_spin; t->n_inc = n_inc; t->NR = NR; t->NPHI = NPHI; t->r_in = r_in;
     t->spins = (double *)malloc(sizeof(double) * n_spin);
-    t->riscos = (double *)malloc(sizeof(double) * n_spin);
     t->thetas = (double *)malloc(sizeof(double) * n_inc);
-    for (int i = 0; i < n_spin; i++) { t->spins[i] = spins[i]; t->riscos[i] = ro_risco(spins[i]); }
+    t->rows = (double *)malloc(sizeof(double) * NR);
+    t->first_row = (int *)calloc(n_spin, sizeof(int));
+    for (int i = 0; i < n_spin; i++) t->spins[i] = spins[i];
     for (int i = 0; i < n_inc; i++) t->thetas[i] = thetas[i];
+    for (int s = 0; s < NR; s++) t->rows[s] = ro_row_radius(r_in, NR, s);
     t->data = (float *)calloc((size_t)n_spin * n_inc * 2 * NR * NPHI, sizeof(float));
+    t->lg = (float *)calloc((size_t)n_spin * n_inc * NR * NPHI, sizeof(float));
     return t;
 }
 
-ro_tables *ro_tables_generate(const double *spins, int n_spin, const double *thetas, int n_inc, int NR, int NPHI, double dl, int threads)
+/* derived arrays; call after the data block has been filled or changed */
+void ro_tables_finish(ro_tables *t)
 {
-    ro_tables *t = ro_tables_create(spins, n_spin, thetas, n_inc, NR, NPHI, dl);
+    size_t plane = (size_t)t->NR * t->NPHI;
+    for (int m = 0; m < t->n_spin; m++) {
+        double rv = ro_r_valid(t->spins[m]);
+        int f = 0;
+        while (f < t->NR && !(t->rows[f] > rv)) f++;
+        t->first_row[m] = f;
+        for (int n = 0; n < t->n_inc; n++) {
+            const float *g = t->data + ((size_t)m * t->n_inc + n) * 2 * plane;
+            float *lg = t->lg + ((size_t)m * t->n_inc + n) * plane;
+            for (size_t i = 0; i < plane; i++) lg[i] = g[i] > 0 ? (float)log((double)g[i]) : 0.0f;
+        }
+    }
+    t->serial = __sync_add_and_fetch(&g_tab_serial, 1);
+    t->ready = 1;
+}
+
+ro_tables *ro_tables_generate(const double *spins, int n_spin, const double *thetas, int n_inc, int NR, int NPHI, double r_in, int threads)
+{
+    ro_tables *t = ro_tables_create(spins, n_spin, thetas, n_inc, NR, NPHI, r_in);
     size_t plane = (size_t)NR * NPHI;
     for (int m = 0; m < n_spin; m++)
         for (int n = 0; n < n_inc; n++) {
             float *base = t->data + ((size_t)m * n_inc + n) * 2 * plane;
-            ro_make_node(spins[m], thetas[n], NR, NPHI, dl, base, base + plane, threads);
+            ro_make_node(spins[m], thetas[n], NR, NPHI, r_in, base, base + plane, threads);
         }
+    ro_tables_finish(t);
     return t;
 }
 
 void ro_tables_free(ro_tables *t)
 {
     if (!t) return;
-    free(t->spins); free(t->riscos); free(t->thetas); free(t->data); free(t);
+    free(t->spins); free(t->thetas); free(t->rows); free(t->first_row); free(t->data); free(t->lg); free(t);
 }
 float *ro_tables_data(ro_tables *t) { return t->data; }
 long ro_tables_nfloats(const ro_tables *t) { return (long)t->n_spin * t->n_inc * 2 * t->NR * t->NPHI; }
+
+/* ------------------------------------------------------------------ */
+/* Lookup for a model (a, theta_o): Lagrange interpolation over up to 4 spin nodes (coordinate a) x up to 4
+ * inclination nodes (coordinate theta) of ln g and Jn AT THE SAME PHYSICAL RADIUS (the rows are shared by all
+ * nodes).  A spin node only enters where it has data: its rows inside ro_r_valid(a_node) are empty, so nodes
+ * whose first row lies above the model's innermost row (the one bracketing risco(a) from below) are dropped
+ * from the low end of the stencil.                                                                         */
+static void lagrange_w(const double *xs, int n, double x, double *w)
+{
+    for (int i = 0; i < n; i++) {
+        double p = 1.0;
+        for (int k = 0; k < n; k++)
+            if (k != i) p *= (x - xs[k]) / (xs[i] - xs[k]);
+        w[i] = p;
+    }
+}
+
+/* nodes [*i0, *i0 + *k) around x (clamped into the node range), k <= 4 */
+static void stencil4(const double *nodes, int n, double x, int *i0, int *k)
+{
+    int i = 0;
+    while (i + 2 < n && x >= nodes[i + 1]) i++;
+    int lo = i - 1, hi = i + 2; /* inclusive */
+    if (lo < 0) lo = 0;
+    if (hi > n - 1) hi = n - 1;
+    *i0 = lo; *k = hi - lo + 1;
+}
+
+double ro_row_pos(const ro_tables *t, double r)
+{
+    double x0 = row_x(t->r_in), x1 = row_x(RO_TAB_ROUT);
+    double ell = (row_x(r) - x0) / ((x1 - x0) / (t->NR - 1));
+    if (!(ell > 0)) ell = 0;
+    if (ell > t->NR - 1) ell = t->NR - 1;
+    return ell;
+}
+
+/* the model's slice: sl_lg[NR][NPHI] = ln g, sl_jn[NR][NPHI] = Jn, rows >= *s_lo filled.  returns 0 ok,
+ * 5 when the table has no valid stencil for this spin (node grid too coarse near the top). */
+int ro_slice(const ro_tables *t, double a, double theta_o, double *sl_lg, double *sl_jn, int *s_lo)
+{
+    int NR = t->NR, NP = t->NPHI;
+    size_t plane = (size_t)NR * NP;
+    double ac = a < t->spins[0] ? t->spins[0] : (a > t->spins[t->n_spin - 1] ? t->spins[t->n_spin - 1] : a);
+    double thc = theta_o < t->thetas[0] ? t->thetas[0] : (theta_o > t->thetas[t->n_inc - 1] ? t->thetas[t->n_inc - 1] : theta_o);
+    int need = (int)floor(ro_row_pos(t, ro_risco(a)));
+    if (need > NR - 2) need = NR - 2;
+    if (need < 0) need = 0;
+    int m0, km, n0, kn;
+    stencil4(t->spins, t->n_spin, ac, &m0, &km);
+    while (km > 1 && t->first_row[m0] > need && ac >= t->spins[m0 + 1]) { m0++; km--; } /* drop empty low-spin nodes */
+    for (int i = 0; i < km; i++)
+        if (t->first_row[m0 + i] > need) return 5;
+    stencil4(t->thetas, t->n_inc, thc, &n0, &kn);
+    double wa[4], wi[4];
+    lagrange_w(t->spins + m0, km, ac, wa);
+    lagrange_w(t->thetas + n0, kn, thc, wi);
+    for (int s = need; s < NR; s++)
+        for (int p = 0; p < NP; p++) {
+            size_t i = (size_t)s * NP + p;
+            double lg = 0, jn = 0;
+            for (int im = 0; im < km; im++)
+                for (int in = 0; in < kn; in++) {
+                    size_t node = (size_t)(m0 + im) * t->n_inc + (n0 + in);
+                    double w = wa[im] * wi[in];
+                    lg += w * (double)t->lg[node * plane + i];
+                    jn += w * (double)t->data[node * 2 * plane + plane + i];
+                }
+            sl_lg[i] = lg; sl_jn[i] = jn;
+        }
+    *s_lo = need;
+    return 0;
+}
 
 /* hat kernel average over [lo,hi] (in units of bins, relative to bin centre 0) */
 static double hat_avg_piece(double lo, double hi, double L, double R, int neg)
@@ -489,38 +682,51 @@ int ro_auto_nsub(double r1, double r2, double dlnE)
     return nsub > 4096 ? 4096 : nsub;
 }
 
+/* per-thread cache of the last slice (the region drivers call the seam once per annulus of the same model) */
+typedef struct { const ro_tables *t; long serial; double a, th; int s_lo, n; double *lg, *w; } slice_cache;
+static __thread slice_cache g_sc;
+
+static int get_slice(const ro_tables *t, double a, double theta_o, const double **lg, const double **w, int *s_lo)
+{
+    size_t n = (size_t)t->NR * t->NPHI;
+    if (g_sc.t == t && g_sc.serial == t->serial && g_sc.a == a && g_sc.th == theta_o && g_sc.n == (int)n) {
+        *lg = g_sc.lg; *w = g_sc.w; *s_lo = g_sc.s_lo;
+        return 0;
+    }
+    if (g_sc.n != (int)n) {
+        free(g_sc.lg); free(g_sc.w);
+        g_sc.lg = (double *)malloc(sizeof(double) * n); g_sc.w = (double *)malloc(sizeof(double) * n);
+        g_sc.n = (int)n;
+    }
+    g_sc.t = NULL;
+    int st = ro_slice(t, a, theta_o, g_sc.lg, g_sc.w, &g_sc.s_lo);
+    if (st) return st;
+    /* weight density w = Jn g^3 per slice sample (a Lagrange overshoot below zero carries no weight) */
+    for (size_t i = (size_t)g_sc.s_lo * t->NPHI; i < n; i++) {
+        double jn = g_sc.w[i] > 0 ? g_sc.w[i] : 0.0;
+        g_sc.w[i] = jn * exp(3.0 * g_sc.lg[i]);
+    }
+    g_sc.t = t; g_sc.serial = t->serial; g_sc.a = a; g_sc.th = theta_o;
+    *lg = g_sc.lg; *w = g_sc.w; *s_lo = g_sc.s_lo;
+    return 0;
+}
+
 int ro_ky_kernel(const ro_tables *t, double a, double theta_o, double r1, double r2,
                  double alpha, double beta, double rb, double zshift, double dlnE, int nsub,
                  double *Hc, int cap, int *kmin, int *nk)
 {
-    if (!t || !(r2 > r1) || !(dlnE > 0)) return 1;
+    if (!t || !t->ready || !(r2 > r1) || !(dlnE > 0)) return 1;
     int NR = t->NR, NP = t->NPHI;
-    size_t plane = (size_t)NR * NP;
-    /* node weights */
-    int m0 = 0;
-    while (m0 + 2 < t->n_spin && a >= t->spins[m0 + 1]) m0++;
-    int m1 = m0 + 1 < t->n_spin ? m0 + 1 : m0;
-    double risco = ro_risco(a), rh = 1 + sqrt(1 - a * a);
-    double fa = 0;
-    if (m1 != m0) { fa = (t->riscos[m0] - risco) / (t->riscos[m0] - t->riscos[m1]); if (fa < 0) fa = 0; if (fa > 1) fa = 1; }
-    int n0 = 0;
-    while (n0 + 2 < t->n_inc && theta_o >= t->thetas[n0 + 1]) n0++;
-    int n1 = n0 + 1 < t->n_inc ? n0 + 1 : n0;
-    double fi = 0;
-    if (n1 != n0) { fi = (theta_o - t->thetas[n0]) / (t->thetas[n1] - t->thetas[n0]); if (fi < 0) fi = 0; if (fi > 1) fi = 1; }
-    const float *N00 = t->data + ((size_t)m0 * t->n_inc + n0) * 2 * plane;
-    const float *N01 = t->data + ((size_t)m0 * t->n_inc + n1) * 2 * plane;
-    const float *N10 = t->data + ((size_t)m1 * t->n_inc + n0) * 2 * plane;
-    const float *N11 = t->data + ((size_t)m1 * t->n_inc + n1) * 2 * plane;
-    double w00 = (1 - fa) * (1 - fi), w01 = (1 - fa) * fi, w10 = fa * (1 - fi), w11 = fa * fi;
-
+    const double *LG, *WT;
+    int s_lo;
+    int st = get_slice(t, a, theta_o, &LG, &WT, &s_lo);
+    if (st) return st;
+    double inv_dlnE = 1.0 / dlnE;
     double lnr = log(r2 / r1);
     if (nsub <= 0) nsub = ro_auto_nsub(r1, r2, dlnE);
     int K_LO = (int)floor(log(0.005) / dlnE) - 2, K_HI = (int)ceil(log(4.0) / dlnE) + 2;
-    int zoff = 0;
     double zs = 0;
     if (zshift != 0) zs = -log(1 + zshift) / dlnE;
-    (void)zoff;
     K_LO += (int)floor(zs) - 1; K_HI += (int)ceil(zs) + 1;
     int nH = K_HI - K_LO + 1;
     double *H = (double *)calloc(nH, sizeof(double));
@@ -534,24 +740,17 @@ int ro_ky_kernel(const ro_tables *t, double a, double theta_o, double r1, double
         double emis = 1.0;
         if (alpha != 0 || beta != 0) emis = rm < rb ? pow(rm, -alpha) : pow(rm, -beta) * pow(rb, beta - alpha);
         double A = 0.5 * (rbb * rbb - ra * ra) * emis;
-        double ell = log10((rm - rh) / (risco - rh)) / t->dl;
-        if (!(rm > rh)) ell = 0;
-        if (ell < 0) ell = 0;
-        if (ell > NR - 1) ell = NR - 1;
+        double ell = ro_row_pos(t, rm);
         int s0 = (int)floor(ell);
         if (s0 > NR - 2) s0 = NR - 2;
-        if (s0 < 0) s0 = 0;
+        if (s0 < s_lo) s0 = s_lo; /* (annuli start at risco: only a caller's r_in below the slice gets here) */
         double fr = ell - s0;
-        int s1 = s0 + 1 < NR ? s0 + 1 : s0;
+        if (fr < 0) fr = 0;
+        int s1 = s0 + 1;
         for (int p = 0; p < NP; p++) {
             size_t i0 = (size_t)s0 * NP + p, i1 = (size_t)s1 * NP + p;
-            double g0 = w00 * N00[i0] + w01 * N01[i0] + w10 * N10[i0] + w11 * N11[i0];
-            double g1 = w00 * N00[i1] + w01 * N01[i1] + w10 * N10[i1] + w11 * N11[i1];
-            double j0 = w00 * N00[plane + i0] + w01 * N01[plane + i0] + w10 * N10[plane + i0] + w11 * N11[plane + i0];
-            double j1 = w00 * N00[plane + i1] + w01 * N01[plane + i1] + w10 * N10[plane + i1] + w11 * N11[plane + i1];
-            double gg = g0 + fr * (g1 - g0), jj = j0 + fr * (j1 - j0);
-            sv[p] = log(gg) / dlnE + zs;
-            wv[p] = jj * gg * gg * gg;
+            sv[p] = (LG[i0] + fr * (LG[i1] - LG[i0])) * inv_dlnE + zs;
+            wv[p] = WT[i0] + fr * (WT[i1] - WT[i0]);
         }
         for (int p = 0; p < NP; p++) {
             int p1 = p + 1 == NP ? 0 : p + 1;

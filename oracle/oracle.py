@@ -65,6 +65,14 @@ def lib():
     L.ro_trace_ray.argtypes = [C.c_double] * 4 + [C.POINTER(C.c_double)] * 2
     L.ro_make_node.restype = C.c_int
     L.ro_make_node.argtypes = [C.c_double, C.c_double, C.c_int, C.c_int, C.c_double, _fp, _fp, C.c_int]
+    L.ro_row_radius.restype = C.c_double
+    L.ro_row_radius.argtypes = [C.c_double, C.c_int, C.c_int]
+    L.ro_r_valid.restype = C.c_double
+    L.ro_r_valid.argtypes = [C.c_double]
+    L.ro_tables_finish.restype = None
+    L.ro_tables_finish.argtypes = [C.c_void_p]
+    L.ro_slice.restype = C.c_int
+    L.ro_slice.argtypes = [C.c_void_p, C.c_double, C.c_double, _dp, _dp, C.POINTER(C.c_int)]
     L.ro_tables_create.restype = C.c_void_p
     L.ro_tables_create.argtypes = [_dp, C.c_int, _dp, C.c_int, C.c_int, C.c_int, C.c_double]
     L.ro_tables_generate.restype = C.c_void_p
@@ -124,18 +132,32 @@ def thcompton(tempbb, theta, gamma):
 class Tables:
     """Kerr transfer tables (CPU-generated or wrapped around a given array)."""
 
-    def __init__(self, spins, thetas, NR, NPHI, dl, data=None, threads=0):
+    def __init__(self, spins, thetas, NR, NPHI, r_in, data=None, threads=0):
         self.spins = np.ascontiguousarray(spins, dtype=np.float64)
         self.thetas = np.ascontiguousarray(thetas, dtype=np.float64)
-        self.NR, self.NPHI, self.dl = int(NR), int(NPHI), float(dl)
+        self.NR, self.NPHI, self.r_in = int(NR), int(NPHI), float(r_in)
         L = lib()
         if data is None:
             self.ptr = L.ro_tables_generate(self.spins, self.spins.size, self.thetas, self.thetas.size, self.NR,
-                                            self.NPHI, self.dl, threads)
+                                            self.NPHI, self.r_in, threads)
         else:
             self.ptr = L.ro_tables_create(self.spins, self.spins.size, self.thetas, self.thetas.size, self.NR,
-                                          self.NPHI, self.dl)
+                                          self.NPHI, self.r_in)
             self.data[...] = np.asarray(data, dtype=np.float32).reshape(self.data.shape)
+            L.ro_tables_finish(self.ptr)
+
+    def rows(self):
+        return np.array([lib().ro_row_radius(self.r_in, self.NR, s) for s in range(self.NR)])
+
+    def slice(self, a, theta_o):
+        """(ln g [NR][NPHI], Jn [NR][NPHI], first row) of the blended slice at (a, theta_o)."""
+        lg = np.zeros((self.NR, self.NPHI))
+        jn = np.zeros((self.NR, self.NPHI))
+        s_lo = C.c_int(0)
+        st = lib().ro_slice(self.ptr, float(a), float(theta_o), lg, jn, C.byref(s_lo))
+        if st:
+            raise RuntimeError("ro_slice status %d" % st)
+        return lg, jn, s_lo.value
 
     @property
     def data(self):
@@ -158,10 +180,10 @@ def trace_ray(a, theta_o, alpha, beta):
     return ok, r.value, p.value
 
 
-def make_node(a, theta_o, NR, NPHI, dl, threads=0):
+def make_node(a, theta_o, NR, NPHI, r_in, threads=0):
     g = np.zeros((NR, NPHI), dtype=np.float32)
     jn = np.zeros((NR, NPHI), dtype=np.float32)
-    nfail = lib().ro_make_node(a, theta_o, NR, NPHI, dl, g, jn, threads)
+    nfail = lib().ro_make_node(a, theta_o, NR, NPHI, r_in, g, jn, threads)
     return g, jn, nfail
 
 

@@ -177,29 +177,29 @@ class Context:
         self.ebins = eb.copy()
 
     # ---- tables ----
-    def tables_upload(self, spins, thetas, NR, NPHI, dl, data):
+    def tables_upload(self, spins, thetas, NR, NPHI, r_in, data):
         sp = np.ascontiguousarray(spins, dtype=np.float64)
         th = np.ascontiguousarray(thetas, dtype=np.float64)
         dat = np.ascontiguousarray(data, dtype=np.float32)
         assert dat.size == sp.size * th.size * 2 * NR * NPHI
-        self._check(self.lib.rg_tables_upload(self.h, _d(sp), sp.size, _d(th), th.size, int(NR), int(NPHI), float(dl),
+        self._check(self.lib.rg_tables_upload(self.h, _d(sp), sp.size, _d(th), th.size, int(NR), int(NPHI), float(r_in),
                                               dat.ctypes.data_as(_fp)))
 
-    def tables_generate(self, spins, thetas, NR, NPHI, dl):
+    def tables_generate(self, spins, thetas, NR, NPHI, r_in):
         sp = np.ascontiguousarray(spins, dtype=np.float64)
         th = np.ascontiguousarray(thetas, dtype=np.float64)
         bad = C.c_long(0)
         self._check(self.lib.rg_tables_generate(self.h, _d(sp), sp.size, _d(th), th.size, int(NR), int(NPHI),
-                                                float(dl), C.byref(bad)))
+                                                float(r_in), C.byref(bad)))
         return bad.value
 
     def tables_info(self):
         ns, ni, nr, nphi = C.c_int(), C.c_int(), C.c_int(), C.c_int()
-        dl = C.c_double()
+        r_in = C.c_double()
         nf = C.c_size_t()
-        self._check(self.lib.rg_tables_info(self.h, C.byref(ns), C.byref(ni), C.byref(nr), C.byref(nphi), C.byref(dl),
+        self._check(self.lib.rg_tables_info(self.h, C.byref(ns), C.byref(ni), C.byref(nr), C.byref(nphi), C.byref(r_in),
                                             C.byref(nf)))
-        return dict(n_spin=ns.value, n_inc=ni.value, NR=nr.value, NPHI=nphi.value, dl=dl.value, n_floats=nf.value)
+        return dict(n_spin=ns.value, n_inc=ni.value, NR=nr.value, NPHI=nphi.value, r_in=r_in.value, n_floats=nf.value)
 
     def tables_download(self):
         info = self.tables_info()

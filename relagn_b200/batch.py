@@ -21,7 +21,7 @@ class BatchEvaluator:
     ebins  : nE+1 bin edges in keV (the reference's `Ebins` / `new_ear`, relagn.py:335,780-805)
     model  : "relagn" (15 params) or "relqso" (7 params)
     tables : None -> default Kerr transfer tables (generated on the device on first use and cached on disk),
-             or a dict(spins, thetas, NR, NPHI, dl, data) to upload.
+             or a dict(spins, thetas, NR, NPHI, r_in, data) to upload.
     """
 
     def __init__(self, ebins, model="relagn", device=None, tables=None, dr_dex=50.0):
@@ -45,7 +45,7 @@ class BatchEvaluator:
         if t is None:
             _tables.load_default(self.ctx)
         else:
-            self.ctx.tables_upload(t["spins"], t["thetas"], t["NR"], t["NPHI"], t["dl"], t["data"])
+            self.ctx.tables_upload(t["spins"], t["thetas"], t["NR"], t["NPHI"], t["r_in"], t["data"])
         self._tables_ready = True
 
     # ---- device-resident path -------------------------------------------------

@@ -48,11 +48,13 @@ struct rg_ctx {
     bool have_tab = false;
     TabDesc td;
     float *d_tab = nullptr;
-    double2 *d_tab2 = nullptr; // (g, jn) pairs in double: one 16-byte load per table node
+    float2 *d_tab2 = nullptr; // (ln g, jn) pairs: one 8-byte load per table node
     double *d_tabmeta = nullptr;
-    double *d_rowrange = nullptr;
+    int *d_firstrow = nullptr;
+    int *d_kystatus = nullptr;
     size_t tab_floats = 0;
     std::vector<double> h_spins, h_thetas;
+    std::vector<int> h_firstrow;
     // batch scratch
     double *d_p10 = nullptr;
     SetRec *d_recs = nullptr;
@@ -164,7 +166,7 @@ extern "C" void rg_ctx_destroy(rg_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    free_dev(c->d_grid); free_dev(c->d_tab); free_dev(c->d_tab2); free_dev(c->d_tabmeta); free_dev(c->d_rowrange); free_dev(c->d_p10); free_dev(c->d_recs);
+    free_dev(c->d_grid); free_dev(c->d_tab); free_dev(c->d_tab2); free_dev(c->d_tabmeta); free_dev(c->d_firstrow); free_dev(c->d_kystatus); free_dev(c->d_p10); free_dev(c->d_recs);
     free_dev(c->d_counter); free_dev(c->d_syslist); free_dev(c->d_sptot); free_dev(c->d_farr); free_dev(c->d_header); free_dev(c->d_sc);
     free_dev(c->d_rq); free_dev(c->d_queue); free_dev(c->d_partial); free_dev(c->d_hist); free_dev(c->d_edges); free_dev(c->d_kyH); free_dev(c->d_kyin); free_dev(c->d_kyout);
     free_dev(c->d_stage_par); free_dev(c->d_stage_out); free_dev(c->d_stage_attr); free_dev(c->d_stats);
@@ -355,35 +357,61 @@ extern "C" int rg_set_grid(rg_ctx *c, const double *eb, int nE)
 // ---------------------------------------------------------------------------
 // tables
 static int tables_alloc(rg_ctx *c, const double *spins, int n_spin, const double *thetas, int n_inc, int NR, int NPHI,
-                        double dl)
+                        double r_in)
 {
-    if (!c || !spins || !thetas || n_spin < 1 || n_inc < 1 || NR < 2 || !(dl > 0))
+    if (!c || !spins || !thetas || n_spin < 1 || n_inc < 1 || NR < 2 || !(r_in > 1.0) || !(r_in < RG_TAB_ROUT))
         return rg_set_error(RG_E_ARG, "tables: bad arguments");
     if (NPHI < 32 || NPHI > RG_SPEC_THREADS || RG_SPEC_THREADS % NPHI != 0)
         return rg_set_error(RG_E_ARG, "tables: NPHI must be 32, 64, 128 or 256");
+    if ((size_t)NR * NPHI * sizeof(double2) > 160 * 1024)
+        return rg_set_error(RG_E_ARG, "tables: NR x NPHI = %d x %d exceeds the shared-memory slice (10240 samples)", NR, NPHI);
     for (int i = 1; i < n_spin; i++)
         if (!(spins[i] > spins[i - 1])) return rg_set_error(RG_E_ARG, "tables: spins must ascend");
     for (int i = 1; i < n_inc; i++)
         if (!(thetas[i] > thetas[i - 1])) return rg_set_error(RG_E_ARG, "tables: inclinations must ascend");
     RG_CUDA_OK(cudaSetDevice(c->device));
-    free_dev(c->d_tab); free_dev(c->d_tab2); free_dev(c->d_tabmeta); free_dev(c->d_rowrange);
-    c->d_tab = nullptr; c->d_tab2 = nullptr; c->d_tabmeta = nullptr; c->d_rowrange = nullptr; c->have_tab = false;
+    free_dev(c->d_tab); free_dev(c->d_tab2); free_dev(c->d_tabmeta); free_dev(c->d_firstrow);
+    c->d_tab = nullptr; c->d_tab2 = nullptr; c->d_tabmeta = nullptr; c->d_firstrow = nullptr; c->have_tab = false;
     c->tab_floats = (size_t)n_spin * n_inc * 2 * NR * NPHI;
     RG_CUDA_OK(cudaMalloc(&c->d_tab, c->tab_floats * sizeof(float)));
-    std::vector<double> meta(2 * n_spin + n_inc);
-    for (int i = 0; i < n_spin; i++) { meta[i] = spins[i]; meta[n_spin + i] = rg_risco(spins[i]); }
-    for (int i = 0; i < n_inc; i++) meta[2 * n_spin + i] = thetas[i];
+    std::vector<double> meta(n_spin + n_inc);
+    for (int i = 0; i < n_spin; i++) meta[i] = spins[i];
+    for (int i = 0; i < n_inc; i++) meta[n_spin + i] = thetas[i];
     RG_CUDA_OK(cudaMalloc(&c->d_tabmeta, meta.size() * sizeof(double)));
     RG_CUDA_OK(cudaMemcpy(c->d_tabmeta, meta.data(), meta.size() * sizeof(double), cudaMemcpyHostToDevice));
+    // first row with data per spin node: rows inside 1.02 x photon orbit are empty (kerr_oracle.c: ro_tables_finish)
+    std::vector<int> first(n_spin);
+    for (int m = 0; m < n_spin; m++) {
+        const double rv = rg_r_valid(spins[m]);
+        int f = 0;
+        while (f < NR && !(rg_row_radius(r_in, NR, f) > rv)) f++;
+        first[m] = f;
+    }
+    RG_CUDA_OK(cudaMalloc(&c->d_firstrow, n_spin * sizeof(int)));
+    RG_CUDA_OK(cudaMemcpy(c->d_firstrow, first.data(), n_spin * sizeof(int), cudaMemcpyHostToDevice));
     TabDesc &t = c->td;
-    t.data = c->d_tab; t.spins = c->d_tabmeta; t.riscos = c->d_tabmeta + n_spin; t.thetas = c->d_tabmeta + 2 * n_spin;
-    t.n_spin = n_spin; t.n_inc = n_inc; t.NR = NR; t.NPHI = NPHI; t.dl = dl;
+    t.data = c->d_tab; t.spins = c->d_tabmeta; t.thetas = c->d_tabmeta + n_spin; t.first_row = c->d_firstrow;
+    t.n_spin = n_spin; t.n_inc = n_inc; t.NR = NR; t.NPHI = NPHI; t.r_in = r_in;
+    t.x0 = rg_row_x(r_in);
+    t.dx = (rg_row_x(RG_TAB_ROUT) - t.x0) / (NR - 1);
     c->h_spins.assign(spins, spins + n_spin);
     c->h_thetas.assign(thetas, thetas + n_inc);
+    c->h_firstrow = first;
+    if (!c->d_kystatus) RG_CUDA_OK(cudaMalloc(&c->d_kystatus, sizeof(int)));
     return RG_OK;
 }
 
-// range of ln g over every node: bounds the shift histogram
+static double host_row_pos(const TabDesc &t, double r)
+{
+    double ell = (rg_row_x(r) - t.x0) / t.dx;
+    if (!(ell > 0)) ell = 0;
+    if (ell > t.NR - 1) ell = t.NR - 1;
+    return ell;
+}
+
+// (ln g, Jn) planes for the kernels (ln g through the host's log(), the oracle's: the float rounding of the planes
+// must not depend on whose libm computed them), validity of the spin stencils, and the range of ln g over the
+// usable rows, which bounds the shift histogram
 static int tables_finish(rg_ctx *c, const float *host_data)
 {
     std::vector<float> tmp;
@@ -392,40 +420,46 @@ static int tables_finish(rg_ctx *c, const float *host_data)
         RG_CUDA_OK(cudaMemcpy(tmp.data(), c->d_tab, c->tab_floats * sizeof(float), cudaMemcpyDeviceToHost));
         host_data = tmp.data();
     }
-    size_t plane = (size_t)c->td.NR * c->td.NPHI;
-    size_t nodes = (size_t)c->td.n_spin * c->td.n_inc;
+    const TabDesc &t = c->td;
+    const int NR = t.NR, NP = t.NPHI, n_spin = t.n_spin, n_inc = t.n_inc;
+    size_t plane = (size_t)NR * NP;
+    size_t nodes = (size_t)n_spin * n_inc;
+    // every spin interval needs its two own nodes down to the innermost row a model of that interval uses
+    for (int m = 0; m + 1 < n_spin || m == 0; m++) {
+        const int top = m + 1 < n_spin ? m + 1 : m;
+        int need = (int)floor(host_row_pos(t, rg_risco(c->h_spins[top])));
+        if (need > NR - 2) need = NR - 2;
+        if (c->h_firstrow[m] > need || c->h_firstrow[top] > need)
+            return rg_set_error(RG_E_ARG, "tables: spin nodes %g and %g are too far apart: node %g has no circular orbit at "
+                                          "the innermost radius of a model with spin %g", c->h_spins[m], c->h_spins[top],
+                                c->h_spins[m], c->h_spins[top]);
+        if (n_spin == 1) break;
+    }
     double gmin = 1e300, gmax = 0;
-    const int NR = c->td.NR, NP = c->td.NPHI;
-    std::vector<double> rr(nodes * NR * 2);
-    for (size_t n = 0; n < nodes; n++) {
-        const float *g = host_data + n * 2 * plane;
-        for (int s = 0; s < NR; s++) {
-            double lo = 1e300, hi = 0;
-            for (int p = 0; p < NP; p++) {
-                double v = g[(size_t)s * NP + p];
-                if (!(v > 0) || !(v < 1e30))
-                    return rg_set_error(RG_E_ARG, "tables: non-positive or non-finite g in node %zu", n);
-                lo = std::min(lo, v); hi = std::max(hi, v);
-            }
-            rr[(n * NR + s) * 2] = log(lo);
-            rr[(n * NR + s) * 2 + 1] = log(hi);
-            gmin = std::min(gmin, lo); gmax = std::max(gmax, hi);
+    std::vector<float2> pairs(nodes * plane);
+    for (int m = 0; m < n_spin; m++) {
+        // rows of node m that can enter a slice: down to the innermost row of the fastest model it is blended into
+        const int mt = m + 2 < n_spin ? m + 2 : n_spin - 1;
+        int use = (int)floor(host_row_pos(t, rg_risco(c->h_spins[mt])));
+        if (use < c->h_firstrow[m]) use = c->h_firstrow[m];
+        for (int n = 0; n < n_inc; n++) {
+            const size_t node = (size_t)m * n_inc + n;
+            const float *g = host_data + node * 2 * plane, *jn = g + plane;
+            for (int s = 0; s < NR; s++)
+                for (int p = 0; p < NP; p++) {
+                    const size_t i = (size_t)s * NP + p;
+                    const double v = g[i];
+                    if (s >= c->h_firstrow[m] && (!(v > 0) || !(v < 1e30)))
+                        return rg_set_error(RG_E_ARG, "tables: non-positive or non-finite g in node %zu row %d", node, s);
+                    pairs[node * plane + i].x = v > 0 ? (float)log(v) : 0.0f;
+                    pairs[node * plane + i].y = jn[i];
+                    if (s >= use) { gmin = std::min(gmin, v); gmax = std::max(gmax, v); }
+                }
         }
     }
-    {
-        std::vector<double2> pairs(nodes * plane);
-        for (size_t n = 0; n < nodes; n++)
-            for (size_t i = 0; i < plane; i++) {
-                pairs[n * plane + i].x = (double)host_data[n * 2 * plane + i];
-                pairs[n * plane + i].y = (double)host_data[n * 2 * plane + plane + i];
-            }
-        RG_CUDA_OK(cudaMalloc(&c->d_tab2, pairs.size() * sizeof(double2)));
-        RG_CUDA_OK(cudaMemcpy(c->d_tab2, pairs.data(), pairs.size() * sizeof(double2), cudaMemcpyHostToDevice));
-        c->td.pairs = c->d_tab2;
-    }
-    RG_CUDA_OK(cudaMalloc(&c->d_rowrange, rr.size() * sizeof(double)));
-    RG_CUDA_OK(cudaMemcpy(c->d_rowrange, rr.data(), rr.size() * sizeof(double), cudaMemcpyHostToDevice));
-    c->td.rowrange = c->d_rowrange;
+    RG_CUDA_OK(cudaMalloc(&c->d_tab2, pairs.size() * sizeof(float2)));
+    RG_CUDA_OK(cudaMemcpy(c->d_tab2, pairs.data(), pairs.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    c->td.pairs = c->d_tab2;
     c->td.lng_min = log(gmin);
     c->td.lng_max = log(gmax);
     c->have_tab = true;
@@ -433,20 +467,20 @@ static int tables_finish(rg_ctx *c, const float *host_data)
 }
 
 extern "C" int rg_tables_upload(rg_ctx *c, const double *spins, int n_spin, const double *thetas, int n_inc, int NR,
-                                int NPHI, double dl, const float *data)
+                                int NPHI, double r_in, const float *data)
 {
     if (!data) return rg_set_error(RG_E_ARG, "rg_tables_upload: data is NULL");
-    RG_TRY(tables_alloc(c, spins, n_spin, thetas, n_inc, NR, NPHI, dl));
+    RG_TRY(tables_alloc(c, spins, n_spin, thetas, n_inc, NR, NPHI, r_in));
     RG_CUDA_OK(cudaMemcpy(c->d_tab, data, c->tab_floats * sizeof(float), cudaMemcpyHostToDevice));
     return tables_finish(c, data);
 }
 
 extern "C" int rg_tables_generate(rg_ctx *c, const double *spins, int n_spin, const double *thetas, int n_inc, int NR,
-                                  int NPHI, double dl, long *n_unresolved)
+                                  int NPHI, double r_in, long *n_unresolved)
 {
-    RG_TRY(tables_alloc(c, spins, n_spin, thetas, n_inc, NR, NPHI, dl));
+    RG_TRY(tables_alloc(c, spins, n_spin, thetas, n_inc, NR, NPHI, r_in));
     long bad = 0;
-    RG_TRY(rg_launch_raytrace(spins, n_spin, thetas, n_inc, NR, NPHI, dl, c->d_tab, &bad, c->stream));
+    RG_TRY(rg_launch_raytrace(spins, n_spin, thetas, n_inc, NR, NPHI, r_in, c->d_tab, &bad, c->stream));
     c->launches += 2L * n_spin * n_inc;
     if (n_unresolved) *n_unresolved = bad;
     return tables_finish(c, nullptr);
@@ -461,14 +495,14 @@ extern "C" int rg_tables_download(rg_ctx *c, float *data, size_t n_floats)
     return RG_OK;
 }
 
-extern "C" int rg_tables_info(rg_ctx *c, int *n_spin, int *n_inc, int *NR, int *NPHI, double *dl, size_t *n_floats)
+extern "C" int rg_tables_info(rg_ctx *c, int *n_spin, int *n_inc, int *NR, int *NPHI, double *r_in, size_t *n_floats)
 {
     if (!c || !c->have_tab) return rg_set_error(RG_E_NOTABLES, "no tables resident");
     if (n_spin) *n_spin = c->td.n_spin;
     if (n_inc) *n_inc = c->td.n_inc;
     if (NR) *NR = c->td.NR;
     if (NPHI) *NPHI = c->td.NPHI;
-    if (dl) *dl = c->td.dl;
+    if (r_in) *r_in = c->td.r_in;
     if (n_floats) *n_floats = c->tab_floats;
     return RG_OK;
 }
@@ -500,11 +534,15 @@ static int ky_hist_host(rg_ctx *c, double a, double th, double r1, double r2, do
         RG_CUDA_OK(cudaMalloc(&c->d_kyH, (size_t)nH * sizeof(double)));
         c->kyH_cap = nH;
     }
-    RG_TRY(rg_launch_ky_hist(c->td, a, th, r1, r2, alpha, beta, rb, zshift, dlnE, nsub, c->d_kyH, K_LO, nH, c->stream));
+    RG_TRY(rg_launch_ky_hist(c->td, a, th, r1, r2, alpha, beta, rb, zshift, dlnE, nsub, c->d_kyH, K_LO, nH, c->d_kystatus,
+                             c->stream));
     c->launches++;
     H.resize(nH);
+    int kst = 0;
     RG_CUDA_OK(cudaMemcpyAsync(H.data(), c->d_kyH, (size_t)nH * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    RG_CUDA_OK(cudaMemcpyAsync(&kst, c->d_kystatus, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     RG_CUDA_OK(cudaStreamSynchronize(c->stream));
+    if (kst) return rg_set_error(RG_E_ARG, "kyconv: the resident tables have no valid spin stencil for a = %g", a);
     return RG_OK;
 }
 

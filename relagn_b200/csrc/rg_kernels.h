@@ -5,17 +5,19 @@
 
 #define RG_SPEC_THREADS 256
 
-// Kerr transfer tables resident on the device
+// Kerr transfer tables resident on the device (format 2: every node on the same physical radii)
+#define RG_TAB_ROUT 1000.0 // outermost table row (the reference leaves kyconv at log r > 3, relagn.py:992)
+#define RG_ROW_C 1.0       // rows uniform in x(r) = 1/r + RG_ROW_C / sqrt(r)
 struct TabDesc {
-    const float *data;     // [n_spin][n_inc][2][NR][NPHI] (the layout of the C ABI)
-    const double2 *pairs;  // [n_spin][n_inc][NR][NPHI] of (g, jn): what the kernels read
+    const float *data;     // [n_spin][n_inc][2][NR][NPHI]: g, Jn (the layout of the C ABI)
+    const float2 *pairs;   // [n_spin][n_inc][NR][NPHI] of (ln g, Jn): what the kernels read
     const double *spins;   // [n_spin] ascending
-    const double *riscos;  // [n_spin]
     const double *thetas;  // [n_inc] ascending, radians
+    const int *first_row;  // [n_spin]: first row with data (rows inside 1.02 x photon orbit are empty)
     int n_spin, n_inc, NR, NPHI;
-    double dl;
-    double lng_min, lng_max; // range of ln g over all nodes (sizes the shift histogram)
-    const double *rowrange;  // [n_spin*n_inc][NR][2]: min / max of ln g over the columns of each table row
+    double r_in;           // radius of row 0
+    double x0, dx;         // row position of radius r: (x(r) - x0) / dx
+    double lng_min, lng_max; // range of ln g over the usable rows of all nodes (sizes the shift histogram)
 };
 
 // energy grid resident on the device (all [nE] unless noted; built by rg_set_grid)
@@ -92,7 +94,7 @@ int rg_launch_edges(const SetRec *recs, int P, double2 *edges, cudaStream_t st);
 
 // generic kyconv seam: histogram of one (possibly wide) annulus into d_H[0..nH) (shift k = K_LO + index)
 int rg_launch_ky_hist(const TabDesc &tab, double a, double theta_o, double r1, double r2, double alpha, double beta,
-                      double rb, double zshift, double dlnE, int nsub, double *d_H, int K_LO, int nH,
+                      double rb, double zshift, double dlnE, int nsub, double *d_H, int K_LO, int nH, int *d_status,
                       cudaStream_t st);
 // out[j] = sum_i H[i] in[j - (kmin + i)]
 int rg_launch_ky_conv(const double *d_H, int kmin, int nk, const double *d_in, double *d_out, int nE,
@@ -100,7 +102,11 @@ int rg_launch_ky_conv(const double *d_H, int kmin, int nk, const double *d_in, d
 
 // table generation (device ray tracer): fills d_data [n_spin][n_inc][2][NR][NPHI]
 int rg_launch_raytrace(const double *h_spins, int n_spin, const double *h_thetas, int n_inc, int NR, int NPHI,
-                       double dl, float *d_data, long *n_unresolved, cudaStream_t st);
+                       double r_in, float *d_data, long *n_unresolved, cudaStream_t st);
+// host-side geometry of the table format (shared by the ray tracer, the loader and the kernels' row lookup)
+double rg_row_x(double r);
+double rg_row_radius(double r_in, int NR, int s);
+double rg_r_valid(double a);
 
 // layout of the resident 10^(0.02 j) table (rg_ctx::d_p10): four runs of RG_NTH + 4 doubles
 #define RG_P10_RDP (3 * (RG_NTH + 4))       // 1 / (10^(0.02 (j+1)) - 10^(0.02 j)): reciprocal cell widths (interpolation kernel)

@@ -1,34 +1,54 @@
 // rg_kyconv.cu -- the stand-alone convolution seam (B1):
 //   xspec.callModelFunction('kyconv', energies, params[12], flux)
 //   (src/python_version/relagn.py:979-1001; tests/blurr_test.py:51-54,111-119)
-// One annulus of arbitrary width and emissivity (alpha, beta, r_break): one CTA of 8 warps builds the shift
-// histogram -- ring m goes to warp m mod 8, every warp deposits into its own shared-memory copy with the
-// warp-shuffle segmented reduction of rg_transfer.cuh (no atomics), the copies are folded in warp order -- then a
-// second kernel applies it to the photon spectrum.  The same device functions build every annulus inside the fused
-// spectrum kernel.
+// One annulus of arbitrary width and emissivity (alpha, beta, r_break): one CTA of 8 warps builds the table slice of
+// (spin, inclination) in shared memory, then the shift histogram -- ring m goes to warp m mod 8, every warp gathers
+// into its own shared-memory copy (rg_transfer.cuh: no atomics), the copies are folded in warp order -- and a
+// second kernel applies it to the photon spectrum.  The same device functions build every annulus in hist_kernel.
 #include "rg_kernels.h"
 #include "rg_transfer.cuh"
 
 #define KT 256
 #define KW (KT / 32)
 
+static __host__ __device__ inline int ky_round_up2(int x) { return (x + 1) & ~1; }
+
 __global__ void __launch_bounds__(KT)
 ky_hist_kernel(TabDesc tab, double a, double theta_o, double r1, double r2, double alpha, double beta, double rb,
-               double zs, double dlnE, int nsub, double *__restrict__ H_out, int K_LO, int nH)
+               double zs, double dlnE, int nsub, double *__restrict__ H_out, int K_LO, int nH, int *__restrict__ status)
 {
     RG_DYN_SMEM(smem_raw);
-    double *H = reinterpret_cast<double *>(smem_raw); // [KW][nH]
+    const int NP = tab.NPHI;
+    double2 *slice = reinterpret_cast<double2 *>(smem_raw);                     // [NR][NPHI]
+    double *H = reinterpret_cast<double *>(slice + (size_t)tab.NR * NP);        // [KW][nH2]
+    const int nH2 = ky_round_up2(nH);
     const int tid = threadIdx.x, warp = tid >> 5;
-    for (int i = tid; i < KW * nH; i += KT) H[i] = 0.0;
-    TabSel ts;
-    rg_tab_select(ts, tab, a, theta_o);
+    double *scr_base = H + (size_t)KW * nH2 + (size_t)warp * ky_round_up2(RG_RING_SCR_DOUBLES(NP));
+    for (int i = tid; i < KW * nH2; i += KT) H[i] = 0.0;
+    __shared__ TabSel s_ts;
+    __shared__ int s_hi;
+    if (tid == 0) {
+        rg_tab_select(s_ts, tab, a, theta_o);
+        const double rtop = r2 < RG_TAB_ROUT ? r2 : RG_TAB_ROUT;
+        int hi = (int)floor(rg_row_pos(tab.x0, tab.dx, tab.NR, rtop)) + 1;
+        if (hi > tab.NR - 1) hi = tab.NR - 1;
+        if (hi < s_ts.s_lo + 1) hi = s_ts.s_lo + 1;
+        s_hi = hi;
+        *status = s_ts.status;
+    }
     __syncthreads();
-    int kmn, kmx;
-    warp_build_rings(H + (size_t)warp * nH, K_LO, nH, ts, r1, r2, dlnE, nsub, warp, KW, alpha, beta, rb, zs, 1.0, kmn, kmx);
+    const TabSel &ts = s_ts;
+    if (ts.status == 0) {
+        rg_build_slice(ts, s_hi, slice, tid, KT);
+        __syncthreads();
+        int kmn, kmx;
+        warp_build_rings(H + (size_t)warp * nH2, K_LO, nH, ts, slice, rg_ring_scr(scr_base, NP), r1, r2, 1.0 / dlnE, nsub,
+                         warp, KW, alpha, beta, rb, zs, 1.0, kmn, kmx);
+    }
     __syncthreads();
     for (int i = tid; i < nH; i += KT) {
         double v = 0.0;
-        for (int w = 0; w < KW; w++) v += H[(size_t)w * nH + i];
+        for (int w = 0; w < KW; w++) v += H[(size_t)w * nH2 + i];
         H_out[i] = v;
     }
 }
@@ -48,18 +68,19 @@ ky_conv_kernel(const double *__restrict__ H, int kmin, int nk, const double *__r
 }
 
 int rg_launch_ky_hist(const TabDesc &tab, double a, double theta_o, double r1, double r2, double alpha, double beta,
-                      double rb, double zshift, double dlnE, int nsub, double *d_H, int K_LO, int nH,
+                      double rb, double zshift, double dlnE, int nsub, double *d_H, int K_LO, int nH, int *d_status,
                       cudaStream_t st)
 {
     if (KT % tab.NPHI != 0 || tab.NPHI < 32) return rg_set_error(RG_E_ARG, "NPHI must divide %d and be >= 32", KT);
-    size_t smem = (size_t)KW * nH * sizeof(double);
+    size_t smem = (size_t)tab.NR * tab.NPHI * sizeof(double2) + (size_t)KW * ky_round_up2(nH) * sizeof(double) +
+                  (size_t)KW * ky_round_up2(RG_RING_SCR_DOUBLES(tab.NPHI)) * sizeof(double);
     if (smem > 220 * 1024) return rg_set_error(RG_E_GRID, "energy grid too fine for the kyconv histogram");
     double zs = 0.0;
     if (zshift != 0) zs = -log(1 + zshift) / dlnE;
     if (nsub <= 0) nsub = rg_auto_nsub(r1, r2, log(r2 / r1), dlnE);
     RG_CUDA_OK(cudaFuncSetAttribute(ky_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     RG_LAUNCH(ky_hist_kernel, dim3(1), dim3(KT), smem, st, tab, a, theta_o, r1, r2, alpha, beta, rb, zs, dlnE, nsub,
-              d_H, K_LO, nH);
+              d_H, K_LO, nH, d_status);
     RG_CUDA_OK(cudaGetLastError());
     return RG_OK;
 }

@@ -5,7 +5,9 @@
 // the lensing/area factor of a Keplerian equatorial disc seen by a distant
 // observer at inclination theta_o around a Kerr hole of spin a.
 //
-// Per table node (a, theta_o):  rows r_s = r_h + (risco - r_h) 10^(s dl),
+// Per table node (a, theta_o):  rows = the same physical radii for every node,
+// uniform in x(r) = 1/r + 1/sqrt(r) from r_in to 1000 (rows inside 1.02 x the
+// photon orbit of the node's spin hold no circular orbit and stay empty),
 // columns phi_t = 2 pi t / NPHI + phi0(r_s) where phi0 is the disc azimuth hit
 // by the ray alpha = 0, beta < 0 (removes the frame-dragging winding between
 // rows).  For every (s, t) the image-plane point (alpha, beta) whose null
@@ -16,10 +18,14 @@
 //
 // Parallelisation: one thread per node for the phi0 chain (rows are chained by
 // continuation of the root bracket), then one thread per (node, column) that
-// walks the rows outside-in with continuation of the Newton start.  The work
+// walks the rows outside-in with continuation of the Newton start, then repair
+// sweeps: points the radial continuation lost (the far side of the innermost
+// rows at high inclination, where the image is stretched along the shadow edge)
+// are retried along the ring from their solved neighbours, one thread per point.  The work
 // is a few seconds once per table set; the result is cached on disk by
 // relagn_b200/tables.py.
 #include "rg_kernels.h"
+#include <vector>
 
 #define NV 9
 
@@ -250,10 +256,31 @@ __device__ static int march_to(double a, double th, double phi, double r_from, d
     return 1;
 }
 
-__device__ static double row_radius(double a, double risco, int s, double dl)
+// continuation along the ring: from the solved point (r, phi_from; A, B) to (r, phi_to), halving the azimuth step on
+// failure (explicit stack instead of recursion; depth limit 8) -- kerr_oracle.c: march_phi
+__device__ static int march_phi(double a, double th, double r, double phi_from, double phi_to, double *A, double *B,
+                                double *g, double *jn)
 {
-    double rh = 1 + sqrt(1 - a * a);
-    return rh + (risco - rh) * pow(10.0, s * dl);
+    double tgt[20];
+    int dep[20];
+    int sp = 0;
+    tgt[0] = phi_to; dep[0] = 0; sp = 1;
+    double cur = phi_from, Ac = *A, Bc = *B;
+    while (sp > 0) {
+        sp--;
+        double t = tgt[sp];
+        int d = dep[sp];
+        double At = Ac, Bt = Bc, gg, jj;
+        if (solve_point(a, th, r, t, &At, &Bt, &gg, &jj)) {
+            cur = t; Ac = At; Bc = Bt; *g = gg; *jn = jj;
+            continue;
+        }
+        if (d >= 8 || sp + 2 > 20) return 0;
+        tgt[sp] = t; dep[sp] = d + 1; sp++;
+        tgt[sp] = 0.5 * (cur + t); dep[sp] = d + 1; sp++;
+    }
+    *A = Ac; *B = Bc;
+    return 1;
 }
 
 // the alpha = 0, beta < 0 ray that lands on radius r_e: beta by bracketing + guarded regula falsi / bisection
@@ -291,17 +318,19 @@ __device__ static int front_ray(double a, double th, double r_e, double *beta_f,
 
 // node n = m * n_inc + i
 __global__ void phi0_kernel(const double *__restrict__ spins, const double *__restrict__ thetas, int n_spin, int n_inc,
-                            int NR, double dl, double *__restrict__ phi0, int *__restrict__ nbad)
+                            int NR, const double *__restrict__ rows, const double *__restrict__ rvalid,
+                            double *__restrict__ phi0, int *__restrict__ nbad)
 {
     int node = blockIdx.x * blockDim.x + threadIdx.x;
     if (node >= n_spin * n_inc) return;
     double a = spins[node / n_inc], th = thetas[node % n_inc];
-    double risco = rg_risco(a);
+    const double rv = rvalid[node / n_inc];
     double bf = 0;
     int bad = 0;
     double *out = phi0 + (size_t)node * NR;
     for (int s = NR - 1; s >= 0; s--) {
-        double r = row_radius(a, risco, s, dl);
+        double r = rows[s];
+        if (!(r > rv)) { out[s] = s + 1 < NR ? out[s + 1] : 0; continue; }
         if (s == NR - 1) bf = -r * cos(th);
         double p = 0;
         if (!front_ray(a, th, r, &bf, &p)) { bad++; p = s + 1 < NR ? out[s + 1] : 0; }
@@ -312,25 +341,33 @@ __global__ void phi0_kernel(const double *__restrict__ spins, const double *__re
 
 __global__ void __launch_bounds__(32)
 node_kernel(const double *__restrict__ spins, const double *__restrict__ thetas, int n_spin, int n_inc, int NR, int NPHI,
-            double dl, const double *__restrict__ phi0_all, float *__restrict__ data, int *__restrict__ nbad)
+            const double *__restrict__ rows, const double *__restrict__ rvalid, const double *__restrict__ phi0_all,
+            float *__restrict__ data, double2 *__restrict__ sol)
 {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_spin * n_inc * NPHI) return;
     int node = idx / NPHI, t = idx - node * NPHI;
     double a = spins[node / n_inc], theta_o = thetas[node % n_inc];
-    double risco = rg_risco(a);
+    const double rv = rvalid[node / n_inc];
     double co = cos(theta_o);
     const double *phi0 = phi0_all + (size_t)node * NR;
     size_t plane = (size_t)NR * NPHI;
     float *g = data + (size_t)node * 2 * plane, *jn = g + plane;
-    int nfail = 0;
+    double2 *so = sol + (size_t)node * plane;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     double A1 = 0, B1 = 0, A2 = 0, B2 = 0, r1 = 0;
     int have = 0;
     for (int s = NR - 1; s >= 0; s--) {
-        double r = row_radius(a, risco, s, dl);
+        double r = rows[s];
         double phi = 2 * RGK_PI * t / NPHI + phi0[s];
         double A, B, gg = 1, jj = co;
         int ok = 0;
+        so[(size_t)s * NPHI + t] = make_double2(qnan, qnan);
+        if (!(r > rv)) { // no circular orbit (r <= photon orbit): the row carries no data
+            g[(size_t)s * NPHI + t] = 0.0f;
+            jn[(size_t)s * NPHI + t] = 0.0f;
+            continue;
+        }
         if (have >= 2) { A = 2 * A1 - A2; B = 2 * B1 - B2; ok = solve_point(a, theta_o, r, phi, &A, &B, &gg, &jj); }
         if (!ok && have >= 1) {
             A = A1; B = B1;
@@ -341,9 +378,7 @@ node_kernel(const double *__restrict__ spins, const double *__restrict__ thetas,
             ok = solve_point(a, theta_o, r, phi, &A, &B, &gg, &jj);
         }
         if (!ok) {
-            // unresolved (the direct image folds into the photon ring at the shadow edge: a ~ 0.998, i > ~80 deg,
-            // r < ~2): the point carries no weight
-            nfail++;
+            // lost by the radial continuation: left to the repair sweeps; carries no weight if they fail too
             if (s + 1 < NR) gg = g[(size_t)(s + 1) * NPHI + t];
             g[(size_t)s * NPHI + t] = (float)gg;
             jn[(size_t)s * NPHI + t] = 0.0f;
@@ -351,36 +386,120 @@ node_kernel(const double *__restrict__ spins, const double *__restrict__ thetas,
         }
         g[(size_t)s * NPHI + t] = (float)gg;
         jn[(size_t)s * NPHI + t] = (float)jj;
+        so[(size_t)s * NPHI + t] = make_double2(A, B);
         if (have >= 1) { A2 = A1; B2 = B1; }
         A1 = A; B1 = B; r1 = r;
         have = have < 2 ? have + 1 : 2;
     }
-    if (nfail) atomicAdd(nbad, nfail);
+}
+
+// one repair sweep: every unresolved point with data (thread = point) is retried from its solved ring neighbours
+// t - 1, then t + 1 (kerr_oracle.c: repair_body).  The solutions found are published by publish_kernel after the
+// sweep, so the result does not depend on the order the points are visited in.
+__global__ void __launch_bounds__(32)
+repair_kernel(const double *__restrict__ spins, const double *__restrict__ thetas, int n_spin, int n_inc, int NR, int NPHI,
+              const double *__restrict__ rows, const double *__restrict__ rvalid, const double *__restrict__ phi0_all,
+              float *__restrict__ data, const double2 *__restrict__ sol, double2 *__restrict__ pending,
+              int *__restrict__ counters)
+{
+    size_t plane = (size_t)NR * NPHI;
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)n_spin * n_inc * plane) return;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    pending[idx] = make_double2(qnan, qnan);
+    int node = (int)(idx / plane);
+    int s = (int)((idx - (size_t)node * plane) / NPHI), t = (int)(idx - (size_t)node * plane - (size_t)s * NPHI);
+    const double r = rows[s];
+    if (!(r > rvalid[node / n_inc])) return;
+    const double2 *so = sol + (size_t)node * plane;
+    if (so[(size_t)s * NPHI + t].x == so[(size_t)s * NPHI + t].x) return; // solved
+    atomicAdd(counters, 1); // unresolved before this sweep
+    double a = spins[node / n_inc], theta_o = thetas[node % n_inc];
+    const double phi = 2 * RGK_PI * t / NPHI + phi0_all[(size_t)node * NR + s];
+    float *g = data + (size_t)node * 2 * plane, *jn = g + plane;
+    for (int side = 0; side < 2; side++) {
+        const int tn = (t + (side ? 1 : NPHI - 1)) % NPHI;
+        double A = so[(size_t)s * NPHI + tn].x, B = so[(size_t)s * NPHI + tn].y;
+        if (A != A) continue;
+        const double phin = phi + (side ? 1 : -1) * 2 * RGK_PI / NPHI;
+        double gg, jj;
+        if (march_phi(a, theta_o, r, phin, phi, &A, &B, &gg, &jj)) {
+            g[(size_t)s * NPHI + t] = (float)gg;
+            jn[(size_t)s * NPHI + t] = (float)jj;
+            pending[idx] = make_double2(A, B);
+            atomicAdd(counters + 1, 1); // repaired in this sweep
+            return;
+        }
+    }
+}
+
+__global__ void publish_kernel(double2 *__restrict__ sol, const double2 *__restrict__ pending, size_t n)
+{
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < n && pending[idx].x == pending[idx].x) sol[idx] = pending[idx];
+}
+
+// geometry of the table format on the host (the same expressions as oracle/kerr_oracle.c, host libm)
+double rg_row_x(double r) { return 1.0 / r + RG_ROW_C / sqrt(r); }
+double rg_row_radius(double r_in, int NR, int s)
+{
+    double x0 = rg_row_x(r_in), x1 = rg_row_x(RG_TAB_ROUT);
+    double x = x0 + s * ((x1 - x0) / (NR - 1));
+    if (s == 0) return r_in;
+    if (s == NR - 1) return RG_TAB_ROUT;
+    double u = 0.5 * (-RG_ROW_C + sqrt(RG_ROW_C * RG_ROW_C + 4 * x));
+    return 1.0 / (u * u);
+}
+double rg_r_valid(double a)
+{
+    double rph = 2 * (1 + cos(2.0 / 3.0 * acos(-a)));
+    return 1.02 * rph;
 }
 
 int rg_launch_raytrace(const double *h_spins, int n_spin, const double *h_thetas, int n_inc, int NR, int NPHI,
-                       double dl, float *d_data, long *n_unresolved, cudaStream_t st)
+                       double r_in, float *d_data, long *n_unresolved, cudaStream_t st)
 {
     int nodes = n_spin * n_inc;
+    size_t plane = (size_t)NR * NPHI, npts = (size_t)nodes * plane;
     double *d_meta = nullptr, *d_phi0 = nullptr;
-    int *d_bad = nullptr;
-    RG_CUDA_OK(cudaMalloc(&d_meta, (size_t)(n_spin + n_inc) * sizeof(double)));
+    double2 *d_sol = nullptr, *d_pend = nullptr;
+    int *d_cnt = nullptr;
+    std::vector<double> meta(2 * n_spin + n_inc + NR);
+    for (int i = 0; i < n_spin; i++) { meta[i] = h_spins[i]; meta[n_spin + n_inc + i] = rg_r_valid(h_spins[i]); }
+    for (int i = 0; i < n_inc; i++) meta[n_spin + i] = h_thetas[i];
+    for (int s = 0; s < NR; s++) meta[2 * n_spin + n_inc + s] = rg_row_radius(r_in, NR, s);
+    RG_CUDA_OK(cudaMalloc(&d_meta, meta.size() * sizeof(double)));
     RG_CUDA_OK(cudaMalloc(&d_phi0, (size_t)nodes * NR * sizeof(double)));
-    RG_CUDA_OK(cudaMalloc(&d_bad, sizeof(int)));
-    RG_CUDA_OK(cudaMemcpyAsync(d_meta, h_spins, n_spin * sizeof(double), cudaMemcpyHostToDevice, st));
-    RG_CUDA_OK(cudaMemcpyAsync(d_meta + n_spin, h_thetas, n_inc * sizeof(double), cudaMemcpyHostToDevice, st));
-    RG_CUDA_OK(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+    RG_CUDA_OK(cudaMalloc(&d_sol, npts * sizeof(double2)));
+    RG_CUDA_OK(cudaMalloc(&d_pend, npts * sizeof(double2)));
+    RG_CUDA_OK(cudaMalloc(&d_cnt, 3 * sizeof(int)));
+    RG_CUDA_OK(cudaMemcpyAsync(d_meta, meta.data(), meta.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    RG_CUDA_OK(cudaMemsetAsync(d_cnt, 0, 3 * sizeof(int), st));
+    const double *d_spins = d_meta, *d_thetas = d_meta + n_spin, *d_rvalid = d_meta + n_spin + n_inc,
+                 *d_rows = d_meta + 2 * n_spin + n_inc;
     // one thread per node, spread over the SMs (the row chain is serial)
-    RG_LAUNCH(phi0_kernel, dim3(nodes), dim3(1), 0, st, d_meta, d_meta + n_spin, n_spin, n_inc, NR, dl, d_phi0, d_bad);
+    RG_LAUNCH(phi0_kernel, dim3(nodes), dim3(1), 0, st, d_spins, d_thetas, n_spin, n_inc, NR, d_rows, d_rvalid, d_phi0,
+              d_cnt + 2);
     RG_CUDA_OK(cudaGetLastError());
     int total = nodes * NPHI;
-    RG_LAUNCH(node_kernel, dim3((total + 31) / 32), dim3(32), 0, st, d_meta, d_meta + n_spin, n_spin, n_inc, NR, NPHI,
-              dl, d_phi0, d_data, d_bad);
+    RG_LAUNCH(node_kernel, dim3((total + 31) / 32), dim3(32), 0, st, d_spins, d_thetas, n_spin, n_inc, NR, NPHI, d_rows,
+              d_rvalid, d_phi0, d_data, d_sol);
     RG_CUDA_OK(cudaGetLastError());
-    int bad = 0;
-    RG_CUDA_OK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
-    RG_CUDA_OK(cudaStreamSynchronize(st));
-    if (n_unresolved) *n_unresolved = bad;
-    cudaFree(d_meta); cudaFree(d_phi0); cudaFree(d_bad);
+    int cnt[3] = {0, 0, 0};
+    long left = 0;
+    for (int sweep = 0; sweep < 6; sweep++) {
+        RG_CUDA_OK(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(int), st));
+        RG_LAUNCH(repair_kernel, dim3((unsigned)((npts + 31) / 32)), dim3(32), 0, st, d_spins, d_thetas, n_spin, n_inc, NR,
+                  NPHI, d_rows, d_rvalid, d_phi0, d_data, d_sol, d_pend, d_cnt);
+        RG_CUDA_OK(cudaGetLastError());
+        RG_LAUNCH(publish_kernel, dim3((unsigned)((npts + 255) / 256)), dim3(256), 0, st, d_sol, d_pend, npts);
+        RG_CUDA_OK(cudaGetLastError());
+        RG_CUDA_OK(cudaMemcpyAsync(cnt, d_cnt, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        RG_CUDA_OK(cudaStreamSynchronize(st));
+        left = (long)cnt[0] - cnt[1];
+        if (cnt[0] == 0 || cnt[1] == 0) break;
+    }
+    if (n_unresolved) *n_unresolved = left + cnt[2];
+    cudaFree(d_meta); cudaFree(d_phi0); cudaFree(d_sol); cudaFree(d_pend); cudaFree(d_cnt);
     return RG_OK;
 }

@@ -27,7 +27,7 @@
 // their histograms are summed (weighted by annulus luminosity) and ONE
 // convolution is done for the region.
 #include "rg_kernels.h"
-#include "rg_transfer.cuh"
+
 
 #define FULL 0xffffffffu
 #define IMAX 0x7fffffff

@@ -1,90 +1,116 @@
 // rg_transfer.cuh -- device code of the relativistic transfer (the KYCONV-style
-// seam, relagn.py:979-1001): table lookup for one (spin, inclination), ring
-// evaluation and the g-shift histogram deposit.  Shared by the fused spectrum
-// kernel and the stand-alone kyconv entry point.
+// seam, relagn.py:979-1001): the table slice of one (spin, inclination), ring
+// evaluation and the g-shift histogram.  Shared by hist_kernel (every annulus of
+// every parameter set) and the stand-alone kyconv entry point.
 //
 // Discretisation (identical to oracle/kerr_oracle.c):
-//   - an annulus [r1,r2] is cut into n_sub rings at log-midpoints r_m with exact
-//     area weights A_m = (r_b^2 - r_a^2)/2;
-//   - on ring m column t (disc azimuth) the tables give g and Jn = dalpha dbeta /
-//     (dX dY); they are blended linearly between the 4 surrounding (spin,
-//     inclination) nodes and the 2 surrounding table rows;
-//   - s_t = ln g_t / dlnE is the energy shift in bins, w_t = Jn_t g_t^3 the weight
-//     density; the segment t..t+1 carries W = (w_t + w_{t+1})/2 dphi A_m spread
-//     uniformly in s over [s_t, s_{t+1}] and is deposited on integer shifts with a
-//     linear (hat) kernel.
+//   - the tables hold, per (spin, inclination) node, g and Jn = dalpha dbeta / (dX dY) on rows of the SAME physical
+//     radii for every node (uniform in x = 1/r + 1/sqrt(r)) and columns phi_t = 2 pi t / NPHI + phi0(r);
+//   - the model's slice is a Lagrange blend over up to 4 spin nodes (coordinate a) x up to 4 inclination nodes
+//     (coordinate theta) of ln g and Jn -- built ONCE per parameter set into shared memory as (ln g, w = Jn g^3);
+//   - an annulus [r1,r2] is cut into n_sub rings at log-midpoints r_m with exact area weights A_m = (r_b^2 - r_a^2)/2;
+//     ring m interpolates the slice linearly between its two rows: s_t = ln g_t / dlnE (shift in bins), w_t;
+//   - the segment t..t+1 carries W = (w_t + w_{t+1})/2 dphi A_m spread uniformly in s over [s_t, s_{t+1}] and is
+//     deposited on integer shifts with a linear (hat) kernel.
 #pragma once
 #include "rg_kernels.h"
 
+#define RG_FULL 0xffffffffu
+#define RG_IMAX 0x7fffffff
+#define RG_MAX_STENCIL 16
+
+// the nodes and weights of one (spin, inclination): lives in shared memory, built by one thread
 struct TabSel {
-    const double2 *n00, *n01, *n10, *n11; // node planes [NR][NPHI] of (g, jn) pairs
-    double w00, w01, w10, w11;
-    double risco, rh;  // of the model's own spin
-    size_t plane;
+    const float2 *plane[RG_MAX_STENCIL]; // node planes [NR][NPHI] of (ln g, Jn)
+    double w[RG_MAX_STENCIL];
+    int n;      // nodes in the stencil
+    int s_lo;   // first row of the slice (the row bracketing risco(a) from below)
+    int status; // 0 ok, 1: the node grid has no valid spin stencil here
     int NR, NPHI;
-    double inv_dl;
-    double dphi; // 2 pi / NPHI
+    double x0, dx; // row position (x(r) - x0) / dx
+    double dphi;   // 2 pi / NPHI
 };
+
+__device__ inline void rg_lagrange_w(const double *xs, int n, double x, double *w)
+{
+    for (int i = 0; i < n; i++) {
+        double p = 1.0;
+        for (int k = 0; k < n; k++)
+            if (k != i) p *= (x - xs[k]) / (xs[i] - xs[k]);
+        w[i] = p;
+    }
+}
+
+// nodes [i0, i0 + k) around x, k <= 4 (kerr_oracle.c: stencil4)
+__device__ inline void rg_stencil4(const double *nodes, int n, double x, int &i0, int &k)
+{
+    int i = 0;
+    while (i + 2 < n && x >= nodes[i + 1]) i++;
+    int lo = i - 1, hi = i + 2;
+    if (lo < 0) lo = 0;
+    if (hi > n - 1) hi = n - 1;
+    i0 = lo; k = hi - lo + 1;
+}
+
+__device__ inline double rg_row_pos(double x0, double dx, int NR, double r)
+{
+    double ell = ((1.0 / r + RG_ROW_C / sqrt(r)) - x0) / dx;
+    if (!(ell > 0)) ell = 0;
+    if (ell > NR - 1) ell = NR - 1;
+    return ell;
+}
 
 __device__ inline void rg_tab_select(TabSel &ts, const TabDesc &t, double a, double theta_o)
 {
-    int m0 = 0;
-    while (m0 + 2 < t.n_spin && a >= t.spins[m0 + 1]) m0++;
-    int m1 = m0 + 1 < t.n_spin ? m0 + 1 : m0;
-    double risco = rg_risco(a);
-    double fa = 0;
-    if (m1 != m0) {
-        fa = (t.riscos[m0] - risco) / (t.riscos[m0] - t.riscos[m1]);
-        fa = fa < 0 ? 0 : (fa > 1 ? 1 : fa);
-    }
-    int n0 = 0;
-    while (n0 + 2 < t.n_inc && theta_o >= t.thetas[n0 + 1]) n0++;
-    int n1 = n0 + 1 < t.n_inc ? n0 + 1 : n0;
-    double fi = 0;
-    if (n1 != n0) {
-        fi = (theta_o - t.thetas[n0]) / (t.thetas[n1] - t.thetas[n0]);
-        fi = fi < 0 ? 0 : (fi > 1 ? 1 : fi);
-    }
-    size_t plane = (size_t)t.NR * t.NPHI;
-    ts.n00 = t.pairs + ((size_t)m0 * t.n_inc + n0) * plane;
-    ts.n01 = t.pairs + ((size_t)m0 * t.n_inc + n1) * plane;
-    ts.n10 = t.pairs + ((size_t)m1 * t.n_inc + n0) * plane;
-    ts.n11 = t.pairs + ((size_t)m1 * t.n_inc + n1) * plane;
-    ts.w00 = (1 - fa) * (1 - fi); ts.w01 = (1 - fa) * fi; ts.w10 = fa * (1 - fi); ts.w11 = fa * fi;
-    ts.risco = risco; ts.rh = 1 + sqrt(1 - a * a);
-    ts.plane = plane; ts.NR = t.NR; ts.NPHI = t.NPHI; ts.inv_dl = 1.0 / t.dl;
+    const double ac = a < t.spins[0] ? t.spins[0] : (a > t.spins[t.n_spin - 1] ? t.spins[t.n_spin - 1] : a);
+    const double thc = theta_o < t.thetas[0] ? t.thetas[0]
+                                             : (theta_o > t.thetas[t.n_inc - 1] ? t.thetas[t.n_inc - 1] : theta_o);
+    int need = (int)floor(rg_row_pos(t.x0, t.dx, t.NR, rg_risco(a)));
+    if (need > t.NR - 2) need = t.NR - 2;
+    if (need < 0) need = 0;
+    int m0, km, n0, kn;
+    rg_stencil4(t.spins, t.n_spin, ac, m0, km);
+    while (km > 1 && t.first_row[m0] > need && ac >= t.spins[m0 + 1]) { m0++; km--; } // drop empty low-spin nodes
+    ts.status = 0;
+    for (int i = 0; i < km; i++)
+        if (t.first_row[m0 + i] > need) ts.status = 1;
+    rg_stencil4(t.thetas, t.n_inc, thc, n0, kn);
+    double wa[4], wi[4];
+    rg_lagrange_w(t.spins + m0, km, ac, wa);
+    rg_lagrange_w(t.thetas + n0, kn, thc, wi);
+    const size_t plane = (size_t)t.NR * t.NPHI;
+    int n = 0;
+    for (int im = 0; im < km; im++)
+        for (int in = 0; in < kn; in++) {
+            ts.plane[n] = t.pairs + ((size_t)(m0 + im) * t.n_inc + (n0 + in)) * plane;
+            ts.w[n] = wa[im] * wi[in];
+            n++;
+        }
+    ts.n = n;
+    ts.s_lo = need;
+    ts.NR = t.NR; ts.NPHI = t.NPHI; ts.x0 = t.x0; ts.dx = t.dx;
     ts.dphi = 2 * RGK_PI / t.NPHI;
 }
 
-struct RingRow { int s0, s1; double fr; };
-
-__device__ inline RingRow rg_ring_row(const TabSel &ts, double rm)
+// The model's slice, rows [ts.s_lo, s_hi], as (ln g, w = max(Jn, 0) g^3) pairs in shared memory: slice[(s - s_lo) NPHI + p].
+// Called by all `nthreads` threads of the CTA (tid = its index); the caller synchronises afterwards.
+__device__ inline void rg_build_slice(const TabSel &ts, int s_hi, double2 *slice, int tid, int nthreads)
 {
-    RingRow rr;
-    double ell = log10((rm - ts.rh) / (ts.risco - ts.rh)) * ts.inv_dl;
-    if (!(rm > ts.rh)) ell = 0;
-    if (ell < 0) ell = 0;
-    if (ell > ts.NR - 1) ell = ts.NR - 1;
-    int s0 = (int)floor(ell);
-    if (s0 > ts.NR - 2) s0 = ts.NR - 2;
-    if (s0 < 0) s0 = 0;
-    rr.s0 = s0; rr.s1 = s0 + 1 < ts.NR ? s0 + 1 : s0; rr.fr = ell - s0;
-    return rr;
-}
-
-// g and Jn at column p of the ring (blend of 4 nodes x 2 rows)
-__device__ inline void rg_ring_sample(const TabSel &ts, int s0, int s1, double fr, int p, double &g, double &jn)
-{
-    // one 16-byte load per node and row brings g and Jn together (the tables are float32 widened once at upload)
-    const int i0 = s0 * ts.NPHI + p, i1 = s1 * ts.NPHI + p;
-    const double2 a0 = __ldg(ts.n00 + i0), b0 = __ldg(ts.n01 + i0), c0 = __ldg(ts.n10 + i0), d0 = __ldg(ts.n11 + i0);
-    const double2 a1 = __ldg(ts.n00 + i1), b1 = __ldg(ts.n01 + i1), c1 = __ldg(ts.n10 + i1), d1 = __ldg(ts.n11 + i1);
-    double g0 = ts.w00 * a0.x + ts.w01 * b0.x + ts.w10 * c0.x + ts.w11 * d0.x;
-    double g1 = ts.w00 * a1.x + ts.w01 * b1.x + ts.w10 * c1.x + ts.w11 * d1.x;
-    double j0 = ts.w00 * a0.y + ts.w01 * b0.y + ts.w10 * c0.y + ts.w11 * d0.y;
-    double j1 = ts.w00 * a1.y + ts.w01 * b1.y + ts.w10 * c1.y + ts.w11 * d1.y;
-    g = g0 + fr * (g1 - g0);
-    jn = j0 + fr * (j1 - j0);
+    const int NP = ts.NPHI;
+    const int first = ts.s_lo * NP, count = (s_hi - ts.s_lo + 1) * NP;
+    const int n = ts.n;
+    for (int i = tid; i < count; i += nthreads) {
+        double lg = 0.0, jn = 0.0;
+#pragma unroll 4
+        for (int k = 0; k < n; k++) {
+            const float2 v = __ldg(ts.plane[k] + first + i);
+            const double w = ts.w[k];
+            lg += w * (double)v.x;
+            jn += w * (double)v.y;
+        }
+        if (!(jn > 0)) jn = 0.0; // a Lagrange overshoot below zero carries no weight
+        slice[i] = make_double2(lg, jn * exp(3.0 * lg));
+    }
 }
 
 // Number of rings an annulus [r1, r2] is cut into: the radial variation of the shift across one ring stays below
@@ -107,7 +133,7 @@ __host__ __device__ inline int rg_auto_nsub(double r1, double r2, double lnr, do
 }
 
 // geometry of ring m of an annulus [r1, r2] cut into nsub rings (kerr_oracle.c: ro_ky_kernel)
-struct RingGeo { double A, fr; int s0, s1; };
+struct RingGeo { double A, fr; int s0; };
 
 __device__ inline RingGeo rg_ring_geo(const TabSel &ts, double r1, double r2, double lnr, int m, int nsub,
                                       double alpha, double beta, double rb)
@@ -115,46 +141,31 @@ __device__ inline RingGeo rg_ring_geo(const TabSel &ts, double r1, double r2, do
     // ring edges r1 (r2/r1)^(m/nsub); the outermost edges are r1 and r2 themselves (most annuli are a single ring)
     const double ra = m == 0 ? r1 : r1 * exp(lnr * m / nsub);
     const double rbb = m == nsub - 1 ? r2 : r1 * exp(lnr * (m + 1) / nsub);
-    double rm = sqrt(ra * rbb);
+    const double rm = sqrt(ra * rbb);
     double emis = 1.0;
     if (alpha != 0 || beta != 0) emis = rm < rb ? pow(rm, -alpha) : pow(rm, -beta) * pow(rb, beta - alpha);
     RingGeo g;
     g.A = 0.5 * (rbb * rbb - ra * ra) * emis;
-    RingRow rr = rg_ring_row(ts, rm);
-    g.s0 = rr.s0; g.s1 = rr.s1; g.fr = rr.fr;
+    const double ell = rg_row_pos(ts.x0, ts.dx, ts.NR, rm);
+    int s0 = (int)floor(ell);
+    if (s0 > ts.NR - 2) s0 = ts.NR - 2;
+    if (s0 < ts.s_lo) s0 = ts.s_lo; // (annuli start at risco: only a caller's r_in below the slice gets here)
+    double fr = ell - s0;
+    if (fr < 0) fr = 0;
+    g.s0 = s0; g.fr = fr;
     return g;
 }
 
-// ln g of a table sample: rg_log_pos (bit-identical to log(), fewer issue slots); RG_HIST_OWN_LOG=0 for A/B
-#ifndef RG_HIST_OWN_LOG
-#define RG_HIST_OWN_LOG 1
-#endif
-#if RG_HIST_OWN_LOG
-#define RG_LOG_G(g) rg_log_pos(g)
-#else
-#define RG_LOG_G(g) log(g)
-#endif
-#define RG_FULL 0xffffffffu
-#define RG_IMAX 0x7fffffff
-
 // ---------------------------------------------------------------------------
-// Deterministic warp-cooperative deposit of one segment per lane into Hs[k - K_LO]
-// (Hs is owned by this warp).  The weight W of segment [sa, sb] (in units of
-// shift bins) is spread uniformly and binned with the linear (hat) kernel onto
-// bins kfirst + c.  The part of the segment inside the unit interval
-// [k, k+1] carries weight wl = W (overlap / length) centred at offset mid in
-// [0, 1]; the hat hands wl mid to bin k+1 and wl - wl mid to bin k -- so one
-// interval evaluation feeds two bins (a degenerate segment is the same formula
-// with wl = W on its own interval).  Neighbouring lanes mostly start in the
-// same bin, so lanes are grouped into runs of equal kfirst (one ballot); for
-// every bin offset c the run is summed by a segmented inclusive scan (shuffles,
-// as many steps as the longest run needs) and written once by the run's last
-// lane.  Runs that are not adjacent but share kfirst are written in successive
-// rounds in lane order, so no two lanes ever update one bin at once and the
-// summation order is fixed.
+// Generic deposit (any ordering of the segments): one segment per lane into Hs[k - K_LO] (Hs is owned by this
+// warp).  The weight W of segment [sa, sb] (in units of shift bins) is spread uniformly and binned with the linear
+// (hat) kernel.  Lanes are grouped into runs of equal first bin (one ballot); for every bin offset the run is summed
+// by a segmented inclusive scan (shuffles) and written once by the run's last lane; runs that are not adjacent but
+// share the first bin are written in successive rounds in lane order, so no two lanes ever update one bin at once
+// and the summation order is fixed.  Used for the rare rings whose shift is not a two-branch function of azimuth;
+// the usual ring goes through warp_ring_gather below.
 struct SegIv { double up, dn; }; // weight handed to bin k+1 / bin k by the part of the segment inside [k, k+1]
 
-// first interval [kf, kf+1], kf = floor(lo): the part starts at lo itself
 __device__ inline SegIv seg_first(bool point, double kf, double lo, double hi, double W, double inv)
 {
     const double b = hi < kf + 1.0 ? hi : kf + 1.0;
@@ -165,7 +176,6 @@ __device__ inline SegIv seg_first(bool point, double kf, double lo, double hi, d
     return r;
 }
 
-// a later interval [km, km+1]: the part starts at km (lo lies below it), its centre sits at half its length
 __device__ inline SegIv seg_next(double km, double hi, double inv)
 {
     const double b = hi < km + 1.0 ? hi : km + 1.0;
@@ -177,8 +187,6 @@ __device__ inline SegIv seg_next(double km, double hi, double inv)
     return r;
 }
 
-// one step of the segmented inclusive scan over the runs: lanes at least d behind their run head take the value d
-// lanes below (the 0/1 factor keeps the addition exact and the code branch-free)
 #define RG_SCAN_STEP(d)                                                              \
     {                                                                                \
         const double mk = (lane - (d) >= start) ? 1.0 : 0.0;                         \
@@ -187,8 +195,7 @@ __device__ inline SegIv seg_next(double km, double hi, double inv)
         if (nlive > 2) v2 = fma(__shfl_up_sync(RG_FULL, v2, (d)), mk, v2);           \
     }
 
-__device__ inline void warp_deposit(double *Hs, int K_LO, int nH, double sa, double sb, double W, int &kf_min,
-                                    int &kl_max)
+static __device__ __noinline__ void warp_deposit(double *Hs, int K_LO, int nH, double sa, double sb, double W)
 {
     const int lane = threadIdx.x & 31;
     double lo = sa < sb ? sa : sb, hi = sa < sb ? sb : sa;
@@ -198,19 +205,11 @@ __device__ inline void warp_deposit(double *Hs, int K_LO, int nH, double sa, dou
     const double kf = floor(lo);
     const int kfirst = (int)kf;
     const int nb = point ? 2 : (int)floor(hi) + 1 - kfirst + 1;
-    const double inv = point ? 0.0 : W * __drcp_rn(len); // len >= 1e-12: the plain reciprocal is safe
-    kf_min = kfirst < kf_min ? kfirst : kf_min;
-    {
-        int kl = kfirst + nb - 1;
-        kl_max = kl > kl_max ? kl : kl_max;
-    }
-    // run structure (the same for every bin offset)
+    const double inv = point ? 0.0 : W * __drcp_rn(len);
     const int kprev = __shfl_up_sync(RG_FULL, kfirst, 1);
     const unsigned heads = __ballot_sync(RG_FULL, lane == 0 || kfirst != kprev);
     const int start = 31 - __clz((int)(heads & (0xffffffffu >> (31 - lane))));
     const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
-    // first bins monotone along the lanes (the usual case: a ring's half is one monotone branch of g(phi)): equal
-    // first bins are neighbours, every bin has one run and one round does it -- no match needed
     int myround, nrounds;
     if (__all_sync(RG_FULL, lane == 0 || kfirst >= kprev) || __all_sync(RG_FULL, lane == 0 || kfirst <= kprev)) {
         myround = tail ? 0 : -1;
@@ -222,10 +221,10 @@ __device__ inline void warp_deposit(double *Hs, int K_LO, int nH, double sa, dou
     }
     const int nbmax = __reduce_max_sync(RG_FULL, nb);
     const int maxrun = __reduce_max_sync(RG_FULL, lane - start + 1);
-    double carry = 0.0; // weight the previous interval hands up to the first bin of this group
-    double km = kf;     // lower edge of the group's first interval
+    double carry = 0.0;
+    double km = kf;
     for (int c0 = 0; c0 < nbmax; c0 += 3) {
-        const int nlive = nbmax - c0 < 3 ? nbmax - c0 : 3; // bins of this group that any lane reaches (warp-uniform)
+        const int nlive = nbmax - c0 < 3 ? nbmax - c0 : 3;
         double v0, v1 = 0.0, v2 = 0.0;
         {
             const SegIv iv = c0 == 0 ? seg_first(point, kf, lo, hi, W, inv) : seg_next(km, hi, inv);
@@ -245,7 +244,7 @@ __device__ inline void warp_deposit(double *Hs, int K_LO, int nH, double sa, dou
             if (c < nlive) {
                 const double v = c == 0 ? v0 : (c == 1 ? v1 : v2);
                 const unsigned i = (unsigned)(ib + c);
-                const bool ok = i < (unsigned)nH; // 0 <= ib + c < nH
+                const bool ok = i < (unsigned)nH;
                 for (int rd = 0; rd < nrounds; rd++) {
                     if (myround == rd && ok) Hs[i] += v;
                     __syncwarp();
@@ -256,60 +255,190 @@ __device__ inline void warp_deposit(double *Hs, int K_LO, int nH, double sa, dou
 }
 #undef RG_SCAN_STEP
 
-// One warp adds weight x (shift histogram of rings m_begin, m_begin + m_step, ... of annulus [r1, r2] cut into nsub
-// rings) to Hs.  alpha, beta, rb: kyconv's broken power-law emissivity; zs: redshift in units of shift bins.
-__device__ inline void warp_build_rings(double *Hs, int K_LO, int nH, const TabSel &ts, double r1, double r2, double dlnE,
-                                        int nsub, int m_begin, int m_step, double alpha, double beta, double rb, double zs,
-                                        double weight, int &kmin_out, int &kmax_out, const RingGeo *single = nullptr,
-                                        double inv_dlnE_in = 0.0)
+// ---------------------------------------------------------------------------
+// Per-warp scratch of the ring routines: NP + 1 entries each.
+struct RingScr {
+    double *S;   // shift of every ring sample (bins), raw column order
+    double *Wv;  // weight density of every sample
+    double2 *P;  // exclusive prefix sums (sum W, sum W mid) over the segments in rotated order; entry NP = totals
+    double *Q;   // W / (2 len) per segment in rotated order (0 for a degenerate segment)
+};
+#define RG_RING_SCR_DOUBLES(NP) (5 * ((NP) + 1) + 1)
+
+__device__ inline RingScr rg_ring_scr(double *base, int NP)
 {
-    // single: geometry of the annulus' only ring when the caller has it already (nsub == 1, warp-uniform)
+    RingScr sc;
+    sc.S = base; sc.Wv = base + (NP + 1); sc.Q = base + 2 * (NP + 1);
+    sc.P = reinterpret_cast<double2 *>(base + 3 * (NP + 1) + ((NP + 1) & 1)); // 16-byte aligned when base is
+    return sc;
+}
+
+// index (lowest on ties) of the smallest / largest of the per-lane candidates (v, idx): three REDUX instead of a
+// five-step shuffle tree.  Doubles are compared through their order-preserving 64-bit integer image.
+__device__ inline int warp_arg_extreme(double v, int idx, bool want_max)
+{
+    long long b = __double_as_longlong(v);
+    unsigned long long key = (unsigned long long)(b < 0 ? ~b : (b | (long long)0x8000000000000000ull));
+    if (want_max) key = ~key;
+    const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+    const unsigned mhi = __reduce_min_sync(RG_FULL, hi);
+    const unsigned mlo = __reduce_min_sync(RG_FULL, hi == mhi ? lo : 0xffffffffu);
+    const bool cand = hi == mhi && lo == mlo;
+    return (int)__reduce_min_sync(RG_FULL, cand ? (unsigned)idx : 0x7fffffffu);
+}
+
+// Shift histogram of ONE ring whose samples (S[t], Wv[t], t < NP) sit in the warp's scratch: Hs[k - K_LO] += ...
+// The usual ring is a closed curve with one minimum and one maximum of the shift: two monotone branches.  Then the
+// hat deposit is a GATHER: with D(x) = int^x int^x' (weight density) -- per segment 0 below it, W (x - lo)^2 / (2 len)
+// inside, W (x - mid) above -- the histogram is the second difference H[k] = D(k+1) - 2 D(k) + D(k-1), and on a
+// monotone branch "the segments entirely below x" are a prefix: D(x) = x P0[i] - P1[i] + Q_i (x - lo_i)^2 with prefix
+// sums P0 = sum W, P1 = sum W mid over the branch and i the segment holding x (binary search).  One lane per
+// integer x, no atomics, no shuffles on the data path but the scan that builds the prefix sums; the summation
+// order is fixed.  Shifts are taken relative to floor(s_min) so that D stays O(W x support).
+// Rings with more than two branches (rare: checked here) go through the generic segmented-scan deposit.
+__device__ inline void warp_ring_gather(double *Hs, int K_LO, int nH, const RingScr &sc, int NP, double cW, int &kf_min,
+                                        int &kl_max)
+{
+    const int lane = threadIdx.x & 31;
+    const int nq = NP >> 5, mask = NP - 1;
+    // ---- extremes of the shift around the ring
+    double vmin = sc.S[lane], vmax = vmin;
+    int imin = lane, imax = lane;
+    for (int q = 1; q < nq; q++) {
+        const int t = lane + 32 * q;
+        const double v = sc.S[t];
+        if (v < vmin) { vmin = v; imin = t; }
+        if (v > vmax) { vmax = v; imax = t; }
+    }
+    imin = warp_arg_extreme(vmin, imin, false);
+    imax = warp_arg_extreme(vmax, imax, true);
+    const double smin = sc.S[imin], smax = sc.S[imax];
+    const int m = (imax - imin) & mask; // rotated position of the maximum: segments [0, m) rise, [m, NP) fall
+    const double xref = floor(smin);
+    // ---- segments in rotated order i = lane + 32 q (sample t = (imin + i) mod NP); branch check; prefix sums
+    bool ok = true;
+    double c0 = 0.0, c1 = 0.0; // running totals of the previous 32-segment groups
+    for (int q = 0; q < nq; q++) {
+        const int i = lane + 32 * q;
+        const int t = (imin + i) & mask, t1 = (t + 1) & mask;
+        const double a = sc.S[t] - xref, b = sc.S[t1] - xref;
+        ok = ok && (i < m ? b >= a : b <= a);
+        const double Ws = (sc.Wv[t] + sc.Wv[t1]) * cW;
+        const double lo = a < b ? a : b, hi = a < b ? b : a, len = hi - lo;
+        const double qv = len > 1e-12 ? (0.5 * Ws) * __drcp_rn(len) : 0.0;
+        double p0 = Ws, p1 = Ws * (0.5 * (lo + hi));
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double u0 = __shfl_up_sync(RG_FULL, p0, d), u1 = __shfl_up_sync(RG_FULL, p1, d);
+            if (lane >= d) { p0 += u0; p1 += u1; }
+        }
+        // exclusive prefix of segment i = inclusive of segment i - 1
+        double e0 = __shfl_up_sync(RG_FULL, p0, 1), e1 = __shfl_up_sync(RG_FULL, p1, 1);
+        if (lane == 0) { e0 = 0.0; e1 = 0.0; }
+        sc.P[i] = make_double2(c0 + e0, c1 + e1);
+        sc.Q[i] = qv;
+        c0 += __shfl_sync(RG_FULL, p0, 31);
+        c1 += __shfl_sync(RG_FULL, p1, 31);
+    }
+    if (lane == 0) sc.P[NP] = make_double2(c0, c1);
+    ok = __all_sync(RG_FULL, ok);
+    __syncwarp();
+    const int kfirst = (int)xref, klast = (int)floor(smax) + 1; // bins the hat deposit can touch
+    kf_min = kfirst < kf_min ? kfirst : kf_min;
+    kl_max = klast > kl_max ? klast : kl_max;
+    if (!ok) {
+        // generic path: segments in raw column order, 32 at a time
+        for (int q = 0; q < nq; q++) {
+            const int t = lane + 32 * q, t1 = (t + 1) & mask;
+            warp_deposit(Hs, K_LO, nH, sc.S[t], sc.S[t1], (sc.Wv[t] + sc.Wv[t1]) * cW);
+        }
+        __syncwarp();
+        return;
+    }
+    // ---- one lane per integer x (relative to xref): D on [-1, klast - kfirst + 1], H on the interior
+    const double tot0 = c0, tot1 = c1;
+    const double rmin = smin - xref, rmax = smax - xref;
+    int lg2 = 5;
+    while ((1 << lg2) < NP) lg2++;
+    for (int xb = -1; xb + 1 <= klast - kfirst; xb += 30) {
+        const int xi = xb + lane;
+        const double x = (double)xi;
+        double D = 0.0;
+        if (x >= rmax) D = x * tot0 - tot1;
+        else if (x > rmin) {
+            // rising branch: largest i in [0, m) with R[i] <= x     (R[0] <= x < R[m])
+            int lo = 0, hi = m;
+            for (int st = 0; st < lg2; st++) {
+                const int mid = (lo + hi) >> 1;
+                if (hi - lo > 1) {
+                    if (sc.S[(imin + mid) & mask] - xref <= x) lo = mid; else hi = mid;
+                }
+            }
+            {
+                const double2 p = sc.P[lo];
+                const double d = x - (sc.S[(imin + lo) & mask] - xref);
+                D = (x * p.x - p.y) + sc.Q[lo] * (d * d);
+            }
+            // falling branch: smallest j in (m, NP] with R[j] <= x  (R[m] > x >= R[NP] = R[0])
+            lo = m; hi = NP;
+            for (int st = 0; st < lg2; st++) {
+                const int mid = (lo + hi) >> 1;
+                if (hi - lo > 1) {
+                    if (sc.S[(imin + mid) & mask] - xref > x) lo = mid; else hi = mid;
+                }
+            }
+            {
+                const double2 p = sc.P[hi];
+                const double d = x - (sc.S[(imin + hi) & mask] - xref);
+                D += (x * (tot0 - p.x) - (tot1 - p.y)) + sc.Q[hi - 1] * (d * d);
+            }
+        }
+        const double Dm = __shfl_up_sync(RG_FULL, D, 1), Dp = __shfl_down_sync(RG_FULL, D, 1);
+        if (lane >= 1 && lane <= 30 && xi <= klast - kfirst) {
+            const unsigned idx = (unsigned)(kfirst + xi - K_LO);
+            if (idx < (unsigned)nH) Hs[idx] += (Dp - D) - (D - Dm);
+        }
+    }
+    __syncwarp();
+}
+
+// One warp adds weight x (shift histogram of rings m_begin, m_begin + m_step, ... of annulus [r1, r2] cut into nsub
+// rings) to Hs, sampling the slice.  alpha, beta, rb: kyconv's broken power-law emissivity; zs: redshift in units
+// of shift bins.  single: geometry of the annulus' only ring when the caller has it already (nsub == 1).
+__device__ inline void warp_build_rings(double *Hs, int K_LO, int nH, const TabSel &ts, const double2 *slice,
+                                        const RingScr &sc, double r1, double r2, double inv_dlnE, int nsub, int m_begin,
+                                        int m_step, double alpha, double beta, double rb, double zs, double weight,
+                                        int &kmin_out, int &kmax_out, const RingGeo *single = nullptr)
+{
     const int lane = threadIdx.x & 31;
     const int NP = ts.NPHI, nq = NP >> 5;
     const double lnr = single ? 0.0 : log(r2 / r1);
-    const double dphi = ts.dphi;
-    // shift in bins = ln g / dlnE, as one multiplication per sample (the caller may pass the reciprocal)
-    const double inv_dlnE = inv_dlnE_in != 0.0 ? inv_dlnE_in : 1.0 / dlnE;
     int kf_min = RG_IMAX, kl_max = -RG_IMAX;
     const int n_mine = m_begin < nsub ? (nsub - m_begin + m_step - 1) / m_step : 0;
     for (int m0 = 0; m0 < n_mine; m0 += 32) {
+        // the geometry of 32 rings at a time, one per lane
         const int nr = n_mine - m0 < 32 ? n_mine - m0 : 32;
-        RingGeo geo;
-        geo.A = 0; geo.fr = 0; geo.s0 = 0; geo.s1 = 0;
-        if (single) geo = *single;
-        else if (lane < nr) geo = rg_ring_geo(ts, r1, r2, lnr, m_begin + (m0 + lane) * m_step, nsub, alpha, beta, rb);
-        for (int m = 0; m < nr; m++) {
-            const double A = single ? geo.A : __shfl_sync(RG_FULL, geo.A, m), fr = single ? geo.fr : __shfl_sync(RG_FULL, geo.fr, m);
-            const int s0 = single ? geo.s0 : __shfl_sync(RG_FULL, geo.s0, m), s1 = single ? geo.s1 : __shfl_sync(RG_FULL, geo.s1, m);
-            double g, jn;
-            rg_ring_sample(ts, s0, s1, fr, lane, g, jn);
-            const double cW = 0.5 * dphi * A * weight; // segment weight = (w_t + w_{t+1}) cW
-            double s_cur = RG_LOG_G(g) * inv_dlnE + zs, w_cur = jn * g * g * g;
-            const double s_first = __shfl_sync(RG_FULL, s_cur, 0), w_first = __shfl_sync(RG_FULL, w_cur, 0);
-            for (int q = 0; q < nq; q++) {
-                double s_nxt = 0, w_nxt = 0, sn0, wn0;
-                if (q + 1 < nq) {
-                    rg_ring_sample(ts, s0, s1, fr, lane + 32 * (q + 1), g, jn);
-                    s_nxt = RG_LOG_G(g) * inv_dlnE + zs; w_nxt = jn * g * g * g;
-                    sn0 = __shfl_sync(RG_FULL, s_nxt, 0); wn0 = __shfl_sync(RG_FULL, w_nxt, 0);
-                } else { sn0 = s_first; wn0 = w_first; }
-                double sb = __shfl_down_sync(RG_FULL, s_cur, 1), wb = __shfl_down_sync(RG_FULL, w_cur, 1);
-                if (lane == 31) { sb = sn0; wb = wn0; }
-                const double W = (w_cur + wb) * cW;
-                warp_deposit(Hs, K_LO, nH, s_cur, sb, W, kf_min, kl_max);
-                s_cur = s_nxt; w_cur = w_nxt;
+        RingGeo mine;
+        mine.A = 0; mine.fr = 0; mine.s0 = ts.s_lo;
+        if (single) mine = *single;
+        else if (lane < nr) mine = rg_ring_geo(ts, r1, r2, lnr, m_begin + (m0 + lane) * m_step, nsub, alpha, beta, rb);
+        for (int mi = 0; mi < nr; mi++) {
+            RingGeo geo = mine;
+            if (!single) {
+                geo.A = __shfl_sync(RG_FULL, mine.A, mi); geo.fr = __shfl_sync(RG_FULL, mine.fr, mi);
+                geo.s0 = __shfl_sync(RG_FULL, mine.s0, mi);
             }
+            const double2 *row0 = slice + (size_t)(geo.s0 - ts.s_lo) * NP, *row1 = row0 + NP;
+            for (int q = 0; q < nq; q++) {
+                const int t = lane + 32 * q;
+                const double2 a = row0[t], b = row1[t];
+                sc.S[t] = (a.x + geo.fr * (b.x - a.x)) * inv_dlnE + zs;
+                sc.Wv[t] = a.y + geo.fr * (b.y - a.y);
+            }
+            __syncwarp();
+            warp_ring_gather(Hs, K_LO, nH, sc, NP, 0.5 * ts.dphi * geo.A * weight, kf_min, kl_max);
         }
     }
-    kmin_out = __reduce_min_sync(RG_FULL, kf_min);
-    kmax_out = __reduce_max_sync(RG_FULL, kl_max);
+    kmin_out = kf_min;
+    kmax_out = kl_max;
 }
-
-// One warp adds weight x (shift histogram of the whole annulus [r1, r2], ring count by rg_auto_nsub) to Hs.
-__device__ inline void warp_build_hist(double *Hs, int K_LO, int nH, const TabSel &ts, double r1, double r2, double dlnE,
-                                       double weight, int &kmin_out, int &kmax_out)
-{
-    const int nsub = rg_auto_nsub(r1, r2, log(r2 / r1), dlnE);
-    warp_build_rings(Hs, K_LO, nH, ts, r1, r2, dlnE, nsub, 0, 1, 0.0, 0.0, 1.0, 0.0, weight, kmin_out, kmax_out);
-}
-

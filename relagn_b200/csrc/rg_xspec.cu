@@ -52,12 +52,12 @@ int xs_fail(const char *who)
 // the Python layer writes (npy_path or $RELAGN_B200_TABLES) or is ray-traced on the device (about 35 s, once).
 extern "C" int rg_tables_default(rg_ctx *ctx, const char *npy_path)
 {
-    static const double spins[11] = {-0.998, -0.5, 0.0, 0.3, 0.5, 0.7, 0.8, 0.9, 0.95, 0.98, 0.998};
-    static const double deg[14] = {3.0, 10.0, 18.0, 26.0, 34.0, 42.0, 50.0, 57.0, 63.0, 69.0, 74.0, 78.0, 82.0, 85.0};
+    static const double spins[14] = {-0.998, -0.6, -0.2, 0.1, 0.3, 0.5, 0.7, 0.8, 0.9, 0.95, 0.975, 0.9875, 0.995, 0.998};
+    static const double deg[14] = {0.0, 10.0, 20.0, 30.0, 40.0, 50.0, 57.5, 65.0, 70.0, 75.0, 77.5, 80.0, 82.5, 85.0};
     double thetas[14];
     for (int i = 0; i < 14; i++) thetas[i] = deg[i] * (RGK_PI / 180.0);
     const int NR = 64, NPHI = 64;
-    const double dl = 3.76 / 63;
+    const double r_in = 1.2369;
     if (!ctx) return rg_set_error(RG_E_ARG, "rg_tables_default: ctx is NULL");
     if (!npy_path) npy_path = getenv("RELAGN_B200_TABLES");
     if (npy_path && *npy_path) {
@@ -65,7 +65,7 @@ extern "C" int rg_tables_default(rg_ctx *ctx, const char *npy_path)
         if (!f) return rg_set_error(RG_E_ARG, "rg_tables_default: cannot open %s", npy_path);
         // .npy: magic(6) version(2) header length (2 bytes v1, 4 bytes v2+), ASCII dict, then the raw array
         unsigned char head[12];
-        size_t n = (size_t)11 * 14 * 2 * NR * NPHI;
+        size_t n = (size_t)14 * 14 * 2 * NR * NPHI;
         std::vector<float> data(n);
         bool ok = fread(head, 1, 10, f) == 10 && memcmp(head, "\x93NUMPY", 6) == 0;
         size_t hlen = 0;
@@ -75,14 +75,14 @@ extern "C" int rg_tables_default(rg_ctx *ctx, const char *npy_path)
         }
         std::vector<char> hdr(hlen + 1, 0);
         ok = ok && fread(hdr.data(), 1, hlen, f) == hlen && strstr(hdr.data(), "'<f4'") && strstr(hdr.data(), "False") &&
-             strstr(hdr.data(), "(11, 14, 2, 64, 64)");
+             strstr(hdr.data(), "(14, 14, 2, 64, 64)");
         ok = ok && fread(data.data(), sizeof(float), n, f) == n;
         fclose(f);
-        if (!ok) return rg_set_error(RG_E_ARG, "rg_tables_default: %s is not the default table array (<f4, C order, 11x14x2x64x64)", npy_path);
-        return rg_tables_upload(ctx, spins, 11, thetas, 14, NR, NPHI, dl, data.data());
+        if (!ok) return rg_set_error(RG_E_ARG, "rg_tables_default: %s is not the default table array (<f4, C order, 14x14x2x64x64)", npy_path);
+        return rg_tables_upload(ctx, spins, 14, thetas, 14, NR, NPHI, r_in, data.data());
     }
     long bad = 0;
-    return rg_tables_generate(ctx, spins, 11, thetas, 14, NR, NPHI, dl, &bad);
+    return rg_tables_generate(ctx, spins, 14, thetas, 14, NR, NPHI, r_in, &bad);
 }
 
 // Use a caller-owned context (with its resident tables) for the XSPEC entry points; NULL: drop the binding.

@@ -42,9 +42,9 @@ def _context(device=None):
 
 
 def set_tables(tables, device=None):
-    """Use explicit Kerr transfer tables (dict spins, thetas, NR, NPHI, dl, data) instead of the default set."""
+    """Use explicit Kerr transfer tables (dict spins, thetas, NR, NPHI, r_in, data) instead of the default set."""
     c = _context(device)
-    c["ctx"].tables_upload(tables["spins"], tables["thetas"], tables["NR"], tables["NPHI"], tables["dl"],
+    c["ctx"].tables_upload(tables["spins"], tables["thetas"], tables["NR"], tables["NPHI"], tables["r_in"],
                            tables["data"])
     c["tables"] = True
 

@@ -108,11 +108,13 @@ def components(obj, rel):
 
 
 def main():
-    tab_spins = np.array([0.0, 0.7, 0.998])
+    # a small table set in format 2 (neighbouring spin nodes must both hold circular orbits at the ISCO of any model
+    # between them, hence the close pair below 0.998)
+    tab_spins = np.array([0.0, 0.5, 0.8, 0.95, 0.9875, 0.998])
     tab_thetas = np.deg2rad([20.0, 45.0, 60.0, 75.0])
-    NR, NPHI, dl = 64, 64, 3.76 / 63
+    NR, NPHI, r_in = 64, 64, 1.2369
     print("generating oracle tables ...", flush=True)
-    tab = O.Tables(tab_spins, tab_thetas, NR, NPHI, dl)
+    tab = O.Tables(tab_spins, tab_thetas, NR, NPHI, r_in)
 
     def ky(energies, params, flux):
         return O.kyconv(tab, energies, params, flux)
@@ -160,7 +162,7 @@ def main():
 
     # ---------------- relativistic (reference driver + oracle kyconv) ----------------
     rel_store = {"grid1000": grid1000, "tab_spins": tab_spins, "tab_thetas": tab_thetas,
-                 "tab_NR": NR, "tab_NPHI": NPHI, "tab_dl": dl, "tab_data": np.array(tab.data)}
+                 "tab_NR": NR, "tab_NPHI": NPHI, "tab_r_in": r_in, "tab_data": np.array(tab.data)}
     rel_relagn = [c for c in relagn_cases() if c[0] in ("default", "a998", "nohot", "nowarm", "rout3", "z05", "c4_0",
                                                          "c4_1", "c4_2")]
     rel_relqso = [c for c in relqso_cases() if c[0] in ("default", "m8", "m5_hi", "m10_lo")]

@@ -137,6 +137,15 @@ static inline int __reduce_min_sync(unsigned, int v)
         if ((live >> l) & 1) { int x = (int)(int64_t)all[l]; if (x < r) r = x; }
     return r;
 }
+static inline unsigned __reduce_min_sync(unsigned, unsigned v)
+{
+    uint64_t all[32];
+    unsigned live = hostsim::warp_gather((uint64_t)v, all);
+    unsigned r = v;
+    for (int l = 0; l < 32; l++)
+        if ((live >> l) & 1) { unsigned x = (unsigned)all[l]; if (x < r) r = x; }
+    return r;
+}
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }

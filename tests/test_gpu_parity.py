@@ -32,12 +32,12 @@ def oracle():
 @pytest.fixture(scope="module")
 def otab(oracle):
     t = golden_tables()
-    return oracle.Tables(t["spins"], t["thetas"], t["NR"], t["NPHI"], t["dl"], data=t["data"])
+    return oracle.Tables(t["spins"], t["thetas"], t["NR"], t["NPHI"], t["r_in"], data=t["data"])
 
 
 def upload_golden_tables(ctx):
     t = golden_tables()
-    ctx.tables_upload(t["spins"], t["thetas"], t["NR"], t["NPHI"], t["dl"], t["data"])
+    ctx.tables_upload(t["spins"], t["thetas"], t["NR"], t["NPHI"], t["r_in"], t["data"])
 
 
 @pytest.mark.parametrize("tag,model", [("relagn", 0), ("relqso", 1)])

@@ -18,7 +18,7 @@ def ctx():
     import sim
     c = sim.context()
     t = golden_tables()
-    c.tables_upload(t["spins"], t["thetas"], t["NR"], t["NPHI"], t["dl"], t["data"])
+    c.tables_upload(t["spins"], t["thetas"], t["NR"], t["NPHI"], t["r_in"], t["data"])
     return c
 
 
@@ -68,7 +68,7 @@ def test_python_default_grid(ctx):
 def test_kyconv_seam(ctx):
     from oracle import oracle as O
     t = golden_tables()
-    otab = O.Tables(t["spins"], t["thetas"], t["NR"], t["NPHI"], t["dl"], data=t["data"])
+    otab = O.Tables(t["spins"], t["thetas"], t["NR"], t["NPHI"], t["r_in"], data=t["data"])
     eb = np.geomspace(0.1, 2.0, 501)
     ec = 0.5 * (eb[1:] + eb[:-1])
     line = np.exp(-0.5 * ((ec - 1.0) / 0.01) ** 2) * np.diff(eb)
@@ -211,7 +211,7 @@ def test_xspec_local_model_abi(ctx):
     from oracle import oracle as O
     from tests.util import xspec_reference
     t = golden_tables()
-    otab = O.Tables(t["spins"], t["thetas"], t["NR"], t["NPHI"], t["dl"], data=t["data"])
+    otab = O.Tables(t["spins"], t["thetas"], t["NR"], t["NPHI"], t["r_in"], data=t["data"])
     ctx.xspec_bind()
     try:
         ear = np.linspace(0.3, 10.0, 101).astype(np.float32)

@@ -85,7 +85,7 @@ def test_rel_golden_reference_driver():
     """reference driver (unmodified relagn.py do_rel*Spec) + oracle kyconv at the seam vs the
     oracle's own whole-path evaluation: pins pack/unpack, the 10^3 Rg switch and the region sums."""
     d = np.load(os.path.join(G, "golden_rel.npz"))
-    tab = O.Tables(d["tab_spins"], d["tab_thetas"], int(d["tab_NR"]), int(d["tab_NPHI"]), float(d["tab_dl"]),
+    tab = O.Tables(d["tab_spins"], d["tab_thetas"], int(d["tab_NR"]), int(d["tab_NPHI"]), float(d["tab_r_in"]),
                    data=d["tab_data"])
     for tag, model in (("relagn", 0), ("relqso", 1)):
         for i, name in enumerate(d[tag + "_names"]):
@@ -98,7 +98,7 @@ def test_rel_golden_reference_driver():
 
 def test_kyconv_flat_limit_and_additivity():
     d = np.load(os.path.join(G, "golden_rel.npz"))
-    tab = O.Tables(d["tab_spins"], d["tab_thetas"], int(d["tab_NR"]), int(d["tab_NPHI"]), float(d["tab_dl"]),
+    tab = O.Tables(d["tab_spins"], d["tab_thetas"], int(d["tab_NR"]), int(d["tab_NPHI"]), float(d["tab_r_in"]),
                    data=d["tab_data"])
     dlnE = np.log(1e7) / 1000
     th = np.deg2rad(60.0)

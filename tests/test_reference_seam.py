@@ -24,7 +24,7 @@ def test_unmodified_reference_through_rg_kyconv():
     from relagn_b200 import xspec_shim
     ctx = sim.context()
     t = golden_tables()
-    ctx.tables_upload(t["spins"], t["thetas"], t["NR"], t["NPHI"], t["dl"], t["data"])
+    ctx.tables_upload(t["spins"], t["thetas"], t["NR"], t["NPHI"], t["r_in"], t["data"])
     xspec_shim.bind(ctx)
     saved = {k: sys.modules.get(k) for k in ("xspec", "astropy", "astropy.units", "astropy.constants", "relagn")}
     try:

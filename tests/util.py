@@ -24,7 +24,7 @@ def peak_relerr(a, b, floor=1e-12):
 def golden_tables():
     d = np.load(os.path.join(GOLDEN, "golden_rel.npz"))
     return dict(spins=d["tab_spins"], thetas=d["tab_thetas"], NR=int(d["tab_NR"]), NPHI=int(d["tab_NPHI"]),
-                dl=float(d["tab_dl"]), data=d["tab_data"])
+                r_in=float(d["tab_r_in"]), data=d["tab_data"])
 
 
 def c4_params(P, seed=20240229, tab_spins=None, tab_thetas=None):
