@@ -71,6 +71,9 @@ struct rg_ctx {
     double *d_rq = nullptr;
     int rq_cap = 0;
     int *d_queue = nullptr;
+    double2 *d_slices = nullptr; // table-slice scratch of the resident hist_kernel CTAs (L2 resident)
+    int slice_slots = 0;
+    size_t slice_elems = 0;
     double *d_partial = nullptr;
     size_t partial_n = 0;
     double *d_hist = nullptr; // shift-histogram arena [annuli of the chunk][hstride]
@@ -168,7 +171,7 @@ extern "C" void rg_ctx_destroy(rg_ctx *c)
     cudaDeviceSynchronize();
     free_dev(c->d_grid); free_dev(c->d_tab); free_dev(c->d_tab2); free_dev(c->d_tabmeta); free_dev(c->d_firstrow); free_dev(c->d_kystatus); free_dev(c->d_p10); free_dev(c->d_recs);
     free_dev(c->d_counter); free_dev(c->d_syslist); free_dev(c->d_sptot); free_dev(c->d_farr); free_dev(c->d_header); free_dev(c->d_sc);
-    free_dev(c->d_rq); free_dev(c->d_queue); free_dev(c->d_partial); free_dev(c->d_hist); free_dev(c->d_edges); free_dev(c->d_kyH); free_dev(c->d_kyin); free_dev(c->d_kyout);
+    free_dev(c->d_rq); free_dev(c->d_queue); free_dev(c->d_slices); free_dev(c->d_partial); free_dev(c->d_hist); free_dev(c->d_edges); free_dev(c->d_kyH); free_dev(c->d_kyin); free_dev(c->d_kyout);
     free_dev(c->d_stage_par); free_dev(c->d_stage_out); free_dev(c->d_stage_attr); free_dev(c->d_stats);
     free_dev(c->d_ebins); free_dev(c->d_ear); free_dev(c->d_sl_off); free_dev(c->d_ell_col); free_dev(c->d_ell_val);
     free_dev(c->d_counts); free_dev(c->d_sigma); free_dev(c->d_slab); free_dev(c->d_stage_stat); free_dev(c->d_pos0);
@@ -401,6 +404,8 @@ static int tables_alloc(rg_ctx *c, const double *spins, int n_spin, const double
     return RG_OK;
 }
 
+static int ensure_slices(rg_ctx *c);
+
 static double host_row_pos(const TabDesc &t, double r)
 {
     double ell = (rg_row_x(r) - t.x0) / t.dx;
@@ -534,8 +539,9 @@ static int ky_hist_host(rg_ctx *c, double a, double th, double r1, double r2, do
         RG_CUDA_OK(cudaMalloc(&c->d_kyH, (size_t)nH * sizeof(double)));
         c->kyH_cap = nH;
     }
+    RG_TRY(ensure_slices(c));
     RG_TRY(rg_launch_ky_hist(c->td, a, th, r1, r2, alpha, beta, rb, zshift, dlnE, nsub, c->d_kyH, K_LO, nH, c->d_kystatus,
-                             c->stream));
+                             c->d_slices, c->stream));
     c->launches++;
     H.resize(nH);
     int kst = 0;
@@ -619,13 +625,27 @@ static int pick_chunk_sets(int P)
     return std::min(want, cap);
 }
 
+// scratch for the table slices of the resident hist_kernel CTAs: 8 per SM at most
+static int ensure_slices(rg_ctx *c)
+{
+    const size_t per = (size_t)c->td.NR * c->td.NPHI;
+    const int slots = c->sm_count * 8;
+    if (c->d_slices && c->slice_elems >= per * slots) { c->slice_slots = slots; return RG_OK; }
+    free_dev(c->d_slices);
+    c->d_slices = nullptr;
+    RG_CUDA_OK(cudaMalloc(&c->d_slices, per * slots * sizeof(double2)));
+    c->slice_elems = per * slots;
+    c->slice_slots = slots;
+    return RG_OK;
+}
+
 static int ensure_batch_scratch(rg_ctx *c, int model, int P)
 {
     if (!c->d_sc) { // persistent nthcomp grid and its scratch planes: sized by the machine, not by the batch
         c->nth_threads = c->sm_count * RG_NTH_MINB * 128;
         // two [RG_NTH][threads] planes (gamma, g of the Thomas sweep) + one row (bet[0])
         RG_CUDA_OK(cudaMalloc(&c->d_sc, ((size_t)2 * RG_NTH + 1) * c->nth_threads * sizeof(double)));
-        RG_CUDA_OK(cudaMalloc(&c->d_queue, 2 * sizeof(int)));
+        RG_CUDA_OK(cudaMalloc(&c->d_queue, 4 * sizeof(int)));
     }
     const int want = pick_chunk_sets(P);
     if (want > c->chunk_sets) { // grow: per-set records, arena of Kompaneets systems
@@ -780,6 +800,8 @@ static int eval_batch_impl(rg_ctx *c, const double *d_params, int P, int model, 
             H.recs = c->d_recs; H.P = n; H.tab = c->td; H.dlnE = c->gd.dlnE; H.inv_dlnE = 1.0 / c->gd.dlnE; H.K_LO = A.K_LO; H.nH = A.nH;
             H.NBH = n >= 2 * c->sm_count ? 1 : (int)std::min<long>(32, (4L * c->sm_count + n - 1) / n);
             H.hist = c->d_hist; H.hstride = A.hstride; H.edges = A.edges;
+            RG_TRY(ensure_slices(c));
+            H.slices = c->d_slices; H.slice_slots = c->slice_slots; H.queue = c->d_queue + 2;
             cudaStream_t hs = st;
             if (!c->profile && nsys > 0 && !getenv("RG_NO_SIDE_STREAM")) {
                 RG_CUDA_OK(cudaEventRecord(c->ev_fork, st));
@@ -789,7 +811,7 @@ static int eval_batch_impl(rg_ctx *c, const double *d_params, int P, int model, 
             }
             if (forked && nth_first) RG_TRY(launch_nth());
             RG_TRY(prof_begin(c, 4, hs));
-            RG_TRY(rg_launch_hist(H, hs));
+            RG_TRY(rg_launch_hist(H, c->sm_count, hs));
             RG_TRY(prof_end(c, 4, hs));
             if (forked) RG_CUDA_OK(cudaEventRecord(c->ev_join, c->side));
             c->launches++;

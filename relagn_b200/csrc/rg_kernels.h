@@ -86,8 +86,11 @@ struct HistArgs {
     double *hist;  // [total annuli][hstride]
     int hstride;   // >= nH + 1
     const double2 *edges; // [total annuli] (lo, hi) in log10 r (edges_kernel)
+    double2 *slices;      // [slice_slots][NR][NPHI] scratch: the table slice of the set a resident CTA works on
+    int slice_slots;
+    int *queue;           // device work-queue counter (zeroed by the launcher)
 };
-int rg_launch_hist(const HistArgs &A, cudaStream_t st);
+int rg_launch_hist(const HistArgs &A, int sm_count, cudaStream_t st);
 // radial bin edges of every annulus of every set (relagn.py:731-776), one thread per (set, region): the chain of
 // repeated subtractions is walked once here instead of by every consumer lane
 int rg_launch_edges(const SetRec *recs, int P, double2 *edges, cudaStream_t st);
@@ -95,7 +98,7 @@ int rg_launch_edges(const SetRec *recs, int P, double2 *edges, cudaStream_t st);
 // generic kyconv seam: histogram of one (possibly wide) annulus into d_H[0..nH) (shift k = K_LO + index)
 int rg_launch_ky_hist(const TabDesc &tab, double a, double theta_o, double r1, double r2, double alpha, double beta,
                       double rb, double zshift, double dlnE, int nsub, double *d_H, int K_LO, int nH, int *d_status,
-                      cudaStream_t st);
+                      double2 *d_slice, cudaStream_t st);
 // out[j] = sum_i H[i] in[j - (kmin + i)]
 int rg_launch_ky_conv(const double *d_H, int kmin, int nk, const double *d_in, double *d_out, int nE,
                       cudaStream_t st);

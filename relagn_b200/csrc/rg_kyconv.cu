@@ -12,18 +12,20 @@
 #define KW (KT / 32)
 
 static __host__ __device__ inline int ky_round_up2(int x) { return (x + 1) & ~1; }
+static __host__ __device__ inline int ky_dn(int nH) { return ky_round_up2(nH) < 512 ? ky_round_up2(nH) : 512; }
 
+template <int NQ>
 __global__ void __launch_bounds__(KT)
 ky_hist_kernel(TabDesc tab, double a, double theta_o, double r1, double r2, double alpha, double beta, double rb,
-               double zs, double dlnE, int nsub, double *__restrict__ H_out, int K_LO, int nH, int *__restrict__ status)
+               double zs, double dlnE, int nsub, double *__restrict__ H_out, int K_LO, int nH, int *__restrict__ status,
+               double2 *slice)
 {
     RG_DYN_SMEM(smem_raw);
-    const int NP = tab.NPHI;
-    double2 *slice = reinterpret_cast<double2 *>(smem_raw);                     // [NR][NPHI]
-    double *H = reinterpret_cast<double *>(slice + (size_t)tab.NR * NP);        // [KW][nH2]
-    const int nH2 = ky_round_up2(nH);
+    constexpr int NP = 32 * NQ;
+    double *H = reinterpret_cast<double *>(smem_raw); // [KW][nH2] | per warp ring scratch
+    const int nH2 = ky_round_up2(nH), DN = ky_dn(nH);
     const int tid = threadIdx.x, warp = tid >> 5;
-    double *scr_base = H + (size_t)KW * nH2 + (size_t)warp * ky_round_up2(RG_RING_SCR_DOUBLES(NP));
+    double *scr_base = H + (size_t)KW * nH2 + (size_t)warp * ky_round_up2(RG_RING_SCR_DOUBLES(NP, DN));
     for (int i = tid; i < KW * nH2; i += KT) H[i] = 0.0;
     __shared__ TabSel s_ts;
     __shared__ int s_hi;
@@ -42,8 +44,8 @@ ky_hist_kernel(TabDesc tab, double a, double theta_o, double r1, double r2, doub
         rg_build_slice(ts, s_hi, slice, tid, KT);
         __syncthreads();
         int kmn, kmx;
-        warp_build_rings(H + (size_t)warp * nH2, K_LO, nH, ts, slice, rg_ring_scr(scr_base, NP), r1, r2, 1.0 / dlnE, nsub,
-                         warp, KW, alpha, beta, rb, zs, 1.0, kmn, kmx);
+        warp_build_rings<NQ>(H + (size_t)warp * nH2, K_LO, nH, ts, slice, rg_ring_scr(scr_base, NP, DN), r1, r2, 1.0 / dlnE,
+                             nsub, warp, KW, alpha, beta, rb, zs, 1.0, kmn, kmx);
     }
     __syncthreads();
     for (int i = tid; i < nH; i += KT) {
@@ -67,22 +69,36 @@ ky_conv_kernel(const double *__restrict__ H, int kmin, int nk, const double *__r
     out[j] = s;
 }
 
+template <int NQ>
+static int launch_ky_hist(const TabDesc &tab, double a, double theta_o, double r1, double r2, double alpha, double beta,
+                          double rb, double zs, double dlnE, int nsub, double *d_H, int K_LO, int nH, int *d_status,
+                          double2 *d_slice, cudaStream_t st)
+{
+    size_t smem = (size_t)KW * ky_round_up2(nH) * sizeof(double) +
+                  (size_t)KW * ky_round_up2(RG_RING_SCR_DOUBLES(32 * NQ, ky_dn(nH))) * sizeof(double);
+    if (smem > 220 * 1024) return rg_set_error(RG_E_GRID, "energy grid too fine for the kyconv histogram");
+    auto kern = ky_hist_kernel<NQ>;
+    RG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RG_LAUNCH(kern, dim3(1), dim3(KT), smem, st, tab, a, theta_o, r1, r2, alpha, beta, rb, zs, dlnE, nsub, d_H, K_LO, nH,
+              d_status, d_slice);
+    RG_CUDA_OK(cudaGetLastError());
+    return RG_OK;
+}
+
 int rg_launch_ky_hist(const TabDesc &tab, double a, double theta_o, double r1, double r2, double alpha, double beta,
                       double rb, double zshift, double dlnE, int nsub, double *d_H, int K_LO, int nH, int *d_status,
-                      cudaStream_t st)
+                      double2 *d_slice, cudaStream_t st)
 {
-    if (KT % tab.NPHI != 0 || tab.NPHI < 32) return rg_set_error(RG_E_ARG, "NPHI must divide %d and be >= 32", KT);
-    size_t smem = (size_t)tab.NR * tab.NPHI * sizeof(double2) + (size_t)KW * ky_round_up2(nH) * sizeof(double) +
-                  (size_t)KW * ky_round_up2(RG_RING_SCR_DOUBLES(tab.NPHI)) * sizeof(double);
-    if (smem > 220 * 1024) return rg_set_error(RG_E_GRID, "energy grid too fine for the kyconv histogram");
     double zs = 0.0;
     if (zshift != 0) zs = -log(1 + zshift) / dlnE;
     if (nsub <= 0) nsub = rg_auto_nsub(r1, r2, log(r2 / r1), dlnE);
-    RG_CUDA_OK(cudaFuncSetAttribute(ky_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    RG_LAUNCH(ky_hist_kernel, dim3(1), dim3(KT), smem, st, tab, a, theta_o, r1, r2, alpha, beta, rb, zs, dlnE, nsub,
-              d_H, K_LO, nH, d_status);
-    RG_CUDA_OK(cudaGetLastError());
-    return RG_OK;
+    switch (tab.NPHI) {
+    case 32: return launch_ky_hist<1>(tab, a, theta_o, r1, r2, alpha, beta, rb, zs, dlnE, nsub, d_H, K_LO, nH, d_status, d_slice, st);
+    case 64: return launch_ky_hist<2>(tab, a, theta_o, r1, r2, alpha, beta, rb, zs, dlnE, nsub, d_H, K_LO, nH, d_status, d_slice, st);
+    case 128: return launch_ky_hist<4>(tab, a, theta_o, r1, r2, alpha, beta, rb, zs, dlnE, nsub, d_H, K_LO, nH, d_status, d_slice, st);
+    case 256: return launch_ky_hist<8>(tab, a, theta_o, r1, r2, alpha, beta, rb, zs, dlnE, nsub, d_H, K_LO, nH, d_status, d_slice, st);
+    }
+    return rg_set_error(RG_E_ARG, "NPHI must be 32, 64, 128 or 256");
 }
 
 int rg_launch_ky_conv(const double *d_H, int kmin, int nk, const double *d_in, double *d_out, int nE,

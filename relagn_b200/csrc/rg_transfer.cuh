@@ -256,20 +256,19 @@ static __device__ __noinline__ void warp_deposit(double *Hs, int K_LO, int nH, d
 #undef RG_SCAN_STEP
 
 // ---------------------------------------------------------------------------
-// Per-warp scratch of the ring routines: NP + 1 entries each.
+// Per-warp scratch of the ring routines.
 struct RingScr {
-    double *S;   // shift of every ring sample (bins), raw column order
-    double *Wv;  // weight density of every sample
-    double2 *P;  // exclusive prefix sums (sum W, sum W mid) over the segments in rotated order; entry NP = totals
-    double *Q;   // W / (2 len) per segment in rotated order (0 for a degenerate segment)
+    double *S;   // [NP] shift of every ring sample (bins), raw column order
+    double *Wv;  // [NP] weight density of every sample
+    double *D;   // [DN] the ring's D(x) on consecutive integer shifts (see warp_ring_gather)
+    int DN;
 };
-#define RG_RING_SCR_DOUBLES(NP) (5 * ((NP) + 1) + 1)
+#define RG_RING_SCR_DOUBLES(NP, DN) (2 * (NP) + (DN))
 
-__device__ inline RingScr rg_ring_scr(double *base, int NP)
+__device__ inline RingScr rg_ring_scr(double *base, int NP, int DN)
 {
     RingScr sc;
-    sc.S = base; sc.Wv = base + (NP + 1); sc.Q = base + 2 * (NP + 1);
-    sc.P = reinterpret_cast<double2 *>(base + 3 * (NP + 1) + ((NP + 1) & 1)); // 16-byte aligned when base is
+    sc.S = base; sc.Wv = base + NP; sc.D = base + 2 * NP; sc.DN = DN;
     return sc;
 }
 
@@ -291,16 +290,19 @@ __device__ inline int warp_arg_extreme(double v, int idx, bool want_max)
 // The usual ring is a closed curve with one minimum and one maximum of the shift: two monotone branches.  Then the
 // hat deposit is a GATHER: with D(x) = int^x int^x' (weight density) -- per segment 0 below it, W (x - lo)^2 / (2 len)
 // inside, W (x - mid) above -- the histogram is the second difference H[k] = D(k+1) - 2 D(k) + D(k-1), and on a
-// monotone branch "the segments entirely below x" are a prefix: D(x) = x P0[i] - P1[i] + Q_i (x - lo_i)^2 with prefix
-// sums P0 = sum W, P1 = sum W mid over the branch and i the segment holding x (binary search).  One lane per
-// integer x, no atomics, no shuffles on the data path but the scan that builds the prefix sums; the summation
-// order is fixed.  Shifts are taken relative to floor(s_min) so that D stays O(W x support).
-// Rings with more than two branches (rare: checked here) go through the generic segmented-scan deposit.
-__device__ inline void warp_ring_gather(double *Hs, int K_LO, int nH, const RingScr &sc, int NP, double cW, int &kf_min,
-                                        int &kl_max)
+// monotone branch "the segments entirely below x" are a prefix of the branch: D(x) = x P0 - P1 + Q (x - lo)^2 with the
+// prefix sums P0 = sum W, P1 = sum W mid over the segments before the one that holds x.  Every lane owns NP / 32
+// consecutive segments (rotated so that the minimum comes first), gets its prefix from ONE warp scan, and evaluates D
+// at the integer shifts inside its own segments -- each integer belongs to exactly one segment of the rising and one
+// of the falling branch, so the two branches are written one after the other without atomics and in a fixed
+// order; then one lane per shift takes the second difference.  Shifts are taken relative to floor(s_min) so that D
+// stays O(W x support).  Rings with more than two branches (not met on the default tables; checked here) go through
+// the generic segmented-scan deposit.
+template <int NQ> // NQ = NPHI / 32 segments per lane
+__device__ inline void warp_ring_gather(double *Hs, int K_LO, int nH, const RingScr &sc, double cW, int &kf_min, int &kl_max)
 {
     const int lane = threadIdx.x & 31;
-    const int nq = NP >> 5, mask = NP - 1;
+    constexpr int nq = NQ, NP = 32 * NQ, mask = NP - 1;
     // ---- extremes of the shift around the ring
     double vmin = sc.S[lane], vmax = vmin;
     int imin = lane, imax = lane;
@@ -315,37 +317,30 @@ __device__ inline void warp_ring_gather(double *Hs, int K_LO, int nH, const Ring
     const double smin = sc.S[imin], smax = sc.S[imax];
     const int m = (imax - imin) & mask; // rotated position of the maximum: segments [0, m) rise, [m, NP) fall
     const double xref = floor(smin);
-    // ---- segments in rotated order i = lane + 32 q (sample t = (imin + i) mod NP); branch check; prefix sums
-    bool ok = true;
-    double c0 = 0.0, c1 = 0.0; // running totals of the previous 32-segment groups
-    for (int q = 0; q < nq; q++) {
-        const int i = lane + 32 * q;
-        const int t = (imin + i) & mask, t1 = (t + 1) & mask;
-        const double a = sc.S[t] - xref, b = sc.S[t1] - xref;
-        ok = ok && (i < m ? b >= a : b <= a);
-        const double Ws = (sc.Wv[t] + sc.Wv[t1]) * cW;
-        const double lo = a < b ? a : b, hi = a < b ? b : a, len = hi - lo;
-        const double qv = len > 1e-12 ? (0.5 * Ws) * __drcp_rn(len) : 0.0;
-        double p0 = Ws, p1 = Ws * (0.5 * (lo + hi));
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const double u0 = __shfl_up_sync(RG_FULL, p0, d), u1 = __shfl_up_sync(RG_FULL, p1, d);
-            if (lane >= d) { p0 += u0; p1 += u1; }
-        }
-        // exclusive prefix of segment i = inclusive of segment i - 1
-        double e0 = __shfl_up_sync(RG_FULL, p0, 1), e1 = __shfl_up_sync(RG_FULL, p1, 1);
-        if (lane == 0) { e0 = 0.0; e1 = 0.0; }
-        sc.P[i] = make_double2(c0 + e0, c1 + e1);
-        sc.Q[i] = qv;
-        c0 += __shfl_sync(RG_FULL, p0, 31);
-        c1 += __shfl_sync(RG_FULL, p1, 31);
-    }
-    if (lane == 0) sc.P[NP] = make_double2(c0, c1);
-    ok = __all_sync(RG_FULL, ok);
-    __syncwarp();
     const int kfirst = (int)xref, klast = (int)floor(smax) + 1; // bins the hat deposit can touch
     kf_min = kfirst < kf_min ? kfirst : kf_min;
     kl_max = klast > kl_max ? klast : kl_max;
+    // ---- this lane's segments i = nq lane + q in rotated order (sample t = (imin + i) mod NP)
+    double r[NQ + 1], ws[NQ];
+    bool ok = true;
+    double l0 = 0.0, l1 = 0.0;
+    {
+        const int i0 = nq * lane;
+        double wprev = sc.Wv[(imin + i0) & mask];
+        r[0] = sc.S[(imin + i0) & mask] - xref;
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+            const int t1 = (imin + i0 + q + 1) & mask;
+            r[q + 1] = sc.S[t1] - xref;
+            const double wn = sc.Wv[t1];
+            ws[q] = (wprev + wn) * cW;
+            wprev = wn;
+            ok = ok && (i0 + q < m ? r[q + 1] >= r[q] : r[q + 1] <= r[q]);
+            l0 += ws[q];
+            l1 += ws[q] * (0.5 * (r[q] + r[q + 1]));
+        }
+    }
+    ok = __all_sync(RG_FULL, ok);
     if (!ok) {
         // generic path: segments in raw column order, 32 at a time
         for (int q = 0; q < nq; q++) {
@@ -355,63 +350,91 @@ __device__ inline void warp_ring_gather(double *Hs, int K_LO, int nH, const Ring
         __syncwarp();
         return;
     }
-    // ---- one lane per integer x (relative to xref): D on [-1, klast - kfirst + 1], H on the interior
-    const double tot0 = c0, tot1 = c1;
-    const double rmin = smin - xref, rmax = smax - xref;
-    int lg2 = 5;
-    while ((1 << lg2) < NP) lg2++;
-    for (int xb = -1; xb + 1 <= klast - kfirst; xb += 30) {
-        const int xi = xb + lane;
-        const double x = (double)xi;
-        double D = 0.0;
-        if (x >= rmax) D = x * tot0 - tot1;
-        else if (x > rmin) {
-            // rising branch: largest i in [0, m) with R[i] <= x     (R[0] <= x < R[m])
-            int lo = 0, hi = m;
-            for (int st = 0; st < lg2; st++) {
-                const int mid = (lo + hi) >> 1;
-                if (hi - lo > 1) {
-                    if (sc.S[(imin + mid) & mask] - xref <= x) lo = mid; else hi = mid;
-                }
-            }
-            {
-                const double2 p = sc.P[lo];
-                const double d = x - (sc.S[(imin + lo) & mask] - xref);
-                D = (x * p.x - p.y) + sc.Q[lo] * (d * d);
-            }
-            // falling branch: smallest j in (m, NP] with R[j] <= x  (R[m] > x >= R[NP] = R[0])
-            lo = m; hi = NP;
-            for (int st = 0; st < lg2; st++) {
-                const int mid = (lo + hi) >> 1;
-                if (hi - lo > 1) {
-                    if (sc.S[(imin + mid) & mask] - xref > x) lo = mid; else hi = mid;
-                }
-            }
-            {
-                const double2 p = sc.P[hi];
-                const double d = x - (sc.S[(imin + hi) & mask] - xref);
-                D += (x * (tot0 - p.x) - (tot1 - p.y)) + sc.Q[hi - 1] * (d * d);
-            }
-        }
-        const double Dm = __shfl_up_sync(RG_FULL, D, 1), Dp = __shfl_down_sync(RG_FULL, D, 1);
-        if (lane >= 1 && lane <= 30 && xi <= klast - kfirst) {
-            const unsigned idx = (unsigned)(kfirst + xi - K_LO);
-            if (idx < (unsigned)nH) Hs[idx] += (Dp - D) - (D - Dm);
-        }
+    // exclusive prefix over the lanes of (sum W, sum W mid), and the ring totals
+    double p0 = l0, p1 = l1;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const double u0 = __shfl_up_sync(RG_FULL, p0, d), u1 = __shfl_up_sync(RG_FULL, p1, d);
+        if (lane >= d) { p0 += u0; p1 += u1; }
     }
-    __syncwarp();
+    const double tot0 = __shfl_sync(RG_FULL, p0, 31), tot1 = __shfl_sync(RG_FULL, p1, 31);
+    p0 -= l0; p1 -= l1;
+    const double rmin = smin - xref, rmax = smax - xref;
+    // ---- D on the integer shifts x = xb .. xb + DN - 1 (relative to xref), windows of DN - 2 interior points
+    const int x_last = klast - kfirst; // last shift with a non-zero histogram entry
+    for (int xb = -1; xb + 1 <= x_last; xb += sc.DN - 2) {
+        const int xe = xb + sc.DN - 1 < x_last + 1 ? xb + sc.DN - 1 : x_last + 1; // window [xb, xe]
+        // shifts outside the ring's range: nothing below it, all of it above
+        for (int xi = xb + lane; xi <= xe; xi += 32) {
+            const double x = (double)xi;
+            if (x <= rmin) sc.D[xi - xb] = 0.0;
+            else if (x >= rmax) sc.D[xi - xb] = x * tot0 - tot1;
+        }
+        // rising branch: the integer shifts a <= x < b inside each of this lane's segments
+        {
+            double q0 = p0, q1 = p1;
+#pragma unroll
+            for (int q = 0; q < NQ; q++) {
+                const double a = r[q], b = r[q + 1];
+                if (nq * lane + q < m && b > a) {
+                    const double len = b - a;
+                    const double qv = len > 1e-12 ? (0.5 * ws[q]) * __drcp_rn(len) : 0.0;
+                    int x0 = (int)ceil(a), x1 = (int)ceil(b) - 1;
+                    if (x0 < xb) x0 = xb;
+                    if (x1 > xe) x1 = xe;
+                    for (int xi = x0; xi <= x1; xi++) {
+                        const double x = (double)xi, d = x - a;
+                        if (x > rmin && x < rmax) sc.D[xi - xb] = (x * q0 - q1) + qv * (d * d);
+                    }
+                }
+                q0 += ws[q];
+                q1 += ws[q] * (0.5 * (a + b));
+            }
+        }
+        __syncwarp();
+        // falling branch: b <= x < a; everything after this segment lies entirely below x
+        {
+            double q0 = p0, q1 = p1;
+#pragma unroll
+            for (int q = 0; q < NQ; q++) {
+                const double a = r[q], b = r[q + 1];
+                q0 += ws[q];
+                q1 += ws[q] * (0.5 * (a + b));
+                if (nq * lane + q >= m && a > b) {
+                    const double len = a - b;
+                    const double qv = len > 1e-12 ? (0.5 * ws[q]) * __drcp_rn(len) : 0.0;
+                    int x0 = (int)ceil(b), x1 = (int)ceil(a) - 1;
+                    if (x0 < xb) x0 = xb;
+                    if (x1 > xe) x1 = xe;
+                    for (int xi = x0; xi <= x1; xi++) {
+                        const double x = (double)xi, d = x - b;
+                        if (x > rmin && x < rmax) sc.D[xi - xb] += (x * (tot0 - q0) - (tot1 - q1)) + qv * (d * d);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        // one lane per shift: second difference on the interior of the window
+        for (int xi = xb + 1 + lane; xi < xe; xi += 32) {
+            const double Dm = sc.D[xi - 1 - xb], D0 = sc.D[xi - xb], Dp = sc.D[xi + 1 - xb];
+            const unsigned idx = (unsigned)(kfirst + xi - K_LO);
+            if (idx < (unsigned)nH) Hs[idx] += (Dp - D0) - (D0 - Dm);
+        }
+        __syncwarp();
+    }
 }
 
 // One warp adds weight x (shift histogram of rings m_begin, m_begin + m_step, ... of annulus [r1, r2] cut into nsub
-// rings) to Hs, sampling the slice.  alpha, beta, rb: kyconv's broken power-law emissivity; zs: redshift in units
-// of shift bins.  single: geometry of the annulus' only ring when the caller has it already (nsub == 1).
+// rings) to Hs, sampling the slice (shared or global memory).  alpha, beta, rb: kyconv's broken power-law emissivity;
+// zs: redshift in units of shift bins.  single: geometry of the annulus' only ring when the caller has it already.
+template <int NQ>
 __device__ inline void warp_build_rings(double *Hs, int K_LO, int nH, const TabSel &ts, const double2 *slice,
                                         const RingScr &sc, double r1, double r2, double inv_dlnE, int nsub, int m_begin,
                                         int m_step, double alpha, double beta, double rb, double zs, double weight,
                                         int &kmin_out, int &kmax_out, const RingGeo *single = nullptr)
 {
     const int lane = threadIdx.x & 31;
-    const int NP = ts.NPHI, nq = NP >> 5;
+    constexpr int NP = 32 * NQ;
     const double lnr = single ? 0.0 : log(r2 / r1);
     int kf_min = RG_IMAX, kl_max = -RG_IMAX;
     const int n_mine = m_begin < nsub ? (nsub - m_begin + m_step - 1) / m_step : 0;
@@ -429,14 +452,16 @@ __device__ inline void warp_build_rings(double *Hs, int K_LO, int nH, const TabS
                 geo.s0 = __shfl_sync(RG_FULL, mine.s0, mi);
             }
             const double2 *row0 = slice + (size_t)(geo.s0 - ts.s_lo) * NP, *row1 = row0 + NP;
-            for (int q = 0; q < nq; q++) {
-                const int t = lane + 32 * q;
-                const double2 a = row0[t], b = row1[t];
-                sc.S[t] = (a.x + geo.fr * (b.x - a.x)) * inv_dlnE + zs;
-                sc.Wv[t] = a.y + geo.fr * (b.y - a.y);
+            double2 a[NQ], b[NQ];
+#pragma unroll
+            for (int q = 0; q < NQ; q++) { a[q] = row0[lane + 32 * q]; b[q] = row1[lane + 32 * q]; }
+#pragma unroll
+            for (int q = 0; q < NQ; q++) {
+                sc.S[lane + 32 * q] = (a[q].x + geo.fr * (b[q].x - a[q].x)) * inv_dlnE + zs;
+                sc.Wv[lane + 32 * q] = a[q].y + geo.fr * (b[q].y - a[q].y);
             }
             __syncwarp();
-            warp_ring_gather(Hs, K_LO, nH, sc, NP, 0.5 * ts.dphi * geo.A * weight, kf_min, kl_max);
+            warp_ring_gather<NQ>(Hs, K_LO, nH, sc, 0.5 * ts.dphi * geo.A * weight, kf_min, kl_max);
         }
     }
     kmin_out = kf_min;

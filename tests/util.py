@@ -101,3 +101,41 @@ def xspec_reference(O, otab, model, rel, ear, par):
     st, out, _ = O.evaluate(par, enew, model=model, rel=rel, tab=otab)
     assert st == 0
     return O.photar(out[3], enew, par[1], z, ear)
+
+
+# ---- off-node accuracy of a Kerr table set (tests/test_tables.py, tests/test_gpu_parity.py, tools/table_error.py) ----
+DLNE_1000 = np.log(1e7) / 1000.0  # bin width of the 1000-bin metric grid
+
+
+def risco(a):
+    a = np.asarray(a, dtype=np.float64)
+    z1 = 1 + (1 - a * a) ** (1 / 3) * ((1 + a) ** (1 / 3) + (1 - a) ** (1 / 3))
+    z2 = np.sqrt(3 * a * a + z1 * z1)
+    return 3 + z2 - np.sign(a) * np.sqrt((3 - z1) * (3 + z1 + 2 * z2))
+
+
+def ring_metrics(lg, w, dlnE=DLNE_1000):
+    """Per table row of a slice (ln g [NR][NPHI], weight density w = Jn g^3): the ring's flux sum_t W_t dphi and the
+    centroid of its shift histogram in energy bins, sum_t W_t (s_t + s_{t+1})/2 / sum W_t with W_t = (w_t + w_{t+1})/2,
+    s = ln g / dlnE -- the two moments the hat deposit of the transfer kernel preserves exactly."""
+    lg = np.asarray(lg, dtype=np.float64)
+    w = np.asarray(w, dtype=np.float64)
+    W = 0.5 * (w + np.roll(w, -1, axis=1))
+    F = W.sum(axis=1) * (2 * np.pi / lg.shape[1])
+    c = (W * 0.5 * (lg + np.roll(lg, -1, axis=1))).sum(axis=1) / W.sum(axis=1) / dlnE
+    return F, c
+
+
+def offnode_errors(rows, a, lg_blend, jn_blend, g_true, jn_true):
+    """(worst |flux ratio - 1|, worst |centroid shift| in bins) over the rows r >= 1.5 r_isco and over all rows the
+    model uses (from the row bracketing r_isco from below): blended slice against a node traced at the same (a, i)."""
+    ri = float(risco(a))
+    s_first = max(int(np.searchsorted(rows, ri, side="right")) - 1, 0)
+    sl = slice(s_first, len(rows))
+    gt = np.asarray(g_true, dtype=np.float64)[sl]
+    F0, c0 = ring_metrics(np.log(gt), np.asarray(jn_true, dtype=np.float64)[sl] * gt ** 3)
+    jb = np.maximum(np.asarray(jn_blend)[sl], 0.0)
+    F1, c1 = ring_metrics(np.asarray(lg_blend)[sl], jb * np.exp(3 * np.asarray(lg_blend)[sl]))
+    fe, ce = np.abs(F1 / F0 - 1), np.abs(c1 - c0)
+    far = rows[sl] >= 1.5 * ri
+    return fe[far].max(), ce[far].max(), fe.max(), ce.max()
