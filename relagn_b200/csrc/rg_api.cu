@@ -71,6 +71,8 @@ struct rg_ctx {
     double *d_rq = nullptr;
     int rq_cap = 0;
     int *d_queue = nullptr;
+    void *d_sel = nullptr;       // [chunk] table selections (SelRec) of the chunk's sets
+    size_t sel_bytes = 0;
     double2 *d_slices = nullptr; // table-slice scratch of the resident hist_kernel CTAs (L2 resident)
     int slice_slots = 0;
     size_t slice_elems = 0;
@@ -171,7 +173,7 @@ extern "C" void rg_ctx_destroy(rg_ctx *c)
     cudaDeviceSynchronize();
     free_dev(c->d_grid); free_dev(c->d_tab); free_dev(c->d_tab2); free_dev(c->d_tabmeta); free_dev(c->d_firstrow); free_dev(c->d_kystatus); free_dev(c->d_p10); free_dev(c->d_recs);
     free_dev(c->d_counter); free_dev(c->d_syslist); free_dev(c->d_sptot); free_dev(c->d_farr); free_dev(c->d_header); free_dev(c->d_sc);
-    free_dev(c->d_rq); free_dev(c->d_queue); free_dev(c->d_slices); free_dev(c->d_partial); free_dev(c->d_hist); free_dev(c->d_edges); free_dev(c->d_kyH); free_dev(c->d_kyin); free_dev(c->d_kyout);
+    free_dev(c->d_rq); free_dev(c->d_queue); free_dev(c->d_slices); free_dev(c->d_sel); free_dev(c->d_partial); free_dev(c->d_hist); free_dev(c->d_edges); free_dev(c->d_kyH); free_dev(c->d_kyin); free_dev(c->d_kyout);
     free_dev(c->d_stage_par); free_dev(c->d_stage_out); free_dev(c->d_stage_attr); free_dev(c->d_stats);
     free_dev(c->d_ebins); free_dev(c->d_ear); free_dev(c->d_sl_off); free_dev(c->d_ell_col); free_dev(c->d_ell_val);
     free_dev(c->d_counts); free_dev(c->d_sigma); free_dev(c->d_slab); free_dev(c->d_stage_stat); free_dev(c->d_pos0);
@@ -802,6 +804,13 @@ static int eval_batch_impl(rg_ctx *c, const double *d_params, int P, int model, 
             H.hist = c->d_hist; H.hstride = A.hstride; H.edges = A.edges;
             RG_TRY(ensure_slices(c));
             H.slices = c->d_slices; H.slice_slots = c->slice_slots; H.queue = c->d_queue + 2;
+            if (c->sel_bytes < (size_t)n * rg_selrec_bytes()) {
+                free_dev(c->d_sel);
+                c->d_sel = nullptr;
+                c->sel_bytes = (size_t)std::max(n, c->chunk_sets) * rg_selrec_bytes();
+                RG_CUDA_OK(cudaMalloc(&c->d_sel, c->sel_bytes));
+            }
+            H.sel = reinterpret_cast<SelRec *>(c->d_sel);
             cudaStream_t hs = st;
             if (!c->profile && nsys > 0 && !getenv("RG_NO_SIDE_STREAM")) {
                 RG_CUDA_OK(cudaEventRecord(c->ev_fork, st));

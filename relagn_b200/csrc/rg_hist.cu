@@ -18,7 +18,7 @@
 #define HIST_WARPS 8
 #endif
 #ifndef RG_HIST_MINB
-#define RG_HIST_MINB 4 // resident CTAs per SM the register budget is cut for
+#define RG_HIST_MINB 3 // resident CTAs per SM the register budget is cut for
 #endif
 
 static __host__ __device__ inline int hist_round_up2(int x) { return (x + 1) & ~1; }
@@ -27,13 +27,32 @@ static __host__ __device__ inline int hist_round_up2(int x) { return (x + 1) & ~
 struct PrepRec { double r1, r2; RingGeo geo; int flag, g, nsub, pad; };
 #define HIST_PREP 8 // annuli a warp prepares per pass
 
-// shared memory per warp: H slot | ring scratch (samples + D) | prepared annuli
+// shared memory per warp, fixed-size pieces first so that their addresses are the warp's base plus a constant:
+//   prepared annuli | ring samples (NP double2) | DA, DB (DN doubles each) | H slot (HSZ doubles)
 static __host__ __device__ inline int hist_dn(int HSZ) { return HSZ < 512 ? HSZ : 512; } // entries of the D window
 static __host__ __device__ inline size_t hist_warp_bytes(int nH, int NP)
 {
     const int HSZ = hist_round_up2(nH + 24);
-    return (size_t)HSZ * sizeof(double) + (size_t)hist_round_up2(RG_RING_SCR_DOUBLES(NP, hist_dn(HSZ))) * sizeof(double) +
-           HIST_PREP * sizeof(PrepRec);
+    return HIST_PREP * sizeof(PrepRec) + (size_t)RG_RING_SCR_DOUBLES(NP, hist_dn(HSZ)) * sizeof(double) + (size_t)HSZ * sizeof(double);
+}
+
+// The table selection of every set of the chunk (stencil nodes, Lagrange weights, slice rows): one thread per set
+// instead of one thread of each hist_kernel CTA while the other 255 wait (24 FP64 divisions and rg_risco in series).
+__global__ void __launch_bounds__(128) tabsel_kernel(const SetRec *__restrict__ recs, int P, TabDesc tab, SelRec *__restrict__ sel)
+{
+    const int set = blockIdx.x * blockDim.x + threadIdx.x;
+    if (set >= P) return;
+    const SetRec &r = recs[set];
+    if (r.status != RG_S_OK) return;
+    SelRec o;
+    rg_tab_select(o.ts, tab, r.a, r.inc);
+    const double rtop = r.r_out < RG_TAB_ROUT ? r.r_out : RG_TAB_ROUT;
+    int hi = (int)floor(rg_row_pos(tab.x0, tab.dx, tab.NR, rtop)) + 1;
+    if (hi > tab.NR - 1) hi = tab.NR - 1;
+    if (hi < o.ts.s_lo + 1) hi = o.ts.s_lo + 1;
+    o.s_hi = hi;
+    o.pad = 0;
+    sel[set] = o;
 }
 
 // Persistent CTAs pull (parameter set, annulus block) items from a device queue.  The set's table slice is built by
@@ -46,15 +65,15 @@ __global__ void __launch_bounds__(32 * HIST_WARPS, MINB) hist_kernel(HistArgs A)
     RG_DYN_SMEM(smem_raw);
     constexpr int NP = 32 * NQ;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int HSZ = hist_round_up2(A.nH + 24);
-    unsigned char *wbase = smem_raw + (size_t)warp * hist_warp_bytes(A.nH, NP);
-    double *Hslot = reinterpret_cast<double *>(wbase); // 8 zero pad | nH bins | zero pad
-    const RingScr scr = rg_ring_scr(Hslot + HSZ, NP, hist_dn(HSZ));
-    PrepRec *prep = reinterpret_cast<PrepRec *>(Hslot + HSZ + hist_round_up2(RG_RING_SCR_DOUBLES(NP, hist_dn(HSZ))));
-    for (int i = lane; i < HSZ; i += 32) Hslot[i] = 0.0;
+    unsigned char *wbase = smem_raw + (size_t)warp * A.warp_bytes;
+    PrepRec *prep = reinterpret_cast<PrepRec *>(wbase);
+    double *scr_base = reinterpret_cast<double *>(wbase + HIST_PREP * sizeof(PrepRec));
+    const RingScr scr = rg_ring_scr(scr_base, NP, A.DN);
+    double *Hslot = scr_base + RG_RING_SCR_DOUBLES(NP, A.DN); // 8 zero pad | nH bins | zero pad
+    for (int i = lane; i < A.HSZ; i += 32) Hslot[i] = 0.0;
     double2 *slice = A.slices + (size_t)blockIdx.x * A.tab.NR * NP;
-    __shared__ TabSel s_ts;
-    __shared__ int s_item, s_hi;
+    __shared__ SelRec s_sel;
+    __shared__ int s_item;
     for (;;) {
         __syncthreads(); // the previous item's slice and selection have been read
         if (threadIdx.x == 0) s_item = atomicAdd(A.queue, 1);
@@ -66,17 +85,11 @@ __global__ void __launch_bounds__(32 * HIST_WARPS, MINB) hist_kernel(HistArgs A)
         if (r.status != RG_S_OK) continue;
         const int n_tot = r.n_disc + r.n_warm + r.n_hot;
         // ---- phase 1: the set's table slice
-        if (threadIdx.x == 0) {
-            rg_tab_select(s_ts, A.tab, r.a, r.inc);
-            const double rtop = r.r_out < RG_TAB_ROUT ? r.r_out : RG_TAB_ROUT;
-            int hi = (int)floor(rg_row_pos(A.tab.x0, A.tab.dx, A.tab.NR, rtop)) + 1;
-            if (hi > A.tab.NR - 1) hi = A.tab.NR - 1;
-            if (hi < s_ts.s_lo + 1) hi = s_ts.s_lo + 1;
-            s_hi = hi;
-        }
+        if (threadIdx.x < sizeof(SelRec) / 8)
+            reinterpret_cast<double *>(&s_sel)[threadIdx.x] = reinterpret_cast<const double *>(A.sel + set)[threadIdx.x];
         __syncthreads();
-        const TabSel &ts = s_ts;
-        rg_build_slice(ts, s_hi, slice, threadIdx.x, blockDim.x);
+        const TabSel &ts = s_sel.ts;
+        rg_build_slice(ts, s_sel.s_hi, slice, threadIdx.x, blockDim.x);
         __syncthreads(); // (global writes of the block are visible to the block after the barrier)
         // ---- phase 2: annulus g -> warp (blk HIST_WARPS + warp) mod (HIST_WARPS NBH)
         const int wstride = HIST_WARPS * A.NBH, w0 = blk * HIST_WARPS + warp;
@@ -131,11 +144,17 @@ __global__ void __launch_bounds__(32 * HIST_WARPS, MINB) hist_kernel(HistArgs A)
 }
 
 template <int NQ, int MINB>
-static int launch_hist(const HistArgs &A, int sm_count, cudaStream_t st)
+static int launch_hist(const HistArgs &A_in, int sm_count, cudaStream_t st)
 {
-    const size_t smem = (size_t)HIST_WARPS * hist_warp_bytes(A.nH, 32 * NQ);
+    HistArgs A = A_in;
+    A.HSZ = hist_round_up2(A.nH + 24);
+    A.DN = hist_dn(A.HSZ);
+    A.warp_bytes = (int)hist_warp_bytes(A.nH, 32 * NQ);
+    const size_t smem = (size_t)HIST_WARPS * A.warp_bytes;
     if (smem > 227 * 1024 - 1024)
         return rg_set_error(RG_E_GRID, "shift histograms: %d shift bins exceed the shared memory", A.nH);
+    RG_LAUNCH(tabsel_kernel, dim3((A.P + 127) / 128), dim3(128), 0, st, A.recs, A.P, A.tab, A.sel);
+    RG_CUDA_OK(cudaGetLastError());
     auto kern = hist_kernel<NQ, MINB>;
     RG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
@@ -149,6 +168,8 @@ static int launch_hist(const HistArgs &A, int sm_count, cudaStream_t st)
     RG_CUDA_OK(cudaGetLastError());
     return RG_OK;
 }
+
+size_t rg_selrec_bytes() { return sizeof(SelRec); }
 
 int rg_launch_hist(const HistArgs &A, int sm_count, cudaStream_t st)
 {

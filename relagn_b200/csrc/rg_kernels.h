@@ -89,8 +89,11 @@ struct HistArgs {
     double2 *slices;      // [slice_slots][NR][NPHI] scratch: the table slice of the set a resident CTA works on
     int slice_slots;
     int *queue;           // device work-queue counter (zeroed by the launcher)
+    struct SelRec *sel;   // [P] table selection of every set (tabsel_kernel)
+    int HSZ, DN, warp_bytes; // shared-memory layout of a warp (filled by the launcher)
 };
 int rg_launch_hist(const HistArgs &A, int sm_count, cudaStream_t st);
+size_t rg_selrec_bytes();
 // radial bin edges of every annulus of every set (relagn.py:731-776), one thread per (set, region): the chain of
 // repeated subtractions is walked once here instead of by every consumer lane
 int rg_launch_edges(const SetRec *recs, int P, double2 *edges, cudaStream_t st);

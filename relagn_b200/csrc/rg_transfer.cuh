@@ -31,6 +31,9 @@ struct TabSel {
     double dphi;   // 2 pi / NPHI
 };
 
+// the selection of one parameter set as tabsel_kernel leaves it for hist_kernel (a multiple of 8 bytes)
+struct SelRec { TabSel ts; int s_hi, pad; };
+
 __device__ inline void rg_lagrange_w(const double *xs, int n, double x, double *w)
 {
     for (int i = 0; i < n; i++) {
@@ -258,17 +261,17 @@ static __device__ __noinline__ void warp_deposit(double *Hs, int K_LO, int nH, d
 // ---------------------------------------------------------------------------
 // Per-warp scratch of the ring routines.
 struct RingScr {
-    double *S;   // [NP] shift of every ring sample (bins), raw column order
-    double *Wv;  // [NP] weight density of every sample
-    double *D;   // [DN] the ring's D(x) on consecutive integer shifts (see warp_ring_gather)
+    double2 *SW;  // [NP] (shift in bins, weight density) of every ring sample, raw column order
+    double *DA;   // [DN] rising-branch part of the ring's D(x) on consecutive integer shifts (see warp_ring_gather)
+    double *DB;   // [DN] falling-branch part
     int DN;
 };
-#define RG_RING_SCR_DOUBLES(NP, DN) (2 * (NP) + (DN))
+#define RG_RING_SCR_DOUBLES(NP, DN) (2 * (NP) + 2 * (DN))
 
 __device__ inline RingScr rg_ring_scr(double *base, int NP, int DN)
 {
     RingScr sc;
-    sc.S = base; sc.Wv = base + NP; sc.D = base + 2 * NP; sc.DN = DN;
+    sc.SW = reinterpret_cast<double2 *>(base); sc.DA = base + 2 * NP; sc.DB = sc.DA + DN; sc.DN = DN;
     return sc;
 }
 
@@ -302,39 +305,39 @@ template <int NQ> // NQ = NPHI / 32 segments per lane
 __device__ inline void warp_ring_gather(double *Hs, int K_LO, int nH, const RingScr &sc, double cW, int &kf_min, int &kl_max)
 {
     const int lane = threadIdx.x & 31;
-    constexpr int nq = NQ, NP = 32 * NQ, mask = NP - 1;
+    constexpr int NP = 32 * NQ, mask = NP - 1;
     // ---- extremes of the shift around the ring
-    double vmin = sc.S[lane], vmax = vmin;
+    double vmin = sc.SW[lane].x, vmax = vmin;
     int imin = lane, imax = lane;
-    for (int q = 1; q < nq; q++) {
+#pragma unroll
+    for (int q = 1; q < NQ; q++) {
         const int t = lane + 32 * q;
-        const double v = sc.S[t];
+        const double v = sc.SW[t].x;
         if (v < vmin) { vmin = v; imin = t; }
         if (v > vmax) { vmax = v; imax = t; }
     }
     imin = warp_arg_extreme(vmin, imin, false);
     imax = warp_arg_extreme(vmax, imax, true);
-    const double smin = sc.S[imin], smax = sc.S[imax];
+    const double smin = sc.SW[imin].x, smax = sc.SW[imax].x;
     const int m = (imax - imin) & mask; // rotated position of the maximum: segments [0, m) rise, [m, NP) fall
     const double xref = floor(smin);
     const int kfirst = (int)xref, klast = (int)floor(smax) + 1; // bins the hat deposit can touch
     kf_min = kfirst < kf_min ? kfirst : kf_min;
     kl_max = klast > kl_max ? klast : kl_max;
-    // ---- this lane's segments i = nq lane + q in rotated order (sample t = (imin + i) mod NP)
+    // ---- this lane's segments i = NQ lane + q in rotated order (sample t = (imin + i) mod NP)
     double r[NQ + 1], ws[NQ];
     bool ok = true;
     double l0 = 0.0, l1 = 0.0;
+    const int i0 = NQ * lane;
     {
-        const int i0 = nq * lane;
-        double wprev = sc.Wv[(imin + i0) & mask];
-        r[0] = sc.S[(imin + i0) & mask] - xref;
+        double2 sw = sc.SW[(imin + i0) & mask];
+        r[0] = sw.x - xref;
 #pragma unroll
         for (int q = 0; q < NQ; q++) {
-            const int t1 = (imin + i0 + q + 1) & mask;
-            r[q + 1] = sc.S[t1] - xref;
-            const double wn = sc.Wv[t1];
-            ws[q] = (wprev + wn) * cW;
-            wprev = wn;
+            const double2 nx = sc.SW[(imin + i0 + q + 1) & mask];
+            r[q + 1] = nx.x - xref;
+            ws[q] = (sw.y + nx.y) * cW;
+            sw = nx;
             ok = ok && (i0 + q < m ? r[q + 1] >= r[q] : r[q + 1] <= r[q]);
             l0 += ws[q];
             l1 += ws[q] * (0.5 * (r[q] + r[q + 1]));
@@ -343,9 +346,9 @@ __device__ inline void warp_ring_gather(double *Hs, int K_LO, int nH, const Ring
     ok = __all_sync(RG_FULL, ok);
     if (!ok) {
         // generic path: segments in raw column order, 32 at a time
-        for (int q = 0; q < nq; q++) {
+        for (int q = 0; q < NQ; q++) {
             const int t = lane + 32 * q, t1 = (t + 1) & mask;
-            warp_deposit(Hs, K_LO, nH, sc.S[t], sc.S[t1], (sc.Wv[t] + sc.Wv[t1]) * cW);
+            warp_deposit(Hs, K_LO, nH, sc.SW[t].x, sc.SW[t1].x, (sc.SW[t].y + sc.SW[t1].y) * cW);
         }
         __syncwarp();
         return;
@@ -364,61 +367,63 @@ __device__ inline void warp_ring_gather(double *Hs, int K_LO, int nH, const Ring
     const int x_last = klast - kfirst; // last shift with a non-zero histogram entry
     for (int xb = -1; xb + 1 <= x_last; xb += sc.DN - 2) {
         const int xe = xb + sc.DN - 1 < x_last + 1 ? xb + sc.DN - 1 : x_last + 1; // window [xb, xe]
-        // shifts outside the ring's range: nothing below it, all of it above
-        for (int xi = xb + lane; xi <= xe; xi += 32) {
+        // every segment writes D_seg(x) = c0 x - c1 + qv (x - lo)^2 at the integer shifts lo <= x < hi it holds: the
+        // rising ones into DA (c = the prefix before the segment), the falling ones into DB (c = everything after it).
+        // Each interior integer of the ring's range is written exactly once per branch.
+        int xn[NQ], xl[NQ];
+        double c0[NQ], c1[NQ], qv[NQ], lo[NQ];
+        int more = 0;
+        {
+            double q0 = p0, q1 = p1;
+#pragma unroll
+            for (int q = 0; q < NQ; q++) {
+                const double a = r[q], b = r[q + 1];
+                const bool rising = i0 + q < m;
+                const double e0 = q0, e1 = q1;
+                q0 += ws[q];
+                q1 += ws[q] * (0.5 * (a + b));
+                lo[q] = rising ? a : b;
+                const double hi = rising ? b : a, len = hi - lo[q];
+                c0[q] = rising ? e0 : tot0 - q0;
+                c1[q] = rising ? e1 : tot1 - q1;
+                qv[q] = len > 1e-12 ? (0.5 * ws[q]) * __drcp_rn(len) : 0.0;
+                int x0 = (int)ceil(lo[q]), x1 = (int)ceil(hi) - 1;
+                if (x0 < xb) x0 = xb;
+                if (x1 > xe) x1 = xe;
+                xn[q] = x0; xl[q] = x1;
+                double *dst = rising ? sc.DA : sc.DB;
+                if (x0 <= x1) {
+                    const double x = (double)x0, d = x - lo[q];
+                    dst[x0 - xb] = fma(qv[q], d * d, fma(x, c0[q], -c1[q]));
+                }
+                more |= x1 > x0;
+            }
+        }
+        if (__any_sync(RG_FULL, more)) { // segments holding more than one integer shift (steep parts of wide rings)
+#pragma unroll
+            for (int q = 0; q < NQ; q++) {
+                double *dst = (i0 + q < m) ? sc.DA : sc.DB;
+                for (int xi = xn[q] + 1; xi <= xl[q]; xi++) {
+                    const double x = (double)xi, d = x - lo[q];
+                    dst[xi - xb] = fma(qv[q], d * d, fma(x, c0[q], -c1[q]));
+                }
+            }
+        }
+        __syncwarp();
+        // one lane per shift: D (exterior shifts in closed form), then the second difference on the window's interior
+        for (int xp = xb; xp + 1 < xe; xp += 30) {
+            const int xi = xp + lane;
             const double x = (double)xi;
-            if (x <= rmin) sc.D[xi - xb] = 0.0;
-            else if (x >= rmax) sc.D[xi - xb] = x * tot0 - tot1;
-        }
-        // rising branch: the integer shifts a <= x < b inside each of this lane's segments
-        {
-            double q0 = p0, q1 = p1;
-#pragma unroll
-            for (int q = 0; q < NQ; q++) {
-                const double a = r[q], b = r[q + 1];
-                if (nq * lane + q < m && b > a) {
-                    const double len = b - a;
-                    const double qv = len > 1e-12 ? (0.5 * ws[q]) * __drcp_rn(len) : 0.0;
-                    int x0 = (int)ceil(a), x1 = (int)ceil(b) - 1;
-                    if (x0 < xb) x0 = xb;
-                    if (x1 > xe) x1 = xe;
-                    for (int xi = x0; xi <= x1; xi++) {
-                        const double x = (double)xi, d = x - a;
-                        if (x > rmin && x < rmax) sc.D[xi - xb] = (x * q0 - q1) + qv * (d * d);
-                    }
-                }
-                q0 += ws[q];
-                q1 += ws[q] * (0.5 * (a + b));
+            double D = 0.0;
+            if (xi <= xe) {
+                if (x >= rmax) D = x * tot0 - tot1;
+                else if (x > rmin) D = sc.DA[xi - xb] + sc.DB[xi - xb];
             }
-        }
-        __syncwarp();
-        // falling branch: b <= x < a; everything after this segment lies entirely below x
-        {
-            double q0 = p0, q1 = p1;
-#pragma unroll
-            for (int q = 0; q < NQ; q++) {
-                const double a = r[q], b = r[q + 1];
-                q0 += ws[q];
-                q1 += ws[q] * (0.5 * (a + b));
-                if (nq * lane + q >= m && a > b) {
-                    const double len = a - b;
-                    const double qv = len > 1e-12 ? (0.5 * ws[q]) * __drcp_rn(len) : 0.0;
-                    int x0 = (int)ceil(b), x1 = (int)ceil(a) - 1;
-                    if (x0 < xb) x0 = xb;
-                    if (x1 > xe) x1 = xe;
-                    for (int xi = x0; xi <= x1; xi++) {
-                        const double x = (double)xi, d = x - b;
-                        if (x > rmin && x < rmax) sc.D[xi - xb] += (x * (tot0 - q0) - (tot1 - q1)) + qv * (d * d);
-                    }
-                }
+            const double Dm = __shfl_up_sync(RG_FULL, D, 1), Dp = __shfl_down_sync(RG_FULL, D, 1);
+            if (lane >= 1 && lane <= 30 && xi < xe) {
+                const unsigned idx = (unsigned)(kfirst + xi - K_LO);
+                if (idx < (unsigned)nH) Hs[idx] += (Dp - D) - (D - Dm);
             }
-        }
-        __syncwarp();
-        // one lane per shift: second difference on the interior of the window
-        for (int xi = xb + 1 + lane; xi < xe; xi += 32) {
-            const double Dm = sc.D[xi - 1 - xb], D0 = sc.D[xi - xb], Dp = sc.D[xi + 1 - xb];
-            const unsigned idx = (unsigned)(kfirst + xi - K_LO);
-            if (idx < (unsigned)nH) Hs[idx] += (Dp - D0) - (D0 - Dm);
         }
         __syncwarp();
     }
@@ -456,10 +461,9 @@ __device__ inline void warp_build_rings(double *Hs, int K_LO, int nH, const TabS
 #pragma unroll
             for (int q = 0; q < NQ; q++) { a[q] = row0[lane + 32 * q]; b[q] = row1[lane + 32 * q]; }
 #pragma unroll
-            for (int q = 0; q < NQ; q++) {
-                sc.S[lane + 32 * q] = (a[q].x + geo.fr * (b[q].x - a[q].x)) * inv_dlnE + zs;
-                sc.Wv[lane + 32 * q] = a[q].y + geo.fr * (b[q].y - a[q].y);
-            }
+            for (int q = 0; q < NQ; q++)
+                sc.SW[lane + 32 * q] = make_double2((a[q].x + geo.fr * (b[q].x - a[q].x)) * inv_dlnE + zs,
+                                                    a[q].y + geo.fr * (b[q].y - a[q].y));
             __syncwarp();
             warp_ring_gather<NQ>(Hs, K_LO, nH, sc, 0.5 * ts.dphi * geo.A * weight, kf_min, kl_max);
         }

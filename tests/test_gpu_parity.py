@@ -553,7 +553,7 @@ def test_xspec_local_model_abi(ctx, oracle, otab):
     if files:
         ctx.tables_default(files[0])
         info = ctx.tables_info()
-        assert (info["n_spin"], info["n_inc"], info["NR"], info["NPHI"]) == (11, 14, 64, 64)
+        assert (info["n_spin"], info["n_inc"], info["NR"], info["NPHI"]) == (14, 14, 64, 64)
         assert np.array_equal(ctx.tables_download(), np.load(files[0]))
     with pytest.raises(Exception):
         ctx.tables_default("/nonexistent/kerr.npy")
