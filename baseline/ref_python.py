@@ -72,24 +72,43 @@ def _run(args):
     return len(params), time.perf_counter() - t0, chk
 
 
-def time_nonrel(params, grid, n_single=48, n_per_proc=24, procs=None):
+def _spawn(params, grid, tmpdir, tag):
+    """One worker process (its own interpreter: the stubs go into sys.modules there, not here)."""
+    import subprocess
+    path = os.path.join(tmpdir, "job_%s.npz" % tag)
+    np.savez(path, params=params, grid=grid)
+    return subprocess.Popen([sys.executable, os.path.abspath(__file__), "--worker", path], stdout=subprocess.PIPE,
+                            stderr=subprocess.DEVNULL, text=True, cwd=ROOT)
+
+
+def _collect(proc, timeout):
+    import json
+    out, _ = proc.communicate(timeout=timeout)
+    return json.loads(out.strip().splitlines()[-1])
+
+
+def time_nonrel(params, grid, n_single=48, n_per_proc=24, procs=None, timeout=600):
     """Spectra/s of the reference's non-relativistic path on 1 core and on `procs` cores (one process each).
     params: [P, 15] C4 sets; bounded samples: n_single sets on one core, n_per_proc sets per process."""
-    import multiprocessing as mp
+    import tempfile
     procs = procs or os.cpu_count() or 1
-    ctx = mp.get_context("spawn")
-    with ctx.Pool(1) as pool:  # (a separate process: the stubs go into sys.modules)
-        n1, t1, _ = pool.apply(_run, ((params[:n_single], grid),))
-    chunks = [params[(k * n_per_proc) % len(params):][:n_per_proc] for k in range(procs)]
-    t0 = time.perf_counter()
-    with ctx.Pool(procs) as pool:
-        res = pool.map(_run, [(c, grid) for c in chunks])
-    wall = time.perf_counter() - t0
-    nN = sum(r[0] for r in res)
-    tN = max(r[1] for r in res)  # the slowest worker's loop (imports and process start-up excluded)
-    return {"single_core": {"value": n1 / t1, "sets": n1, "seconds": t1},
+    with tempfile.TemporaryDirectory() as tmp:
+        r1 = _collect(_spawn(params[:n_single], grid, tmp, "single"), timeout)
+        t0 = time.perf_counter()
+        ps = [_spawn(params[(k * n_per_proc) % len(params):][:n_per_proc], grid, tmp, "w%d" % k) for k in range(procs)]
+        res = [_collect(p, timeout) for p in ps]
+        wall = time.perf_counter() - t0
+    nN = sum(r["n"] for r in res)
+    tN = max(r["seconds"] for r in res)  # the slowest worker's loop (imports and process start-up excluded)
+    return {"single_core": {"value": r1["n"] / r1["seconds"], "sets": r1["n"], "seconds": r1["seconds"]},
             "all_cores": {"value": nN / tN, "sets": nN, "seconds": tN, "processes": procs, "wall_with_startup": wall}}
 
 
 if __name__ == "__main__":
-    print(install_from())
+    if len(sys.argv) == 3 and sys.argv[1] == "--worker":
+        import json
+        job = np.load(sys.argv[2])
+        n, dt, chk = _run((job["params"], job["grid"]))
+        print(json.dumps({"n": int(n), "seconds": dt, "checksum": chk}))
+    else:
+        print(install_from())

@@ -214,52 +214,77 @@ def piece_edges(P, pieces=None, chunk_max=65536, piece_min=8192):
 
 
 class PeerGather:
-    """Gather of the spectra to one rank by peer-to-peer copies over NVLink (copy engines) instead of NCCL kernels:
-    every rank owns a window [world, P, nE] in torch symmetric memory, maps the destination rank's window and writes
-    its pieces straight into its own row there.  No SM is taken from the compute kernels, so the pieces can follow the
-    completion hook of rg_eval_batch_pieces.  Opt-in (evaluate_sharded(transport=PeerGather(...))): needs P2P access
-    between all GPUs of the group and a driver that exports symmetric allocations; construct it collectively."""
+    """Gather of the spectra to one rank WITHOUT a gather step: every rank owns a window [2, world, P_max, nE] in torch
+    symmetric memory and maps the destination rank's window; `evaluate_sharded(transport=...)` hands the library the
+    rank's own rows of the DESTINATION's window as the output buffer, so the spectrum kernel's epilogue stores (coalesced
+    8 kB rows) travel straight over NVLink / NVSwitch -- no NCCL kernels competing with the persistent compute
+    kernels for SMs, no copy engines, no host callbacks; one barrier closes the step.  The window is double buffered
+    (step parity): while the destination's consumers read step k, step k + 1 is written into the other half; before
+    step k + 2 reuses a half, the destination waits for everything it had enqueued when step k + 1 began.
+    Shards may differ in size (P_max = the largest, agreed at construction).  Needs P2P access between all GPUs of
+    the group and a driver that exports symmetric allocations; construct it collectively."""
 
     def __init__(self, P, nE, device, group=None, dst=0):
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
         self.group = group if group is not None else dist.group.WORLD
         self.world, self.rank, self.dst = dist.get_world_size(self.group), dist.get_rank(self.group), dst
-        self.P, self.nE = P, nE
-        self.window = symm_mem.empty((self.world, P, nE), dtype=torch.float64, device=device)
+        sizes = torch.zeros(self.world, dtype=torch.int64, device=device)
+        sizes[self.rank] = P
+        dist.all_reduce(sizes, group=self.group)
+        self.sizes = [int(v) for v in sizes.cpu()]
+        self.P, self.P_max, self.nE = P, max(self.sizes), nE
+        self.window = symm_mem.empty((2, self.world, self.P_max, nE), dtype=torch.float64, device=device)
         self.hdl = symm_mem.rendezvous(self.window, self.group)
-        self.remote = self.hdl.get_buffer(dst, (self.world, P, nE), torch.float64)
-        self.side = torch.cuda.Stream(device=device)
+        self.remote = self.hdl.get_buffer(dst, (2, self.world, self.P_max, nE), torch.float64)
+        self.step = 0
+        self.device = device
+        self._mark = [None, None]  # destination: event recorded when the step of that parity began
 
-    def put(self, piece, lo):
-        """Called after the kernels that complete `piece` (rows lo.. of the local shard) are enqueued."""
-        done = torch.cuda.Event()
-        done.record()
-        with torch.cuda.stream(self.side):
-            self.side.wait_event(done)
-            self.remote[self.rank, lo:lo + piece.shape[0]].copy_(piece, non_blocking=True)
+    def begin(self):
+        """Start of a step: returns this rank's output rows [P, nE] inside the destination's window."""
+        import torch.distributed as dist
+        half = self.step & 1
+        if self.rank == self.dst:
+            # everything enqueued on the current stream up to the start of the previous step (the consumers of the step
+            # that last used this half among it) must have finished before any rank overwrites the half
+            prev = self._mark[half ^ 1]
+            if prev is not None:
+                prev.synchronize()
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            self._mark[half] = ev
+        if self.step >= 2:
+            dist.barrier(group=self.group)
+        return self.remote[half, self.rank, :self.P]
 
     def finish(self):
-        """All pieces of all ranks have landed when this returns on the destination rank.  The returned rows are views
-        of the window: the next evaluate_sharded(transport=self) of any rank overwrites them, so the destination rank
-        consumes (or copies) them and the group synchronises before the next step is started."""
+        """All rows of all ranks have landed when this returns: on the destination rank the list of per-rank views
+        [P_r, nE] of the window half of this step (valid until the step after the next one begins)."""
         import torch.distributed as dist
-        self.side.synchronize()
+        half = self.step & 1
+        torch.cuda.current_stream(self.device).synchronize()  # this rank's stores (incl. the remote ones) are done
         dist.barrier(group=self.group)
-        return [self.window[r] for r in range(self.world)] if self.rank == self.dst else None
+        self.step += 1
+        if self.rank != self.dst:
+            return None
+        return [self.window[half, r, :self.sizes[r]] for r in range(self.world)]
 
 
 def evaluate_sharded(evaluator, params_local, rel=True, gather_dst=0, group=None, pieces=None, out=None, attrs=None,
                      gathered=None, hook=False, piece_sets=16384, transport=None):
-    """One process per GPU: every rank evaluates its own shard (device tensor [P_local, 15]); the only collective
-    is the gather of the spectra to `gather_dst` over NCCL (gather_dst=None: no gather).  The shard is evaluated in
-    contiguous pieces (`piece_edges`) and the gather of piece i is issued on a side stream while piece i+1 is
-    computed, so only the last (small) piece's transfer is exposed.  hook=True: the library evaluates the shard in its
-    own large chunks and the gathers are issued from the completion hook of rg_eval_batch_pieces instead -- measured
-    slower at 8 GPUs (156.4 against 151.9 ms per step: the NCCL kernels of eight gathers per step compete with the
-    persistent spectrum kernel for the SMs of the receiving rank), kept for transports that do not need SMs.  out / attrs / gathered: optional preallocated result tensors
-    ([P_local, nE], [P_local, 24], list of world x [P_local, nE] on the destination rank).
-    Returns (local_out, gathered or None)."""
+    """One process per GPU: every rank evaluates its own shard (device tensor [P_local, 15]); the only exchange is the
+    gather of the spectra to `gather_dst` (gather_dst=None: no gather).
+    transport=PeerGather(...): the library writes the spectra straight into the destination rank's window over
+    NVLink (see PeerGather); `out` is then ignored and the returned local spectra ARE this rank's window rows.
+    Otherwise NCCL: the shard is evaluated in contiguous pieces (`piece_edges`) and the gather of piece i is issued on a
+    side stream while piece i+1 is computed, so only the last (small) piece's transfer is exposed; shards of different
+    size are padded to the largest (one extra all-reduce of the sizes) and trimmed on the destination.  hook=True: the
+    library evaluates the shard in its own large chunks and the gathers are issued from the completion hook of
+    rg_eval_batch_pieces instead -- measured slower at 8 GPUs (the NCCL kernels of eight gathers per step compete
+    with the persistent spectrum kernel for the SMs of the receiving rank).  out / attrs / gathered: optional
+    preallocated result tensors ([P_local, nE], [P_local, 24], list of world x [P_max, nE] on the destination rank).
+    Returns (local_out, list of per-rank spectra on the destination rank or None)."""
     import torch.distributed as dist
     P = params_local.shape[0]
     multi = gather_dst is not None and dist.is_initialized() and dist.get_world_size(group) > 1
@@ -272,13 +297,23 @@ def evaluate_sharded(evaluator, params_local, rel=True, gather_dst=0, group=None
     cuda = params_local.is_cuda
     side = torch.cuda.Stream(device=params_local.device) if cuda else None
     if cuda and transport is not None:
-        # peer-to-peer transport: large chunks, every finished piece is written into the destination rank's window
-        if out is None:
-            out = torch.empty((P, evaluator.nE), dtype=torch.float64, device=params_local.device)
-        evaluator.evaluate_device_pieces(params_local, lambda lo, n: transport.put(out[lo:lo + n], lo),
-                                         piece_sets=piece_sets, rel=rel, out=out, attrs=attrs)
-        return out, transport.finish()
-    if cuda and hook and hasattr(evaluator, "evaluate_device_pieces"):
+        assert gather_dst == transport.dst, "the transport was built for destination rank %d" % transport.dst
+        assert P == transport.P, "the transport was built for a shard of %d sets, got %d" % (transport.P, P)
+        rows = transport.begin()
+        evaluator.evaluate_device(params_local, rel=rel, out=rows, attrs=attrs)
+        return rows, transport.finish()
+    # shards of different size: agree on the largest, pad the pieces, trim on the destination
+    sizes = torch.zeros(world, dtype=torch.int64, device=params_local.device)
+    sizes[rank] = P
+    dist.all_reduce(sizes, group=group)
+    sizes = [int(v) for v in sizes.cpu()]
+    P_max = max(sizes)
+
+    def trimmed(g):
+        return [g[r][:sizes[r]] for r in range(world)] if g is not None else None
+
+    nE_shape = None
+    if cuda and hook and hasattr(evaluator, "evaluate_device_pieces") and P == P_max and min(sizes) == P_max:
         # the library evaluates the shard in its own (large) chunks and reports every finished piece of the spectra:
         # its gather is issued on the side stream while the next piece is computed
         if out is None:
@@ -300,20 +335,36 @@ def evaluate_sharded(evaluator, params_local, rel=True, gather_dst=0, group=None
             w.wait()
         torch.cuda.current_stream(params_local.device).wait_stream(side)
         return out, gathered if rank == gather_dst else None
-    edges = piece_edges(P, pieces)
+    edges = piece_edges(P_max, pieces)  # the same piece plan on every rank
     outs, works = [], []
     for lo, hi in zip(edges[:-1], edges[1:]):
         if hi <= lo:
             continue
-        if out is not None:
+        mine_hi = min(hi, P)  # rows of this piece the rank really owns
+        n_mine = max(mine_hi - lo, 0)
+        if out is not None and hi <= P:
             evaluator.evaluate_device(params_local[lo:hi], rel=rel, out=out[lo:hi],
                                       attrs=None if attrs is None else attrs[lo:hi])
             piece = out[lo:hi]
         else:
-            piece = evaluator.evaluate_device(params_local[lo:hi], rel=rel)[0]
-            outs.append(piece)
+            if n_mine > 0:
+                dst_out = out[lo:mine_hi] if out is not None else None
+                got = evaluator.evaluate_device(params_local[lo:mine_hi], rel=rel, out=dst_out,
+                                                attrs=None if attrs is None else attrs[lo:mine_hi])[0]
+                if nE_shape is None:
+                    nE_shape = tuple(got.shape[1:])
+            if n_mine == hi - lo:
+                piece = got
+            else:  # short or empty piece of a smaller shard: pad with zero rows (trimmed on the destination)
+                if nE_shape is None:
+                    nE_shape = (evaluator.nE,)
+                piece = torch.zeros((hi - lo,) + nE_shape, dtype=torch.float64, device=params_local.device)
+                if n_mine > 0:
+                    piece[:n_mine] = got
+            if out is None and n_mine > 0:
+                outs.append(got)
         if rank == gather_dst and gathered is None:
-            gathered = [torch.empty((P,) + tuple(piece.shape[1:]), dtype=piece.dtype, device=piece.device)
+            gathered = [torch.empty((P_max,) + tuple(piece.shape[1:]), dtype=piece.dtype, device=piece.device)
                         for _ in range(world)]
         dst_views = [g[lo:hi] for g in gathered] if rank == gather_dst else None
         if cuda:
@@ -330,7 +381,7 @@ def evaluate_sharded(evaluator, params_local, rel=True, gather_dst=0, group=None
         torch.cuda.current_stream(params_local.device).wait_stream(side)
     if out is None:
         out = outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
-    return out, gathered if rank == gather_dst else None
+    return out, trimmed(gathered) if rank == gather_dst else None
 
 
 def fitstat_sharded(evaluator, params_local, rel=True, gather_dst=0, group=None):

@@ -15,9 +15,15 @@ from relagn_b200.batch import shard_bounds, evaluate_sharded
 class _StubEvaluator:
     """Stands in for BatchEvaluator on CPU: the 'spectrum' of a set is a deterministic function of its params."""
 
-    def evaluate_device(self, params, rel=True):
+    nE = 8
+
+    def evaluate_device(self, params, rel=True, out=None, attrs=None):
         e = torch.arange(8, dtype=torch.float64)
-        return params[:, :1] * 1000 + params[:, 2:3] + e[None, :], None
+        v = params[:, :1] * 1000 + params[:, 2:3] + e[None, :]
+        if out is not None:
+            out.copy_(v)
+            return out, None
+        return v, None
 
 
 def _free_port():
@@ -66,12 +72,14 @@ def test_piece_edges_cover_the_shard():
         assert all(n % 8192 == 0 for n in sizes[:-1])
 
 
-@pytest.mark.parametrize("P", [10, 80000])  # 80000: four shrinking pieces per rank (40000 sets each), gathered piece by piece
+# 80000: four shrinking pieces per rank (40000 sets each), gathered piece by piece.  11 and 24577: shards of different
+# size (6 + 5; 12289 + 12288 sets -- two pieces on rank 0 where rank 1 alone would plan one): padded to the largest
+# shard with the same piece plan on every rank, trimmed on the destination
+@pytest.mark.parametrize("P", [10, 11, 24577, 80000])
 def test_two_rank_gather_gloo(P):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    # equal shards: dist.gather needs equal sizes (the driver pads otherwise)
     procs = [ctx.Process(target=_worker, args=(r, 2, port, P, q)) for r in range(2)]
     for p in procs:
         p.start()
