@@ -160,8 +160,8 @@ extern "C" int rg_ctx_create(int device, rg_ctx **out)
     }
     RG_CUDA_OK(cudaMalloc(&c->d_p10, p10.size() * sizeof(double)));
     RG_CUDA_OK(cudaMemcpy(c->d_p10, p10.data(), p10.size() * sizeof(double), cudaMemcpyHostToDevice));
-    RG_CUDA_OK(cudaMalloc(&c->d_counter, 2 * sizeof(int)));
-    RG_CUDA_OK(cudaMallocHost(&c->h_counter, 2 * sizeof(int)));
+    RG_CUDA_OK(cudaMalloc(&c->d_counter, 4 * sizeof(int)));
+    RG_CUDA_OK(cudaMallocHost(&c->h_counter, 4 * sizeof(int)));
     *out = c;
     return RG_OK;
 }
@@ -755,7 +755,8 @@ static int eval_batch_impl(rg_ctx *c, const double *d_params, int P, int model, 
         c->launches += model == RG_MODEL_RELQSO ? 2 : 1;
         RG_TRY(rg_launch_counters_out(c->d_counter, c->h_counter, st)); // zero-copy store, not a D2H copy
         RG_CUDA_OK(cudaStreamSynchronize(st));
-        int nsys = c->h_counter[0];
+        const int n_warm_sys = c->h_counter[0], n_hot_sys = c->h_counter[2];
+        int nsys = n_warm_sys + n_hot_sys;
         const size_t hist_need = rel ? (size_t)c->h_counter[1] * (size_t)A.hstride : 0;
         if (nsys > c->farr_cap || hist_need * sizeof(double) > (size_t)(8e9 * (c->chunk_sets / 16384.0))) {
             if (n == 1) return rg_set_error(RG_E_NOMEM, "one parameter set needs %d Kompaneets systems (cap %d) / %zu histogram doubles", nsys, c->farr_cap, hist_need);
@@ -787,7 +788,7 @@ static int eval_batch_impl(rg_ctx *c, const double *d_params, int P, int model, 
             if (nsys <= 0) return RG_OK;
             c->launches++; // nthcomp_interp_kernel
             RG_TRY(prof_begin(c, 1, st));
-            RG_TRY(rg_launch_nthcomp(c->d_recs, c->d_syslist, nsys, c->d_p10, c->d_sc,
+            RG_TRY(rg_launch_nthcomp(c->d_recs, c->d_syslist, n_warm_sys, n_hot_sys, c->farr_cap, c->d_p10, c->d_sc,
                                      c->d_sc + (size_t)RG_NTH * c->nth_threads,
                                      c->d_sc + (size_t)2 * RG_NTH * c->nth_threads, nth_run, c->d_sptot,
                                      c->d_header, c->gd, c->d_farr, stats, st));

@@ -56,90 +56,121 @@ __global__ void __launch_bounds__(128) tabsel_kernel(const SetRec *__restrict__ 
 }
 
 // Persistent CTAs pull (parameter set, annulus block) items from a device queue.  The set's table slice is built by
-// the whole CTA into the CTA's own scratch region of a global arena (64 kB per resident CTA: it never leaves L2) --
-// in shared memory it would cap the kernel at 16 warps per SM, and the ring routine is a chain of dependent
+// the whole CTA into the CTA's own scratch region of a global arena (2 x 64 kB per resident CTA: it never leaves
+// L2) -- in shared memory it would cap the kernel at 16 warps per SM, and the ring routine is a chain of dependent
 // shared-memory and shuffle steps that needs the warps to hide its latency.
+// Software pipeline, ONE block barrier per item: in iteration k every warp walks its annuli of item k (slice half
+// k & 1) and then, without waiting for the other warps, builds its share of the slice of item k + 1 into the other
+// half; warp 0 meanwhile fetches item k + 2 from the queue and loads its table selection (three slots).
 template <int NQ, int MINB>
 __global__ void __launch_bounds__(32 * HIST_WARPS, MINB) hist_kernel(HistArgs A)
 {
     RG_DYN_SMEM(smem_raw);
     constexpr int NP = 32 * NQ;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
     unsigned char *wbase = smem_raw + (size_t)warp * A.warp_bytes;
+    // (the lane index and the warp's base are used all over the ring routine: opaque to the compiler from here on, so
+    //  that it keeps them in registers instead of rebuilding them from the thread index at every use -- 7 % of the
+    //  kernel's instructions in profiles/r2c)
+    asm volatile("" : "+r"(lane));
+    asm volatile("" : "+l"(wbase));
     PrepRec *prep = reinterpret_cast<PrepRec *>(wbase);
     double *scr_base = reinterpret_cast<double *>(wbase + HIST_PREP * sizeof(PrepRec));
     const RingScr scr = rg_ring_scr(scr_base, NP, A.DN);
     double *Hslot = scr_base + RG_RING_SCR_DOUBLES(NP, A.DN); // 8 zero pad | nH bins | zero pad
     for (int i = lane; i < A.HSZ; i += 32) Hslot[i] = 0.0;
-    double2 *slice = A.slices + (size_t)blockIdx.x * A.tab.NR * NP;
-    __shared__ SelRec s_sel;
-    __shared__ int s_item;
-    for (;;) {
-        __syncthreads(); // the previous item's slice and selection have been read
-        if (threadIdx.x == 0) s_item = atomicAdd(A.queue, 1);
-        __syncthreads();
-        const int item = s_item;
-        if (item >= A.P * A.NBH) break;
-        const int set = item / A.NBH, blk = item - set * A.NBH;
-        const SetRec &r = A.recs[set];
-        if (r.status != RG_S_OK) continue;
-        const int n_tot = r.n_disc + r.n_warm + r.n_hot;
-        // ---- phase 1: the set's table slice
-        if (threadIdx.x < sizeof(SelRec) / 8)
-            reinterpret_cast<double *>(&s_sel)[threadIdx.x] = reinterpret_cast<const double *>(A.sel + set)[threadIdx.x];
-        __syncthreads();
-        const TabSel &ts = s_sel.ts;
-        rg_build_slice(ts, s_sel.s_hi, slice, threadIdx.x, blockDim.x);
-        __syncthreads(); // (global writes of the block are visible to the block after the barrier)
-        // ---- phase 2: annulus g -> warp (blk HIST_WARPS + warp) mod (HIST_WARPS NBH)
-        const int wstride = HIST_WARPS * A.NBH, w0 = blk * HIST_WARPS + warp;
-        const int n_mine = w0 < n_tot ? (n_tot - w0 + wstride - 1) / wstride : 0;
-        for (int m0 = 0; m0 < n_mine; m0 += HIST_PREP) {
-            // lane m prepares this warp's annulus number m0 + m: its edges (relagn.py:731-776, :962-964) and whether
-            // the reference sends it through kyconv (:992)
-            __syncwarp(); // the previous pass has been read
-            if (lane < HIST_PREP && m0 + lane < n_mine) {
-                PrepRec pr;
-                pr.r1 = 0; pr.r2 = 0; pr.flag = 0; pr.g = 0; pr.nsub = 1; pr.pad = 0;
-                pr.geo.A = 0; pr.geo.fr = 0; pr.geo.s0 = ts.s_lo; // of the annulus' only ring when nsub == 1 (most annuli)
-                const int g = w0 + wstride * (m0 + lane);
-                const double2 eg = __ldg(A.edges + r.ann_base + g); // (lo, hi) in log10 r (edges_kernel)
-                const double lo = eg.x, hi = eg.y;
-                pr.r1 = pow(10.0, lo); pr.r2 = pow(10.0, hi);
-                pr.flag = (lo <= 3 && hi <= 3) ? 1 : 0;
-                pr.g = g;
-                if (pr.flag) {
-                    const double lnr = log(pr.r2 / pr.r1);
-                    pr.nsub = rg_auto_nsub(pr.r1, pr.r2, lnr, A.dlnE);
-                    if (pr.nsub == 1) pr.geo = rg_ring_geo(ts, pr.r1, pr.r2, lnr, 0, 1, 0.0, 0.0, 1.0);
-                }
-                prep[lane] = pr;
-            }
-            __syncwarp();
-            const int mt = n_mine - m0 < HIST_PREP ? n_mine - m0 : HIST_PREP;
-            for (int mi = 0; mi < mt; mi++) {
-                const double r1 = prep[mi].r1, r2 = prep[mi].r2;
-                const int flag = prep[mi].flag, g = prep[mi].g, nsub = prep[mi].nsub;
-                const RingGeo geo = prep[mi].geo;
-                double *row = A.hist + (size_t)(r.ann_base + g) * A.hstride;
-                int kmn = 0, kmx = -1;
-                if (flag && ts.status == 0) {
-                    warp_build_rings<NQ>(Hslot + 8, A.K_LO, A.nH, ts, slice, scr, r1, r2, A.inv_dlnE, nsub, 0, 1, 0.0, 0.0,
-                                         1.0, 0.0, 1.0, kmn, kmx, nsub == 1 ? &geo : nullptr);
-                    if (kmn < A.K_LO) kmn = A.K_LO;
-                    if (kmx > A.K_LO + A.nH - 1) kmx = A.K_LO + A.nH - 1;
-                    __syncwarp();
-                }
-                const int nk = kmx >= kmn ? kmx - kmn + 1 : 0;
-                if (lane == 0) *reinterpret_cast<int2 *>(row) = make_int2(kmn, nk);
-                for (int k = lane; k < nk; k += 32) {
-                    const int q = 8 + kmn - A.K_LO + k;
-                    row[1 + k] = Hslot[q];
-                    Hslot[q] = 0.0; // leave the slot clean for the next annulus
-                }
-                __syncwarp();
+    double2 *slice2 = A.slices + (size_t)2 * blockIdx.x * A.tab.NR * NP; // two halves
+    const size_t slice_elems = (size_t)A.tab.NR * NP;
+    __shared__ SelRec s_sel[3];
+    __shared__ int s_items[3];
+    const int n_items = A.P * A.NBH;
+    // warp 0: next item from the queue and its table selection into slot `slot`
+    auto fetch = [&](int slot) {
+        int id = 0;
+        if (lane == 0) id = atomicAdd(A.queue, 1);
+        id = __shfl_sync(RG_FULL, id, 0);
+        if (lane == 0) s_items[slot] = id;
+        if (id < n_items) {
+            const int set = id / A.NBH;
+            if (A.recs[set].status == RG_S_OK) {
+                const double *src = reinterpret_cast<const double *>(A.sel + set);
+                double *dst = reinterpret_cast<double *>(&s_sel[slot]);
+                for (int i = lane; i < (int)(sizeof(SelRec) / 8); i += 32) dst[i] = src[i];
             }
         }
+    };
+    auto build = [&](int slot, int half) {
+        const int id = s_items[slot];
+        if (id >= n_items) return;
+        if (A.recs[id / A.NBH].status != RG_S_OK) return;
+        rg_build_slice(s_sel[slot].ts, s_sel[slot].s_hi, slice2 + half * slice_elems, threadIdx.x, blockDim.x);
+    };
+    if (warp == 0) { fetch(0); fetch(1); }
+    __syncthreads();
+    build(0, 0);
+    for (int k = 0;; k++) {
+        __syncthreads(); // half k & 1 is complete, the slots of items k and k + 1 are filled, iteration k - 1 is over
+        const int item = s_items[k % 3];
+        if (item >= n_items) break;
+        if (warp == 0) fetch((k + 2) % 3);
+        const int set = item / A.NBH, blk = item - set * A.NBH;
+        const SetRec &r = A.recs[set];
+        if (r.status == RG_S_OK) {
+            const TabSel &ts = s_sel[k % 3].ts;
+            const double2 *slice = slice2 + (k & 1) * slice_elems;
+            const int n_tot = r.n_disc + r.n_warm + r.n_hot;
+            // annulus g -> warp (blk HIST_WARPS + warp) mod (HIST_WARPS NBH)
+            const int wstride = HIST_WARPS * A.NBH, w0 = blk * HIST_WARPS + warp;
+            const int n_mine = w0 < n_tot ? (n_tot - w0 + wstride - 1) / wstride : 0;
+            for (int m0 = 0; m0 < n_mine; m0 += HIST_PREP) {
+                // lane m prepares this warp's annulus number m0 + m: its edges (relagn.py:731-776, :962-964) and
+                // whether the reference sends it through kyconv (:992)
+                __syncwarp(); // the previous pass has been read
+                if (lane < HIST_PREP && m0 + lane < n_mine) {
+                    PrepRec pr;
+                    pr.r1 = 0; pr.r2 = 0; pr.flag = 0; pr.g = 0; pr.nsub = 1; pr.pad = 0;
+                    pr.geo.A = 0; pr.geo.fr = 0; pr.geo.s0 = ts.s_lo; // of the annulus' only ring when nsub == 1 (most annuli)
+                    const int g = w0 + wstride * (m0 + lane);
+                    const double2 eg = __ldg(A.edges + r.ann_base + g); // (lo, hi) in log10 r (edges_kernel)
+                    const double lo = eg.x, hi = eg.y;
+                    pr.r1 = pow(10.0, lo); pr.r2 = pow(10.0, hi);
+                    pr.flag = (lo <= 3 && hi <= 3) ? 1 : 0;
+                    pr.g = g;
+                    if (pr.flag) {
+                        const double lnr = log(pr.r2 / pr.r1);
+                        pr.nsub = rg_auto_nsub(pr.r1, pr.r2, lnr, A.dlnE);
+                        if (pr.nsub == 1) pr.geo = rg_ring_geo(ts, pr.r1, pr.r2, lnr, 0, 1, 0.0, 0.0, 1.0);
+                    }
+                    prep[lane] = pr;
+                }
+                __syncwarp();
+                const int mt = n_mine - m0 < HIST_PREP ? n_mine - m0 : HIST_PREP;
+                for (int mi = 0; mi < mt; mi++) {
+                    const double r1 = prep[mi].r1, r2 = prep[mi].r2;
+                    const int flag = prep[mi].flag, g = prep[mi].g, nsub = prep[mi].nsub;
+                    const RingGeo geo = prep[mi].geo;
+                    double *row = A.hist + (size_t)(r.ann_base + g) * A.hstride;
+                    int kmn = 0, kmx = -1;
+                    if (flag && ts.status == 0) {
+                        warp_build_rings<NQ>(Hslot + 8, A.K_LO, A.nH, ts, slice, scr, r1, r2, A.inv_dlnE, nsub, 0, 1, 0.0,
+                                             0.0, 1.0, 0.0, 1.0, kmn, kmx, nsub == 1 ? &geo : nullptr);
+                        if (kmn < A.K_LO) kmn = A.K_LO;
+                        if (kmx > A.K_LO + A.nH - 1) kmx = A.K_LO + A.nH - 1;
+                        __syncwarp();
+                    }
+                    const int nk = kmx >= kmn ? kmx - kmn + 1 : 0;
+                    if (lane == 0) *reinterpret_cast<int2 *>(row) = make_int2(kmn, nk);
+                    for (int q = lane; q < nk; q += 32) {
+                        const int i = 8 + kmn - A.K_LO + q;
+                        row[1 + q] = Hslot[i];
+                        Hslot[i] = 0.0; // leave the slot clean for the next annulus
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        build((k + 1) % 3, (k + 1) & 1);
     }
 }
 
@@ -162,7 +193,7 @@ static int launch_hist(const HistArgs &A_in, int sm_count, cudaStream_t st)
     if (per_sm < 1) per_sm = 1;
     long ctas = (long)A.P * A.NBH;
     if (ctas > (long)sm_count * per_sm) ctas = (long)sm_count * per_sm;
-    if (ctas > A.slice_slots) ctas = A.slice_slots;
+    if (ctas > A.slice_slots / 2) ctas = A.slice_slots / 2; // two slice halves per CTA
     RG_CUDA_OK(cudaMemsetAsync(A.queue, 0, sizeof(int), st));
     RG_LAUNCH(kern, dim3((unsigned)ctas), dim3(32 * HIST_WARPS), smem, st, A);
     RG_CUDA_OK(cudaGetLastError());

@@ -69,7 +69,8 @@ int rg_launch_setup(const double *d_params, int P, int model, double dr_dex, Set
                     int2 *syslist, int sys_cap, double *rq_scratch, int rq_cap, double *d_attrs, cudaStream_t st);
 
 // persistent: n_threads = total launched threads = rows of the [RG_NTH][n_threads] scratch planes
-int rg_launch_nthcomp(const SetRec *recs, const int2 *syslist, int nsys, const double *p10tab, double *sc_gam,
+int rg_launch_nthcomp(const SetRec *recs, const int2 *syslist, int n_warm_sys, int n_hot_sys, int sys_cap,
+                      const double *p10tab, double *sc_gam,
                       double *sc_g, double *sc_bet, int n_threads, double *sptot, double *header,
                       const GridDesc &grid, double *farr, unsigned long long *stats, cudaStream_t st);
 

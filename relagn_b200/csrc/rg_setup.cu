@@ -250,14 +250,21 @@ setup_kernel(const double *__restrict__ params, int P, int model, double dr_dex,
         }
         r.ann_base = atomicAdd(sys_counter + 1, r.n_disc + r.n_warm + r.n_hot); // rows of the shift-histogram arena
         int need_hot = (r.n_hot > 0 && r.has_hotshape) ? 1 : 0;
-        int nsys = r.n_warm + need_hot;
         r.sys_base = 0;
-        if (nsys > 0) {
-            int base = atomicAdd(sys_counter, nsys);
+        r.hot_sys = 0;
+        // warm systems from the bottom of the arena, hot shapes from the top (the host checks that the two did not meet)
+        if (r.n_warm > 0) {
+            int base = atomicAdd(sys_counter, r.n_warm);
             r.sys_base = base;
-            if (base + nsys <= sys_cap) {
+            if (base + r.n_warm <= sys_cap) {
                 for (int s = 0; s < r.n_warm; s++) syslist[base + s] = make_int2(idx, s);
-                if (need_hot) syslist[base + r.n_warm] = make_int2(idx, -1);
+            } else status = RG_S_CAP;
+        }
+        if (need_hot) {
+            int k = atomicAdd(sys_counter + 2, 1);
+            if (k < sys_cap) {
+                r.hot_sys = sys_cap - 1 - k;
+                syslist[r.hot_sys] = make_int2(idx, -1);
             } else status = RG_S_CAP;
         }
     }
@@ -483,7 +490,8 @@ __device__ static void nthcomp_system(bool valid, const SetRec &r, int which, co
 }
 
 __global__ void __launch_bounds__(128, RG_NTH_MINB)
-nthcomp_kernel(const SetRec *__restrict__ recs, const int2 *__restrict__ syslist, int nsys,
+nthcomp_kernel(const SetRec *__restrict__ recs, const int2 *__restrict__ syslist, int nsys, int n_warm_sys, int n_warm_pad,
+               int hot_first,
                const double *__restrict__ p10tab, double *__restrict__ sc_gam, double *__restrict__ sc_g,
                double *__restrict__ sc_bet, int n_threads, double *__restrict__ sptot, double *__restrict__ header,
                unsigned long long *stats)
@@ -501,8 +509,10 @@ nthcomp_kernel(const SetRec *__restrict__ recs, const int2 *__restrict__ syslist
     unsigned long long sumj = 0, nsolved = 0;
     const int lane = threadIdx.x & 31;
     for (int s0 = gtid - lane; s0 < nsys; s0 += n_threads) { // warp-uniform trip count: the lanes solve together
-        const int sys = s0 + lane;
-        bool valid = sys < nsys;
+        // logical index -> arena row: the warm systems fill rows [0, n_warm_sys), the hot shapes the top of the arena
+        const int li = s0 + lane;
+        bool valid = li < nsys && (li < n_warm_sys || li >= n_warm_pad);
+        const int sys = li < n_warm_pad ? li : hot_first + (li - n_warm_pad);
         int2 ent = valid ? syslist[sys] : make_int2(0, 0);
         const SetRec &r = recs[ent.x];
         valid = valid && r.status == RG_S_OK;
@@ -525,8 +535,8 @@ nthcomp_kernel(const SetRec *__restrict__ recs, const int2 *__restrict__ syslist
 // The reference's monotone cursor is restated as a direct search seeded from log10(E) and fixed up with the
 // reference's own comparisons, so every bin lands in exactly the cell the cursor would have reached.
 __global__ void __launch_bounds__(256)
-nthcomp_interp_kernel(const SetRec *__restrict__ recs, const int2 *__restrict__ syslist, int nsys,
-                      const double *__restrict__ p10tab, const double *__restrict__ sptot,
+nthcomp_interp_kernel(const SetRec *__restrict__ recs, const int2 *__restrict__ syslist, int nsys, int n_warm_sys,
+                      int n_warm_pad, int hot_first, const double *__restrict__ p10tab, const double *__restrict__ sptot,
                       const double *__restrict__ header, GridDesc grid, double *__restrict__ farr)
 {
     __shared__ double s_p10[RG_NTH + 4];
@@ -535,8 +545,9 @@ nthcomp_interp_kernel(const SetRec *__restrict__ recs, const int2 *__restrict__ 
     for (int i = threadIdx.x; i < RG_NTH + 3; i += blockDim.x) s_rdp[i] = p10tab[RG_P10_RDP + i];
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const int sys = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (sys >= nsys) return;
+    const int li = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (li >= nsys || (li >= n_warm_sys && li < n_warm_pad)) return;
+    const int sys = li < n_warm_pad ? li : hot_first + (li - n_warm_pad);
     if (recs[syslist[sys].x].status != RG_S_OK) return;
     const double *hd = header + (size_t)sys * 4;
     const double xmin = hd[0], normfac = hd[1], lgx = hd[3];
@@ -586,7 +597,7 @@ nthcomp_interp_kernel(const SetRec *__restrict__ recs, const int2 *__restrict__ 
 int rg_launch_setup(const double *d_params, int P, int model, double dr_dex, SetRec *recs, int *sys_counter,
                     int2 *syslist, int sys_cap, double *rq_scratch, int rq_cap, double *d_attrs, cudaStream_t st)
 {
-    RG_CUDA_OK(cudaMemsetAsync(sys_counter, 0, 2 * sizeof(int), st)); // [0] Kompaneets systems, [1] annuli
+    RG_CUDA_OK(cudaMemsetAsync(sys_counter, 0, 3 * sizeof(int), st)); // [0] warm Kompaneets systems, [1] annuli, [2] hot shapes
     if (model == RG_MODEL_RELQSO) {
         RG_LAUNCH(relqso_rhot_kernel, dim3(P), dim3(128), 0, st, d_params, P, rq_scratch);
         RG_CUDA_OK(cudaGetLastError());
@@ -635,6 +646,7 @@ __global__ void counters_out_kernel(const int *__restrict__ ctr, int *__restrict
 {
     host_mapped[0] = ctr[0];
     host_mapped[1] = ctr[1];
+    host_mapped[2] = ctr[2];
     __threadfence_system();
 }
 
@@ -645,18 +657,23 @@ int rg_launch_counters_out(const int *d_counter, int *h_mapped, cudaStream_t st)
     return RG_OK;
 }
 
-int rg_launch_nthcomp(const SetRec *recs, const int2 *syslist, int nsys, const double *p10tab, double *sc_gam,
+int rg_launch_nthcomp(const SetRec *recs, const int2 *syslist, int n_warm_sys, int n_hot_sys, int sys_cap,
+                      const double *p10tab, double *sc_gam,
                       double *sc_g, double *sc_bet, int n_threads, double *sptot, double *header,
                       const GridDesc &grid, double *farr, unsigned long long *stats, cudaStream_t st)
 {
+    // logical order: the warm systems, padded to a whole warp, then the hot shapes -- no warp mixes the two kinds
+    const int n_warm_pad = (n_warm_sys + 31) & ~31;
+    const int nsys = n_hot_sys > 0 ? n_warm_pad + n_hot_sys : n_warm_sys;
+    const int hot_first = sys_cap - n_hot_sys;
     if (nsys <= 0) return RG_OK;
     int blocks = (nsys + 127) / 128;
     if (blocks * 128 > n_threads) blocks = n_threads / 128;
-    RG_LAUNCH(nthcomp_kernel, dim3(blocks), dim3(128), 0, st, recs, syslist, nsys, p10tab, sc_gam, sc_g, sc_bet,
+    RG_LAUNCH(nthcomp_kernel, dim3(blocks), dim3(128), 0, st, recs, syslist, nsys, n_warm_sys, n_warm_pad, hot_first, p10tab, sc_gam, sc_g, sc_bet,
               blocks * 128, sptot, header, stats);
     RG_CUDA_OK(cudaGetLastError());
     RG_LAUNCH(nthcomp_interp_kernel, dim3((unsigned)(((size_t)nsys * 32 + 255) / 256)), dim3(256), 0, st, recs, syslist,
-              nsys, p10tab, sptot, header, grid, farr);
+              nsys, n_warm_sys, n_warm_pad, hot_first, p10tab, sptot, header, grid, farr);
     RG_CUDA_OK(cudaGetLastError());
     return RG_OK;
 }

@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(NC <= 4 ? (sizeof(R) == 4 ? 512 : 32 * RG_SPEC
         double shape_int = 0.0;
         const double *hot_F = nullptr;
         if (need_shape) {
-            if (r.has_hotshape) hot_F = A.farr + (size_t)(r.sys_base + r.n_warm) * nE;
+            if (r.has_hotshape) hot_F = A.farr + (size_t)r.hot_sys * nE;
             double part = 0;
             if (hot_F)
                 for (int j = tid; j < nE; j += nthreads) part += __ldg(hot_F + j) * __ldg(A.grid.wt + j);
