@@ -244,6 +244,12 @@ int rg_xspec_bind(rg_ctx *ctx);
 int rg_tables_default(rg_ctx *ctx, const char *npy_path);
 
 /* number of kernels launched by this context so far (for accounting) */
+/* Fnu_seed_hot (relagn.py:1200-1223; an attribute of the reference's class): the hot corona's Comptonised spectral
+ * shape of parameter set `set` of the LAST evaluated batch on the energy grid, W/Hz-shaped, nE doubles on the host;
+ * zeros when the seed temperature is not below kTe_hot or the set has no hot region.  Valid for sets of the last
+ * chunk of the last rg_eval_batch* call (any batch of <= 4096 sets is one chunk). */
+int rg_last_hot_shape(rg_ctx *ctx, int set, double *out_host);
+
 long rg_launch_count(rg_ctx *ctx);
 
 /* ---- instrumentation (bench.py's roofline block) ----

@@ -59,6 +59,8 @@ def lib():
     L.ro_eval_batch.restype = None
     L.ro_eval_batch.argtypes = [_dp, C.c_int, C.c_int, C.c_double, _dp, C.c_int, C.c_int, C.c_void_p, _dp, _dp, _ip,
                                 C.c_int]
+    L.ro_hot_shape.restype = C.c_int
+    L.ro_hot_shape.argtypes = [_dp, C.c_int, C.c_double, _dp, C.c_int, _dp]
     L.ro_setup.restype = C.c_int
     L.ro_setup.argtypes = [_dp, C.c_int, C.c_double, _dp]
     L.ro_trace_ray.restype = C.c_int
@@ -215,6 +217,16 @@ def setup(params, model=0, dr_dex=50.0):
     at = np.zeros(NATTR)
     st = lib().ro_setup(p, model, dr_dex, at)
     return st, dict(zip(ATTR_NAMES, at))
+
+
+def hot_shape(params, ebins, model=0, dr_dex=50.0):
+    """Fnu_seed_hot (relagn.py:1200-1223) of one parameter set on the grid."""
+    p = np.zeros(NPAR)
+    p[:len(params)] = params
+    ebins = np.ascontiguousarray(ebins, dtype=np.float64)
+    F = np.zeros(ebins.size - 1)
+    lib().ro_hot_shape(p, model, dr_dex, ebins, ebins.size - 1, F)
+    return F
 
 
 def evaluate(params, ebins, model=0, rel=False, tab=None, dr_dex=50.0):

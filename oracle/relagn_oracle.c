@@ -590,6 +590,20 @@ static int ky_annulus(const model_t *m, const grid_t *g, const ro_tables *tab,
     return 0;
 }
 
+/* Fnu_seed_hot (relagn.py:1200-1223): the hot corona's spectral shape on the grid; zeros without a hot region */
+int ro_hot_shape(const double *params, int model, double dr_dex, const double *ebins, int nE, double *F)
+{
+    model_t m;
+    memset(F, 0, sizeof(double) * nE);
+    int st = m_init(&m, params, model, dr_dex);
+    if (st != RO_OK) return st;
+    grid_t g;
+    grid_init(&g, ebins, nE);
+    if (m.r_h != m.risco || model == 1) hot_shape(&m, &g, F);
+    grid_free(&g);
+    return RO_OK;
+}
+
 int ro_eval(const double *params, int model, double dr_dex, const double *ebins,
             int nE, int rel, const ro_tables *tab, double *out, double *attrs)
 {

@@ -30,7 +30,7 @@ SYMBOLS = ["rg_version", "rg_last_error", "rg_ctx_create", "rg_ctx_destroy", "rg
            "rg_eval_batch_pieces", "rg_eval_batch_host", "rg_launch_count", "rg_measure_fp64_peak", "rg_set_option", "rg_get_stat",
            "rg_reset_stats", "rg_convert_batch", "rg_set_instrument", "rg_photar_batch", "rg_set_response",
            "rg_set_data", "rg_fitstat_batch", "rg_eval_fitstat_batch", "rg_eval_fitstat_batch_host",
-           "rg_xspec_eval", "rg_xspec_bind", "rg_tables_default"]
+           "rg_xspec_eval", "rg_xspec_bind", "rg_tables_default", "rg_last_hot_shape"]
 XSPEC_SYMBOLS = ["relagn_", "relqso_"]  # gfortran names of the XSPEC local models (seam B3)
 
 UNITS = {"SI": 0, "cgs": 1, "cgs_wave": 2, "SI_wave": 3, "counts": 4}  # RG_UNIT_*
@@ -85,6 +85,8 @@ def bind(lib):
                                          C.c_void_p, C.c_void_p, C.c_int, PIECE_FN, C.c_void_p]
     lib.rg_eval_batch_host.restype = C.c_int
     lib.rg_eval_batch_host.argtypes = [C.c_void_p, _dp, C.c_int, C.c_int, C.c_double, C.c_uint, _dp, _dp]
+    lib.rg_last_hot_shape.restype = C.c_int
+    lib.rg_last_hot_shape.argtypes = [C.c_void_p, C.c_int, _dp]
     lib.rg_launch_count.restype = C.c_long
     lib.rg_launch_count.argtypes = [C.c_void_p]
     lib.rg_measure_fp64_peak.restype = C.c_int
@@ -385,6 +387,12 @@ class Context:
         for name, key in STATS.items():
             self._check(self.lib.rg_get_stat(self.h, key, C.byref(v)))
             out[name] = v.value
+        return out
+
+    def last_hot_shape(self, set_index=0):
+        """Fnu_seed_hot (relagn.py:1200-1223) of a set of the last evaluated batch."""
+        out = np.zeros(self.nE)
+        self._check(self.lib.rg_last_hot_shape(self.h, int(set_index), _d(out)))
         return out
 
     def launch_count(self):

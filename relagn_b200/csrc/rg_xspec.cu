@@ -36,7 +36,7 @@ struct XsState {
     int oldmodel = -1;
     unsigned oldflags = 0;
     std::vector<double> photar;           // memoised result on `ear`
-    double *d_par = nullptr, *d_lnu = nullptr, *d_pho = nullptr;
+    double *d_par = nullptr, *d_lnu = nullptr, *d_pho = nullptr, *d_attr = nullptr;
     size_t pho_cap = 0;
 };
 XsState g_xs;
@@ -90,6 +90,8 @@ extern "C" int rg_xspec_bind(rg_ctx *ctx)
 {
     if (g_xs.d_par) cudaFree(g_xs.d_par);
     if (g_xs.d_lnu) cudaFree(g_xs.d_lnu);
+    if (g_xs.d_attr) cudaFree(g_xs.d_attr);
+    g_xs.d_attr = nullptr;
     if (g_xs.d_pho) cudaFree(g_xs.d_pho);
     if (g_xs.own_ctx && g_xs.ctx) rg_ctx_destroy(g_xs.ctx);
     g_xs = XsState(); // (while bound, the context's model and instrument grids belong to the XSPEC entry points)
@@ -142,8 +144,24 @@ extern "C" int rg_xspec_eval(int model, unsigned flags, const double *ear, int n
                 return rg_set_error(RG_E_NOMEM, "rg_xspec_eval: device allocation failed");
             S.pho_cap = ne;
         }
+        if (!S.d_attr && cudaMalloc(&S.d_attr, RG_NATTR * sizeof(double)) != cudaSuccess)
+            return rg_set_error(RG_E_NOMEM, "rg_xspec_eval: device allocation failed");
         RG_CUDA_OK(cudaMemcpy(S.d_par, par, RG_NPAR * sizeof(double), cudaMemcpyHostToDevice));
-        RG_TRY_XS(rg_eval_batch(S.ctx, S.d_par, 1, model, 50.0, flags, S.d_lnu, nullptr, nullptr));
+        RG_TRY_XS(rg_eval_batch(S.ctx, S.d_par, 1, model, 50.0, flags, S.d_lnu, S.d_attr, nullptr));
+        {
+            // the reference raises ValueError for these parameter sets (relagn.py:372-386, 1861-1874); XSPEC gets an
+            // error return (zeros + a message from the caller) instead of a silently memoised all-zero spectrum
+            double at[RG_NATTR];
+            RG_CUDA_OK(cudaMemcpy(at, S.d_attr, sizeof at, cudaMemcpyDeviceToHost));
+            const int st = (int)at[RG_A_STATUS];
+            if (st != RG_S_OK) {
+                S.oldpar.clear();
+                return rg_set_error(RG_E_ARG, "parameter set rejected: %s",
+                                    st == RG_S_SPIN ? "spin outside -0.998 <= a <= 0.998"
+                                    : st == RG_S_INC ? "inclination outside 0.09 <= cos(inc) <= 1"
+                                    : st == RG_S_MDOT ? "log mdot outside -1.65 ... 0.5" : "arena capacity");
+            }
+        }
         RG_TRY_XS(rg_photar_batch(S.ctx, S.d_lnu, S.d_par, 1, model, S.d_pho, nullptr));
         S.photar.resize(ne);
         RG_CUDA_OK(cudaMemcpy(S.photar.data(), S.d_pho, (size_t)ne * sizeof(double), cudaMemcpyDeviceToHost));

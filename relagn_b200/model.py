@@ -133,6 +133,8 @@ class relagn:
         p = np.zeros((1, _capi.NPAR))
         p[0, :len(self._params)] = self._params
         out, at = ctx.eval_batch_host(p, model=self._model, rel=rel, components=True, dr_dex=float(self.dr_dex))
+        # the hot corona's spectral shape (relagn.py:1200-1223), a public attribute of the reference's class
+        self.Fnu_seed_hot = ctx.last_hot_shape(0)
         return out[0], at[0]
 
     def _evaluate_setup(self):

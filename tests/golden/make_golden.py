@@ -137,12 +137,14 @@ def main():
     store = {"grid1000": grid1000, "grid_def": grid_def, "attr_names": np.array(ATTRS)}
     for model, cases in ((0, relagn_cases()), (1, relqso_cases())):
         tag = "relagn" if model == 0 else "relqso"
-        names, P, A, S1000, Sdef, extra = [], [], [], [], [], []
+        names, P, A, S1000, Sdef, extra, Fhot = [], [], [], [], [], [], []
         for name, pars in cases:
             o = build(ref, model, pars, grid1000)
             at = [float(getattr(o, k)) for k in ATTRS]
             nb = [len(o.logr_ad_bins), len(o.logr_wc_bins), len(o.logr_hc_bins)]
             S1000.append(components(o, False))
+            # the hot corona's spectral shape (relagn.py:1200-1223): only set when a hot region exists (:356-357)
+            Fhot.append(np.array(getattr(o, "Fnu_seed_hot", np.zeros(len(grid1000) - 1)), dtype=np.float64))
             with contextlib.redirect_stdout(io.StringIO()):
                 o.hotCorona_lumin()
             extra.append([o.Ldiss, o.Lseed] + nb)
@@ -157,6 +159,7 @@ def main():
         store[tag + "_attrs"] = np.array(A)
         store[tag + "_extra"] = np.array(extra)
         store[tag + "_spec1000"] = np.array(S1000)
+        store[tag + "_fnu_seed_hot1000"] = np.array(Fhot)
         store[tag + "_specdef"] = np.array(Sdef)
     np.savez_compressed(os.path.join(HERE, "golden_nonrel.npz"), **store)
 

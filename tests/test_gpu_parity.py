@@ -192,6 +192,26 @@ def test_offnode_self_consistency_default_tables(ctx, oracle):
     upload_golden_tables(ctx)
 
 
+def test_hot_spectral_shape_attribute(ctx):
+    """Fnu_seed_hot (relagn.py:1200-1223), a public attribute of the reference's class: through
+    rg_last_hot_shape for every golden relagn / relqso set, and as the attribute of the class mirror."""
+    d = np.load(os.path.join(GOLDEN, "golden_nonrel.npz"))
+    ctx.set_grid(d["grid1000"])
+    for tag, model in (("relagn", 0), ("relqso", 1)):
+        ctx.eval_batch_host(d[tag + "_params"], model=model, rel=False)
+        for i in range(len(d[tag + "_names"])):
+            ref = d[tag + "_fnu_seed_hot1000"][i]
+            got = ctx.last_hot_shape(i)
+            if ref.max() == 0:
+                assert got.max() == 0, (tag, i)
+            else:
+                assert peak_relerr(got, ref) < TOL, (tag, str(d[tag + "_names"][i]))
+    import relagn_b200
+    m = relagn_b200.relagn()
+    m.new_ear(d["grid1000"])
+    assert peak_relerr(m.Fnu_seed_hot, d["relagn_fnu_seed_hot1000"][0]) < TOL
+
+
 def test_invalid_sets_are_flagged(ctx):
     ctx.set_grid(np.geomspace(1e-4, 1e3, 1001))
     p = c4_params(4, seed=3)

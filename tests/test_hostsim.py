@@ -229,3 +229,18 @@ def test_xspec_local_model_abi(ctx):
         np.testing.assert_allclose(got, ref.astype(np.float32), rtol=3e-7)
     finally:
         ctx.lib.rg_xspec_bind(None)
+
+
+def test_hot_spectral_shape_attribute(ctx):
+    """rg_last_hot_shape: Fnu_seed_hot (relagn.py:1200-1223) of a set of the last batch, against the reference."""
+    d = np.load(os.path.join(GOLDEN, "golden_nonrel.npz"))
+    ctx.set_grid(d["grid1000"])
+    sel = [0, 1, 4]
+    ctx.eval_batch_host(d["relagn_params"][sel], model=0, rel=False)
+    for k, i in enumerate(sel):
+        ref = d["relagn_fnu_seed_hot1000"][i]
+        got = ctx.last_hot_shape(k)
+        if ref.max() == 0:
+            assert got.max() == 0
+        else:
+            assert peak_relerr(got, ref) < 1e-10, i

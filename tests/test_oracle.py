@@ -153,3 +153,16 @@ def test_observation_epilogue_oracle_pins():
     assert abs(c0) < 1e-6 * folded.sum() * 1e-6 + 1e-290 * 2 * folded.size + 1e-9
     c1, _ = O.fold_stat(pa, rp, cl, vl, 1e4, 1.2 * folded, None, 1)
     assert c1 > 0
+
+
+def test_hot_spectral_shape_vs_reference():
+    """Fnu_seed_hot (relagn.py:1200-1223), an attribute of the reference's class, on the 1000-bin grid."""
+    d = np.load(os.path.join(G, "golden_nonrel.npz"))
+    for tag, model in (("relagn", 0), ("relqso", 1)):
+        for i in range(len(d[tag + "_names"])):
+            ref = d[tag + "_fnu_seed_hot1000"][i]
+            got = O.hot_shape(d[tag + "_params"][i], d["grid1000"], model=model)
+            if ref.max() == 0:
+                assert got.max() == 0, (tag, i)
+            else:
+                assert peak_relerr(got, ref) < 1e-10, (tag, d[tag + "_names"][i])
