@@ -645,9 +645,10 @@ static int ensure_slices(rg_ctx *c)
 
 static int ensure_batch_scratch(rg_ctx *c, int model, int P)
 {
-    if (!c->d_sc) { // global rows for Kompaneets grids longer than the shared-memory rows of nthcomp_kernel (rare)
-        c->nth_threads = 0;
-        RG_CUDA_OK(cudaMalloc(&c->d_sc, (size_t)rg_nthcomp_scratch_doubles(c->sm_count) * sizeof(double)));
+    if (!c->d_sc) { // persistent nthcomp grid and its scratch planes: sized by the machine, not by the batch
+        c->nth_threads = c->sm_count * RG_NTH_MINB * 128;
+        // two [RG_NTH][threads] planes (gamma, g of the Thomas sweep) + one row (bet[0])
+        RG_CUDA_OK(cudaMalloc(&c->d_sc, ((size_t)2 * RG_NTH + 1) * c->nth_threads * sizeof(double)));
         RG_CUDA_OK(cudaMalloc(&c->d_queue, 4 * sizeof(int)));
     }
     const int want = pick_chunk_sets(P);
@@ -659,6 +660,8 @@ static int ensure_batch_scratch(rg_ctx *c, int model, int P)
         c->sys_cap = want * 40;
         RG_CUDA_OK(cudaMalloc(&c->d_recs, (size_t)want * sizeof(SetRec)));
         RG_CUDA_OK(cudaMalloc(&c->d_syslist, (size_t)c->sys_cap * sizeof(int2)));
+        RG_CUDA_OK(cudaMalloc(&c->d_sptot, (size_t)c->sys_cap * RG_SPT_STRIDE * sizeof(double)));
+        RG_CUDA_OK(cudaMalloc(&c->d_header, (size_t)c->sys_cap * 4 * sizeof(double)));
         c->chunk_sets = want;
     }
     if (c->farr_nE != c->nE) { // Comptonised spectra on the grid: [farr_cap][nE], 6 GB per 16 384 sets of the chunk
@@ -772,6 +775,11 @@ static int eval_batch_impl(rg_ctx *c, const double *d_params, int P, int model, 
         A.edges = reinterpret_cast<const double2 *>(c->d_edges);
         bool forked = false;
         unsigned long long *stats = c->profile ? c->d_stats : nullptr;
+        int nth_run = c->nth_threads; // threads of the persistent nthcomp grid
+        if (const char *e = getenv("RG_NTH_CTAS")) { // tuning knob: resident nthcomp CTAs per SM (<= RG_NTH_MINB)
+            int k = atoi(e);
+            if (k >= 1 && k <= RG_NTH_MINB) nth_run = c->sm_count * k * 128;
+        }
         // Which of the two gets the SMs first is decided by the launch order.  hist_kernel first: its CTAs take every
         // SM and the persistent nthcomp grid moves in as they drain (144.8 ms per 125 000 sets); nthcomp first: the
         // two share the SMs for the whole solve and slow each other down (155.2 ms; one stream, no overlap: 146.8 ms).
@@ -780,10 +788,12 @@ static int eval_batch_impl(rg_ctx *c, const double *d_params, int P, int model, 
         const bool nth_first = getenv("RG_NTH_FIRST") != nullptr;
         auto launch_nth = [&]() -> int {
             if (nsys <= 0) return RG_OK;
+            c->launches++; // nthcomp_interp_kernel
             RG_TRY(prof_begin(c, 1, st));
-            RG_TRY(rg_launch_nthcomp(c->d_recs, c->d_syslist, n_warm_sys, n_hot_sys, c->farr_cap, c->d_p10,
-                                     reinterpret_cast<const double2 *>(c->d_edges), c->d_sc, c->sm_count, c->gd, c->d_farr,
-                                     c->d_queue + 3, stats, st));
+            RG_TRY(rg_launch_nthcomp(c->d_recs, c->d_syslist, n_warm_sys, n_hot_sys, c->farr_cap, c->d_p10, c->d_sc,
+                                     c->d_sc + (size_t)RG_NTH * c->nth_threads,
+                                     c->d_sc + (size_t)2 * RG_NTH * c->nth_threads, nth_run, c->d_sptot,
+                                     c->d_header, c->gd, c->d_farr, stats, st));
             RG_TRY(prof_end(c, 1, st));
             c->launches++;
             return RG_OK;

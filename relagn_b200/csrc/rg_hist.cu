@@ -69,12 +69,13 @@ __global__ void __launch_bounds__(32 * HIST_WARPS, MINB) hist_kernel(HistArgs A)
     constexpr int NP = 32 * NQ;
     int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    unsigned char *wbase = smem_raw + (size_t)warp * A.warp_bytes;
-    // (the lane index and the warp's base are used all over the ring routine: opaque to the compiler from here on, so
-    //  that it keeps them in registers instead of rebuilding them from the thread index at every use -- 7 % of the
-    //  kernel's instructions in profiles/r2c)
+    // (the lane index and the warp's offset are used all over the ring routine: opaque to the compiler from here on,
+    //  so that it keeps them in registers instead of rebuilding them from the thread index at every use -- 7 % of the
+    //  kernel's instructions in profiles/r2c.  The OFFSET, not the pointer: the accesses must stay LDS / STS)
+    unsigned woff = (unsigned)warp * (unsigned)A.warp_bytes;
     asm volatile("" : "+r"(lane));
-    asm volatile("" : "+l"(wbase));
+    asm volatile("" : "+r"(woff));
+    unsigned char *wbase = smem_raw + woff;
     PrepRec *prep = reinterpret_cast<PrepRec *>(wbase);
     double *scr_base = reinterpret_cast<double *>(wbase + HIST_PREP * sizeof(PrepRec));
     const RingScr scr = rg_ring_scr(scr_base, NP, A.DN);

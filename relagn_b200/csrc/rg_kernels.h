@@ -68,12 +68,11 @@ int rg_spectrum_pick_warps(int NC, int nH, int HL, int HH, int fp32);
 int rg_launch_setup(const double *d_params, int P, int model, double dr_dex, SetRec *recs, int *sys_counter,
                     int2 *syslist, int sys_cap, double *rq_scratch, int rq_cap, double *d_attrs, cudaStream_t st);
 
-// Kompaneets solves + interpolation onto the grid (rg_nthcomp.cu): one warp per system, persistent grid.
-// gscratch: rg_nthcomp_scratch_doubles(sm_count) doubles for the rare grids longer than the shared-memory rows.
-int rg_nthcomp_scratch_doubles(int sm_count);
+// persistent: n_threads = total launched threads = rows of the [RG_NTH][n_threads] scratch planes
 int rg_launch_nthcomp(const SetRec *recs, const int2 *syslist, int n_warm_sys, int n_hot_sys, int sys_cap,
-                      const double *p10tab, const double2 *edges, double *gscratch, int sm_count, const GridDesc &grid,
-                      double *farr, int *queue, unsigned long long *stats, cudaStream_t st);
+                      const double *p10tab, double *sc_gam,
+                      double *sc_g, double *sc_bet, int n_threads, double *sptot, double *header,
+                      const GridDesc &grid, double *farr, unsigned long long *stats, cudaStream_t st);
 
 int rg_launch_spectrum(const SpecArgs &args, int sm_count, cudaStream_t st);
 

@@ -282,6 +282,318 @@ setup_kernel(const double *__restrict__ params, int P, int model, double dr_dex,
 }
 
 // ---------------------------------------------------------------------------
+// nthcomp: one thread per system, persistent grid.
+//   scratch planes gam, g: [RG_NTH][n_threads] (bet: row 0 only, the rest is recomputed), indexed by the launching
+//   thread (not the system) so the footprint is bounded by the resident
+//   threads; a warp's accesses to one j are contiguous.
+//   sptot arena: [sys][RG_SPT_STRIDE];  header: [sys][4] = xmin, normfac, jmax, log10(511 xmin);
+//   farr arena: [sys][nE] = the Comptonised spectrum on the caller's energy grid
+// Called by all 32 lanes of a warp together (`valid` = this lane has a system): the back substitution walks the
+// scratch rows in warp-uniform order so that a warp's loads of one row stay contiguous.
+#ifndef RG_NTH_WARPMAJOR
+#define RG_NTH_WARPMAJOR 1
+#endif
+#if RG_NTH_WARPMAJOR
+// warp-major scratch [warp][row][gamma | g][32 lanes]: the 512 bytes a warp writes per row follow each other in
+// memory, so the forward sweep streams through its own 450 kB region and the back substitution walks it in reverse --
+// DRAM pages see runs of rows instead of one 256-byte burst per row-major plane row (758 kB apart)
+#define SC_GAM(j) sc_gam[((size_t)(sys >> 5) * RG_NTH + (size_t)(j)) * 64 + (sys & 31)]
+#define SC_G(j) sc_gam[((size_t)(sys >> 5) * RG_NTH + (size_t)(j)) * 64 + 32 + (sys & 31)]
+#else
+#define SC_GAM(j) sc_gam[(size_t)(j) * sc_stride + sys]
+#define SC_G(j) sc_g[(size_t)(j) * sc_stride + sys]
+#endif
+__device__ static void nthcomp_system(bool valid, const SetRec &r, int which, const double *p10tab,
+                                      double *__restrict__ sc_gam, double *__restrict__ sc_g,
+                                      double *__restrict__ sc_bet, size_t sc_stride, int slot, double *__restrict__ spt,
+                                      double *__restrict__ hd)
+{
+    const int sys = slot; // scratch column of this thread
+    double gamma = 2.0, kte = 1.0, ktbb = 0.01;
+    if (!valid) {
+    } else if (which < 0) { // hot shape: relagn.py:1200-1223
+        gamma = r.gamma_h; kte = r.kTe_h; ktbb = r.kTseed;
+    } else {         // warm annulus `which` (counted top-down): relagn.py:900-927
+        NtConst nt;
+        rg_nt_prepare(nt, r);
+        BinIter it;
+        it.start(r.lg_rh, r.lg_rw, r.dlog_r);
+        double lo = 0, hi = 0;
+        for (int s = 0; s <= which; s++) it.next(lo, hi);
+        double rmid = pow(10.0, lo + r.dlog_r / 2);
+        double Tann = pow(rg_tnt4(nt, rmid), 0.25);
+        gamma = r.gamma_w; kte = r.kTe_w; ktbb = Tann / 1.16048e7;
+    }
+    // ---- _thcompton (pyNTHCOMP.py:80-173) ----
+    double tempbb = ktbb / 511.0, theta = kte / 511.0;
+    double tautom = sqrt(2.250 + 3.0 / (theta * ((gamma + .50) * (gamma + .50) - 2.250))) - 1.50;
+    const double delta = 0.02;
+    double deltal = delta * log(10.0);
+    double xmin = 1e-4 * tempbb, xmax = 40.0 * theta;
+    int jmax = (int)(log10(xmax / xmin) / delta) + 1;
+    if (jmax > 899) jmax = 899;
+    if (valid && jmax < 4) { // degenerate grid: the reference would index out of range; flag as empty
+        hd[0] = xmin; hd[1] = 0.0; hd[2] = 0.0; hd[3] = log10(511.0 * xmin);
+        valid = false;
+    }
+    if (!valid) jmax = 0; // idle lane: both sweeps fall through, the warp collectives below still see it
+    int jmaxth = (int)(log10(50 * tempbb / xmin) / delta);
+    if (jmaxth > 900) jmaxth = 900;
+    if (jmaxth > jmax) jmaxth = jmax;
+    double pt = RGK_PI * tempbb;
+    double planck = 15.0 / (pt * pt * pt * pt);
+    int jnr = (int)(log10(0.10 / xmin) / delta + 1);
+    if (jnr > jmax - 1) jnr = jmax - 1;
+    int jrel = (int)(log10(1 / xmin) / delta + 1);
+    if (jrel > jmax) jrel = jmax;
+    double xnr = xmin * p10tab[jnr - 1 > 0 ? jnr - 1 : 0];
+    double xr = xmin * p10tab[jrel - 1 > 0 ? jrel - 1 : 0];
+    double c20 = tautom / deltal;
+    double tod = theta / deltal;
+
+    // rolling values: x[j-1], x[j], x[j+1], c2[j-1], c2[j]
+    double xm = xmin * p10tab[0], x0 = xmin * p10tab[1], xp;
+    double x32 = sqrt(xm * x0);
+    double aa = (tod / x32 + 0.5) / (tod / x32 - 0.5);
+    double w1 = x32;
+    double c2m = (w1 * w1 * w1 * w1) / (1.0 + 4.60 * w1 + 1.1 * w1 * w1); // c2[0]
+    double gam_prev = 0, g_prev = 0;
+    // w2[j] = sqrt(x[j-1] x[j]) is w1[j-1], and theta/deltal/w2[j] the previous step's theta/deltal/w1: carried over
+    // (same operands, same operations: bit-identical to recomputing them as pyNTHCOMP.py:211-212 does)
+    double tow1_prev = tod / x32;
+    // bet[0]
+    {
+        double w = xm, rel;
+        if (w <= 0.05) rel = (1.0 - 2.0 * w + 26.0 * w * w * 0.2);
+        else {
+            double z1 = (1.0 + w) / (w * w * w), z2 = 1.0 + 2.0 * w, z3 = log(z2), z4 = 2.0 * w * (1.0 + w) / z2;
+            double z5 = z3 / 2.0 / w, z6 = (1.0 + 3.0 * w) / z2 / z2;
+            rel = (0.75 * (z1 * (z4 - z3) + z5 - z6));
+        }
+        double b0;
+        if (0 < jnr - 1) b0 = 1.0 / tautom / (1.0 + tautom * rel / 3.0);
+        else if (0 < jrel) { double flz = 1 - (w - xnr) / (xr - xnr); b0 = 1.0 / tautom / (1.0 + tautom * rel / 3.0 * flz); }
+        else b0 = 1.0 / tautom;
+        if (valid) { sc_bet[sys] = b0; SC_GAM(0) = 0; SC_G(0) = 0; }
+    }
+    const double itau = 1.0 / tautom, rxr = 1.0 / (xr - xnr), itbb = 1.0 / tempbb, todx = tod / xmin;
+    const double third = 1.0 / 3.0;
+    // bet[j] of pyNTHCOMP.py:124-148 at x = x[j] (j >= 1); a pure function of the row, so the back substitution can
+    // recompute it bit for bit instead of reading a third scratch plane back (the solve is bound by the
+    // HBM round trip of the planes, not by instructions: 37 -> 34 ms per 125 000 sets)
+    auto bet_at = [&](int j, double w) -> double {
+        if (j >= jrel) return itau;
+        double rel;
+        if (w <= 0.05) rel = (1.0 - 2.0 * w + 26.0 * w * w * 0.2);
+        else {
+            // Klein-Nishina factor (pyNTHCOMP.py:128-136) with the six divisions by w and 1 + 2w folded into
+            // two reciprocals (last-bit differences only)
+            const double rw = 1.0 / w, z2 = 1.0 + 2.0 * w, rz = 1.0 / z2, z3 = log(z2);
+            double z1 = (1.0 + w) * (rw * rw * rw), z4 = 2.0 * w * (1.0 + w) * rz;
+            double z5 = z3 * 0.5 * rw, z6 = (1.0 + 3.0 * w) * (rz * rz);
+            rel = (0.75 * (z1 * (z4 - z3) + z5 - z6));
+        }
+        const double taukn = tautom * rel;
+        if (j < jnr - 1) return itau * __drcp_rn(1.0 + taukn * third);
+        const double flz = 1 - (w - xnr) * rxr;
+        return itau * __drcp_rn(1.0 + taukn * third * flz);
+    };
+    for (int j = 1; j < jmax - 1; j++) {
+        xp = xmin * p10tab[j + 1];
+        // w1 = sqrt(x[j] x[j+1]) = xmin 10^(0.02 j + 0.01) and theta / deltal / w1 from the resident tables: no
+        // square root and one division less per row (last-bit differences against pyNTHCOMP.py:117,211)
+        const double w1j = xmin * p10tab[RG_P10_W1 + j];
+        // (quotients as reciprocal multiplies: rcp.rn + mul instead of div.rn, last-bit differences)
+        double c2j = (w1j * w1j * w1j * w1j) * __drcp_rn(1.0 + 4.60 * w1j + 1.1 * w1j * w1j);
+        // rel, bet at j
+        const double betj = bet_at(j, x0);
+        double dph = (j < jmaxth) ? planck * (x0 * x0) * __drcp_rn(rg_exp_pos(x0 * itbb) - 1) : 0.0;
+        // coefficients (pyNTHCOMP.py:210-221)
+        const double tow1 = todx * p10tab[RG_P10_RW1 + j], tow2 = tow1_prev;
+        double aj = -c20 * c2j * (tow1 + 0.5);
+        double t1 = -c20 * c2j * (0.5 - tow1);
+        double t2 = c20 * c2m * (tow2 + 0.5);
+        double t3 = (x0 * x0 * x0) * (tautom * betj);
+        double bj = t1 + t2 + t3;
+        double cj = c20 * c2m * (0.5 - tow2);
+        double dj = x0 * dph;
+        // Thomas forward sweep (pyNTHCOMP.py:233-242)
+        // one reciprocal of the pivot serves both quotients (pyNTHCOMP.py:234-241)
+        double alp, gj;
+        if (j == 1) alp = bj + cj * aa; else alp = bj - cj * gam_prev;
+        const double ralp = 1.0 / alp;
+        if (j == 1) gj = dj * ralp; else gj = (dj - cj * g_prev) * ralp;
+        double gamj = aj * ralp;
+        RG_STCS(&SC_GAM(j), gamj); RG_STCS(&SC_G(j), gj); // streamed: read back once
+        gam_prev = gamj; g_prev = gj;
+        xm = x0; x0 = xp; c2m = c2j; tow1_prev = tow1;
+    }
+    // back substitution (pyNTHCOMP.py:243-249) and sptot = dphesc x^2 (pyNTHCOMP.py:170-171)
+    double u_next = 0.0; // u[jmax-1]
+    double u1 = 0.0;
+    if (valid) { spt[jmax] = 0.0; spt[jmax - 1] = 0.0; }
+    // The scratch planes are far larger than L2, so the reads below come from HBM.  Neighbouring lanes hold systems
+    // whose jmax differ by a step or two: the warp walks the rows from its highest jmax down TOGETHER (a lane joins
+    // when the row reaches its own jmax - 2), so every row is read as one contiguous run of the plane instead of 32
+    // scattered sectors.  The loads of 4 rows are issued together (their addresses do not depend on u), then the
+    // dependent recurrence runs on registers.
+    const int jtop_me = jmax - 2;
+    const int jtop = __reduce_max_sync(0xffffffffu, jtop_me);
+    // The next group's loads are in flight while the current group's dependent chain runs (register double buffer).
+    double gg[4] = {0, 0, 0, 0}, gm[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        if (jtop - q >= 1 && jtop - q <= jtop_me) {
+            gg[q] = RG_LDCS(&SC_G(jtop - q)); gm[q] = RG_LDCS(&SC_GAM(jtop - q));
+        }
+    }
+    for (int jj = jtop; jj >= 1;) {
+        const int nb = jj >= 4 ? 4 : jj; // rows jj, jj-1, ..., jj-nb+1
+        const int jn = jj - nb;          // first row of the next group
+        double ngg[4] = {0, 0, 0, 0}, ngm[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (jn - q >= 1 && jn - q <= jtop_me) {
+                ngg[q] = RG_LDCS(&SC_G(jn - q)); ngm[q] = RG_LDCS(&SC_GAM(jn - q));
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (q < nb && jj - q <= jtop_me) {
+                double u = gg[q] - gm[q] * u_next;
+                double x = xmin * p10tab[jj - q];
+                const double btq = bet_at(jj - q, x); // recomputed: no third scratch plane
+                spt[jj - q] = (x * x * u * btq * tautom) * (x * x);
+                u_next = u;
+                if (jj - q == 1) u1 = u;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) { gg[q] = ngg[q]; gm[q] = ngm[q]; }
+        jj = jn;
+    }
+    if (!valid) return;
+    {
+        double u = aa * u1;
+        double x = xmin * p10tab[0];
+        spt[0] = (x * x * u * sc_bet[sys] * tautom) * (x * x);
+    }
+    // normalisation at 1 keV (pyNTHCOMP.py:49-56)
+    double xx = 1.0 / 511.0;
+    int ih = 1;
+    while (ih < jmax && xx > xmin * p10tab[ih]) ih++;
+    int il = ih - 1;
+    double xl = xmin * p10tab[il], xh = xmin * p10tab[ih];
+    double spp = spt[il] + (spt[ih] - spt[il]) * (xx - xl) / (xh - xl);
+    const double normfac = 1.0 / spp;
+    hd[0] = xmin; hd[1] = normfac; hd[2] = (double)jmax; hd[3] = log10(511.0 * xmin);
+}
+
+__global__ void __launch_bounds__(128, RG_NTH_MINB)
+nthcomp_kernel(const SetRec *__restrict__ recs, const int2 *__restrict__ syslist, int nsys, int n_warm_sys, int n_warm_pad,
+               int hot_first,
+               const double *__restrict__ p10tab, double *__restrict__ sc_gam, double *__restrict__ sc_g,
+               double *__restrict__ sc_bet, int n_threads, double *__restrict__ sptot, double *__restrict__ header,
+               unsigned long long *stats)
+{
+    // 10^(0.02 j) is read at every step of both sweeps: keep it in shared memory (the scratch stream would keep
+    // evicting it from L1)
+    __shared__ double s_p10[RG_P10_RW1 + RG_NTH + 4]; // 10^(0.02 j) | w1 | 1 / w1
+    for (int i = threadIdx.x; i < RG_NTH + 4; i += blockDim.x) {
+        s_p10[i] = p10tab[i];
+        s_p10[RG_P10_W1 + i] = p10tab[RG_P10_W1 + i];
+        s_p10[RG_P10_RW1 + i] = p10tab[RG_P10_RW1 + i];
+    }
+    __syncthreads();
+    int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long sumj = 0, nsolved = 0;
+    const int lane = threadIdx.x & 31;
+    for (int s0 = gtid - lane; s0 < nsys; s0 += n_threads) { // warp-uniform trip count: the lanes solve together
+        // logical index -> arena row: the warm systems fill rows [0, n_warm_sys), the hot shapes the top of the arena
+        const int li = s0 + lane;
+        bool valid = li < nsys && (li < n_warm_sys || li >= n_warm_pad);
+        const int sys = li < n_warm_pad ? li : hot_first + (li - n_warm_pad);
+        int2 ent = valid ? syslist[sys] : make_int2(0, 0);
+        const SetRec &r = recs[ent.x];
+        valid = valid && r.status == RG_S_OK;
+        const size_t so = valid ? (size_t)sys : 0;
+        nthcomp_system(valid, r, ent.y, s_p10, sc_gam, sc_g, sc_bet, (size_t)n_threads, gtid,
+                       sptot + so * RG_SPT_STRIDE, header + so * 4);
+        if (valid) {
+            sumj += (unsigned long long)header[(size_t)sys * 4 + 2];
+            nsolved++;
+        }
+    }
+    if (stats && nsolved) {
+        atomicAdd(&stats[2], sumj);
+        atomicAdd(&stats[3], nsolved);
+    }
+}
+
+// donthcomp's interpolation of the Kompaneets solution onto the caller's grid (pyNTHCOMP.py:57-76), then * h / keV
+// (relagn.py:929-930, 1217-1218): one warp per system, lanes over consecutive energy bins (coalesced stores).
+// The reference's monotone cursor is restated as a direct search seeded from log10(E) and fixed up with the
+// reference's own comparisons, so every bin lands in exactly the cell the cursor would have reached.
+__global__ void __launch_bounds__(256)
+nthcomp_interp_kernel(const SetRec *__restrict__ recs, const int2 *__restrict__ syslist, int nsys, int n_warm_sys,
+                      int n_warm_pad, int hot_first, const double *__restrict__ p10tab, const double *__restrict__ sptot,
+                      const double *__restrict__ header, GridDesc grid, double *__restrict__ farr)
+{
+    __shared__ double s_p10[RG_NTH + 4];
+    __shared__ double s_rdp[RG_NTH + 4]; // 1 / (10^(0.02 (j+1)) - 10^(0.02 j)): the cell width of the x grid, per unit xmin
+    for (int i = threadIdx.x; i < RG_NTH + 4; i += blockDim.x) s_p10[i] = p10tab[i];
+    for (int i = threadIdx.x; i < RG_NTH + 3; i += blockDim.x) s_rdp[i] = p10tab[RG_P10_RDP + i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int li = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (li >= nsys || (li >= n_warm_sys && li < n_warm_pad)) return;
+    const int sys = li < n_warm_pad ? li : hot_first + (li - n_warm_pad);
+    if (recs[syslist[sys].x].status != RG_S_OK) return;
+    const double *hd = header + (size_t)sys * 4;
+    const double xmin = hd[0], normfac = hd[1], lgx = hd[3];
+    const double rxmin = 1.0 / xmin;
+    // photon flux -> W/Hz (relagn.py:929-930) folded into the normalisation
+    const double outfac = (1.0 / RGK_KEV) * RGK_H;
+    const int nth = (int)hd[2];
+    const double *spt = sptot + (size_t)sys * RG_SPT_STRIDE;
+    double *F = farr + (size_t)sys * grid.nE;
+    const int nE = grid.nE;
+    double carry_pr = 0.0, carry_e = 0.0; // bin i0 - 1 of the previous pass
+    for (int i0 = 0; i0 < nE; i0 += 32) {
+        const int i = i0 + lane;
+        double e = 0.0, pr = 0.0;
+        if (i < nE) {
+            e = __ldg(grid.Egrid + i);
+            int j = (int)ceil((__ldg(grid.lgE + i) - lgx) * 50.0);
+            if (j < 0) j = 0;
+            if (j > nth + 1) j = nth + 1;
+            while (j > 0 && !(511.0 * (xmin * s_p10[j - 1]) < e)) j--;
+            while (j <= nth && 511.0 * (xmin * s_p10[j]) < e) j++;
+            double prim = 0.0;
+            if (j <= nth) {
+                if (j > 0) {
+                    const int jl = j - 1;
+                    // linear interpolation inside the cell [xl, xh] (pyNTHCOMP.py:66-71); the division by the cell
+                    // width is a multiplication by (1 / xmin) (1 / (10^(0.02 (jl+1)) - 10^(0.02 jl)))
+                    const double xl = xmin * s_p10[jl];
+                    const double sl = spt[jl], sh = spt[jl + 1];
+                    prim = sl + ((__ldg(grid.e511 + i) - xl) * (sh - sl)) * (rxmin * s_rdp[jl]);
+                } else prim = spt[0];
+            }
+            pr = prim * __ldg(grid.rear2 + i); // prim / E^2 (pyNTHCOMP.py:75)
+        }
+        double pr_prev = __shfl_up_sync(0xffffffffu, pr, 1), e_prev = __shfl_up_sync(0xffffffffu, e, 1);
+        if (lane == 0) { pr_prev = carry_pr; e_prev = carry_e; }
+        if (i < nE) {
+            const double ph = i > 0 ? (0.5 * (pr + pr_prev) * (e - e_prev) * normfac) : 0.0;
+            F[i] = ph * outfac;
+        }
+        carry_pr = __shfl_sync(0xffffffffu, pr, 31);
+        carry_e = __shfl_sync(0xffffffffu, e, 31);
+    }
+}
+
+// ---------------------------------------------------------------------------
 int rg_launch_setup(const double *d_params, int P, int model, double dr_dex, SetRec *recs, int *sys_counter,
                     int2 *syslist, int sys_cap, double *rq_scratch, int rq_cap, double *d_attrs, cudaStream_t st)
 {
@@ -341,6 +653,27 @@ __global__ void counters_out_kernel(const int *__restrict__ ctr, int *__restrict
 int rg_launch_counters_out(const int *d_counter, int *h_mapped, cudaStream_t st)
 {
     RG_LAUNCH(counters_out_kernel, dim3(1), dim3(1), 0, st, d_counter, h_mapped);
+    RG_CUDA_OK(cudaGetLastError());
+    return RG_OK;
+}
+
+int rg_launch_nthcomp(const SetRec *recs, const int2 *syslist, int n_warm_sys, int n_hot_sys, int sys_cap,
+                      const double *p10tab, double *sc_gam,
+                      double *sc_g, double *sc_bet, int n_threads, double *sptot, double *header,
+                      const GridDesc &grid, double *farr, unsigned long long *stats, cudaStream_t st)
+{
+    // logical order: the warm systems, padded to a whole warp, then the hot shapes -- no warp mixes the two kinds
+    const int n_warm_pad = (n_warm_sys + 31) & ~31;
+    const int nsys = n_hot_sys > 0 ? n_warm_pad + n_hot_sys : n_warm_sys;
+    const int hot_first = sys_cap - n_hot_sys;
+    if (nsys <= 0) return RG_OK;
+    int blocks = (nsys + 127) / 128;
+    if (blocks * 128 > n_threads) blocks = n_threads / 128;
+    RG_LAUNCH(nthcomp_kernel, dim3(blocks), dim3(128), 0, st, recs, syslist, nsys, n_warm_sys, n_warm_pad, hot_first, p10tab, sc_gam, sc_g, sc_bet,
+              blocks * 128, sptot, header, stats);
+    RG_CUDA_OK(cudaGetLastError());
+    RG_LAUNCH(nthcomp_interp_kernel, dim3((unsigned)(((size_t)nsys * 32 + 255) / 256)), dim3(256), 0, st, recs, syslist,
+              nsys, n_warm_sys, n_warm_pad, hot_first, p10tab, sptot, header, grid, farr);
     RG_CUDA_OK(cudaGetLastError());
     return RG_OK;
 }
