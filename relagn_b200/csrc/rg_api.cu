@@ -410,6 +410,13 @@ static int tables_alloc(rg_ctx *c, const double *spins, int n_spin, const double
 
 static int ensure_slices(rg_ctx *c);
 
+// (dE_0 4 / E_0) (E_0 / dE_0) with the reference's operations (relagn.py:970-974, 1003-1006) on the first bin
+static double pack_unpack_const(const std::vector<double> &eb)
+{
+    const double dE = eb[1] - eb[0], E = eb[0] + dE / 2;
+    return ((dE * 4) / E) * (E / dE);
+}
+
 static double host_row_pos(const TabDesc &t, double r)
 {
     double ell = (rg_row_x(r) - t.x0) / t.dx;
@@ -704,6 +711,7 @@ static int eval_batch_impl(rg_ctx *c, const double *d_params, int P, int model, 
     A.flags = flags;
     A.farr = c->d_farr;
     A.queue = c->d_queue;
+    A.pkupk = c->h_ebins.size() > 1 ? pack_unpack_const(c->h_ebins) : 4.0;
     if (rel) {
         A.tab = c->td;
         int kl, kh;

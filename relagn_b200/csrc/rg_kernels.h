@@ -56,6 +56,7 @@ struct SpecArgs {
     int hstride;
     const double2 *edges; // (lo, hi) of every annulus in log10 r: [annulus], rows as in the histogram arena (edges_kernel)
     int *queue;           // device work-queue counter (zeroed before the launch)
+    double pkupk;         // (4 dE / E) (E / dE) of the geometric grid: the pack-unpack factor of relagn.py:970-974, 1003-1006
     int warps;            // warps per CTA
     unsigned long long *stats; // optional device counters [4]: sum W_ann, conv annuli, sum jmax, systems
 };

@@ -34,7 +34,7 @@
 #ifndef RG_LOCKSTEP
 #define RG_LOCKSTEP 4 // block barrier every RG_LOCKSTEP rounds (power of two)
 #endif
-#define NGRID 5 // per-bin constant arrays staged in shared memory: hnu, bbpre, wt, pk, upk
+#define NGRID 3 // per-bin constant arrays staged in shared memory: hnu, bbpre, wt
 #ifndef RG_SPEC_W64
 #define RG_SPEC_W64 12 // warps per CTA of the FP64 kernel on grids of <= 1024 bins (register budget 65536 / (32 W))
 #endif
@@ -177,18 +177,6 @@ struct GridAcc {
         int j = 8 * col + c;
         return (R)(j < g->nE ? __ldg(g->wt + j) : 0.0);
     }
-    __device__ inline R pk(int c, int col) const // pack factor of relagn.py:970-974 (h, 4 pi d^2 cancel)
-    {
-        if (GS) return sm[(3 * 8 + c) * (32 * NC) + col];
-        int j = 8 * col + c;
-        return (R)(j < g->nE ? (__ldg(g->dE + j) * 4) / __ldg(g->Egrid + j) : 0.0);
-    }
-    __device__ inline R upk(int c, int col) const // unpack factor of relagn.py:1003-1006
-    {
-        if (GS) return sm[(4 * 8 + c) * (32 * NC) + col];
-        int j = 8 * col + c;
-        return (R)(j < g->nE ? __ldg(g->Egrid + j) / __ldg(g->dE + j) : 0.0);
-    }
 };
 
 // Accumulators: registers (statically indexed through a switch on the chunk, so that the chunk loops with their
@@ -318,8 +306,6 @@ __global__ void __launch_bounds__(NC <= 4 ? (sizeof(R) == 4 ? 512 : 32 * RG_SPEC
             sgrid[(0 * 8 + c) * NCOL + col] = (R)(ok ? A.grid.hnu[j] : 1.0); // padding bins: 0 / (exp(1/kT) - 1) = 0
             sgrid[(1 * 8 + c) * NCOL + col] = (R)(ok ? A.grid.bbpre[j] : 0.0);
             sgrid[(2 * 8 + c) * NCOL + col] = (R)(ok ? A.grid.wt[j] : 0.0);
-            sgrid[(3 * 8 + c) * NCOL + col] = (R)(ok ? (A.grid.dE[j] * 4) / A.grid.Egrid[j] : 0.0);
-            sgrid[(4 * 8 + c) * NCOL + col] = (R)(ok ? A.grid.Egrid[j] / A.grid.dE[j] : 0.0);
         }
     }
     for (int i = lane; i < 8 * RS; i += 32) inT[i] = 0;
@@ -544,14 +530,12 @@ __global__ void __launch_bounds__(NC <= 4 ? (sizeof(R) == 4 ? 512 : 32 * RG_SPEC
                             part += L[c] * G.wt(c, col);
                         }
                     }
-                    // publish: packed for the transfer convolution, plain for the flat / non-relativistic sum
-                    if (conv) {
+                    // publish.  The reference packs W/Hz into photons per bin before kyconv and unpacks afterwards
+                    // (x dE 4 / E, relagn.py:970-974; x E / dE, :1003-1006): on the geometric grid the transfer needs,
+                    // dE / E is the same for every bin (to rounding), so the two factors are one constant, folded into the
+                    // histogram's scale below
 #pragma unroll
-                        for (int c = 0; c < 8; c++) inBase[c * RS + 32 * ch] = L[c] * G.pk(c, col);
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < 8; c++) inBase[c * RS + 32 * ch] = L[c];
-                    }
+                    for (int c = 0; c < 8; c++) inBase[c * RS + 32 * ch] = L[c];
                 }
                 if (region == 0 && A.grid.n_ext) { // relagn.py:868-873
                     for (int q = lane; q < A.grid.n_ext; q += 32) {
@@ -562,10 +546,13 @@ __global__ void __launch_bounds__(NC <= 4 ? (sizeof(R) == 4 ? 512 : 32 * RG_SPEC
                 const double radiance = (double)warp_sum(part);
                 __syncwarp();
                 // Lnu = norm * (B / radiance), zero when the annulus emits nothing (relagn.py:885-889, 933-937)
-                if (conv) install_hist(true, 1.0);
+                // (the histogram is installed already scaled: norm / radiance x the pack-unpack constant)
+                // (FP32 mode keeps the histogram unscaled -- the scale alone can exceed the single-precision range -- and
+                //  multiplies afterwards in double)
+                const double hscale = radiance != 0 ? (s2 / radiance) * A.pkupk : 0.0;
+                if (conv) install_hist(true, sizeof(R) == 8 ? hscale : 1.0);
                 if (radiance != 0) {
                     if (conv) {
-                        const double scale = s2 / radiance;
                         for (int ch = 0; ch < NC; ch++) {
                             // taps whose sources all lie in the zero zones (j - k >= jz or j - k < 0) are skipped
                             int k_lo = 256 * ch - (region == 0 ? jz : nE) + 1, k_hi = 256 * ch + 255;
@@ -575,9 +562,10 @@ __global__ void __launch_bounds__(NC <= 4 ? (sizeof(R) == 4 ? 512 : 32 * RG_SPEC
                             const int col = 32 * ch + lane;
                             R tmp[8];
                             convolve8<R>(Hslot + 8, K_LO, nH, k_lo, k_hi, inBase + 32 * ch, RS, tmp);
-                            // (the scale factor alone can exceed the single-precision range: multiply in double)
+                            if (sizeof(R) != 8) {
 #pragma unroll
-                            for (int c = 0; c < 8; c++) tmp[c] = (R)((double)tmp[c] * (scale * (double)G.upk(c, col)));
+                                for (int c = 0; c < 8; c++) tmp[c] = (R)((double)tmp[c] * hscale);
+                            }
                             acc.add(ch, tmp);
                         }
                     } else {
@@ -663,7 +651,7 @@ __global__ void __launch_bounds__(NC <= 4 ? (sizeof(R) == 4 ? 512 : 32 * RG_SPEC
 #pragma unroll
                 for (int c = 0; c < 8; c++) {
                     const int j = 8 * col + c;
-                    inBase[c * RS + 32 * ch] = (hot_F && j < nE) ? (R)__ldg(hot_F + j) * G.pk(c, col) : (R)0;
+                    inBase[c * RS + 32 * ch] = (hot_F && j < nE) ? (R)__ldg(hot_F + j) : (R)0;
                 }
             }
             __syncwarp();
@@ -672,7 +660,7 @@ __global__ void __launch_bounds__(NC <= 4 ? (sizeof(R) == 4 ? 512 : 32 * RG_SPEC
             // 1 / trapz(Fnu) and the factors of relagn.py:1362 once per item instead of three divisions per bin and warp
             // (0 / 0 -> NaN as the reference's division gives, relagn.py:1316: 1/0 = inf, 0 * inf = NaN)
             const double r_shape = 1.0 / shape_int;
-            const double conv_fac = (conv_unit / shape_int) / cosfac;
+            const double conv_fac = ((conv_unit / shape_int) / cosfac) * A.pkupk; // (pack x unpack: one constant, see above)
             for (int ch = 0; ch < NC; ch++) {
                 const int col = 32 * ch + lane;
                 R tmp[8];
@@ -684,11 +672,11 @@ __global__ void __launch_bounds__(NC <= 4 ? (sizeof(R) == 4 ? 512 : 32 * RG_SPEC
                 for (int c = 0; c < 8; c++) {
                     v[c] = 0;
                     if (8 * col + c < nE) {
-                        // the buffer holds F * pk and pk * upk = 4; F / shape_int: 0/0 -> NaN as the reference (:1316)
-                        double F = (double)inBase[c * RS + 32 * ch] * (double)G.upk(c, col) * 0.25;
+                        // F / shape_int: 0/0 -> NaN as the reference (:1316)
+                        double F = (double)inBase[c * RS + 32 * ch];
                         if (rel) {
                             double vv = hot_mine ? Sflat * (F * r_shape) : 0.0;
-                            if (conv_here) vv += ((double)tmp[c] * conv_fac) * (double)G.upk(c, col); // relagn.py:1362
+                            if (conv_here) vv += (double)tmp[c] * conv_fac; // relagn.py:1362
                             v[c] = (R)vv;
                         } else {
                             v[c] = (R)(Lum * (F * r_shape));
