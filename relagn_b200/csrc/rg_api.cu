@@ -408,7 +408,7 @@ static int tables_alloc(rg_ctx *c, const double *spins, int n_spin, const double
     return RG_OK;
 }
 
-static int ensure_slices(rg_ctx *c);
+static int ensure_slices(rg_ctx *c, long ctas);
 
 // (dE_0 4 / E_0) (E_0 / dE_0) with the reference's operations (relagn.py:970-974, 1003-1006) on the first bin
 static double pack_unpack_const(const std::vector<double> &eb)
@@ -550,7 +550,7 @@ static int ky_hist_host(rg_ctx *c, double a, double th, double r1, double r2, do
         RG_CUDA_OK(cudaMalloc(&c->d_kyH, (size_t)nH * sizeof(double)));
         c->kyH_cap = nH;
     }
-    RG_TRY(ensure_slices(c));
+    RG_TRY(ensure_slices(c, 1));
     RG_TRY(rg_launch_ky_hist(c->td, a, th, r1, r2, alpha, beta, rb, zshift, dlnE, nsub, c->d_kyH, K_LO, nH, c->d_kystatus,
                              c->d_slices, c->stream));
     c->launches++;
@@ -631,16 +631,16 @@ static int pick_chunk_sets(int P)
         int v = atoi(e);
         if (v >= 1024 && v <= 131072) cap = v;
     }
-    int want = 4096;
+    int want = 64; // a single model object (P = 1) gets arenas of tens of MB, not the GBs of a 4096-set chunk
     while (want < P && want < cap) want *= 4;
     return std::min(want, cap);
 }
 
-// scratch for the table slices of the resident hist_kernel CTAs: 8 per SM at most
-static int ensure_slices(rg_ctx *c)
+// scratch for the table slices of the resident hist_kernel CTAs (two halves each): 8 per SM at most
+static int ensure_slices(rg_ctx *c, long ctas = 1L << 30)
 {
     const size_t per = (size_t)c->td.NR * c->td.NPHI;
-    const int slots = c->sm_count * 8;
+    const int slots = (int)std::min<long>(c->sm_count * 8L, std::max<long>(2 * ctas, 2));
     if (c->d_slices && c->slice_elems >= per * slots) { c->slice_slots = slots; return RG_OK; }
     free_dev(c->d_slices);
     c->d_slices = nullptr;
@@ -652,13 +652,19 @@ static int ensure_slices(rg_ctx *c)
 
 static int ensure_batch_scratch(rg_ctx *c, int model, int P)
 {
-    if (!c->d_sc) { // persistent nthcomp grid and its scratch planes: sized by the machine, not by the batch
-        c->nth_threads = c->sm_count * RG_NTH_MINB * 128;
-        // two [RG_NTH][threads] planes (gamma, g of the Thomas sweep) + one row (bet[0])
-        RG_CUDA_OK(cudaMalloc(&c->d_sc, ((size_t)2 * RG_NTH + 1) * c->nth_threads * sizeof(double)));
-        RG_CUDA_OK(cudaMalloc(&c->d_queue, 4 * sizeof(int)));
-    }
+    if (!c->d_queue) RG_CUDA_OK(cudaMalloc(&c->d_queue, 4 * sizeof(int)));
     const int want = pick_chunk_sets(P);
+    {   // persistent nthcomp grid and its scratch planes: sized by the machine, or by the chunk when that is smaller
+        const int full = c->sm_count * RG_NTH_MINB * 128;
+        const int need = (int)std::min<long>(full, (((long)std::max(want, c->chunk_sets) * 40 + 127) / 128) * 128);
+        if (need > c->nth_threads) {
+            free_dev(c->d_sc);
+            c->d_sc = nullptr;
+            // two [RG_NTH][threads] planes (gamma, g of the Thomas sweep) + one row (bet[0])
+            RG_CUDA_OK(cudaMalloc(&c->d_sc, ((size_t)2 * RG_NTH + 1) * need * sizeof(double)));
+            c->nth_threads = need;
+        }
+    }
     if (want > c->chunk_sets) { // grow: per-set records, arena of Kompaneets systems
         free_dev(c->d_recs); free_dev(c->d_syslist); free_dev(c->d_sptot); free_dev(c->d_header); free_dev(c->d_rq);
         free_dev(c->d_farr);
@@ -813,7 +819,7 @@ static int eval_batch_impl(rg_ctx *c, const double *d_params, int P, int model, 
             H.recs = c->d_recs; H.P = n; H.tab = c->td; H.dlnE = c->gd.dlnE; H.inv_dlnE = 1.0 / c->gd.dlnE; H.K_LO = A.K_LO; H.nH = A.nH;
             H.NBH = n >= 2 * c->sm_count ? 1 : (int)std::min<long>(32, (4L * c->sm_count + n - 1) / n);
             H.hist = c->d_hist; H.hstride = A.hstride; H.edges = A.edges;
-            RG_TRY(ensure_slices(c));
+            RG_TRY(ensure_slices(c, (long)n * H.NBH));
             H.slices = c->d_slices; H.slice_slots = c->slice_slots; H.queue = c->d_queue + 2;
             if (c->sel_bytes < (size_t)n * rg_selrec_bytes()) {
                 free_dev(c->d_sel);
