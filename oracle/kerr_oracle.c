@@ -115,6 +115,17 @@ static double dopri_step(const geo_t *G, rhs_fn rhs, const double *y, const doub
 }
 
 static double g_rtol = 1e-12, g_atol = 1e-14;
+/* limb-darkening law of the local emission (kyconv parameter 10, relagn.py:988; KY: Dovciak et al. 2004):
+ * 0 isotropic (what the reference passes), -1 Laor (1991) 1 + 2.06 mu_e, -2 Haardt (1993) ln(1 + 1/mu_e).
+ * The law multiplies the weight Jn of every table sample: a table set is built for one law. */
+static int g_limb = 0;
+void ro_set_limb(int law) { g_limb = law; }
+double ro_limb_factor(int law, double mue)
+{
+    if (law == -1) return 1.0 + 2.06 * mue;
+    if (law == -2) return log(1.0 + 1.0 / mue);
+    return 1.0;
+}
 void ro_set_ray_tol(double rtol, double atol) { g_rtol = rtol; g_atol = atol; }
 
 int ro_trace_ray(double a, double theta_o, double alpha, double beta, double *r_hit, double *phi_hit)
@@ -254,7 +265,10 @@ int ro_solve_point(double a, double th, double r_e, double phi_e, double *al, do
     double det = r_e * (dr[0] * dp[1] - dr[1] * dp[0]);
     *al = A; *be = B;
     *g = kep_g(a, r_e, -A * sin(th));
-    *jn = 1.0 / fabs(det);
+    /* cosine of the local emission angle: mu_e = g sqrt(q) / r, q = beta^2 + cos^2(theta_o) (alpha^2 - a^2) */
+    double q = B * B + cos(th) * cos(th) * (A * A - a * a);
+    double mue = *g * sqrt(q > 0 ? q : 0.0) / r_e;
+    *jn = ro_limb_factor(g_limb, mue) / fabs(det);
     return 1;
 }
 
@@ -447,6 +461,14 @@ static void repair_body(int i, void *vc)
     }
 }
 
+/* optional extras of the last ro_make_node_rows call of this thread: image-plane coordinates and emission cosine */
+static __thread double *g_extra_alpha = NULL, *g_extra_beta = NULL, *g_extra_mue = NULL;
+static __thread int g_phi0_zero = 0;
+void ro_node_extras(double *alpha, double *beta, double *mue, int absolute_phi)
+{
+    g_extra_alpha = alpha; g_extra_beta = beta; g_extra_mue = mue; g_phi0_zero = absolute_phi;
+}
+
 int ro_make_node_rows(double a, double theta_o, int NR, const double *rows, int NPHI, float *g, float *jn, int threads)
 {
     int *fail = (int *)calloc(NPHI, sizeof(int));
@@ -454,6 +476,7 @@ int ro_make_node_rows(double a, double theta_o, int NR, const double *rows, int 
     size_t np = (size_t)NR * NPHI;
     double *solA = (double *)malloc(sizeof(double) * 2 * np), *solB = (double *)malloc(sizeof(double) * 2 * np);
     int nbad0 = ro_node_phi0(a, theta_o, NR, rows, phi0);
+    if (g_phi0_zero) memset(phi0, 0, sizeof(double) * NR); /* columns at absolute azimuth (KY's own layout) */
     node_ctx c = {a, theta_o, cos(theta_o), NR, NPHI, g, jn, fail, phi0, rows, ro_r_valid(a), solA, solB};
     ro_par_for(NPHI, threads, node_body, &c);
     int nfail = 0;
@@ -474,6 +497,16 @@ int ro_make_node_rows(double a, double theta_o, int NR, const double *rows, int 
         if (nfix == 0) break;
     }
     nfail += nbad0;
+    if (g_extra_alpha || g_extra_beta || g_extra_mue) {
+        for (size_t i = 0; i < np; i++) {
+            double A = solA[i], B = solB[i], r = rows[i / NPHI];
+            double q = B * B + cos(theta_o) * cos(theta_o) * (A * A - a * a);
+            double gg = A == A ? kep_g(a, r, -A * sin(theta_o)) : 0.0;
+            if (g_extra_alpha) g_extra_alpha[i] = A;
+            if (g_extra_beta) g_extra_beta[i] = B;
+            if (g_extra_mue) g_extra_mue[i] = A == A ? gg * sqrt(q > 0 ? q : 0.0) / r : 0.0;
+        }
+    }
     free(fail); free(phi0); free(solA); free(solB);
     return nfail;
 }

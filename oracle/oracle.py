@@ -71,6 +71,12 @@ def lib():
     L.ro_row_radius.argtypes = [C.c_double, C.c_int, C.c_int]
     L.ro_r_valid.restype = C.c_double
     L.ro_r_valid.argtypes = [C.c_double]
+    L.ro_set_limb.restype = None
+    L.ro_set_limb.argtypes = [C.c_int]
+    L.ro_node_extras.restype = None
+    L.ro_node_extras.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    L.ro_make_node_rows.restype = C.c_int
+    L.ro_make_node_rows.argtypes = [C.c_double, C.c_double, C.c_int, _dp, C.c_int, _fp, _fp, C.c_int]
     L.ro_tables_finish.restype = None
     L.ro_tables_finish.argtypes = [C.c_void_p]
     L.ro_slice.restype = C.c_int
@@ -187,6 +193,25 @@ def make_node(a, theta_o, NR, NPHI, r_in, threads=0):
     jn = np.zeros((NR, NPHI), dtype=np.float32)
     nfail = lib().ro_make_node(a, theta_o, NR, NPHI, r_in, g, jn, threads)
     return g, jn, nfail
+
+
+def make_node_full(a, theta_o, rows, NPHI, limb=0, absolute_phi=False):
+    """One node on explicit row radii with the image-plane coordinates and the emission cosine:
+    dict(g, jn, alpha, beta, mue, unresolved).  Runs single-threaded (the extras are per thread)."""
+    rows = np.ascontiguousarray(rows, dtype=np.float64)
+    NR = rows.size
+    g = np.zeros((NR, NPHI), dtype=np.float32)
+    jn = np.zeros((NR, NPHI), dtype=np.float32)
+    al, be, mu = np.zeros((NR, NPHI)), np.zeros((NR, NPHI)), np.zeros((NR, NPHI))
+    L = lib()
+    L.ro_set_limb(int(limb))
+    L.ro_node_extras(al.ctypes.data, be.ctypes.data, mu.ctypes.data, int(bool(absolute_phi)))
+    try:
+        bad = L.ro_make_node_rows(float(a), float(theta_o), NR, rows, int(NPHI), g, jn, 1)
+    finally:
+        L.ro_node_extras(None, None, None, 0)
+        L.ro_set_limb(0)
+    return dict(g=g, jn=jn, alpha=al, beta=be, mue=mu, unresolved=bad)
 
 
 def ky_kernel(tab, a, theta_o, r1, r2, dlnE, alpha=0.0, beta=0.0, rb=1.0, zshift=0.0, nsub=0, cap=65536):
