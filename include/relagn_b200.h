@@ -119,6 +119,11 @@ int rg_tables_generate(rg_ctx *ctx, const double *spins, int n_spin, const doubl
                        int NPHI, double r_in, long *n_unresolved);
 int rg_tables_upload(rg_ctx *ctx, const double *spins, int n_spin, const double *thetas, int n_inc, int NR, int NPHI,
                      double r_in, const float *data_host);
+/* Limb-darkening law of the local emission (kyconv parameter 10, relagn.py:988; the reference passes 0): 0 isotropic,
+ * -1 Laor (1991) 1 + 2.06 mu_e, -2 Haardt (1993) ln(1 + 1/mu_e).  The law is a property of the table set (it multiplies
+ * the weight of every sample): call before rg_tables_generate, or after rg_tables_upload to state what the uploaded
+ * set was built with.  rg_kyconv refuses a parameter 10 that differs from it. */
+int rg_tables_set_limb(rg_ctx *ctx, int law);
 int rg_tables_download(rg_ctx *ctx, float *data_host, size_t n_floats);
 int rg_tables_info(rg_ctx *ctx, int *n_spin, int *n_inc, int *NR, int *NPHI, double *r_in, size_t *n_floats);
 

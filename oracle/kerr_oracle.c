@@ -807,7 +807,8 @@ int ro_ky_kernel(const ro_tables *t, double a, double theta_o, double r1, double
 int ro_kyconv(const ro_tables *t, const double *eb, int nE, const double *par, double *flux)
 {
     if (!t || nE < 2) return 1;
-    if (par[3] != 0 || par[9] != 0 || par[11] != -1) return 3; /* ms, ntable, norm: unsupported modes */
+    if (par[3] != 0 || par[11] != -1) return 3; /* ms, norm: unsupported modes */
+    if (par[9] != 0 && par[9] != -1 && par[9] != -2) return 3; /* limb law: a property of the table set (ro_set_limb) */
     double dlnE = log(eb[nE] / eb[0]) / nE;
     for (int j = 0; j <= nE; j++)
         if (fabs(log(eb[j] / eb[0]) - j * dlnE) > 1e-4 * dlnE) return 4; /* not a geometric grid */

@@ -30,7 +30,7 @@ SYMBOLS = ["rg_version", "rg_last_error", "rg_ctx_create", "rg_ctx_destroy", "rg
            "rg_eval_batch_pieces", "rg_eval_batch_host", "rg_launch_count", "rg_measure_fp64_peak", "rg_set_option", "rg_get_stat",
            "rg_reset_stats", "rg_convert_batch", "rg_set_instrument", "rg_photar_batch", "rg_set_response",
            "rg_set_data", "rg_fitstat_batch", "rg_eval_fitstat_batch", "rg_eval_fitstat_batch_host",
-           "rg_xspec_eval", "rg_xspec_bind", "rg_tables_default", "rg_last_hot_shape"]
+           "rg_xspec_eval", "rg_xspec_bind", "rg_tables_default", "rg_last_hot_shape", "rg_tables_set_limb"]
 XSPEC_SYMBOLS = ["relagn_", "relqso_"]  # gfortran names of the XSPEC local models (seam B3)
 
 UNITS = {"SI": 0, "cgs": 1, "cgs_wave": 2, "SI_wave": 3, "counts": 4}  # RG_UNIT_*
@@ -69,6 +69,8 @@ def bind(lib):
                                        C.POINTER(C.c_long)]
     lib.rg_tables_upload.restype = C.c_int
     lib.rg_tables_upload.argtypes = [C.c_void_p, _dp, C.c_int, _dp, C.c_int, C.c_int, C.c_int, C.c_double, _fp]
+    lib.rg_tables_set_limb.restype = C.c_int
+    lib.rg_tables_set_limb.argtypes = [C.c_void_p, C.c_int]
     lib.rg_tables_download.restype = C.c_int
     lib.rg_tables_download.argtypes = [C.c_void_p, _fp, C.c_size_t]
     lib.rg_tables_info.restype = C.c_int
@@ -194,6 +196,10 @@ class Context:
         self._check(self.lib.rg_tables_generate(self.h, _d(sp), sp.size, _d(th), th.size, int(NR), int(NPHI),
                                                 float(r_in), C.byref(bad)))
         return bad.value
+
+    def tables_set_limb(self, law):
+        """kyconv parameter 10: 0 isotropic, -1 Laor, -2 Haardt -- before tables_generate, or after tables_upload."""
+        self._check(self.lib.rg_tables_set_limb(self.h, int(law)))
 
     def tables_info(self):
         ns, ni, nr, nphi = C.c_int(), C.c_int(), C.c_int(), C.c_int()

@@ -55,6 +55,7 @@ struct rg_ctx {
     size_t tab_floats = 0;
     std::vector<double> h_spins, h_thetas;
     std::vector<int> h_firstrow;
+    int tab_limb = 0; // limb-darkening law the resident / next generated tables are built with (rg_tables_set_limb)
     int last_first = 0, last_n = 0; // sets of the last evaluated chunk (rg_last_hot_shape)
     cudaStream_t last_stream = nullptr;
     // batch scratch
@@ -496,10 +497,21 @@ extern "C" int rg_tables_generate(rg_ctx *c, const double *spins, int n_spin, co
 {
     RG_TRY(tables_alloc(c, spins, n_spin, thetas, n_inc, NR, NPHI, r_in));
     long bad = 0;
-    RG_TRY(rg_launch_raytrace(spins, n_spin, thetas, n_inc, NR, NPHI, r_in, c->d_tab, &bad, c->stream));
+    RG_TRY(rg_launch_raytrace(spins, n_spin, thetas, n_inc, NR, NPHI, r_in, c->tab_limb, c->d_tab, &bad, c->stream));
     c->launches += 2L * n_spin * n_inc;
     if (n_unresolved) *n_unresolved = bad;
     return tables_finish(c, nullptr);
+}
+
+// kyconv parameter 10 (relagn.py:988): the law multiplies the weight of every table sample, so it belongs to the table
+// set.  Call before rg_tables_generate (the ray tracer bakes it in) or after rg_tables_upload (states what the
+// uploaded set was built with, e.g. by relagn_b200.ky_fits.import_ky_tables(limb=...)).
+extern "C" int rg_tables_set_limb(rg_ctx *c, int law)
+{
+    if (!c || (law != 0 && law != -1 && law != -2))
+        return rg_set_error(RG_E_ARG, "rg_tables_set_limb: law must be 0 (isotropic), -1 (Laor) or -2 (Haardt)");
+    c->tab_limb = law;
+    return RG_OK;
 }
 
 extern "C" int rg_tables_download(rg_ctx *c, float *data, size_t n_floats)
@@ -585,9 +597,12 @@ extern "C" int rg_ky_kernel(rg_ctx *c, double a, double theta_o, double r1, doub
 extern "C" int rg_kyconv(rg_ctx *c, const double *eb, int nE, const double *par, double *flux)
 {
     if (!c || !eb || !par || !flux || nE < 2) return rg_set_error(RG_E_ARG, "rg_kyconv: bad arguments");
-    if (par[3] != 0 || par[9] != 0 || par[11] != -1)
-        return rg_set_error(RG_E_UNSUPPORTED, "rg_kyconv: only ms=0, ntable=0 (isotropic), norm=-1 are implemented "
-                                              "(what relagn.py:997-998 passes)");
+    if (par[3] != 0 || par[11] != -1)
+        return rg_set_error(RG_E_UNSUPPORTED, "rg_kyconv: only ms=0 and norm=-1 are implemented (what relagn.py:997-998 passes)");
+    if (par[9] != (double)c->tab_limb)
+        return rg_set_error(RG_E_UNSUPPORTED, "rg_kyconv: limb-darkening law %g requested, the resident tables were built "
+                                              "for law %d (rg_tables_set_limb before rg_tables_generate / after upload)",
+                            par[9], c->tab_limb);
     double dlnE = log(eb[nE] / eb[0]) / nE;
     for (int j = 0; j <= nE; j++)
         if (fabs(log(eb[j] / eb[0]) - j * dlnE) > 1e-4 * dlnE)

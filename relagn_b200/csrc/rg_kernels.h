@@ -110,7 +110,7 @@ int rg_launch_ky_conv(const double *d_H, int kmin, int nk, const double *d_in, d
 
 // table generation (device ray tracer): fills d_data [n_spin][n_inc][2][NR][NPHI]
 int rg_launch_raytrace(const double *h_spins, int n_spin, const double *h_thetas, int n_inc, int NR, int NPHI,
-                       double r_in, float *d_data, long *n_unresolved, cudaStream_t st);
+                       double r_in, int limb, float *d_data, long *n_unresolved, cudaStream_t st);
 // host-side geometry of the table format (shared by the ray tracer, the loader and the kernels' row lookup)
 double rg_row_x(double r);
 double rg_row_radius(double r_in, int NR, int s);

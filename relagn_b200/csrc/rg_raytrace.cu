@@ -256,6 +256,18 @@ __device__ static int march_to(double a, double th, double phi, double r_from, d
     return 1;
 }
 
+// limb-darkening law of the local emission (kyconv parameter 10; relagn.py:988 passes 0 = isotropic): -1 Laor (1991)
+// 1 + 2.06 mu_e, -2 Haardt (1993) ln(1 + 1/mu_e), with mu_e = g sqrt(q) / r, q = beta^2 + cos^2(theta_o)(alpha^2 - a^2).
+// The law multiplies the weight Jn of every table sample: a table set is built for one law.
+__device__ static double limb_weight(int law, double a, double th, double r, double A, double B, double g)
+{
+    if (law == 0) return 1.0;
+    const double co = cos(th);
+    const double q = B * B + co * co * (A * A - a * a);
+    const double mue = g * sqrt(q > 0 ? q : 0.0) / r;
+    return law == -1 ? 1.0 + 2.06 * mue : log(1.0 + 1.0 / mue);
+}
+
 // continuation along the ring: from the solved point (r, phi_from; A, B) to (r, phi_to), halving the azimuth step on
 // failure (explicit stack instead of recursion; depth limit 8) -- kerr_oracle.c: march_phi
 __device__ static int march_phi(double a, double th, double r, double phi_from, double phi_to, double *A, double *B,
@@ -342,7 +354,7 @@ __global__ void phi0_kernel(const double *__restrict__ spins, const double *__re
 __global__ void __launch_bounds__(32)
 node_kernel(const double *__restrict__ spins, const double *__restrict__ thetas, int n_spin, int n_inc, int NR, int NPHI,
             const double *__restrict__ rows, const double *__restrict__ rvalid, const double *__restrict__ phi0_all,
-            float *__restrict__ data, double2 *__restrict__ sol)
+            float *__restrict__ data, double2 *__restrict__ sol, int limb)
 {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_spin * n_inc * NPHI) return;
@@ -385,7 +397,7 @@ node_kernel(const double *__restrict__ spins, const double *__restrict__ thetas,
             continue;
         }
         g[(size_t)s * NPHI + t] = (float)gg;
-        jn[(size_t)s * NPHI + t] = (float)jj;
+        jn[(size_t)s * NPHI + t] = (float)(jj * limb_weight(limb, a, theta_o, r, A, B, gg));
         so[(size_t)s * NPHI + t] = make_double2(A, B);
         if (have >= 1) { A2 = A1; B2 = B1; }
         A1 = A; B1 = B; r1 = r;
@@ -400,7 +412,7 @@ __global__ void __launch_bounds__(32)
 repair_kernel(const double *__restrict__ spins, const double *__restrict__ thetas, int n_spin, int n_inc, int NR, int NPHI,
               const double *__restrict__ rows, const double *__restrict__ rvalid, const double *__restrict__ phi0_all,
               float *__restrict__ data, const double2 *__restrict__ sol, double2 *__restrict__ pending,
-              int *__restrict__ counters)
+              int *__restrict__ counters, int limb)
 {
     size_t plane = (size_t)NR * NPHI;
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -425,7 +437,7 @@ repair_kernel(const double *__restrict__ spins, const double *__restrict__ theta
         double gg, jj;
         if (march_phi(a, theta_o, r, phin, phi, &A, &B, &gg, &jj)) {
             g[(size_t)s * NPHI + t] = (float)gg;
-            jn[(size_t)s * NPHI + t] = (float)jj;
+            jn[(size_t)s * NPHI + t] = (float)(jj * limb_weight(limb, a, theta_o, r, A, B, gg));
             pending[idx] = make_double2(A, B);
             atomicAdd(counters + 1, 1); // repaired in this sweep
             return;
@@ -457,7 +469,7 @@ double rg_r_valid(double a)
 }
 
 int rg_launch_raytrace(const double *h_spins, int n_spin, const double *h_thetas, int n_inc, int NR, int NPHI,
-                       double r_in, float *d_data, long *n_unresolved, cudaStream_t st)
+                       double r_in, int limb, float *d_data, long *n_unresolved, cudaStream_t st)
 {
     int nodes = n_spin * n_inc;
     size_t plane = (size_t)NR * NPHI, npts = (size_t)nodes * plane;
@@ -483,14 +495,14 @@ int rg_launch_raytrace(const double *h_spins, int n_spin, const double *h_thetas
     RG_CUDA_OK(cudaGetLastError());
     int total = nodes * NPHI;
     RG_LAUNCH(node_kernel, dim3((total + 31) / 32), dim3(32), 0, st, d_spins, d_thetas, n_spin, n_inc, NR, NPHI, d_rows,
-              d_rvalid, d_phi0, d_data, d_sol);
+              d_rvalid, d_phi0, d_data, d_sol, limb);
     RG_CUDA_OK(cudaGetLastError());
     int cnt[3] = {0, 0, 0};
     long left = 0;
     for (int sweep = 0; sweep < 6; sweep++) {
         RG_CUDA_OK(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(int), st));
         RG_LAUNCH(repair_kernel, dim3((unsigned)((npts + 31) / 32)), dim3(32), 0, st, d_spins, d_thetas, n_spin, n_inc, NR,
-                  NPHI, d_rows, d_rvalid, d_phi0, d_data, d_sol, d_pend, d_cnt);
+                  NPHI, d_rows, d_rvalid, d_phi0, d_data, d_sol, d_pend, d_cnt, limb);
         RG_CUDA_OK(cudaGetLastError());
         RG_LAUNCH(publish_kernel, dim3((unsigned)((npts + 255) / 256)), dim3(256), 0, st, d_sol, d_pend, npts);
         RG_CUDA_OK(cudaGetLastError());

@@ -249,6 +249,68 @@ def test_kyconv_seam_blurr_config(ctx, oracle, otab):
     assert k0 == k1 and np.allclose(H, H1, rtol=1e-10, atol=1e-12 * H1.max())
 
 
+def test_kyconv_config2_inclination_sweep(ctx, oracle):
+    """BASELINE config 2 as SURVEY 8(d) C2 specifies it (tests/blurr_test.py:23-54, 77-139): Gaussian line at 1 keV
+    (sigma 0.01 keV) on 500 log bins 0.1-2 keV, a = 0.998, r_in = 1.236, r_out = 100, over the inclination sweep
+    cos i = 0.09 ... 0.998, on the DEFAULT tables.  (i) one call with emissivity alpha = beta = 3, r_break = 10 against
+    the oracle; (ii) 199 log-spaced annuli with alpha = beta = 0 and explicit r_mid^-3 weights summed: the additivity
+    the RELAGN design rests on.  (ii) is a coarser quadrature of the same r^-3 integral (midpoint weights over annuli of
+    0.022 dex), so it agrees with (i) to the quadrature error, not to rounding: 1 % of the line flux, 2 % in the L1
+    norm of the profile."""
+    from relagn_b200 import tables as T
+    T.load_default(ctx)
+    cfg = T.DEFAULT
+    otab = oracle.Tables(cfg["spins"], cfg["thetas"], cfg["NR"], cfg["NPHI"], cfg["r_in"], data=ctx.tables_download())
+    eb = np.geomspace(0.1, 2.0, 501)
+    ec = 0.5 * (eb[1:] + eb[:-1])
+    line = np.exp(-0.5 * ((ec - 1.0) / 0.01) ** 2) / (0.01 * np.sqrt(2 * np.pi)) * np.diff(eb)
+    edges = np.geomspace(1.236, 100.0, 200)
+    for ci in (0.09, 0.2, 0.3, 0.5, 0.7, 0.9, 0.998):
+        inc = float(np.rad2deg(np.arccos(ci)))
+        par = [0.998, inc, 1.236, 0, 100.0, 3.0, 3.0, 10.0, 0, 0, 500, -1]
+        ref = oracle.kyconv(otab, eb, par, line)
+        got = ctx.kyconv(eb, par, line.copy())
+        assert peak_relerr(got, ref) < TOL, ci
+        acc = np.zeros_like(line)
+        for r1, r2 in zip(edges[:-1], edges[1:]):
+            rm = 0.5 * (r1 + r2)  # blurr_test.py:89
+            acc += rm ** -3 * ctx.kyconv(eb, [0.998, inc, r1, 0, r2, 0, 0, rm, 0, 0, 500, -1], line.copy())
+        assert abs(acc.sum() / got.sum() - 1) < 1e-2, (ci, acc.sum() / got.sum())
+        assert np.abs(acc - got).sum() / got.sum() < 2e-2, (ci, np.abs(acc - got).sum() / got.sum())
+        # unit bookkeeping (blurr_test.py:148-150): the kernel of the whole disc integrates the r^-3 emissivity times
+        # the projected area: positive, finite, and the redshifted wing carries flux below the line energy
+        assert np.isfinite(got).all() and got.min() >= 0 and got[ec < 0.95].sum() > 0
+    upload_golden_tables(ctx)
+
+
+def test_limb_darkening_tables(ctx, oracle):
+    """kyconv parameter 10 (relagn.py:988): the device ray tracer with the law baked in (rg_tables_set_limb before
+    rg_tables_generate) against the oracle's, and the seam's check of the parameter against the resident set."""
+    NR, NPHI, r_in = 32, 32, 2.0
+    a, th = np.array([0.9]), np.array([np.deg2rad(60.0)])
+    rows = np.array([oracle.lib().ro_row_radius(r_in, NR, s) for s in range(NR)])
+    try:
+        for law in (-1, -2):
+            ctx.tables_set_limb(law)
+            bad = ctx.tables_generate(a, th, NR, NPHI, r_in)
+            d = ctx.tables_download()[0, 0]
+            ref = oracle.make_node_full(0.9, th[0], rows, NPHI, limb=law)
+            assert bad == 0 and ref["unresolved"] == 0
+            np.testing.assert_allclose(d[0], ref["g"], rtol=2.4e-7)
+            np.testing.assert_allclose(d[1], ref["jn"], rtol=2e-5)
+            eb = np.geomspace(0.1, 10.0, 201)
+            line = np.zeros(200)
+            line[100] = 1.0
+            par = [0.9, 60.0, 6.0, 0, 20.0, 0, 0, 10.0, 0, float(law), 200, -1]
+            out = ctx.kyconv(eb, par, line.copy())
+            assert out.sum() > 0
+            with pytest.raises(Exception):
+                ctx.kyconv(eb, par[:9] + [0.0] + par[10:], line.copy())   # isotropic asked, Laor / Haardt resident
+    finally:
+        ctx.tables_set_limb(0)
+        upload_golden_tables(ctx)
+
+
 def test_full_size_properties_relqso_grid(ctx):
     """Config 3 at full size (1e4 sets): properties that need no oracle."""
     grid = np.geomspace(1e-4, 1e3, 1001)
