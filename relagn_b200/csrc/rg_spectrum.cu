@@ -122,10 +122,14 @@ __device__ inline void convolve8(const double *Hs0, int K_LO, int nH, int kmin, 
 #pragma unroll
     for (int c = 4; c < 8; c++) w[c] = half ? pg[c * RS] : base[c * RS - g];
     int kb = k0;
+    // (the histogram value of tap u + 1 is requested before the 8 FMAs of tap u: the shared-memory latency of the
+    //  broadcast load hides behind them instead of in front of every tap -- the slot is zero padded 16 behind)
+    R hn = (R)Hk[half ? 4 : 0];
     if (half) {
 #pragma unroll
         for (int u = 4; u < 8; u++) {
-            const R h = (R)Hk[u];
+            const R h = hn;
+            hn = (R)Hk[u + 1];
 #pragma unroll
             for (int c = 0; c < 8; c++) tmp[c] = fma(h, w[(c - u + 8) % 8], tmp[c]);
             w[(7 - u) % 8] = pg[((7 - u) % 8) * RS];
@@ -143,7 +147,12 @@ __device__ inline void convolve8(const double *Hs0, int K_LO, int nH, int kmin, 
 #pragma unroll
         for (int u = 0; u < 8; u++) {
             if (u == 4 && k + 4 > kmax) break; // the last group's upper half holds no tap (warp-uniform)
+#if RG_CONV_HALFSTART
+            const R h = hn;
+            hn = (R)Hk[u + 1];
+#else
             const R h = (R)Hk[u];
+#endif
 #pragma unroll
             for (int c = 0; c < 8; c++) tmp[c] = fma(h, w[(c - u + 8) % 8], tmp[c]);
             // next tap needs in[8 col - (k+u+1)]: row 7-u, column col - g - 1

@@ -40,11 +40,14 @@ res["C3_relqso_grid_1e4_rel_ms"] = ms
 res["C3_relqso_grid_1e4_spectra_per_s"] = 1e4 / (ms * 1e-3)
 evq.ctx.set_profile(True); evq.ctx.reset_stats(); evq.evaluate_device(p3, rel=True); torch.cuda.synchronize()
 s = evq.ctx.stats(); evq.ctx.set_profile(False)
-res["C3_kernels_ms"] = {k: s[k] for k in ("ms_setup", "ms_nthcomp", "ms_spectrum")}
+res["C3_kernels_ms"] = {k: s[k] for k in ("ms_setup", "ms_nthcomp", "ms_hist", "ms_spectrum")}
 g5000 = np.geomspace(1e-4, 1e3, 5001)
 ev5 = BatchEvaluator(g5000, model="relagn", device=0, dr_dex=700.0)
 p5 = torch.tensor([[1e8, 100, -1, 0.998, 0.5, 100, 0.2, 1.7, 2.7, 10, 20, 3, 1, 10, 0]] * 8, dtype=torch.float64, device=dev)
 ms = timed(lambda: ev5.evaluate_device(p5, rel=True), reps=3, warm=1)
 res["C5_hires_5000x2034_P8_ms"] = ms
 res["C5_hires_spectra_per_s"] = 8 / (ms * 1e-3)
+ev5.ctx.set_profile(True); ev5.ctx.reset_stats(); ev5.evaluate_device(p5, rel=True); torch.cuda.synchronize()
+s = ev5.ctx.stats(); ev5.ctx.set_profile(False)
+res["C5_kernels_ms"] = {k: s[k] for k in ("ms_setup", "ms_nthcomp", "ms_hist", "ms_spectrum")}
 print(json.dumps(res))
