@@ -789,7 +789,8 @@ static int eval_batch_impl(rg_ctx *c, const double *d_params, int P, int model, 
         const int n_warm_sys = c->h_counter[0], n_hot_sys = c->h_counter[2];
         int nsys = n_warm_sys + n_hot_sys;
         const size_t hist_need = rel ? (size_t)c->h_counter[1] * (size_t)A.hstride : 0;
-        if (nsys > c->farr_cap || hist_need * sizeof(double) > (size_t)(8e9 * (c->chunk_sets / 16384.0))) {
+        // (the histogram arena is allocated on demand: 8 GB per 16 384 sets of the chunk at most, 2 GB for the small chunks)
+        if (nsys > c->farr_cap || hist_need * sizeof(double) > (size_t)std::max(2e9, 8e9 * (c->chunk_sets / 16384.0))) {
             if (n == 1) return rg_set_error(RG_E_NOMEM, "one parameter set needs %d Kompaneets systems (cap %d) / %zu histogram doubles", nsys, c->farr_cap, hist_need);
             chunk = std::max(1, n / 2); // arenas too small for this chunk: retry with fewer sets
             continue;
