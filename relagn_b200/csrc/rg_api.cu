@@ -744,6 +744,9 @@ static int eval_batch_impl(rg_ctx *c, const double *d_params, int P, int model, 
         A.nH = K_HI - K_LO + 1;
         A.HL = std::max(K_HI, 0) / 8 + 3;
         A.HH = std::max(-K_LO, 0) / 8 + 3;
+        // row stride HL + columns + HH = 2 (mod 16) doubles: the Planck stage stores bin 32 g + lane at row lane mod 8,
+        // column 4 g + lane div 8 -- with this stride the 16 lanes of a half warp hit 16 different bank pairs
+        A.HH += ((2 - (A.HL + A.HH)) % 16 + 16) % 16;
         A.hstride = (A.nH + 2) & ~1; // slot 0 = (first shift, count), then up to nH bins
     } else {
         A.K_LO = 0; A.nH = 1; A.HL = 1; A.HH = 1;

@@ -34,7 +34,7 @@
 #ifndef RG_LOCKSTEP
 #define RG_LOCKSTEP 4 // block barrier every RG_LOCKSTEP rounds (power of two)
 #endif
-#define NGRID 3 // per-bin constant arrays staged in shared memory: hnu, bbpre, wt
+#define NGRID 4 // per-bin constant arrays staged in shared memory: hnu, bbpre, wt in bin order + wt transposed
 #ifndef RG_SPEC_W64
 #define RG_SPEC_W64 12 // warps per CTA of the FP64 kernel on grids of <= 1024 bins (register budget 65536 / (32 W))
 #endif
@@ -73,6 +73,9 @@ int rg_spectrum_pick_warps(int NC, int nH, int HL, int HH, int fp32)
 #endif
 #ifndef RG_WARM_PREFETCH
 #define RG_WARM_PREFETCH 1
+#endif
+#ifndef RG_WIEN_CUT
+#define RG_WIEN_CUT 1 // skip the Wien-tail bins of an annulus whose share of the total is below FP64 resolution
 #endif
 
 template <typename T>
@@ -163,26 +166,19 @@ __device__ inline void convolve8(const double *Hs0, int K_LO, int nH, int kmin, 
     }
 }
 
-// per-bin constants: shared memory (transposed [row c][column]) or global memory for the finest grids
+// per-bin constants: shared memory or global memory for the finest grids.  h nu, 2 h nu^3 / c^2 and the trapezoid
+// weights in bin order (the Planck evaluation walks the bins lane by lane) and the weights once more transposed
+// ([row c][column], bin 8 col + c: the layout of the 8-bins-per-lane stages)
 template <int NC, bool GS, typename R>
 struct GridAcc {
-    const R *sm;       // [NGRID][8][32 NC]
+    const R *sm;       // [hnu | bbpre | wt][8 * 32 NC] | wt transposed [8][32 NC]
     const GridDesc *g;
-    __device__ inline R hnu(int c, int col) const
-    {
-        if (GS) return sm[(0 * 8 + c) * (32 * NC) + col];
-        int j = 8 * col + c;
-        return (R)(j < g->nE ? __ldg(g->hnu + j) : 1.0);
-    }
-    __device__ inline R bbpre(int c, int col) const
-    {
-        if (GS) return sm[(1 * 8 + c) * (32 * NC) + col];
-        int j = 8 * col + c;
-        return (R)(j < g->nE ? __ldg(g->bbpre + j) : 0.0);
-    }
+    __device__ inline R hnu_n(int j) const { return GS ? sm[j] : (R)(j < g->nE ? __ldg(g->hnu + j) : 1.0); }
+    __device__ inline R bbpre_n(int j) const { return GS ? sm[8 * 32 * NC + j] : (R)(j < g->nE ? __ldg(g->bbpre + j) : 0.0); }
+    __device__ inline R wt_n(int j) const { return GS ? sm[2 * 8 * 32 * NC + j] : (R)(j < g->nE ? __ldg(g->wt + j) : 0.0); }
     __device__ inline R wt(int c, int col) const
     {
-        if (GS) return sm[(2 * 8 + c) * (32 * NC) + col];
+        if (GS) return sm[(3 * 8 + c) * (32 * NC) + col];
         int j = 8 * col + c;
         return (R)(j < g->nE ? __ldg(g->wt + j) : 0.0);
     }
@@ -312,9 +308,10 @@ __global__ void __launch_bounds__(NC <= 4 ? (sizeof(R) == 4 ? 512 : 32 * RG_SPEC
             int c = i / NCOL, col = i - c * NCOL;
             int j = 8 * col + c;
             bool ok = j < nE;
-            sgrid[(0 * 8 + c) * NCOL + col] = (R)(ok ? A.grid.hnu[j] : 1.0); // padding bins: 0 / (exp(1/kT) - 1) = 0
-            sgrid[(1 * 8 + c) * NCOL + col] = (R)(ok ? A.grid.bbpre[j] : 0.0);
-            sgrid[(2 * 8 + c) * NCOL + col] = (R)(ok ? A.grid.wt[j] : 0.0);
+            sgrid[j] = (R)(ok ? A.grid.hnu[j] : 1.0); // padding bins: 0 / (exp(1/kT) - 1) = 0
+            sgrid[8 * NCOL + j] = (R)(ok ? A.grid.bbpre[j] : 0.0);
+            sgrid[2 * 8 * NCOL + j] = (R)(ok ? A.grid.wt[j] : 0.0);
+            sgrid[(3 * 8 + c) * NCOL + col] = (R)(ok ? A.grid.wt[j] : 0.0);
         }
     }
     for (int i = lane; i < 8 * RS; i += 32) inT[i] = 0;
@@ -371,6 +368,60 @@ __global__ void __launch_bounds__(NC <= 4 ? (sizeof(R) == 4 ? 512 : 32 * RG_SPEC
         rg_nt_prepare(nt, r);
         // shift range of the histograms (hist_kernel builds them on the same range): widest support over the table
         const int K_LO = A.K_LO, nH = A.nH;
+#if RG_WIEN_CUT
+        // ---- reference annulus of the Wien cut: the disc annulus with the highest colour temperature kT* and the shift
+        //      k* of the strongest tap of its transfer histogram.  At an observed energy where annulus i's share is below
+        //      1e-18 of the reference annulus' share (itself a lower bound of the total there), annulus i cannot move the
+        //      FP64 sum: its Planck function and its transfer are skipped there -- see the cut in the prologue below.
+        double kT_ref = 0.0;
+        int k_ref = 0;
+        if (r.n_disc > 0) {
+            double best = 0.0;
+            int bestg = -1;
+            for (int g = tid; g < r.n_disc; g += nthreads) {
+                const double lo = __ldg(A.edges + r.ann_base + g).x;
+                const double T4 = rg_tnt4(nt, pow(10.0, lo + r.dlog_r / 2));
+                if (T4 > 0) {
+                    const double Tann = pow(T4, 0.25);
+                    const double kT = RGK_KB * (Tann * (r.fcol < 0 ? rg_fcol(Tann) : r.fcol));
+                    if (kT > best) { best = kT; bestg = g; }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ob = __shfl_xor_sync(FULL, best, o);
+                const int og = __shfl_xor_sync(FULL, bestg, o);
+                if (ob > best || (ob == best && og > bestg)) { best = ob; bestg = og; }
+            }
+            __syncthreads(); // (s_red / s_hot are free: the previous item is over)
+            if (lane == 0) { s_red[warp] = best; s_hot[warp] = bestg; }
+            __syncthreads();
+            for (int w = 0; w < nwarps; w++)
+                if (s_red[w] > best || (s_red[w] == best && s_hot[w] > bestg)) { best = s_red[w]; bestg = s_hot[w]; }
+            kT_ref = best;
+            if (bestg >= 0 && rel) {
+                const double2 eg = __ldg(A.edges + r.ann_base + bestg);
+                if (eg.x <= 3 && eg.y <= 3) { // the reference annulus goes through the transfer: its strongest tap
+                    const double *row = A.hist + (size_t)(r.ann_base + bestg) * A.hstride;
+                    const int2 hd = __ldg(reinterpret_cast<const int2 *>(row));
+                    double hv = -1.0;
+                    int hk = 0;
+                    for (int k = lane; k < hd.y; k += 32) {
+                        const double v = __ldg(row + 1 + k);
+                        if (v > hv) { hv = v; hk = hd.x + k; }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const double ov = __shfl_xor_sync(FULL, hv, o);
+                        const int ok = __shfl_xor_sync(FULL, hk, o);
+                        if (ov > hv || (ov == hv && ok < hk)) { hv = ov; hk = ok; }
+                    }
+                    k_ref = hk;
+                }
+            }
+            __syncthreads(); // s_red / s_hot are reused below
+        }
+#endif
         const double Rg2 = r.Rg * r.Rg;
         const double cosfac = r.cosinc / 0.5;
 
@@ -381,6 +432,7 @@ __global__ void __launch_bounds__(NC <= 4 ? (sizeof(R) == 4 ? 512 : 32 * RG_SPEC
         __syncwarp();
         int cur_region = 0;                // component mode: region the accumulators currently belong to
         int hz_min = IMAX, hz_max = -IMAX; // touched range of the H slot (for re-zeroing)
+        int live_steps = 8 * NC;           // 32-bin steps of the warp's buffer that may hold non-zero values
         bool hot_any_conv = false, hot_mine = false;
         int hk_min = IMAX, hk_max = -IMAX;
         double Sflat = 0.0;
@@ -410,7 +462,26 @@ __global__ void __launch_bounds__(NC <= 4 ? (sizeof(R) == 4 ? 512 : 32 * RG_SPEC
                         p_s2 = RGK_SB * (t * t * t * t) * Rg2;
                         // first bin whose Planck exponent overflows (exp(x) = inf for x > 709.78 -> B = 0 exactly)
                         // (single precision: expm1f overflows past x = 88.7)
-                        const double lim = (sizeof(R) == 4 ? 89.0 : 710.0) * p_s1;
+                        double lim = (sizeof(R) == 4 ? 89.0 : 710.0) * p_s1;
+#if RG_WIEN_CUT
+                        // Wien cut: an input bin h nu of this annulus reaches the observer through tap k at h nu e^(k dlnE),
+                        // where the reference annulus (kT*, tap k*) alone contributes C*; in the Wien regime the ratio of
+                        // the two shares is P exp(-h nu [1/kT - e^((k - k*) dlnE) / kT*]) with a prefactor P (ratio of areas,
+                        // norms and tap weights) below 1e15.  Past h nu = 80 / bracket(k = k_max of this annulus) the share
+                        // is below 1e-18 of the total for every tap: those bins are neither evaluated nor convolved.
+                        // (only for annuli whose Planck peak lies on the grid, kT >= h nu_0: the reference normalises B by its
+                        //  integral over the GRID, relagn.py:883-889, so an annulus that shows only its Wien tail is scaled
+                        //  up by an unbounded factor and the bound on P does not hold)
+                        if (kT_ref > 0 && p_s1 >= __ldg(A.grid.hnu)) {
+                            int kmax_i = 0;
+                            if (rel && lo <= 3 && hi <= 3) {
+                                const int2 hd = __ldg(reinterpret_cast<const int2 *>(A.hist + (size_t)(r.ann_base + g) * A.hstride));
+                                kmax_i = hd.x + hd.y - 1;
+                            }
+                            const double br = 1.0 / p_s1 - (rel ? exp((kmax_i - k_ref) * A.grid.dlnE) : 1.0) / kT_ref;
+                            if (br > 0 && 80.0 / br < lim) lim = 80.0 / br;
+                        }
+#endif
                         int lo_j = 0, hi_j = nE;
                         while (lo_j < hi_j) {
                             int m = (lo_j + hi_j) >> 1;
@@ -511,41 +582,63 @@ __global__ void __launch_bounds__(NC <= 4 ? (sizeof(R) == 4 ? 512 : 32 * RG_SPEC
                     continue;
                 }
 
-                // ---- local spectrum, chunk by chunk ----
-                const int nch_live = region == 0 ? ((jz + 255) >> 8) : NC; // chunks holding a non-zero bin
-                const R inv_kT = (R)(region == 0 ? 1.0 / s1 : 0.0);
+                // ---- local spectrum into the warp's transposed buffer (row j mod 8, column j div 8) ----
                 R part = 0;
-                // warm annulus: its Comptonised spectrum is already on the grid (nthcomp_kernel)
-                const double *w_F = region == 1 ? A.farr + (size_t)(r.sys_base + loc) * nE : nullptr;
-                for (int ch = 0; ch < NC; ch++) {
-                    const int col = 32 * ch + lane, j0 = 8 * col;
-                    R L[8];
+                if (region == 0) {
+                    // Planck function, one bin per lane and step (bins 32 g + lane): the live range [0, jz) is walked in
+                    // steps of 32 bins -- in the 8-bins-per-lane layout of the transfer stage the unit of skipping would
+                    // be a 256-bin chunk -- four steps at a time for four independent exp / reciprocal chains per lane.
+                    // x = h nu / kT as a multiplication by 1/kT (one division per annulus instead of one per bin; the
+                    // last-bit difference in x moves exp(x) by < 1e-13 relative)
+                    const R inv_kT = (R)(1.0 / s1);
+                    R *const inLane = inT + A.HL + (lane & 7) * RS + (lane >> 3); // bin `lane`; bin 32 g + lane: + 4 g
+                    const int n_steps = (jz + 31) >> 5;
+                    int gq = 0;
+                    for (; gq + 4 <= n_steps; gq += 4) {
+                        R Lq[4];
 #pragma unroll
-                    for (int c = 0; c < 8; c++) L[c] = 0;
-                    if (ch >= nch_live) {
-                        // Wien tail past the overflow point: identically zero
-                    } else if (region == 0) {
-                        // x = h nu / kT as a multiplication by 1/kT (one division per annulus instead of one per bin;
-                        // the last-bit difference in x moves exp(x) by < 1e-13 relative)
-#pragma unroll
-                        for (int c = 0; c < 8; c++) {
-                            L[c] = planck_bin(G.hnu(c, col), G.bbpre(c, col), inv_kT);
-                            part += L[c] * G.wt(c, col);
+                        for (int q = 0; q < 4; q++) {
+                            const int j = 32 * (gq + q) + lane;
+                            Lq[q] = j < jz ? planck_bin(G.hnu_n(j), G.bbpre_n(j), inv_kT) : (R)0;
                         }
-                    } else if (j0 < nE) {
 #pragma unroll
-                        for (int c = 0; c < 8; c++) {
-                            L[c] = (R)(j0 + c < nE ? __ldg(w_F + j0 + c) : 0.0);
-                            part += L[c] * G.wt(c, col);
+                        for (int q = 0; q < 4; q++) {
+                            part += Lq[q] * G.wt_n(32 * (gq + q) + lane);
+                            inLane[4 * (gq + q)] = Lq[q];
                         }
                     }
-                    // publish.  The reference packs W/Hz into photons per bin before kyconv and unpacks afterwards
-                    // (x dE 4 / E, relagn.py:970-974; x E / dE, :1003-1006): on the geometric grid the transfer needs,
-                    // dE / E is the same for every bin (to rounding), so the two factors are one constant, folded into the
-                    // histogram's scale below
+                    for (; gq < n_steps; gq++) {
+                        const int j = 32 * gq + lane;
+                        const R Lv = j < jz ? planck_bin(G.hnu_n(j), G.bbpre_n(j), inv_kT) : (R)0;
+                        part += Lv * G.wt_n(j);
+                        inLane[4 * gq] = Lv;
+                    }
+                    // zeros where the previous annulus of this warp left values beyond this one's live range
+                    for (int gz = n_steps; gz < live_steps; gz++) inLane[4 * gz] = (R)0;
+                    live_steps = n_steps;
+                } else {
+                    // warm annulus: its Comptonised spectrum is already on the grid (nthcomp kernels)
+                    const double *w_F = A.farr + (size_t)(r.sys_base + loc) * nE;
+                    for (int ch = 0; ch < NC; ch++) {
+                        const int col = 32 * ch + lane, j0 = 8 * col;
+                        R L[8];
 #pragma unroll
-                    for (int c = 0; c < 8; c++) inBase[c * RS + 32 * ch] = L[c];
+                        for (int c = 0; c < 8; c++) L[c] = 0;
+                        if (j0 < nE) {
+#pragma unroll
+                            for (int c = 0; c < 8; c++) {
+                                L[c] = (R)(j0 + c < nE ? __ldg(w_F + j0 + c) : 0.0);
+                                part += L[c] * G.wt(c, col);
+                            }
+                        }
+#pragma unroll
+                        for (int c = 0; c < 8; c++) inBase[c * RS + 32 * ch] = L[c];
+                    }
+                    live_steps = 8 * NC;
                 }
+                // (the reference packs W/Hz into photons per bin before kyconv and unpacks afterwards -- x dE 4 / E,
+                //  relagn.py:970-974; x E / dE, :1003-1006: on the geometric grid the transfer needs, dE / E is the same
+                //  for every bin (to rounding), so the two factors are one constant, folded into the histogram's scale)
                 if (region == 0 && A.grid.n_ext) { // relagn.py:868-873
                     for (int q = lane; q < A.grid.n_ext; q += 32) {
                         double ef = exp(A.grid.x_hnu[q] / s1) - 1;
@@ -579,6 +672,7 @@ __global__ void __launch_bounds__(NC <= 4 ? (sizeof(R) == 4 ? 512 : 32 * RG_SPEC
                         }
                     } else {
                         const double scale = (s2 / radiance) * geo;
+                        const int nch_live = region == 0 ? ((jz + 255) >> 8) : NC; // chunks holding a non-zero bin
                         for (int ch = 0; ch < nch_live; ch++) {
                             R v[8];
 #pragma unroll
