@@ -74,6 +74,8 @@ struct rg_ctx {
     double *d_rq = nullptr;
     int rq_cap = 0;
     int *d_queue = nullptr;
+    double *d_wien = nullptr;    // [chunk] (kT*, k*) of the Wien cut's reference annulus
+    size_t wien_n = 0;
     void *d_sel = nullptr;       // [chunk] table selections (SelRec) of the chunk's sets
     size_t sel_bytes = 0;
     double2 *d_slices = nullptr; // table-slice scratch of the resident hist_kernel CTAs (L2 resident)
@@ -176,7 +178,7 @@ extern "C" void rg_ctx_destroy(rg_ctx *c)
     cudaDeviceSynchronize();
     free_dev(c->d_grid); free_dev(c->d_tab); free_dev(c->d_tab2); free_dev(c->d_tabmeta); free_dev(c->d_firstrow); free_dev(c->d_kystatus); free_dev(c->d_p10); free_dev(c->d_recs);
     free_dev(c->d_counter); free_dev(c->d_syslist); free_dev(c->d_sptot); free_dev(c->d_farr); free_dev(c->d_header); free_dev(c->d_sc);
-    free_dev(c->d_rq); free_dev(c->d_queue); free_dev(c->d_slices); free_dev(c->d_sel); free_dev(c->d_partial); free_dev(c->d_hist); free_dev(c->d_edges); free_dev(c->d_kyH); free_dev(c->d_kyin); free_dev(c->d_kyout);
+    free_dev(c->d_rq); free_dev(c->d_queue); free_dev(c->d_slices); free_dev(c->d_sel); free_dev(c->d_wien); free_dev(c->d_partial); free_dev(c->d_hist); free_dev(c->d_edges); free_dev(c->d_kyH); free_dev(c->d_kyin); free_dev(c->d_kyout);
     free_dev(c->d_stage_par); free_dev(c->d_stage_out); free_dev(c->d_stage_attr); free_dev(c->d_stats);
     free_dev(c->d_ebins); free_dev(c->d_ear); free_dev(c->d_sl_off); free_dev(c->d_ell_col); free_dev(c->d_ell_val);
     free_dev(c->d_counts); free_dev(c->d_sigma); free_dev(c->d_slab); free_dev(c->d_stage_stat); free_dev(c->d_pos0);
@@ -864,6 +866,12 @@ static int eval_batch_impl(rg_ctx *c, const double *d_params, int P, int model, 
         }
         if (!(forked && nth_first)) RG_TRY(launch_nth());
         if (forked) RG_CUDA_OK(cudaStreamWaitEvent(st, c->ev_join, 0));
+        // reference annulus of every set for the Wien cut of the spectrum kernel (needs the histograms: after the join)
+        RG_TRY(ensure_dev(&c->d_wien, &c->wien_n, (size_t)2 * std::max(n, c->chunk_sets)));
+        RG_TRY(rg_launch_wienref(c->d_recs, n, A.edges, rel ? c->d_hist : nullptr, A.hstride, rel ? 1 : 0,
+                                 reinterpret_cast<double2 *>(c->d_wien), st));
+        c->launches++;
+        A.wien = reinterpret_cast<const double2 *>(c->d_wien);
         A.recs = c->d_recs;
         A.P = n;
         A.out = d_out + (size_t)p0 * ncomp * nE;

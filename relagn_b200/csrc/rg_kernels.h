@@ -55,6 +55,7 @@ struct SpecArgs {
     const double *hist;   // shift histograms built by hist_kernel: [annulus][hstride], slot 0 = (first shift, count)
     int hstride;
     const double2 *edges; // (lo, hi) of every annulus in log10 r: [annulus], rows as in the histogram arena (edges_kernel)
+    const double2 *wien;  // [P] (kT*, k*) of every set's reference annulus for the Wien cut (wienref_kernel), or null
     int *queue;           // device work-queue counter (zeroed before the launch)
     double pkupk;         // (4 dE / E) (E / dE) of the geometric grid: the pack-unpack factor of relagn.py:970-974, 1003-1006
     int warps;            // warps per CTA
@@ -76,6 +77,8 @@ int rg_launch_nthcomp(const SetRec *recs, const int2 *syslist, int n_warm_sys, i
                       const GridDesc &grid, double *farr, unsigned long long *stats, cudaStream_t st);
 
 int rg_launch_spectrum(const SpecArgs &args, int sm_count, cudaStream_t st);
+int rg_launch_wienref(const SetRec *recs, int P, const double2 *edges, const double *hist, int hstride, int rel,
+                      double2 *wien, cudaStream_t st);
 
 // shift histograms of every annulus of every set (rg_hist.cu); annulus g of set p lives at row recs[p].ann_base + g
 struct HistArgs {

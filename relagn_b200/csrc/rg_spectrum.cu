@@ -369,57 +369,13 @@ __global__ void __launch_bounds__(NC <= 4 ? (sizeof(R) == 4 ? 512 : 32 * RG_SPEC
         // shift range of the histograms (hist_kernel builds them on the same range): widest support over the table
         const int K_LO = A.K_LO, nH = A.nH;
 #if RG_WIEN_CUT
-        // ---- reference annulus of the Wien cut: the disc annulus with the highest colour temperature kT* and the shift
-        //      k* of the strongest tap of its transfer histogram.  At an observed energy where annulus i's share is below
-        //      1e-18 of the reference annulus' share (itself a lower bound of the total there), annulus i cannot move the
-        //      FP64 sum: its Planck function and its transfer are skipped there -- see the cut in the prologue below.
+        // reference annulus of the Wien cut (wienref_kernel): the disc annulus with the highest colour temperature kT* and
+        // the shift k* of the strongest tap of its transfer histogram -- see the cut in the prologue below
         double kT_ref = 0.0;
         int k_ref = 0;
-        if (r.n_disc > 0) {
-            double best = 0.0;
-            int bestg = -1;
-            for (int g = tid; g < r.n_disc; g += nthreads) {
-                const double lo = __ldg(A.edges + r.ann_base + g).x;
-                const double T4 = rg_tnt4(nt, pow(10.0, lo + r.dlog_r / 2));
-                if (T4 > 0) {
-                    const double Tann = pow(T4, 0.25);
-                    const double kT = RGK_KB * (Tann * (r.fcol < 0 ? rg_fcol(Tann) : r.fcol));
-                    if (kT > best) { best = kT; bestg = g; }
-                }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double ob = __shfl_xor_sync(FULL, best, o);
-                const int og = __shfl_xor_sync(FULL, bestg, o);
-                if (ob > best || (ob == best && og > bestg)) { best = ob; bestg = og; }
-            }
-            __syncthreads(); // (s_red / s_hot are free: the previous item is over)
-            if (lane == 0) { s_red[warp] = best; s_hot[warp] = bestg; }
-            __syncthreads();
-            for (int w = 0; w < nwarps; w++)
-                if (s_red[w] > best || (s_red[w] == best && s_hot[w] > bestg)) { best = s_red[w]; bestg = s_hot[w]; }
-            kT_ref = best;
-            if (bestg >= 0 && rel) {
-                const double2 eg = __ldg(A.edges + r.ann_base + bestg);
-                if (eg.x <= 3 && eg.y <= 3) { // the reference annulus goes through the transfer: its strongest tap
-                    const double *row = A.hist + (size_t)(r.ann_base + bestg) * A.hstride;
-                    const int2 hd = __ldg(reinterpret_cast<const int2 *>(row));
-                    double hv = -1.0;
-                    int hk = 0;
-                    for (int k = lane; k < hd.y; k += 32) {
-                        const double v = __ldg(row + 1 + k);
-                        if (v > hv) { hv = v; hk = hd.x + k; }
-                    }
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        const double ov = __shfl_xor_sync(FULL, hv, o);
-                        const int ok = __shfl_xor_sync(FULL, hk, o);
-                        if (ov > hv || (ov == hv && ok < hk)) { hv = ov; hk = ok; }
-                    }
-                    k_ref = hk;
-                }
-            }
-            __syncthreads(); // s_red / s_hot are reused below
+        if (A.wien && r.n_disc > 0) {
+            const double2 wr = __ldg(A.wien + set);
+            kT_ref = wr.x; k_ref = (int)wr.y;
         }
 #endif
         const double Rg2 = r.Rg * r.Rg;
@@ -815,6 +771,76 @@ __global__ void __launch_bounds__(NC <= 4 ? (sizeof(R) == 4 ? 512 : 32 * RG_SPEC
         atomicAdd(&A.stats[0], st_w);
         atomicAdd(&A.stats[1], st_n);
     }
+}
+
+// Reference annulus of the Wien cut, one warp per parameter set: the disc annulus with the highest colour temperature
+// kT* (relagn.py:857-866) and the shift k* of the strongest tap of its transfer histogram (0 when it does not go through
+// the transfer).  At an observed energy where annulus i's share is below 1e-18 of the reference annulus' share (itself
+// a lower bound of the total there), annulus i cannot move the FP64 sum: spectrum_kernel skips its Planck function and
+// its transfer there.  wien[set] = (kT*, k*).
+__global__ void __launch_bounds__(256) wienref_kernel(const SetRec *__restrict__ recs, int P, const double2 *__restrict__ edges,
+                                                      const double *__restrict__ hist, int hstride, int rel,
+                                                      double2 *__restrict__ wien)
+{
+    const int lane = threadIdx.x & 31;
+    const int set = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (set >= P) return;
+    const SetRec &r = recs[set];
+    if (r.status != RG_S_OK || r.n_disc <= 0) {
+        if (lane == 0) wien[set] = make_double2(0.0, 0.0);
+        return;
+    }
+    NtConst nt;
+    rg_nt_prepare(nt, r);
+    double best = 0.0;
+    int bestg = -1;
+    for (int g = lane; g < r.n_disc; g += 32) {
+        const double lo = __ldg(edges + r.ann_base + g).x;
+        const double T4 = rg_tnt4(nt, pow(10.0, lo + r.dlog_r / 2));
+        if (T4 > 0) {
+            const double Tann = pow(T4, 0.25);
+            const double kT = RGK_KB * (Tann * (r.fcol < 0 ? rg_fcol(Tann) : r.fcol));
+            if (kT > best) { best = kT; bestg = g; }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(FULL, best, o);
+        const int og = __shfl_xor_sync(FULL, bestg, o);
+        if (ob > best || (ob == best && og > bestg)) { best = ob; bestg = og; }
+    }
+    int k_ref = 0;
+    if (bestg >= 0 && rel) {
+        const double2 eg = __ldg(edges + r.ann_base + bestg);
+        if (eg.x <= 3 && eg.y <= 3) { // the reference annulus goes through the transfer: its strongest tap
+            const double *row = hist + (size_t)(r.ann_base + bestg) * hstride;
+            const int2 hd = __ldg(reinterpret_cast<const int2 *>(row));
+            double hv = -1.0;
+            int hk = 0;
+            for (int k = lane; k < hd.y; k += 32) {
+                const double v = __ldg(row + 1 + k);
+                if (v > hv) { hv = v; hk = hd.x + k; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(FULL, hv, o);
+                const int ok = __shfl_xor_sync(FULL, hk, o);
+                if (ov > hv || (ov == hv && ok < hk)) { hv = ov; hk = ok; }
+            }
+            k_ref = hk;
+        }
+    }
+    if (lane == 0) wien[set] = make_double2(best, (double)k_ref);
+}
+
+int rg_launch_wienref(const SetRec *recs, int P, const double2 *edges, const double *hist, int hstride, int rel,
+                      double2 *wien, cudaStream_t st)
+{
+    if (P <= 0) return RG_OK;
+    RG_LAUNCH(wienref_kernel, dim3((unsigned)(((size_t)P * 32 + 255) / 256)), dim3(256), 0, st, recs, P, edges, hist,
+              hstride, rel, wien);
+    RG_CUDA_OK(cudaGetLastError());
+    return RG_OK;
 }
 
 // Fold partial spectra: out[set][c] = sum_q partial[set][q][c] in fixed order q = 0..nparts-1
