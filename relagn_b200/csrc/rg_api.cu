@@ -56,6 +56,8 @@ struct rg_ctx {
     std::vector<double> h_spins, h_thetas;
     std::vector<int> h_firstrow;
     int tab_limb = 0; // limb-darkening law the resident / next generated tables are built with (rg_tables_set_limb)
+    double *h_pin = nullptr;        // pinned staging of the small-batch host path: params | spectra | attrs
+    size_t h_pin_n = 0;
     int last_first = 0, last_n = 0; // sets of the last evaluated chunk (rg_last_hot_shape)
     cudaStream_t last_stream = nullptr;
     // batch scratch
@@ -184,6 +186,7 @@ extern "C" void rg_ctx_destroy(rg_ctx *c)
     free_dev(c->d_counts); free_dev(c->d_sigma); free_dev(c->d_slab); free_dev(c->d_stage_stat); free_dev(c->d_pos0);
     prof_collect(c);
     if (c->h_counter) cudaFreeHost(c->h_counter);
+    if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->side) cudaStreamDestroy(c->side);
@@ -709,8 +712,14 @@ static int ensure_batch_scratch(rg_ctx *c, int model, int P)
     return RG_OK;
 }
 
+// nosync: the small-batch path.  The arenas are sized from caps (every row of the small system arena is scanned, the
+// histogram arena holds RG_SMALL_ANN annuli per set) instead of the setup kernel's counters, so no host round trip
+// separates the setup kernel from the rest of the chain; sets that do not fit are flagged RG_S_CAP by the setup kernel
+// and the caller re-runs the batch through the counting path (the counters are still written, *overflow reports it).
+#define RG_SMALL_SETS 64
 static int eval_batch_impl(rg_ctx *c, const double *d_params, int P, int model, double dr_dex, unsigned flags,
-                           double *d_out, double *d_attrs, void *stream, int piece_sets, rg_piece_fn on_piece, void *user)
+                           double *d_out, double *d_attrs, void *stream, int piece_sets, rg_piece_fn on_piece, void *user,
+                           bool nosync = false)
 {
     if (!c || !d_params || !d_out || P < 0) return rg_set_error(RG_E_ARG, "rg_eval_batch: bad arguments");
     if (model != RG_MODEL_RELAGN && model != RG_MODEL_RELQSO) return rg_set_error(RG_E_ARG, "unknown model %d", model);
@@ -784,18 +793,25 @@ static int eval_batch_impl(rg_ctx *c, const double *d_params, int P, int model, 
         int n = std::min(chunk, P - p0);
         const double *par = d_params + (size_t)p0 * RG_NPAR;
         double *attrs = d_attrs ? d_attrs + (size_t)p0 * RG_NATTR : nullptr;
+        // annuli the chunk may hold: unbounded on the counting path, a cap per set on the small-batch path
+        const int ann_per_set = (int)std::min(100000.0, dr_dex * 8.0 + 3.0);
+        const int ann_cap = nosync ? n * ann_per_set : 0x7fffffff;
+        if (nosync) // unreserved rows of the system arena are recognised by a negative set index
+            RG_CUDA_OK(cudaMemsetAsync(c->d_syslist, 0xff, (size_t)c->farr_cap * sizeof(int2), st));
         RG_TRY(prof_begin(c, 0, st));
         RG_TRY(rg_launch_setup(par, n, model, dr_dex, c->d_recs, c->d_counter, c->d_syslist, c->farr_cap, c->d_rq,
-                               c->rq_cap, attrs, st));
+                               c->rq_cap, attrs, ann_cap, st));
         RG_TRY(prof_end(c, 0, st));
         c->launches += model == RG_MODEL_RELQSO ? 2 : 1;
         RG_TRY(rg_launch_counters_out(c->d_counter, c->h_counter, st)); // zero-copy store, not a D2H copy
-        RG_CUDA_OK(cudaStreamSynchronize(st));
-        const int n_warm_sys = c->h_counter[0], n_hot_sys = c->h_counter[2];
-        int nsys = n_warm_sys + n_hot_sys;
-        const size_t hist_need = rel ? (size_t)c->h_counter[1] * (size_t)A.hstride : 0;
+        if (!nosync) RG_CUDA_OK(cudaStreamSynchronize(st));
+        // (small-batch path: every row of the arena but the top n is scanned for warm systems, the top n for hot shapes)
+        const int n_warm_sys = nosync ? c->farr_cap - n : c->h_counter[0], n_hot_sys = nosync ? n : c->h_counter[2];
+        int nsys = nosync ? 1 : n_warm_sys + n_hot_sys;
+        const int n_ann_rows = nosync ? ann_cap : c->h_counter[1];
+        const size_t hist_need = rel ? (size_t)n_ann_rows * (size_t)A.hstride : 0;
         // (the histogram arena is allocated on demand: 8 GB per 16 384 sets of the chunk at most, 2 GB for the small chunks)
-        if (nsys > c->farr_cap || hist_need * sizeof(double) > (size_t)std::max(2e9, 8e9 * (c->chunk_sets / 16384.0))) {
+        if (!nosync && (nsys > c->farr_cap || hist_need * sizeof(double) > (size_t)std::max(2e9, 8e9 * (c->chunk_sets / 16384.0)))) {
             if (n == 1) return rg_set_error(RG_E_NOMEM, "one parameter set needs %d Kompaneets systems (cap %d) / %zu histogram doubles", nsys, c->farr_cap, hist_need);
             chunk = std::max(1, n / 2); // arenas too small for this chunk: retry with fewer sets
             continue;
@@ -804,7 +820,7 @@ static int eval_batch_impl(rg_ctx *c, const double *d_params, int P, int model, 
         // kernel only and are both latency bound: they run side by side, the histograms on the context's side stream
         // (with profiling on they are serialised on the caller's stream so that the event brackets mean something).
         // radial bin edges of every annulus of the chunk, for hist_kernel and spectrum_kernel
-        RG_TRY(ensure_dev(&c->d_edges, &c->edges_n, (size_t)2 * std::max(c->h_counter[1], 1)));
+        RG_TRY(ensure_dev(&c->d_edges, &c->edges_n, (size_t)2 * std::max(n_ann_rows, 1)));
         RG_TRY(rg_launch_edges(c->d_recs, n, reinterpret_cast<double2 *>(c->d_edges), st));
         c->launches++;
         A.edges = reinterpret_cast<const double2 *>(c->d_edges);
@@ -965,6 +981,40 @@ extern "C" int rg_eval_batch_host(rg_ctx *c, const double *params, int P, int mo
     // is the last piece's.  (Until r1r the slabs themselves shrank towards the end of the batch; small chunks run
     // 6-12 % slower per set than large ones.)  Batches beyond SUPER sets go in rounds so that the staging buffer stays
     // bounded.
+    // ---- small batches (a single model object above all): one stream, pinned staging owned by the context, no host
+    //      round trip between the setup kernel and the rest of the chain (eval_batch_impl nosync), one synchronisation
+    if (P <= RG_SMALL_SETS && !c->profile && !getenv("RG_NO_SMALL_PATH")) {
+        const size_t n_par = (size_t)P * RG_NPAR, n_out = (size_t)P * per_out, n_at = (size_t)P * RG_NATTR;
+        if (c->h_pin_n < n_par + n_out + n_at) {
+            if (c->h_pin) cudaFreeHost(c->h_pin);
+            c->h_pin = nullptr; c->h_pin_n = 0;
+            const size_t want = (size_t)RG_SMALL_SETS * RG_NPAR + (size_t)RG_SMALL_SETS * std::max(per_out, (size_t)4 * c->nE) +
+                                (size_t)RG_SMALL_SETS * RG_NATTR;
+            RG_CUDA_OK(cudaMallocHost(&c->h_pin, want * sizeof(double)));
+            c->h_pin_n = want;
+        }
+        double *h_par = c->h_pin, *h_out = h_par + n_par, *h_at = h_out + n_out;
+        RG_TRY(ensure_dev(&c->d_stage_par, &c->d_stage_par_n, n_par));
+        RG_TRY(ensure_dev(&c->d_stage_out, &c->d_stage_out_n, n_out));
+        RG_TRY(ensure_dev(&c->d_stage_attr, &c->d_stage_attr_n, n_at));
+        memcpy(h_par, params, n_par * sizeof(double));
+        RG_CUDA_OK(cudaMemcpyAsync(c->d_stage_par, h_par, n_par * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        int rc = eval_batch_impl(c, c->d_stage_par, P, model, dr_dex, flags, c->d_stage_out, c->d_stage_attr, c->stream, 0,
+                                 nullptr, nullptr, true);
+        if (rc != RG_OK) return rc;
+        RG_CUDA_OK(cudaMemcpyAsync(h_out, c->d_stage_out, n_out * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        RG_CUDA_OK(cudaMemcpyAsync(h_at, c->d_stage_attr, n_at * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        RG_CUDA_OK(cudaStreamSynchronize(c->stream));
+        const int ann_cap = P * (int)std::min(100000.0, dr_dex * 8.0 + 3.0);
+        bool fits = c->h_counter[1] <= ann_cap && c->h_counter[0] + c->h_counter[2] <= c->farr_cap;
+        for (int i = 0; i < P && fits; i++) fits = (int)h_at[(size_t)i * RG_NATTR + RG_A_STATUS] != RG_S_CAP;
+        if (fits) {
+            memcpy(out, h_out, n_out * sizeof(double));
+            if (attrs) memcpy(attrs, h_at, n_at * sizeof(double));
+            return RG_OK;
+        }
+        // a set outgrew the caps (dr_dex x 8 + 3 annuli, 40 Kompaneets systems per set): the counting path below
+    }
     int PIECE = 16384;
     if (const char *e = getenv("RG_PIECE_SETS")) { int v = atoi(e); if (v >= 1 && v <= 65536) PIECE = v; } // tuning / test knob
     const int SUPER = 262144;

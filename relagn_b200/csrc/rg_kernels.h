@@ -68,7 +68,8 @@ size_t rg_spectrum_smem_bytes(int NC, int nH, int HL, int HH, int warps, int fp3
 int rg_spectrum_pick_warps(int NC, int nH, int HL, int HH, int fp32);
 
 int rg_launch_setup(const double *d_params, int P, int model, double dr_dex, SetRec *recs, int *sys_counter,
-                    int2 *syslist, int sys_cap, double *rq_scratch, int rq_cap, double *d_attrs, cudaStream_t st);
+                    int2 *syslist, int sys_cap, double *rq_scratch, int rq_cap, double *d_attrs, int ann_cap,
+                    cudaStream_t st);
 
 // persistent: n_threads = total launched threads = rows of the [RG_NTH][n_threads] scratch planes
 int rg_launch_nthcomp(const SetRec *recs, const int2 *syslist, int n_warm_sys, int n_hot_sys, int sys_cap,

@@ -174,7 +174,7 @@ relqso_rhot_kernel(const double *__restrict__ params, int P, double *__restrict_
 __global__ void __launch_bounds__(128)
 setup_kernel(const double *__restrict__ params, int P, int model, double dr_dex, SetRec *__restrict__ recs,
              int *__restrict__ sys_counter, int2 *__restrict__ syslist, int sys_cap, double *__restrict__ rq_scratch,
-             int rq_cap, double *__restrict__ attrs)
+             int rq_cap, double *__restrict__ attrs, int ann_cap)
 {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= P) return;
@@ -249,6 +249,9 @@ setup_kernel(const double *__restrict__ params, int P, int model, double dr_dex,
             else r.flags |= RG_F_HOT_SEED_GE_KTE;
         }
         r.ann_base = atomicAdd(sys_counter + 1, r.n_disc + r.n_warm + r.n_hot); // rows of the shift-histogram arena
+        // (the small-batch path sizes the arenas from a cap instead of reading the counters back: a set that does not
+        //  fit is flagged and skipped by every later kernel; the host re-runs the batch through the counting path)
+        if (r.ann_base + r.n_disc + r.n_warm + r.n_hot > ann_cap) status = RG_S_CAP;
         int need_hot = (r.n_hot > 0 && r.has_hotshape) ? 1 : 0;
         r.sys_base = 0;
         r.hot_sys = 0;
@@ -514,6 +517,7 @@ nthcomp_kernel(const SetRec *__restrict__ recs, const int2 *__restrict__ syslist
         bool valid = li < nsys && (li < n_warm_sys || li >= n_warm_pad);
         const int sys = li < n_warm_pad ? li : hot_first + (li - n_warm_pad);
         int2 ent = valid ? syslist[sys] : make_int2(0, 0);
+        if (ent.x < 0) { valid = false; ent.x = 0; } // a row nobody reserved (the small-batch path scans up to a cap)
         const SetRec &r = recs[ent.x];
         valid = valid && r.status == RG_S_OK;
         const size_t so = valid ? (size_t)sys : 0;
@@ -548,7 +552,7 @@ nthcomp_interp_kernel(const SetRec *__restrict__ recs, const int2 *__restrict__ 
     const int li = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (li >= nsys || (li >= n_warm_sys && li < n_warm_pad)) return;
     const int sys = li < n_warm_pad ? li : hot_first + (li - n_warm_pad);
-    if (recs[syslist[sys].x].status != RG_S_OK) return;
+    if (syslist[sys].x < 0 || recs[syslist[sys].x].status != RG_S_OK) return;
     const double *hd = header + (size_t)sys * 4;
     const double xmin = hd[0], normfac = hd[1], lgx = hd[3];
     const double rxmin = 1.0 / xmin;
@@ -595,7 +599,8 @@ nthcomp_interp_kernel(const SetRec *__restrict__ recs, const int2 *__restrict__ 
 
 // ---------------------------------------------------------------------------
 int rg_launch_setup(const double *d_params, int P, int model, double dr_dex, SetRec *recs, int *sys_counter,
-                    int2 *syslist, int sys_cap, double *rq_scratch, int rq_cap, double *d_attrs, cudaStream_t st)
+                    int2 *syslist, int sys_cap, double *rq_scratch, int rq_cap, double *d_attrs, int ann_cap,
+                    cudaStream_t st)
 {
     RG_CUDA_OK(cudaMemsetAsync(sys_counter, 0, 3 * sizeof(int), st)); // [0] warm Kompaneets systems, [1] annuli, [2] hot shapes
     if (model == RG_MODEL_RELQSO) {
@@ -603,7 +608,7 @@ int rg_launch_setup(const double *d_params, int P, int model, double dr_dex, Set
         RG_CUDA_OK(cudaGetLastError());
     }
     RG_LAUNCH(setup_kernel, dim3((P + 127) / 128), dim3(128), 0, st, d_params, P, model, dr_dex, recs, sys_counter,
-              syslist, sys_cap, rq_scratch, rq_cap, d_attrs);
+              syslist, sys_cap, rq_scratch, rq_cap, d_attrs, ann_cap);
     RG_CUDA_OK(cudaGetLastError());
     return RG_OK;
 }
