@@ -839,6 +839,14 @@ static int eval_batch_impl(rg_ctx *c, const double *d_params, int P, int model, 
         const bool nth_first = getenv("RG_NTH_FIRST") != nullptr;
         auto launch_nth = [&]() -> int {
             if (nsys <= 0) return RG_OK;
+            if (nosync) { // small batches: the latency variant, one warp per system
+                RG_TRY(rg_launch_nthcomp_small(c->d_recs, c->d_syslist, n_warm_sys, n_hot_sys, c->farr_cap, c->d_p10,
+                                               reinterpret_cast<const double2 *>(c->d_edges), c->d_sc,
+                                               ((size_t)2 * RG_NTH + 1) * c->nth_threads, c->sm_count, c->gd, c->d_farr,
+                                               c->d_queue + 3, stats, st));
+                c->launches++;
+                return RG_OK;
+            }
             c->launches++; // nthcomp_interp_kernel
             RG_TRY(prof_begin(c, 1, st));
             RG_TRY(rg_launch_nthcomp(c->d_recs, c->d_syslist, n_warm_sys, n_hot_sys, c->farr_cap, c->d_p10, c->d_sc,

@@ -77,6 +77,11 @@ int rg_launch_nthcomp(const SetRec *recs, const int2 *syslist, int n_warm_sys, i
                       double *sc_g, double *sc_bet, int n_threads, double *sptot, double *header,
                       const GridDesc &grid, double *farr, unsigned long long *stats, cudaStream_t st);
 
+// latency variant of the Kompaneets kernels for small batches (rg_nthcomp_small.cu): one warp per system
+int rg_launch_nthcomp_small(const SetRec *recs, const int2 *syslist, int n_warm_sys, int n_hot_sys, int sys_cap,
+                            const double *p10tab, const double2 *edges, double *gscratch, size_t gscratch_doubles,
+                            int sm_count, const GridDesc &grid, double *farr, int *queue, unsigned long long *stats,
+                            cudaStream_t st);
 int rg_launch_spectrum(const SpecArgs &args, int sm_count, cudaStream_t st);
 int rg_launch_wienref(const SetRec *recs, int P, const double2 *edges, const double *hist, int hstride, int rel,
                       double2 *wien, cudaStream_t st);

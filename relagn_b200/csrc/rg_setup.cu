@@ -34,54 +34,98 @@ __device__ static double seed_temp(const SetRec &r, const NtConst &nt)
     return kT_seed;
 }
 
-__device__ static double lseed_sum(const SetRec &r, const NtConst &nt)
-{   // relagn.py:1227-1264 (summed top-down; the reference sums bottom-up)
-    BinIter it;
-    it.start(log10(r.r_h), log10(r.r_out), r.dlog_r);
-    double lo, hi, tot = 0;
-    double hc = r.r_h < r.hmax ? r.r_h : r.hmax;
-    double Rg2 = r.Rg * r.Rg;
-    while (it.next(lo, hi)) {
-        double dr = pow(10.0, hi) - pow(10.0, lo);
-        double rmid = pow(10.0, lo + r.dlog_r / 2);
-        double cov = 0;
-        if (hc <= rmid) {
-            double th0 = asin(hc / rmid);
-            cov = th0 - 0.5 * sin(2 * th0);
-        }
-        double Fr = RGK_SB * rg_tnt4(nt, rmid);
-        tot += 2 * 2 * RGK_PI * rmid * dr * Fr * cov / RGK_PI * Rg2;
-    }
-    return tot;
+// ---------------------------------------------------------------------------
+// Corona energetics (relagn.py:1227-1292), one WARP per parameter set: the seed-photon sum over the annuli r_h .. r_out
+// and the dissipation integral are a few hundred Novikov-Thorne evaluations each -- run by one thread they were 0.45 ms of
+// serial latency in front of every single-object evaluation (setup_kernel was one thread per set).  Lanes take annuli /
+// quadrature points in turn; partial sums are folded in a fixed order (lane-strided sums, then a butterfly), so the
+// result does not depend on the batch.
+#define LUM_BLOCK 256 // edges of the seed-photon grid a warp buffers at a time
+
+__device__ static double lum_warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
 }
 
-__device__ static double ldiss_quad(const SetRec &r, const NtConst &nt)
-{   // relagn.py:1285-1286: int_{risco}^{r_h} 2 sigma T^4 2 pi r Rg^2 dr, composite GL16 in ln r
-    if (!(r.r_h > r.risco)) return 0.0;
-    double ta = log(r.risco), tb = log(r.r_h);
-    int npan = 2 + (int)ceil((tb - ta) * 2.0);
-    if (npan > 16) npan = 16;
-    // 16-point Gauss-Legendre nodes/weights on [-1,1] (positive half)
-    const double RG_GL16_X[8] = {0.0950125098376374401853193, 0.2816035507792589132304605,
-                                 0.4580167776572273863424194, 0.6178762444026437484466718,
-                                 0.7554044083550030338951012, 0.8656312023878317438804679,
-                                 0.9445750230732325760779884, 0.9894009349916499325961542};
-    const double RG_GL16_W[8] = {0.1894506104550684962853967, 0.1826034150449235888667637,
-                                 0.1691565193950025381893121, 0.1495959888165767320815017,
-                                 0.1246289712555338720524763, 0.0951585116824927848099251,
-                                 0.0622535239386478928628438, 0.0271524594117540948517806};
-    double tot = 0;
-    for (int p = 0; p < npan; p++) {
-        double t0 = ta + (tb - ta) * p / npan, t1 = ta + (tb - ta) * (p + 1) / npan;
-        double tm = 0.5 * (t0 + t1), th = 0.5 * (t1 - t0);
-        double s = 0;
-        for (int i = 0; i < 8; i++) {
-            double rp = exp(tm + th * RG_GL16_X[i]), rm = exp(tm - th * RG_GL16_X[i]);
-            s += RG_GL16_W[i] * (rg_tnt4(nt, rp) * rp * rp + rg_tnt4(nt, rm) * rm * rm);
+__global__ void __launch_bounds__(128) lumin_kernel(SetRec *__restrict__ recs, int P, int model, double *__restrict__ attrs)
+{
+    __shared__ double s_edges[4][LUM_BLOCK + 1];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int set = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (set >= P) return;
+    SetRec &rr = recs[set];
+    if (rr.status != RG_S_OK && rr.status != RG_S_CAP) return;
+    const SetRec r = rr;
+    NtConst nt;
+    rg_nt_prepare(nt, r);
+    // ---- Ldiss: int_{risco}^{r_h} 2 sigma T^4 2 pi r Rg^2 dr, composite 16-point Gauss-Legendre in ln r (relagn.py:1285-1286)
+    double Ldiss = 0.0;
+    if (r.r_h > r.risco) {
+        const double ta = log(r.risco), tb = log(r.r_h);
+        int npan = 2 + (int)ceil((tb - ta) * 2.0);
+        if (npan > 16) npan = 16;
+        const double GX[8] = {0.0950125098376374401853193, 0.2816035507792589132304605, 0.4580167776572273863424194,
+                              0.6178762444026437484466718, 0.7554044083550030338951012, 0.8656312023878317438804679,
+                              0.9445750230732325760779884, 0.9894009349916499325961542};
+        const double GW[8] = {0.1894506104550684962853967, 0.1826034150449235888667637, 0.1691565193950025381893121,
+                              0.1495959888165767320815017, 0.1246289712555338720524763, 0.0951585116824927848099251,
+                              0.0622535239386478928628438, 0.0271524594117540948517806};
+        double s = 0.0;
+        for (int q = lane; q < npan * 8; q += 32) { // (panel, node pair)
+            const int p = q >> 3, i = q & 7;
+            const double t0 = ta + (tb - ta) * p / npan, t1 = ta + (tb - ta) * (p + 1) / npan;
+            const double tm = 0.5 * (t0 + t1), th = 0.5 * (t1 - t0);
+            const double rp = exp(tm + th * GX[i]), rm = exp(tm - th * GX[i]);
+            s += (GW[i] * (rg_tnt4(nt, rp) * rp * rp + rg_tnt4(nt, rm) * rm * rm)) * th;
         }
-        tot += s * th;
+        Ldiss = 2 * RGK_SB * 2 * RGK_PI * (r.Rg * r.Rg) * lum_warp_sum(s);
     }
-    return 2 * RGK_SB * 2 * RGK_PI * (r.Rg * r.Rg) * tot;
+    // ---- Lseed: sum over the annuli of _make_rbins(log r_h, log r_out) (relagn.py:1227-1264), top-down; lane 0 walks the
+    //      chain of repeated subtractions LUM_BLOCK edges at a time, the lanes evaluate the annuli
+    double Lseed = 0.0;
+    {
+        BinIter it;
+        it.start(log10(r.r_h), log10(r.r_out), r.dlog_r);
+        const double hc = r.r_h < r.hmax ? r.r_h : r.hmax;
+        const double Rg2 = r.Rg * r.Rg;
+        double *E = s_edges[wib];
+        double s = 0.0;
+        for (;;) {
+            int n = 0;
+            if (lane == 0) { // edges E[2k] = lo, E[2k+1] = hi of up to LUM_BLOCK / 2 annuli
+                double lo, hi;
+                while (n < LUM_BLOCK / 2 && it.next(lo, hi)) { E[2 * n] = lo; E[2 * n + 1] = hi; n++; }
+            }
+            n = __shfl_sync(0xffffffffu, n, 0);
+            __syncwarp();
+            for (int k = lane; k < n; k += 32) {
+                const double lo = E[2 * k], hi = E[2 * k + 1];
+                const double dr = pow(10.0, hi) - pow(10.0, lo);
+                const double rmid = pow(10.0, lo + r.dlog_r / 2);
+                double cov = 0;
+                if (hc <= rmid) {
+                    const double th0 = asin(hc / rmid);
+                    cov = th0 - 0.5 * sin(2 * th0);
+                }
+                const double Fr = RGK_SB * rg_tnt4(nt, rmid);
+                s += 2 * 2 * RGK_PI * rmid * dr * Fr * cov / RGK_PI * Rg2;
+            }
+            __syncwarp();
+            if (n < LUM_BLOCK / 2) break;
+        }
+        Lseed = lum_warp_sum(s);
+    }
+    if (lane == 0) {
+        rr.Ldiss = Ldiss; rr.Lseed = Lseed;
+        double gamma_h = r.gamma_h;
+        if (model == RG_MODEL_RELQSO) { gamma_h = (7.0 / 3) * pow(Ldiss / Lseed, -0.1); rr.gamma_h = gamma_h; }
+        if (attrs) {
+            double *at = attrs + (size_t)set * RG_NATTR;
+            at[RG_A_LDISS] = Ldiss; at[RG_A_LSEED] = Lseed; at[RG_A_GAMMA_H] = gamma_h;
+        }
+    }
 }
 
 // relqso._set_rhot (relagn.py:1877-1898): r_hot is the mid-radius of the fine-grid bin (1000 per decade, built
@@ -237,9 +281,8 @@ setup_kernel(const double *__restrict__ params, int P, int model, double dr_dex,
     }
     if (status == RG_S_OK) {
         r.lg_risco = log10(r.risco); r.lg_rh = log10(r.r_h); r.lg_rw = log10(r.r_w); r.lg_rout = log10(r.r_out);
-        r.Ldiss = ldiss_quad(r, nt);
-        r.Lseed = lseed_sum(r, nt);
-        if (model == RG_MODEL_RELQSO) r.gamma_h = (7.0 / 3) * pow(r.Ldiss / r.Lseed, -0.1);
+        // (Ldiss, Lseed and relqso's gamma_hot: lumin_kernel, one warp per set, right after this kernel)
+        r.Ldiss = 0.0; r.Lseed = 0.0;
         r.n_disc = (r.r_w != r.r_out) ? rg_count_bins(r.lg_rw, r.lg_rout, r.dlog_r) : 0;
         r.n_warm = (r.r_w != r.r_h) ? rg_count_bins(r.lg_rh, r.lg_rw, r.dlog_r) : 0;
         r.n_hot = (r.r_h != r.risco) ? rg_count_bins(r.lg_risco, r.lg_rh, r.dlog_r) : 0;
@@ -609,6 +652,8 @@ int rg_launch_setup(const double *d_params, int P, int model, double dr_dex, Set
     }
     RG_LAUNCH(setup_kernel, dim3((P + 127) / 128), dim3(128), 0, st, d_params, P, model, dr_dex, recs, sys_counter,
               syslist, sys_cap, rq_scratch, rq_cap, d_attrs, ann_cap);
+    RG_CUDA_OK(cudaGetLastError());
+    RG_LAUNCH(lumin_kernel, dim3((unsigned)(((size_t)P * 32 + 127) / 128)), dim3(128), 0, st, recs, P, model, d_attrs);
     RG_CUDA_OK(cudaGetLastError());
     return RG_OK;
 }
