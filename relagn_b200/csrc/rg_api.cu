@@ -164,6 +164,8 @@ extern "C" int rg_ctx_create(int device, rg_ctx **out)
         p10[RG_P10_RDP + j] = 1.0 / (p10[j + 1] - p10[j]);
         p10[RG_P10_W1 + j] = sqrt(p10[j] * p10[j + 1]);
         p10[RG_P10_RW1 + j] = 1.0 / p10[RG_P10_W1 + j];
+        // x[j] dphdot[j] per unit planck xmin^3 (pyNTHCOMP.py:120-122): x[j] / tempbb = 1e-4 10^(0.02 j) for every system
+        p10[RG_P10_DPH + j] = (p10[j] * p10[j] * p10[j]) / (exp(1e-4 * p10[j]) - 1);
     }
     RG_CUDA_OK(cudaMalloc(&c->d_p10, p10.size() * sizeof(double)));
     RG_CUDA_OK(cudaMemcpy(c->d_p10, p10.data(), p10.size() * sizeof(double), cudaMemcpyHostToDevice));
@@ -693,7 +695,8 @@ static int ensure_batch_scratch(rg_ctx *c, int model, int P)
         c->sys_cap = want * 40;
         RG_CUDA_OK(cudaMalloc(&c->d_recs, (size_t)want * sizeof(SetRec)));
         RG_CUDA_OK(cudaMalloc(&c->d_syslist, (size_t)c->sys_cap * sizeof(int2)));
-        RG_CUDA_OK(cudaMalloc(&c->d_sptot, (size_t)c->sys_cap * RG_SPT_STRIDE * sizeof(double)));
+        // (G', M) of every row of every system: what the forward sweep leaves for the back substitution (rg_setup.cu)
+        RG_CUDA_OK(cudaMalloc(&c->d_sptot, (size_t)c->sys_cap * RG_SPT_STRIDE * sizeof(double2)));
         RG_CUDA_OK(cudaMalloc(&c->d_header, (size_t)c->sys_cap * 4 * sizeof(double)));
         c->chunk_sets = want;
     }
@@ -849,10 +852,9 @@ static int eval_batch_impl(rg_ctx *c, const double *d_params, int P, int model, 
             }
             c->launches++; // nthcomp_interp_kernel
             RG_TRY(prof_begin(c, 1, st));
-            RG_TRY(rg_launch_nthcomp(c->d_recs, c->d_syslist, n_warm_sys, n_hot_sys, c->farr_cap, c->d_p10, c->d_sc,
-                                     c->d_sc + (size_t)RG_NTH * c->nth_threads,
-                                     c->d_sc + (size_t)2 * RG_NTH * c->nth_threads, nth_run, c->d_sptot,
-                                     c->d_header, c->gd, c->d_farr, stats, st));
+            RG_TRY(rg_launch_nthcomp(c->d_recs, c->d_syslist, n_warm_sys, n_hot_sys, c->farr_cap, c->d_p10, nth_run,
+                                     reinterpret_cast<double2 *>(c->d_sptot), c->d_header, c->sm_count, c->gd,
+                                     log10(c->h_ebins[0] + 0.5 * (c->h_ebins[1] - c->h_ebins[0])), c->d_farr, stats, st));
             RG_TRY(prof_end(c, 1, st));
             c->launches++;
             return RG_OK;

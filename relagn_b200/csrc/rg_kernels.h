@@ -71,11 +71,10 @@ int rg_launch_setup(const double *d_params, int P, int model, double dr_dex, Set
                     int2 *syslist, int sys_cap, double *rq_scratch, int rq_cap, double *d_attrs, int ann_cap,
                     cudaStream_t st);
 
-// persistent: n_threads = total launched threads = rows of the [RG_NTH][n_threads] scratch planes
+// n_threads = threads of the solve kernel's grid (systems are dealt round robin); coef = [sys_cap][RG_SPT_STRIDE] double2
 int rg_launch_nthcomp(const SetRec *recs, const int2 *syslist, int n_warm_sys, int n_hot_sys, int sys_cap,
-                      const double *p10tab, double *sc_gam,
-                      double *sc_g, double *sc_bet, int n_threads, double *sptot, double *header,
-                      const GridDesc &grid, double *farr, unsigned long long *stats, cudaStream_t st);
+                      const double *p10tab, int n_threads, double2 *coef, double *header, int sm_count,
+                      const GridDesc &grid, double lgE0, double *farr, unsigned long long *stats, cudaStream_t st);
 
 // latency variant of the Kompaneets kernels for small batches (rg_nthcomp_small.cu): one warp per system
 int rg_launch_nthcomp_small(const SetRec *recs, const int2 *syslist, int n_warm_sys, int n_hot_sys, int sys_cap,
@@ -125,11 +124,12 @@ double rg_row_x(double r);
 double rg_row_radius(double r_in, int NR, int s);
 double rg_r_valid(double a);
 
-// layout of the resident 10^(0.02 j) table (rg_ctx::d_p10): four runs of RG_NTH + 4 doubles
-#define RG_P10_RDP (3 * (RG_NTH + 4))       // 1 / (10^(0.02 (j+1)) - 10^(0.02 j)): reciprocal cell widths (interpolation kernel)
+// layout of the resident 10^(0.02 j) table (rg_ctx::d_p10): five runs of RG_NTH + 4 doubles
+#define RG_P10_DPH (3 * (RG_NTH + 4))       // 10^(0.06 j) / (exp(1e-4 10^(0.02 j)) - 1): seed photons x dphdot per unit planck xmin^3
+#define RG_P10_RDP (4 * (RG_NTH + 4))       // 1 / (10^(0.02 (j+1)) - 10^(0.02 j)): reciprocal cell widths (interpolation kernel)
 #define RG_P10_W1 (RG_NTH + 4)       // sqrt(10^(0.02 j) 10^(0.02 (j+1))): w1 of pyNTHCOMP.py:117 per unit xmin
 #define RG_P10_RW1 (2 * (RG_NTH + 4)) // 1 / that
-#define RG_P10_LEN (4 * (RG_NTH + 4))
+#define RG_P10_LEN (5 * (RG_NTH + 4))
 #ifndef RG_NTH_MINB
 #define RG_NTH_MINB 5 // resident 128-thread CTAs per SM of the persistent nthcomp grid
 #endif

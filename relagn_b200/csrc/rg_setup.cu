@@ -328,33 +328,42 @@ setup_kernel(const double *__restrict__ params, int P, int model, double dr_dex,
 }
 
 // ---------------------------------------------------------------------------
-// nthcomp: one thread per system, persistent grid.
-//   scratch planes gam, g: [RG_NTH][n_threads] (bet: row 0 only, the rest is recomputed), indexed by the launching
-//   thread (not the system) so the footprint is bounded by the resident
-//   threads; a warp's accesses to one j are contiguous.
-//   sptot arena: [sys][RG_SPT_STRIDE];  header: [sys][4] = xmin, normfac, jmax, log10(511 xmin);
-//   farr arena: [sys][nE] = the Comptonised spectrum on the caller's energy grid
-// Called by all 32 lanes of a warp together (`valid` = this lane has a system): the back substitution walks the
-// scratch rows in warp-uniform order so that a warp's loads of one row stay contiguous.
-#ifndef RG_NTH_WARPMAJOR
-#define RG_NTH_WARPMAJOR 1
-#endif
-#if RG_NTH_WARPMAJOR
-// warp-major scratch [warp][row][gamma | g][32 lanes]: the 512 bytes a warp writes per row follow each other in
-// memory, so the forward sweep streams through its own 450 kB region and the back substitution walks it in reverse --
-// DRAM pages see runs of rows instead of one 256-byte burst per row-major plane row (758 kB apart)
-#define SC_GAM(j) sc_gam[((size_t)(sys >> 5) * RG_NTH + (size_t)(j)) * 64 + (sys & 31)]
-#define SC_G(j) sc_gam[((size_t)(sys >> 5) * RG_NTH + (size_t)(j)) * 64 + 32 + (sys & 31)]
+// nthcomp: one thread per system runs the coefficient phase and the FORWARD sweep of the Thomas algorithm
+// (pyNTHCOMP.py:80-242) and leaves, per row, the two numbers the back substitution needs; the back substitution
+// itself is a first-order linear recurrence and runs in nthcomp_interp_kernel as a warp scan, fused with the
+// interpolation onto the caller's grid.  Nothing is read back here: the kernel has no memory stalls to hide.
+//   coef arena: [sys][RG_SPT_STRIDE] double2 = (G'_j, M_j), see below;  header: [sys][4] = xmin, c0, jmax + 1024 jstop,
+//   log10(511 xmin);  farr arena: [sys][nE] = the Comptonised spectrum on the caller's energy grid
+//
+// The reference's back substitution is u[j] = g[j] - gam[j] u[j+1] (pyNTHCOMP.py:243-247) followed by
+// sptot[j] = x[j]^4 u[j] bet[j] tautom (pyNTHCOMP.py:249, 170-171).  With s_j = x[j]^4 bet[j] tautom and v_j = s_j u[j]
+// (= sptot[j]) this is v_j = G'_j - M_j v_{j+1}, G'_j = s_j g[j], M_j = gam[j] s_j / s_{j+1}: the row scale moves into
+// the forward sweep, where bet[j] is at hand, and the back substitution is one fused multiply-add per row.
+// s_j / s_{j+1} = 10^-0.08 bet[j] / bet[j+1], and 1 / bet[j+1] is the denominator of pyNTHCOMP.py:141,147 times
+// tautom -- no extra division.  (Differences against the reference's operation order: a few 1e-16 per row.)
+//
+// Rows the caller's grid cannot reach are not stored: the interpolation (pyNTHCOMP.py:57-76) touches the rows from the
+// cell of the first grid energy upwards and the two rows around 1 keV (normalisation, pyNTHCOMP.py:49-56); the
+// recurrence runs from the top of the grid downwards, so it can stop at `jstop`.
+// a thread's stores walk its own system's rows, 16 bytes per row: the two halves of a 32-byte sector arrive one row
+// apart, so the line must stay in L2 until then (default policy; RG_COEF_STREAM=1: evict-first, for the A/B)
+#if defined(RG_COEF_STREAM) && RG_COEF_STREAM
+#define RG_COEF_ST(p, v) RG_STCS2((p), (v))
 #else
-#define SC_GAM(j) sc_gam[(size_t)(j) * sc_stride + sys]
-#define SC_G(j) sc_g[(size_t)(j) * sc_stride + sys]
+#define RG_COEF_ST(p, v) (*(p) = (v))
 #endif
-__device__ static void nthcomp_system(bool valid, const SetRec &r, int which, const double *p10tab,
-                                      double *__restrict__ sc_gam, double *__restrict__ sc_g,
-                                      double *__restrict__ sc_bet, size_t sc_stride, int slot, double *__restrict__ spt,
-                                      double *__restrict__ hd)
+#define RG_NTH_Q4 0.83176377110267100 // 10^-0.08 = (x[j] / x[j+1])^4
+__device__ __forceinline__ int rg_nth_jstop(double lgx, double lgE0)
 {
-    const int sys = slot; // scratch column of this thread
+    // 3 rows of margin below the cell of the lowest energy needed (the cursor's start value is within one row)
+    const double lo = lgE0 < 0.0 ? lgE0 : 0.0;
+    const double f = floor((lo - lgx) * 50.0) - 3.0;
+    return f < 1.0 ? 1 : (f > 1000.0 ? 1000 : (int)f);
+}
+
+__device__ static void nthcomp_system(bool valid, const SetRec &r, int which, const double *p10tab, double lgE0,
+                                      double2 *__restrict__ coef, double *__restrict__ hd)
+{
     double gamma = 2.0, kte = 1.0, ktbb = 0.01;
     if (!valid) {
     } else if (which < 0) { // hot shape: relagn.py:1200-1223
@@ -378,11 +387,13 @@ __device__ static void nthcomp_system(bool valid, const SetRec &r, int which, co
     double xmin = 1e-4 * tempbb, xmax = 40.0 * theta;
     int jmax = (int)(log10(xmax / xmin) / delta) + 1;
     if (jmax > 899) jmax = 899;
+    const double lgx = log10(511.0 * xmin);
     if (valid && jmax < 4) { // degenerate grid: the reference would index out of range; flag as empty
-        hd[0] = xmin; hd[1] = 0.0; hd[2] = 0.0; hd[3] = log10(511.0 * xmin);
+        hd[0] = xmin; hd[1] = 0.0; hd[2] = 0.0; hd[3] = lgx;
         valid = false;
     }
-    if (!valid) jmax = 0; // idle lane: both sweeps fall through, the warp collectives below still see it
+    if (!valid) return;
+    const int jstop = rg_nth_jstop(lgx, lgE0);
     int jmaxth = (int)(log10(50 * tempbb / xmin) / delta);
     if (jmaxth > 900) jmaxth = 900;
     if (jmaxth > jmax) jmaxth = jmax;
@@ -397,7 +408,7 @@ __device__ static void nthcomp_system(bool valid, const SetRec &r, int which, co
     double c20 = tautom / deltal;
     double tod = theta / deltal;
 
-    // rolling values: x[j-1], x[j], x[j+1], c2[j-1], c2[j]
+    // rolling values: x[j], x[j+1], c2[j-1]
     double xm = xmin * p10tab[0], x0 = xmin * p10tab[1], xp;
     double x32 = sqrt(xm * x0);
     double aa = (tod / x32 + 0.5) / (tod / x32 - 0.5);
@@ -407,7 +418,7 @@ __device__ static void nthcomp_system(bool valid, const SetRec &r, int which, co
     // w2[j] = sqrt(x[j-1] x[j]) is w1[j-1], and theta/deltal/w2[j] the previous step's theta/deltal/w1: carried over
     // (same operands, same operations: bit-identical to recomputing them as pyNTHCOMP.py:211-212 does)
     double tow1_prev = tod / x32;
-    // bet[0]
+    double b0; // bet[0]
     {
         double w = xm, rel;
         if (w <= 0.05) rel = (1.0 - 2.0 * w + 26.0 * w * w * 0.2);
@@ -416,18 +427,15 @@ __device__ static void nthcomp_system(bool valid, const SetRec &r, int which, co
             double z5 = z3 / 2.0 / w, z6 = (1.0 + 3.0 * w) / z2 / z2;
             rel = (0.75 * (z1 * (z4 - z3) + z5 - z6));
         }
-        double b0;
         if (0 < jnr - 1) b0 = 1.0 / tautom / (1.0 + tautom * rel / 3.0);
         else if (0 < jrel) { double flz = 1 - (w - xnr) / (xr - xnr); b0 = 1.0 / tautom / (1.0 + tautom * rel / 3.0 * flz); }
         else b0 = 1.0 / tautom;
-        if (valid) { sc_bet[sys] = b0; SC_GAM(0) = 0; SC_G(0) = 0; }
     }
-    const double itau = 1.0 / tautom, rxr = 1.0 / (xr - xnr), itbb = 1.0 / tempbb, todx = tod / xmin;
+    const double itau = 1.0 / tautom, rxr = 1.0 / (xr - xnr), todx = tod / xmin;
     const double third = 1.0 / 3.0;
-    // bet[j] of pyNTHCOMP.py:124-148 at x = x[j] (j >= 1); a pure function of the row, so the back substitution can
-    // recompute it bit for bit instead of reading a third scratch plane back (the solve is bound by the
-    // HBM round trip of the planes, not by instructions: 37 -> 34 ms per 125 000 sets)
-    auto bet_at = [&](int j, double w) -> double {
+    // bet[j] of pyNTHCOMP.py:124-148 at x = x[j] (j >= 1) and its denominator (bet = 1 / tautom / den)
+    auto bet_at = [&](int j, double w, double &den) -> double {
+        den = 1.0;
         if (j >= jrel) return itau;
         double rel;
         if (w <= 0.05) rel = (1.0 - 2.0 * w + 26.0 * w * w * 0.2);
@@ -440,20 +448,27 @@ __device__ static void nthcomp_system(bool valid, const SetRec &r, int which, co
             rel = (0.75 * (z1 * (z4 - z3) + z5 - z6));
         }
         const double taukn = tautom * rel;
-        if (j < jnr - 1) return itau * __drcp_rn(1.0 + taukn * third);
-        const double flz = 1 - (w - xnr) * rxr;
-        return itau * __drcp_rn(1.0 + taukn * third * flz);
+        if (j < jnr - 1) den = 1.0 + taukn * third;
+        else den = 1.0 + taukn * third * (1 - (w - xnr) * rxr);
+        return itau * __drcp_rn(den);
     };
+    // seed photons (pyNTHCOMP.py:120-122): x[j] / tempbb = 1e-4 10^(0.02 j) for every system, so
+    // d[j] = x[j] dphdot[j] = (planck xmin^3) 10^(0.06 j) / (exp(1e-4 10^(0.02 j)) - 1) comes from a resident table
+    const double pk3 = planck * (xmin * xmin * xmin);
+    double den_cur, den_nxt;
+    double bet_cur = bet_at(1, x0, den_cur), bet_nxt;
+    // sptot[0] = s_0 aa u[1] = c0 v_1 (pyNTHCOMP.py:248)
+    const double c0 = aa * (RG_NTH_Q4 * b0) * (tautom * den_cur);
+    hd[0] = xmin; hd[1] = c0; hd[2] = (double)(jmax + 1024 * jstop); hd[3] = lgx;
     for (int j = 1; j < jmax - 1; j++) {
         xp = xmin * p10tab[j + 1];
+        bet_nxt = bet_at(j + 1, xp, den_nxt);
         // w1 = sqrt(x[j] x[j+1]) = xmin 10^(0.02 j + 0.01) and theta / deltal / w1 from the resident tables: no
         // square root and one division less per row (last-bit differences against pyNTHCOMP.py:117,211)
         const double w1j = xmin * p10tab[RG_P10_W1 + j];
         // (quotients as reciprocal multiplies: rcp.rn + mul instead of div.rn, last-bit differences)
         double c2j = (w1j * w1j * w1j * w1j) * __drcp_rn(1.0 + 4.60 * w1j + 1.1 * w1j * w1j);
-        // rel, bet at j
-        const double betj = bet_at(j, x0);
-        double dph = (j < jmaxth) ? planck * (x0 * x0) * __drcp_rn(rg_exp_pos(x0 * itbb) - 1) : 0.0;
+        const double betj = bet_cur;
         // coefficients (pyNTHCOMP.py:210-221)
         const double tow1 = todx * p10tab[RG_P10_RW1 + j], tow2 = tow1_prev;
         double aj = -c20 * c2j * (tow1 + 0.5);
@@ -462,99 +477,41 @@ __device__ static void nthcomp_system(bool valid, const SetRec &r, int which, co
         double t3 = (x0 * x0 * x0) * (tautom * betj);
         double bj = t1 + t2 + t3;
         double cj = c20 * c2m * (0.5 - tow2);
-        double dj = x0 * dph;
-        // Thomas forward sweep (pyNTHCOMP.py:233-242)
-        // one reciprocal of the pivot serves both quotients (pyNTHCOMP.py:234-241)
+        double dj = (j < jmaxth) ? pk3 * p10tab[RG_P10_DPH + j] : 0.0;
+        // Thomas forward sweep (pyNTHCOMP.py:233-242); one reciprocal of the pivot serves both quotients
         double alp, gj;
         if (j == 1) alp = bj + cj * aa; else alp = bj - cj * gam_prev;
         const double ralp = 1.0 / alp;
         if (j == 1) gj = dj * ralp; else gj = (dj - cj * g_prev) * ralp;
         double gamj = aj * ralp;
-        RG_STCS(&SC_GAM(j), gamj); RG_STCS(&SC_G(j), gj); // streamed: read back once
+        if (j >= jstop) {
+            const double sj = x0 * t3;                                      // x^4 bet tautom
+            const double ratio = (RG_NTH_Q4 * betj) * (tautom * den_nxt);   // s_j / s_{j+1}
+            RG_COEF_ST(&coef[j], make_double2(sj * gj, gamj * ratio));
+        }
         gam_prev = gamj; g_prev = gj;
-        xm = x0; x0 = xp; c2m = c2j; tow1_prev = tow1;
+        x0 = xp; c2m = c2j; tow1_prev = tow1; bet_cur = bet_nxt; den_cur = den_nxt;
     }
-    // back substitution (pyNTHCOMP.py:243-249) and sptot = dphesc x^2 (pyNTHCOMP.py:170-171)
-    double u_next = 0.0; // u[jmax-1]
-    double u1 = 0.0;
-    if (valid) { spt[jmax] = 0.0; spt[jmax - 1] = 0.0; }
-    // The scratch planes are far larger than L2, so the reads below come from HBM.  Neighbouring lanes hold systems
-    // whose jmax differ by a step or two: the warp walks the rows from its highest jmax down TOGETHER (a lane joins
-    // when the row reaches its own jmax - 2), so every row is read as one contiguous run of the plane instead of 32
-    // scattered sectors.  The loads of 4 rows are issued together (their addresses do not depend on u), then the
-    // dependent recurrence runs on registers.
-    const int jtop_me = jmax - 2;
-    const int jtop = __reduce_max_sync(0xffffffffu, jtop_me);
-    // The next group's loads are in flight while the current group's dependent chain runs (register double buffer).
-    double gg[4] = {0, 0, 0, 0}, gm[4] = {0, 0, 0, 0};
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        if (jtop - q >= 1 && jtop - q <= jtop_me) {
-            gg[q] = RG_LDCS(&SC_G(jtop - q)); gm[q] = RG_LDCS(&SC_GAM(jtop - q));
-        }
-    }
-    for (int jj = jtop; jj >= 1;) {
-        const int nb = jj >= 4 ? 4 : jj; // rows jj, jj-1, ..., jj-nb+1
-        const int jn = jj - nb;          // first row of the next group
-        double ngg[4] = {0, 0, 0, 0}, ngm[4] = {0, 0, 0, 0};
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            if (jn - q >= 1 && jn - q <= jtop_me) {
-                ngg[q] = RG_LDCS(&SC_G(jn - q)); ngm[q] = RG_LDCS(&SC_GAM(jn - q));
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            if (q < nb && jj - q <= jtop_me) {
-                double u = gg[q] - gm[q] * u_next;
-                double x = xmin * p10tab[jj - q];
-                const double btq = bet_at(jj - q, x); // recomputed: no third scratch plane
-                spt[jj - q] = (x * x * u * btq * tautom) * (x * x);
-                u_next = u;
-                if (jj - q == 1) u1 = u;
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < 4; q++) { gg[q] = ngg[q]; gm[q] = ngm[q]; }
-        jj = jn;
-    }
-    if (!valid) return;
-    {
-        double u = aa * u1;
-        double x = xmin * p10tab[0];
-        spt[0] = (x * x * u * sc_bet[sys] * tautom) * (x * x);
-    }
-    // normalisation at 1 keV (pyNTHCOMP.py:49-56)
-    double xx = 1.0 / 511.0;
-    int ih = 1;
-    while (ih < jmax && xx > xmin * p10tab[ih]) ih++;
-    int il = ih - 1;
-    double xl = xmin * p10tab[il], xh = xmin * p10tab[ih];
-    double spp = spt[il] + (spt[ih] - spt[il]) * (xx - xl) / (xh - xl);
-    const double normfac = 1.0 / spp;
-    hd[0] = xmin; hd[1] = normfac; hd[2] = (double)jmax; hd[3] = log10(511.0 * xmin);
 }
 
 __global__ void __launch_bounds__(128, RG_NTH_MINB)
 nthcomp_kernel(const SetRec *__restrict__ recs, const int2 *__restrict__ syslist, int nsys, int n_warm_sys, int n_warm_pad,
-               int hot_first,
-               const double *__restrict__ p10tab, double *__restrict__ sc_gam, double *__restrict__ sc_g,
-               double *__restrict__ sc_bet, int n_threads, double *__restrict__ sptot, double *__restrict__ header,
-               unsigned long long *stats)
+               int hot_first, const double *__restrict__ p10tab, int n_threads, double lgE0,
+               double2 *__restrict__ coef, double *__restrict__ header, unsigned long long *stats)
 {
-    // 10^(0.02 j) is read at every step of both sweeps: keep it in shared memory (the scratch stream would keep
-    // evicting it from L1)
-    __shared__ double s_p10[RG_P10_RW1 + RG_NTH + 4]; // 10^(0.02 j) | w1 | 1 / w1
+    // the resident tables are read at every row: keep them in shared memory
+    __shared__ double s_p10[RG_P10_RDP]; // 10^(0.02 j) | w1 | 1 / w1 | seed photons
     for (int i = threadIdx.x; i < RG_NTH + 4; i += blockDim.x) {
         s_p10[i] = p10tab[i];
         s_p10[RG_P10_W1 + i] = p10tab[RG_P10_W1 + i];
         s_p10[RG_P10_RW1 + i] = p10tab[RG_P10_RW1 + i];
+        s_p10[RG_P10_DPH + i] = p10tab[RG_P10_DPH + i];
     }
     __syncthreads();
     int gtid = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long sumj = 0, nsolved = 0;
     const int lane = threadIdx.x & 31;
-    for (int s0 = gtid - lane; s0 < nsys; s0 += n_threads) { // warp-uniform trip count: the lanes solve together
+    for (int s0 = gtid - lane; s0 < nsys; s0 += n_threads) {
         // logical index -> arena row: the warm systems fill rows [0, n_warm_sys), the hot shapes the top of the arena
         const int li = s0 + lane;
         bool valid = li < nsys && (li < n_warm_sys || li >= n_warm_pad);
@@ -564,10 +521,9 @@ nthcomp_kernel(const SetRec *__restrict__ recs, const int2 *__restrict__ syslist
         const SetRec &r = recs[ent.x];
         valid = valid && r.status == RG_S_OK;
         const size_t so = valid ? (size_t)sys : 0;
-        nthcomp_system(valid, r, ent.y, s_p10, sc_gam, sc_g, sc_bet, (size_t)n_threads, gtid,
-                       sptot + so * RG_SPT_STRIDE, header + so * 4);
+        nthcomp_system(valid, r, ent.y, s_p10, lgE0, coef + so * RG_SPT_STRIDE, header + so * 4);
         if (valid) {
-            sumj += (unsigned long long)header[(size_t)sys * 4 + 2];
+            sumj += (unsigned long long)((int)header[(size_t)sys * 4 + 2] & 1023);
             nsolved++;
         }
     }
@@ -577,66 +533,187 @@ nthcomp_kernel(const SetRec *__restrict__ recs, const int2 *__restrict__ syslist
     }
 }
 
-// donthcomp's interpolation of the Kompaneets solution onto the caller's grid (pyNTHCOMP.py:57-76), then * h / keV
-// (relagn.py:929-930, 1217-1218): one warp per system, lanes over consecutive energy bins (coalesced stores).
-// The reference's monotone cursor is restated as a direct search seeded from log10(E) and fixed up with the
-// reference's own comparisons, so every bin lands in exactly the cell the cursor would have reached.
-__global__ void __launch_bounds__(256)
+// Back substitution + donthcomp's interpolation of the Kompaneets solution onto the caller's grid
+// (pyNTHCOMP.py:243-249, 49-76), then * h / keV (relagn.py:929-930, 1217-1218).  A CTA of 8 warps takes 8 systems
+// at a time:
+//  A. one warp per system: v_j = G'_j - M_j v_{j+1} from the top row down to jstop, 32 rows per step -- every lane
+//     holds the affine map of its row, five shuffle steps compose them (Kogge-Stone), the value entering from above
+//     is applied last.  The rows go into the warp's shared-memory copy of sptot (the solution never exists in HBM);
+//     then the normalisation at 1 keV.
+//  B. one warp per eighth of the energy grid, for all 8 systems: a pass loads the grid values of its 32 bins once and
+//     uses them for 8 systems (with one warp per system the four grid arrays were re-read from L2 by every system:
+//     the shared-memory copies leave too little L1 to hold them, r2r).  The reference's monotone cursor is restated as
+//     a direct search seeded from log10(E) and fixed up with the reference's own comparisons, so every bin lands in
+//     exactly the cell the cursor would have reached.  The first lane of a warp's first pass computes the bin in front
+//     of the warp's range, for the trapezoid of pyNTHCOMP.py:75 only.
+#define RG_INTERP_WARPS 8
+#ifndef RG_INTERP_GROUP
+#define RG_INTERP_GROUP 4 // steps of 32 rows whose loads are in flight together
+#endif
+#define RG_INTERP_ROWS (RG_NTH + 4)
+#ifndef RG_INTERP_PASSES
+#define RG_INTERP_PASSES 4 // passes of 32 bins per register-resident chunk of the grid (1000 bins / 8 warps + 1)
+#endif
+__global__ void __launch_bounds__(RG_INTERP_WARPS * 32)
 nthcomp_interp_kernel(const SetRec *__restrict__ recs, const int2 *__restrict__ syslist, int nsys, int n_warm_sys,
-                      int n_warm_pad, int hot_first, const double *__restrict__ p10tab, const double *__restrict__ sptot,
+                      int n_warm_pad, int hot_first, const double *__restrict__ p10tab, const double2 *__restrict__ coef,
                       const double *__restrict__ header, GridDesc grid, double *__restrict__ farr)
 {
-    __shared__ double s_p10[RG_NTH + 4];
-    __shared__ double s_rdp[RG_NTH + 4]; // 1 / (10^(0.02 (j+1)) - 10^(0.02 j)): the cell width of the x grid, per unit xmin
+    RG_DYN_SMEM(smem_raw);
+    double *s_p10 = reinterpret_cast<double *>(smem_raw);
+    double *s_rdp = s_p10 + RG_INTERP_ROWS; // 1 / (10^(0.02 (j+1)) - 10^(0.02 j)): the cell width of the x grid, per unit xmin
+    double *s_vall = s_rdp + RG_INTERP_ROWS; // [warp][row]: sptot of the 8 systems
+    double *s_sc = s_vall + (size_t)RG_INTERP_WARPS * RG_INTERP_ROWS; // [warp][4]: xmin, 1 / xmin, log10(511 xmin), normfac
+    int *s_nth = reinterpret_cast<int *>(s_sc + 4 * RG_INTERP_WARPS); // [warp]: rows, -1 = no system here
+    int *s_row = s_nth + RG_INTERP_WARPS;                            // [warp]: arena row of the system
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *s_v = s_vall + (size_t)warp * RG_INTERP_ROWS;
     for (int i = threadIdx.x; i < RG_NTH + 4; i += blockDim.x) s_p10[i] = p10tab[i];
     for (int i = threadIdx.x; i < RG_NTH + 3; i += blockDim.x) s_rdp[i] = p10tab[RG_P10_RDP + i];
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int li = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (li >= nsys || (li >= n_warm_sys && li < n_warm_pad)) return;
-    const int sys = li < n_warm_pad ? li : hot_first + (li - n_warm_pad);
-    if (syslist[sys].x < 0 || recs[syslist[sys].x].status != RG_S_OK) return;
-    const double *hd = header + (size_t)sys * 4;
-    const double xmin = hd[0], normfac = hd[1], lgx = hd[3];
-    const double rxmin = 1.0 / xmin;
+    const unsigned FULL = 0xffffffffu;
+    const int nE = grid.nE;
     // photon flux -> W/Hz (relagn.py:929-930) folded into the normalisation
     const double outfac = (1.0 / RGK_KEV) * RGK_H;
-    const int nth = (int)hd[2];
-    const double *spt = sptot + (size_t)sys * RG_SPT_STRIDE;
-    double *F = farr + (size_t)sys * grid.nE;
-    const int nE = grid.nE;
-    double carry_pr = 0.0, carry_e = 0.0; // bin i0 - 1 of the previous pass
-    for (int i0 = 0; i0 < nE; i0 += 32) {
-        const int i = i0 + lane;
-        double e = 0.0, pr = 0.0;
-        if (i < nE) {
-            e = __ldg(grid.Egrid + i);
-            int j = (int)ceil((__ldg(grid.lgE + i) - lgx) * 50.0);
-            if (j < 0) j = 0;
-            if (j > nth + 1) j = nth + 1;
-            while (j > 0 && !(511.0 * (xmin * s_p10[j - 1]) < e)) j--;
-            while (j <= nth && 511.0 * (xmin * s_p10[j]) < e) j++;
-            double prim = 0.0;
-            if (j <= nth) {
-                if (j > 0) {
-                    const int jl = j - 1;
-                    // linear interpolation inside the cell [xl, xh] (pyNTHCOMP.py:66-71); the division by the cell
-                    // width is a multiplication by (1 / xmin) (1 / (10^(0.02 (jl+1)) - 10^(0.02 jl)))
-                    const double xl = xmin * s_p10[jl];
-                    const double sl = spt[jl], sh = spt[jl + 1];
-                    prim = sl + ((__ldg(grid.e511 + i) - xl) * (sh - sl)) * (rxmin * s_rdp[jl]);
-                } else prim = spt[0];
+    // phase B: this warp's bins [b_lo, b_hi) and the passes that cover b_lo - 1 ... b_hi - 1
+    const int bpw = (nE + RG_INTERP_WARPS - 1) / RG_INTERP_WARPS;
+    const int b_lo = warp * bpw, b_hi = b_lo + bpw < nE ? b_lo + bpw : nE;
+    // The header of the next system is requested while the current one is processed: the chain system list -> set
+    // record -> header -> coefficient rows is four dependent trips to memory, and a warp has nothing else to do.
+    struct Hd { double xmin, c0, lgx; int packed, sys; };
+    auto fetch = [&](int li) -> Hd {
+        Hd h; h.xmin = 1.0; h.c0 = 0.0; h.lgx = 0.0; h.packed = -1; h.sys = 0;
+        if (li >= nsys || (li >= n_warm_sys && li < n_warm_pad)) return h;
+        h.sys = li < n_warm_pad ? li : hot_first + (li - n_warm_pad);
+        const int set = __ldg(&syslist[h.sys].x);
+        if (set < 0 || recs[set].status != RG_S_OK) return h;
+        const double *hd = header + (size_t)h.sys * 4;
+        h.xmin = __ldg(hd); h.c0 = __ldg(hd + 1); h.packed = (int)__ldg(hd + 2); h.lgx = __ldg(hd + 3);
+        return h;
+    };
+    const int stride = gridDim.x * RG_INTERP_WARPS;
+    Hd nxt = fetch(blockIdx.x * RG_INTERP_WARPS + warp);
+    for (int base = blockIdx.x * RG_INTERP_WARPS; base < nsys; base += stride) {
+        const Hd cur = nxt;
+        nxt = fetch(base + warp + stride);
+        // ---- A. back substitution and normalisation of system base + warp ----
+        int nth = cur.packed < 0 ? -1 : (cur.packed & 1023);
+        if (nth >= 0 && nth < 4) nth = 0; // degenerate grid (flagged by the solve): the spectrum is empty
+        if (nth > 0) {
+            const int jstop = cur.packed >> 10;
+            const double xmin = cur.xmin, lgx = cur.lgx;
+            const double2 *cf = coef + (size_t)cur.sys * RG_SPT_STRIDE;
+            const int jtop = nth - 2; // rows jtop down to jstop
+            for (int j = lane; j < jstop && j <= nth; j += 32) s_v[j] = 0.0; // rows below jstop: never referenced
+            if (lane < 2) s_v[nth - 1 + lane] = 0.0;                        // sptot[jmax-1], sptot[jmax] (pyNTHCOMP.py:170)
+            double carry = 0.0; // v of the row above the current step (u[jmax-1] = 0)
+            // the rows of RG_INTERP_GROUP steps are requested together (their addresses do not depend on the recurrence)
+            for (int jg = jtop; jg >= jstop; jg -= 32 * RG_INTERP_GROUP) {
+                double2 c[RG_INTERP_GROUP];
+#pragma unroll
+                for (int q = 0; q < RG_INTERP_GROUP; q++) {
+                    const int j = jg - 32 * q - lane;
+                    c[q] = j >= jstop ? RG_LDCS2(&cf[j]) : make_double2(0.0, 0.0);
+                }
+#pragma unroll
+                for (int q = 0; q < RG_INTERP_GROUP; q++) {
+                    const int j = jg - 32 * q - lane;
+                    if (jg - 32 * q < jstop) break; // warp-uniform
+                    double A = -c[q].y, B = c[q].x; // v_j = A v_{j+1} + B
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const double Ap = __shfl_up_sync(FULL, A, d), Bp = __shfl_up_sync(FULL, B, d);
+                        if (lane >= d) { B = fma(A, Bp, B); A = A * Ap; }
+                    }
+                    const double v = fma(A, carry, B);
+                    if (j >= jstop) s_v[j] = v;
+                    carry = __shfl_sync(FULL, v, 31);
+                }
             }
-            pr = prim * __ldg(grid.rear2 + i); // prim / E^2 (pyNTHCOMP.py:75)
+            __syncwarp();
+            if (jstop <= 1 && lane == 0) s_v[0] = cur.c0 * s_v[1];
+            __syncwarp();
+            // normalisation at 1 keV (pyNTHCOMP.py:49-56)
+            const double xx = 1.0 / 511.0;
+            int ih = (int)ceil((0.0 - lgx) * 50.0);
+            if (ih < 1) ih = 1;
+            if (ih > nth) ih = nth;
+            while (ih > 1 && !(xx > xmin * s_p10[ih - 1])) ih--;
+            while (ih < nth && xx > xmin * s_p10[ih]) ih++;
+            const int il = ih - 1;
+            const double xl = xmin * s_p10[il], xh = xmin * s_p10[ih];
+            const double spp = s_v[il] + (s_v[ih] - s_v[il]) * (xx - xl) / (xh - xl);
+            if (lane == 0) {
+                s_sc[4 * warp] = xmin; s_sc[4 * warp + 1] = 1.0 / xmin; s_sc[4 * warp + 2] = lgx;
+                s_sc[4 * warp + 3] = 1.0 / spp;
+            }
         }
-        double pr_prev = __shfl_up_sync(0xffffffffu, pr, 1), e_prev = __shfl_up_sync(0xffffffffu, e, 1);
-        if (lane == 0) { pr_prev = carry_pr; e_prev = carry_e; }
-        if (i < nE) {
-            const double ph = i > 0 ? (0.5 * (pr + pr_prev) * (e - e_prev) * normfac) : 0.0;
-            F[i] = ph * outfac;
+        if (lane == 0) { s_nth[warp] = nth; s_row[warp] = cur.sys; }
+        __syncthreads();
+        // ---- B. interpolation onto the grid (pyNTHCOMP.py:57-76): bins b_lo ... b_hi - 1 of all 8 systems ----
+        // in chunks of RG_INTERP_PASSES passes whose grid values stay in registers for the 8 systems; every chunk
+        // starts one bin early (lane 0 of its first pass supplies the left end of the first trapezoid only)
+        for (int c_lo = b_lo; c_lo < b_hi; c_lo += 32 * RG_INTERP_PASSES - 1) {
+            double ge[RG_INTERP_PASSES], glg[RG_INTERP_PASSES], ge5[RG_INTERP_PASSES], gr2[RG_INTERP_PASSES], gde[RG_INTERP_PASSES];
+#pragma unroll
+            for (int p = 0; p < RG_INTERP_PASSES; p++) {
+                const int i = c_lo - 1 + 32 * p + lane;
+                const bool in = i >= 0 && i < b_hi;
+                ge[p] = in ? __ldg(grid.Egrid + i) : 0.0;
+                glg[p] = in ? __ldg(grid.lgE + i) : 0.0;
+                ge5[p] = in ? __ldg(grid.e511 + i) : 0.0;
+                gr2[p] = in ? __ldg(grid.rear2 + i) : 0.0;
+                gde[p] = in && i > 0 ? ge[p] - __ldg(grid.Egrid + i - 1) : 0.0;
+            }
+            for (int q = 0; q < RG_INTERP_WARPS; q++) {
+                const int nq = s_nth[q];
+                if (nq < 0) continue; // warp-uniform
+                double *F = farr + (size_t)s_row[q] * nE;
+                const double xmin = s_sc[4 * q], rxmin = s_sc[4 * q + 1], lgx = s_sc[4 * q + 2], normfac = s_sc[4 * q + 3];
+                const double *v = s_vall + (size_t)q * RG_INTERP_ROWS;
+                double carry_pr = 0.0;
+#pragma unroll
+                for (int p = 0; p < RG_INTERP_PASSES; p++) {
+                    const int i0 = c_lo - 1 + 32 * p;
+                    if (i0 >= b_hi) break; // warp-uniform
+                    const int i = i0 + lane;
+                    const bool in = i >= 0 && i < b_hi;
+                    const bool store = in && !(p == 0 && lane == 0);
+                    if (nq == 0) { // degenerate Kompaneets grid: empty spectrum
+                        if (store) RG_STCG(&F[i], 0.0);
+                        continue;
+                    }
+                    const double e = ge[p];
+                    // The cursor of pyNTHCOMP.py:61-62 stops at the first row j with 511 x[j] >= E.  The start value is
+                    // that row unless E lies within rounding (1e-13 of a cell) of a cell boundary, where it can be one
+                    // off: one comparison on either side, the reference's own, settles it.
+                    int j = (int)ceil((glg[p] - lgx) * 50.0);
+                    j = j < 0 ? 0 : (j > nq + 1 ? nq + 1 : j);
+                    const int ja = j > 0 ? j - 1 : 0, jb = j <= nq ? j : nq;
+                    const bool below = j > 0 && !(511.0 * (xmin * s_p10[ja]) < e);   // the cursor would have stopped earlier
+                    const bool above = j <= nq && 511.0 * (xmin * s_p10[jb]) < e;    // ... or gone one further
+                    j += above ? 1 : (below ? -1 : 0);
+                    double prim = 0.0;
+                    if (j <= nq) {
+                        // linear interpolation inside the cell [xl, xh] (pyNTHCOMP.py:66-71); the division by the cell
+                        // width is a multiplication by (1 / xmin) (1 / (10^(0.02 (jl+1)) - 10^(0.02 jl)))
+                        const int jl = j > 0 ? j - 1 : 0;
+                        const double xl = xmin * s_p10[jl];
+                        const double sl = v[jl], sh = v[jl + 1];
+                        prim = j > 0 ? sl + ((ge5[p] - xl) * (sh - sl)) * (rxmin * s_rdp[jl]) : sl;
+                    }
+                    const double pr = in ? prim * gr2[p] : 0.0; // prim / E^2 (pyNTHCOMP.py:75)
+                    double pr_prev = __shfl_up_sync(FULL, pr, 1);
+                    if (lane == 0) pr_prev = carry_pr;
+                    if (store) {
+                        const double ph = i > 0 ? (0.5 * (pr + pr_prev) * gde[p] * normfac) : 0.0;
+                        RG_STCG(&F[i], ph * outfac);
+                    }
+                    carry_pr = __shfl_sync(FULL, pr, 31);
+                }
+            }
         }
-        carry_pr = __shfl_sync(0xffffffffu, pr, 31);
-        carry_e = __shfl_sync(0xffffffffu, e, 31);
+        __syncthreads();
     }
 }
 
@@ -708,9 +785,8 @@ int rg_launch_counters_out(const int *d_counter, int *h_mapped, cudaStream_t st)
 }
 
 int rg_launch_nthcomp(const SetRec *recs, const int2 *syslist, int n_warm_sys, int n_hot_sys, int sys_cap,
-                      const double *p10tab, double *sc_gam,
-                      double *sc_g, double *sc_bet, int n_threads, double *sptot, double *header,
-                      const GridDesc &grid, double *farr, unsigned long long *stats, cudaStream_t st)
+                      const double *p10tab, int n_threads, double2 *coef, double *header, int sm_count,
+                      const GridDesc &grid, double lgE0, double *farr, unsigned long long *stats, cudaStream_t st)
 {
     // logical order: the warm systems, padded to a whole warp, then the hot shapes -- no warp mixes the two kinds
     const int n_warm_pad = (n_warm_sys + 31) & ~31;
@@ -719,11 +795,22 @@ int rg_launch_nthcomp(const SetRec *recs, const int2 *syslist, int n_warm_sys, i
     if (nsys <= 0) return RG_OK;
     int blocks = (nsys + 127) / 128;
     if (blocks * 128 > n_threads) blocks = n_threads / 128;
-    RG_LAUNCH(nthcomp_kernel, dim3(blocks), dim3(128), 0, st, recs, syslist, nsys, n_warm_sys, n_warm_pad, hot_first, p10tab, sc_gam, sc_g, sc_bet,
-              blocks * 128, sptot, header, stats);
+    RG_LAUNCH(nthcomp_kernel, dim3(blocks), dim3(128), 0, st, recs, syslist, nsys, n_warm_sys, n_warm_pad, hot_first, p10tab,
+              blocks * 128, lgE0, coef, header, stats);
     RG_CUDA_OK(cudaGetLastError());
-    RG_LAUNCH(nthcomp_interp_kernel, dim3((unsigned)(((size_t)nsys * 32 + 255) / 256)), dim3(256), 0, st, recs, syslist,
-              nsys, n_warm_sys, n_warm_pad, hot_first, p10tab, sptot, header, grid, farr);
+    // persistent warps, one system at a time: tables + RG_INTERP_WARPS private sptot copies in shared memory
+    const size_t smem = (size_t)(2 + RG_INTERP_WARPS) * RG_INTERP_ROWS * sizeof(double) + (size_t)RG_INTERP_WARPS * (4 * sizeof(double) + 2 * sizeof(int));
+#ifndef RG_HOSTSIM
+    static bool attr_set = false;
+    if (!attr_set) {
+        RG_CUDA_OK(cudaFuncSetAttribute(nthcomp_interp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+#endif
+    long ictas = ((long)nsys + RG_INTERP_WARPS - 1) / RG_INTERP_WARPS;
+    if (ictas > 3L * sm_count) ictas = 3L * sm_count;
+    RG_LAUNCH(nthcomp_interp_kernel, dim3((unsigned)ictas), dim3(RG_INTERP_WARPS * 32), smem, st, recs, syslist,
+              nsys, n_warm_sys, n_warm_pad, hot_first, p10tab, coef, header, grid, farr);
     RG_CUDA_OK(cudaGetLastError());
     return RG_OK;
 }
