@@ -854,7 +854,9 @@ static int eval_batch_impl(rg_ctx *c, const double *d_params, int P, int model, 
             RG_TRY(prof_begin(c, 1, st));
             RG_TRY(rg_launch_nthcomp(c->d_recs, c->d_syslist, n_warm_sys, n_hot_sys, c->farr_cap, c->d_p10, nth_run,
                                      reinterpret_cast<double2 *>(c->d_sptot), c->d_header, c->sm_count, c->gd,
-                                     log10(c->h_ebins[0] + 0.5 * (c->h_ebins[1] - c->h_ebins[0])), c->d_farr, stats, st));
+                                     log10(c->h_ebins[0] + 0.5 * (c->h_ebins[1] - c->h_ebins[0])),
+                                     c->h_ebins[nE - 1] + 0.5 * (c->h_ebins[nE] - c->h_ebins[nE - 1]), c->d_sc,
+                                     ((size_t)2 * RG_NTH + 1) * c->nth_threads, c->d_farr, stats, st));
             RG_TRY(prof_end(c, 1, st));
             c->launches++;
             return RG_OK;

@@ -192,6 +192,10 @@ static int launch_hist(const HistArgs &A_in, int sm_count, cudaStream_t st)
     int per_sm = 1;
     RG_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * HIST_WARPS, smem));
     if (per_sm < 1) per_sm = 1;
+    if (const char *e = getenv("RG_HIST_RES")) { // tuning knob: fewer resident CTAs per SM (room for the Kompaneets solve)
+        const int k = atoi(e);
+        if (k >= 1 && k < per_sm) per_sm = k;
+    }
     long ctas = (long)A.P * A.NBH;
     if (ctas > (long)sm_count * per_sm) ctas = (long)sm_count * per_sm;
     if (ctas > A.slice_slots / 2) ctas = A.slice_slots / 2; // two slice halves per CTA

@@ -74,7 +74,8 @@ int rg_launch_setup(const double *d_params, int P, int model, double dr_dex, Set
 // n_threads = threads of the solve kernel's grid (systems are dealt round robin); coef = [sys_cap][RG_SPT_STRIDE] double2
 int rg_launch_nthcomp(const SetRec *recs, const int2 *syslist, int n_warm_sys, int n_hot_sys, int sys_cap,
                       const double *p10tab, int n_threads, double2 *coef, double *header, int sm_count,
-                      const GridDesc &grid, double lgE0, double *farr, unsigned long long *stats, cudaStream_t st);
+                      const GridDesc &grid, double lgE0, double grid_E1, double *gtab, size_t gtab_doubles, double *farr,
+                      unsigned long long *stats, cudaStream_t st);
 
 // latency variant of the Kompaneets kernels for small batches (rg_nthcomp_small.cu): one warp per system
 int rg_launch_nthcomp_small(const SetRec *recs, const int2 *syslist, int n_warm_sys, int n_hot_sys, int sys_cap,

@@ -538,14 +538,20 @@ nthcomp_kernel(const SetRec *__restrict__ recs, const int2 *__restrict__ syslist
 // at a time:
 //  A. one warp per system: v_j = G'_j - M_j v_{j+1} from the top row down to jstop, 32 rows per step -- every lane
 //     holds the affine map of its row, five shuffle steps compose them (Kogge-Stone), the value entering from above
-//     is applied last.  The rows go into the warp's shared-memory copy of sptot (the solution never exists in HBM);
-//     then the normalisation at 1 keV.
-//  B. one warp per eighth of the energy grid, for all 8 systems: a pass loads the grid values of its 32 bins once and
-//     uses them for 8 systems (with one warp per system the four grid arrays were re-read from L2 by every system:
-//     the shared-memory copies leave too little L1 to hold them, r2r).  The reference's monotone cursor is restated as
-//     a direct search seeded from log10(E) and fixed up with the reference's own comparisons, so every bin lands in
-//     exactly the cell the cursor would have reached.  The first lane of a warp's first pass computes the bin in front
-//     of the warp's range, for the trapezoid of pyNTHCOMP.py:75 only.
+//     is applied last.  The solution never exists in HBM, and not even as rows: a lane that holds v_j and v_{j+1} turns
+//     the cell between them into the line prim(E) = a + b (E / 511) of pyNTHCOMP.py:66-71 and stores (a, b) into the
+//     warp's table, indexed by the cursor value (0: below the x grid, prim = sptot[0]; nth + 1: above it, 0).  The
+//     lane that holds the cell around 1 keV computes the normalisation (pyNTHCOMP.py:49-56).
+//  B. one warp per eighth of the energy grid, for all 8 systems: a chunk of passes loads the grid values of its bins
+//     once and uses them for 8 systems (with one warp per system the four grid arrays were re-read from L2 by every
+//     system: the shared-memory tables leave too little L1 to hold them, r2r).  Per bin: cursor value from log10 E,
+//     one 16-byte table read, one fused multiply-add.  The reference's monotone cursor (pyNTHCOMP.py:61-62) stops at
+//     the first row with 511 x[j] >= E; ceil((log10 E - log10(511 xmin)) / 0.02) is that row unless E lies within
+//     rounding of a cell boundary, and only those bins (closer than 1e-9 of a cell; the rounding is 1e-13) run the
+//     reference's own comparisons -- every bin lands in exactly the cell the cursor would have reached.  The first
+//     lane of a chunk's first pass computes the bin in front of the chunk, for the trapezoid of pyNTHCOMP.py:75 only.
+// The table of a warp holds RG_INTERP_RCAP cursor values from the one of the grid's first bin: enough for a grid of
+// (RG_INTERP_RCAP - 6) / 50 = 8.8 decades; wider grids take the GLOBAL variant (whole tables in an L2-resident scratch).
 #define RG_INTERP_WARPS 8
 #ifndef RG_INTERP_GROUP
 #define RG_INTERP_GROUP 4 // steps of 32 rows whose loads are in flight together
@@ -554,20 +560,26 @@ nthcomp_kernel(const SetRec *__restrict__ recs, const int2 *__restrict__ syslist
 #ifndef RG_INTERP_PASSES
 #define RG_INTERP_PASSES 4 // passes of 32 bins per register-resident chunk of the grid (1000 bins / 8 warps + 1)
 #endif
+#define RG_INTERP_RCAP 448
+template <bool GLOBAL>
 __global__ void __launch_bounds__(RG_INTERP_WARPS * 32)
 nthcomp_interp_kernel(const SetRec *__restrict__ recs, const int2 *__restrict__ syslist, int nsys, int n_warm_sys,
                       int n_warm_pad, int hot_first, const double *__restrict__ p10tab, const double2 *__restrict__ coef,
-                      const double *__restrict__ header, GridDesc grid, double *__restrict__ farr)
+                      const double *__restrict__ header, GridDesc grid, double lgE0, double2 *__restrict__ gtab,
+                      double *__restrict__ farr)
 {
     RG_DYN_SMEM(smem_raw);
     double *s_p10 = reinterpret_cast<double *>(smem_raw);
     double *s_rdp = s_p10 + RG_INTERP_ROWS; // 1 / (10^(0.02 (j+1)) - 10^(0.02 j)): the cell width of the x grid, per unit xmin
-    double *s_vall = s_rdp + RG_INTERP_ROWS; // [warp][row]: sptot of the 8 systems
-    double *s_sc = s_vall + (size_t)RG_INTERP_WARPS * RG_INTERP_ROWS; // [warp][4]: xmin, 1 / xmin, log10(511 xmin), normfac
+    double *s_sc = s_rdp + RG_INTERP_ROWS;  // [warp][4]: xmin, log10(511 xmin), normfac h / keV, -
     int *s_nth = reinterpret_cast<int *>(s_sc + 4 * RG_INTERP_WARPS); // [warp]: rows, -1 = no system here
     int *s_row = s_nth + RG_INTERP_WARPS;                            // [warp]: arena row of the system
+    int *s_jb = s_row + RG_INTERP_WARPS;                             // [warp]: cursor value of table entry 0
+    double2 *s_tab = reinterpret_cast<double2 *>(s_jb + RG_INTERP_WARPS); // [warp][RG_INTERP_RCAP] (offset 14 816: 16-byte aligned)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double *s_v = s_vall + (size_t)warp * RG_INTERP_ROWS;
+    const int tcap = GLOBAL ? RG_INTERP_ROWS : RG_INTERP_RCAP;
+    double2 *tabs = GLOBAL ? gtab + (size_t)blockIdx.x * RG_INTERP_WARPS * RG_INTERP_ROWS : s_tab;
+    double2 *tab = tabs + (size_t)warp * tcap;
     for (int i = threadIdx.x; i < RG_NTH + 4; i += blockDim.x) s_p10[i] = p10tab[i];
     for (int i = threadIdx.x; i < RG_NTH + 3; i += blockDim.x) s_rdp[i] = p10tab[RG_P10_RDP + i];
     __syncthreads();
@@ -575,7 +587,7 @@ nthcomp_interp_kernel(const SetRec *__restrict__ recs, const int2 *__restrict__ 
     const int nE = grid.nE;
     // photon flux -> W/Hz (relagn.py:929-930) folded into the normalisation
     const double outfac = (1.0 / RGK_KEV) * RGK_H;
-    // phase B: this warp's bins [b_lo, b_hi) and the passes that cover b_lo - 1 ... b_hi - 1
+    // phase B: this warp's bins [b_lo, b_hi)
     const int bpw = (nE + RG_INTERP_WARPS - 1) / RG_INTERP_WARPS;
     const int b_lo = warp * bpw, b_hi = b_lo + bpw < nE ? b_lo + bpw : nE;
     // The header of the next system is requested while the current one is processed: the chain system list -> set
@@ -596,16 +608,35 @@ nthcomp_interp_kernel(const SetRec *__restrict__ recs, const int2 *__restrict__ 
     for (int base = blockIdx.x * RG_INTERP_WARPS; base < nsys; base += stride) {
         const Hd cur = nxt;
         nxt = fetch(base + warp + stride);
-        // ---- A. back substitution and normalisation of system base + warp ----
+        // ---- A. back substitution of system base + warp into its table of interpolation lines ----
         int nth = cur.packed < 0 ? -1 : (cur.packed & 1023);
         if (nth >= 0 && nth < 4) nth = 0; // degenerate grid (flagged by the solve): the spectrum is empty
         if (nth > 0) {
             const int jstop = cur.packed >> 10;
-            const double xmin = cur.xmin, lgx = cur.lgx;
+            const double xmin = cur.xmin, lgx = cur.lgx, rxmin = 1.0 / xmin;
             const double2 *cf = coef + (size_t)cur.sys * RG_SPT_STRIDE;
             const int jtop = nth - 2; // rows jtop down to jstop
-            for (int j = lane; j < jstop && j <= nth; j += 32) s_v[j] = 0.0; // rows below jstop: never referenced
-            if (lane < 2) s_v[nth - 1 + lane] = 0.0;                        // sptot[jmax-1], sptot[jmax] (pyNTHCOMP.py:170)
+            // cursor value of table entry 0: one below the start value of the grid's first bin
+            int jb = 0;
+            if (!GLOBAL) {
+                const double f = floor((lgE0 - lgx) * 50.0) - 1.0;
+                jb = f < 0.0 ? 0 : (f > (double)(nth + 1) ? nth + 1 : (int)f);
+            }
+            // the cell around 1 keV (pyNTHCOMP.py:49-56): rows il = ih - 1 and ih
+            const double xx = 1.0 / 511.0;
+            int ih = (int)ceil((0.0 - lgx) * 50.0);
+            if (ih < 1) ih = 1;
+            if (ih > nth) ih = nth;
+            while (ih > 1 && !(xx > xmin * s_p10[ih - 1])) ih--;
+            while (ih < nth && xx > xmin * s_p10[ih]) ih++;
+            const int il = ih - 1;
+            double spp_l = 0.0;
+            bool have_spp = false;
+            // cursor values nth, nth + 1: the cell between the two zero rows, and everything above the x grid
+            if (lane < 2) {
+                const int k = nth + lane - jb;
+                if (k >= 0 && k < tcap) tab[k] = make_double2(0.0, 0.0);
+            }
             double carry = 0.0; // v of the row above the current step (u[jmax-1] = 0)
             // the rows of RG_INTERP_GROUP steps are requested together (their addresses do not depend on the recurrence)
             for (int jg = jtop; jg >= jstop; jg -= 32 * RG_INTERP_GROUP) {
@@ -626,26 +657,42 @@ nthcomp_interp_kernel(const SetRec *__restrict__ recs, const int2 *__restrict__ 
                         if (lane >= d) { B = fma(A, Bp, B); A = A * Ap; }
                     }
                     const double v = fma(A, carry, B);
-                    if (j >= jstop) s_v[j] = v;
+                    double vup = __shfl_up_sync(FULL, v, 1); // v_{j+1}
+                    if (lane == 0) vup = carry;
                     carry = __shfl_sync(FULL, v, 31);
+                    if (j >= jstop) {
+                        // cell [x_j, x_{j+1}], cursor value j + 1: prim = sl + (E/511 - xl) (sh - sl) / (xh - xl)
+                        //   = a + b E/511, the division by the cell width as a multiplication by
+                        //   (1 / xmin) (1 / (10^(0.02 (j+1)) - 10^(0.02 j)))
+                        const double xl = xmin * s_p10[j];
+                        const double bb = (vup - v) * (rxmin * s_rdp[j]);
+                        const int k = j + 1 - jb;
+                        if (k >= 0 && k < tcap) tab[k] = make_double2(fma(-xl, bb, v), bb);
+                        if (j == il) { // (il >= 1 here; il = 0 is the lane of row 1, below)
+                            const double xh = xmin * s_p10[ih];
+                            spp_l = v + (vup - v) * (xx - xl) / (xh - xl);
+                            have_spp = true;
+                        }
+                        if (j == 1) { // sptot[0] = c0 v_1 (pyNTHCOMP.py:248): cursor value 1 (cell [x_0, x_1]) and 0 (below the grid)
+                            const double v0 = cur.c0 * v;
+                            const double x0 = xmin * s_p10[0];
+                            const double b0 = (v - v0) * (rxmin * s_rdp[0]);
+                            if (jb <= 1 && 1 - jb < tcap) tab[1 - jb] = make_double2(fma(-x0, b0, v0), b0);
+                            if (jb == 0) tab[0] = make_double2(v0, 0.0);
+                            if (il == 0) {
+                                const double xh = xmin * s_p10[1];
+                                spp_l = v0 + (v - v0) * (xx - x0) / (xh - x0);
+                                have_spp = true;
+                            }
+                        }
+                    }
                 }
             }
-            __syncwarp();
-            if (jstop <= 1 && lane == 0) s_v[0] = cur.c0 * s_v[1];
-            __syncwarp();
-            // normalisation at 1 keV (pyNTHCOMP.py:49-56)
-            const double xx = 1.0 / 511.0;
-            int ih = (int)ceil((0.0 - lgx) * 50.0);
-            if (ih < 1) ih = 1;
-            if (ih > nth) ih = nth;
-            while (ih > 1 && !(xx > xmin * s_p10[ih - 1])) ih--;
-            while (ih < nth && xx > xmin * s_p10[ih]) ih++;
-            const int il = ih - 1;
-            const double xl = xmin * s_p10[il], xh = xmin * s_p10[ih];
-            const double spp = s_v[il] + (s_v[ih] - s_v[il]) * (xx - xl) / (xh - xl);
+            const unsigned m = __ballot_sync(FULL, have_spp);
+            const double spp = m ? __shfl_sync(FULL, spp_l, __ffs(m) - 1) : 0.0; // rows above the top are zero
             if (lane == 0) {
-                s_sc[4 * warp] = xmin; s_sc[4 * warp + 1] = 1.0 / xmin; s_sc[4 * warp + 2] = lgx;
-                s_sc[4 * warp + 3] = 1.0 / spp;
+                s_sc[4 * warp] = xmin; s_sc[4 * warp + 1] = lgx; s_sc[4 * warp + 2] = (1.0 / spp) * outfac;
+                s_jb[warp] = jb;
             }
         }
         if (lane == 0) { s_nth[warp] = nth; s_row[warp] = cur.sys; }
@@ -654,7 +701,7 @@ nthcomp_interp_kernel(const SetRec *__restrict__ recs, const int2 *__restrict__ 
         // in chunks of RG_INTERP_PASSES passes whose grid values stay in registers for the 8 systems; every chunk
         // starts one bin early (lane 0 of its first pass supplies the left end of the first trapezoid only)
         for (int c_lo = b_lo; c_lo < b_hi; c_lo += 32 * RG_INTERP_PASSES - 1) {
-            double ge[RG_INTERP_PASSES], glg[RG_INTERP_PASSES], ge5[RG_INTERP_PASSES], gr2[RG_INTERP_PASSES], gde[RG_INTERP_PASSES];
+            double ge[RG_INTERP_PASSES], glg[RG_INTERP_PASSES], ge5[RG_INTERP_PASSES], gr2[RG_INTERP_PASSES], ghd[RG_INTERP_PASSES];
 #pragma unroll
             for (int p = 0; p < RG_INTERP_PASSES; p++) {
                 const int i = c_lo - 1 + 32 * p + lane;
@@ -663,14 +710,15 @@ nthcomp_interp_kernel(const SetRec *__restrict__ recs, const int2 *__restrict__ 
                 glg[p] = in ? __ldg(grid.lgE + i) : 0.0;
                 ge5[p] = in ? __ldg(grid.e511 + i) : 0.0;
                 gr2[p] = in ? __ldg(grid.rear2 + i) : 0.0;
-                gde[p] = in && i > 0 ? ge[p] - __ldg(grid.Egrid + i - 1) : 0.0;
+                ghd[p] = in && i > 0 ? 0.5 * (ge[p] - __ldg(grid.Egrid + i - 1)) : 0.0; // half the trapezoid's width; bin 0 is 0
             }
             for (int q = 0; q < RG_INTERP_WARPS; q++) {
                 const int nq = s_nth[q];
                 if (nq < 0) continue; // warp-uniform
                 double *F = farr + (size_t)s_row[q] * nE;
-                const double xmin = s_sc[4 * q], rxmin = s_sc[4 * q + 1], lgx = s_sc[4 * q + 2], normfac = s_sc[4 * q + 3];
-                const double *v = s_vall + (size_t)q * RG_INTERP_ROWS;
+                const double xmin = s_sc[4 * q], lgx = s_sc[4 * q + 1], nf = s_sc[4 * q + 2];
+                const int jb = s_jb[q];
+                const double2 *tq = tabs + (size_t)q * tcap;
                 double carry_pr = 0.0;
 #pragma unroll
                 for (int p = 0; p < RG_INTERP_PASSES; p++) {
@@ -683,32 +731,23 @@ nthcomp_interp_kernel(const SetRec *__restrict__ recs, const int2 *__restrict__ 
                         if (store) RG_STCG(&F[i], 0.0);
                         continue;
                     }
-                    const double e = ge[p];
-                    // The cursor of pyNTHCOMP.py:61-62 stops at the first row j with 511 x[j] >= E.  The start value is
-                    // that row unless E lies within rounding (1e-13 of a cell) of a cell boundary, where it can be one
-                    // off: one comparison on either side, the reference's own, settles it.
-                    int j = (int)ceil((glg[p] - lgx) * 50.0);
+                    const double t = (glg[p] - lgx) * 50.0, tc = ceil(t), fr = tc - t;
+                    int j = (int)tc;
                     j = j < 0 ? 0 : (j > nq + 1 ? nq + 1 : j);
-                    const int ja = j > 0 ? j - 1 : 0, jb = j <= nq ? j : nq;
-                    const bool below = j > 0 && !(511.0 * (xmin * s_p10[ja]) < e);   // the cursor would have stopped earlier
-                    const bool above = j <= nq && 511.0 * (xmin * s_p10[jb]) < e;    // ... or gone one further
-                    j += above ? 1 : (below ? -1 : 0);
-                    double prim = 0.0;
-                    if (j <= nq) {
-                        // linear interpolation inside the cell [xl, xh] (pyNTHCOMP.py:66-71); the division by the cell
-                        // width is a multiplication by (1 / xmin) (1 / (10^(0.02 (jl+1)) - 10^(0.02 jl)))
-                        const int jl = j > 0 ? j - 1 : 0;
-                        const double xl = xmin * s_p10[jl];
-                        const double sl = v[jl], sh = v[jl + 1];
-                        prim = j > 0 ? sl + ((ge5[p] - xl) * (sh - sl)) * (rxmin * s_rdp[jl]) : sl;
+                    if (fr < 1e-9 || fr > 1.0 - 1e-9) { // on a cell boundary to rounding: the reference's comparisons decide
+                        const double e = ge[p];
+                        const int ja = j > 0 ? j - 1 : 0, jc = j <= nq ? j : nq;
+                        const bool below = j > 0 && !(511.0 * (xmin * s_p10[ja]) < e);
+                        const bool above = j <= nq && 511.0 * (xmin * s_p10[jc]) < e;
+                        j += above ? 1 : (below ? -1 : 0);
                     }
-                    const double pr = in ? prim * gr2[p] : 0.0; // prim / E^2 (pyNTHCOMP.py:75)
+                    int k = in ? j - jb : 0;
+                    k = k < 0 ? 0 : (k > tcap - 1 ? tcap - 1 : k); // (never outside for a bin of the grid)
+                    const double2 ab = tq[k];
+                    const double pr = in ? fma(ab.y, ge5[p], ab.x) * gr2[p] : 0.0; // prim / E^2 (pyNTHCOMP.py:75)
                     double pr_prev = __shfl_up_sync(FULL, pr, 1);
                     if (lane == 0) pr_prev = carry_pr;
-                    if (store) {
-                        const double ph = i > 0 ? (0.5 * (pr + pr_prev) * gde[p] * normfac) : 0.0;
-                        RG_STCG(&F[i], ph * outfac);
-                    }
+                    if (store) RG_STCG(&F[i], (pr + pr_prev) * (ghd[p] * nf));
                     carry_pr = __shfl_sync(FULL, pr, 31);
                 }
             }
@@ -786,8 +825,10 @@ int rg_launch_counters_out(const int *d_counter, int *h_mapped, cudaStream_t st)
 
 int rg_launch_nthcomp(const SetRec *recs, const int2 *syslist, int n_warm_sys, int n_hot_sys, int sys_cap,
                       const double *p10tab, int n_threads, double2 *coef, double *header, int sm_count,
-                      const GridDesc &grid, double lgE0, double *farr, unsigned long long *stats, cudaStream_t st)
+                      const GridDesc &grid, double lgE0, double grid_E1, double *gtab, size_t gtab_doubles, double *farr,
+                      unsigned long long *stats, cudaStream_t st)
 {
+    const bool gtab_force = getenv("RG_INTERP_GLOBAL") != nullptr; // test knob: the wide-grid variant on any grid
     // logical order: the warm systems, padded to a whole warp, then the hot shapes -- no warp mixes the two kinds
     const int n_warm_pad = (n_warm_sys + 31) & ~31;
     const int nsys = n_hot_sys > 0 ? n_warm_pad + n_hot_sys : n_warm_sys;
@@ -798,19 +839,31 @@ int rg_launch_nthcomp(const SetRec *recs, const int2 *syslist, int n_warm_sys, i
     RG_LAUNCH(nthcomp_kernel, dim3(blocks), dim3(128), 0, st, recs, syslist, nsys, n_warm_sys, n_warm_pad, hot_first, p10tab,
               blocks * 128, lgE0, coef, header, stats);
     RG_CUDA_OK(cudaGetLastError());
-    // persistent warps, one system at a time: tables + RG_INTERP_WARPS private sptot copies in shared memory
-    const size_t smem = (size_t)(2 + RG_INTERP_WARPS) * RG_INTERP_ROWS * sizeof(double) + (size_t)RG_INTERP_WARPS * (4 * sizeof(double) + 2 * sizeof(int));
+    // persistent CTAs, 8 systems at a time: resident tables + RG_INTERP_WARPS tables of interpolation lines
+    const double lgE1 = log10(grid_E1);
+    const bool global = (lgE1 - lgE0) * 50.0 + 6.0 > (double)RG_INTERP_RCAP || gtab_force;
+    const size_t smem = (size_t)2 * RG_INTERP_ROWS * sizeof(double) + (size_t)RG_INTERP_WARPS * (4 * sizeof(double) + 3 * sizeof(int)) +
+                        (global ? 0 : (size_t)RG_INTERP_WARPS * RG_INTERP_RCAP * sizeof(double2));
 #ifndef RG_HOSTSIM
     static bool attr_set = false;
     if (!attr_set) {
-        RG_CUDA_OK(cudaFuncSetAttribute(nthcomp_interp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RG_CUDA_OK(cudaFuncSetAttribute(nthcomp_interp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(smem + (global ? (size_t)RG_INTERP_WARPS * RG_INTERP_RCAP * sizeof(double2) : 0))));
         attr_set = true;
     }
 #endif
     long ictas = ((long)nsys + RG_INTERP_WARPS - 1) / RG_INTERP_WARPS;
     if (ictas > 3L * sm_count) ictas = 3L * sm_count;
-    RG_LAUNCH(nthcomp_interp_kernel, dim3((unsigned)ictas), dim3(RG_INTERP_WARPS * 32), smem, st, recs, syslist,
-              nsys, n_warm_sys, n_warm_pad, hot_first, p10tab, coef, header, grid, farr);
+    if (global) {
+        const long fit = (long)(gtab_doubles / ((size_t)2 * RG_INTERP_WARPS * RG_INTERP_ROWS));
+        if (fit < 1) return rg_set_error(RG_E_NOMEM, "nthcomp_interp: no scratch for the interpolation tables");
+        if (ictas > fit) ictas = fit;
+        RG_LAUNCH(nthcomp_interp_kernel<true>, dim3((unsigned)ictas), dim3(RG_INTERP_WARPS * 32), smem, st, recs, syslist,
+                  nsys, n_warm_sys, n_warm_pad, hot_first, p10tab, coef, header, grid, lgE0, reinterpret_cast<double2 *>(gtab), farr);
+    } else {
+        RG_LAUNCH(nthcomp_interp_kernel<false>, dim3((unsigned)ictas), dim3(RG_INTERP_WARPS * 32), smem, st, recs, syslist,
+                  nsys, n_warm_sys, n_warm_pad, hot_first, p10tab, coef, header, grid, lgE0, (double2 *)nullptr, farr);
+    }
     RG_CUDA_OK(cudaGetLastError());
     return RG_OK;
 }
