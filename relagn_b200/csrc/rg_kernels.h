@@ -132,7 +132,7 @@ double rg_r_valid(double a);
 #define RG_P10_RW1 (2 * (RG_NTH + 4)) // 1 / that
 #define RG_P10_LEN (5 * (RG_NTH + 4))
 #ifndef RG_NTH_MINB
-#define RG_NTH_MINB 5 // resident 128-thread CTAs per SM of the persistent nthcomp grid
+#define RG_NTH_MINB 4 // resident 128-thread CTAs per SM of the persistent nthcomp grid
 #endif
 int rg_fp64_peak(double *tflops, cudaStream_t st);
 int rg_launch_counters_out(const int *d_counter, int *h_mapped, cudaStream_t st);

@@ -712,42 +712,50 @@ nthcomp_interp_kernel(const SetRec *__restrict__ recs, const int2 *__restrict__ 
                 gr2[p] = in ? __ldg(grid.rear2 + i) : 0.0;
                 ghd[p] = in && i > 0 ? 0.5 * (ge[p] - __ldg(grid.Egrid + i - 1)) : 0.0; // half the trapezoid's width; bin 0 is 0
             }
+            unsigned inmask = 0; // bit p: this lane's bin of pass p belongs to the warp's range
+#pragma unroll
+            for (int p = 0; p < RG_INTERP_PASSES; p++) {
+                const int i = c_lo - 1 + 32 * p + lane;
+                if (i >= 0 && i < b_hi) inmask |= 1u << p;
+            }
+            const int npass = (b_hi - (c_lo - 1) + 31) >> 5; // passes of this chunk that reach into the range
             for (int q = 0; q < RG_INTERP_WARPS; q++) {
                 const int nq = s_nth[q];
                 if (nq < 0) continue; // warp-uniform
-                double *F = farr + (size_t)s_row[q] * nE;
+                double *Fl = farr + (size_t)s_row[q] * nE + (c_lo - 1 + lane); // this lane's bin of pass 0
+                if (nq == 0) { // degenerate Kompaneets grid: empty spectrum
+#pragma unroll
+                    for (int p = 0; p < RG_INTERP_PASSES; p++)
+                        if (((inmask >> p) & 1u) && !(p == 0 && lane == 0)) RG_STCG(&Fl[32 * p], 0.0);
+                    continue;
+                }
                 const double xmin = s_sc[4 * q], lgx = s_sc[4 * q + 1], nf = s_sc[4 * q + 2];
                 const int jb = s_jb[q];
+                const int khi = nq + 1 - jb < tcap - 1 ? nq + 1 - jb : tcap - 1; // entry of "above the x grid"
                 const double2 *tq = tabs + (size_t)q * tcap;
                 double carry_pr = 0.0;
 #pragma unroll
                 for (int p = 0; p < RG_INTERP_PASSES; p++) {
-                    const int i0 = c_lo - 1 + 32 * p;
-                    if (i0 >= b_hi) break; // warp-uniform
-                    const int i = i0 + lane;
-                    const bool in = i >= 0 && i < b_hi;
-                    const bool store = in && !(p == 0 && lane == 0);
-                    if (nq == 0) { // degenerate Kompaneets grid: empty spectrum
-                        if (store) RG_STCG(&F[i], 0.0);
-                        continue;
-                    }
+                    if (p >= npass) break; // warp-uniform
+                    const bool in = (inmask >> p) & 1u;
                     const double t = (glg[p] - lgx) * 50.0, tc = ceil(t), fr = tc - t;
-                    int j = (int)tc;
-                    j = j < 0 ? 0 : (j > nq + 1 ? nq + 1 : j);
+                    // entry = cursor value clamped to [0, nth + 1], minus the table's first (jb >= 0)
+                    int k = (int)tc - jb;
                     if (fr < 1e-9 || fr > 1.0 - 1e-9) { // on a cell boundary to rounding: the reference's comparisons decide
                         const double e = ge[p];
+                        int j = (int)tc;
+                        j = j < 0 ? 0 : (j > nq + 1 ? nq + 1 : j);
                         const int ja = j > 0 ? j - 1 : 0, jc = j <= nq ? j : nq;
                         const bool below = j > 0 && !(511.0 * (xmin * s_p10[ja]) < e);
                         const bool above = j <= nq && 511.0 * (xmin * s_p10[jc]) < e;
-                        j += above ? 1 : (below ? -1 : 0);
+                        k = j + (above ? 1 : (below ? -1 : 0)) - jb;
                     }
-                    int k = in ? j - jb : 0;
-                    k = k < 0 ? 0 : (k > tcap - 1 ? tcap - 1 : k); // (never outside for a bin of the grid)
-                    const double2 ab = tq[k];
+                    k = k < 0 ? 0 : (k > khi ? khi : k);
+                    const double2 ab = tq[in ? k : 0];
                     const double pr = in ? fma(ab.y, ge5[p], ab.x) * gr2[p] : 0.0; // prim / E^2 (pyNTHCOMP.py:75)
                     double pr_prev = __shfl_up_sync(FULL, pr, 1);
                     if (lane == 0) pr_prev = carry_pr;
-                    if (store) RG_STCG(&F[i], (pr + pr_prev) * (ghd[p] * nf));
+                    if (in && !(p == 0 && lane == 0)) RG_STCG(&Fl[32 * p], (pr + pr_prev) * (ghd[p] * nf));
                     carry_pr = __shfl_sync(FULL, pr, 31);
                 }
             }
