@@ -722,7 +722,7 @@ static int ensure_batch_scratch(rg_ctx *c, int model, int P)
 #define RG_SMALL_SETS 64
 static int eval_batch_impl(rg_ctx *c, const double *d_params, int P, int model, double dr_dex, unsigned flags,
                            double *d_out, double *d_attrs, void *stream, int piece_sets, rg_piece_fn on_piece, void *user,
-                           bool nosync = false)
+                           bool nosync = false, bool shrink = false)
 {
     if (!c || !d_params || !d_out || P < 0) return rg_set_error(RG_E_ARG, "rg_eval_batch: bad arguments");
     if (model != RG_MODEL_RELAGN && model != RG_MODEL_RELQSO) return rg_set_error(RG_E_ARG, "unknown model %d", model);
@@ -905,11 +905,19 @@ static int eval_batch_impl(rg_ctx *c, const double *d_params, int P, int model, 
         A.out = d_out + (size_t)p0 * ncomp * nE;
         A.stats = stats;
         RG_TRY(prof_begin(c, 2, st));
-        if (on_piece && piece_sets > 0 && A.NB == 1 && n > piece_sets + piece_sets / 2) {
+        if (on_piece && piece_sets > 0 && A.NB == 1 && (shrink ? n > piece_sets / 4 : n > piece_sets + piece_sets / 2)) {
             // the chunk's spectrum kernel in sub-launches of piece_sets sets (setup, Kompaneets solves and histograms
             // stay chunk-wide): the caller starts moving a piece out while the next one is computed
             for (int q0 = 0; q0 < n;) {
                 int nq = std::min(piece_sets, n - q0);
+                if (shrink) {
+                    // host pipeline: every piece is half of what is left of the BATCH (between piece_sets / 8 and
+                    // piece_sets): few launches (each has a tail) while the batch is long, and a small last piece --
+                    // its copy to the host is the only one nothing hides
+                    const long left = (long)(n - q0) + (long)(P - p0 - n);
+                    nq = (int)std::min<long>(std::min<long>(piece_sets, std::max<long>(piece_sets / 8, left / 2)), n - q0);
+                    if (n - q0 - nq < piece_sets / 16) nq = n - q0;
+                } else
                 if (n - q0 - nq < piece_sets / 2) nq = n - q0; // a short remainder joins the last piece
                 A.recs = c->d_recs + q0;
                 A.P = nq;
@@ -1027,8 +1035,9 @@ extern "C" int rg_eval_batch_host(rg_ctx *c, const double *params, int P, int mo
         }
         // a set outgrew the caps (dr_dex x 8 + 3 annuli, 40 Kompaneets systems per set): the counting path below
     }
-    int PIECE = 16384;
-    if (const char *e = getenv("RG_PIECE_SETS")) { int v = atoi(e); if (v >= 1 && v <= 65536) PIECE = v; } // tuning / test knob
+    int PIECE = 32768; // largest piece; the pieces shrink towards the end of the batch (eval_batch_impl)
+    bool shrink = true;
+    if (const char *e = getenv("RG_PIECE_SETS")) { int v = atoi(e); if (v >= 1 && v <= 65536) { PIECE = v; shrink = false; } } // tuning / test knob: fixed pieces
     const int SUPER = 262144;
     const int stage_rows = std::min(P, SUPER);
     RG_TRY(ensure_dev(&c->d_stage_par, &c->d_stage_par_n, (size_t)P * RG_NPAR));
@@ -1070,7 +1079,7 @@ extern "C" int rg_eval_batch_host(rg_ctx *c, const double *params, int P, int mo
         pipe.base = r0;
         if (r0 > 0) cudaStreamSynchronize(pipe.copy_st); // the staging buffer is about to be overwritten
         rc = eval_batch_impl(c, c->d_stage_par + (size_t)r0 * RG_NPAR, nr, model, dr_dex, flags, c->d_stage_out,
-                             c->d_stage_attr + (size_t)r0 * RG_NATTR, c->stream, PIECE, on_piece, &pipe);
+                             c->d_stage_attr + (size_t)r0 * RG_NATTR, c->stream, PIECE, on_piece, &pipe, false, shrink);
     }
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(pipe.copy_st);
