@@ -22,12 +22,13 @@ out = {"command": "python bench.py --sets %d --steps 1 --warmup 3 --no-cpu under
                   "--import-source on -k regex:<kernel> -s 3 -c 1` (tools/gpu_profile.sh %s), after the same command "
                   "exited 0 without ncu" % (sets, tag), "sets_per_launch": sets}
 for name, rep in (("spectrum_kernel", "prof_spectrum_%s.ncu-rep" % tag), ("nthcomp_kernel", "prof_nthcomp_%s.ncu-rep" % tag),
-                  ("hist_kernel", "prof_hist_%s.ncu-rep" % tag)):
+                  ("hist_kernel", "prof_hist_%s.ncu-rep" % tag), ("nthcomp_interp_kernel", "prof_interp_%s.ncu-rep" % tag)):
     if not os.path.exists(os.path.join(ROOT, "gpurun_out", rep)):
         continue
     path = os.path.join(ROOT, "gpurun_out", rep)
     raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    open(os.path.join(ROOT, "profiles", "%s_%s_raw.csv" % (tag, name.split("_")[0])), "w").write(raw)
+    short = "interp" if "interp" in name else name.split("_")[0]
+    open(os.path.join(ROOT, "profiles", "%s_%s_raw.csv" % (tag, short)), "w").write(raw)
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, vals = rows[0], rows[1], rows[2]
     d = {}
