@@ -73,6 +73,7 @@ struct rg_ctx {
     int farr_cap = 0; // systems the farr arena holds at the current grid (<= sys_cap)
     double *d_sc = nullptr;
     int nth_threads = 0;
+    size_t sc_doubles = 0;
     double *d_rq = nullptr;
     int rq_cap = 0;
     int *d_queue = nullptr;
@@ -676,14 +677,15 @@ static int ensure_batch_scratch(rg_ctx *c, int model, int P)
 {
     if (!c->d_queue) RG_CUDA_OK(cudaMalloc(&c->d_queue, 4 * sizeof(int)));
     const int want = pick_chunk_sets(P);
-    {   // persistent nthcomp grid and its scratch planes: sized by the machine, or by the chunk when that is smaller
+    {   // threads of the solve kernel's grid: sized by the machine, or by the chunk when that is smaller; and the global
+        // scratch of the small-batch Kompaneets kernel / the wide-grid interpolation tables (64 MB at most)
         const int full = c->sm_count * RG_NTH_MINB * 128;
         const int need = (int)std::min<long>(full, (((long)std::max(want, c->chunk_sets) * 40 + 127) / 128) * 128);
         if (need > c->nth_threads) {
             free_dev(c->d_sc);
             c->d_sc = nullptr;
-            // two [RG_NTH][threads] planes (gamma, g of the Thomas sweep) + one row (bet[0])
-            RG_CUDA_OK(cudaMalloc(&c->d_sc, ((size_t)2 * RG_NTH + 1) * need * sizeof(double)));
+            c->sc_doubles = std::min<size_t>(((size_t)2 * RG_NTH + 1) * need, (size_t)8 << 20);
+            RG_CUDA_OK(cudaMalloc(&c->d_sc, c->sc_doubles * sizeof(double)));
             c->nth_threads = need;
         }
     }
@@ -845,7 +847,7 @@ static int eval_batch_impl(rg_ctx *c, const double *d_params, int P, int model, 
             if (nosync) { // small batches: the latency variant, one warp per system
                 RG_TRY(rg_launch_nthcomp_small(c->d_recs, c->d_syslist, n_warm_sys, n_hot_sys, c->farr_cap, c->d_p10,
                                                reinterpret_cast<const double2 *>(c->d_edges), c->d_sc,
-                                               ((size_t)2 * RG_NTH + 1) * c->nth_threads, c->sm_count, c->gd, c->d_farr,
+                                               c->sc_doubles, c->sm_count, c->gd, c->d_farr,
                                                c->d_queue + 3, stats, st));
                 c->launches++;
                 return RG_OK;
@@ -856,7 +858,7 @@ static int eval_batch_impl(rg_ctx *c, const double *d_params, int P, int model, 
                                      reinterpret_cast<double2 *>(c->d_sptot), c->d_header, c->sm_count, c->gd,
                                      log10(c->h_ebins[0] + 0.5 * (c->h_ebins[1] - c->h_ebins[0])),
                                      c->h_ebins[nE - 1] + 0.5 * (c->h_ebins[nE] - c->h_ebins[nE - 1]), c->d_sc,
-                                     ((size_t)2 * RG_NTH + 1) * c->nth_threads, c->d_farr, stats, st));
+                                     c->sc_doubles, c->d_farr, stats, st));
             RG_TRY(prof_end(c, 1, st));
             c->launches++;
             return RG_OK;
