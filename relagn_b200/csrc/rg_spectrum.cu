@@ -32,7 +32,8 @@
 #define FULL 0xffffffffu
 #define IMAX 0x7fffffff
 #ifndef RG_LOCKSTEP
-#define RG_LOCKSTEP 4 // block barrier every RG_LOCKSTEP rounds (power of two)
+#define RG_LOCKSTEP 0 // > 0: block barrier every RG_LOCKSTEP rounds (power of two).  Round 1 gained 3 % from keeping the
+                      // warps in one code region; with the round-2 kernel the barrier costs 2.4 % (r2z_ab2), so: off
 #endif
 #define NGRID 4 // per-bin constant arrays staged in shared memory: hnu, bbpre, wt in bin order + wt transposed
 #ifndef RG_SPEC_W64
@@ -73,6 +74,9 @@ int rg_spectrum_pick_warps(int NC, int nH, int HL, int HH, int fp32)
 #endif
 #ifndef RG_WARM_PREFETCH
 #define RG_WARM_PREFETCH 1
+#endif
+#ifndef RG_PLANCK_CHAINS
+#define RG_PLANCK_CHAINS 4 // 32-bin steps of the Planck stage in flight per lane (independent exp / reciprocal chains)
 #endif
 #ifndef RG_WIEN_CUT
 #define RG_WIEN_CUT 1 // skip the Wien-tail bins of an annulus whose share of the total is below FP64 resolution
@@ -465,7 +469,9 @@ __global__ void __launch_bounds__(NC <= 4 ? (sizeof(R) == 4 ? 512 : 32 * RG_SPEC
             }
             const int mt = n_rounds - m0 < 32 ? n_rounds - m0 : 32;
             for (int mi = 0; mi < mt; mi++) {
+#if RG_LOCKSTEP > 0
                 if (((m0 + mi) & (RG_LOCKSTEP - 1)) == 0) __syncthreads(); // lockstep only: no data crosses warps here
+#endif
                 const int region = __shfl_sync(FULL, p_region, mi);
                 if (region < 0) continue; // no annulus left for this warp in this round
                 if (region == 2 && !rel) continue; // non-relativistic hot component needs no annuli (relagn.py:1387-1401)
@@ -550,15 +556,15 @@ __global__ void __launch_bounds__(NC <= 4 ? (sizeof(R) == 4 ? 512 : 32 * RG_SPEC
                     R *const inLane = inT + A.HL + (lane & 7) * RS + (lane >> 3); // bin `lane`; bin 32 g + lane: + 4 g
                     const int n_steps = (jz + 31) >> 5;
                     int gq = 0;
-                    for (; gq + 4 <= n_steps; gq += 4) {
-                        R Lq[4];
+                    for (; gq + RG_PLANCK_CHAINS <= n_steps; gq += RG_PLANCK_CHAINS) {
+                        R Lq[RG_PLANCK_CHAINS];
 #pragma unroll
-                        for (int q = 0; q < 4; q++) {
+                        for (int q = 0; q < RG_PLANCK_CHAINS; q++) {
                             const int j = 32 * (gq + q) + lane;
                             Lq[q] = j < jz ? planck_bin(G.hnu_n(j), G.bbpre_n(j), inv_kT) : (R)0;
                         }
 #pragma unroll
-                        for (int q = 0; q < 4; q++) {
+                        for (int q = 0; q < RG_PLANCK_CHAINS; q++) {
                             part += Lq[q] * G.wt_n(32 * (gq + q) + lane);
                             inLane[4 * (gq + q)] = Lq[q];
                         }
