@@ -75,6 +75,9 @@ int rg_spectrum_pick_warps(int NC, int nH, int HL, int HH, int fp32)
 #ifndef RG_WARM_PREFETCH
 #define RG_WARM_PREFETCH 1
 #endif
+#ifndef RG_WARM_BATCH
+#define RG_WARM_BATCH 2 // warm annuli: farr loads of 2 chunks (2), of the whole row (1) before the first use; 3: cp.async into the buffer; 0: per chunk
+#endif
 #ifndef RG_PLANCK_CHAINS
 #define RG_PLANCK_CHAINS 4 // 32-bin steps of the Planck stage in flight per lane (independent exp / reciprocal chains)
 #endif
@@ -581,6 +584,58 @@ __global__ void __launch_bounds__(NC <= 4 ? (sizeof(R) == 4 ? 512 : 32 * RG_SPEC
                 } else {
                     // warm annulus: its Comptonised spectrum is already on the grid (nthcomp kernels)
                     const double *w_F = A.farr + (size_t)(r.sys_base + loc) * nE;
+#if RG_WARM_BATCH == 3
+                    if (sizeof(R) == 8) {
+                        // the row goes global -> shared by asynchronous 8-byte copies, every element straight to its
+                        // place in the transposed buffer (bin 8 col + c: row c, column col): no register staging, all
+                        // 8 NC copies of a lane in flight at once -- one trip to L2 per annulus -- then the
+                        // trapezoid sum reads the buffer back in the order of the register variant
+                        for (int ch = 0; ch < NC; ch++) {
+                            const int j0 = 8 * (32 * ch + lane);
+#pragma unroll
+                            for (int c = 0; c < 8; c++) {
+                                const bool ok = j0 + c < nE;
+                                RG_CP_ASYNC8(reinterpret_cast<double *>(&inBase[c * RS + 32 * ch]), ok ? w_F + j0 + c : w_F, ok);
+                            }
+                        }
+                        RG_CP_ASYNC_WAIT();
+                        __syncwarp();
+                        for (int ch = 0; ch < NC; ch++) {
+                            const int col = 32 * ch + lane;
+                            if (8 * col < nE) {
+#pragma unroll
+                                for (int c = 0; c < 8; c++) part += inBase[c * RS + 32 * ch] * G.wt(c, col);
+                            }
+                        }
+                    } else
+#endif
+#if RG_WARM_BATCH
+                    if (ACC_REG) {
+                        // all loads of the row first (the conv registers are free in this stage), then the sums in
+                        // the same order: one trip to L2 per annulus instead of one per 256-bin chunk
+                        constexpr int WB = NC <= 4 ? (RG_WARM_BATCH == 1 ? NC : (NC >= 2 ? 2 : 1)) : 1; // chunks per batch
+#pragma unroll
+                        for (int cb = 0; cb < (NC <= 4 ? NC : 1); cb += WB) {
+                            R L[WB][8];
+#pragma unroll
+                            for (int b = 0; b < WB; b++) {
+                                const int j0 = 8 * (32 * (cb + b) + lane);
+#pragma unroll
+                                for (int c = 0; c < 8; c++) L[b][c] = (R)(j0 + c < nE ? __ldg(w_F + j0 + c) : 0.0);
+                            }
+#pragma unroll
+                            for (int b = 0; b < WB; b++) {
+                                const int col = 32 * (cb + b) + lane, j0 = 8 * col;
+                                if (j0 < nE) {
+#pragma unroll
+                                    for (int c = 0; c < 8; c++) part += L[b][c] * G.wt(c, col);
+                                }
+#pragma unroll
+                                for (int c = 0; c < 8; c++) inBase[c * RS + 32 * (cb + b)] = L[b][c];
+                            }
+                        }
+                    } else
+#endif
                     for (int ch = 0; ch < NC; ch++) {
                         const int col = 32 * ch + lane, j0 = 8 * col;
                         R L[8];
