@@ -922,6 +922,7 @@ static int eval_batch_impl(rg_ctx *c, const double *d_params, int P, int model, 
                 } else
                 if (n - q0 - nq < piece_sets / 2) nq = n - q0; // a short remainder joins the last piece
                 A.recs = c->d_recs + q0;
+                A.wien = reinterpret_cast<const double2 *>(c->d_wien) + q0; // per-set arrays follow the piece
                 A.P = nq;
                 A.out = d_out + (size_t)(p0 + q0) * ncomp * nE;
                 RG_TRY(rg_launch_spectrum(A, c->sm_count, st));

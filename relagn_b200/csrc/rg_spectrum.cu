@@ -76,7 +76,10 @@ int rg_spectrum_pick_warps(int NC, int nH, int HL, int HH, int fp32)
 #define RG_WARM_PREFETCH 1
 #endif
 #ifndef RG_WARM_BATCH
-#define RG_WARM_BATCH 2 // warm annuli: farr loads of 2 chunks (2), of the whole row (1) before the first use; 3: cp.async into the buffer; 0: per chunk
+#define RG_WARM_BATCH 4 // warm annuli: 4 = one bin per lane and step, coalesced, RG_WARM_STEPS loads in flight; 2 / 1 = 8 bins per lane, loads of 2 chunks / the whole row first; 3 = cp.async into the buffer; 0 = per chunk
+#endif
+#ifndef RG_WARM_STEPS
+#define RG_WARM_STEPS 16 // RG_WARM_BATCH 4: 32-bin steps of a warm row in flight per lane (divides 8 NC)
 #endif
 #ifndef RG_PLANCK_CHAINS
 #define RG_PLANCK_CHAINS 4 // 32-bin steps of the Planck stage in flight per lane (independent exp / reciprocal chains)
@@ -605,6 +608,31 @@ __global__ void __launch_bounds__(NC <= 4 ? (sizeof(R) == 4 ? 512 : 32 * RG_SPEC
                             if (8 * col < nE) {
 #pragma unroll
                                 for (int c = 0; c < 8; c++) part += inBase[c * RS + 32 * ch] * G.wt(c, col);
+                            }
+                        }
+                    } else
+#endif
+#if RG_WARM_BATCH == 4
+                    if (true) {
+                        // one bin per lane and step, as the Planck stage walks the grid: a warp's load is one contiguous
+                        // 256-byte run of the row (with 8 consecutive bins per lane every load touched 32 sectors), the
+                        // stores into the transposed buffer are conflict-free (row stride = 2 mod 16), RG_WARM_STEPS
+                        // loads in flight per lane
+                        R *const inLane = inT + A.HL + (lane & 7) * RS + (lane >> 3); // bin `lane`; bin 32 g + lane: + 4 g
+                        constexpr int WS = 8 * NC < RG_WARM_STEPS ? 8 * NC : RG_WARM_STEPS; // (8 NC is a multiple of it)
+                        static_assert((8 * NC) % WS == 0, "RG_WARM_STEPS must divide the steps of a row");
+#pragma unroll 1
+                        for (int g0 = 0; g0 < 8 * NC; g0 += WS) {
+                            R L[WS];
+#pragma unroll
+                            for (int q = 0; q < WS; q++) {
+                                const int j = 32 * (g0 + q) + lane;
+                                L[q] = (R)(j < nE ? __ldg(w_F + j) : 0.0);
+                            }
+#pragma unroll
+                            for (int q = 0; q < WS; q++) {
+                                part += L[q] * G.wt_n(32 * (g0 + q) + lane);
+                                inLane[4 * (g0 + q)] = L[q];
                             }
                         }
                     } else
