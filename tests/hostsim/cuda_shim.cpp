@@ -7,6 +7,9 @@
 #include <ucontext.h>
 
 #include <vector>
+#include <unordered_map>
+#include <string.h>
+#include <stdlib.h>
 
 uint3 threadIdx, blockIdx;
 dim3 blockDim, gridDim;
@@ -111,12 +114,38 @@ unsigned warp_gather(uint64_t v, uint64_t *out32)
 void *dyn_smem() { return dsm.data(); }
 long launches() { return n_launch; }
 
+// Out-of-bounds stores: 64 guard bytes behind the dynamic shared memory and behind every device allocation carry a
+// pattern that is checked after every launch (the GPU box has no compute-sanitizer; this is the memcheck the kernels get).
+static const unsigned char GUARD = 0xA5;
+static std::unordered_map<void *, size_t> &allocs()
+{
+    static std::unordered_map<void *, size_t> m;
+    return m;
+}
+void guard_alloc(void *p, size_t n) { memset((char *)p + n, GUARD, 64); allocs()[p] = n; }
+void guard_free(void *p) { allocs().erase(p); }
+static void check_guards(const char *what, size_t smem)
+{
+    for (size_t i = 0; i < 64; i++)
+        if (dsm[smem + i] != GUARD) {
+            fprintf(stderr, "hostsim: store behind the dynamic shared memory (%zu bytes, offset +%zu) in launch %ld (%s)\n", smem, i, n_launch, what);
+            abort();
+        }
+    for (auto &kv : allocs())
+        for (size_t i = 0; i < 64; i++)
+            if (((unsigned char *)kv.first)[kv.second + i] != GUARD) {
+                fprintf(stderr, "hostsim: store behind a device allocation of %zu bytes (offset +%zu) in launch %ld (%s)\n", kv.second, i, n_launch, what);
+                abort();
+            }
+}
+
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &body)
 {
     n_launch++;
     size_t nt = (size_t)block.x * block.y * block.z;
     if (nt == 0 || (size_t)grid.x * grid.y * grid.z == 0) return;
     if (dsm.size() < smem + 64) dsm.resize(smem + 64);
+    memset(dsm.data() + smem, GUARD, 64);
     while (stack_pool.size() < nt) stack_pool.push_back((char *)malloc(STACK));
     gridDim = grid;
     blockDim = block;
@@ -158,6 +187,7 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &bod
             }
     cur = -1;
     cur_body = nullptr;
+    check_guards("after the last block", smem);
 }
 } // namespace hostsim
 
@@ -169,10 +199,16 @@ static double now_ms()
     clock_gettime(CLOCK_MONOTONIC, &ts);
     return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
 }
-cudaError_t cudaMalloc(void **p, size_t n) { *p = calloc(1, n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
-cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+cudaError_t cudaMalloc(void **p, size_t n)
+{
+    *p = calloc(1, (n ? n : 1) + 64);
+    if (!*p) return cudaErrorMemoryAllocation;
+    hostsim::guard_alloc(*p, n ? n : 1);
+    return cudaSuccess;
+}
+cudaError_t cudaFree(void *p) { if (p) hostsim::guard_free(p); free(p); return cudaSuccess; }
 cudaError_t cudaMallocHost(void **p, size_t n) { return cudaMalloc(p, n); }
-cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
+cudaError_t cudaFreeHost(void *p) { return cudaFree(p); }
 cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { memmove(d, s, n); return cudaSuccess; }
 cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { memmove(d, s, n); return cudaSuccess; }
 cudaError_t cudaMemset(void *d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
