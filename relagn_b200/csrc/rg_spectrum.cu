@@ -82,7 +82,7 @@ int rg_spectrum_pick_warps(int NC, int nH, int HL, int HH, int fp32)
 #define RG_WARM_STEPS 16 // RG_WARM_BATCH 4: 32-bin steps of a warm row in flight per lane (divides 8 NC)
 #endif
 #ifndef RG_PLANCK_CHAINS
-#define RG_PLANCK_CHAINS 4 // 32-bin steps of the Planck stage in flight per lane (independent exp / reciprocal chains)
+#define RG_PLANCK_CHAINS 5 // 32-bin steps of the Planck stage in flight per lane (independent exp / reciprocal chains; r2zh: 4 -> 60.6, 5 -> 59.6, 6 -> 61.4, 8 -> 60.1 ms)
 #endif
 #ifndef RG_WIEN_CUT
 #define RG_WIEN_CUT 1 // skip the Wien-tail bins of an annulus whose share of the total is below FP64 resolution
