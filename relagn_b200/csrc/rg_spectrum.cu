@@ -696,7 +696,18 @@ __global__ void __launch_bounds__(NC <= 4 ? (sizeof(R) == 4 ? 512 : 32 * RG_SPEC
                 // (the histogram is installed already scaled: norm / radiance x the pack-unpack constant)
                 // (FP32 mode keeps the histogram unscaled -- the scale alone can exceed the single-precision range -- and
                 //  multiplies afterwards in double)
-                const double hscale = radiance != 0 ? (s2 / radiance) * A.pkupk : 0.0;
+                // norm / radiance can exceed the double range although norm (B / radiance), what the reference computes,
+                // does not: a grid that shows only the far Wien tail of a cold annulus (a hard X-ray band) has B ~ 1e-300
+                // and the reference scales it up to the annulus' full luminosity.  Then the buffer is multiplied by
+                // 2^600 (exact) and the scale carries 2^-600.
+                double nr = radiance != 0 ? s2 / radiance : 0.0;
+                if (sizeof(R) == 8 && !(fabs(nr) <= 1e290)) { // (the area factor, up to ~1e12, still multiplies it)
+                    const double up = 4.149515568880993e180, dn = 2.409919865102884e-181; // 2^600, 2^-600
+                    nr = (s2 * dn) / radiance;
+                    for (int i = lane; i < 8 * RS; i += 32) inT[i] = (R)((double)inT[i] * up);
+                    __syncwarp();
+                }
+                const double hscale = nr * A.pkupk;
                 if (conv) install_hist(true, sizeof(R) == 8 ? hscale : 1.0);
                 if (radiance != 0) {
                     if (conv) {
@@ -716,7 +727,7 @@ __global__ void __launch_bounds__(NC <= 4 ? (sizeof(R) == 4 ? 512 : 32 * RG_SPEC
                             acc.add(ch, tmp);
                         }
                     } else {
-                        const double scale = (s2 / radiance) * geo;
+                        const double scale = nr * geo;
                         const int nch_live = region == 0 ? ((jz + 255) >> 8) : NC; // chunks holding a non-zero bin
                         for (int ch = 0; ch < nch_live; ch++) {
                             R v[8];

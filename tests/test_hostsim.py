@@ -244,3 +244,47 @@ def test_hot_spectral_shape_attribute(ctx):
             assert got.max() == 0
         else:
             assert peak_relerr(got, ref) < 1e-10, i
+
+
+@pytest.mark.parametrize("grid_case", ["wide_10_decades", "hard_band_above_1keV", "soft_band_below_1keV"])
+def test_kompaneets_large_path_unusual_grids_vs_oracle(ctx, monkeypatch, grid_case):
+    """The large-batch Kompaneets kernels (forward sweep per thread, back substitution as a warp scan, interpolation
+    lines in shared memory) on grids that move their row bookkeeping: a 10-decade grid (wider than a warp's table: the
+    variant with the tables in global scratch; starts below 1e-4 keV: low-frequency extension of the disc), a band that
+    starts above 1 keV (the normalisation rows at 1 keV lie below the grid's first cell) and one that ends below it
+    (they lie above its last).  Non-relativistic, against the oracle's restatement of pyNTHCOMP.py."""
+    from oracle import oracle as O
+    from tests.util import c4_params
+    grid = {"wide_10_decades": np.geomspace(1e-6, 1e4, 1201), "hard_band_above_1keV": np.geomspace(2.0, 150.0, 401),
+            "soft_band_below_1keV": np.geomspace(1e-3, 0.5, 301)}[grid_case]
+    monkeypatch.setenv("RG_NO_SMALL_PATH", "1")
+    p = c4_params(6, seed=77)
+    ctx.set_grid(grid)
+    st, ref, _ = O.evaluate_batch(p, grid, model=0, rel=False)
+    outs = []
+    for force_global in (False, True):
+        if force_global:
+            monkeypatch.setenv("RG_INTERP_GLOBAL", "1")
+        out, at = ctx.eval_batch_host(p, model=0, rel=False, components=True)
+        outs.append(out)
+        for k in range(p.shape[0]):
+            if st[k] != 0:
+                continue
+            for c in range(4):
+                assert peak_relerr(out[k, c], ref[k, c]) < 1e-9, (grid_case, force_global, k, c)
+    np.testing.assert_array_equal(outs[0], outs[1])  # both table placements: same bits
+    if grid_case == "hard_band_above_1keV":
+        # relativistic, same band: the cold annuli show only their far Wien tail, which the reference scales up to the
+        # annulus' full luminosity -- norm / radiance leaves the double range, norm (B / radiance) does not
+        t = golden_tables()
+        otab = O.Tables(t["spins"], t["thetas"], t["NR"], t["NPHI"], t["r_in"], t["data"])
+        pr = p[:3].copy()
+        pr[:, 3] = np.clip(pr[:, 3], t["spins"].min(), t["spins"].max())
+        st, ref, _ = O.evaluate_batch(pr, grid, model=0, rel=True, tab=otab)
+        out, at = ctx.eval_batch_host(pr, model=0, rel=True, components=True)
+        assert np.isfinite(out).all()
+        for k in range(pr.shape[0]):
+            if st[k] != 0:
+                continue
+            for c in range(4):
+                assert peak_relerr(out[k, c], ref[k, c]) < 1e-9, ("rel", k, c)
