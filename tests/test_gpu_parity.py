@@ -442,7 +442,8 @@ def test_edge_grids(ctx, oracle, otab):
     assert out0.shape == (0, 8) and at0.shape == (0, 24)
 
 
-@pytest.mark.parametrize("grid_case", ["wide_10_decades", "hard_band_above_1keV", "soft_band_below_1keV"])
+@pytest.mark.parametrize("grid_case", ["wide_10_decades", "hard_band_above_1keV", "soft_band_below_1keV",
+                                       "above_the_warm_x_grid", "below_every_x_grid"])
 def test_band_grids_large_batch_vs_oracle(ctx, oracle, otab, monkeypatch, grid_case):
     """The large-batch path (200 sets: forward sweep per thread, back substitution as a warp scan, interpolation lines in
     shared memory) on grids that move the Kompaneets row bookkeeping and the scale of the local spectra: a 10-decade
@@ -450,7 +451,10 @@ def test_band_grids_large_batch_vs_oracle(ctx, oracle, otab, monkeypatch, grid_c
     that starts above 1 keV (normalisation rows below the grid's first cell; cold annuli show only their far Wien
     tail and norm / radiance leaves the double range) and one that ends below 1 keV."""
     grid = {"wide_10_decades": np.geomspace(1e-6, 1e4, 1201), "hard_band_above_1keV": np.geomspace(2.0, 150.0, 401),
-            "soft_band_below_1keV": np.geomspace(1e-3, 0.5, 301)}[grid_case]
+            "soft_band_below_1keV": np.geomspace(1e-3, 0.5, 301),
+            # every bin above the top of the warm Comptonisation grids / below the first row of every Kompaneets grid
+            "above_the_warm_x_grid": np.geomspace(45.0, 400.0, 101),
+            "below_every_x_grid": np.geomspace(1e-11, 3e-10, 65)}[grid_case]
     upload_golden_tables(ctx)
     t = golden_tables()
     p = c4_params(200, seed=77)

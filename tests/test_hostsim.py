@@ -246,7 +246,8 @@ def test_hot_spectral_shape_attribute(ctx):
             assert peak_relerr(got, ref) < 1e-10, i
 
 
-@pytest.mark.parametrize("grid_case", ["wide_10_decades", "hard_band_above_1keV", "soft_band_below_1keV"])
+@pytest.mark.parametrize("grid_case", ["wide_10_decades", "hard_band_above_1keV", "soft_band_below_1keV",
+                                       "above_the_warm_x_grid", "below_every_x_grid"])
 def test_kompaneets_large_path_unusual_grids_vs_oracle(ctx, monkeypatch, grid_case):
     """The large-batch Kompaneets kernels (forward sweep per thread, back substitution as a warp scan, interpolation
     lines in shared memory) on grids that move their row bookkeeping: a 10-decade grid (wider than a warp's table: the
@@ -256,7 +257,11 @@ def test_kompaneets_large_path_unusual_grids_vs_oracle(ctx, monkeypatch, grid_ca
     from oracle import oracle as O
     from tests.util import c4_params
     grid = {"wide_10_decades": np.geomspace(1e-6, 1e4, 1201), "hard_band_above_1keV": np.geomspace(2.0, 150.0, 401),
-            "soft_band_below_1keV": np.geomspace(1e-3, 0.5, 301)}[grid_case]
+            "soft_band_below_1keV": np.geomspace(1e-3, 0.5, 301),
+            # every bin above the top of the warm Comptonisation grids (40 kTe_w <= 40 keV) / below the first row of every
+            # Kompaneets grid (511 xmin = 1e-4 kT_seed ~ 1e-7 keV): the cursor's clamps, empty and constant spectra
+            "above_the_warm_x_grid": np.geomspace(45.0, 400.0, 101),
+            "below_every_x_grid": np.geomspace(1e-11, 3e-10, 65)}[grid_case]
     monkeypatch.setenv("RG_NO_SMALL_PATH", "1")
     p = c4_params(6, seed=77)
     ctx.set_grid(grid)
