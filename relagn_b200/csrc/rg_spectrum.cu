@@ -37,7 +37,13 @@
 #endif
 #define NGRID 4 // per-bin constant arrays staged in shared memory: hnu, bbpre, wt in bin order + wt transposed
 #ifndef RG_SPEC_W64
-#define RG_SPEC_W64 12 // warps per CTA of the FP64 kernel on grids of <= 1024 bins (register budget 65536 / (32 W))
+#define RG_SPEC_W64 6 // warps per CTA of the FP64 kernel on grids of <= 1024 bins (register budget 65536 / (32 W x CTAs per SM))
+#endif
+#ifndef RG_SPEC_CPS
+#define RG_SPEC_CPS 2 // resident CTAs per SM of that kernel (RG_SPEC_W64 x RG_SPEC_CPS warps share the register file).
+                      // Two CTAs of 6 warps instead of one of 12 (r2zj: 56.7 against 59.9 ms): an item's annuli go to 6
+                      // warps instead of 12, so the warps' shares differ by one annulus in 21 instead of one in 11, and
+                      // while one CTA waits for its slowest warp and folds its item the other keeps the SM busy
 #endif
 
 static __host__ __device__ inline int round_up2(int x) { return (x + 1) & ~1; }
@@ -64,8 +70,9 @@ size_t rg_spectrum_smem_bytes(int NC, int nH, int HL, int HH, int warps, int fp3
 
 int rg_spectrum_pick_warps(int NC, int nH, int HL, int HH, int fp32)
 {
+    const int per_sm = (NC <= 4 && !fp32) ? RG_SPEC_CPS : 1; // (each resident CTA also pays 1 kB of system shared memory)
     for (int w = (NC <= 4 ? (fp32 ? 16 : RG_SPEC_W64) : 8); w >= 1; w--)
-        if (rg_spectrum_smem_bytes(NC, nH, HL, HH, w, fp32) <= 227 * 1024 - 512) return w;
+        if (rg_spectrum_smem_bytes(NC, nH, HL, HH, w, fp32) <= (size_t)(228 * 1024) / per_sm - 1024 - 512) return w;
     return 0;
 }
 
@@ -283,7 +290,7 @@ struct Acc {
 // buffer, the convolution and the accumulators in single precision -- the histogram, every per-annulus scalar, the
 // Kompaneets solve and the normalisations stay FP64.
 template <int NC, typename R>
-__global__ void __launch_bounds__(NC <= 4 ? (sizeof(R) == 4 ? 512 : 32 * RG_SPEC_W64) : 256, 1) spectrum_kernel(SpecArgs A)
+__global__ void __launch_bounds__(NC <= 4 ? (sizeof(R) == 4 ? 512 : 32 * RG_SPEC_W64) : 256, (NC <= 4 && sizeof(R) == 8) ? RG_SPEC_CPS : 1) spectrum_kernel(SpecArgs A)
 {
     constexpr bool GS = NC <= 8;       // grid constants in shared memory
     constexpr bool ACC_REG = NC <= 4;  // accumulators in registers
@@ -969,7 +976,8 @@ static int launch_spec(const SpecArgs &args, int sm_count, cudaStream_t st)
     auto kern = spectrum_kernel<NC, R>;
     RG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long items = (long)args.P * args.NB;
-    long ctas = items < sm_count ? items : sm_count; // persistent: one CTA per SM, CTAs pull items from the queue
+    const long per_sm = (NC <= 4 && sizeof(R) == 8) ? RG_SPEC_CPS : 1;
+    long ctas = items < sm_count * per_sm ? items : sm_count * per_sm; // persistent CTAs pull items from the queue
     RG_CUDA_OK(cudaMemsetAsync(args.queue, 0, sizeof(int), st));
     RG_LAUNCH(kern, dim3((unsigned)ctas), dim3(32 * args.warps), smem, st, args);
     RG_CUDA_OK(cudaGetLastError());

@@ -107,6 +107,27 @@ def test_random_batch_vs_oracle(ctx, oracle, otab, rel):
     np.testing.assert_allclose(tot, out[:, 3], rtol=1e-13)
 
 
+def test_relqso_grid_large_batch_vs_oracle(ctx, oracle, otab):
+    """relqso through the large-batch path (a 10 x 10 mass x mdot grid = 100 sets, config 3 in small): r_hot search,
+    gamma_hot from Ldiss / Lseed (lumin_kernel), Kompaneets kernels, against the oracle; spin and inclination varied."""
+    grid = np.geomspace(1e-4, 1e3, 1001)
+    ctx.set_grid(grid)
+    upload_golden_tables(ctx)
+    p = c3_params(10)
+    p[:, 3] = np.linspace(0.0, 0.95, p.shape[0])
+    p[:, 4] = np.linspace(0.2, 0.95, p.shape[0])[::-1]
+    for rel in (False, True):
+        st, ref, rat = oracle.evaluate_batch(p, grid, model=1, rel=rel, tab=otab)
+        out, at = ctx.eval_batch_host(p, model=1, rel=rel, components=True)
+        np.testing.assert_array_equal(at[:, 21].astype(int), st)
+        ok = st == 0
+        assert ok.sum() >= 80
+        np.testing.assert_allclose(at[ok, 10], rat[ok, 10], rtol=1e-9)  # gamma_h
+        for i in np.nonzero(ok)[0]:
+            for c in range(4):
+                assert peak_relerr(out[i, c], ref[i, c]) < TOL, (rel, i, c)
+
+
 def test_raytracer_vs_oracle_nodes(ctx, oracle):
     """The device ray tracer (rg_tables_generate, csrc/rg_raytrace.cu) against the oracle's node generator
     (kerr_oracle.c: ro_make_node) on 9 nodes incl. the corners of the default grid: retrograde / maximal spin,
