@@ -14,11 +14,15 @@
 #include "rg_kernels.h"
 #include "rg_transfer.cuh"
 
+// CTA shape: warps per CTA x resident CTAs per SM the register budget is cut for.  Swept in r2zl-r2zn (ms per 125 000
+// sets): 8 x 3 (80 registers, 84 bytes of spills) 23.4; 6 x 4 (80, spills) 23.0; 6 x 3 22.6; 10 x 2 22.5; 4 x 4 (127
+// registers) 22.1; 5 x 4 (96 registers, no spills, 20 warps per SM) 21.1 -- the ring routine wants ~96 registers more
+// than it wants the last four warps
 #ifndef HIST_WARPS
-#define HIST_WARPS 8
+#define HIST_WARPS 5
 #endif
 #ifndef RG_HIST_MINB
-#define RG_HIST_MINB 3 // resident CTAs per SM the register budget is cut for
+#define RG_HIST_MINB 4
 #endif
 
 static __host__ __device__ inline int hist_round_up2(int x) { return (x + 1) & ~1; }
@@ -211,11 +215,9 @@ int rg_launch_hist(const HistArgs &A, int sm_count, cudaStream_t st)
 {
     if (A.P == 0) return RG_OK;
     // resident CTAs per SM the register budget is cut for: 4 (64 registers) or 3 (80); RG_HIST_CTAS: tuning knob
-    int minb = RG_HIST_MINB;
-    if (const char *e = getenv("RG_HIST_CTAS")) minb = atoi(e);
     switch (A.tab.NPHI) {
     case 32: return launch_hist<1, 4>(A, sm_count, st);
-    case 64: return minb == 3 ? launch_hist<2, 3>(A, sm_count, st) : launch_hist<2, 4>(A, sm_count, st);
+    case 64: return launch_hist<2, RG_HIST_MINB>(A, sm_count, st);
     case 128: return launch_hist<4, 3>(A, sm_count, st);
     case 256: return launch_hist<8, 2>(A, sm_count, st);
     }
