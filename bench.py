@@ -469,7 +469,7 @@ def run_ours(args):
         # this run's sets per launch; the excess over bytes_per_launch is the Comptonised-spectra arena (farr) that
         # nthcomp_interp_kernel writes and this kernel reads once (~29 systems x 8 kB per set), not a re-read
         traffic, traffic_src = None, None
-        for tag in ("r2z", "r2x", "r2n", "r1r", "r1q", "r1p", "r1n"):  # latest capture first
+        for tag in ("r2zz", "r2z", "r2x", "r2n", "r1r", "r1q", "r1p", "r1n"):  # latest capture first
             try:
                 prof = json.load(open(os.path.join(ROOT, "profiles", tag + "_summary.json")))
                 traffic = prof["spectrum_dram_bytes_per_set"] * (P / n_launch)
