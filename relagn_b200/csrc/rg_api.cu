@@ -697,8 +697,7 @@ static int ensure_batch_scratch(rg_ctx *c, int model, int P)
         c->sys_cap = want * 40;
         RG_CUDA_OK(cudaMalloc(&c->d_recs, (size_t)want * sizeof(SetRec)));
         RG_CUDA_OK(cudaMalloc(&c->d_syslist, (size_t)c->sys_cap * sizeof(int2)));
-        // (G', M) of every row of every system: what the forward sweep leaves for the back substitution (rg_setup.cu)
-        RG_CUDA_OK(cudaMalloc(&c->d_sptot, (size_t)c->sys_cap * RG_SPT_STRIDE * sizeof(double2)));
+        // (the coefficient arena of the large-batch Kompaneets kernels is allocated when they first run: ensure_coef)
         RG_CUDA_OK(cudaMalloc(&c->d_header, (size_t)c->sys_cap * 4 * sizeof(double)));
         c->chunk_sets = want;
     }
@@ -853,6 +852,8 @@ static int eval_batch_impl(rg_ctx *c, const double *d_params, int P, int model, 
                 return RG_OK;
             }
             c->launches++; // nthcomp_interp_kernel
+            if (!c->d_sptot) // (G', M) of every row of every system: what the forward sweep leaves for the back substitution
+                RG_CUDA_OK(cudaMalloc(&c->d_sptot, (size_t)c->sys_cap * RG_SPT_STRIDE * sizeof(double2)));
             RG_TRY(prof_begin(c, 1, st));
             RG_TRY(rg_launch_nthcomp(c->d_recs, c->d_syslist, n_warm_sys, n_hot_sys, c->farr_cap, c->d_p10, nth_run,
                                      reinterpret_cast<double2 *>(c->d_sptot), c->d_header, c->sm_count, c->gd,
