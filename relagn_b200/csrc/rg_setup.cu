@@ -346,18 +346,8 @@ setup_kernel(const double *__restrict__ params, int P, int model, double dr_dex,
 // cell of the first grid energy upwards and the two rows around 1 keV (normalisation, pyNTHCOMP.py:49-56); the
 // recurrence runs from the top of the grid downwards, so it can stop at `jstop`.
 // a thread's stores walk its own system's rows, 16 bytes per row: the two halves of a 32-byte sector arrive one row
-// apart, so the line must stay in L2 until then (default policy; RG_COEF_STREAM=1: evict-first, for the A/B)
-#if defined(RG_COEF_STREAM) && RG_COEF_STREAM
-#define RG_COEF_ST(p, v) RG_STCS2((p), (v))
-#else
+// apart, so the line must stay in L2 until then: default cache policy (evict-first stores measured +-0, r2r)
 #define RG_COEF_ST(p, v) (*(p) = (v))
-#endif
-#ifndef RG_NTH_UNROLL
-#define RG_NTH_UNROLL 1
-#endif
-#ifndef RG_NTH_MERGE_RCP
-#define RG_NTH_MERGE_RCP 0
-#endif
 #define RG_NTH_Q4 0.83176377110267100 // 10^-0.08 = (x[j] / x[j+1])^4
 __device__ __forceinline__ int rg_nth_jstop(double lgx, double lgE0)
 {
@@ -440,15 +430,9 @@ __device__ static void nthcomp_system(bool valid, const SetRec &r, int which, co
     const double itau = 1.0 / tautom, rxr = 1.0 / (xr - xnr), todx = tod / xmin;
     const double third = 1.0 / 3.0;
     // bet[j] of pyNTHCOMP.py:124-148 at x = x[j] (j >= 1) and its denominator (bet = 1 / tautom / den)
-#if RG_NTH_MERGE_RCP
-    auto bet_at = [&](int j, double w, double &den, double other, double &rother) -> double {
-        den = 1.0;
-        if (j >= jrel) { rother = __drcp_rn(other); return itau; }
-#else
     auto bet_at = [&](int j, double w, double &den) -> double {
         den = 1.0;
         if (j >= jrel) return itau;
-#endif
         double rel;
         if (w <= 0.05) rel = (1.0 - 2.0 * w + 26.0 * w * w * 0.2);
         else {
@@ -462,46 +446,25 @@ __device__ static void nthcomp_system(bool valid, const SetRec &r, int which, co
         const double taukn = tautom * rel;
         if (j < jnr - 1) den = 1.0 + taukn * third;
         else den = 1.0 + taukn * third * (1 - (w - xnr) * rxr);
-#if RG_NTH_MERGE_RCP
-        const double rr = __drcp_rn(den * other);
-        rother = rr * den;
-        return itau * (rr * other);
-#else
         return itau * __drcp_rn(den);
-#endif
     };
     // seed photons (pyNTHCOMP.py:120-122): x[j] / tempbb = 1e-4 10^(0.02 j) for every system, so
     // d[j] = x[j] dphdot[j] = (planck xmin^3) 10^(0.06 j) / (exp(1e-4 10^(0.02 j)) - 1) comes from a resident table
     const double pk3 = planck * (xmin * xmin * xmin);
     double den_cur, den_nxt;
-#if RG_NTH_MERGE_RCP
-    double rdummy;
-    double bet_cur = bet_at(1, x0, den_cur, 1.0, rdummy), bet_nxt;
-#else
     double bet_cur = bet_at(1, x0, den_cur), bet_nxt;
-#endif
     // sptot[0] = s_0 aa u[1] = c0 v_1 (pyNTHCOMP.py:248)
     const double c0 = aa * (RG_NTH_Q4 * b0) * (tautom * den_cur);
     hd[0] = xmin; hd[1] = c0; hd[2] = (double)(jmax + 1024 * jstop); hd[3] = lgx;
-#if RG_NTH_UNROLL == 2
-#pragma unroll 2
-#elif RG_NTH_UNROLL == 4
-#pragma unroll 4
-#endif
+    // (unrolling by 2 and one reciprocal for the two independent denominators of a row were measured: +-0, r2w)
     for (int j = 1; j < jmax - 1; j++) {
         xp = xmin * p10tab[j + 1];
         // w1 = sqrt(x[j] x[j+1]) = xmin 10^(0.02 j + 0.01) and theta / deltal / w1 from the resident tables: no
         // square root and one division less per row (last-bit differences against pyNTHCOMP.py:117,211)
         const double w1j = xmin * p10tab[RG_P10_W1 + j];
         const double c2den = 1.0 + 4.60 * w1j + 1.1 * w1j * w1j;
-#if RG_NTH_MERGE_RCP
-        // the reciprocals of c2's denominator and of bet's (row j + 1) from one: 1/a = b/(ab), 1/b = a/(ab)
-        double rc2den;
-        bet_nxt = bet_at(j + 1, xp, den_nxt, c2den, rc2den);
-#else
         bet_nxt = bet_at(j + 1, xp, den_nxt);
         const double rc2den = __drcp_rn(c2den);
-#endif
         // (quotients as reciprocal multiplies: rcp.rn + mul instead of div.rn, last-bit differences)
         double c2j = (w1j * w1j * w1j * w1j) * rc2den;
         const double betj = bet_cur;
