@@ -293,3 +293,30 @@ def test_kompaneets_large_path_unusual_grids_vs_oracle(ctx, monkeypatch, grid_ca
                 continue
             for c in range(4):
                 assert peak_relerr(out[k, c], ref[k, c]) < 1e-9, ("rel", k, c)
+
+
+def test_large_path_random_sets_vs_oracle(ctx, monkeypatch):
+    """The large-batch kernels over a spread of corona parameters (24 C4 draws: Gamma 1.3-5, kTe 0.1-300 keV, seed
+    temperatures from 1e5 to 1e10 solar masses' discs): Kompaneets forward sweep + scan + interpolation lines, the
+    coalesced warm-row loads and the two-CTA item loop of the spectrum kernel, against the oracle; non-relativistic
+    for all, relativistic for the first six."""
+    from oracle import oracle as O
+    from tests.util import c4_params
+    monkeypatch.setenv("RG_NO_SMALL_PATH", "1")
+    grid = np.geomspace(1e-4, 1e3, 1001)
+    ctx.set_grid(grid)
+    t = golden_tables()
+    p = c4_params(24, seed=2024)
+    p[:, 3] = np.clip(p[:, 3], t["spins"].min(), t["spins"].max())
+    st, ref, rat = O.evaluate_batch(p, grid, model=0, rel=False)
+    out, at = ctx.eval_batch_host(p, model=0, rel=False, components=True)
+    np.testing.assert_array_equal(at[:, 21].astype(int), st)
+    for k in np.nonzero(st == 0)[0]:
+        for c in range(4):
+            assert peak_relerr(out[k, c], ref[k, c]) < 1e-9, (k, c)
+    otab = O.Tables(t["spins"], t["thetas"], t["NR"], t["NPHI"], t["r_in"], t["data"])
+    st, ref, _ = O.evaluate_batch(p[:6], grid, model=0, rel=True, tab=otab)
+    out, at = ctx.eval_batch_host(p[:6], model=0, rel=True, components=True)
+    for k in np.nonzero(st == 0)[0]:
+        for c in range(4):
+            assert peak_relerr(out[k, c], ref[k, c]) < 1e-9, ("rel", k, c)
