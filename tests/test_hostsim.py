@@ -320,3 +320,28 @@ def test_large_path_random_sets_vs_oracle(ctx, monkeypatch):
     for k in np.nonzero(st == 0)[0]:
         for c in range(4):
             assert peak_relerr(out[k, c], ref[k, c]) < 1e-9, ("rel", k, c)
+
+
+def test_large_path_relqso_vs_oracle(ctx, monkeypatch):
+    """relqso through the large-batch kernels (r_hot search, gamma_hot from lumin_kernel's Ldiss / Lseed, Kompaneets
+    kernels) against the oracle: a 3 x 3 mass x mdot grid with spin and inclination varied."""
+    from oracle import oracle as O
+    from tests.util import c3_params
+    monkeypatch.setenv("RG_NO_SMALL_PATH", "1")
+    grid = np.geomspace(1e-4, 1e3, 1001)
+    ctx.set_grid(grid)
+    t = golden_tables()
+    otab = O.Tables(t["spins"], t["thetas"], t["NR"], t["NPHI"], t["r_in"], t["data"])
+    p = c3_params(3)
+    p[:, 3] = np.linspace(0.0, 0.9, p.shape[0])
+    p[:, 4] = np.linspace(0.3, 0.95, p.shape[0])
+    for rel in (False, True):
+        st, ref, rat = O.evaluate_batch(p, grid, model=1, rel=rel, tab=otab)
+        out, at = ctx.eval_batch_host(p, model=1, rel=rel, components=True)
+        np.testing.assert_array_equal(at[:, 21].astype(int), st)
+        ok = np.nonzero(st == 0)[0]
+        assert ok.size >= 6
+        np.testing.assert_allclose(at[ok, 10], rat[ok, 10], rtol=1e-9)  # gamma_h
+        for k in ok:
+            for c in range(4):
+                assert peak_relerr(out[k, c], ref[k, c]) < 1e-9, (rel, k, c)
