@@ -852,12 +852,9 @@ int rg_launch_nthcomp(const SetRec *recs, const int2 *syslist, int n_warm_sys, i
     const size_t smem = (size_t)2 * RG_INTERP_ROWS * sizeof(double) + (size_t)RG_INTERP_WARPS * (4 * sizeof(double) + 3 * sizeof(int)) +
                         (global ? 0 : (size_t)RG_INTERP_WARPS * RG_INTERP_RCAP * sizeof(double2));
 #ifndef RG_HOSTSIM
-    static bool attr_set = false;
-    if (!attr_set) {
-        RG_CUDA_OK(cudaFuncSetAttribute(nthcomp_interp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)(smem + (global ? (size_t)RG_INTERP_WARPS * RG_INTERP_RCAP * sizeof(double2) : 0))));
-        attr_set = true;
-    }
+    // (per launch, like the other kernels: the attribute belongs to the current device, and a process may drive several)
+    if (!global)
+        RG_CUDA_OK(cudaFuncSetAttribute(nthcomp_interp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 #endif
     long ictas = ((long)nsys + RG_INTERP_WARPS - 1) / RG_INTERP_WARPS;
     if (ictas > 3L * sm_count) ictas = 3L * sm_count;
